@@ -1,0 +1,185 @@
+/*
+ * mmi_b200.h -- C ABI of libmmi_b200.so: hand-written sm_100a CUDA kernels for the
+ * MMinterest training step (hezy18/SegMMInterest, MMinterest/).
+ *
+ * The reference has no FFI: its hot path is eager PyTorch.  Each entry point below
+ * replaces a group of ATen/cuBLAS library calls; the reference call site it replaces
+ * is cited as file:line relative to /root/reference/MMinterest/.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (workspace included);
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and never syncs the host;
+ *   - row-major everywhere, leading dimensions in ELEMENTS;
+ *   - dtype codes: MMI_F32 = 0, MMI_BF16 = 1 (activations / table); parameters,
+ *     gradients, optimizer state, LayerNorm statistics and reductions are fp32;
+ *   - return value: 0 on success, negative MMI_E* otherwise; mmi_last_error() gives
+ *     a thread-local message.  No C++ exception crosses this boundary.
+ */
+#ifndef MMI_B200_H_
+#define MMI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMI_F32 0
+#define MMI_BF16 1
+
+#define MMI_OK 0
+#define MMI_EINVAL (-1)   /* bad shape / dtype / alignment */
+#define MMI_ECUDA (-2)    /* CUDA runtime error at launch   */
+#define MMI_ENOSUP (-3)   /* configuration not implemented  */
+
+#define MMI_ACT_NONE 0
+#define MMI_ACT_GELU 1    /* erf GELU, kn_util/nn_utils/layers/mlp.py:30-31 */
+
+/* GEMM operand layouts (mmi_gemm): C[M,N] = op(A) * op(B)                          */
+#define MMI_GEMM_NT 0     /* A [M,K] row-major, B [N,K] row-major  (y = x W^T)       */
+#define MMI_GEMM_NN 1     /* A [M,K] row-major, B [K,N] row-major  (dx = dy W)       */
+#define MMI_GEMM_TN 2     /* A [K,M] row-major, B [K,N] row-major  (dW = dy^T x)     */
+
+/* GEMM implementations */
+#define MMI_IMPL_SIMT 0   /* fp32-FFMA CUDA-core tiles (strict-parity mode)          */
+#define MMI_IMPL_TC 1     /* bf16 tcgen05.mma + TMEM accumulators + TMA operands     */
+
+typedef void* mmi_stream_t; /* cudaStream_t */
+
+int mmi_version(void);
+const char* mmi_last_error(void);
+/* 1 if the tcgen05 GEMM path was compiled in and the device is sm_100 */
+int mmi_has_tc(void);
+
+/* ---- a-1..a-3: gather + zero-pad + mask (+ L1 normalise) ---------------------------
+ * replaces utils/dataloader_SegMM.py:301-350 (row gather, _pad_feature_list :251-268)
+ * and main_for_seq_leave_earlystop_SegMM.py:272-273 (x / (||x||_1 + 1e-6)).
+ * idx[n_tokens] int32 row ids into table[n_rows, din], -1 = pad (row of zeros, mask 0).
+ * normalise = 0 gives a bit-exact copy. out_dtype may differ from table_dtype.       */
+int mmi_gather_l1norm_fwd(const void* table, int table_dtype, int64_t n_rows, int din,
+                          const int32_t* idx, int64_t n_tokens, void* out, int out_dtype,
+                          uint8_t* mask, int normalise, mmi_stream_t stream);
+
+/* ---- generic GEMM with fused epilogue ----------------------------------------------
+ * replaces every nn.Linear on the path (models/encoder.py:50-62,95-98,163-164,432-445;
+ * kn_util/nn_utils/layers/mlp.py:17-24) and their autograd mm/addmm backward.
+ *   acc  = op(A) op(B)                                   (fp32 accumulate)
+ *   z    = acc + bias[n]                                 (bias may be NULL)
+ *   if preact: preact[m,n] = z                           (saved for GELU backward)
+ *   y    = act(z)
+ *   if mul_gelu_grad: y *= gelu'(mul_gelu_grad[m,n])     (dgrad through GELU)
+ *   if add:  y += add[(m % add_mod) * ld_add + n]        (residual / position embedding)
+ *   C    = y                (accumulate == 0)
+ *   C   += y                (accumulate == 1, C must be fp32; used for weight grads)
+ * in_dtype applies to A, B, add, preact, mul_gelu_grad; out_dtype to C.
+ * split_k > 1 is only legal with accumulate == 1 (atomic fp32 adds).                  */
+typedef struct {
+  int layout;       /* MMI_GEMM_* */
+  int impl;         /* MMI_IMPL_* */
+  int in_dtype;     /* dtype of A and B */
+  int out_dtype;    /* dtype of C */
+  int64_t M;
+  int64_t N;
+  int64_t K;
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  void* C; int64_t ldc;
+  const float* bias;
+  int act;
+  void* preact; int64_t ld_preact;            /* in_dtype */
+  const void* mul_gelu_grad; int64_t ld_mul;  /* in_dtype */
+  const void* add; int64_t ld_add; int64_t add_mod; int add_dtype;
+  int accumulate;
+  int split_k;
+} mmi_gemm_args;
+int mmi_gemm(const mmi_gemm_args* args, mmi_stream_t stream);
+
+/* column sums: out[n] += sum_m X[m,n]  (bias gradients).  out is fp32.               */
+int mmi_colsum_acc(const void* x, int dtype, int64_t M, int N, int64_t ldx, float* out,
+                   float* workspace, int64_t workspace_floats, mmi_stream_t stream);
+
+/* ---- LayerNorm(eps) over the last dim, fp32 statistics ------------------------------
+ * replaces torch.nn.LayerNorm(d, 1e-12) at models/encoder.py:39-40,185-186,383-385.
+ * stats[row] = (mean, rstd).                                                          */
+int mmi_layernorm_fwd(const void* x, int dtype, int64_t rows, int d, const float* gamma,
+                      const float* beta, float eps, void* y, float* stats, mmi_stream_t stream);
+/* dx = LN'(dy) (+ add); dgamma += sum dy*xhat; dbeta += sum dy.
+ * workspace: at least mmi_layernorm_bwd_workspace(d) floats.                          */
+int64_t mmi_layernorm_bwd_workspace(int d);
+int mmi_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int d,
+                      const float* gamma, const float* stats, const void* add, void* dx,
+                      float* dgamma, float* dbeta, float* workspace, mmi_stream_t stream);
+
+/* ---- a-5/a-6: candidate x history attention -----------------------------------------
+ * replaces models/encoder.py:44-73 (get_attn_logits: QK^T, outer-product mask,
+ * "set to -10000"), :138-161 (concat of two key blocks, /sqrt(dh), joint softmax, PV).
+ * One call handles ONE query side (candidate or history queries) over TWO key blocks
+ * with different query projections:
+ *     S = [ Qa Ka^T | Qb Kb^T ],  S[!(mq_i & mk_j)] = -10000,  P = softmax(S / sqrt(dh)),
+ *     O = P [Va ; Vb]
+ * Tensors are [B*L, ld] with head h at columns [h*dh, (h+1)*dh).  nblk may be 1.      */
+typedef struct {
+  const void* q; int64_t ldq;      /* query projection used against this key block */
+  const void* k; int64_t ldk;
+  const void* v; int64_t ldv;
+  const uint8_t* mask_k;           /* [B, Lk] */
+  int Lk;
+  /* backward outputs (same layout as q/k/v); may be NULL in forward */
+  void* dq; int64_t lddq;
+  void* dk; int64_t lddk;
+  void* dv; int64_t lddv;
+} mmi_attn_block;
+typedef struct {
+  int dtype; int impl;
+  int B; int H; int dh; int Lq;
+  const uint8_t* mask_q;           /* [B, Lq] */
+  int nblk; mmi_attn_block blk[2];
+  void* out; int64_t ldo;          /* [B*Lq, H*dh] */
+  float* lse;                      /* [B, H, Lq]  log-sum-exp of scaled logits */
+  /* backward only */
+  const void* dout; int64_t lddo;
+  float* delta;                    /* [B, H, Lq] scratch: rowsum(dO * O) */
+} mmi_attn_args;
+int mmi_attn_fwd(const mmi_attn_args* a, mmi_stream_t stream);
+/* writes dq for both blocks and delta */
+int mmi_attn_bwd_dq(const mmi_attn_args* a, mmi_stream_t stream);
+/* writes dk, dv of block `which` (needs lse and delta from the calls above) */
+int mmi_attn_bwd_dkv(const mmi_attn_args* a, int which, mmi_stream_t stream);
+
+/* ---- a-9: head Linear(d -> 1)  (models/decoder_leave_focal.py:451,596) ---------------*/
+int mmi_head_fwd(const void* x, int dtype, int64_t rows, int d, const float* w,
+                 const float* b, float* logits, mmi_stream_t stream);
+int64_t mmi_head_bwd_workspace(int d);
+int mmi_head_bwd(const void* x, int dtype, int64_t rows, int d, const float* w,
+                 const float* dlogits, const float* gscale /* device scalar or NULL */,
+                 void* dx, float* dw, float* db, float* workspace, mmi_stream_t stream);
+
+/* ---- a-10..a-12: loss --------------------------------------------------------------
+ * replaces models/decoder_leave_focal.py:490-572 for loss_type `focal`
+ * (my_sigmoid_focal_loss :35-59, alpha 0.5, gamma 2, masked sum / bsz) plus the
+ * diagnostics mse / mse2 (:552-558).  gt int64 [B,L] in {1,0,-1,-2}; gt is rewritten in
+ * place exactly as the reference does (:534-535) when rewrite_gt != 0.
+ * scalars (fp32[8]): 0 focal, 1 mse, 2 mse2, 3 loss(=weight*focal).
+ * dlogits[B,L] = d loss / d logits (already includes weight and inv_bsz).             */
+int mmi_focal_loss_fwd_bwd(const float* logits, int64_t* gt, int B, int L,
+                           const float* exposure_prob, float inv_bsz, float weight,
+                           int rewrite_gt, float* scalars, float* dlogits, mmi_stream_t stream);
+
+/* ---- a-14: global-norm clip + AdamW on flat fp32 buffers ----------------------------
+ * replaces main_for_seq_leave_earlystop_SegMM.py:298-299 (clip_grad_norm_(10.0),
+ * torch.optim.AdamW.step).  norm_out[0] = pre-clip global L2 norm, norm_out[1] = clip
+ * coefficient.  bf16_out (optional) receives the bf16 copy of the updated parameters.  */
+int64_t mmi_clip_adamw_workspace(int64_t n);
+int mmi_clip_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                   int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float max_norm, int step, float* norm_out, void* bf16_out,
+                   float* workspace, mmi_stream_t stream);
+
+/* fp32 -> bf16 cast, optionally transposed: src [rows, cols] -> dst [cols, rows]      */
+int mmi_cast_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int transpose,
+                  mmi_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMI_B200_H_ */

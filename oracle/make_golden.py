@@ -1,0 +1,191 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, via oracle/ref_shim.py).  Build-container only; the fixtures
+are committed so the GPU box never needs the reference tree.
+
+    python -m oracle.make_golden
+
+torch 2.11.0+cu128 (CPU), numpy 2.3, eval() mode (dropout off) -- see SURVEY
+section 8c for why bit-level comparison is only meaningful with dropout off.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import gather_oracle, ref_shim  # noqa: E402
+from segmminterest_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def run_model_case(name, d_model, nhead, nlayers, din, Lt, B, seed, store_sd=True, loss_types=("focal",),
+                   fill_seed=None):
+    args = ref_shim.make_args(d_model=d_model, nhead=nhead, num_layers_enc=nlayers,
+                              loss_type_list=list(loss_types))
+    model = ref_shim.build_reference_model(args, din=din, max_usr_len=Lt, seed=seed)
+    if fill_seed is not None:
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        sd = {k: torch.from_numpy(v) for k, v in synth.fill_state_dict(shapes, fill_seed).items()}
+        model.load_state_dict(sd)
+    else:
+        # the reference initialises biases / LN to 0 / 1; perturb so those paths are exercised
+        g = torch.Generator().manual_seed(seed + 1)
+        with torch.no_grad():
+            for k, p in model.named_parameters():
+                if p.ndim == 1:
+                    p.add_(torch.randn(p.shape, generator=g) * 0.05)
+                if k == "stage_mlp1.weight":
+                    p.mul_(3.0)
+    model.eval()
+    rng = np.random.default_rng(seed + 7)
+    usr, usr_mask, vid, vid_mask, gt = synth.make_dense_batch(rng, B, Lt, din)
+    batch = dict(usr_image=torch.from_numpy(usr), usr_id=torch.zeros(B, dtype=torch.long),
+                 usr_mask=torch.from_numpy(usr_mask), vid_image=torch.from_numpy(vid),
+                 vid_id=torch.zeros(B, dtype=torch.long), vid_mask=torch.from_numpy(vid_mask),
+                 gt=torch.from_numpy(gt.copy()))
+    out = ref_shim.run_reference(model, batch, mode="train")
+    out["loss"].backward()
+    save = dict(cfg=json.dumps(dict(d_model=d_model, nhead=nhead, num_layers_enc=nlayers, din=din, Lt=Lt, B=B,
+                                    seed=seed, loss_types=list(loss_types), fill_seed=fill_seed)),
+                usr_mask=usr_mask, vid_mask=vid_mask, gt_in=gt,
+                logits=out["logits"].detach().numpy(), gt_out=out["gt"].numpy(),
+                loss=np.float64(out["loss"].item()), mse=np.float64(out["mse"].item()),
+                mse2=np.float64(out["mse2"].item()))
+    for lt_ in loss_types:
+        save[lt_] = np.float64(out[lt_].item())
+    with torch.no_grad():
+        batch["gt"] = torch.from_numpy(gt.copy())
+        inf = ref_shim.run_reference(model, batch, mode="inference")
+    save["logits_inference"] = inf["logits"].numpy()
+    dead = []
+    if store_sd:
+        save["usr_image"] = usr
+        save["vid_image"] = vid
+        for k, v in model.state_dict().items():
+            save["sd/" + k] = v.numpy()
+        for k, p in model.named_parameters():
+            if p.grad is None:
+                dead.append(k)
+            else:
+                save["grad/" + k] = p.grad.numpy()
+    else:
+        save["data_seed"] = np.int64(seed + 7)
+        for k, p in model.named_parameters():
+            if p.grad is None:
+                dead.append(k)
+            else:
+                g = p.grad.numpy()
+                save["gradnorm/" + k] = np.float64(np.sqrt((g.astype(np.float64) ** 2).sum()))
+                save["gradhead/" + k] = g.reshape(-1)[:16].copy()
+    save["dead_params"] = json.dumps(dead)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print(name, "loss", save["loss"], "n_dead", len(dead))
+
+
+def run_loss_cases():
+    """compute_loss alone (decoder_leave_focal.py:490-572) on hand-made edge cases."""
+    args = ref_shim.make_args(d_model=32, nhead=2, num_layers_enc=2, loss_type_list=["focal", "interestBPR"])
+    model = ref_shim.build_reference_model(args, din=8, max_usr_len=4)
+    rng = np.random.default_rng(99)
+    B = 24
+    nv = rng.integers(1, 41, size=B)
+    nv[:3] = [40, 1, 2]
+    gt = synth.make_labels(rng, nv)
+    gt[3] = 1  # fully watched 40-segment video: view_len == 40 row (excluded from BPR)
+    gt[4, :] = -2
+    gt[4, :5] = 1  # fully watched short video -> BPR positive is the first pad position
+    logits = (rng.standard_normal((B, 40)) * 3).astype(np.float32)
+    logits[5, :4] = [30.0, -30.0, 60.0, -60.0]  # saturating sigmoids
+    lt = torch.from_numpy(logits).requires_grad_(True)
+    ep = list(np.linspace(1.0, 0.6, 40).astype(np.float64))
+    model.exposure_prob = ep
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = model.compute_loss(stage_logits=lt[..., None], gt=torch.from_numpy(gt.copy()))
+    (g_focal,) = torch.autograd.grad(out["focal"], lt, retain_graph=True)
+    (g_bpr,) = torch.autograd.grad(out["interestBPR"], lt, retain_graph=True)
+    np.savez_compressed(os.path.join(OUT, "loss_cases.npz"), logits=logits, gt_in=gt,
+                        exposure_prob=np.array(ep), gt_out=out["gt"].numpy(),
+                        focal=np.float64(out["focal"].item()), interestBPR=np.float64(out["interestBPR"].item()),
+                        mse=np.float64(out["mse"].item()), mse2=np.float64(out["mse2"].item()),
+                        loss=np.float64(out["loss"].item()), grad_focal=g_focal.numpy(), grad_bpr=g_bpr.numpy())
+    print("loss_cases focal", out["focal"].item(), "bpr", out["interestBPR"].item())
+
+
+def run_gather_case():
+    """FrameDatasetSeq_SegMM + DataCollator (utils/dataloader_SegMM.py:186-382) on a
+    5-video fixture; stores the inputs in index form plus the dense outputs."""
+    import pandas as pd
+    dl = ref_shim.load_dataloader()
+    rng = np.random.default_rng(5)
+    din = 1024
+    # videos 101..105 with 3,2,40,1,6 segments
+    nseg = {101: 3, 102: 2, 103: 40, 104: 1, 105: 6}
+    lineid, r = {}, 0
+    for pid, n in nseg.items():
+        for i in range(n):
+            lineid[f"{pid}-{i}"] = r
+            r += 1
+    lineid["105-25"] = 5  # reachable only through user_input_dict ("pid_sec")
+    table = rng.standard_normal((r, din), dtype=np.float32)
+    rows = [
+        # user, video, time, duration_ms, playing, label, hist items, hist playing, hist len
+        (7, 101, 1000, 14999, 6000, "[ 1 0 -1]", "[102 103]", "[ 9000 12000]", 2),
+        (7, 103, 2000, 200000, 200000, "[" + " ".join(["1"] * 40) + "]", "[101 102 105]", "[15000  5000 31000]", 3),
+        (8, 104, 3000, 4000, 1000, "[0]", "[]", "[]", 0),
+        (9, 105, 4000, 27000, 27000, "[1 1 1 1 1 1]", "[103 999]", "[100000 5000]", 2),
+    ]
+    df = pd.DataFrame(rows, columns=["user_id", "video_id", "time_ms", "duration_ms", "playing_time_x", "label_1D",
+                                     "history_items", "history_playing", "history_lengths"])
+    uid_dict = {"7": ["105_25", "555_0"], "8": ["104_0"], "9": ["101_0"]}  # NB: a user with zero rows crashes the reference (IndexError at :259)
+
+    class Corpus:
+        data_df = {"test": df}
+        user_input_dict = uid_dict
+
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "SegMM"))
+        json.dump({"7": 1, "8": 2, "9": 3}, open(os.path.join(td, "SegMM", "second_map_user2id.json"), "w"))
+        json.dump({str(p): i + 1 for i, p in enumerate(nseg)}, open(os.path.join(td, "SegMM", "second_map_item2id.json"), "w"))
+        os.chdir(td)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                ds = dl.FrameDatasetSeq_SegMM(corpus=Corpus(), lineid_map=lineid, feat_memmap=table, phase="test",
+                                              shuffle=False, verbose=False)
+                batch = dl.DataCollator()(list(ds))
+        finally:
+            os.chdir(cwd)
+    save = {"out/" + k: v.numpy() for k, v in batch.items()}
+    save["table"] = table
+    save["lineid_json"] = json.dumps(lineid)
+    save["user_input_json"] = json.dumps(uid_dict)
+    save["rows_json"] = json.dumps(rows)
+    save["user2id_json"] = json.dumps({"7": 1, "8": 2, "9": 3})
+    save["item2id_json"] = json.dumps({str(p): i + 1 for i, p in enumerate(nseg)})
+    np.savez_compressed(os.path.join(OUT, "gather_small.npz"), **save)
+    print("gather_small", {k: tuple(v.shape) for k, v in batch.items()})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    assert ref_shim.available(), "reference tree missing"
+    run_gather_case()
+    run_loss_cases()
+    run_model_case("model_small_dh32", d_model=64, nhead=2, nlayers=3, din=48, Lt=12, B=5, seed=11)
+    run_model_case("model_small_dh16", d_model=64, nhead=4, nlayers=4, din=40, Lt=20, B=4, seed=12)
+    run_model_case("model_full_b4", d_model=512, nhead=16, nlayers=6, din=1024, Lt=100, B=4, seed=13,
+                   store_sd=False, fill_seed=42)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,268 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the reference's MMinterest
+training-step arithmetic, written as plain functional
+PyTorch on a ``state_dict``.  It is the checker the CUDA path is compared with;
+nothing in ``segmminterest_b200/`` may import it.
+
+Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks this file against
+fixtures under ``tests/golden/`` that were produced by running the reference's
+own unmodified ``models/encoder.py`` + ``models/decoder_leave_focal.py``
+(``oracle/make_golden.py`` via ``oracle/ref_shim.py``), torch 2.11.0 CPU.
+The reference ships no tests / golden vectors of its own.
+
+Each function cites the reference file:line it restates (paths relative to
+/root/reference/MMinterest).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------
+# a-3  L1 normalisation of gathered features
+# --------------------------------------------------------------------------
+def l1_normalise(x: torch.Tensor) -> torch.Tensor:
+    """main_for_seq_leave_earlystop_SegMM.py:272-273: x / (||x||_1 + 1e-6)."""
+    return x / (x.norm(p=1, dim=-1, keepdim=True) + 1e-6)
+
+
+# --------------------------------------------------------------------------
+# a-4  embedding: Linear(Din->d) + PE + LN(eps 1e-12)
+# --------------------------------------------------------------------------
+def embed(sd, prefix, usr, vid, use_pe=True):
+    """models/encoder.py:425-473 (image inputs, dropout off)."""
+    d = sd[prefix + "vid_ln.weight"].shape[0]
+    v = F.linear(vid, sd[prefix + "vid_proj.weight"], sd[prefix + "vid_proj.bias"])
+    u = F.linear(usr, sd[prefix + "usr_proj.weight"], sd[prefix + "usr_proj.bias"])
+    if use_pe:
+        v = v + sd[prefix + "vid_pe.weight"][None, : v.shape[1]]
+        u = u + sd[prefix + "usr_pe.weight"][None, : u.shape[1]]
+    v = F.layer_norm(v, (d,), sd[prefix + "vid_ln.weight"], sd[prefix + "vid_ln.bias"], 1e-12)
+    u = F.layer_norm(u, (d,), sd[prefix + "usr_ln.weight"], sd[prefix + "usr_ln.bias"], 1e-12)
+    return v, u
+
+
+# --------------------------------------------------------------------------
+# a-5  one block of attention logits, with the "set to -10000" mask
+# --------------------------------------------------------------------------
+def attn_logits(sd, p, feat_k, mask_k, feat_q, mask_q, nhead):
+    """models/encoder.py:44-73.  q = proj[0](feat_q), k = proj[1](feat_k);
+    logits[b,h,i,j] = <q_i, k_j>; positions with mask_q[i] & mask_k[j] == 0 are
+    SET to -10000 (not added)."""
+    B, Lq, d = feat_q.shape
+    Lk = feat_k.shape[1]
+    dh = d // nhead
+    q = F.linear(feat_q, sd[p + "0.weight"], sd[p + "0.bias"]).view(B, Lq, nhead, dh)
+    k = F.linear(feat_k, sd[p + "1.weight"], sd[p + "1.bias"]).view(B, Lk, nhead, dh)
+    logits = torch.einsum("bqhd,bkhd->bhqk", q, k)
+    m = (mask_q[:, :, None] & mask_k[:, None, :])[:, None].expand(B, nhead, Lq, Lk)
+    return torch.where(m, logits, torch.full_like(logits, -10000.0))
+
+
+# --------------------------------------------------------------------------
+# a-6  four-way attention + output projection + residual LN
+# --------------------------------------------------------------------------
+def cross_attention(sd, p, vid, vid_mask, usr, usr_mask, nhead, need_usr=True):
+    """models/encoder.py:75-175 with sr_ratio=1, ablation 'ours', dropout off.
+    Joint softmax over [v2v | t2v] for candidate queries and [v2t | t2t] for
+    history queries; scale 1/sqrt(dh) is applied AFTER the mask fill."""
+    B, Lv, d = vid.shape
+    dh = d // nhead
+    scale = 1.0 / math.sqrt(dh)
+
+    def val(name, x):
+        return F.linear(x, sd[p + name + "_proj.2.weight"], sd[p + name + "_proj.2.bias"])
+
+    v_logits = torch.cat([attn_logits(sd, p + "v2v_proj.", vid, vid_mask, vid, vid_mask, nhead),
+                          attn_logits(sd, p + "t2v_proj.", usr, usr_mask, vid, vid_mask, nhead)], -1) * scale
+    v_value = torch.cat([val("v2v", vid), val("t2v", usr)], 1).view(B, -1, nhead, dh)
+    vid_ = torch.einsum("bhqk,bkhd->bqhd", F.softmax(v_logits, -1), v_value).reshape(B, Lv, d)
+    vid_ = F.linear(vid_, sd[p + "ff_vid.weight"], sd[p + "ff_vid.bias"])
+    vid_out = F.layer_norm(vid + vid_, (d,), sd[p + "ln_vid.weight"], sd[p + "ln_vid.bias"], 1e-12)
+    if not need_usr:
+        return vid_out, None
+    Lt = usr.shape[1]
+    t_logits = torch.cat([attn_logits(sd, p + "v2t_proj.", vid, vid_mask, usr, usr_mask, nhead),
+                          attn_logits(sd, p + "t2t_proj.", usr, usr_mask, usr, usr_mask, nhead)], -1) * scale
+    t_value = torch.cat([val("v2t", vid), val("t2t", usr)], 1).view(B, -1, nhead, dh)
+    usr_ = torch.einsum("bhqk,bkhd->bqhd", F.softmax(t_logits, -1), t_value).reshape(B, Lt, d)
+    usr_ = F.linear(usr_, sd[p + "ff_usr.weight"], sd[p + "ff_usr.bias"])
+    usr_out = F.layer_norm(usr + usr_, (d,), sd[p + "ln_usr.weight"], sd[p + "ln_usr.bias"], 1e-12)
+    return vid_out, usr_out
+
+
+# --------------------------------------------------------------------------
+# a-7  FFN + residual LN
+# --------------------------------------------------------------------------
+def ffn(sd, p, side, x):
+    """models/encoder.py:202-206 + kn_util/nn_utils/layers/mlp.py:17-24:
+    LN(x + W2 gelu_erf(W1 x)), eps 1e-12."""
+    d = x.shape[-1]
+    h = F.gelu(F.linear(x, sd[p + f"ff_{side}.layers.0.weight"], sd[p + f"ff_{side}.layers.0.bias"]))
+    h = F.linear(h, sd[p + f"ff_{side}.layers.1.weight"], sd[p + f"ff_{side}.layers.1.bias"])
+    return F.layer_norm(x + h, (d,), sd[p + f"ln_{side}.weight"], sd[p + f"ln_{side}.bias"], 1e-12)
+
+
+# --------------------------------------------------------------------------
+# a-8  encoder stack; output = INPUT of the last layer
+# --------------------------------------------------------------------------
+def backbone(sd, prefix, usr, usr_mask, vid, vid_mask, nhead, num_layers, use_pe=True):
+    """models/encoder.py:302-324,475-520.  intermediate_states records vid_feat
+    BEFORE each layer and the caller takes [-1], so layer N-1 never reaches the
+    output, nor does the history side of layer N-2."""
+    v, u = embed(sd, prefix, usr, vid, use_pe)
+    for i in range(num_layers - 1):
+        p = f"{prefix}encoder.layers.{i}."
+        need_usr = i < num_layers - 2
+        v, u2 = cross_attention(sd, p + "cross_attn.", v, vid_mask, u, usr_mask, nhead, need_usr)
+        v = ffn(sd, p, "vid", v)
+        if need_usr:
+            u = ffn(sd, p, "usr", u2)
+    return v
+
+
+# --------------------------------------------------------------------------
+# a-9/a-10  head (+ optional learnable position bias)
+# --------------------------------------------------------------------------
+def head_logits(sd, x):
+    """models/decoder_leave_focal.py:451,596 and :497-504."""
+    logits = F.linear(x, sd["stage_mlp1.weight"], sd["stage_mlp1.bias"]).squeeze(-1)
+    if "bias_weight" in sd:
+        pos = torch.arange(logits.shape[1], dtype=logits.dtype)
+        logits = logits + (pos + 1) * sd["bias_weight"] + sd["bias_bias"]
+    return logits
+
+
+# --------------------------------------------------------------------------
+# a-11/a-12  loss (focal) + diagnostics
+# --------------------------------------------------------------------------
+def focal_loss_sum(logits, gt_mut, mask, exposure_prob, bsz):
+    """models/decoder_leave_focal.py:35-59,533-538: alpha 0.5, gamma 2, masked
+    sum / batch size.  ``gt_mut`` is gt after the in-place rewrite
+    (gt>0 -> 1, gt==-1 -> 0; -2 stays)."""
+    t = gt_mut.to(logits.dtype)
+    ep = torch.as_tensor(exposure_prob, dtype=logits.dtype)[None, : logits.shape[1]]
+    p = torch.sigmoid(logits) * ep
+    ce = F.binary_cross_entropy_with_logits(logits, t, reduction="none")
+    p_t = p * t + (1 - p) * (1 - t)
+    loss = ce * (1 - p_t) ** 2
+    alpha_t = 0.5 * t + 0.5 * (1 - t)
+    loss = alpha_t * loss
+    return (loss * mask.to(loss.dtype)).sum() / bsz
+
+
+def interest_bpr_all(logits, gt):
+    """models/decoder_leave_focal.py:163-221 (default loss `interestBPR`)."""
+    view = (gt == 1).sum(1)
+    rows = view < 40
+    lg = logits[rows]
+    vl = view[rows]
+    n = lg.shape[0]
+    pos = lg[torch.arange(n), vl]
+    neg_mask = torch.ones_like(lg, dtype=torch.bool)
+    neg_mask[torch.arange(n), vl] = False
+    neg = lg[neg_mask].view(n, -1)
+    neg_softmax = (neg - neg.max()).softmax(1)
+    soft = (neg - pos[:, None]).sigmoid() * neg_softmax
+    return -(soft.sum(1)).clamp(min=1e-8, max=1 - 1e-8).log().mean()
+
+
+def compute_loss(logits, gt, exposure_prob, loss_type_list=("focal",), loss_weight=None):
+    """models/decoder_leave_focal.py:490-572.  Returns the same dict (tensors).
+    ``gt`` is NOT modified here; the returned ``gt`` is the rewritten copy the
+    reference leaves behind when 'focal' is in the list."""
+    loss_weight = loss_weight or {}
+    B = gt.shape[0]
+    mask = gt != -2
+    p = torch.sigmoid(logits)
+    h_t = torch.cumsum(torch.log(p), 1)
+    survival = torch.exp(h_t)
+    view_lengths = (gt == 1).to(logits.dtype).sum(1, keepdim=True)
+    durations = mask.sum(1)
+    survival_masked = torch.where(mask, survival, torch.zeros_like(survival))
+    out = {}
+    gt_cur = gt.clone()
+    for name in loss_type_list:
+        if name == "focal":
+            gt_cur = torch.where(gt_cur > 0, torch.ones_like(gt_cur), gt_cur)
+            gt_cur = torch.where(gt_cur == -1, torch.zeros_like(gt_cur), gt_cur)
+            out["focal"] = focal_loss_sum(logits, gt_cur, mask, exposure_prob, B)
+        elif name == "interestBPR":
+            out["interestBPR"] = interest_bpr_all(logits, gt)
+        else:
+            raise NotImplementedError(name)
+    s = survival_masked.sum(1)  # [B]
+    # nn.MSELoss()([B], [B,1]) broadcasts to [B,B] (reference quirk, :552)
+    out["mse"] = ((s[None, :] - view_lengths) ** 2).mean()
+    sm2 = survival_masked.clone()
+    sm2[torch.arange(B), (durations - 1) % sm2.shape[1]] = 1.0  # :554-555 (index -1 wraps)
+    view_lengths2 = (gt_cur >= 0).sum(1, keepdim=True).to(logits.dtype)
+    out["mse2"] = ((sm2.sum(1)[None, :] - view_lengths2) ** 2).mean()
+    loss = 0.0
+    for name in loss_type_list:
+        loss = loss + out[name] * loss_weight.get(name, 1.0)
+    out["loss"] = loss
+    out["logits"] = logits
+    out["gt"] = gt_cur
+    return out
+
+
+# --------------------------------------------------------------------------
+# full forward (image modality, single backbone)
+# --------------------------------------------------------------------------
+def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_layers,
+            exposure_prob=None, loss_type_list=("focal",), use_pe=True, mode="train"):
+    """models/decoder_leave_focal.py:574-658 for input_type image/image,
+    backbone2=None, head=None."""
+    x = backbone(sd, "backbone1.", usr_image, usr_mask.bool(), vid_image, vid_mask.bool(),
+                 nhead, num_layers, use_pe)
+    logits = head_logits(sd, x)
+    if mode == "inference":
+        return dict(logits=logits, gt=gt)
+    exposure_prob = exposure_prob if exposure_prob is not None else [1.0] * logits.shape[1]
+    return compute_loss(logits, gt, exposure_prob, loss_type_list)
+
+
+def live_param_names(sd_keys, num_layers):
+    """Names of parameters that receive a gradient in the reference (SURVEY
+    section 0 fact 5): everything except layer N-1, the history side of layer
+    N-2 (its v2t/t2t projections, ff_usr, ln_usr), and the never-called
+    pe_lns / txt_lvl_projs / patch_merge."""
+    live = []
+    N = num_layers
+    for k in sd_keys:
+        if any(s in k for s in ("pe_lns", "txt_lvl_projs", "patch_merge")):
+            continue
+        if ".encoder.layers." in k:
+            i = int(k.split(".encoder.layers.")[1].split(".")[0])
+            if i == N - 1:
+                continue
+            if i == N - 2 and any(s in k for s in ("v2t_proj", "t2t_proj", "ff_usr", "ln_usr")):
+                continue
+        live.append(k)
+    return live
+
+
+# --------------------------------------------------------------------------
+# a-14  step tail: global-norm clip + AdamW
+# --------------------------------------------------------------------------
+def clip_and_adamw(params, grads, exp_avg, exp_avg_sq, step, lr=1e-3, wd=1e-4, betas=(0.9, 0.999),
+                   eps=1e-8, max_norm=10.0):
+    """main_for_seq_leave_earlystop_SegMM.py:298-299: clip_grad_norm_(10.0) then
+    torch.optim.AdamW(lr, weight_decay).step().  Lists of tensors, updated in
+    place; returns the pre-clip global norm."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).to(grads[0].dtype)
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    b1, b2 = betas
+    for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq):
+        g = g * coef
+        p.mul_(1 - lr * wd)
+        m.mul_(b1).add_(g, alpha=1 - b1)
+        v.mul_(b2).addcmul_(g, g, value=1 - b2)
+        bc1 = 1 - b1 ** step
+        bc2 = 1 - b2 ** step
+        denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+        p.addcdiv_(m, denom, value=-lr / bc1)
+    return total

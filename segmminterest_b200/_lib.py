@@ -1,0 +1,96 @@
+"""ctypes binding of libmmi_b200.so (include/mmi_b200.h).  Fails loudly when the library
+is missing: there is no CPU / eager fallback in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmmi_b200.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU = 0, 1
+GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
+IMPL_SIMT, IMPL_TC = 0, 1
+
+c_p = C.c_void_p
+i64 = C.c_int64
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [("layout", C.c_int), ("impl", C.c_int), ("in_dtype", C.c_int), ("out_dtype", C.c_int),
+                ("M", i64), ("N", i64), ("K", i64),
+                ("A", c_p), ("lda", i64), ("B", c_p), ("ldb", i64), ("C", c_p), ("ldc", i64),
+                ("bias", c_p), ("act", C.c_int),
+                ("preact", c_p), ("ld_preact", i64),
+                ("mul_gelu_grad", c_p), ("ld_mul", i64),
+                ("add", c_p), ("ld_add", i64), ("add_mod", i64), ("add_dtype", C.c_int),
+                ("accumulate", C.c_int), ("split_k", C.c_int)]
+
+
+class AttnBlock(C.Structure):
+    _fields_ = [("q", c_p), ("ldq", i64), ("k", c_p), ("ldk", i64), ("v", c_p), ("ldv", i64),
+                ("mask_k", c_p), ("Lk", C.c_int),
+                ("dq", c_p), ("lddq", i64), ("dk", c_p), ("lddk", i64), ("dv", c_p), ("lddv", i64)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("dtype", C.c_int), ("impl", C.c_int),
+                ("B", C.c_int), ("H", C.c_int), ("dh", C.c_int), ("Lq", C.c_int),
+                ("mask_q", c_p), ("nblk", C.c_int), ("blk", AttnBlock * 2),
+                ("out", c_p), ("ldo", i64), ("lse", c_p),
+                ("dout", c_p), ("lddo", i64), ("delta", c_p)]
+
+
+_SIGS = {
+    "mmi_version": (C.c_int, []),
+    "mmi_last_error": (C.c_char_p, []),
+    "mmi_has_tc": (C.c_int, []),
+    "mmi_gather_l1norm_fwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, i64, c_p, C.c_int, c_p, C.c_int, c_p]),
+    "mmi_gemm": (C.c_int, [C.POINTER(GemmArgs), c_p]),
+    "mmi_colsum_acc": (C.c_int, [c_p, C.c_int, i64, C.c_int, i64, c_p, c_p, i64, c_p]),
+    "mmi_layernorm_fwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, C.c_float, c_p, c_p, c_p]),
+    "mmi_layernorm_bwd_workspace": (i64, [C.c_int]),
+    "mmi_layernorm_bwd": (C.c_int, [c_p, c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "mmi_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), c_p]),
+    "mmi_attn_bwd_dq": (C.c_int, [C.POINTER(AttnArgs), c_p]),
+    "mmi_attn_bwd_dkv": (C.c_int, [C.POINTER(AttnArgs), C.c_int, c_p]),
+    "mmi_head_fwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p]),
+    "mmi_head_bwd_workspace": (i64, [C.c_int]),
+    "mmi_head_bwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "mmi_focal_loss_fwd_bwd": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, C.c_float, C.c_float, C.c_int, c_p, c_p, c_p]),
+    "mmi_clip_adamw_workspace": (i64, [i64]),
+    "mmi_clip_adamw": (C.c_int, [c_p, c_p, c_p, c_p, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                 C.c_float, C.c_int, c_p, c_p, c_p, c_p]),
+    "mmi_cast_bf16": (C.c_int, [c_p, c_p, i64, i64, C.c_int, c_p]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+_lib = None
+
+
+class MMIError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MMIError(f"{LIB_PATH} is missing: run `python -m segmminterest_b200.build` (nvcc, sm_100a). "
+                       "There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().mmi_last_error().decode()
+        raise MMIError(f"{what} failed (rc={rc}): {msg}")

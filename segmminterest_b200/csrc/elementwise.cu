@@ -1,0 +1,569 @@
+// HBM-bound row kernels of the MMinterest step: LayerNorm fwd/bwd, bias-gradient column
+// sums, the Linear(d->1) head, the fused focal-loss/diagnostics kernel, global-norm clip +
+// AdamW, and the fp32->bf16 parameter cast.  Reductions use warp shuffles; cross-CTA
+// reductions are two-stage (fixed order => run-to-run deterministic).
+#include "common.cuh"
+
+namespace mmi {
+
+constexpr int kMaxVecPerLane = 8;   // d <= 1024
+constexpr int kRedCtas = kNumSMs * 4;
+
+// ------------------------------------------------------------------ LayerNorm forward
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, int64_t rows, int d,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float eps, T* __restrict__ y, float* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = d >> 2;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    const T* xr = x + row * (int64_t)d;
+    float4 v[kMaxVecPerLane];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerLane; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = (c < nvec) ? load4(xr + c * 4) : make_float4(0, 0, 0, 0);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    const float mean = warp_sum(s) / (float)d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, e = v[i].w - mean;
+        q += a * a + b * b + cc * cc + e * e;
+      }
+    }
+    const float var = warp_sum(q) / (float)d;
+    const float rstd = 1.0f / sqrtf(var + eps);
+    if (lane == 0 && stats != nullptr) {
+      stats[2 * row] = mean;
+      stats[2 * row + 1] = rstd;
+    }
+    T* yr = y + row * (int64_t)d;
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c * 4);
+        const float4 b = *reinterpret_cast<const float4*>(beta + c * 4);
+        float4 o;
+        o.x = (v[i].x - mean) * rstd * g.x + b.x;
+        o.y = (v[i].y - mean) * rstd * g.y + b.y;
+        o.z = (v[i].z - mean) * rstd * g.z + b.z;
+        o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        store4(yr + c * 4, o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+// partial layout: [gridDim.x][2][d]  (dgamma then dbeta)
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t rows, int d,
+                                                            const float* __restrict__ gamma, const float* __restrict__ stats,
+                                                            const T* __restrict__ add, T* __restrict__ dx,
+                                                            float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [8 warps][2][d]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = d >> 2;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float4 dg[kMaxVecPerLane], db[kMaxVecPerLane];
+#pragma unroll
+  for (int i = 0; i < kMaxVecPerLane; ++i) dg[i] = db[i] = make_float4(0, 0, 0, 0);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += wstride) {
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    const T* xr = x + row * (int64_t)d;
+    const T* dyr = dy + row * (int64_t)d;
+    float4 xh[kMaxVecPerLane], g[kMaxVecPerLane];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 xv = load4(xr + c * 4);
+        const float4 dv = load4(dyr + c * 4);
+        const float4 gm = *reinterpret_cast<const float4*>(gamma + c * 4);
+        xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        g[i] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
+        c1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        c2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+        dg[i].x += dv.x * xh[i].x; dg[i].y += dv.y * xh[i].y; dg[i].z += dv.z * xh[i].z; dg[i].w += dv.w * xh[i].w;
+        db[i].x += dv.x; db[i].y += dv.y; db[i].z += dv.z; db[i].w += dv.w;
+      } else {
+        xh[i] = g[i] = make_float4(0, 0, 0, 0);
+      }
+    }
+    c1 = warp_sum(c1) / (float)d;
+    c2 = warp_sum(c2) / (float)d;
+    T* dxr = dx + row * (int64_t)d;
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        float4 o;
+        o.x = rstd * (g[i].x - c1 - xh[i].x * c2);
+        o.y = rstd * (g[i].y - c1 - xh[i].y * c2);
+        o.z = rstd * (g[i].z - c1 - xh[i].z * c2);
+        o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
+        if (add != nullptr) {
+          const float4 a = load4(add + row * (int64_t)d + c * 4);
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        }
+        store4(dxr + c * 4, o);
+      }
+    }
+  }
+  // CTA reduction of the per-warp column sums (fixed order)
+  float* mine = sm + (size_t)warp * 2 * d;
+#pragma unroll
+  for (int i = 0; i < kMaxVecPerLane; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      *reinterpret_cast<float4*>(mine + c * 4) = dg[i];
+      *reinterpret_cast<float4*>(mine + d + c * 4) = db[i];
+    }
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += sm[(size_t)w * 2 * d + c];
+    partial[(size_t)blockIdx.x * 2 * d + c] = s;
+  }
+}
+
+// out[c] += sum_b partial[b][c]   (c < ncols); out2 takes the second half when split_at > 0
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int ncols, float* __restrict__ out_a,
+                                       float* __restrict__ out_b, int split_at) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncols) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * ncols + c];
+  if (split_at > 0 && c >= split_at) {
+    if (out_b) out_b[c - split_at] += s;
+  } else if (out_a) {
+    out_a[c] += s;
+  }
+}
+
+// ------------------------------------------------------------------ column sums (bias grads)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int64_t M, int N, int64_t ldx, float* __restrict__ partial) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= N) return;
+  const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float4 s = make_float4(0, 0, 0, 0);
+  for (int64_t r = r0; r < r1; ++r) {
+    const float4 v = load4(x + r * ldx + c);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * N + c) = s;
+}
+
+// ------------------------------------------------------------------ head Linear(d -> 1)
+template <typename T>
+__global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ x, int64_t rows, int d, const float* __restrict__ w,
+                                                       const float* __restrict__ b, float* __restrict__ logits) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = d >> 2;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    const T* xr = x + row * (int64_t)d;
+    float s = 0.f;
+    for (int c = lane; c < nvec; c += 32) {
+      const float4 v = load4(xr + c * 4);
+      const float4 ww = *reinterpret_cast<const float4*>(w + c * 4);
+      s += v.x * ww.x + v.y * ww.y + v.z * ww.z + v.w * ww.w;
+    }
+    s = warp_sum(s);
+    if (lane == 0) logits[row] = s + b[0];
+  }
+}
+
+// partial layout [gridDim.x][d + 1]: dw then db
+template <typename T>
+__global__ void __launch_bounds__(256) head_bwd_kernel(const T* __restrict__ x, int64_t rows, int d, const float* __restrict__ w,
+                                                       const float* __restrict__ dlogits, const float* __restrict__ gscale,
+                                                       T* __restrict__ dx, float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [8][d+1]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = d >> 2;
+  const float gs = gscale ? gscale[0] : 1.0f;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float4 dw[kMaxVecPerLane];
+#pragma unroll
+  for (int i = 0; i < kMaxVecPerLane; ++i) dw[i] = make_float4(0, 0, 0, 0);
+  float dbias = 0.f;
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += wstride) {
+    const float g = dlogits[row] * gs;
+    dbias += g;
+#pragma unroll
+    for (int i = 0; i < kMaxVecPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const float4 xv = load4(x + row * (int64_t)d + c * 4);
+        const float4 ww = *reinterpret_cast<const float4*>(w + c * 4);
+        dw[i].x += g * xv.x; dw[i].y += g * xv.y; dw[i].z += g * xv.z; dw[i].w += g * xv.w;
+        store4(dx + row * (int64_t)d + c * 4, make_float4(g * ww.x, g * ww.y, g * ww.z, g * ww.w));
+      }
+    }
+  }
+  float* mine = sm + (size_t)warp * (d + 1);
+#pragma unroll
+  for (int i = 0; i < kMaxVecPerLane; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      mine[c * 4 + 0] = dw[i].x; mine[c * 4 + 1] = dw[i].y; mine[c * 4 + 2] = dw[i].z; mine[c * 4 + 3] = dw[i].w;
+    }
+  }
+  if (lane == 0) mine[d] = dbias;  // every lane carries the same dbias
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < d + 1; c += blockDim.x) {
+    float s = 0.f;
+    for (int wi = 0; wi < nw; ++wi) s += sm[(size_t)wi * (d + 1) + c];
+    partial[(size_t)blockIdx.x * (d + 1) + c] = s;
+  }
+}
+
+// ------------------------------------------------------------------ focal loss + diagnostics
+// One CTA (<= 32 warps), one warp per row, L <= 64.  models/decoder_leave_focal.py:490-572.
+__global__ void __launch_bounds__(1024) focal_loss_kernel(const float* __restrict__ logits, int64_t* __restrict__ gt, int B, int L,
+                                                          const float* __restrict__ ep, float inv_bsz, float weight, int rewrite_gt,
+                                                          float* __restrict__ scalars, float* __restrict__ dlogits) {
+  __shared__ double red[32][9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double acc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+  for (int row = warp; row < B; row += nw) {
+    float x[2], sig[2], logp[2];
+    long long g[2];
+    bool in[2], valid[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int l = lane + 32 * h;
+      in[h] = l < L;
+      x[h] = in[h] ? logits[(size_t)row * L + l] : 0.f;
+      g[h] = in[h] ? gt[(size_t)row * L + l] : -2;
+      valid[h] = in[h] && g[h] != -2;
+      sig[h] = 1.0f / (1.0f + expf(-x[h]));
+      logp[h] = in[h] ? logf(sig[h]) : 0.f;
+    }
+    // inclusive scan of log p over the row: h_t = cumsum(log sigmoid(x))  (:506-510)
+    float sc0 = logp[0];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float n = __shfl_up_sync(0xffffffffu, sc0, o);
+      if (lane >= o) sc0 += n;
+    }
+    const float tot0 = __shfl_sync(0xffffffffu, sc0, 31);
+    float sc1 = logp[1];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float n = __shfl_up_sync(0xffffffffu, sc1, o);
+      if (lane >= o) sc1 += n;
+    }
+    sc1 += tot0;
+    const float surv[2] = {expf(sc0), expf(sc1)};
+    const float sm0 = valid[0] ? surv[0] : 0.f, sm1 = valid[1] ? surv[1] : 0.f;
+    const float s_row = warp_sum(sm0 + sm1);
+    const int n_valid = __popc(__ballot_sync(0xffffffffu, valid[0])) + __popc(__ballot_sync(0xffffffffu, valid[1]));
+    const int n_view = __popc(__ballot_sync(0xffffffffu, in[0] && g[0] == 1)) + __popc(__ballot_sync(0xffffffffu, in[1] && g[1] == 1));
+    const int n_nonneg_orig = __popc(__ballot_sync(0xffffffffu, in[0] && g[0] >= 0)) + __popc(__ballot_sync(0xffffffffu, in[1] && g[1] >= 0));
+    // mse2: survival_masked[i, durations[i]-1] = 1 (python index -1 wraps to L-1)  (:554-555)
+    const int pos = (n_valid - 1 + L) % L;
+    const float at_pos = (pos < 32) ? __shfl_sync(0xffffffffu, sm0, pos) : __shfl_sync(0xffffffffu, sm1, pos - 32);
+    const float s2_row = s_row - at_pos + 1.0f;
+    // after the in-place rewrite gt in {1,0,-2}: (gt>=0).sum() == n_valid; otherwise count of {1,0}
+    const float v2 = rewrite_gt ? (float)n_valid : (float)n_nonneg_orig;
+    float lsum = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int l = lane + 32 * h;
+      if (!in[h]) continue;
+      const long long gn = (g[h] > 0) ? 1 : (g[h] == -1 ? 0 : g[h]);
+      if (rewrite_gt) gt[(size_t)row * L + l] = gn;
+      float dl = 0.f;
+      if (valid[h]) {
+        const float t = (float)gn;
+        const float e = ep[l];
+        const float p = sig[h] * e;
+        const float ce = fmaxf(x[h], 0.f) - x[h] * t + log1pf(expf(-fabsf(x[h])));
+        const float pt = p * t + (1.f - p) * (1.f - t);
+        const float om = 1.f - pt;
+        lsum += 0.5f * ce * om * om;
+        const float dp = e * sig[h] * (1.f - sig[h]);
+        dl = 0.5f * ((sig[h] - t) * om * om - ce * 2.f * om * (2.f * t - 1.f) * dp);
+      }
+      dlogits[(size_t)row * L + l] = dl * weight * inv_bsz;
+    }
+    lsum = warp_sum(lsum);
+    if (lane == 0) {
+      acc[0] += lsum;
+      acc[1] += s_row; acc[2] += (double)s_row * s_row;
+      acc[3] += n_view; acc[4] += (double)n_view * n_view;
+      acc[5] += s2_row; acc[6] += (double)s2_row * s2_row;
+      acc[7] += v2; acc[8] += (double)v2 * v2;
+    }
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) red[warp][i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[9];
+    for (int i = 0; i < 9; ++i) {
+      t[i] = 0.0;
+      for (int w = 0; w < nw; ++w) t[i] += red[w][i];
+    }
+    const double b = (double)B;
+    const double focal = t[0] * (double)inv_bsz;
+    // nn.MSELoss()([B], [B,1]) broadcasts to [B,B]: mean_ij (s_j - v_i)^2  (:552)
+    const double mse = t[2] / b - 2.0 * (t[1] / b) * (t[3] / b) + t[4] / b;
+    const double mse2 = t[6] / b - 2.0 * (t[5] / b) * (t[7] / b) + t[8] / b;
+    scalars[0] = (float)focal;
+    scalars[1] = (float)mse;
+    scalars[2] = (float)mse2;
+    scalars[3] = (float)(focal * (double)weight);
+  }
+}
+
+// ------------------------------------------------------------------ clip + AdamW
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ partial) {
+  __shared__ double red[8];
+  float s = 0.f;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  int iter = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = *reinterpret_cast<const float4*>(g + i * 4);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    if (++iter == 64) { acc += s; s = 0.f; iter = 0; }
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) s += g[i] * g[i];
+  acc += s;
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void clip_coef_kernel(const double* __restrict__ partial, int n, float max_norm, float* __restrict__ norm_out) {
+  double t = 0.0;
+  for (int i = threadIdx.x; i < n; i += 32) t += partial[i];
+  t = warp_sum_d(t);
+  if (threadIdx.x == 0) {
+    const float norm = (float)sqrt(t);
+    float coef = max_norm / (norm + 1e-6f);  // torch.nn.utils.clip_grad_norm_
+    coef = coef > 1.0f ? 1.0f : coef;
+    norm_out[0] = norm;
+    norm_out[1] = coef;
+  }
+}
+
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, int64_t n, float lr_wd, float beta1, float beta2,
+                                                    float eps, float step_size, float bc2_sqrt, const float* __restrict__ norm_out,
+                                                    __nv_bfloat16* __restrict__ bf16_out) {
+  const float coef = norm_out ? norm_out[1] : 1.0f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * coef;
+    float pi = p[i] * (1.0f - lr_wd);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (bf16_out) bf16_out[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+// ------------------------------------------------------------------ cast
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void cast_bf16_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int64_t cols) {
+  __shared__ float tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[c * rows + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+static int grid_for_rows(int64_t rows, int warps_per_cta, int cap) {
+  int64_t ctas = (rows + warps_per_cta - 1) / warps_per_cta;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  return (int)ctas;
+}
+
+}  // namespace mmi
+
+using namespace mmi;
+
+extern "C" int mmi_layernorm_fwd(const void* x, int dtype, int64_t rows, int d, const float* gamma, const float* beta, float eps,
+                                 void* y, float* stats, mmi_stream_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMI_CHECK_ARG(x && y && gamma && beta, "layernorm_fwd: null pointer");
+  MMI_CHECK_ARG(d % 4 == 0 && d <= 128 * kMaxVecPerLane && d > 0, "layernorm: d=%d must be a multiple of 4 and <= %d", d, 128 * kMaxVecPerLane);
+  if (rows == 0) return MMI_OK;
+  const int grid = grid_for_rows(rows, 8, kNumSMs * 8);
+  if (dtype == MMI_F32) layernorm_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, rows, d, gamma, beta, eps, (float*)y, stats);
+  else if (dtype == MMI_BF16) layernorm_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, rows, d, gamma, beta, eps, (__nv_bfloat16*)y, stats);
+  else { set_error("layernorm_fwd: bad dtype %d", dtype); return MMI_EINVAL; }
+  MMI_CHECK_LAUNCH();
+  return MMI_OK;
+}
+
+extern "C" int64_t mmi_layernorm_bwd_workspace(int d) { return (int64_t)kRedCtas * 2 * d; }
+
+extern "C" int mmi_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int d, const float* gamma, const float* stats,
+                                 const void* add, void* dx, float* dgamma, float* dbeta, float* workspace, mmi_stream_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMI_CHECK_ARG(dy && x && gamma && stats && dx && workspace, "layernorm_bwd: null pointer");
+  MMI_CHECK_ARG(d % 4 == 0 && d <= 128 * kMaxVecPerLane && d > 0, "layernorm: d=%d must be a multiple of 4 and <= %d", d, 128 * kMaxVecPerLane);
+  if (rows == 0) return MMI_OK;
+  const int grid = grid_for_rows(rows, 8, kRedCtas);
+  const size_t smem = (size_t)8 * 2 * d * sizeof(float);
+  if (dtype == MMI_F32) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layernorm_bwd_kernel<float><<<grid, 256, smem, st>>>((const float*)dy, (const float*)x, rows, d, gamma, stats, (const float*)add, (float*)dx, workspace);
+  } else if (dtype == MMI_BF16) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    layernorm_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, rows, d, gamma, stats,
+                                                                  (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, workspace);
+  } else { set_error("layernorm_bwd: bad dtype %d", dtype); return MMI_EINVAL; }
+  MMI_CHECK_LAUNCH();
+  if (dgamma || dbeta) {
+    reduce_partials_kernel<<<(2 * d + 255) / 256, 256, 0, st>>>(workspace, grid, 2 * d, dgamma, dbeta, d);
+    MMI_CHECK_LAUNCH();
+  }
+  return MMI_OK;
+}
+
+extern "C" int mmi_colsum_acc(const void* x, int dtype, int64_t M, int N, int64_t ldx, float* out, float* workspace,
+                              int64_t workspace_floats, mmi_stream_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMI_CHECK_ARG(x && out && workspace, "colsum: null pointer");
+  MMI_CHECK_ARG(N % 4 == 0 && N > 0, "colsum: N=%d must be a multiple of 4", N);
+  if (M == 0) return MMI_OK;
+  const int gx = (N / 4 + 255) / 256;
+  int64_t gy = (2 * kNumSMs + gx - 1) / gx;
+  if (gy > M) gy = M;
+  if (gy * N > workspace_floats) gy = workspace_floats / N;
+  MMI_CHECK_ARG(gy >= 1, "colsum: workspace too small (%lld floats for N=%d)", (long long)workspace_floats, N);
+  dim3 grid(gx, (unsigned)gy);
+  if (dtype == MMI_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, M, N, ldx, workspace);
+  else if (dtype == MMI_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, M, N, ldx, workspace);
+  else { set_error("colsum: bad dtype %d", dtype); return MMI_EINVAL; }
+  MMI_CHECK_LAUNCH();
+  reduce_partials_kernel<<<(N + 255) / 256, 256, 0, st>>>(workspace, (int)gy, N, out, nullptr, 0);
+  MMI_CHECK_LAUNCH();
+  return MMI_OK;
+}
+
+extern "C" int mmi_head_fwd(const void* x, int dtype, int64_t rows, int d, const float* w, const float* b, float* logits,
+                            mmi_stream_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMI_CHECK_ARG(x && w && b && logits, "head_fwd: null pointer");
+  MMI_CHECK_ARG(d % 4 == 0 && d > 0, "head: d=%d must be a multiple of 4", d);
+  if (rows == 0) return MMI_OK;
+  const int grid = grid_for_rows(rows, 8, kNumSMs * 8);
+  if (dtype == MMI_F32) head_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, rows, d, w, b, logits);
+  else if (dtype == MMI_BF16) head_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, rows, d, w, b, logits);
+  else { set_error("head_fwd: bad dtype %d", dtype); return MMI_EINVAL; }
+  MMI_CHECK_LAUNCH();
+  return MMI_OK;
+}
+
+extern "C" int64_t mmi_head_bwd_workspace(int d) { return (int64_t)kRedCtas * (d + 1); }
+
+extern "C" int mmi_head_bwd(const void* x, int dtype, int64_t rows, int d, const float* w, const float* dlogits, const float* gscale,
+                            void* dx, float* dw, float* db, float* workspace, mmi_stream_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMI_CHECK_ARG(x && w && dlogits && dx && dw && db && workspace, "head_bwd: null pointer");
+  MMI_CHECK_ARG(d % 4 == 0 && d <= 128 * kMaxVecPerLane && d > 0, "head: d=%d must be a multiple of 4 and <= %d", d, 128 * kMaxVecPerLane);
+  if (rows == 0) return MMI_OK;
+  const int grid = grid_for_rows(rows, 8, kRedCtas);
+  const size_t smem = (size_t)8 * (d + 1) * sizeof(float);
+  if (dtype == MMI_F32) head_bwd_kernel<float><<<grid, 256, smem, st>>>((const float*)x, rows, d, w, dlogits, gscale, (float*)dx, workspace);
+  else if (dtype == MMI_BF16) head_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, rows, d, w, dlogits, gscale, (__nv_bfloat16*)dx, workspace);
+  else { set_error("head_bwd: bad dtype %d", dtype); return MMI_EINVAL; }
+  MMI_CHECK_LAUNCH();
+  reduce_partials_kernel<<<(d + 1 + 255) / 256, 256, 0, st>>>(workspace, grid, d + 1, dw, db, d);
+  MMI_CHECK_LAUNCH();
+  return MMI_OK;
+}
+
+extern "C" int mmi_focal_loss_fwd_bwd(const float* logits, int64_t* gt, int B, int L, const float* exposure_prob, float inv_bsz,
+                                      float weight, int rewrite_gt, float* scalars, float* dlogits, mmi_stream_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMI_CHECK_ARG(logits && gt && exposure_prob && scalars && dlogits, "focal_loss: null pointer");
+  MMI_CHECK_ARG(L > 0 && L <= 64 && B > 0, "focal_loss: need 0 < L <= 64 (got %d), B > 0 (got %d)", L, B);
+  int threads = B >= 32 ? 1024 : 32 * B;
+  focal_loss_kernel<<<1, threads, 0, st>>>(logits, (int64_t*)gt, B, L, exposure_prob, inv_bsz, weight, rewrite_gt, scalars, dlogits);
+  MMI_CHECK_LAUNCH();
+  return MMI_OK;
+}
+
+extern "C" int64_t mmi_clip_adamw_workspace(int64_t n) { (void)n; return 2 * (int64_t)kRedCtas + 4; }
+
+extern "C" int mmi_clip_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, float max_norm, int step, float* norm_out, void* bf16_out,
+                              float* workspace, mmi_stream_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMI_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && norm_out && workspace, "clip_adamw: null pointer");
+  MMI_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7) == 0 && (reinterpret_cast<uintptr_t>(grads) & 15) == 0, "clip_adamw: alignment");
+  MMI_CHECK_ARG(step >= 1, "clip_adamw: step must be >= 1");
+  if (n == 0) return MMI_OK;
+  double* partial = reinterpret_cast<double*>(workspace);
+  int64_t g64 = (n / 4 + 255) / 256;
+  const int grid = (int)(g64 > kRedCtas ? kRedCtas : (g64 < 1 ? 1 : g64));
+  sumsq_kernel<<<grid, 256, 0, st>>>(grads, n, partial);
+  MMI_CHECK_LAUNCH();
+  clip_coef_kernel<<<1, 32, 0, st>>>(partial, grid, max_norm, norm_out);
+  MMI_CHECK_LAUNCH();
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  int64_t ga = (n + 255) / 256;
+  const int grid_a = (int)(ga > kNumSMs * 8 ? kNumSMs * 8 : ga);
+  adamw_kernel<<<grid_a, 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, lr * weight_decay, beta1, beta2, eps, (float)(lr / bc1),
+                                       (float)sqrt(bc2), max_norm > 0 ? norm_out : nullptr, (__nv_bfloat16*)bf16_out);
+  MMI_CHECK_LAUNCH();
+  return MMI_OK;
+}
+
+extern "C" int mmi_cast_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int transpose, mmi_stream_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMI_CHECK_ARG(src && dst, "cast_bf16: null pointer");
+  if (rows * cols == 0) return MMI_OK;
+  if (!transpose) {
+    int64_t g = (rows * cols + 255) / 256;
+    cast_bf16_kernel<<<(int)(g > kNumSMs * 8 ? kNumSMs * 8 : g), 256, 0, st>>>(src, (__nv_bfloat16*)dst, rows * cols);
+  } else {
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    cast_bf16_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(src, (__nv_bfloat16*)dst, rows, cols);
+  }
+  MMI_CHECK_LAUNCH();
+  return MMI_OK;
+}

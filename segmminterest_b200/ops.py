@@ -1,0 +1,179 @@
+"""Thin tensor -> pointer wrappers over the C ABI (include/mmi_b200.h).  torch is used for
+device memory and the current stream only; every computation below is one of our kernels."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, BF16, F32, GEMM_NN, GEMM_NT, GEMM_TN, IMPL_SIMT, IMPL_TC  # noqa: F401
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def dt(t: torch.Tensor) -> int:
+    return _DT[t.dtype]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MMIError("segmminterest_b200 kernels need CUDA tensors; there is no CPU fallback")
+
+
+class LaunchCounter:
+    """Counts kernel launches issued through this module (bench.py `gpu_launches`)."""
+    n = 0
+
+
+def gather_l1norm(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor, mask: torch.Tensor | None,
+                  normalise: bool = True):
+    _need_cuda(table, idx, out)
+    lib = _lib.load()
+    assert idx.dtype == torch.int32 and idx.is_contiguous() and table.is_contiguous() and out.is_contiguous()
+    n_tokens = idx.numel()
+    rc = lib.mmi_gather_l1norm_fwd(table.data_ptr(), dt(table), table.shape[0], table.shape[1], idx.data_ptr(), n_tokens,
+                                   out.data_ptr(), dt(out), _ptr(mask), 1 if normalise else 0, _stream())
+    _lib.check(rc, "mmi_gather_l1norm_fwd")
+    LaunchCounter.n += 1
+
+
+def gemm(layout, impl, A, lda, B, ldb, Cm, ldc, M, N, K, *, bias=None, act=ACT_NONE, preact=None, mul_gelu_grad=None,
+         add=None, add_mod=0, ld_add=0, accumulate=False, split_k=1, in_dtype=None, out_dtype=None):
+    lib = _lib.load()
+    a = _lib.GemmArgs()
+    a.layout, a.impl = layout, impl
+    a.in_dtype = dt(A) if in_dtype is None else in_dtype
+    a.out_dtype = dt(Cm) if out_dtype is None else out_dtype
+    a.M, a.N, a.K = M, N, K
+    a.A, a.lda, a.B, a.ldb, a.C, a.ldc = A.data_ptr(), lda, B.data_ptr(), ldb, Cm.data_ptr(), ldc
+    a.bias = _ptr(bias)
+    a.act = act
+    a.preact = _ptr(preact)
+    a.ld_preact = N if preact is not None else 0
+    a.mul_gelu_grad = _ptr(mul_gelu_grad)
+    a.ld_mul = N if mul_gelu_grad is not None else 0
+    a.add = _ptr(add)
+    a.ld_add = ld_add
+    a.add_mod = add_mod
+    a.add_dtype = dt(add) if add is not None else F32
+    a.accumulate = 1 if accumulate else 0
+    a.split_k = split_k
+    rc = lib.mmi_gemm(C.byref(a), _stream())
+    _lib.check(rc, "mmi_gemm")
+    LaunchCounter.n += 1
+
+
+def colsum_acc(x, M, N, ldx, out, ws):
+    rc = _lib.load().mmi_colsum_acc(x.data_ptr(), dt(x), M, N, ldx, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, "mmi_colsum_acc")
+    LaunchCounter.n += 2
+
+
+def layernorm_fwd(x, rows, d, gamma, beta, y, stats, eps=1e-12):
+    rc = _lib.load().mmi_layernorm_fwd(x.data_ptr(), dt(x), rows, d, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(),
+                                       _ptr(stats), _stream())
+    _lib.check(rc, "mmi_layernorm_fwd")
+    LaunchCounter.n += 1
+
+
+def layernorm_bwd(dy, x, rows, d, gamma, stats, add, dx, dgamma, dbeta, ws):
+    lib = _lib.load()
+    assert ws.numel() >= lib.mmi_layernorm_bwd_workspace(d)
+    rc = lib.mmi_layernorm_bwd(dy.data_ptr(), x.data_ptr(), dt(x), rows, d, gamma.data_ptr(), stats.data_ptr(), _ptr(add),
+                               dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), ws.data_ptr(), _stream())
+    _lib.check(rc, "mmi_layernorm_bwd")
+    LaunchCounter.n += 2
+
+
+class AttnSide:
+    """One query side of the 4-way attention: two key blocks sharing a softmax."""
+
+    def __init__(self, dtype, impl, B, H, dh, Lq, mask_q, out, ldo, lse, blocks):
+        a = _lib.AttnArgs()
+        a.dtype, a.impl, a.B, a.H, a.dh, a.Lq = dtype, impl, B, H, dh, Lq
+        a.mask_q = mask_q.data_ptr()
+        a.nblk = len(blocks)
+        for i, b in enumerate(blocks):
+            k = a.blk[i]
+            k.q, k.ldq = b["q"]
+            k.k, k.ldk = b["k"]
+            k.v, k.ldv = b["v"]
+            k.mask_k = b["mask_k"].data_ptr()
+            k.Lk = b["Lk"]
+        a.out, a.ldo = out.data_ptr(), ldo
+        a.lse = lse.data_ptr()
+        self.a = a
+
+    def fwd(self):
+        rc = _lib.load().mmi_attn_fwd(C.byref(self.a), _stream())
+        _lib.check(rc, "mmi_attn_fwd")
+        LaunchCounter.n += 1
+
+    def set_bwd(self, dout, lddo, delta, grads):
+        a = self.a
+        a.dout, a.lddo, a.delta = dout.data_ptr(), lddo, delta.data_ptr()
+        for i, g in enumerate(grads):
+            k = a.blk[i]
+            k.dq, k.lddq = g["dq"]
+            k.dk, k.lddk = g["dk"]
+            k.dv, k.lddv = g["dv"]
+
+    def bwd_dq(self):
+        rc = _lib.load().mmi_attn_bwd_dq(C.byref(self.a), _stream())
+        _lib.check(rc, "mmi_attn_bwd_dq")
+        LaunchCounter.n += 1
+
+    def bwd_dkv(self, which):
+        rc = _lib.load().mmi_attn_bwd_dkv(C.byref(self.a), which, _stream())
+        _lib.check(rc, "mmi_attn_bwd_dkv")
+        LaunchCounter.n += 1
+
+
+def head_fwd(x, rows, d, w, b, logits):
+    rc = _lib.load().mmi_head_fwd(x.data_ptr(), dt(x), rows, d, w.data_ptr(), b.data_ptr(), logits.data_ptr(), _stream())
+    _lib.check(rc, "mmi_head_fwd")
+    LaunchCounter.n += 1
+
+
+def head_bwd(x, rows, d, w, dlogits, gscale, dx, dw, db, ws):
+    lib = _lib.load()
+    assert ws.numel() >= lib.mmi_head_bwd_workspace(d)
+    rc = lib.mmi_head_bwd(x.data_ptr(), dt(x), rows, d, w.data_ptr(), dlogits.data_ptr(), _ptr(gscale), dx.data_ptr(),
+                          dw.data_ptr(), db.data_ptr(), ws.data_ptr(), _stream())
+    _lib.check(rc, "mmi_head_bwd")
+    LaunchCounter.n += 2
+
+
+def focal_loss(logits, gt, exposure_prob, inv_bsz, weight, rewrite_gt, scalars, dlogits):
+    B, L = logits.shape
+    assert gt.dtype == torch.int64 and gt.is_contiguous() and logits.is_contiguous() and logits.dtype == torch.float32
+    rc = _lib.load().mmi_focal_loss_fwd_bwd(logits.data_ptr(), gt.data_ptr(), B, L, exposure_prob.data_ptr(), inv_bsz, weight,
+                                            1 if rewrite_gt else 0, scalars.data_ptr(), dlogits.data_ptr(), _stream())
+    _lib.check(rc, "mmi_focal_loss_fwd_bwd")
+    LaunchCounter.n += 1
+
+
+def clip_adamw(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, wd, max_norm, step, norm_out, bf16_out, ws):
+    lib = _lib.load()
+    n = params.numel()
+    assert ws.numel() >= lib.mmi_clip_adamw_workspace(n)
+    rc = lib.mmi_clip_adamw(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n, lr, beta1, beta2,
+                            eps, wd, max_norm, step, norm_out.data_ptr(), _ptr(bf16_out), ws.data_ptr(), _stream())
+    _lib.check(rc, "mmi_clip_adamw")
+    LaunchCounter.n += 3
+
+
+def cast_bf16(src, dst, rows, cols, transpose=False):
+    rc = _lib.load().mmi_cast_bf16(src.data_ptr(), dst.data_ptr(), rows, cols, 1 if transpose else 0, _stream())
+    _lib.check(rc, "mmi_cast_bf16")
+    LaunchCounter.n += 1

@@ -1,0 +1,274 @@
+"""GPU parity of each C-ABI kernel against the CPU oracle / plain torch fp32-fp64 maths.
+Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rel(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "needs a CUDA device"
+    from segmminterest_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")
+
+
+# ----------------------------------------------------------------------------- gather
+@pytest.mark.parametrize("din", [640, 1024, 48, 768])
+def test_gather_bit_exact_and_l1(dev, din):
+    from oracle import gather_oracle
+    from segmminterest_b200 import ops
+    rng = np.random.default_rng(din)
+    table = rng.standard_normal((997, din), dtype=np.float32)
+    idx = rng.integers(-1, 997, size=(13, 57)).astype(np.int32)
+    idx[0, :] = -1  # a fully padded history
+    t = torch.from_numpy(table).to(dev)
+    i = torch.from_numpy(idx).to(dev)
+    out = torch.empty(13, 57, din, device=dev)
+    mask = torch.empty(13, 57, dtype=torch.uint8, device=dev)
+    ops.gather_l1norm(t, i, out, mask, normalise=False)
+    ref, m = gather_oracle.gather_dense(table, idx)
+    assert np.array_equal(out.cpu().numpy(), ref)          # bit-exact copy, zero pad rows
+    assert np.array_equal(mask.cpu().numpy().astype(bool), m)
+    ops.gather_l1norm(t, i, out, mask, normalise=True)
+    refn = gather_oracle.l1_normalise(ref)
+    got = out.cpu().numpy()
+    assert np.allclose(got, refn, rtol=1e-6, atol=0)
+    assert not got[~m].any()
+    # bf16 output (tensor-core path input)
+    outb = torch.empty(13, 57, din, device=dev, dtype=torch.bfloat16)
+    ops.gather_l1norm(t, i, outb, mask, normalise=True)
+    assert np.allclose(outb.float().cpu().numpy(), refn, rtol=2 ** -8, atol=0)
+
+
+def test_gather_bf16_table(dev):
+    from segmminterest_b200 import ops
+    rng = np.random.default_rng(3)
+    table = torch.from_numpy(rng.standard_normal((300, 768), dtype=np.float32)).to(dev).bfloat16()
+    idx = torch.from_numpy(rng.integers(-1, 300, size=(5, 33)).astype(np.int32)).to(dev)
+    out = torch.empty(5, 33, 768, device=dev, dtype=torch.bfloat16)
+    mask = torch.empty(5, 33, dtype=torch.uint8, device=dev)
+    ops.gather_l1norm(table, idx, out, mask, normalise=False)
+    ref = table[idx.clamp_min(0).long()] * (idx >= 0)[..., None]
+    assert torch.equal(out, ref.to(torch.bfloat16))
+    assert torch.equal(mask.bool(), idx >= 0)
+
+
+def test_gather_rejects_bad_din(dev):
+    from segmminterest_b200 import _lib, ops
+    t = torch.zeros(10, 6, device=dev)
+    with pytest.raises(_lib.MMIError):
+        ops.gather_l1norm(t, torch.zeros(4, dtype=torch.int32, device=dev), torch.empty(4, 6, device=dev), None)
+
+
+# ----------------------------------------------------------------------------- GEMM (SIMT)
+@pytest.mark.parametrize("layout", ["NT", "NN", "TN"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gemm_simt_layouts(dev, layout, dtype):
+    from segmminterest_b200 import ops
+    torch.manual_seed(0)
+    M, N, K = 333 * 4, 200, 136
+    A = torch.randn(M, K, device=dev).to(dtype)
+    Bm = torch.randn(N, K, device=dev).to(dtype)
+    ref = A.double() @ Bm.double().T
+    C = torch.empty(M, N, device=dev, dtype=dtype)
+    if layout == "NT":
+        ops.gemm(ops.GEMM_NT, ops.IMPL_SIMT, A, K, Bm, K, C, N, M, N, K)
+    elif layout == "NN":
+        Bt = Bm.T.contiguous()
+        ops.gemm(ops.GEMM_NN, ops.IMPL_SIMT, A, K, Bt, N, C, N, M, N, K)
+    else:
+        At = A.T.contiguous()
+        Bt = Bm.T.contiguous()
+        C = torch.zeros(M, N, device=dev, dtype=torch.float32)
+        ops.gemm(ops.GEMM_TN, ops.IMPL_SIMT, At, M, Bt, N, C, N, M, N, K, accumulate=True, split_k=3)
+    tol = 2e-6 if dtype == torch.float32 or layout == "TN" else 4e-3
+    assert _rel(C, ref) < tol
+
+
+def test_gemm_simt_epilogue(dev):
+    from segmminterest_b200 import ops
+    torch.manual_seed(1)
+    M, N, K, L = 96, 64, 48, 12
+    A, W = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev)
+    b, pe = torch.randn(N, device=dev), torch.randn(L, N, device=dev)
+    C = torch.empty(M, N, device=dev)
+    pre = torch.empty(M, N, device=dev)
+    ops.gemm(ops.GEMM_NT, ops.IMPL_SIMT, A, K, W, K, C, N, M, N, K, bias=b, act=ops.ACT_GELU, preact=pre, add=pe, add_mod=L, ld_add=N)
+    z = A.double() @ W.double().T + b.double()
+    ref = torch.nn.functional.gelu(z) + pe.double().repeat(M // L, 1)
+    assert _rel(pre, z) < 2e-6 and _rel(C, ref) < 2e-6
+    # dgrad through GELU: y = (A W^T) * gelu'(Z) + R
+    Z, R = torch.randn(M, N, device=dev), torch.randn(M, N, device=dev)
+    ops.gemm(ops.GEMM_NT, ops.IMPL_SIMT, A, K, W, K, C, N, M, N, K, mul_gelu_grad=Z, add=R, add_mod=M, ld_add=N)
+    zz = Z.double().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    ref = (A.double() @ W.double().T) * zz.grad + R.double()
+    assert _rel(C, ref) < 2e-6
+
+
+# ----------------------------------------------------------------------------- LayerNorm, colsum, head
+@pytest.mark.parametrize("d", [64, 512])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm_fwd_bwd(dev, d, dtype):
+    from segmminterest_b200 import _lib, ops
+    torch.manual_seed(2)
+    rows = 777
+    x = (torch.randn(rows, d, device=dev) * 2 + 0.5).to(dtype)
+    g, b = torch.randn(d, device=dev), torch.randn(d, device=dev)
+    dy, add = torch.randn(rows, d, device=dev).to(dtype), torch.randn(rows, d, device=dev).to(dtype)
+    y = torch.empty_like(x)
+    st = torch.empty(rows, 2, device=dev)
+    ops.layernorm_fwd(x, rows, d, g, b, y, st)
+    xr = x.double().requires_grad_(True)
+    gr, br = g.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (d,), gr, br, 1e-12)
+    tol = 2e-6 if dtype == torch.float32 else 6e-3
+    assert _rel(y, yr) < tol
+    yr.backward(dy.double())
+    dx = torch.empty_like(x)
+    dg, db = torch.ones(d, device=dev), torch.ones(d, device=dev)  # accumulate semantics
+    ws = torch.empty(int(_lib.load().mmi_layernorm_bwd_workspace(d)), device=dev)
+    ops.layernorm_bwd(dy, x, rows, d, g, st, add, dx, dg, db, ws)
+    assert _rel(dx, xr.grad + add.double()) < tol
+    assert _rel(dg - 1, gr.grad) < tol and _rel(db - 1, br.grad) < tol
+
+
+def test_colsum_and_head(dev):
+    from segmminterest_b200 import _lib, ops
+    torch.manual_seed(3)
+    M, N = 1234, 96
+    x = torch.randn(M, 2 * N, device=dev)
+    out = torch.ones(N, device=dev)
+    ws = torch.empty(1 << 16, device=dev)
+    ops.colsum_acc(x, M, N, 2 * N, out, ws)  # first N columns of a wider matrix
+    assert _rel(out - 1, x[:, :N].double().sum(0)) < 2e-6
+    d = 64
+    X, w, b = torch.randn(M, d, device=dev), torch.randn(1, d, device=dev), torch.randn(1, device=dev)
+    logits = torch.empty(M, device=dev)
+    ops.head_fwd(X, M, d, w, b, logits)
+    assert _rel(logits, X.double() @ w.double().T.squeeze(-1) + b.double()) < 2e-6
+    dl, gs = torch.randn(M, device=dev), torch.tensor(0.5, device=dev)
+    dx, dw, db = torch.empty_like(X), torch.zeros(1, d, device=dev), torch.zeros(1, device=dev)
+    ops.head_bwd(X, M, d, w, dl, gs, dx, dw, db, torch.empty(int(_lib.load().mmi_head_bwd_workspace(d)), device=dev))
+    assert _rel(dx, 0.5 * dl.double()[:, None] * w.double()) < 2e-6
+    assert _rel(dw, 0.5 * (dl.double()[:, None] * X.double()).sum(0, keepdim=True)) < 2e-6
+    assert _rel(db, 0.5 * dl.double().sum().reshape(1)) < 2e-6
+
+
+# ----------------------------------------------------------------------------- attention
+def _ref_attention(qa, ka, va, mka, qb, kb, vb, mkb, mq, H):
+    """oracle.mmi_oracle.cross_attention's softmax part on explicit q/k/v (fp64)."""
+    B, Lq, d = qa.shape
+    dh = d // H
+
+    def logits(q, k, mk):
+        s = torch.einsum("bqhd,bkhd->bhqk", q.view(B, Lq, H, dh), k.view(B, -1, H, dh))
+        m = (mq[:, :, None] & mk[:, None, :])[:, None].expand_as(s)
+        return torch.where(m, s, torch.full_like(s, -10000.0))
+
+    S = torch.cat([logits(qa, ka, mka), logits(qb, kb, mkb)], -1) / math.sqrt(dh)
+    V = torch.cat([va, vb], 1).view(B, -1, H, dh)
+    return torch.einsum("bhqk,bkhd->bqhd", S.softmax(-1), V).reshape(B, Lq, d)
+
+
+@pytest.mark.parametrize("dh,dtype", [(32, torch.float32), (16, torch.float32), (32, torch.bfloat16)])
+def test_attention_fwd_bwd(dev, dh, dtype):
+    from segmminterest_b200 import ops
+    torch.manual_seed(4)
+    B, H, Lq, La, Lb = 3, 2, 70, 40, 150
+    d = H * dh
+
+    def mk(L):
+        n = torch.randint(1, L + 1, (B,))
+        return (torch.arange(L)[None] < n[:, None])
+
+    mq, mka, mkb = mk(Lq), mk(La), mk(Lb)
+    mq[0, :] = True
+    t = [torch.randn(B, L, d) * 0.7 for L in (Lq, La, La, Lq, Lb, Lb)]
+    t = [x.to(dtype).to(dev) for x in t]
+    qa, ka, va, qb, kb, vb = t
+    ref_in = [x.double().cpu().requires_grad_(True) for x in t]
+    ref = _ref_attention(ref_in[0], ref_in[1], ref_in[2], mka, ref_in[3], ref_in[4], ref_in[5], mkb, mq, H)
+    out = torch.empty(B * Lq, d, device=dev, dtype=dtype)
+    lse = torch.empty(B, H, Lq, device=dev)
+    mqd, mkad, mkbd = [m.to(dev).view(torch.uint8) for m in (mq, mka, mkb)]
+    blocks = [dict(q=(qa.data_ptr(), d), k=(ka.data_ptr(), d), v=(va.data_ptr(), d), mask_k=mkad, Lk=La),
+              dict(q=(qb.data_ptr(), d), k=(kb.data_ptr(), d), v=(vb.data_ptr(), d), mask_k=mkbd, Lk=Lb)]
+    side = ops.AttnSide(ops.dt(out), ops.IMPL_SIMT, B, H, dh, Lq, mqd, out, d, lse, blocks)
+    side.fwd()
+    tol = 3e-6 if dtype == torch.float32 else 8e-3
+    assert _rel(out.view(B, Lq, d), ref) < tol
+    dO = (torch.randn(B, Lq, d) * 0.5).to(dtype).to(dev)
+    ref.backward(dO.double().cpu())
+    grads = [torch.zeros_like(x) for x in t]
+    delta = torch.empty(B, H, Lq, device=dev)
+    side.set_bwd(dO, d, delta, [dict(dq=(grads[0].data_ptr(), d), dk=(grads[1].data_ptr(), d), dv=(grads[2].data_ptr(), d)),
+                                dict(dq=(grads[3].data_ptr(), d), dk=(grads[4].data_ptr(), d), dv=(grads[5].data_ptr(), d))])
+    side.bwd_dq()
+    side.bwd_dkv(0)
+    side.bwd_dkv(1)
+    for g, r, name in zip(grads, ref_in, ["dqa", "dka", "dva", "dqb", "dkb", "dvb"]):
+        assert _rel(g, r.grad) < (1e-5 if dtype == torch.float32 else 1.5e-2), name
+
+
+# ----------------------------------------------------------------------------- loss
+def test_focal_loss_matches_reference_golden(dev):
+    from segmminterest_b200 import ops
+    z = np.load(os.path.join(GOLDEN, "loss_cases.npz"))
+    logits = torch.from_numpy(z["logits"]).to(dev)
+    gt = torch.from_numpy(z["gt_in"]).to(dev)
+    B = logits.shape[0]
+    ep = torch.from_numpy(z["exposure_prob"]).float().to(dev)
+    scal, dl = torch.zeros(8, device=dev), torch.empty_like(logits)
+    ops.focal_loss(logits, gt, ep, 1.0 / B, 1.0, True, scal, dl)
+    s = scal.cpu().numpy()
+    assert abs(s[0] - float(z["focal"])) < 2e-6 * abs(float(z["focal"]))
+    assert abs(s[1] - float(z["mse"])) < 1e-5 * abs(float(z["mse"]))
+    assert abs(s[2] - float(z["mse2"])) < 1e-5 * abs(float(z["mse2"]))
+    assert np.array_equal(gt.cpu().numpy(), z["gt_out"])   # in-place rewrite, bit-exact
+    assert _rel(dl, torch.from_numpy(z["grad_focal"])) < 5e-6
+
+
+# ----------------------------------------------------------------------------- clip + AdamW
+def test_clip_adamw_matches_torch(dev):
+    from segmminterest_b200 import _lib, ops
+    torch.manual_seed(5)
+    n = 100_003
+    p = torch.randn(n, device=dev)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, weight_decay=1e-4)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    norm = torch.zeros(2, device=dev)
+    ws = torch.empty(int(_lib.load().mmi_clip_adamw_workspace(n)), device=dev)
+    lp = torch.empty(n, device=dev, dtype=torch.bfloat16)
+    for step in (1, 2, 3):
+        g = torch.randn(n, device=dev) * (0.5 if step == 2 else 0.01)
+        ref.grad = g.clone()
+        nref = torch.nn.utils.clip_grad_norm_([ref], 10.0)
+        opt.step()
+        ops.clip_adamw(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, 1e-4, 10.0, step, norm, lp, ws)
+        assert abs(norm[0].item() - nref.item()) < 1e-5 * nref.item()
+        assert torch.allclose(p, ref.detach(), rtol=1e-6, atol=1e-7)
+        assert torch.equal(lp, p.bfloat16())
+
+
+def test_cast_bf16_transpose(dev):
+    from segmminterest_b200 import ops
+    x = torch.randn(70, 130, device=dev)
+    y = torch.empty(130, 70, device=dev, dtype=torch.bfloat16)
+    ops.cast_bf16(x, y, 70, 130, transpose=True)
+    assert torch.equal(y, x.T.contiguous().bfloat16())

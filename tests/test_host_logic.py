@@ -1,0 +1,95 @@
+"""CPU tests: the C-ABI library loads and exports every symbol the header declares, the
+drop-in modules carry the reference's state_dict schema, the engine's live-parameter set is
+the oracle's, and product code never touches oracle/."""
+import os
+import re
+from types import SimpleNamespace
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def make_args(**over):
+    a = dict(debug=0, input_type={"user": "image", "photo": "image"}, d_model=64, nhead=2, learnable_bias=0,
+             exposure_prob=[1.0] * 40, fusion_heads=2, loss_type_list=["focal"], loss_weight={"focal": 1.0},
+             mask_loss=0, num_layers_enc=4, ablation_type="ours", use_pe=1)
+    a.update(over)
+    return SimpleNamespace(**a)
+
+
+def test_library_exports_every_declared_symbol():
+    from segmminterest_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "mmi_b200.h")).read()
+    declared = set(re.findall(r"\b(mmi_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mmi_stream_t"}
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/mmi_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS)
+    assert lib.mmi_version() >= 100
+
+
+def test_state_dict_schema_matches_reference_dump():
+    from segmminterest_b200.model import build_model, reference_state_shapes
+    m = build_model(make_args(), din=48, max_usr_len=12)
+    shapes = reference_state_shapes(64, 4, 48, 12, 40)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == list(shapes.items())
+
+
+def test_state_dict_schema_matches_golden_reference_keys():
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "model_small_dh32.npz"))
+    keys = [k[3:] for k in z.files if k.startswith("sd/")]
+    from segmminterest_b200.model import reference_state_shapes
+    assert keys == list(reference_state_shapes(64, 3, 48, 12, 40).keys())
+
+
+def test_engine_live_parameters_equal_oracle_live_set():
+    from oracle import mmi_oracle
+    from segmminterest_b200.engine import Engine, EngineConfig
+    from segmminterest_b200.model import build_model
+    for n in (2, 3, 6):
+        m = build_model(make_args(num_layers_enc=n), din=48, max_usr_len=12)
+        eng = Engine(EngineConfig(d_model=64, nhead=2, num_layers=n, din_vid=48, din_usr=48, max_usr_len=12), m,
+                     torch.device("cpu"))
+        live = set(mmi_oracle.live_param_names([k for k, _ in m.named_parameters()], n))
+        assert set(eng.live_names) == live
+        offs = sorted((s.off, s.numel) for s in eng.slots)
+        for (o1, n1), (o2, _) in zip(offs, offs[1:]):
+            assert o1 + n1 <= o2
+        # the fused projection group is contiguous: 6 (or 4 / 2) d x d matrices back to back
+        off, cnt = eng.groups["L0.vid.w6"]
+        assert cnt == (6 if n > 2 else 4) * 64 * 64 and off % 64 == 0
+
+
+def test_cpu_forward_fails_loudly():
+    from segmminterest_b200 import _lib
+    from segmminterest_b200.model import build_model
+    model = build_model(make_args(num_layers_enc=2), din=16, max_usr_len=4)
+    with pytest.raises(_lib.MMIError):
+        model(usr_image=torch.zeros(1, 4, 16), usr_id=torch.zeros(1, dtype=torch.long),
+              usr_mask=torch.ones(1, 4, dtype=torch.bool), vid_image=torch.zeros(1, 40, 16),
+              vid_id=torch.zeros(1, dtype=torch.long), vid_mask=torch.ones(1, 40, dtype=torch.bool),
+              gt=torch.zeros(1, 40, dtype=torch.long), mode="train")
+
+
+def test_unsupported_configs_raise():
+    from segmminterest_b200.model import SegFormerX, build_model
+    with pytest.raises(NotImplementedError):
+        build_model(make_args(loss_type_list=["interestBPR"]), din=16, max_usr_len=4)
+    with pytest.raises(NotImplementedError):
+        SegFormerX(d_model_in=64, d_model_lvls=[64], num_head_lvls=[2], ff_dim_lvls=[64], sr_ratio_lvls=[1],
+                   use_patch_merge=[False], output_layers=[-1], model_cfg=make_args(), user_id_max=10)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "segmminterest_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "/root/reference" not in src, f

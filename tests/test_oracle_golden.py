@@ -1,0 +1,146 @@
+"""Pins the oracle restatement (oracle/) against fixtures produced by the
+unmodified reference (oracle/make_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gather_oracle, mmi_oracle
+from segmminterest_b200 import synth
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+@pytest.mark.parametrize("name", ["model_small_dh32", "model_small_dh16"])
+def test_model_small_matches_reference(name):
+    z = _load(name)
+    cfg = json.loads(str(z["cfg"]))
+    sd = {k[3:]: torch.from_numpy(z[k]).clone().requires_grad_(True) for k in z.files if k.startswith("sd/")}
+    out = mmi_oracle.forward(sd, torch.from_numpy(z["usr_image"]), torch.from_numpy(z["usr_mask"]),
+                             torch.from_numpy(z["vid_image"]), torch.from_numpy(z["vid_mask"]),
+                             torch.from_numpy(z["gt_in"]), nhead=cfg["nhead"], num_layers=cfg["num_layers_enc"])
+    assert _rel(out["logits"].detach().numpy(), z["logits"]) < 1e-5
+    assert abs(out["loss"].item() - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    assert abs(out["mse"].item() - float(z["mse"])) <= 1e-5 * abs(float(z["mse"]))
+    assert abs(out["mse2"].item() - float(z["mse2"])) <= 1e-5 * abs(float(z["mse2"]))
+    assert np.array_equal(out["gt"].numpy(), z["gt_out"])
+    out["loss"].backward()
+    dead = set(json.loads(str(z["dead_params"])))
+    live = set(mmi_oracle.live_param_names(list(sd.keys()), cfg["num_layers_enc"]))
+    named_params = {k for k in sd if ("grad/" + k) in z.files} | dead
+    assert live == {k for k in named_params if k not in dead}
+    for k in sorted(live):
+        g = sd[k].grad
+        assert g is not None, k
+        assert _rel(g.numpy(), z["grad/" + k]) < 2e-5, k
+    for k in dead:
+        assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+    inf = mmi_oracle.forward({k: v.detach() for k, v in sd.items()}, torch.from_numpy(z["usr_image"]),
+                             torch.from_numpy(z["usr_mask"]), torch.from_numpy(z["vid_image"]),
+                             torch.from_numpy(z["vid_mask"]), torch.from_numpy(z["gt_in"]), nhead=cfg["nhead"],
+                             num_layers=cfg["num_layers_enc"], mode="inference")
+    assert _rel(inf["logits"].numpy(), z["logits_inference"]) < 1e-5
+
+
+def test_model_full_matches_reference():
+    z = _load("model_full_b4")
+    cfg = json.loads(str(z["cfg"]))
+    from segmminterest_b200.model import reference_state_shapes
+    shapes = reference_state_shapes(d_model=cfg["d_model"], num_layers=cfg["num_layers_enc"], din=cfg["din"],
+                                    max_usr_len=cfg["Lt"], max_vid_len=40)
+    sd = {k: torch.from_numpy(v).requires_grad_(True) for k, v in synth.fill_state_dict(shapes, cfg["fill_seed"]).items()}
+    rng = np.random.default_rng(int(z["data_seed"]))
+    usr, usr_mask, vid, vid_mask, gt = synth.make_dense_batch(rng, cfg["B"], cfg["Lt"], cfg["din"])
+    assert np.array_equal(gt, z["gt_in"]) and np.array_equal(usr_mask, z["usr_mask"])
+    out = mmi_oracle.forward(sd, torch.from_numpy(usr), torch.from_numpy(usr_mask), torch.from_numpy(vid),
+                             torch.from_numpy(vid_mask), torch.from_numpy(gt), nhead=cfg["nhead"],
+                             num_layers=cfg["num_layers_enc"])
+    assert _rel(out["logits"].detach().numpy(), z["logits"]) < 1e-5
+    assert abs(out["loss"].item() - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    out["loss"].backward()
+    for k in z.files:
+        if k.startswith("gradnorm/"):
+            name = k[len("gradnorm/"):]
+            g = sd[name].grad.numpy()
+            gn = np.sqrt((g.astype(np.float64) ** 2).sum())
+            assert abs(gn - float(z[k])) <= 1e-4 * float(z[k]) + 1e-12, name
+            assert np.allclose(g.reshape(-1)[:16], z["gradhead/" + name], rtol=1e-3, atol=1e-7 + 1e-4 * np.abs(g).max()), name
+
+
+def test_loss_cases_match_reference():
+    z = _load("loss_cases")
+    logits = torch.from_numpy(z["logits"]).double().requires_grad_(True)
+    gt = torch.from_numpy(z["gt_in"])
+    out = mmi_oracle.compute_loss(logits, gt, list(z["exposure_prob"]), ("focal", "interestBPR"))
+    for k in ("focal", "interestBPR", "mse", "mse2", "loss"):
+        assert abs(out[k].item() - float(z[k])) <= 2e-6 * abs(float(z[k])), k
+    assert np.array_equal(out["gt"].numpy(), z["gt_out"])
+    (gf,) = torch.autograd.grad(out["focal"], logits, retain_graph=True)
+    (gb,) = torch.autograd.grad(out["interestBPR"], logits)
+    assert _rel(gf.numpy(), z["grad_focal"]) < 1e-5
+    assert _rel(gb.numpy(), z["grad_bpr"]) < 1e-5
+
+
+def test_gather_oracle_matches_reference_dataloader():
+    z = _load("gather_small")
+    table = z["table"]
+    lineid = json.loads(str(z["lineid_json"]))
+    uin = json.loads(str(z["user_input_json"]))
+    rows = json.loads(str(z["rows_json"]))
+    for b, (uid, pid, t, dur, play, lab, hi, hp, hl) in enumerate(rows):
+        cand = gather_oracle.candidate_rows(pid, dur, lineid)
+        photo, pmask = gather_oracle.gather_pad_mask(table, cand, 40)
+        assert np.array_equal(photo, z["out/photo"][b]) and np.array_equal(pmask, z["out/photo_mask"][b])
+        hist = gather_oracle.history_rows(uid, gather_oracle.parse_int_list(hi) if hl > 0 else [],
+                                          gather_oracle.parse_int_list(hp) if hl > 0 else [], lineid, uin)
+        assert len(hist) <= 100
+        user, umask = gather_oracle.gather_pad_mask(table, hist, 100)
+        assert np.array_equal(user, z["out/user"][b]) and np.array_equal(umask, z["out/user_mask"][b])
+        assert np.array_equal(gather_oracle.pad_labels(lab), z["out/label"][b])
+        assert int(play / 5000) == int(z["out/play_time"][b]) and int(dur / 5000) == int(z["out/duration"][b])
+    with pytest.raises(ValueError):
+        gather_oracle.candidate_rows(104, 9000, lineid)  # 2 segments wanted, only 1 in the map
+
+
+def test_gather_dense_and_l1():
+    rng = np.random.default_rng(0)
+    table = rng.standard_normal((50, 24), dtype=np.float32)
+    idx = rng.integers(-1, 50, size=(3, 7)).astype(np.int32)
+    out, m = gather_oracle.gather_dense(table, idx)
+    assert np.array_equal(m, idx >= 0)
+    assert np.array_equal(out[m], table[idx[m]]) and not out[~m].any()
+    x = torch.from_numpy(out)
+    ref = (x / (x.norm(p=1, dim=-1, keepdim=True) + 1e-6)).numpy()
+    assert np.allclose(gather_oracle.l1_normalise(out), ref, rtol=1e-6, atol=0)  # sum order of the norm differs by ulps
+
+
+def test_clip_adamw_oracle_matches_torch():
+    torch.manual_seed(0)
+    ps = [torch.randn(7, 5), torch.randn(11)]
+    gs = [torch.randn(7, 5) * 30, torch.randn(11) * 30]
+    ref_p = [torch.nn.Parameter(p.clone()) for p in ps]
+    opt = torch.optim.AdamW(ref_p, lr=1e-3, weight_decay=1e-4)
+    mine = [p.clone() for p in ps]
+    m = [torch.zeros_like(p) for p in ps]
+    v = [torch.zeros_like(p) for p in ps]
+    for step in (1, 2, 3):
+        for p, g in zip(ref_p, gs):
+            p.grad = g.clone() * step
+        n_ref = torch.nn.utils.clip_grad_norm_(ref_p, 10.0)
+        opt.step()
+        n = mmi_oracle.clip_and_adamw(mine, [g.clone() * step for g in gs], m, v, step)
+        assert abs(n.item() - n_ref.item()) < 1e-4 * n_ref.item()
+        for a, b in zip(mine, ref_p):
+            assert torch.allclose(a, b.detach(), rtol=1e-6, atol=1e-7)

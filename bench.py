@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- MMinterest training step throughput (BASELINE.json metric: train interactions/s).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path (default workload c2)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU PyTorch path (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...        # weak scaling: per-GPU batch fixed
+
+One JSON line on stdout (rank 0).  A "step" = gather+pad+mask+L1-normalise -> forward -> focal loss
+-> backward -> (gradient all-reduce) -> clip + AdamW over one batch of synthetic interactions.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from segmminterest_b200 import synth  # noqa: E402
+
+
+def model_args(precision):
+    return SimpleNamespace(debug=0, input_type={"user": "image", "photo": "image"}, d_model=512, nhead=16,
+                           learnable_bias=0, exposure_prob=[1.0] * 40, fusion_heads=2, loss_type_list=["focal"],
+                           loss_weight={"focal": 1.0}, mask_loss=0, num_layers_enc=6, ablation_type="ours", use_pe=1,
+                           mmi_precision=precision)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu),
+                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_builder(wl, b_cpu, seed=0, threads=None):
+    """The reference's training step on host cores, restated by oracle/mmi_oracle.py (the reference
+    is pure Python and does not travel to the GPU box; the port is pinned to it by tests/golden)."""
+    from oracle import gather_oracle, mmi_oracle
+    from segmminterest_b200.model import reference_state_shapes
+    torch.set_num_threads(threads or os.cpu_count())
+    shapes = reference_state_shapes(512, 6, wl.din, wl.lt, 40)
+    sd = {k: torch.from_numpy(v) for k, v in synth.fill_state_dict(shapes, 42).items()}
+    live = mmi_oracle.live_param_names(list(sd.keys()), 6)
+    for k in live:
+        sd[k].requires_grad_(True)
+    params = [sd[k] for k in live]
+    m = [torch.zeros_like(p) for p in params]
+    v = [torch.zeros_like(p) for p in params]
+    n_rows = 1 << 14
+    table = synth.make_table(n_rows, wl.din, seed=1234)
+    usr_idx, vid_idx, gt = synth.make_indices(b_cpu, wl.lt, wl.segs_per_video, n_rows, seed=2025 + seed)
+    state = {"step": 0}
+
+    def step():
+        u, um = gather_oracle.gather_dense(table, usr_idx)
+        c, cm = gather_oracle.gather_dense(table, vid_idx)
+        u = torch.from_numpy(gather_oracle.l1_normalise(u))
+        c = torch.from_numpy(gather_oracle.l1_normalise(c))
+        for p in params:
+            p.grad = None
+        out = mmi_oracle.forward(sd, u, torch.from_numpy(um), c, torch.from_numpy(cm), torch.from_numpy(gt), nhead=16, num_layers=6)
+        out["loss"].backward()
+        state["step"] += 1
+        with torch.no_grad():
+            mmi_oracle.clip_and_adamw(params, [p.grad for p in params], m, v, state["step"])
+        return float(out["loss"].detach())
+
+    return step
+
+
+def run_cpu_sample(wl, budget_s, steps, warmup):
+    """Sizes the sample so (steps+warmup) CPU steps fit in ~budget_s; returns (interactions/s, B, cores, ms/step)."""
+    probe = cpu_step_builder(wl, 2)
+    t0 = time.perf_counter(); probe(); t1 = time.perf_counter(); probe(); t2 = time.perf_counter()
+    per_inter = max((t2 - t1) / 2, 1e-3)
+    b = int(max(1, min(32, budget_s / ((steps + warmup) * per_inter))))
+    step = cpu_step_builder(wl, b)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter(); step(); ts.append(time.perf_counter() - t0)
+    dt = float(np.median(ts))
+    return b / dt, b, torch.get_num_threads(), dt * 1e3
+
+
+def reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    val, b, cores, ms = run_cpu_sample(wl, 150.0, steps, warmup)
+    line = {"impl": "reference", "metric": "train_interactions_per_s", "value": val, "unit": "interactions/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": wl.name, "cpu_batch": b},
+            "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": cores, "kind": "port",
+                             "sample": f"{b} interactions/step of {wl.name} (oracle port of the reference's eager PyTorch step, fp32, dropout off)"},
+            "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(synth.WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=25.0)
+    args = ap.parse_args()
+    wl = synth.WORKLOADS[args.workload]
+    if args.impl == "reference":
+        reference_arm(args, wl)
+        return
+
+    import torch.distributed as dist
+    from segmminterest_b200 import ops
+    from segmminterest_b200.model import build_model
+    from segmminterest_b200.profiler import TIMER
+    from segmminterest_b200.train import TrainStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU: there is no CPU fallback (use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    B = args.batch or wl.batch
+    if args.workload in ("c3", "c4") and not args.batch:
+        B = max(1, wl.batch // max(world, 1))
+    Lt = wl.lt
+
+    torch.manual_seed(42)
+    model = build_model(model_args(args.precision), din=wl.din, max_usr_len=Lt).to(dev)
+    model.eval()  # dropout is not applied by the engine in this round (parity mode, p=0)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    table = torch.randn(wl.n_rows, wl.din, generator=g, device=dev, dtype=torch.float32)
+    ts = TrainStep(model, table, lr=1e-3, weight_decay=1e-4, max_norm=10.0, global_batch=B * world)
+
+    n_batches = 4
+    host, devb = [], []
+    for i in range(n_batches):
+        u, v, gt = synth.make_indices(B, Lt, wl.segs_per_video, wl.n_rows, seed=2025 + 97 * rank + i)
+        hu, hv, hg = torch.from_numpy(u).pin_memory(), torch.from_numpy(v).pin_memory(), torch.from_numpy(gt).pin_memory()
+        host.append((hu, hv, hg))
+        devb.append((hu.to(dev), hv.to(dev), hg.to(dev)))
+    staging = (torch.empty_like(devb[0][0]), torch.empty_like(devb[0][1]), torch.empty_like(devb[0][2]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    for i in range(W):
+        ts.step(*devb[i % n_batches])
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.LaunchCounter.n
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        scal = ts.step(*devb[i % n_batches])
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.LaunchCounter.n - n0
+    clocks = sampler.stop() if rank == 0 else None
+    loss_last = float(scal[3].item())
+    value = K * B * world / (ms_total * 1e-3)
+
+    # ---- timed region 2: end to end from pinned host buffers, loss read back every step -----------
+    ts.step_host(*host[0], staging)
+    barrier()
+    e0.record()
+    for i in range(K):
+        ts.step_host(*host[i % n_batches], staging)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_val = K * B * world / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    # ---- per-kernel CUDA-event pass for the roofline -------------------------------------------------
+    TIMER.enabled = True
+    TIMER.reset()
+    barrier()
+    for i in range(K):
+        ts.step(*devb[i % n_batches])
+    summ = TIMER.summary()
+    TIMER.enabled = False
+    pk = peaks()
+    tot_ms = sum(v["ms"] for v in summ.values())
+    dom = max(summ, key=lambda k: summ[k]["ms"])
+    d = summ[dom]
+    if dom == "gather":
+        ach = d["work"] / (d["ms"] * 1e-3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None}
+    else:
+        ach = d["work"] / (d["ms"] * 1e-3) / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                "traffic": None}
+    roof["peak_source"] = pk["src"] + (" (sustained bf16, kernel timed inside a long step)" if roof["bound"] == "tensor" else "")
+    roof["share_of_step"] = d["ms"] / tot_ms
+    roof["avg_launch_ms"] = d["ms"] / d["launches"]
+    breakdown = {k: {"ms_per_step": round(v["ms"] / K, 3), "launches_per_step": v["launches"] // K,
+                     "achieved": (round(v["work"] / (v["ms"] * 1e-3) / (1e9 if k == "gather" else 1e12), 2) if v["work"] else None)}
+                 for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
+    # gather roofline is always reported too (HBM-bound stage the north star names)
+    if "gather" in summ:
+        gsum = summ["gather"]
+        gbs = gsum["work"] / (gsum["ms"] * 1e-3) / 1e9
+        gather_roof = {"achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}
+    else:
+        gather_roof = None
+
+    line = {"metric": "train_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": wl.name, "per_gpu_batch": B, "global_batch": B * world, "hist_len": Lt, "cand_pad": 40,
+                       "cand_valid": wl.segs_per_video, "din": wl.din, "d_model": 512, "heads": 16, "layers": 6,
+                       "table_rows": wl.n_rows, "parallelism": f"dp{world}", "optimizer": "AdamW lr1e-3 wd1e-4 clip10",
+                       "dropout": "off (parity mode)", "l2": "activations/step >> 126 MB L2 (inputs larger than L2, no flush needed)"},
+            "e2e": {"value": e2e_val, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "gather_roofline": gather_roof,
+            "kernel_breakdown": breakdown, "loss_last": loss_last, "use_tc": bool(ts.engine.use_tc)}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            val, b, cores, ms = run_cpu_sample(wl, args.cpu_budget, 2, 1)
+            line["cpu_baseline"] = {"value": val, "unit": "interactions/s", "cores": cores, "kind": "port",
+                                    "sample": f"{b} interactions/step of {wl.name}, median of 2 steps after 1 warm-up "
+                                              f"({ms:.0f} ms/step; oracle port of the reference's eager PyTorch step, fp32, dropout off)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -338,7 +338,7 @@ class Engine:
         return self.scalars
 
     # ------------------------------------------------------------------ backward
-    def backward(self, gscale=None):
+    def backward(self, gscale=None, on_ready=None):
         """Accumulates d(loss)/d(param) into the flat gradient buffer.  `gscale` is the upstream
         gradient of the loss (device scalar) -- never read on the host."""
         sv = self._saved
@@ -360,6 +360,8 @@ class Engine:
         dX = {"vid": scratch("dx", "vid"), "usr": None}
         ops.head_bwd(sv["x_out"], Ts["vid"], d, self.w("head.w"), sv["dlogits"], gscale, dX["vid"], self.g("head.w"),
                      self.g("head.b"), self.red_ws)
+        if on_ready is not None:
+            on_ready(self.groups["head.w"][0])
         for i in reversed(range(N - 1)):
             lay = sv["layers"][i]
             full, nq, Xin = lay["full"], lay["nq"], lay["x"]
@@ -408,6 +410,8 @@ class Engine:
                 self._linear_bwd(dqkv[s], Xin[s], Ts[s], nq[s] * d, d, pre + "w6", pre + "b6", out, add=dP1.get(s))
                 new_dX[s] = out
             dX = new_dX
+            if on_ready is not None:
+                on_ready(self.groups[f"L{i}.vid.w6"][0])  # first group of layer i in the flat layout
         for s in ("vid", "usr"):
             de = self._buf(f"bw.de.{s}", (Ts[s], d), T)
             if dX[s] is None:
@@ -418,4 +422,6 @@ class Engine:
                 # d pe[l,:] = sum_b dE[b,l,:]  -> column sums of dE viewed as [B, L*d]
                 ops.colsum_acc(de, B, Ls[s] * d, Ls[s] * d, self.g(f"{s}_pe")[: Ls[s] * d], self.red_ws)
             self._linear_bwd(de, sv["x_in"][s], Ts[s], d, din[s], f"{s}_proj.w", f"{s}_proj.b", None, need_dx=False)
+        if on_ready is not None:
+            on_ready(0)
         self._saved = None

@@ -7,6 +7,7 @@ import ctypes as C
 import torch
 
 from . import _lib
+from .profiler import TIMER
 from ._lib import ACT_GELU, ACT_NONE, BF16, F32, GEMM_NN, GEMM_NT, GEMM_TN, IMPL_SIMT, IMPL_TC  # noqa: F401
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
@@ -41,8 +42,9 @@ def gather_l1norm(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor, mas
     lib = _lib.load()
     assert idx.dtype == torch.int32 and idx.is_contiguous() and table.is_contiguous() and out.is_contiguous()
     n_tokens = idx.numel()
-    rc = lib.mmi_gather_l1norm_fwd(table.data_ptr(), dt(table), table.shape[0], table.shape[1], idx.data_ptr(), n_tokens,
-                                   out.data_ptr(), dt(out), _ptr(mask), 1 if normalise else 0, _stream())
+    with TIMER.region("gather", float(n_tokens) * table.shape[1] * (table.element_size() + out.element_size())):
+        rc = lib.mmi_gather_l1norm_fwd(table.data_ptr(), dt(table), table.shape[0], table.shape[1], idx.data_ptr(), n_tokens,
+                                       out.data_ptr(), dt(out), _ptr(mask), 1 if normalise else 0, _stream())
     _lib.check(rc, "mmi_gather_l1norm_fwd")
     LaunchCounter.n += 1
 
@@ -68,20 +70,23 @@ def gemm(layout, impl, A, lda, B, ldb, Cm, ldc, M, N, K, *, bias=None, act=ACT_N
     a.add_dtype = dt(add) if add is not None else F32
     a.accumulate = 1 if accumulate else 0
     a.split_k = split_k
-    rc = lib.mmi_gemm(C.byref(a), _stream())
+    with TIMER.region("gemm_tc" if impl == IMPL_TC else "gemm_simt", 2.0 * M * N * K):
+        rc = lib.mmi_gemm(C.byref(a), _stream())
     _lib.check(rc, "mmi_gemm")
     LaunchCounter.n += 1
 
 
 def colsum_acc(x, M, N, ldx, out, ws):
-    rc = _lib.load().mmi_colsum_acc(x.data_ptr(), dt(x), M, N, ldx, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+    with TIMER.region("colsum"):
+        rc = _lib.load().mmi_colsum_acc(x.data_ptr(), dt(x), M, N, ldx, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
     _lib.check(rc, "mmi_colsum_acc")
     LaunchCounter.n += 2
 
 
 def layernorm_fwd(x, rows, d, gamma, beta, y, stats, eps=1e-12):
-    rc = _lib.load().mmi_layernorm_fwd(x.data_ptr(), dt(x), rows, d, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(),
-                                       _ptr(stats), _stream())
+    with TIMER.region("ln_fwd"):
+        rc = _lib.load().mmi_layernorm_fwd(x.data_ptr(), dt(x), rows, d, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(),
+                                           _ptr(stats), _stream())
     _lib.check(rc, "mmi_layernorm_fwd")
     LaunchCounter.n += 1
 
@@ -89,8 +94,9 @@ def layernorm_fwd(x, rows, d, gamma, beta, y, stats, eps=1e-12):
 def layernorm_bwd(dy, x, rows, d, gamma, stats, add, dx, dgamma, dbeta, ws):
     lib = _lib.load()
     assert ws.numel() >= lib.mmi_layernorm_bwd_workspace(d)
-    rc = lib.mmi_layernorm_bwd(dy.data_ptr(), x.data_ptr(), dt(x), rows, d, gamma.data_ptr(), stats.data_ptr(), _ptr(add),
-                               dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), ws.data_ptr(), _stream())
+    with TIMER.region("ln_bwd"):
+        rc = lib.mmi_layernorm_bwd(dy.data_ptr(), x.data_ptr(), dt(x), rows, d, gamma.data_ptr(), stats.data_ptr(), _ptr(add),
+                                   dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), ws.data_ptr(), _stream())
     _lib.check(rc, "mmi_layernorm_bwd")
     LaunchCounter.n += 2
 
@@ -114,8 +120,15 @@ class AttnSide:
         a.lse = lse.data_ptr()
         self.a = a
 
+    def flops(self, which=None):
+        """QK^T + PV MACs*2 over all (padded) positions of the given key block(s)."""
+        a = self.a
+        lk = sum(a.blk[i].Lk for i in range(a.nblk)) if which is None else a.blk[which].Lk
+        return 4.0 * a.B * a.H * a.Lq * lk * a.dh
+
     def fwd(self):
-        rc = _lib.load().mmi_attn_fwd(C.byref(self.a), _stream())
+        with TIMER.region("attn_fwd", self.flops()):
+            rc = _lib.load().mmi_attn_fwd(C.byref(self.a), _stream())
         _lib.check(rc, "mmi_attn_fwd")
         LaunchCounter.n += 1
 
@@ -129,18 +142,21 @@ class AttnSide:
             k.dv, k.lddv = g["dv"]
 
     def bwd_dq(self):
-        rc = _lib.load().mmi_attn_bwd_dq(C.byref(self.a), _stream())
+        with TIMER.region("attn_bwd_dq", 1.5 * self.flops()):
+            rc = _lib.load().mmi_attn_bwd_dq(C.byref(self.a), _stream())
         _lib.check(rc, "mmi_attn_bwd_dq")
         LaunchCounter.n += 1
 
     def bwd_dkv(self, which):
-        rc = _lib.load().mmi_attn_bwd_dkv(C.byref(self.a), which, _stream())
+        with TIMER.region("attn_bwd_dkv", 2.0 * self.flops(which)):
+            rc = _lib.load().mmi_attn_bwd_dkv(C.byref(self.a), which, _stream())
         _lib.check(rc, "mmi_attn_bwd_dkv")
         LaunchCounter.n += 1
 
 
 def head_fwd(x, rows, d, w, b, logits):
-    rc = _lib.load().mmi_head_fwd(x.data_ptr(), dt(x), rows, d, w.data_ptr(), b.data_ptr(), logits.data_ptr(), _stream())
+    with TIMER.region("head"):
+        rc = _lib.load().mmi_head_fwd(x.data_ptr(), dt(x), rows, d, w.data_ptr(), b.data_ptr(), logits.data_ptr(), _stream())
     _lib.check(rc, "mmi_head_fwd")
     LaunchCounter.n += 1
 
@@ -148,8 +164,9 @@ def head_fwd(x, rows, d, w, b, logits):
 def head_bwd(x, rows, d, w, dlogits, gscale, dx, dw, db, ws):
     lib = _lib.load()
     assert ws.numel() >= lib.mmi_head_bwd_workspace(d)
-    rc = lib.mmi_head_bwd(x.data_ptr(), dt(x), rows, d, w.data_ptr(), dlogits.data_ptr(), _ptr(gscale), dx.data_ptr(),
-                          dw.data_ptr(), db.data_ptr(), ws.data_ptr(), _stream())
+    with TIMER.region("head"):
+        rc = lib.mmi_head_bwd(x.data_ptr(), dt(x), rows, d, w.data_ptr(), dlogits.data_ptr(), _ptr(gscale), dx.data_ptr(),
+                              dw.data_ptr(), db.data_ptr(), ws.data_ptr(), _stream())
     _lib.check(rc, "mmi_head_bwd")
     LaunchCounter.n += 2
 
@@ -157,8 +174,9 @@ def head_bwd(x, rows, d, w, dlogits, gscale, dx, dw, db, ws):
 def focal_loss(logits, gt, exposure_prob, inv_bsz, weight, rewrite_gt, scalars, dlogits):
     B, L = logits.shape
     assert gt.dtype == torch.int64 and gt.is_contiguous() and logits.is_contiguous() and logits.dtype == torch.float32
-    rc = _lib.load().mmi_focal_loss_fwd_bwd(logits.data_ptr(), gt.data_ptr(), B, L, exposure_prob.data_ptr(), inv_bsz, weight,
-                                            1 if rewrite_gt else 0, scalars.data_ptr(), dlogits.data_ptr(), _stream())
+    with TIMER.region("loss"):
+        rc = _lib.load().mmi_focal_loss_fwd_bwd(logits.data_ptr(), gt.data_ptr(), B, L, exposure_prob.data_ptr(), inv_bsz, weight,
+                                                1 if rewrite_gt else 0, scalars.data_ptr(), dlogits.data_ptr(), _stream())
     _lib.check(rc, "mmi_focal_loss_fwd_bwd")
     LaunchCounter.n += 1
 
@@ -167,13 +185,15 @@ def clip_adamw(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, wd, ma
     lib = _lib.load()
     n = params.numel()
     assert ws.numel() >= lib.mmi_clip_adamw_workspace(n)
-    rc = lib.mmi_clip_adamw(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n, lr, beta1, beta2,
-                            eps, wd, max_norm, step, norm_out.data_ptr(), _ptr(bf16_out), ws.data_ptr(), _stream())
+    with TIMER.region("clip_adamw"):
+        rc = lib.mmi_clip_adamw(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), n, lr, beta1, beta2,
+                                eps, wd, max_norm, step, norm_out.data_ptr(), _ptr(bf16_out), ws.data_ptr(), _stream())
     _lib.check(rc, "mmi_clip_adamw")
     LaunchCounter.n += 3
 
 
 def cast_bf16(src, dst, rows, cols, transpose=False):
-    rc = _lib.load().mmi_cast_bf16(src.data_ptr(), dst.data_ptr(), rows, cols, 1 if transpose else 0, _stream())
+    with TIMER.region("cast"):
+        rc = _lib.load().mmi_cast_bf16(src.data_ptr(), dst.data_ptr(), rows, cols, 1 if transpose else 0, _stream())
     _lib.check(rc, "mmi_cast_bf16")
     LaunchCounter.n += 1

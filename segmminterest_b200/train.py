@@ -1,0 +1,84 @@
+"""The fused training step behind the reference driver's loop body
+(main_for_seq_leave_earlystop_SegMM.py:270-300): device-side gather + pad + mask +
+L1-normalise -> forward -> focal loss -> hand-written backward -> bucketed gradient
+all-reduce -> global-norm clip + AdamW, all on one stream with no host synchronisation."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, ops
+from .dp import GradBuckets
+
+PHOTO_MAX = 40
+
+
+class DeviceGather:
+    """a-1..a-3: the embedding table lives in HBM; a batch is described by int32 row ids
+    (-1 = pad) instead of the reference's per-segment string-keyed dict lookups
+    (utils/dataloader_SegMM.py:301-350)."""
+
+    def __init__(self, table: torch.Tensor, out_dtype=torch.float32):
+        if not table.is_cuda:
+            raise _lib.MMIError("DeviceGather needs the table in device memory; there is no CPU fallback")
+        self.table = table.contiguous()
+        self.out_dtype = out_dtype
+        self._buf = {}
+
+    def __call__(self, idx: torch.Tensor, tag: str, normalise: bool = True):
+        B, L = idx.shape
+        key = (tag, B, L)
+        if key not in self._buf:
+            self._buf[key] = (torch.empty(B, L, self.table.shape[1], device=idx.device, dtype=self.out_dtype),
+                              torch.empty(B, L, device=idx.device, dtype=torch.uint8))
+        out, mask = self._buf[key]
+        ops.gather_l1norm(self.table, idx, out, mask, normalise)
+        return out, mask.view(torch.bool)
+
+
+class TrainStep:
+    def __init__(self, model, table: torch.Tensor, lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
+                 max_norm=10.0, process_group=None, global_batch=None, bucket_bytes=25 << 20):
+        self.model = model
+        self.engine = model.engine()
+        eng = self.engine
+        self.gather = DeviceGather(table, eng.act_dtype)
+        self.lr, self.wd, self.betas, self.eps, self.max_norm = lr, weight_decay, betas, eps, max_norm
+        self.exp_avg = torch.zeros_like(eng.flat)
+        self.exp_avg_sq = torch.zeros_like(eng.flat)
+        self.norm = torch.zeros(2, device=eng.device)
+        self.ws = torch.empty(int(_lib.load().mmi_clip_adamw_workspace(eng.n_flat)), device=eng.device)
+        self.step_no = 0
+        self.buckets = GradBuckets(eng.flat_grad, process_group, bucket_bytes)
+        self.global_batch = global_batch
+        self.weight = float(model.model_cfg.loss_weight["focal"])
+
+    def step(self, usr_idx: torch.Tensor, vid_idx: torch.Tensor, gt: torch.Tensor):
+        """One training step on device-resident int32 indices [B,Lt], [B,40] and int64 labels
+        [B,40] (rewritten in place like the reference).  Returns the device scalars
+        [focal, mse, mse2, loss]; nothing is synchronised."""
+        eng = self.engine
+        B = usr_idx.shape[0]
+        usr, um = self.gather(usr_idx, "usr")
+        vid, vm = self.gather(vid_idx, "vid")
+        logits = eng.forward(usr, um, vid, vm)
+        gb = self.global_batch or B * self.buckets.world
+        scal = eng.loss(logits, gt, self.model.exposure_prob, inv_bsz=1.0 / gb, weight=self.weight)
+        eng.bind_grads()           # Parameters' .grad alias the flat gradient buffer
+        eng.flat_grad.zero_()
+        self.buckets.begin()
+        eng.backward(None, on_ready=self.buckets.ready)
+        self.buckets.finish()
+        self.step_no += 1
+        ops.clip_adamw(eng.flat, eng.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
+                       self.wd, self.max_norm if self.max_norm else 0.0, self.step_no, self.norm, None, self.ws)
+        return scal
+
+    def step_host(self, usr_idx_h, vid_idx_h, gt_h, dev_bufs):
+        """End-to-end variant: pinned host index/label buffers -> H2D inside the call, loss read
+        back to the host (one D2H + sync), as the reference loop's `loss.item()` does."""
+        u, v, g = dev_bufs
+        u.copy_(usr_idx_h, non_blocking=True)
+        v.copy_(vid_idx_h, non_blocking=True)
+        g.copy_(gt_h, non_blocking=True)
+        scal = self.step(u, v, g)
+        return float(scal[3].item())

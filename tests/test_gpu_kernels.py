@@ -222,7 +222,7 @@ def test_attention_fwd_bwd(dev, dh, dtype):
     side.bwd_dkv(0)
     side.bwd_dkv(1)
     for g, r, name in zip(grads, ref_in, ["dqa", "dka", "dva", "dqb", "dkb", "dvb"]):
-        assert _rel(g, r.grad) < (1e-5 if dtype == torch.float32 else 1.5e-2), name
+        assert _rel(g, r.grad) < (5e-5 if dtype == torch.float32 else 1.5e-2), name
 
 
 # ----------------------------------------------------------------------------- loss

@@ -72,7 +72,8 @@ int mmi_gather_l1norm_fwd(const void* table, int table_dtype, int64_t n_rows, in
  *   C    = y                (accumulate == 0)
  *   C   += y                (accumulate == 1, C must be fp32; used for weight grads)
  * in_dtype applies to A, B, add, preact, mul_gelu_grad; out_dtype to C.
- * split_k > 1 is only legal with accumulate == 1 (atomic fp32 adds).                  */
+ * split_k > 1 is only legal with accumulate == 1 (atomic fp32 adds); split_k == 0 lets
+ * the tensor-core path pick a split that fills the 148 SMs.                          */
 typedef struct {
   int layout;       /* MMI_GEMM_* */
   int impl;         /* MMI_IMPL_* */

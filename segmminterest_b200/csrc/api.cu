@@ -35,7 +35,7 @@ extern "C" int mmi_gemm(const mmi_gemm_args* a, mmi_stream_t stream) {
   MMI_CHECK_ARG(a->layout >= MMI_GEMM_NT && a->layout <= MMI_GEMM_TN, "gemm: bad layout %d", a->layout);
   MMI_CHECK_ARG(a->N % 4 == 0 && a->ldc % 4 == 0, "gemm: N and ldc must be multiples of 4");
   MMI_CHECK_ARG(!(a->accumulate && a->out_dtype != MMI_F32), "gemm: accumulate needs an fp32 C");
-  MMI_CHECK_ARG(a->split_k >= 1 && (a->split_k == 1 || a->accumulate), "gemm: split_k > 1 needs accumulate=1");
+  MMI_CHECK_ARG(a->split_k >= 0 && (a->split_k == 1 || a->accumulate), "gemm: split_k != 1 needs accumulate=1 (0 = auto)");
   MMI_CHECK_ARG(!(a->add && a->add_mod <= 0), "gemm: add needs add_mod > 0");
   if (a->M == 0) return MMI_OK;
   GemmParams p;
@@ -46,6 +46,7 @@ extern "C" int mmi_gemm(const mmi_gemm_args* a, mmi_stream_t stream) {
   p.mul_gelu_grad = a->mul_gelu_grad; p.ld_mul = a->ld_mul;
   p.add = a->add; p.ld_add = a->ld_add; p.add_mod = a->add_mod; p.add_dtype = a->add_dtype;
   p.accumulate = a->accumulate; p.split_k = a->split_k;
+  if (a->impl != MMI_IMPL_TC && p.split_k == 0) p.split_k = 1;
   if (a->impl == MMI_IMPL_TC) {
     if (!tc_available()) { set_error("gemm: tcgen05 path requested but not available on this device/build"); return MMI_ENOSUP; }
     return gemm_tc(p, st);

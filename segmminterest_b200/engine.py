@@ -206,9 +206,15 @@ class Engine:
         return t
 
     def _impl(self, M, N, K, layout):
+        """tcgen05 path whenever TMA's 16-byte stride rule holds (all model dims that are multiples
+        of 8); otherwise the SIMT kernel (still CUDA, still ours)."""
         if not self.use_tc:
             return IMPL_SIMT
-        return IMPL_TC
+        if layout == GEMM_NT:
+            ok = K % 8 == 0
+        else:  # TN: A [K, M], B [K, N]
+            ok = M % 8 == 0 and N % 8 == 0
+        return IMPL_TC if ok else IMPL_SIMT
 
     # ------------------------------------------------------------------ building blocks
     def _linear(self, x, M, K, wkey, bkey, N, out, *, act=ACT_NONE, preact=None, add=None, add_mod=0, ld_add=0,
@@ -223,14 +229,15 @@ class Engine:
         """dW += dy^T x ; db += colsum(dy) ; dx = dy W (* gelu'(mul)) (+ add)."""
         lp = self.cfg.precision == "bf16"
         ops.colsum_acc(dy, M, N, N, self.g(bkey), self.red_ws)
-        split = 1
-        if not self.use_tc:
+        impl_w = self._impl(N, K, M, GEMM_TN)
+        if impl_w == IMPL_TC:
+            split = 0  # auto: fill the SMs
+        else:
             tiles = ((N + 127) // 128) * ((K + 127) // 128)
             split = max(1, min(32, (2 * 148) // tiles, (M + 4095) // 4096))
-        ops.gemm(GEMM_TN, self._impl(N, K, M, GEMM_TN), dy, N, x, K, self.g(wkey), K, N, K, M, accumulate=True,
-                 split_k=split, out_dtype=_lib.F32)
+        ops.gemm(GEMM_TN, impl_w, dy, N, x, K, self.g(wkey), K, N, K, M, accumulate=True, split_k=split, out_dtype=_lib.F32)
         if need_dx:
-            if self.use_tc:
+            if self._impl(M, K, N, GEMM_NT) == IMPL_TC:
                 ops.gemm(GEMM_NT, IMPL_TC, dy, N, self.wT(wkey), N, dx, K, M, K, N, mul_gelu_grad=mul_gelu_grad, add=add,
                          add_mod=M if add is not None else 0, ld_add=K)
             else:

@@ -10,7 +10,7 @@ constexpr int kMaxVecPerLane = 8;   // d <= 1024
 constexpr int kRedCtas = kNumSMs * 4;
 
 // ------------------------------------------------------------------ LayerNorm forward
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, int64_t rows, int d,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float eps, T* __restrict__ y, float* __restrict__ stats) {
@@ -19,10 +19,10 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
   const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
     const T* xr = x + row * (int64_t)d;
-    float4 v[kMaxVecPerLane];
+    float4 v[NV];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVecPerLane; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       v[i] = (c < nvec) ? load4(xr + c * 4) : make_float4(0, 0, 0, 0);
       s += v[i].x + v[i].y + v[i].z + v[i].w;
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
     const float mean = warp_sum(s) / (float)d;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVecPerLane; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
         const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, e = v[i].w - mean;
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
     }
     T* yr = y + row * (int64_t)d;
 #pragma unroll
-    for (int i = 0; i < kMaxVecPerLane; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
         const float4 g = *reinterpret_cast<const float4*>(gamma + c * 4);
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
 
 // ------------------------------------------------------------------ LayerNorm backward
 // partial layout: [gridDim.x][2][d]  (dgamma then dbeta)
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t rows, int d,
                                                             const float* __restrict__ gamma, const float* __restrict__ stats,
                                                             const T* __restrict__ add, T* __restrict__ dx,
@@ -72,17 +72,17 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = d >> 2;
   const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
-  float4 dg[kMaxVecPerLane], db[kMaxVecPerLane];
+  float4 dg[NV], db[NV];
 #pragma unroll
-  for (int i = 0; i < kMaxVecPerLane; ++i) dg[i] = db[i] = make_float4(0, 0, 0, 0);
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0, 0, 0, 0);
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += wstride) {
     const float mean = stats[2 * row], rstd = stats[2 * row + 1];
     const T* xr = x + row * (int64_t)d;
     const T* dyr = dy + row * (int64_t)d;
-    float4 xh[kMaxVecPerLane], g[kMaxVecPerLane];
+    float4 xh[NV], g[NV];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kMaxVecPerLane; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
         const float4 xv = load4(xr + c * 4);
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
     c2 = warp_sum(c2) / (float)d;
     T* dxr = dx + row * (int64_t)d;
 #pragma unroll
-    for (int i = 0; i < kMaxVecPerLane; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
         float4 o;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
   // CTA reduction of the per-warp column sums (fixed order)
   float* mine = sm + (size_t)warp * 2 * d;
 #pragma unroll
-  for (int i = 0; i < kMaxVecPerLane; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
     if (c < nvec) {
       *reinterpret_cast<float4*>(mine + c * 4) = dg[i];
@@ -152,18 +152,38 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nb
 }
 
 // ------------------------------------------------------------------ column sums (bias grads)
+// block (32, 8): a warp covers 128 columns (4 per lane), 8 warps stride over the rows of this
+// CTA's row chunk with 4 independent loads in flight each; partial[gridDim.y][N].
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int64_t M, int N, int64_t ldx, float* __restrict__ partial) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (c >= N) return;
+  __shared__ float4 red[8][32];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const bool cin = c < N;
   const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
   float4 s = make_float4(0, 0, 0, 0);
-  for (int64_t r = r0; r < r1; ++r) {
-    const float4 v = load4(x + r * ldx + c);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  if (cin) {
+    int64_t r = r0 + threadIdx.y;
+    for (; r + 24 < r1; r += 32) {
+      const float4 a = load4(x + r * ldx + c), b = load4(x + (r + 8) * ldx + c);
+      const float4 cc = load4(x + (r + 16) * ldx + c), d = load4(x + (r + 24) * ldx + c);
+      s.x += (a.x + b.x) + (cc.x + d.x); s.y += (a.y + b.y) + (cc.y + d.y);
+      s.z += (a.z + b.z) + (cc.z + d.z); s.w += (a.w + b.w) + (cc.w + d.w);
+    }
+    for (; r < r1; r += 8) {
+      const float4 a = load4(x + r * ldx + c);
+      s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+    }
   }
-  *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * N + c) = s;
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && cin) {
+    for (int w = 1; w < 8; ++w) {
+      const float4 o = red[w][threadIdx.x];
+      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
+    *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * N + c) = s;
+  }
 }
 
 // ------------------------------------------------------------------ head Linear(d -> 1)
@@ -187,7 +207,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ x, 
 }
 
 // partial layout [gridDim.x][d + 1]: dw then db
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(256) head_bwd_kernel(const T* __restrict__ x, int64_t rows, int d, const float* __restrict__ w,
                                                        const float* __restrict__ dlogits, const float* __restrict__ gscale,
                                                        T* __restrict__ dx, float* __restrict__ partial) {
@@ -196,15 +216,15 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const T* __restrict__ x, 
   const int nvec = d >> 2;
   const float gs = gscale ? gscale[0] : 1.0f;
   const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
-  float4 dw[kMaxVecPerLane];
+  float4 dw[NV];
 #pragma unroll
-  for (int i = 0; i < kMaxVecPerLane; ++i) dw[i] = make_float4(0, 0, 0, 0);
+  for (int i = 0; i < NV; ++i) dw[i] = make_float4(0, 0, 0, 0);
   float dbias = 0.f;
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; row < rows; row += wstride) {
     const float g = dlogits[row] * gs;
     dbias += g;
 #pragma unroll
-    for (int i = 0; i < kMaxVecPerLane; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
         const float4 xv = load4(x + row * (int64_t)d + c * 4);
@@ -216,7 +236,7 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const T* __restrict__ x, 
   }
   float* mine = sm + (size_t)warp * (d + 1);
 #pragma unroll
-  for (int i = 0; i < kMaxVecPerLane; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane + 32 * i;
     if (c < nvec) {
       mine[c * 4 + 0] = dw[i].x; mine[c * 4 + 1] = dw[i].y; mine[c * 4 + 2] = dw[i].z; mine[c * 4 + 3] = dw[i].w;
@@ -428,9 +448,14 @@ extern "C" int mmi_layernorm_fwd(const void* x, int dtype, int64_t rows, int d, 
   MMI_CHECK_ARG(d % 4 == 0 && d <= 128 * kMaxVecPerLane && d > 0, "layernorm: d=%d must be a multiple of 4 and <= %d", d, 128 * kMaxVecPerLane);
   if (rows == 0) return MMI_OK;
   const int grid = grid_for_rows(rows, 8, kNumSMs * 8);
-  if (dtype == MMI_F32) layernorm_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, rows, d, gamma, beta, eps, (float*)y, stats);
-  else if (dtype == MMI_BF16) layernorm_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, rows, d, gamma, beta, eps, (__nv_bfloat16*)y, stats);
+  const int nv = d <= 128 ? 1 : (d <= 256 ? 2 : (d <= 512 ? 4 : 8));
+#define MMI_LN_FWD(T_, NV_) layernorm_fwd_kernel<T_, NV_><<<grid, 256, 0, st>>>((const T_*)x, rows, d, gamma, beta, eps, (T_*)y, stats)
+#define MMI_LN_FWD_NV(T_) do { if (nv == 1) MMI_LN_FWD(T_, 1); else if (nv == 2) MMI_LN_FWD(T_, 2); else if (nv == 4) MMI_LN_FWD(T_, 4); else MMI_LN_FWD(T_, 8); } while (0)
+  if (dtype == MMI_F32) MMI_LN_FWD_NV(float);
+  else if (dtype == MMI_BF16) MMI_LN_FWD_NV(__nv_bfloat16);
   else { set_error("layernorm_fwd: bad dtype %d", dtype); return MMI_EINVAL; }
+#undef MMI_LN_FWD_NV
+#undef MMI_LN_FWD
   MMI_CHECK_LAUNCH();
   return MMI_OK;
 }
@@ -445,14 +470,18 @@ extern "C" int mmi_layernorm_bwd(const void* dy, const void* x, int dtype, int64
   if (rows == 0) return MMI_OK;
   const int grid = grid_for_rows(rows, 8, kRedCtas);
   const size_t smem = (size_t)8 * 2 * d * sizeof(float);
-  if (dtype == MMI_F32) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    layernorm_bwd_kernel<float><<<grid, 256, smem, st>>>((const float*)dy, (const float*)x, rows, d, gamma, stats, (const float*)add, (float*)dx, workspace);
-  } else if (dtype == MMI_BF16) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    layernorm_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, rows, d, gamma, stats,
-                                                                  (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, workspace);
-  } else { set_error("layernorm_bwd: bad dtype %d", dtype); return MMI_EINVAL; }
+  const int nv = d <= 128 ? 1 : (d <= 256 ? 2 : (d <= 512 ? 4 : 8));
+#define MMI_LN_BWD(T_, NV_)                                                                                                   \
+  do {                                                                                                                        \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<T_, NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    layernorm_bwd_kernel<T_, NV_><<<grid, 256, smem, st>>>((const T_*)dy, (const T_*)x, rows, d, gamma, stats, (const T_*)add, (T_*)dx, workspace); \
+  } while (0)
+#define MMI_LN_BWD_NV(T_) do { if (nv == 1) MMI_LN_BWD(T_, 1); else if (nv == 2) MMI_LN_BWD(T_, 2); else if (nv == 4) MMI_LN_BWD(T_, 4); else MMI_LN_BWD(T_, 8); } while (0)
+  if (dtype == MMI_F32) MMI_LN_BWD_NV(float);
+  else if (dtype == MMI_BF16) MMI_LN_BWD_NV(__nv_bfloat16);
+  else { set_error("layernorm_bwd: bad dtype %d", dtype); return MMI_EINVAL; }
+#undef MMI_LN_BWD_NV
+#undef MMI_LN_BWD
   MMI_CHECK_LAUNCH();
   if (dgamma || dbeta) {
     reduce_partials_kernel<<<(2 * d + 255) / 256, 256, 0, st>>>(workspace, grid, 2 * d, dgamma, dbeta, d);
@@ -467,14 +496,15 @@ extern "C" int mmi_colsum_acc(const void* x, int dtype, int64_t M, int N, int64_
   MMI_CHECK_ARG(x && out && workspace, "colsum: null pointer");
   MMI_CHECK_ARG(N % 4 == 0 && N > 0, "colsum: N=%d must be a multiple of 4", N);
   if (M == 0) return MMI_OK;
-  const int gx = (N / 4 + 255) / 256;
-  int64_t gy = (2 * kNumSMs + gx - 1) / gx;
-  if (gy > M) gy = M;
+  const int gx = (N / 4 + 31) / 32;
+  int64_t gy = (4 * kNumSMs + gx - 1) / gx;
+  if (gy > (M + 63) / 64) gy = (M + 63) / 64;
   if (gy * N > workspace_floats) gy = workspace_floats / N;
   MMI_CHECK_ARG(gy >= 1, "colsum: workspace too small (%lld floats for N=%d)", (long long)workspace_floats, N);
   dim3 grid(gx, (unsigned)gy);
-  if (dtype == MMI_F32) colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, M, N, ldx, workspace);
-  else if (dtype == MMI_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, M, N, ldx, workspace);
+  dim3 block(32, 8);
+  if (dtype == MMI_F32) colsum_kernel<float><<<grid, block, 0, st>>>((const float*)x, M, N, ldx, workspace);
+  else if (dtype == MMI_BF16) colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, M, N, ldx, workspace);
   else { set_error("colsum: bad dtype %d", dtype); return MMI_EINVAL; }
   MMI_CHECK_LAUNCH();
   reduce_partials_kernel<<<(N + 255) / 256, 256, 0, st>>>(workspace, (int)gy, N, out, nullptr, 0);
@@ -506,9 +536,13 @@ extern "C" int mmi_head_bwd(const void* x, int dtype, int64_t rows, int d, const
   if (rows == 0) return MMI_OK;
   const int grid = grid_for_rows(rows, 8, kRedCtas);
   const size_t smem = (size_t)8 * (d + 1) * sizeof(float);
-  if (dtype == MMI_F32) head_bwd_kernel<float><<<grid, 256, smem, st>>>((const float*)x, rows, d, w, dlogits, gscale, (float*)dx, workspace);
-  else if (dtype == MMI_BF16) head_bwd_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, rows, d, w, dlogits, gscale, (__nv_bfloat16*)dx, workspace);
-  else { set_error("head_bwd: bad dtype %d", dtype); return MMI_EINVAL; }
+  if (dtype == MMI_F32) {
+    if (d <= 512) head_bwd_kernel<float, 4><<<grid, 256, smem, st>>>((const float*)x, rows, d, w, dlogits, gscale, (float*)dx, workspace);
+    else head_bwd_kernel<float, 8><<<grid, 256, smem, st>>>((const float*)x, rows, d, w, dlogits, gscale, (float*)dx, workspace);
+  } else if (dtype == MMI_BF16) {
+    if (d <= 512) head_bwd_kernel<__nv_bfloat16, 4><<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, rows, d, w, dlogits, gscale, (__nv_bfloat16*)dx, workspace);
+    else head_bwd_kernel<__nv_bfloat16, 8><<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, rows, d, w, dlogits, gscale, (__nv_bfloat16*)dx, workspace);
+  } else { set_error("head_bwd: bad dtype %d", dtype); return MMI_EINVAL; }
   MMI_CHECK_LAUNCH();
   reduce_partials_kernel<<<(d + 1 + 255) / 256, 256, 0, st>>>(workspace, grid, d + 1, dw, db, d);
   MMI_CHECK_LAUNCH();

@@ -38,7 +38,7 @@ __device__ __forceinline__ void gemm_epilogue4(const GemmParams& p, int64_t m, i
     v[0] *= gelu_grad_f(z.x); v[1] *= gelu_grad_f(z.y); v[2] *= gelu_grad_f(z.z); v[3] *= gelu_grad_f(z.w);
   }
   if (lead && p.add != nullptr) {
-    const int64_t r = m % p.add_mod;
+    const int64_t r = (m < p.add_mod) ? m : m % p.add_mod;
     float4 a;
     if (p.add_dtype == MMI_F32) a = load4(reinterpret_cast<const float*>(p.add) + r * p.ld_add + n);
     else a = load4(reinterpret_cast<const __nv_bfloat16*>(p.add) + r * p.ld_add + n);
@@ -59,6 +59,67 @@ __device__ __forceinline__ void gemm_epilogue4(const GemmParams& p, int64_t m, i
     }
   } else {
     store4(c, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+// erf GELU for the bf16 tensor-core epilogue: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7,
+// far below bf16 resolution) so that the epilogue stays under the MMA time of a K=512 tile:
+// one MUFU.EX2 + one MUFU.RCP + ~12 FMA-pipe ops per element instead of erff's ~30.
+// exp(-u^2) with u = x/sqrt(2) equals exp(-x^2/2), which is also the Gaussian pdf factor of gelu'.
+__device__ __forceinline__ void gelu_parts(float x, float& cdf, float& e) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  e = __expf(-0.5f * x * x);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * e;            // erf(|x|/sqrt2)
+  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+}
+__device__ __forceinline__ float gelu_fast(float x) { float cdf, e; gelu_parts(x, cdf, e); return x * cdf; }
+__device__ __forceinline__ float gelu_grad_fast(float x) { float cdf, e; gelu_parts(x, cdf, e); return fmaf(x * 0.39894228040143267794f, e, cdf); }
+
+// 2 consecutive elements <-> float2 (coalesced row-wise epilogue of the tcgen05 kernel)
+__device__ __forceinline__ float2 load2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 load2(const __nv_bfloat16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+__device__ __forceinline__ void store2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+__device__ __forceinline__ void store2(__nv_bfloat16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
+
+// Columns n, n+1 of row m; consecutive lanes own consecutive column pairs of the SAME row, so
+// every global access below is a fully coalesced 128 B (bf16) / 256 B (fp32) row segment.
+// b0/b1: bias of the two columns (already zero when there is no bias or this is not the lead split).
+template <typename TIN, typename TOUT>
+__device__ __forceinline__ void gemm_epilogue2(const GemmParams& p, int64_t m, int64_t n, float v0, float v1, float b0, float b1,
+                                               bool lead) {
+  v0 += b0; v1 += b1;
+  if (p.preact != nullptr) store2(reinterpret_cast<TIN*>(p.preact) + m * p.ld_preact + n, make_float2(v0, v1));
+  if (p.act == MMI_ACT_GELU) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); }
+  if (p.mul_gelu_grad != nullptr) {
+    const float2 z = load2(reinterpret_cast<const TIN*>(p.mul_gelu_grad) + m * p.ld_mul + n);
+    v0 *= gelu_grad_fast(z.x); v1 *= gelu_grad_fast(z.y);
+  }
+  if (lead && p.add != nullptr) {
+    const int64_t r = (m < p.add_mod) ? m : m % p.add_mod;  // residual: add_mod == M (no division)
+    float2 a;
+    if (p.add_dtype == MMI_F32) a = load2(reinterpret_cast<const float*>(p.add) + r * p.ld_add + n);
+    else a = load2(reinterpret_cast<const __nv_bfloat16*>(p.add) + r * p.ld_add + n);
+    v0 += a.x; v1 += a.y;
+  }
+  TOUT* c = reinterpret_cast<TOUT*>(p.C) + m * p.ldc + n;
+  if (p.accumulate) {
+    if constexpr (sizeof(TOUT) == 4) {
+      float* cf = reinterpret_cast<float*>(c);
+      if (p.split_k > 1) {
+        atomicAdd(reinterpret_cast<float2*>(cf), make_float2(v0, v1));  // red.global.add.v2.f32 (sm_90+)
+      } else {
+        float2 o = *reinterpret_cast<float2*>(cf);
+        o.x += v0; o.y += v1;
+        *reinterpret_cast<float2*>(cf) = o;
+      }
+    }
+  } else {
+    store2(c, make_float2(v0, v1));
   }
 }
 

@@ -15,13 +15,9 @@
 // Layouts: NT uses K-major operands (A [M,K], B [N,K]); TN (weight gradient, dW = dY^T X)
 // uses MN-major operands straight from the row-major activations -- no transposes in HBM.
 // NN is not needed: the engine keeps a transposed bf16 shadow of each weight for dgrad.
-#include <cuda.h>
-
-#include <mutex>
-#include <unordered_map>
-
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
+#include "tc_common.cuh"
 
 namespace mmi {
 
@@ -29,88 +25,12 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle row
-constexpr int STAGES = 4;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192; // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
-constexpr uint32_t SPIN_LIMIT = 1u << 24;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (done) break;
-    if (++spins > SPIN_LIMIT) __trap();  // a protocol bug must fail the launch, not hang the GPU
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
-//   K-major : rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused
-//   MN-major: 64-element (128 B) MN chunks `lbo_bytes` apart, 8-k-row groups 1024 B apart
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);          // start address  [0,14)
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;     // leading byte offset [16,30)
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;     // stride byte offset  [32,46)
-  d |= static_cast<uint64_t>(1) << 46;                             // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;                             // SWIZZLE_128B
-  return d;
-}
-
-// Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
+constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue
+constexpr int STG_COLS = 64;     // epilogue staging: 32 rows x 64 fp32 per warp (8 KB), XOR-swizzled
+constexpr int STG_BYTES = 32 * STG_COLS * 4;
+__host__ __device__ constexpr int stages_for(int bn) { return bn == 256 ? 3 : 4; }
 struct TileInfo {
   int m_blk, n_blk, kb0, kb1;
   bool lead;
@@ -134,6 +54,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p,
                int m_tiles, int n_tiles, int num_kb, int split) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int STAGES = stages_for(BN);
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -144,6 +65,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES + 256;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = m_tiles * n_tiles * split;
@@ -152,7 +74,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {  // one warp owns TMEM alloc + dealloc; 2 accumulator buffers of BN fp32 columns
@@ -227,31 +149,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     __syncwarp();
   } else {
-    // ===================================================================== epilogue (4 warps)
+    // ===================================================================== epilogue (8 warps)
+    // TMEM -> registers (thread = accumulator row) -> swizzled smem -> registers (lane = column pair
+    // of one row) -> fused epilogue with fully coalesced global reads / writes.
+    const int ew = warp - 2;
     const int q = warp & 3;                            // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                          // which half of the 64-column chunks
+    float* stg = reinterpret_cast<float*>(stg_base + ew * STG_BYTES);
+    constexpr int CHUNKS = BN / STG_COLS;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const TileInfo ti = get_tile(t, m_tiles, n_tiles, num_kb, split);
       const uint32_t buf = it & 1, use = it >> 1;
       mbar_wait(&tmem_full[buf], use & 1);
       tcgen05_fence_after();
-      const int64_t m = static_cast<int64_t>(ti.m_blk) * BM + q * 32 + lane;
+      const int64_t m_base = static_cast<int64_t>(ti.m_blk) * BM + q * 32;
+      const int64_t rem_rows = p.M - m_base;
+      const int rows = rem_rows >= 32 ? 32 : (rem_rows > 0 ? (int)rem_rows : 0);   // warp-uniform
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + c * 32, r);
-        tmem_ld_wait();
-        if (m < p.M) {
+      for (int cc = half; cc < CHUNKS; cc += 2) {
+        {
+          uint32_t r0[32], r1[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + cc * STG_COLS;
+          tmem_ld_32x32(taddr, r0);
+          tmem_ld_32x32(taddr + 32, r1);
+          tmem_ld_wait();
 #pragma unroll
-          for (int g4 = 0; g4 < 8; ++g4) {
-            const int64_t n = static_cast<int64_t>(ti.n_blk) * BN + c * 32 + g4 * 4;
-            if (n < p.N) {
-              float v[4] = {__uint_as_float(r[g4 * 4]), __uint_as_float(r[g4 * 4 + 1]), __uint_as_float(r[g4 * 4 + 2]),
-                            __uint_as_float(r[g4 * 4 + 3])};
-              gemm_epilogue4<__nv_bfloat16, TOUT>(p, m, n, v, ti.lead);
-            }
+          for (int v = 0; v < 8; ++v) {
+            *reinterpret_cast<uint4*>(stg + lane * STG_COLS + ((v ^ (lane & 7)) << 2)) = make_uint4(r0[4 * v], r0[4 * v + 1], r0[4 * v + 2], r0[4 * v + 3]);
+            *reinterpret_cast<uint4*>(stg + lane * STG_COLS + (((v + 8) ^ (lane & 7)) << 2)) = make_uint4(r1[4 * v], r1[4 * v + 1], r1[4 * v + 2], r1[4 * v + 3]);
           }
         }
+        __syncwarp();
+        const int64_t n = static_cast<int64_t>(ti.n_blk) * BN + cc * STG_COLS + 2 * lane;
+        if (n < p.N) {
+          float b0 = 0.f, b1 = 0.f;
+          if (ti.lead && p.bias != nullptr) { const float2 b = *reinterpret_cast<const float2*>(p.bias + n); b0 = b.x; b1 = b.y; }
+#pragma unroll 4
+          for (int rr = 0; rr < rows; ++rr) {
+            const float2 x = *reinterpret_cast<const float2*>(stg + rr * STG_COLS + (((lane >> 1) ^ (rr & 7)) << 2) + ((lane & 1) << 1));
+            gemm_epilogue2<__nv_bfloat16, TOUT>(p, m_base + rr, n, x.x, x.y, b0, b1, ti.lead);
+          }
+        }
+        __syncwarp();
       }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty[buf]);
@@ -266,72 +206,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(f);
-  }
-  return fn;
-}
-
-struct MapKey {
-  const void* ptr; uint64_t inner, outer, stride; uint32_t box_inner, box_outer;
-  bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && inner == o.inner && outer == o.outer && stride == o.stride && box_inner == o.box_inner && box_outer == o.box_outer;
-  }
-};
-struct MapKeyHash {
-  size_t operator()(const MapKey& k) const {
-    size_t h = reinterpret_cast<size_t>(k.ptr);
-    auto mix = [&h](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
-    mix(k.inner); mix(k.outer); mix(k.stride); mix(k.box_inner); mix(k.box_outer);
-    return h;
-  }
-};
-
-// immutable per-(pointer, shape) descriptor cache; the only global state of the library
-static bool get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride_elems, uint32_t box_inner,
-                           uint32_t box_outer, CUtensorMap* out) {
-  static std::mutex mu;
-  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, inner, outer, stride_elems, box_inner, box_outer};
-  std::lock_guard<std::mutex> lock(mu);
-  auto it = cache.find(key);
-  if (it != cache.end()) { *out = it->second; return true; }
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return false; }
-  cuuint64_t gdim[2] = {inner, outer};
-  cuuint64_t gstride[1] = {stride_elems * 2};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%llu outer=%llu stride=%llu box=%ux%u", (int)r, ptr,
-              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)stride_elems, box_inner, box_outer);
-    return false;
-  }
-  if (cache.size() > 4096) cache.clear();
-  cache.emplace(key, m);
-  *out = m;
-  return true;
-}
-
 template <int BN, bool MN_MAJOR, typename TOUT>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int m_tiles, int n_tiles, int num_kb, int split,
                   cudaStream_t st) {
-  constexpr size_t smem = STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/;
+  constexpr size_t smem = stages_for(BN) * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * STG_BYTES;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MN_MAJOR, TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -353,7 +231,7 @@ bool tc_available() {
     int dev = 0, major = 0;
     ok = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess &&
-        major == 10 && tc::get_encode() != nullptr)
+        major == 10 && tc::encode_available())
       ok = 1;
     cudaGetLastError();
   }
@@ -385,11 +263,11 @@ int gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   p.split_k = split;
   CUtensorMap ta, tb;
   if (!mn) {
-    if (!get_tensor_map(p.A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.lda, BK, BM, &ta)) return MMI_ECUDA;
-    if (!get_tensor_map(p.B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.ldb, BK, (uint32_t)bn, &tb)) return MMI_ECUDA;
+    if (!get_tensor_map(p.A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B, &ta)) return MMI_ECUDA;
+    if (!get_tensor_map(p.B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.ldb, BK, (uint32_t)bn, CU_TENSOR_MAP_SWIZZLE_128B, &tb)) return MMI_ECUDA;
   } else {
-    if (!get_tensor_map(p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, 64, BK, &ta)) return MMI_ECUDA;
-    if (!get_tensor_map(p.B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldb, 64, BK, &tb)) return MMI_ECUDA;
+    if (!get_tensor_map(p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B, &ta)) return MMI_ECUDA;
+    if (!get_tensor_map(p.B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldb, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B, &tb)) return MMI_ECUDA;
   }
   const bool f32out = p.out_dtype == MMI_F32;
   MMI_CHECK_ARG(f32out || p.out_dtype == MMI_BF16, "gemm_tc: bad out dtype");
@@ -399,11 +277,6 @@ int gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   if (bn == 256) return mn ? MMI_TC_LAUNCH(256, true) : MMI_TC_LAUNCH(256, false);
   return mn ? MMI_TC_LAUNCH(128, true) : MMI_TC_LAUNCH(128, false);
 #undef MMI_TC_LAUNCH
-}
-
-int attn_tc(int, const mmi_attn_args*, int, cudaStream_t) {
-  set_error("attn_tc: not built yet");
-  return MMI_ENOSUP;
 }
 
 }  // namespace mmi

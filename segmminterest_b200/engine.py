@@ -300,7 +300,8 @@ class Engine:
                 else:
                     blocks = [dict(q=col("usr", 2), k=col("vid", 4), v=col("vid", 5), mask_k=mask["vid"], Lk=Lv),
                               dict(q=col("usr", 3), k=col("usr", 4), v=col("usr", 5), mask_k=mask["usr"], Lk=Lt)]
-                side = ops.AttnSide(ops.dt(a_out), IMPL_SIMT, B, H, d // H, Ls[s], mask[s], a_out, d, lse, blocks)
+                attn_impl = IMPL_TC if (self.use_tc and d // H == 32 and d % 8 == 0) else IMPL_SIMT
+                side = ops.AttnSide(ops.dt(a_out), attn_impl, B, H, d // H, Ls[s], mask[s], a_out, d, lse, blocks)
                 side.fwd()
                 attn[s] = (side, a_out, lse)
             lay["attn"] = attn

@@ -70,7 +70,11 @@ def gemm(layout, impl, A, lda, B, ldb, Cm, ldc, M, N, K, *, bias=None, act=ACT_N
     a.add_dtype = dt(add) if add is not None else F32
     a.accumulate = 1 if accumulate else 0
     a.split_k = split_k
-    with TIMER.region("gemm_tc" if impl == IMPL_TC else "gemm_simt", 2.0 * M * N * K):
+    cat = "gemm_tc" if impl == IMPL_TC else "gemm_simt"
+    if TIMER.detail:
+        cat += f" {('NT', 'NN', 'TN')[layout]} M={M} N={N} K={K}" + (" gelu" if act else "") + (" mulgelu" if mul_gelu_grad is not None else "") \
+            + (" add" if add is not None else "") + (" acc" if accumulate else "")
+    with TIMER.region(cat, 2.0 * M * N * K):
         rc = lib.mmi_gemm(C.byref(a), _stream())
     _lib.check(rc, "mmi_gemm")
     LaunchCounter.n += 1

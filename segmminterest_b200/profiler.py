@@ -10,6 +10,7 @@ import torch
 class KernelTimer:
     def __init__(self):
         self.enabled = False
+        self.detail = False   # per-shape categories (tools/profile_step.py --table)
         self.records = []   # (category, start_event, end_event, work)  work = flops or bytes
 
     @contextlib.contextmanager

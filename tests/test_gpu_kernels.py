@@ -185,12 +185,17 @@ def _ref_attention(qa, ka, va, mka, qb, kb, vb, mkb, mq, H):
     return torch.einsum("bhqk,bkhd->bqhd", S.softmax(-1), V).reshape(B, Lq, d)
 
 
-@pytest.mark.parametrize("dh,dtype", [(32, torch.float32), (16, torch.float32), (32, torch.bfloat16)])
-def test_attention_fwd_bwd(dev, dh, dtype):
+@pytest.mark.parametrize("dh,dtype,impl,shape", [
+    (32, torch.float32, "simt", (3, 2, 70, 40, 150)), (16, torch.float32, "simt", (3, 2, 70, 40, 150)),
+    (32, torch.bfloat16, "simt", (3, 2, 70, 40, 150)),
+    (32, torch.bfloat16, "tc", (3, 2, 70, 40, 150)), (32, torch.bfloat16, "tc", (2, 16, 500, 40, 500)),
+    (32, torch.bfloat16, "tc", (2, 16, 40, 40, 500)), (32, torch.bfloat16, "tc", (1, 4, 129, 64, 65))])
+def test_attention_fwd_bwd(dev, dh, dtype, impl, shape):
     from segmminterest_b200 import ops
     torch.manual_seed(4)
-    B, H, Lq, La, Lb = 3, 2, 70, 40, 150
+    B, H, Lq, La, Lb = shape
     d = H * dh
+    impl = ops.IMPL_TC if impl == "tc" else ops.IMPL_SIMT
 
     def mk(L):
         n = torch.randint(1, L + 1, (B,))
@@ -208,7 +213,7 @@ def test_attention_fwd_bwd(dev, dh, dtype):
     mqd, mkad, mkbd = [m.to(dev).view(torch.uint8) for m in (mq, mka, mkb)]
     blocks = [dict(q=(qa.data_ptr(), d), k=(ka.data_ptr(), d), v=(va.data_ptr(), d), mask_k=mkad, Lk=La),
               dict(q=(qb.data_ptr(), d), k=(kb.data_ptr(), d), v=(vb.data_ptr(), d), mask_k=mkbd, Lk=Lb)]
-    side = ops.AttnSide(ops.dt(out), ops.IMPL_SIMT, B, H, dh, Lq, mqd, out, d, lse, blocks)
+    side = ops.AttnSide(ops.dt(out), impl, B, H, dh, Lq, mqd, out, d, lse, blocks)
     side.fwd()
     tol = 3e-6 if dtype == torch.float32 else 8e-3
     assert _rel(out.view(B, Lq, d), ref) < tol

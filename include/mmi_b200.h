@@ -65,13 +65,19 @@ int mmi_gather_l1norm_fwd(const void* table, int table_dtype, int64_t n_rows, in
  * kn_util/nn_utils/layers/mlp.py:17-24) and their autograd mm/addmm backward.
  *   acc  = op(A) op(B)                                   (fp32 accumulate)
  *   z    = acc + bias[n]                                 (bias may be NULL)
- *   if preact: preact[m,n] = z                           (saved for GELU backward)
+ *   if preact: preact[m,n] = z                           (saved for GELU backward; save_act_grad = 0)
+ *              preact[m,n] = gelu'(z)                    (save_act_grad = 1: backward needs no erf)
  *   y    = act(z)
- *   if mul_gelu_grad: y *= gelu'(mul_gelu_grad[m,n])     (dgrad through GELU)
+ *   if mul_gelu_grad: y *= gelu'(mul_gelu_grad[m,n])     (dgrad through GELU; mul_is_grad = 0)
+ *                     y *= mul_gelu_grad[m,n]            (mul_is_grad = 1: operand saved by save_act_grad)
  *   if add:  y += add[(m % add_mod) * ld_add + n]        (residual / position embedding)
  *   C    = y                (accumulate == 0)
  *   C   += y                (accumulate == 1, C must be fp32; used for weight grads)
  * in_dtype applies to A, B, add, preact, mul_gelu_grad; out_dtype to C.
+ * The tcgen05 path (MMI_IMPL_TC) stores bf16 outputs through shared memory with TMA
+ * (cp.async.bulk.tensor) and prefetches the add / mul_gelu_grad tile the same way whenever the
+ * operands allow it (bf16, 16-byte aligned rows, add_mod >= M); other cases take a generic
+ * register epilogue with identical results.
  * split_k > 1 is only legal with accumulate == 1 (atomic fp32 adds); split_k == 0 lets
  * the tensor-core path pick a split that fills the 148 SMs.                          */
 typedef struct {
@@ -92,6 +98,8 @@ typedef struct {
   const void* add; int64_t ld_add; int64_t add_mod; int add_dtype;
   int accumulate;
   int split_k;
+  int save_act_grad;   /* 1: preact receives gelu'(z) instead of z */
+  int mul_is_grad;     /* 1: mul_gelu_grad already holds gelu'(z)  */
 } mmi_gemm_args;
 int mmi_gemm(const mmi_gemm_args* args, mmi_stream_t stream);
 

@@ -25,7 +25,7 @@ class GemmArgs(C.Structure):
                 ("preact", c_p), ("ld_preact", i64),
                 ("mul_gelu_grad", c_p), ("ld_mul", i64),
                 ("add", c_p), ("ld_add", i64), ("add_mod", i64), ("add_dtype", C.c_int),
-                ("accumulate", C.c_int), ("split_k", C.c_int)]
+                ("accumulate", C.c_int), ("split_k", C.c_int), ("save_act_grad", C.c_int), ("mul_is_grad", C.c_int)]
 
 
 class AttnBlock(C.Structure):

@@ -18,6 +18,8 @@ struct GemmParams {
   const void* add; int64_t ld_add; int64_t add_mod; int add_dtype;
   int accumulate;
   int split_k;
+  int save_act_grad;
+  int mul_is_grad;
 };
 
 // 4 consecutive columns n..n+3 of row m.  `lead` = this CTA owns the bias/add terms
@@ -28,14 +30,19 @@ __device__ __forceinline__ void gemm_epilogue4(const GemmParams& p, int64_t m, i
     const float4 b = *reinterpret_cast<const float4*>(p.bias + n);
     v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
   }
-  if (p.preact != nullptr) store4(reinterpret_cast<TIN*>(p.preact) + m * p.ld_preact + n, make_float4(v[0], v[1], v[2], v[3]));
+  if (p.preact != nullptr) {
+    float4 z = make_float4(v[0], v[1], v[2], v[3]);
+    if (p.save_act_grad) z = make_float4(gelu_grad_f(v[0]), gelu_grad_f(v[1]), gelu_grad_f(v[2]), gelu_grad_f(v[3]));
+    store4(reinterpret_cast<TIN*>(p.preact) + m * p.ld_preact + n, z);
+  }
   if (p.act == MMI_ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = gelu_f(v[j]);
   }
   if (p.mul_gelu_grad != nullptr) {
     const float4 z = load4(reinterpret_cast<const TIN*>(p.mul_gelu_grad) + m * p.ld_mul + n);
-    v[0] *= gelu_grad_f(z.x); v[1] *= gelu_grad_f(z.y); v[2] *= gelu_grad_f(z.z); v[3] *= gelu_grad_f(z.w);
+    if (p.mul_is_grad) { v[0] *= z.x; v[1] *= z.y; v[2] *= z.z; v[3] *= z.w; }
+    else { v[0] *= gelu_grad_f(z.x); v[1] *= gelu_grad_f(z.y); v[2] *= gelu_grad_f(z.z); v[3] *= gelu_grad_f(z.w); }
   }
   if (lead && p.add != nullptr) {
     const int64_t r = (m < p.add_mod) ? m : m % p.add_mod;
@@ -93,11 +100,14 @@ template <typename TIN, typename TOUT>
 __device__ __forceinline__ void gemm_epilogue2(const GemmParams& p, int64_t m, int64_t n, float v0, float v1, float b0, float b1,
                                                bool lead) {
   v0 += b0; v1 += b1;
-  if (p.preact != nullptr) store2(reinterpret_cast<TIN*>(p.preact) + m * p.ld_preact + n, make_float2(v0, v1));
+  if (p.preact != nullptr)
+    store2(reinterpret_cast<TIN*>(p.preact) + m * p.ld_preact + n,
+           p.save_act_grad ? make_float2(gelu_grad_fast(v0), gelu_grad_fast(v1)) : make_float2(v0, v1));
   if (p.act == MMI_ACT_GELU) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); }
   if (p.mul_gelu_grad != nullptr) {
     const float2 z = load2(reinterpret_cast<const TIN*>(p.mul_gelu_grad) + m * p.ld_mul + n);
-    v0 *= gelu_grad_fast(z.x); v1 *= gelu_grad_fast(z.y);
+    if (p.mul_is_grad) { v0 *= z.x; v1 *= z.y; }
+    else { v0 *= gelu_grad_fast(z.x); v1 *= gelu_grad_fast(z.y); }
   }
   if (lead && p.add != nullptr) {
     const int64_t r = (m < p.add_mod) ? m : m % p.add_mod;  // residual: add_mod == M (no division)

@@ -8,6 +8,11 @@
 //   * epilogue warps read TMEM with tcgen05.ld (32 lanes x 32 columns per warp) and apply
 //     the fused epilogue of mmi_gemm (bias, GELU + saved pre-activation, GELU' multiply,
 //     residual / position-embedding add, fp32 accumulate for weight gradients);
+//   * TMA epilogue (bf16 outputs): thread = accumulator row; the residual / GELU' tile of the
+//     NEXT output tile is prefetched by TMA into the warp's staging buffers while the tensor
+//     core works, the result is written in place (SWIZZLE_128B, conflict-free 16 B accesses) and
+//     leaves with one cp.async.bulk.tensor store per 32 x 64 block -- no per-row global
+//     latency in the epilogue, so the kernel stays MMA-bound at K = 512;
 //   * persistent CTAs (one per SM), tile order n-fastest so an activation row-block is
 //     fetched from HBM once and re-read from L2; split-K (atomic fp32) for the
 //     weight-gradient GEMMs whose K dimension is the token count.
@@ -18,6 +23,7 @@
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "tc_common.cuh"
+#include <string.h>
 
 namespace mmi {
 
@@ -49,10 +55,16 @@ __device__ __forceinline__ TileInfo get_tile(int t, int m_tiles, int n_tiles, in
   return ti;
 }
 
-template <int BN, bool MN_MAJOR, typename TOUT>
+struct EpiMaps {
+  CUtensorMap c, aux, c2;   // output, prefetched add / mul operand, second output (saved pre-activation)
+};
+
+constexpr int EBUF_BYTES = 32 * 64 * 2;   // 32 rows x 64 bf16 (one SWIZZLE_128B box per warp and chunk)
+
+template <int BN, bool MN_MAJOR, typename TOUT, bool TMA_EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p,
-               int m_tiles, int n_tiles, int num_kb, int split) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ EpiMaps em, const GemmParams p, int m_tiles, int n_tiles, int num_kb, int split) {
   extern __shared__ uint8_t smem_raw[];
   constexpr int STAGES = stages_for(BN);
   constexpr uint32_t A_BYTES = BM * BK * 2;
@@ -64,8 +76,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint8_t* stg_base = smem + STAGES * STAGE_BYTES + 256;
+  uint64_t* aux_bars = tmem_empty + 2;        // [EPI_WARPS][2]  (TMA epilogue)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(aux_bars + 2 * EPI_WARPS);
+  uint8_t* stg_base = smem + STAGES * STAGE_BYTES + 256;   // 1024-aligned: STAGE_BYTES is a multiple of 1024
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = m_tiles * n_tiles * split;
@@ -75,6 +88,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * EPI_WARPS); }
+    for (int b = 0; b < 2 * EPI_WARPS; ++b) mbar_init(&aux_bars[b], 1);
+    if constexpr (TMA_EPI) { tma_prefetch_desc(&em.c); tma_prefetch_desc(&em.aux); tma_prefetch_desc(&em.c2); }
     fence_barrier_init();
   }
   if (warp == 1) {  // one warp owns TMEM alloc + dealloc; 2 accumulator buffers of BN fp32 columns
@@ -148,6 +163,131 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
     __syncwarp();
+  } else if constexpr (TMA_EPI) {
+    // ===================================================================== TMA epilogue (8 warps)
+    // warp = 32 accumulator rows (its TMEM lane quarter) x every other 64-column chunk of the tile.
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    constexpr int CPW = BN / 128;                      // chunks per warp per tile
+    uint8_t* epi_base = smem + STAGES * STAGE_BYTES + 1024;            // 1024-aligned (SWIZZLE_128B); barriers sit below
+    uint8_t* ebuf = epi_base + ew * (2 * EBUF_BYTES);
+    float* sbias = reinterpret_cast<float*>(epi_base + EPI_WARPS * 2 * EBUF_BYTES) + ew * 64;
+    uint64_t* aux_bar = aux_bars + 2 * ew;
+    const bool aux_add = p.add != nullptr, aux_mul = p.mul_gelu_grad != nullptr;
+    const bool has_aux = aux_add || aux_mul;
+    const bool second = p.preact != nullptr;           // host: never together with an aux operand
+    const bool do_gelu = p.act == MMI_ACT_GELU;
+    auto issue_aux = [&](int t) {                      // lane 0 only
+      const TileInfo ti = get_tile(t, m_tiles, n_tiles, num_kb, split);
+#pragma unroll
+      for (int k = 0; k < CPW; ++k) {
+        mbar_expect_tx(&aux_bar[k], EBUF_BYTES);
+        tma_load_2d(&em.aux, &aux_bar[k], ebuf + k * EBUF_BYTES, ti.n_blk * BN + (half + 2 * k) * 64, ti.m_blk * BM + q * 32);
+      }
+    };
+    if (has_aux && lane == 0 && (int)blockIdx.x < total_tiles) issue_aux(blockIdx.x);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const TileInfo ti = get_tile(t, m_tiles, n_tiles, num_kb, split);
+      const uint32_t buf = it & 1, use = it >> 1;
+      const int m0 = ti.m_blk * BM + q * 32;
+      mbar_wait(&tmem_full[buf], use & 1);
+      tcgen05_fence_after();
+      if (!has_aux) {                                  // last tile's stores have finished reading the staging buffers
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int k = 0; k < CPW; ++k) {
+        const int n0 = ti.n_blk * BN + (half + 2 * k) * 64;
+        uint32_t acc[64];
+        {
+          uint32_t (&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&acc[0]);
+          uint32_t (&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&acc[32]);
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + (half + 2 * k) * 64;
+          tmem_ld_32x32(taddr, lo);
+          tmem_ld_32x32(taddr + 32, hi);
+          tmem_ld_wait();
+        }
+        if (k == CPW - 1) {                            // accumulator fully read: hand it back to the MMA warp
+          tcgen05_fence_before();
+          mbar_arrive(&tmem_empty[buf]);
+        }
+        if (second && k > 0) {                         // both staging buffers are reused within the tile
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+        }
+        {
+          const int n = n0 + 2 * lane;
+          float2 b = make_float2(0.f, 0.f);
+          if (p.bias != nullptr && n < p.N) b = *reinterpret_cast<const float2*>(p.bias + n);
+          *reinterpret_cast<float2*>(sbias + 2 * lane) = b;
+        }
+        __syncwarp();
+        uint8_t* row1 = ebuf + (second ? 0 : k * EBUF_BYTES) + lane * 128;
+        uint8_t* row2 = ebuf + EBUF_BYTES + lane * 128;
+        if (has_aux) mbar_wait(&aux_bar[k], it & 1);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const int phys = (v ^ (lane & 7)) << 4;
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(sbias + 8 * v + j);
+            x[j] = __uint_as_float(acc[8 * v + j]) + b.x;
+            x[j + 1] = __uint_as_float(acc[8 * v + j + 1]) + b.y;
+            x[j + 2] = __uint_as_float(acc[8 * v + j + 2]) + b.z;
+            x[j + 3] = __uint_as_float(acc[8 * v + j + 3]) + b.w;
+          }
+          if (has_aux) {
+            const uint4 a = *reinterpret_cast<const uint4*>(row1 + phys);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a0 = __uint_as_float(aw[j] << 16), a1 = __uint_as_float(aw[j] & 0xffff0000u);
+              if (aux_add) { x[2 * j] += a0; x[2 * j + 1] += a1; }
+              else if (p.mul_is_grad) { x[2 * j] *= a0; x[2 * j + 1] *= a1; }
+              else { x[2 * j] *= gelu_grad_fast(a0); x[2 * j + 1] *= gelu_grad_fast(a1); }
+            }
+          }
+          if (second) {
+            float z[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float cdf, e;
+              z[j] = x[j];
+              if (do_gelu || p.save_act_grad) {
+                gelu_parts(x[j], cdf, e);
+                if (p.save_act_grad) z[j] = fmaf(x[j] * 0.39894228040143267794f, e, cdf);
+                if (do_gelu) x[j] *= cdf;
+              }
+            }
+            *reinterpret_cast<uint4*>(row2 + phys) = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
+          } else if (do_gelu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = gelu_fast(x[j]);
+          }
+          *reinterpret_cast<uint4*>(row1 + phys) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&em.c, row1 - lane * 128, n0, m0);
+          if (second) tma_store_2d(&em.c2, row2 - lane * 128, n0, m0);
+          bulk_commit();
+        }
+      }
+      if (has_aux) {                                   // recycle the buffers: prefetch the next tile's operand
+        if (lane == 0) {
+          bulk_wait_read0();
+          if (t + (int)gridDim.x < total_tiles) issue_aux(t + gridDim.x);
+        }
+        __syncwarp();
+      }
+    }
+    if (lane == 0) bulk_wait0();
+    __syncwarp();
   } else {
     // ===================================================================== epilogue (8 warps)
     // TMEM -> registers (thread = accumulator row) -> swizzled smem -> registers (lane = column pair
@@ -206,22 +346,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------ host side
-template <int BN, bool MN_MAJOR, typename TOUT>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int m_tiles, int n_tiles, int num_kb, int split,
-                  cudaStream_t st) {
-  constexpr size_t smem = stages_for(BN) * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * STG_BYTES;
+template <int BN, bool TMA_EPI>
+constexpr size_t smem_bytes() {
+  return stages_for(BN) * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ +
+         (TMA_EPI ? 1024 /*barriers*/ + EPI_WARPS * 2 * EBUF_BYTES + EPI_WARPS * 64 * 4 : 256 /*barriers*/ + EPI_WARPS * STG_BYTES);
+}
+
+template <int BN, bool MN_MAJOR, typename TOUT, bool TMA_EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmParams& p, int m_tiles, int n_tiles,
+                  int num_kb, int split, cudaStream_t st) {
+  constexpr size_t smem = smem_bytes<BN, TMA_EPI>();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MN_MAJOR, TOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MN_MAJOR, TOUT, TMA_EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return MMI_ECUDA; }
     configured = true;
   }
   const int total = m_tiles * n_tiles * split;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  gemm_tc_kernel<BN, MN_MAJOR, TOUT><<<grid, NUM_THREADS, smem, st>>>(ta, tb, p, m_tiles, n_tiles, num_kb, split);
+  gemm_tc_kernel<BN, MN_MAJOR, TOUT, TMA_EPI><<<grid, NUM_THREADS, smem, st>>>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split);
   MMI_CHECK_LAUNCH();
   return MMI_OK;
 }
+
+static bool tma_ok(const void* ptr, int64_t ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 8 == 0; }
 
 }  // namespace tc
 
@@ -271,9 +419,26 @@ int gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   }
   const bool f32out = p.out_dtype == MMI_F32;
   MMI_CHECK_ARG(f32out || p.out_dtype == MMI_BF16, "gemm_tc: bad out dtype");
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  // TMA epilogue: bf16 output tiles leave through shared memory; at most one tile-shaped bf16 side operand
+  bool tma_epi = !mn && !f32out && !p.accumulate && split == 1 && tma_ok(p.C, p.ldc) && !(p.add && p.mul_gelu_grad);
+  if (tma_epi && p.add) tma_epi = p.add_dtype == MMI_BF16 && p.add_mod >= p.M && tma_ok(p.add, p.ld_add);
+  if (tma_epi && p.mul_gelu_grad) tma_epi = tma_ok(p.mul_gelu_grad, p.ld_mul);
+  if (tma_epi && p.preact) tma_epi = !p.add && !p.mul_gelu_grad && tma_ok(p.preact, p.ld_preact);
+  if (tma_epi) {
+    const void* aux = p.add ? p.add : p.mul_gelu_grad;
+    const int64_t ld_aux = p.add ? p.ld_add : p.ld_mul;
+    if (!get_tensor_map(p.C, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldc, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &em.c)) return MMI_ECUDA;
+    em.aux = em.c; em.c2 = em.c;
+    if (aux && !get_tensor_map(aux, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)ld_aux, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &em.aux)) return MMI_ECUDA;
+    if (p.preact && !get_tensor_map(p.preact, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ld_preact, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &em.c2)) return MMI_ECUDA;
+    if (bn == 256) return launch<256, false, __nv_bfloat16, true>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st);
+    return launch<128, false, __nv_bfloat16, true>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st);
+  }
 #define MMI_TC_LAUNCH(BN_, MN_)                                                                                         \
-  (f32out ? launch<BN_, MN_, float>(ta, tb, p, m_tiles, n_tiles, num_kb, split, st)                                     \
-          : launch<BN_, MN_, __nv_bfloat16>(ta, tb, p, m_tiles, n_tiles, num_kb, split, st))
+  (f32out ? launch<BN_, MN_, float, false>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st)                          \
+          : launch<BN_, MN_, __nv_bfloat16, false>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st))
   if (bn == 256) return mn ? MMI_TC_LAUNCH(256, true) : MMI_TC_LAUNCH(256, false);
   return mn ? MMI_TC_LAUNCH(128, true) : MMI_TC_LAUNCH(128, false);
 #undef MMI_TC_LAUNCH

@@ -219,11 +219,12 @@ class Engine:
     # ------------------------------------------------------------------ building blocks
     def _linear(self, x, M, K, wkey, bkey, N, out, *, act=ACT_NONE, preact=None, add=None, add_mod=0, ld_add=0,
                 n_prefix=None):
-        """out[M,N] = act(x[M,K] W[N,K]^T + b) (+ add)."""
+        """out[M,N] = act(x[M,K] W[N,K]^T + b) (+ add).  On the tensor-core path `preact` receives
+        gelu'(z) instead of z (the backward epilogue then needs no erf; see mmi_gemm save_act_grad)."""
         lp = self.cfg.precision == "bf16"
         W = self.w(wkey, lp)
         ops.gemm(GEMM_NT, self._impl(M, N, K, GEMM_NT), x, K, W, K, out, N, M, N, K, bias=self.w(bkey), act=act,
-                 preact=preact, add=add, add_mod=add_mod, ld_add=ld_add)
+                 preact=preact, add=add, add_mod=add_mod, ld_add=ld_add, save_act_grad=self.use_tc and preact is not None)
 
     def _linear_bwd(self, dy, x, M, N, K, wkey, bkey, dx, *, mul_gelu_grad=None, add=None, need_dx=True):
         """dW += dy^T x ; db += colsum(dy) ; dx = dy W (* gelu'(mul)) (+ add)."""
@@ -239,10 +240,10 @@ class Engine:
         if need_dx:
             if self._impl(M, K, N, GEMM_NT) == IMPL_TC:
                 ops.gemm(GEMM_NT, IMPL_TC, dy, N, self.wT(wkey), N, dx, K, M, K, N, mul_gelu_grad=mul_gelu_grad, add=add,
-                         add_mod=M if add is not None else 0, ld_add=K)
+                         add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=self.use_tc)
             else:
                 ops.gemm(GEMM_NN, IMPL_SIMT, dy, N, self.w(wkey, lp), K, dx, K, M, K, N, mul_gelu_grad=mul_gelu_grad,
-                         add=add, add_mod=M if add is not None else 0, ld_add=K)
+                         add=add, add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=self.use_tc)
 
     # ------------------------------------------------------------------ forward
     def forward(self, usr_image, usr_mask, vid_image, vid_mask):

@@ -50,7 +50,8 @@ def gather_l1norm(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor, mas
 
 
 def gemm(layout, impl, A, lda, B, ldb, Cm, ldc, M, N, K, *, bias=None, act=ACT_NONE, preact=None, mul_gelu_grad=None,
-         add=None, add_mod=0, ld_add=0, accumulate=False, split_k=1, in_dtype=None, out_dtype=None):
+         add=None, add_mod=0, ld_add=0, accumulate=False, split_k=1, in_dtype=None, out_dtype=None, save_act_grad=False,
+         mul_is_grad=False):
     lib = _lib.load()
     a = _lib.GemmArgs()
     a.layout, a.impl = layout, impl
@@ -70,6 +71,8 @@ def gemm(layout, impl, A, lda, B, ldb, Cm, ldc, M, N, K, *, bias=None, act=ACT_N
     a.add_dtype = dt(add) if add is not None else F32
     a.accumulate = 1 if accumulate else 0
     a.split_k = split_k
+    a.save_act_grad = 1 if save_act_grad else 0
+    a.mul_is_grad = 1 if mul_is_grad else 0
     cat = "gemm_tc" if impl == IMPL_TC else "gemm_simt"
     if TIMER.detail:
         cat += f" {('NT', 'NN', 'TN')[layout]} M={M} N={N} K={K}" + (" gelu" if act else "") + (" mulgelu" if mul_gelu_grad is not None else "") \

@@ -89,3 +89,62 @@ def test_tc_gemm_matches_simt_bit_pattern_scale(dev):
     ops.gemm(ops.GEMM_NT, ops.IMPL_TC, A, K, W, K, c1, N, M, N, K)
     ops.gemm(ops.GEMM_NT, ops.IMPL_SIMT, A, K, W, K, c2, N, M, N, K)
     assert _rel(c1, c2) < 2e-6
+
+
+def _gelu_grad(z):
+    zz = z.double().clone().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    return zz.grad
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 512, 512), (4133, 256, 512), (300, 3072, 512), (257, 128, 64), (2048, 512, 3072), (999, 192, 128)])
+def test_tc_gemm_tma_epilogue_variants(dev, M, N, K):
+    """The TMA-store / TMA-prefetch epilogue (bf16 out): plain, bias, residual add, GELU with saved z or saved
+    gelu'(z), multiply by gelu'(z) or by a saved derivative -- including ragged M and N tails."""
+    from segmminterest_b200 import ops
+    torch.manual_seed(M * 7 + N + K)
+    A = torch.randn(M, K, device=dev).bfloat16()
+    W = (torch.randn(N, K, device=dev) * 0.06).bfloat16()
+    b = torch.randn(N, device=dev)
+    R = torch.randn(M, N, device=dev).bfloat16()
+    Z = torch.randn(M, N, device=dev).bfloat16()
+    base = A.double() @ W.double().T
+
+    def run(**kw):
+        C = torch.full((M + 3, N), 7.0, device=dev, dtype=torch.bfloat16)   # 3 guard rows: the TMA store must clip at M
+        ops.gemm(ops.GEMM_NT, ops.IMPL_TC, A, K, W, K, C, N, M, N, K, **kw)
+        torch.cuda.synchronize()
+        assert bool((C[M:] == 7.0).all()), "store wrote past row M"
+        return C[:M]
+
+    tol = 5e-3
+    assert _rel(run(), base) < tol
+    assert _rel(run(bias=b), base + b.double()) < tol
+    assert _rel(run(bias=b, add=R, add_mod=M, ld_add=N), base + b.double() + R.double()) < tol
+    assert _rel(run(mul_gelu_grad=Z), base * _gelu_grad(Z)) < tol
+    assert _rel(run(mul_gelu_grad=Z, mul_is_grad=True), base * Z.double()) < tol
+    assert _rel(run(bias=b, act=ops.ACT_GELU), torch.nn.functional.gelu(base + b.double())) < tol
+    for save_grad in (False, True):
+        pre = torch.full((M + 3, N), 7.0, device=dev, dtype=torch.bfloat16)
+        out = run(bias=b, act=ops.ACT_GELU, preact=pre, save_act_grad=save_grad)
+        z = base + b.double()
+        assert _rel(out, torch.nn.functional.gelu(z)) < tol
+        assert _rel(pre[:M], _gelu_grad(z) if save_grad else z) < tol
+        assert bool((pre[M:] == 7.0).all())
+
+
+def test_tc_gemm_tma_epilogue_strided_outputs(dev):
+    """Output / residual that are column slices of wider tensors (ldc != N), as the fused-projection buffers are."""
+    from segmminterest_b200 import ops
+    torch.manual_seed(11)
+    M, N, K = 1500, 512, 512
+    A = torch.randn(M, K, device=dev).bfloat16()
+    W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    wide = torch.zeros(M, 3 * N, device=dev, dtype=torch.bfloat16)
+    Rw = torch.randn(M, 2 * N, device=dev).bfloat16()
+    Cview = wide.view(-1)[N:]
+    Rview = Rw.view(-1)[N:]
+    ops.gemm(ops.GEMM_NT, ops.IMPL_TC, A, K, W, K, Cview, 3 * N, M, N, K, add=Rview, add_mod=M, ld_add=2 * N)
+    ref = A.double() @ W.double().T + Rw[:, N:].double()
+    assert _rel(wide[:, N:2 * N], ref) < 5e-3
+    assert float(wide[:, :N].abs().max()) == 0.0 and float(wide[:, 2 * N:].abs().max()) == 0.0

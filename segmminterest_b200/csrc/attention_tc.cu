@@ -1,16 +1,26 @@
 // MMI_IMPL_TC attention (bf16, head dim 32): the candidate x history attention of
 // models/encoder.py:44-73,138-161 on the 5th-gen tensor cores.
 //
-// Per CTA (serial pipeline, 2-4 CTAs per SM overlap each other's MMA / softmax phases):
-//   fwd      : 128 queries x 64-key tiles.  S = Q K^T (tcgen05.mma 128x64x16, fp32 in TMEM) ->
-//              128 threads (one per TMEM lane = query row) read S with tcgen05.ld, apply the
-//              reference's "set to -10000 then / sqrt(dh)" mask, online softmax in the exp2
-//              domain, write bf16 P into swizzled smem -> O_tile = P V (tcgen05.mma 128x32x16) ->
-//              rescale-and-accumulate O in registers.  The two key blocks ([Qa Ka^T | Qb Kb^T])
-//              stream through the same running max / sum: one joint softmax, never materialised.
-//   bwd dq   : same tiling; recomputes S, dP = dO V^T, dS = P (dP - delta) scale, dQ += dS K.
-//   bwd dk/dv: 128 keys x 64-query tiles, transposed formulation (thread = key row):
-//              S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q, accumulated in TMEM.
+// With dh = 32 the tensor pipe needs 128 cycles per 128 x 64 score tile while the exponentials
+// need 512 (16 MUFU/clk/SM), so these kernels are built around the SOFTMAX threads, not the MMA:
+//   * every score tile is produced ahead of time: S (and dP) are double-buffered in TMEM and the
+//     single MMA thread issues tile j+2 as soon as the softmax threads have pulled tile j into
+//     registers; P / dS staging in shared memory is double-buffered too, so the softmax warps of
+//     the two resident CTAs never wait for the tensor pipe in steady state;
+//   * forward is two-pass: pass 1 takes the exact row maximum (one FMNMX per score, no MUFU),
+//     pass 2 recomputes S, exponentiates against the final maximum and lets P V accumulate in
+//     TMEM across all key tiles -- no running rescale, no TMEM round trip per tile;
+//   * per score the fast path (tile without masked keys) is FFMA + EX2 + FADD + half a pack in
+//     forward, FFMA + EX2 + FFMA + FMUL + pack in backward; the reference's "set to -10000, then
+//     / sqrt(dh)" masking (padded queries get a uniform softmax, masked logits pass no gradient)
+//     is handled exactly on a slow path chosen per warp and tile.
+//
+//   fwd      : CTA = 128 queries x (b, h); 64-key tiles; the two key blocks ([Qa Ka^T | Qb Kb^T])
+//              share one softmax.  TMEM: S[2] 128 cols | O 32 cols.
+//   bwd dq   : same rows, 32-key tiles: S, dP = dO V^T -> dS = P (dP - delta) scale -> dQ += dS K.
+//              TMEM: S[2] | dP[2] | dQa | dQb (192 cols).
+//   bwd dk/dv: CTA = 128 keys of one block, 32-query tiles, transposed formulation (thread = key):
+//              S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q.  TMEM: S^T[2] | dP^T[2] | dK | dV.
 // Operands arrive by TMA (64 B rows, SWIZZLE_64B) straight from the fused-projection buffers:
 // head h of a [tokens, ld] tensor is the 32-column box at column h*32.
 #include "common.cuh"
@@ -21,13 +31,17 @@ namespace tc {
 
 constexpr int DH = 32;
 constexpr int QT = 128;                 // rows per CTA (TMEM lanes)
-constexpr int NKT = 64;                 // columns per tile
+constexpr int FWD_NT = 64;              // key columns per forward tile
+constexpr int BWD_NT = 32;              // columns per backward tile
+constexpr int KV_STAGES = 4;
 constexpr int ATT_THREADS = 192;        // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 softmax
+constexpr int ATT_TMEM_COLS = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-constexpr uint32_t TILE64 = NKT * DH * 2;    // 4 KB : 64 rows x 64 B
+constexpr uint32_t TILE32 = 32 * DH * 2;     // 2 KB : 32 rows x 64 B
+constexpr uint32_t TILE64 = 64 * DH * 2;     // 4 KB : 64 rows x 64 B
 constexpr uint32_t TILE128 = QT * DH * 2;    // 8 KB : 128 rows x 64 B
-constexpr uint32_t PBYTES = QT * NKT * 2;    // 16 KB: 128 rows x 128 B (SWIZZLE_128B, K-major)
+constexpr uint32_t PBYTES = QT * FWD_NT * 2; // 16 KB: 128 rows x 128 B (SWIZZLE_128B, K-major)
 
 struct AttnTcParams {
   int B, H, Lq, nblk;
@@ -52,11 +66,7 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-// 64 bf16 (32 packed words) of row `row` into a [rows x 128 B] SWIZZLE_128B K-major tile
+// 32 bf16 (16 packed words) = columns [32*half, 32*half+32) of row `row` of a [rows x 128 B] SWIZZLE_128B K-major tile
 __device__ __forceinline__ void write_row_sw128_half(uint8_t* tile, int row, int half, const uint32_t (&w)[16]) {
 #pragma unroll
   for (int v = 0; v < 4; ++v) {
@@ -64,197 +74,293 @@ __device__ __forceinline__ void write_row_sw128_half(uint8_t* tile, int row, int
     *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
   }
 }
-// bit c of the result = mask[base + c] != 0 for c < count (c in 0..31), whole warp participates
+// 32 bf16 = the whole row `row` of a [rows x 64 B] SWIZZLE_64B K-major tile (address bits [4,6) ^= bits [7,9))
+__device__ __forceinline__ void write_row_sw64(uint8_t* tile, int row, const uint32_t (&w)[16]) {
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+    *reinterpret_cast<uint4*>(tile + row * 64 + ((v ^ ((row >> 1) & 3)) << 4)) = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+}
+// bit c of the result = mask[base + off + c] != 0 for off + c < count, whole warp participates
 __device__ __forceinline__ uint32_t mask_bits32(const uint8_t* mask, int64_t base, int off, int count, int lane) {
   const int c = off + lane;
   const bool v = (c < count) ? (mask[base + c] != 0) : false;
   return __ballot_sync(0xffffffffu, v);
 }
-__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ uint32_t range_bits32(int off, int count) {   // bit c set iff off + c < count
+  const int n = count - off;
+  return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
+}
 
-constexpr uint32_t IDESC_S = make_idesc(QT, NKT, false, false);    // 128 x 64, A/B K-major
-constexpr uint32_t IDESC_O = make_idesc(QT, DH, false, true);      // 128 x 32, A K-major (P), B MN-major
+constexpr uint32_t IDESC_S64 = make_idesc(QT, FWD_NT, false, false);   // 128 x 64, A/B K-major
+constexpr uint32_t IDESC_S32 = make_idesc(QT, BWD_NT, false, false);   // 128 x 32, A/B K-major
+constexpr uint32_t IDESC_O = make_idesc(QT, DH, false, true);          // 128 x 32, A K-major, B MN-major
 
 __device__ __forceinline__ uint64_t desc_k64(uint32_t addr, int kstep) { return make_smem_desc(addr + kstep * 32, 16, 512, 4); }      // K-major SW64
 __device__ __forceinline__ uint64_t desc_mn64(uint32_t addr, int kstep) { return make_smem_desc(addr + kstep * 1024, 512, 512, 4); }  // MN-major SW64, 16 rows/step
 __device__ __forceinline__ uint64_t desc_p128(uint32_t addr, int kstep) { return make_smem_desc(addr + kstep * 32, 16, 1024, 2); }   // K-major SW128
 
-// ====================================================================================== forward
-__global__ void __launch_bounds__(ATT_THREADS, 3)
-attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
-                   const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
-                   const __grid_constant__ CUtensorMap tmVa, const __grid_constant__ CUtensorMap tmVb, const AttnTcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;                       // [2][8 KB]
-  uint8_t* sKV = sQ + 2 * TILE128;          // [2 stages][K 4 KB | V 4 KB]
-  uint8_t* sP = sKV + 2 * 2 * TILE64;       // 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + PBYTES);
-  uint64_t* bar_q = bars;                   // 1
-  uint64_t* full_kv = bars + 1;             // [2]
-  uint64_t* empty_kv = bars + 3;            // [2]
-  uint64_t* s_ready = bars + 5;
-  uint64_t* p_ready = bars + 6;
-  uint64_t* pv_ready = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+// barrier slots shared by the three kernels
+struct Bars {
+  uint64_t once;                 // one-shot operand load (Q / K,V of the CTA's rows)
+  uint64_t kv_full[KV_STAGES];
+  uint64_t kv_empty[KV_STAGES];
+  uint64_t a_ready[2];           // MMA  -> softmax : S (and dP) tile in TMEM
+  uint64_t s_free[2];            // softmax -> MMA  : tile pulled into registers
+  uint64_t p_ready[2];           // softmax -> MMA  : P / dS staged in shared memory
+  uint64_t p_free[2];            // MMA  -> softmax : staging buffer consumed
+  uint64_t done;                 // MMA  -> softmax : accumulators complete
+  uint32_t tmem_slot;
+};
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
-  int ntile[2] = {(p.Lk[0] + NKT - 1) / NKT, p.nblk > 1 ? (p.Lk[1] + NKT - 1) / NKT : 0};
-  const int ntiles = ntile[0] + ntile[1];
-
-  if (warp == 0 && lane == 0) {
-    mbar_init(bar_q, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&full_kv[s], 1); mbar_init(&empty_kv[s], 1); }
-    mbar_init(s_ready, 1); mbar_init(p_ready, 128); mbar_init(pv_ready, 1);
-    fence_barrier_init();
+__device__ __forceinline__ void init_bars(Bars* bars, int softmax_threads) {
+  mbar_init(&bars->once, 1);
+  for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&bars->kv_full[s], 1); mbar_init(&bars->kv_empty[s], 1); }
+  for (int b = 0; b < 2; ++b) {
+    mbar_init(&bars->a_ready[b], 1);
+    mbar_init(&bars->s_free[b], softmax_threads);
+    mbar_init(&bars->p_ready[b], softmax_threads);
+    mbar_init(&bars->p_free[b], 1);
   }
+  mbar_init(&bars->done, 1);
+  fence_barrier_init();
+}
+__device__ __forceinline__ uint32_t tmem_setup(Bars* bars, int warp) {
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "r"(ATT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tO = tmem + NKT;
+  return bars->tmem_slot;
+}
+__device__ __forceinline__ void tmem_teardown(uint32_t tmem, int warp) {
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ATT_TMEM_COLS) : "memory");
+  }
+}
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint32_t (&r)[32], float mul) {
+#pragma unroll
+  for (int d = 0; d < DH; d += 8)
+    *reinterpret_cast<uint4*>(dst + d) =
+        make_uint4(pack_bf16x2(__uint_as_float(r[d]) * mul, __uint_as_float(r[d + 1]) * mul), pack_bf16x2(__uint_as_float(r[d + 2]) * mul, __uint_as_float(r[d + 3]) * mul),
+                   pack_bf16x2(__uint_as_float(r[d + 4]) * mul, __uint_as_float(r[d + 5]) * mul), pack_bf16x2(__uint_as_float(r[d + 6]) * mul, __uint_as_float(r[d + 7]) * mul));
+}
+
+// ====================================================================================== forward
+// smem: Q [2][8 KB] | K,V ring [4][4 KB + 4 KB] | P [2][16 KB] | barriers
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
+                   const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
+                   const __grid_constant__ CUtensorMap tmVa, const __grid_constant__ CUtensorMap tmVb, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + 2 * TILE128;
+  uint8_t* sP = sKV + KV_STAGES * 2 * TILE64;
+  Bars* bars = reinterpret_cast<Bars*>(sP + 2 * PBYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
+  const int nt0 = (p.Lk[0] + FWD_NT - 1) / FWD_NT, nt1 = p.nblk > 1 ? (p.Lk[1] + FWD_NT - 1) / FWD_NT : 0;
+  const int T = nt0 + nt1;
+  const int rows_valid = min(QT, p.Lq - q0);
+  const int nact = (rows_valid + 31) >> 5;                  // softmax warps with at least one real query
+
+  if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
+  const uint32_t tmem = tmem_setup(bars, warp);
+  const uint32_t tO = tmem + 2 * FWD_NT;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar_q, (p.nblk > 1 ? 2 : 1) * TILE128);
-      tma_load_2d(&tmQa, bar_q, sQ, h * DH, b * p.Lq + q0);
-      if (p.nblk > 1) tma_load_2d(&tmQb, bar_q, sQ + TILE128, h * DH, b * p.Lq + q0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1, blk = j < ntile[0] ? 0 : 1, kt = blk ? j - ntile[0] : j;
-        mbar_wait(&empty_kv[s], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&full_kv[s], 2 * TILE64);
-        uint8_t* dst = sKV + s * 2 * TILE64;
-        const int row = b * p.Lk[blk] + kt * NKT;
-        tma_load_2d(blk ? &tmKb : &tmKa, &full_kv[s], dst, h * DH, row);
-        tma_load_2d(blk ? &tmVb : &tmVa, &full_kv[s], dst + TILE64, h * DH, row);
+      mbar_expect_tx(&bars->once, (p.nblk > 1 ? 2 : 1) * TILE128);
+      tma_load_2d(&tmQa, &bars->once, sQ, h * DH, b * p.Lq + q0);
+      if (p.nblk > 1) tma_load_2d(&tmQb, &bars->once, sQ + TILE128, h * DH, b * p.Lq + q0);
+      for (int jj = 0; jj < 2 * T; ++jj) {
+        const bool pass2 = jj >= T;
+        const int j = pass2 ? jj - T : jj, blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = jj & (KV_STAGES - 1);
+        mbar_wait(&bars->kv_empty[st], ((jj / KV_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&bars->kv_full[st], pass2 ? 2 * TILE64 : TILE64);
+        uint8_t* dst = sKV + st * 2 * TILE64;
+        const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * FWD_NT;
+        tma_load_2d(blk ? &tmKb : &tmKa, &bars->kv_full[st], dst, h * DH, row);
+        if (pass2) tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[st], dst + TILE64, h * DH, row);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      mbar_wait(bar_q, 0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1, blk = j < ntile[0] ? 0 : 1;
-        mbar_wait(&full_kv[s], (j >> 1) & 1);
+      mbar_wait(&bars->once, 0);
+      auto issue_pv = [&](int u, int st) {               // O += P(u) V(u)
+        const int pb = u & 1;
+        mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
         tcgen05_fence_after();
-        const uint32_t aQ = smem_u32(sQ + blk * TILE128), aK = smem_u32(sKV + s * 2 * TILE64), aV = aK + TILE64;
+        const uint32_t aP = smem_u32(sP + pb * PBYTES), aV = smem_u32(sKV + st * 2 * TILE64 + TILE64);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tS, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S, k);
-        umma_commit(s_ready);
-        mbar_wait(p_ready, j & 1);
+        for (int k = 0; k < 4; ++k) umma_f16(tO, desc_p128(aP, k), desc_mn64(aV, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&bars->p_free[pb]);
+        umma_commit(&bars->kv_empty[st]);
+      };
+      for (int jj = 0; jj < 2 * T; ++jj) {
+        const int j = jj >= T ? jj - T : jj, blk = j < nt0 ? 0 : 1, st = jj & (KV_STAGES - 1), sb = jj & 1;
+        mbar_wait(&bars->kv_full[st], (jj / KV_STAGES) & 1);
+        if (jj >= 2) mbar_wait(&bars->s_free[sb], ((jj >> 1) - 1) & 1);
         tcgen05_fence_after();
-        const uint32_t aP = smem_u32(sP);
+        const uint32_t aQ = smem_u32(sQ + blk * TILE128), aK = smem_u32(sKV + st * 2 * TILE64);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tO, desc_p128(aP, k), desc_mn64(aV, k), IDESC_O, k);
-        umma_commit(pv_ready);
-        umma_commit(&empty_kv[s]);
+        for (int k = 0; k < 2; ++k) umma_f16(tmem + sb * FWD_NT, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S64, k);
+        umma_commit(&bars->a_ready[sb]);
+        if (jj < T) umma_commit(&bars->kv_empty[st]);     // pass 1 needs K only
+        if (jj - 1 >= T) issue_pv(jj - 1 - T, (jj - 1) & (KV_STAGES - 1));
       }
+      issue_pv(T - 1, (2 * T - 1) & (KV_STAGES - 1));
+      umma_commit(&bars->done);
     }
     __syncwarp();
-  } else {
+  } else if ((warp & 3) < nact) {
     const int qd = warp & 3, row = qd * 32 + lane;
     const int qi = q0 + row;
     const bool q_in = qi < p.Lq;
-    const bool mq = q_in ? (p.mask_q[(int64_t)b * p.Lq + qi] != 0) : false;
+    // rows past Lq compute on whatever the TMA box held (finite) and are never stored
+    const bool mq = q_in ? (p.mask_q[(int64_t)b * p.Lq + qi] != 0) : true;
+    const bool warp_all_mq = __all_sync(0xffffffffu, mq);
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-    float m = -INFINITY, l = 0.f, o[DH];
-#pragma unroll
-    for (int d = 0; d < DH; ++d) o[d] = 0.f;
-    for (int j = 0; j < ntiles; ++j) {
-      const int blk = j < ntile[0] ? 0 : 1, kt = blk ? j - ntile[0] : j;
-      const int k0 = kt * NKT, nvalid = min(NKT, p.Lk[blk] - k0);
-      const int64_t mbase = (int64_t)b * p.Lk[blk] + k0;
-      const uint32_t w[2] = {mask_bits32(p.mask_k[blk], mbase, 0, nvalid, lane), mask_bits32(p.mask_k[blk], mbase, 32, nvalid, lane)};
-      mbar_wait(s_ready, j & 1);
+    // ---- pass 1: exact row maximum of the masked logits
+    float mx = -INFINITY;
+    bool any_masked = false;
+    for (int j = 0; j < T; ++j) {
+      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, sb = j & 1;
+      const int k0 = kt * FWD_NT, nvalid = min(FWD_NT, (blk ? p.Lk[1] : p.Lk[0]) - k0);
+      const int64_t mbase = (int64_t)b * (blk ? p.Lk[1] : p.Lk[0]) + k0;
+      const uint32_t wv[2] = {mask_bits32((blk ? p.mask_k[1] : p.mask_k[0]), mbase, 0, nvalid, lane), mask_bits32((blk ? p.mask_k[1] : p.mask_k[0]), mbase, 32, nvalid, lane)};
+      const uint32_t wr[2] = {range_bits32(0, nvalid), range_bits32(32, nvalid)};
+      any_masked |= ((wr[0] & ~wv[0]) | (wr[1] & ~wv[1])) != 0u;
+      mbar_wait(&bars->a_ready[sb], (j >> 1) & 1);
       tcgen05_fence_after();
-      // pass 1: row max of the masked, scaled logits (log2 domain)
-      float mx = -INFINITY;
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(tmem + lane_addr + sb * FWD_NT, r0);
+      if (nvalid > 32) tmem_ld_32x32(tmem + lane_addr + sb * FWD_NT + 32, r1);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&bars->s_free[sb]);
+      if (wv[0] == 0xffffffffu) {
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        if (hf * 32 < nvalid) {
-          uint32_t r[32];
-          tmem_ld_32x32(tS + lane_addr + hf * 32, r);
-          tmem_ld_wait();
+        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r0[c]));
+      } else {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if (hf * 32 + c < nvalid) {
-              const float x = (mq && ((w[hf] >> c) & 1u)) ? __uint_as_float(r[c]) * p.scale_log2 : p.fill_log2;
-              mx = fmaxf(mx, x);
-            }
-          }
+        for (int c = 0; c < 32; ++c) if ((wv[0] >> c) & 1u) mx = fmaxf(mx, __uint_as_float(r0[c]));
+      }
+      if (nvalid > 32) {
+        if (wv[1] == 0xffffffffu) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r1[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) if ((wv[1] >> c) & 1u) mx = fmaxf(mx, __uint_as_float(r1[c]));
         }
       }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = ex2(m - m_new);
-      float rowsum = 0.f;
-      // pass 2: p = exp2(x - m_new) -> bf16 -> swizzled smem (A operand of the PV MMA)
+    }
+    // log2-domain maximum of x = valid ? s * scale : fill  (a padded query sees fill everywhere)
+    float m;
+    if (!mq) m = p.fill_log2;
+    else {
+      m = any_masked ? p.fill_log2 : -INFINITY;
+      if (mx > -INFINITY) m = fmaxf(m, mx * p.scale_log2);
+    }
+    const float scale_t = mq ? p.scale_log2 : 0.f;
+    const float nb_t = (mq ? 0.f : p.fill_log2) - m;     // x - m = s * scale_t + nb_t
+    const float pm = ex2(p.fill_log2 - m);               // probability weight of a masked key
+    // ---- pass 2: P = exp2(x - m) -> bf16 -> swizzled smem, O accumulates in TMEM
+    float l = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const int jj = T + j, blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, sb = jj & 1, pb = j & 1;
+      const int k0 = kt * FWD_NT, nvalid = min(FWD_NT, (blk ? p.Lk[1] : p.Lk[0]) - k0);
+      const int64_t mbase = (int64_t)b * (blk ? p.Lk[1] : p.Lk[0]) + k0;
+      const uint32_t wv[2] = {mask_bits32((blk ? p.mask_k[1] : p.mask_k[0]), mbase, 0, nvalid, lane), mask_bits32((blk ? p.mask_k[1] : p.mask_k[0]), mbase, 32, nvalid, lane)};
+      const uint32_t wr[2] = {range_bits32(0, nvalid), range_bits32(32, nvalid)};
+      mbar_wait(&bars->a_ready[sb], (jj >> 1) & 1);
+      tcgen05_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32(tmem + lane_addr + sb * FWD_NT, r0);
+      if (nvalid > 32) tmem_ld_32x32(tmem + lane_addr + sb * FWD_NT + 32, r1);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive(&bars->s_free[sb]);
+      uint32_t pk0[16], pk1[16];
+      float sum0 = 0.f, sum1 = 0.f;
+      if (warp_all_mq && wv[0] == 0xffffffffu) {
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t pk[16];
-        if (hf * 32 < nvalid) {
-          uint32_t r[32];
-          tmem_ld_32x32(tS + lane_addr + hf * 32, r);
-          tmem_ld_wait();
+        for (int c = 0; c < 32; c += 2) {
+          const float e0 = ex2(fmaf(__uint_as_float(r0[c]), scale_t, nb_t)), e1 = ex2(fmaf(__uint_as_float(r0[c + 1]), scale_t, nb_t));
+          sum0 += e0; sum1 += e1;
+          pk0[c >> 1] = pack_bf16x2(e0, e1);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float e[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int cc = c + t;
+            const float ev = ex2(fmaf(__uint_as_float(r0[cc]), scale_t, nb_t));
+            e[t] = ((wv[0] >> cc) & 1u) ? ev : (((wr[0] >> cc) & 1u) ? pm : 0.f);
+          }
+          sum0 += e[0]; sum1 += e[1];
+          pk0[c >> 1] = pack_bf16x2(e[0], e[1]);
+        }
+      }
+      if (nvalid > 32) {
+        if (warp_all_mq && wv[1] == 0xffffffffu) {
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
-            float pv[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int cc = c + e;
-              float x = (mq && ((w[hf] >> cc) & 1u)) ? __uint_as_float(r[cc]) * p.scale_log2 : p.fill_log2;
-              pv[e] = (hf * 32 + cc < nvalid) ? ex2(x - m_new) : 0.f;
-            }
-            rowsum += pv[0] + pv[1];
-            pk[c >> 1] = pack_bf16(pv[0], pv[1]);
+            const float e0 = ex2(fmaf(__uint_as_float(r1[c]), scale_t, nb_t)), e1 = ex2(fmaf(__uint_as_float(r1[c + 1]), scale_t, nb_t));
+            sum0 += e0; sum1 += e1;
+            pk1[c >> 1] = pack_bf16x2(e0, e1);
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) pk[c] = 0u;
+          for (int c = 0; c < 32; c += 2) {
+            float e[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int cc = c + t;
+              const float ev = ex2(fmaf(__uint_as_float(r1[cc]), scale_t, nb_t));
+              e[t] = ((wv[1] >> cc) & 1u) ? ev : (((wr[1] >> cc) & 1u) ? pm : 0.f);
+            }
+            sum0 += e[0]; sum1 += e[1];
+            pk1[c >> 1] = pack_bf16x2(e[0], e[1]);
+          }
         }
-        write_row_sw128_half(sP, row, hf, pk);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) pk1[c] = 0u;
       }
-      l = l * alpha + rowsum;
-      m = m_new;
-      tcgen05_fence_before();
+      l += sum0 + sum1;
+      if (j >= 2) mbar_wait(&bars->p_free[pb], ((j >> 1) - 1) & 1);   // P V of tile j-2 has consumed this buffer
+      write_row_sw128_half(sP + pb * PBYTES, row, 0, pk0);
+      write_row_sw128_half(sP + pb * PBYTES, row, 1, pk1);
       fence_proxy_async_smem();
-      mbar_arrive(p_ready);
-      mbar_wait(pv_ready, j & 1);
-      tcgen05_fence_after();
-      {
-        uint32_t r[32];
-        tmem_ld_32x32(tO + lane_addr, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int d = 0; d < DH; ++d) o[d] = fmaf(o[d], alpha, __uint_as_float(r[d]));
-      }
-      tcgen05_fence_before();
+      mbar_arrive(&bars->p_ready[pb]);
     }
+    mbar_wait(&bars->done, 0);
+    tcgen05_fence_after();
+    uint32_t ro[32];
+    tmem_ld_32x32(tO + lane_addr, ro);
+    tmem_ld_wait();
     if (q_in) {
-      const float inv = 1.0f / l;
-      __nv_bfloat16* dst = p.out + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH;
-#pragma unroll
-      for (int d = 0; d < DH; d += 8) {
-        *reinterpret_cast<uint4*>(dst + d) = make_uint4(pack_bf16(o[d] * inv, o[d + 1] * inv), pack_bf16(o[d + 2] * inv, o[d + 3] * inv),
-                                                        pack_bf16(o[d + 4] * inv, o[d + 5] * inv), pack_bf16(o[d + 6] * inv, o[d + 7] * inv));
-      }
+      store_row32_bf16(p.out + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH, ro, 1.0f / l);
       p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = m * kLn2 + logf(l);
     }
   }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128) : "memory");
-  }
+  tmem_teardown(tmem, warp);
 }
 
 // ====================================================================================== backward: dQ
-// TMEM: S [0,64) | dP [64,128) | dQ [128,160)  -> 256 columns
+// smem: Q [2][8 KB] | dO 8 KB | K,V ring [4][2 KB + 2 KB] | dS [2][8 KB] | barriers
+// TMEM: S[2] @0,32 | dP[2] @64,96 | dQa @128 | dQb @160
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
                       const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
@@ -262,89 +368,79 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
                       const __grid_constant__ CUtensorMap tmdO, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sQ = smem;                       // [2][8 KB]
-  uint8_t* sdO = sQ + 2 * TILE128;          // 8 KB
-  uint8_t* sKV = sdO + TILE128;             // [2][K 4 KB | V 4 KB]
-  uint8_t* sdS = sKV + 2 * 2 * TILE64;      // 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + PBYTES);
-  uint64_t* bar_q = bars;
-  uint64_t* full_kv = bars + 1;
-  uint64_t* empty_kv = bars + 3;
-  uint64_t* sdp_ready = bars + 5;
-  uint64_t* ds_ready = bars + 6;
-  uint64_t* ds_free = bars + 7;
-  uint64_t* dq_ready = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + 2 * TILE128;
+  uint8_t* sKV = sdO + TILE128;
+  uint8_t* sdS = sKV + KV_STAGES * 2 * TILE32;
+  Bars* bars = reinterpret_cast<Bars*>(sdS + 2 * TILE128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
-  int ntile[2] = {(p.Lk[0] + NKT - 1) / NKT, p.nblk > 1 ? (p.Lk[1] + NKT - 1) / NKT : 0};
-  const int ntiles = ntile[0] + ntile[1];
+  const int nt0 = (p.Lk[0] + BWD_NT - 1) / BWD_NT, nt1 = p.nblk > 1 ? (p.Lk[1] + BWD_NT - 1) / BWD_NT : 0;
+  const int T = nt0 + nt1;
+  const int rows_valid = min(QT, p.Lq - q0);
+  const int nact = (rows_valid + 31) >> 5;
 
-  if (warp == 0 && lane == 0) {
-    mbar_init(bar_q, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&full_kv[s], 1); mbar_init(&empty_kv[s], 1); }
-    mbar_init(sdp_ready, 1); mbar_init(ds_ready, 128); mbar_init(ds_free, 1); mbar_init(dq_ready, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tdP = tmem + NKT, tdQ = tmem + 2 * NKT;
+  if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
+  const uint32_t tmem = tmem_setup(bars, warp);
+  const uint32_t tdP = tmem + 2 * BWD_NT, tdQ = tmem + 4 * BWD_NT;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar_q, (p.nblk > 1 ? 3 : 2) * TILE128);
-      tma_load_2d(&tmQa, bar_q, sQ, h * DH, b * p.Lq + q0);
-      if (p.nblk > 1) tma_load_2d(&tmQb, bar_q, sQ + TILE128, h * DH, b * p.Lq + q0);
-      tma_load_2d(&tmdO, bar_q, sdO, h * DH, b * p.Lq + q0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1, blk = j < ntile[0] ? 0 : 1, kt = blk ? j - ntile[0] : j;
-        mbar_wait(&empty_kv[s], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&full_kv[s], 2 * TILE64);
-        uint8_t* dst = sKV + s * 2 * TILE64;
-        const int row = b * p.Lk[blk] + kt * NKT;
-        tma_load_2d(blk ? &tmKb : &tmKa, &full_kv[s], dst, h * DH, row);
-        tma_load_2d(blk ? &tmVb : &tmVa, &full_kv[s], dst + TILE64, h * DH, row);
+      mbar_expect_tx(&bars->once, (p.nblk > 1 ? 3 : 2) * TILE128);
+      tma_load_2d(&tmQa, &bars->once, sQ, h * DH, b * p.Lq + q0);
+      if (p.nblk > 1) tma_load_2d(&tmQb, &bars->once, sQ + TILE128, h * DH, b * p.Lq + q0);
+      tma_load_2d(&tmdO, &bars->once, sdO, h * DH, b * p.Lq + q0);
+      for (int j = 0; j < T; ++j) {
+        const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j & (KV_STAGES - 1);
+        mbar_wait(&bars->kv_empty[st], ((j / KV_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
+        uint8_t* dst = sKV + st * 2 * TILE32;
+        const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * BWD_NT;
+        tma_load_2d(blk ? &tmKb : &tmKa, &bars->kv_full[st], dst, h * DH, row);
+        tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[st], dst + TILE32, h * DH, row);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      mbar_wait(bar_q, 0);
-      const uint32_t adO = smem_u32(sdO), adS = smem_u32(sdS);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1, blk = j < ntile[0] ? 0 : 1, kt = blk ? j - ntile[0] : j;
-        mbar_wait(&full_kv[s], (j >> 1) & 1);
+      mbar_wait(&bars->once, 0);
+      const uint32_t adO = smem_u32(sdO);
+      auto issue_dq = [&](int u) {                       // dQ[blk(u)] += dS(u) K(u)
+        const int pb = u & 1, st = u & (KV_STAGES - 1), blk = u < nt0 ? 0 : 1, kt = blk ? u - nt0 : u;
+        mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
         tcgen05_fence_after();
-        const uint32_t aQ = smem_u32(sQ + blk * TILE128), aK = smem_u32(sKV + s * 2 * TILE64), aV = aK + TILE64;
+        const uint32_t adS = smem_u32(sdS + pb * TILE128), aK = smem_u32(sKV + st * 2 * TILE32);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tS, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S, k);
-#pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tdP, desc_k64(adO, k), desc_k64(aV, k), IDESC_S, k);
-        umma_commit(sdp_ready);
-        mbar_wait(ds_ready, j & 1);
+        for (int k = 0; k < 2; ++k) umma_f16(tdQ + blk * DH, desc_k64(adS, k), desc_mn64(aK, k), IDESC_O, (kt > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&bars->p_free[pb]);
+        umma_commit(&bars->kv_empty[st]);
+      };
+      for (int j = 0; j < T; ++j) {
+        const int blk = j < nt0 ? 0 : 1, st = j & (KV_STAGES - 1), sb = j & 1;
+        mbar_wait(&bars->kv_full[st], (j / KV_STAGES) & 1);
+        if (j >= 2) mbar_wait(&bars->s_free[sb], ((j >> 1) - 1) & 1);
         tcgen05_fence_after();
+        const uint32_t aQ = smem_u32(sQ + blk * TILE128), aK = smem_u32(sKV + st * 2 * TILE32), aV = aK + TILE32;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tdQ, desc_p128(adS, k), desc_mn64(aK, k), IDESC_O, (kt > 0 || k > 0) ? 1u : 0u);
-        umma_commit(ds_free);
-        umma_commit(&empty_kv[s]);
-        if (kt == ntile[blk] - 1) umma_commit(dq_ready);
+        for (int k = 0; k < 2; ++k) umma_f16(tmem + sb * BWD_NT, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S32, k);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) umma_f16(tdP + sb * BWD_NT, desc_k64(adO, k), desc_k64(aV, k), IDESC_S32, k);
+        umma_commit(&bars->a_ready[sb]);
+        if (j >= 1) issue_dq(j - 1);
       }
+      issue_dq(T - 1);
+      umma_commit(&bars->done);
     }
     __syncwarp();
-  } else {
+  } else if ((warp & 3) < nact) {
     const int qd = warp & 3, row = qd * 32 + lane;
     const int qi = q0 + row;
     const bool q_in = qi < p.Lq;
     const bool mq = q_in ? (p.mask_q[(int64_t)b * p.Lq + qi] != 0) : false;
+    const bool warp_all_mq = __all_sync(0xffffffffu, mq);
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-    float delta = 0.f, lse2 = 0.f;
+    float delta = 0.f, nlse2 = -INFINITY;               // rows past Lq: p = exp2(-inf) = 0
     if (q_in) {
       const __nv_bfloat16* orow = p.out + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH;
       const __nv_bfloat16* dorow = p.dout + ((int64_t)b * p.Lq + qi) * p.lddo + h * DH;
@@ -354,255 +450,227 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
         delta += a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
       }
       const int64_t li = ((int64_t)b * p.H + h) * p.Lq + qi;
-      lse2 = p.lse[li] * kLog2e;
+      nlse2 = -p.lse[li] * kLog2e;
       p.delta[li] = delta;
     }
-    int blk_phase = 0;
-    for (int j = 0; j < ntiles; ++j) {
-      const int blk = j < ntile[0] ? 0 : 1, kt = blk ? j - ntile[0] : j;
-      const int k0 = kt * NKT, nvalid = min(NKT, p.Lk[blk] - k0);
-      const int64_t mbase = (int64_t)b * p.Lk[blk] + k0;
-      const uint32_t w[2] = {mask_bits32(p.mask_k[blk], mbase, 0, nvalid, lane), mask_bits32(p.mask_k[blk], mbase, 32, nvalid, lane)};
-      mbar_wait(sdp_ready, j & 1);
+    const float nds = -delta * p.scale;                  // dS = P * (dP * scale + nds)
+    for (int j = 0; j < T; ++j) {
+      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, sb = j & 1;
+      const int k0 = kt * BWD_NT, nvalid = min(BWD_NT, (blk ? p.Lk[1] : p.Lk[0]) - k0);
+      const uint32_t wv = mask_bits32((blk ? p.mask_k[1] : p.mask_k[0]), (int64_t)b * (blk ? p.Lk[1] : p.Lk[0]) + k0, 0, nvalid, lane);
+      mbar_wait(&bars->a_ready[sb], (j >> 1) & 1);
       tcgen05_fence_after();
-      if (j > 0) mbar_wait(ds_free, (j - 1) & 1);   // the previous dQ MMA has finished reading sdS
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t pk[16];
-        if (hf * 32 < nvalid) {   // warp-uniform: tcgen05.ld is .sync.aligned
-          uint32_t rs[32], rp[32];
-          tmem_ld_32x32(tS + lane_addr + hf * 32, rs);
-          tmem_ld_32x32(tdP + lane_addr + hf * 32, rp);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float ds[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int cc = c + e;
-              const bool valid = mq && (((w[hf] >> cc) & 1u) != 0);   // overwritten (masked) logits pass no gradient
-              const float pr = ex2(__uint_as_float(rs[cc]) * p.scale_log2 - lse2);
-              ds[e] = valid ? pr * (__uint_as_float(rp[cc]) - delta) * p.scale : 0.f;
-            }
-            pk[c >> 1] = pack_bf16(ds[0], ds[1]);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) pk[c] = 0u;
-        }
-        write_row_sw128_half(sdS, row, hf, pk);
-      }
+      uint32_t rs[32], rp[32];
+      tmem_ld_32x32(tmem + lane_addr + sb * BWD_NT, rs);
+      tmem_ld_32x32(tdP + lane_addr + sb * BWD_NT, rp);
+      tmem_ld_wait();
       tcgen05_fence_before();
-      fence_proxy_async_smem();
-      mbar_arrive(ds_ready);
-      if (kt == ntile[blk] - 1) {  // dQ of this key block is complete
-        mbar_wait(dq_ready, blk_phase);
-        blk_phase ^= 1;
-        tcgen05_fence_after();
-        uint32_t r[32];
-        tmem_ld_32x32(tdQ + lane_addr, r);
-        tmem_ld_wait();
-        if (q_in && p.dq[blk] != nullptr) {
-          __nv_bfloat16* dst = p.dq[blk] + ((int64_t)b * p.Lq + qi) * p.lddq[blk] + h * DH;
+      mbar_arrive(&bars->s_free[sb]);
+      uint32_t pk[16];
+      if (warp_all_mq && wv == 0xffffffffu) {
 #pragma unroll
-          for (int d = 0; d < DH; d += 8) {
-            *reinterpret_cast<uint4*>(dst + d) =
-                make_uint4(pack_bf16(__uint_as_float(r[d]), __uint_as_float(r[d + 1])), pack_bf16(__uint_as_float(r[d + 2]), __uint_as_float(r[d + 3])),
-                           pack_bf16(__uint_as_float(r[d + 4]), __uint_as_float(r[d + 5])), pack_bf16(__uint_as_float(r[d + 6]), __uint_as_float(r[d + 7])));
-          }
+        for (int c = 0; c < 32; c += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(rs[c]), p.scale_log2, nlse2)), p1 = ex2(fmaf(__uint_as_float(rs[c + 1]), p.scale_log2, nlse2));
+          pk[c >> 1] = pack_bf16x2(p0 * fmaf(__uint_as_float(rp[c]), p.scale, nds), p1 * fmaf(__uint_as_float(rp[c + 1]), p.scale, nds));
         }
-        tcgen05_fence_before();
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float ds[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int cc = c + t;
+            const bool valid = mq && (((wv >> cc) & 1u) != 0);   // overwritten (masked) logits pass no gradient
+            const float pr = ex2(fmaf(__uint_as_float(rs[cc]), p.scale_log2, nlse2));
+            ds[t] = valid ? pr * fmaf(__uint_as_float(rp[cc]), p.scale, nds) : 0.f;
+          }
+          pk[c >> 1] = pack_bf16x2(ds[0], ds[1]);
+        }
       }
+      if (j >= 2) mbar_wait(&bars->p_free[sb], ((j >> 1) - 1) & 1);
+      write_row_sw64(sdS + sb * TILE128, row, pk);
+      fence_proxy_async_smem();
+      mbar_arrive(&bars->p_ready[sb]);
+    }
+    mbar_wait(&bars->done, 0);
+    tcgen05_fence_after();
+    uint32_t ra[32], rb[32];
+    tmem_ld_32x32(tdQ + lane_addr, ra);
+    if (p.nblk > 1) tmem_ld_32x32(tdQ + DH + lane_addr, rb);
+    tmem_ld_wait();
+    if (q_in) {
+      if (p.dq[0] != nullptr) store_row32_bf16(p.dq[0] + ((int64_t)b * p.Lq + qi) * p.lddq[0] + h * DH, ra, 1.0f);
+      if (p.nblk > 1 && p.dq[1] != nullptr) store_row32_bf16(p.dq[1] + ((int64_t)b * p.Lq + qi) * p.lddq[1] + h * DH, rb, 1.0f);
     }
   }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
-  }
+  tmem_teardown(tmem, warp);
 }
 
 // ====================================================================================== backward: dK, dV
-// CTA = 128 keys of one key block; loops over 64-query tiles.  thread = key row.
-// TMEM: S^T [0,64) | dP^T [64,128) | dK [128,160) | dV [160,192)  -> 256 columns
+// CTA = 128 keys of one key block; loops over 32-query tiles.  thread = key row.
+// smem: K 8 KB | V 8 KB | Q,dO ring [4][2 KB + 2 KB] | P^T [2][8 KB] | dS^T [2][8 KB] | per-query vectors | barriers
+// TMEM: S^T[2] @0,32 | dP^T[2] @64,96 | dK @128 | dV @160
+struct QVec {
+  float nlse2[BWD_NT];     // -lse * log2(e)          (+/-inf tricks: -inf for queries past Lq => P = 0)
+  float nds[BWD_NT];       // -delta * scale
+  uint32_t mq;             // valid-query bits
+  uint32_t pad[3];
+};
+
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* sK = smem;                        // 8 KB (128 keys)
-  uint8_t* sV = sK + TILE128;                // 8 KB
-  uint8_t* sQdO = sV + TILE128;              // [2 stages][Q 4 KB | dO 4 KB]
-  uint8_t* sPT = sQdO + 2 * 2 * TILE64;      // 16 KB
-  uint8_t* sdST = sPT + PBYTES;              // 16 KB
-  float* sLse = reinterpret_cast<float*>(sdST + PBYTES);   // [2][64]
-  float* sDelta = sLse + 2 * NKT;                          // [2][64]
-  uint32_t* sMq = reinterpret_cast<uint32_t*>(sDelta + 2 * NKT);  // [2][2] bit masks (valid & in-range queries)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMq + 4);
-  uint64_t* bar_kv = bars;
-  uint64_t* full_q = bars + 1;
-  uint64_t* empty_q = bars + 3;
-  uint64_t* sdp_ready = bars + 5;
-  uint64_t* pds_ready = bars + 6;
-  uint64_t* pds_free = bars + 7;
-  uint64_t* dkv_ready = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + TILE128;
+  uint8_t* sQdO = sV + TILE128;
+  uint8_t* sPT = sQdO + KV_STAGES * 2 * TILE32;
+  uint8_t* sdST = sPT + 2 * TILE128;
+  QVec* qv = reinterpret_cast<QVec*>(sdST + 2 * TILE128);
+  Bars* bars = reinterpret_cast<Bars*>(qv + KV_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * QT;
   const int blk = p.which;
-  const int Lk = p.Lk[blk];
-  const int nq = (p.Lq + NKT - 1) / NKT;
+  const int Lk = (blk ? p.Lk[1] : p.Lk[0]);
+  const int T = (p.Lq + BWD_NT - 1) / BWD_NT;
+  const int rows_valid = min(QT, Lk - k0);
+  const int nact = (rows_valid + 31) >> 5;
 
-  if (warp == 0 && lane == 0) {
-    mbar_init(bar_kv, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&full_q[s], 1); mbar_init(&empty_q[s], 1); }
-    mbar_init(sdp_ready, 1); mbar_init(pds_ready, 128); mbar_init(pds_free, 1); mbar_init(dkv_ready, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tST = tmem, tdPT = tmem + NKT, tdK = tmem + 2 * NKT, tdV = tmem + 2 * NKT + DH;
+  if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
+  const uint32_t tmem = tmem_setup(bars, warp);
+  const uint32_t tdPT = tmem + 2 * BWD_NT, tdK = tmem + 4 * BWD_NT, tdV = tmem + 4 * BWD_NT + DH;
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(bar_kv, 2 * TILE128);
-      tma_load_2d(&tmK, bar_kv, sK, h * DH, b * Lk + k0);
-      tma_load_2d(&tmV, bar_kv, sV, h * DH, b * Lk + k0);
-      for (int i = 0; i < nq; ++i) {
-        const int s = i & 1;
-        mbar_wait(&empty_q[s], ((i >> 1) & 1) ^ 1);
-        mbar_expect_tx(&full_q[s], 2 * TILE64);
-        uint8_t* dst = sQdO + s * 2 * TILE64;
-        const int row = b * p.Lq + i * NKT;
-        tma_load_2d(&tmQ, &full_q[s], dst, h * DH, row);
-        tma_load_2d(&tmdO, &full_q[s], dst + TILE64, h * DH, row);
+      mbar_expect_tx(&bars->once, 2 * TILE128);
+      tma_load_2d(&tmK, &bars->once, sK, h * DH, b * Lk + k0);
+      tma_load_2d(&tmV, &bars->once, sV, h * DH, b * Lk + k0);
+    }
+    for (int i = 0; i < T; ++i) {
+      const int st = i & (KV_STAGES - 1);
+      if (lane == 0) mbar_wait(&bars->kv_empty[st], ((i / KV_STAGES) & 1) ^ 1);
+      __syncwarp();
+      // per-query vectors of this tile (one query per lane), published with the TMA barrier below
+      const int qi = i * BWD_NT + lane;
+      const bool in = qi < p.Lq;
+      const int64_t li = ((int64_t)b * p.H + h) * p.Lq + qi;
+      qv[st].nlse2[lane] = in ? -p.lse[li] * kLog2e : -INFINITY;
+      qv[st].nds[lane] = in ? -p.delta[li] * p.scale : 0.f;
+      const uint32_t mqb = __ballot_sync(0xffffffffu, in && p.mask_q[(int64_t)b * p.Lq + (in ? qi : 0)] != 0);
+      if (lane == 0) qv[st].mq = mqb;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
+        uint8_t* dst = sQdO + st * 2 * TILE32;
+        const int row = b * p.Lq + i * BWD_NT;
+        tma_load_2d(&tmQ, &bars->kv_full[st], dst, h * DH, row);
+        tma_load_2d(&tmdO, &bars->kv_full[st], dst + TILE32, h * DH, row);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      mbar_wait(bar_kv, 0);
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aPT = smem_u32(sPT), adST = smem_u32(sdST);
-      for (int i = 0; i < nq; ++i) {
-        const int s = i & 1;
-        mbar_wait(&full_q[s], (i >> 1) & 1);
+      mbar_wait(&bars->once, 0);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+      auto issue_dkv = [&](int u) {
+        const int pb = u & 1, st = u & (KV_STAGES - 1);
+        mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
         tcgen05_fence_after();
-        const uint32_t aQ = smem_u32(sQdO + s * 2 * TILE64), adO = aQ + TILE64;
+        const uint32_t aPT = smem_u32(sPT + pb * TILE128), adST = smem_u32(sdST + pb * TILE128);
+        const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE32), adO = aQ + TILE32;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tST, desc_k64(aK, k), desc_k64(aQ, k), IDESC_S, k);      // S^T  = K Q^T
+        for (int k = 0; k < 2; ++k) umma_f16(tdV, desc_k64(aPT, k), desc_mn64(adO, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);   // dV += P^T dO
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tdPT, desc_k64(aV, k), desc_k64(adO, k), IDESC_S, k);    // dP^T = V dO^T
-        umma_commit(sdp_ready);
-        mbar_wait(pds_ready, i & 1);
+        for (int k = 0; k < 2; ++k) umma_f16(tdK, desc_k64(adST, k), desc_mn64(aQ, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);   // dK += dS^T Q
+        umma_commit(&bars->p_free[pb]);
+        umma_commit(&bars->kv_empty[st]);
+      };
+      for (int i = 0; i < T; ++i) {
+        const int st = i & (KV_STAGES - 1), sb = i & 1;
+        mbar_wait(&bars->kv_full[st], (i / KV_STAGES) & 1);
+        if (i >= 2) mbar_wait(&bars->s_free[sb], ((i >> 1) - 1) & 1);
         tcgen05_fence_after();
+        const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE32), adO = aQ + TILE32;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tdV, desc_p128(aPT, k), desc_mn64(adO, k), IDESC_O, (i > 0 || k > 0) ? 1u : 0u);  // dV += P^T dO
+        for (int k = 0; k < 2; ++k) umma_f16(tmem + sb * BWD_NT, desc_k64(aK, k), desc_k64(aQ, k), IDESC_S32, k);      // S^T  = K Q^T
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tdK, desc_p128(adST, k), desc_mn64(aQ, k), IDESC_O, (i > 0 || k > 0) ? 1u : 0u);  // dK += dS^T Q
-        umma_commit(pds_free);
-        umma_commit(&empty_q[s]);
+        for (int k = 0; k < 2; ++k) umma_f16(tdPT + sb * BWD_NT, desc_k64(aV, k), desc_k64(adO, k), IDESC_S32, k);    // dP^T = V dO^T
+        umma_commit(&bars->a_ready[sb]);
+        if (i >= 1) issue_dkv(i - 1);
       }
-      umma_commit(dkv_ready);
+      issue_dkv(T - 1);
+      umma_commit(&bars->done);
     }
     __syncwarp();
-  } else {
+  } else if ((warp & 3) < nact) {
     const int qd = warp & 3, row = qd * 32 + lane;
     const int kj = k0 + row;
     const bool k_in = kj < Lk;
-    const bool mk = k_in ? (p.mask_k[blk][(int64_t)b * Lk + kj] != 0) : false;
+    const bool mk = k_in ? ((blk ? p.mask_k[1] : p.mask_k[0])[(int64_t)b * Lk + kj] != 0) : false;
+    const bool warp_all_mk = __all_sync(0xffffffffu, mk);
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-    const int st = threadIdx.x - 64;   // 0..127 among the softmax threads
-    for (int i = 0; i < nq; ++i) {
-      const int s = i & 1, qbase = i * NKT, nvalid = min(NKT, p.Lq - qbase);
-      // per-query vectors of this tile (stage s is free: its previous user, tile i-2, was consumed before pds_ready(i-2))
-      if (st < NKT) {
-        const bool in = st < nvalid;
-        const int64_t li = ((int64_t)b * p.H + h) * p.Lq + qbase + st;
-        sLse[s * NKT + st] = in ? p.lse[li] * kLog2e : 0.f;
-        sDelta[s * NKT + st] = in ? p.delta[li] : 0.f;
-      }
-      if (warp == 2) {
-        const uint32_t w0 = mask_bits32(p.mask_q, (int64_t)b * p.Lq + qbase, 0, nvalid, lane);
-        const uint32_t w1 = mask_bits32(p.mask_q, (int64_t)b * p.Lq + qbase, 32, nvalid, lane);
-        if (lane == 0) { sMq[s * 2] = w0; sMq[s * 2 + 1] = w1; }
-      }
-      named_bar_sync(1, 128);
-      const uint32_t wq[2] = {sMq[s * 2], sMq[s * 2 + 1]};
-      mbar_wait(sdp_ready, i & 1);
+    for (int i = 0; i < T; ++i) {
+      const int st = i & (KV_STAGES - 1), sb = i & 1;
+      mbar_wait(&bars->a_ready[sb], (i >> 1) & 1);
       tcgen05_fence_after();
-      if (i > 0) mbar_wait(pds_free, (i - 1) & 1);
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t pp[16], pd[16];
-        if (hf * 32 < nvalid) {   // warp-uniform: tcgen05.ld is .sync.aligned
-          uint32_t rs[32], rp[32];
-          tmem_ld_32x32(tST + lane_addr + hf * 32, rs);
-          tmem_ld_32x32(tdPT + lane_addr + hf * 32, rp);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float pr[2], ds[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int cc = c + e, qc = hf * 32 + cc;
-              const bool valid = mk && (((wq[hf] >> cc) & 1u) != 0);
-              const float x = valid ? __uint_as_float(rs[cc]) * p.scale_log2 : p.fill_log2;
-              pr[e] = (qc < nvalid) ? ex2(x - sLse[s * NKT + qc]) : 0.f;
-              ds[e] = valid ? pr[e] * (__uint_as_float(rp[cc]) - sDelta[s * NKT + qc]) * p.scale : 0.f;
-            }
-            pp[c >> 1] = pack_bf16(pr[0], pr[1]);
-            pd[c >> 1] = pack_bf16(ds[0], ds[1]);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) { pp[c] = 0u; pd[c] = 0u; }
-        }
-        write_row_sw128_half(sPT, row, hf, pp);
-        write_row_sw128_half(sdST, row, hf, pd);
-      }
+      uint32_t rs[32], rp[32];
+      tmem_ld_32x32(tmem + lane_addr + sb * BWD_NT, rs);
+      tmem_ld_32x32(tdPT + lane_addr + sb * BWD_NT, rp);
+      tmem_ld_wait();
       tcgen05_fence_before();
+      mbar_arrive(&bars->s_free[sb]);
+      mbar_wait(&bars->kv_full[st], (i / KV_STAGES) & 1);   // acquire the loader's per-query vectors (already complete)
+      const QVec& v = qv[st];
+      const uint32_t wq = v.mq;
+      uint32_t pp[16], pd[16];
+      if (warp_all_mk && wq == 0xffffffffu) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 nl = *reinterpret_cast<const float4*>(&v.nlse2[c]);
+          const float4 nd = *reinterpret_cast<const float4*>(&v.nds[c]);
+          const float p0 = ex2(fmaf(__uint_as_float(rs[c]), p.scale_log2, nl.x)), p1 = ex2(fmaf(__uint_as_float(rs[c + 1]), p.scale_log2, nl.y));
+          const float p2 = ex2(fmaf(__uint_as_float(rs[c + 2]), p.scale_log2, nl.z)), p3 = ex2(fmaf(__uint_as_float(rs[c + 3]), p.scale_log2, nl.w));
+          pp[c >> 1] = pack_bf16x2(p0, p1);
+          pp[(c >> 1) + 1] = pack_bf16x2(p2, p3);
+          pd[c >> 1] = pack_bf16x2(p0 * fmaf(__uint_as_float(rp[c]), p.scale, nd.x), p1 * fmaf(__uint_as_float(rp[c + 1]), p.scale, nd.y));
+          pd[(c >> 1) + 1] = pack_bf16x2(p2 * fmaf(__uint_as_float(rp[c + 2]), p.scale, nd.z), p3 * fmaf(__uint_as_float(rp[c + 3]), p.scale, nd.w));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float pr[2], ds[2];
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int cc = c + t;
+            const bool valid = mk && (((wq >> cc) & 1u) != 0);
+            const float x = valid ? __uint_as_float(rs[cc]) * p.scale_log2 : p.fill_log2;
+            pr[t] = ex2(x + v.nlse2[cc]);                // queries past Lq: nlse2 = -inf => 0
+            ds[t] = valid ? pr[t] * fmaf(__uint_as_float(rp[cc]), p.scale, v.nds[cc]) : 0.f;
+          }
+          pp[c >> 1] = pack_bf16x2(pr[0], pr[1]);
+          pd[c >> 1] = pack_bf16x2(ds[0], ds[1]);
+        }
+      }
+      if (i >= 2) mbar_wait(&bars->p_free[sb], ((i >> 1) - 1) & 1);
+      write_row_sw64(sPT + sb * TILE128, row, pp);
+      write_row_sw64(sdST + sb * TILE128, row, pd);
       fence_proxy_async_smem();
-      mbar_arrive(pds_ready);
+      mbar_arrive(&bars->p_ready[sb]);
     }
-    mbar_wait(dkv_ready, 0);
+    mbar_wait(&bars->done, 0);
     tcgen05_fence_after();
     uint32_t rk[32], rv[32];
     tmem_ld_32x32(tdK + lane_addr, rk);
     tmem_ld_32x32(tdV + lane_addr, rv);
     tmem_ld_wait();
     if (k_in) {
-      if (p.dk != nullptr) {
-        __nv_bfloat16* dst = p.dk + ((int64_t)b * Lk + kj) * p.lddk + h * DH;
-#pragma unroll
-        for (int d = 0; d < DH; d += 8)
-          *reinterpret_cast<uint4*>(dst + d) =
-              make_uint4(pack_bf16(__uint_as_float(rk[d]), __uint_as_float(rk[d + 1])), pack_bf16(__uint_as_float(rk[d + 2]), __uint_as_float(rk[d + 3])),
-                         pack_bf16(__uint_as_float(rk[d + 4]), __uint_as_float(rk[d + 5])), pack_bf16(__uint_as_float(rk[d + 6]), __uint_as_float(rk[d + 7])));
-      }
-      if (p.dv != nullptr) {
-        __nv_bfloat16* dst = p.dv + ((int64_t)b * Lk + kj) * p.lddv + h * DH;
-#pragma unroll
-        for (int d = 0; d < DH; d += 8)
-          *reinterpret_cast<uint4*>(dst + d) =
-              make_uint4(pack_bf16(__uint_as_float(rv[d]), __uint_as_float(rv[d + 1])), pack_bf16(__uint_as_float(rv[d + 2]), __uint_as_float(rv[d + 3])),
-                         pack_bf16(__uint_as_float(rv[d + 4]), __uint_as_float(rv[d + 5])), pack_bf16(__uint_as_float(rv[d + 6]), __uint_as_float(rv[d + 7])));
-      }
+      if (p.dk != nullptr) store_row32_bf16(p.dk + ((int64_t)b * Lk + kj) * p.lddk + h * DH, rk, 1.0f);
+      if (p.dv != nullptr) store_row32_bf16(p.dv + ((int64_t)b * Lk + kj) * p.lddv + h * DH, rv, 1.0f);
     }
   }
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
-  }
+  tmem_teardown(tmem, warp);
 }
 
 // ====================================================================================== host
@@ -643,25 +711,27 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
   if (a->nblk == 1) { p.Lk[1] = 0; p.mask_k[1] = p.mask_k[0]; }
   const int64_t q_rows = (int64_t)a->B * a->Lq;
   static bool cfg_done[3] = {false, false, false};
+  const size_t bar_bytes = sizeof(Bars) + 1024 /*align*/;
   if (kind == 0 || kind == 1) {
+    const uint32_t kbox = kind == 0 ? FWD_NT : BWD_NT;
     CUtensorMap mQ[2], mK[2], mV[2], mdO;
     for (int i = 0; i < 2; ++i) {
       const mmi_attn_block& s = a->blk[i < a->nblk ? i : 0];
       const int64_t k_rows = (int64_t)a->B * s.Lk;
       if (!map_rows(s.q, s.ldq, q_rows, width, QT, &mQ[i])) return MMI_ECUDA;
-      if (!map_rows(s.k, s.ldk, k_rows, width, NKT, &mK[i])) return MMI_ECUDA;
-      if (!map_rows(s.v, s.ldv, k_rows, width, NKT, &mV[i])) return MMI_ECUDA;
+      if (!map_rows(s.k, s.ldk, k_rows, width, kbox, &mK[i])) return MMI_ECUDA;
+      if (!map_rows(s.v, s.ldv, k_rows, width, kbox, &mV[i])) return MMI_ECUDA;
     }
     dim3 grid((a->Lq + QT - 1) / QT, a->H, a->B);
     if (kind == 0) {
-      const size_t smem = 2 * TILE128 + 4 * TILE64 + PBYTES + 256 + 1024;
+      const size_t smem = 2 * TILE128 + KV_STAGES * 2 * TILE64 + 2 * PBYTES + bar_bytes;
       if (!cfg_done[0]) { int rc = set_smem(attn_fwd_tc_kernel, smem); if (rc) return rc; cfg_done[0] = true; }
       attn_fwd_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
     } else {
       MMI_CHECK_ARG(a->dout && a->delta, "attn_tc bwd: null dout/delta");
       MMI_CHECK_ARG(a->lddo % 8 == 0, "attn_tc: lddo must be a multiple of 8");
       if (!map_rows(a->dout, a->lddo, q_rows, width, QT, &mdO)) return MMI_ECUDA;
-      const size_t smem = 3 * TILE128 + 4 * TILE64 + PBYTES + 256 + 1024;
+      const size_t smem = 3 * TILE128 + KV_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes;
       if (!cfg_done[1]) { int rc = set_smem(attn_bwd_dq_tc_kernel, smem); if (rc) return rc; cfg_done[1] = true; }
       attn_bwd_dq_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p);
     }
@@ -674,12 +744,12 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     p.dv = reinterpret_cast<__nv_bfloat16*>(s.dv); p.lddv = s.lddv;
     const int64_t k_rows = (int64_t)a->B * s.Lk;
     CUtensorMap mQ, mK, mV, mdO;
-    if (!map_rows(s.q, s.ldq, q_rows, width, NKT, &mQ)) return MMI_ECUDA;
-    if (!map_rows(a->dout, a->lddo, q_rows, width, NKT, &mdO)) return MMI_ECUDA;
+    if (!map_rows(s.q, s.ldq, q_rows, width, BWD_NT, &mQ)) return MMI_ECUDA;
+    if (!map_rows(a->dout, a->lddo, q_rows, width, BWD_NT, &mdO)) return MMI_ECUDA;
     if (!map_rows(s.k, s.ldk, k_rows, width, QT, &mK)) return MMI_ECUDA;
     if (!map_rows(s.v, s.ldv, k_rows, width, QT, &mV)) return MMI_ECUDA;
     dim3 grid((s.Lk + QT - 1) / QT, a->H, a->B);
-    const size_t smem = 2 * TILE128 + 4 * TILE64 + 2 * PBYTES + 4 * NKT * 4 + 16 + 256 + 1024;
+    const size_t smem = 2 * TILE128 + KV_STAGES * 2 * TILE32 + 4 * TILE128 + KV_STAGES * sizeof(QVec) + bar_bytes;
     if (!cfg_done[2]) { int rc = set_smem(attn_bwd_dkv_tc_kernel, smem); if (rc) return rc; cfg_done[2] = true; }
     attn_bwd_dkv_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ, mK, mV, mdO, p);
   }

@@ -191,6 +191,16 @@ def _ref_attention(qa, ka, va, mka, qb, kb, vb, mkb, mq, H):
     (32, torch.bfloat16, "tc", (3, 2, 70, 40, 150)), (32, torch.bfloat16, "tc", (2, 16, 500, 40, 500)),
     (32, torch.bfloat16, "tc", (2, 16, 40, 40, 500)), (32, torch.bfloat16, "tc", (1, 4, 129, 64, 65))])
 def test_attention_fwd_bwd(dev, dh, dtype, impl, shape):
+    _check_attention(dev, dh, dtype, impl, shape, ragged=True)
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 500, 40, 500), (2, 4, 40, 40, 100), (1, 2, 128, 64, 256), (1, 2, 300, 33, 1030)])
+def test_attention_tc_unmasked_fast_path(dev, shape):
+    """Full histories (no masked key, no padded query): the mask-free fast path of the tcgen05 kernels."""
+    _check_attention(dev, 32, torch.bfloat16, "tc", shape, ragged=False)
+
+
+def _check_attention(dev, dh, dtype, impl, shape, ragged):
     from segmminterest_b200 import ops
     torch.manual_seed(4)
     B, H, Lq, La, Lb = shape
@@ -198,7 +208,7 @@ def test_attention_fwd_bwd(dev, dh, dtype, impl, shape):
     impl = ops.IMPL_TC if impl == "tc" else ops.IMPL_SIMT
 
     def mk(L):
-        n = torch.randint(1, L + 1, (B,))
+        n = torch.randint(1, L + 1, (B,)) if ragged else torch.full((B,), L)
         return (torch.arange(L)[None] < n[:, None])
 
     mq, mka, mkb = mk(Lq), mk(La), mk(Lb)

@@ -91,6 +91,22 @@ __device__ __forceinline__ uint32_t range_bits32(int off, int count) {   // bit 
   return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u));
 }
 
+// Key-validity bit words of every key tile of the CTA, built ONCE (all warps, before the role split) so that the
+// softmax loop reads them from shared memory instead of paying a global-load latency per tile.
+// words_per_tile = tile_cols / 32; word w of tile j covers keys [j_k0 + 32 w, +32); bits past Lk are 0.
+template <int TILE_COLS>
+__device__ __forceinline__ void build_key_bits(uint32_t* kb, const AttnTcParams& p, int b, int nt0, int T, int warp, int lane, int nwarps) {
+  constexpr int WPT = TILE_COLS / 32;
+  for (int w = warp; w < T * WPT; w += nwarps) {
+    const int j = w / WPT, sub = w % WPT;
+    const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
+    const int Lk = blk ? p.Lk[1] : p.Lk[0];
+    const int k0 = kt * TILE_COLS + sub * 32;
+    const uint32_t bits = mask_bits32(blk ? p.mask_k[1] : p.mask_k[0], (int64_t)b * Lk, k0, Lk, lane);
+    if (lane == 0) kb[w] = bits;
+  }
+}
+
 constexpr uint32_t IDESC_S64 = make_idesc(QT, FWD_NT, false, false);   // 128 x 64, A/B K-major
 constexpr uint32_t IDESC_S32 = make_idesc(QT, BWD_NT, false, false);   // 128 x 32, A/B K-major
 constexpr uint32_t IDESC_O = make_idesc(QT, DH, false, true);          // 128 x 32, A K-major, B MN-major
@@ -162,6 +178,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
   uint8_t* sKV = sQ + 2 * TILE128;
   uint8_t* sP = sKV + KV_STAGES * 2 * TILE64;
   Bars* bars = reinterpret_cast<Bars*>(sP + 2 * PBYTES);
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(bars + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
@@ -171,6 +188,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
   const int nact = (rows_valid + 31) >> 5;                  // softmax warps with at least one real query
 
   if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
+  build_key_bits<FWD_NT>(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
   const uint32_t tmem = tmem_setup(bars, warp);
   const uint32_t tO = tmem + 2 * FWD_NT;
 
@@ -234,8 +252,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
     for (int j = 0; j < T; ++j) {
       const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, sb = j & 1;
       const int k0 = kt * FWD_NT, nvalid = min(FWD_NT, (blk ? p.Lk[1] : p.Lk[0]) - k0);
-      const int64_t mbase = (int64_t)b * (blk ? p.Lk[1] : p.Lk[0]) + k0;
-      const uint32_t wv[2] = {mask_bits32((blk ? p.mask_k[1] : p.mask_k[0]), mbase, 0, nvalid, lane), mask_bits32((blk ? p.mask_k[1] : p.mask_k[0]), mbase, 32, nvalid, lane)};
+      const uint32_t wv[2] = {kbits[2 * j], kbits[2 * j + 1]};
       const uint32_t wr[2] = {range_bits32(0, nvalid), range_bits32(32, nvalid)};
       any_masked |= ((wr[0] & ~wv[0]) | (wr[1] & ~wv[1])) != 0u;
       mbar_wait(&bars->a_ready[sb], (j >> 1) & 1);
@@ -278,8 +295,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
     for (int j = 0; j < T; ++j) {
       const int jj = T + j, blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, sb = jj & 1, pb = j & 1;
       const int k0 = kt * FWD_NT, nvalid = min(FWD_NT, (blk ? p.Lk[1] : p.Lk[0]) - k0);
-      const int64_t mbase = (int64_t)b * (blk ? p.Lk[1] : p.Lk[0]) + k0;
-      const uint32_t wv[2] = {mask_bits32((blk ? p.mask_k[1] : p.mask_k[0]), mbase, 0, nvalid, lane), mask_bits32((blk ? p.mask_k[1] : p.mask_k[0]), mbase, 32, nvalid, lane)};
+      const uint32_t wv[2] = {kbits[2 * j], kbits[2 * j + 1]};
       const uint32_t wr[2] = {range_bits32(0, nvalid), range_bits32(32, nvalid)};
       mbar_wait(&bars->a_ready[sb], (jj >> 1) & 1);
       tcgen05_fence_after();
@@ -373,6 +389,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
   uint8_t* sKV = sdO + TILE128;
   uint8_t* sdS = sKV + KV_STAGES * 2 * TILE32;
   Bars* bars = reinterpret_cast<Bars*>(sdS + 2 * TILE128);
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(bars + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
@@ -382,6 +399,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
   const int nact = (rows_valid + 31) >> 5;
 
   if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
+  build_key_bits<BWD_NT>(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
   const uint32_t tmem = tmem_setup(bars, warp);
   const uint32_t tdP = tmem + 2 * BWD_NT, tdQ = tmem + 4 * BWD_NT;
 
@@ -455,9 +473,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
     }
     const float nds = -delta * p.scale;                  // dS = P * (dP * scale + nds)
     for (int j = 0; j < T; ++j) {
-      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, sb = j & 1;
-      const int k0 = kt * BWD_NT, nvalid = min(BWD_NT, (blk ? p.Lk[1] : p.Lk[0]) - k0);
-      const uint32_t wv = mask_bits32((blk ? p.mask_k[1] : p.mask_k[0]), (int64_t)b * (blk ? p.Lk[1] : p.Lk[0]) + k0, 0, nvalid, lane);
+      const int sb = j & 1;
+      const uint32_t wv = kbits[j];
       mbar_wait(&bars->a_ready[sb], (j >> 1) & 1);
       tcgen05_fence_after();
       uint32_t rs[32], rp[32];
@@ -548,17 +565,28 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tma_load_2d(&tmK, &bars->once, sK, h * DH, b * Lk + k0);
       tma_load_2d(&tmV, &bars->once, sV, h * DH, b * Lk + k0);
     }
+    // per-query vectors (one query per lane) are fetched one tile AHEAD so that their global-load latency
+    // overlaps the wait for a free stage instead of pacing the whole pipeline
+    float lse_n = 0.f, delta_n = 0.f;
+    uint8_t mq_n = 0;
+    auto fetch = [&](int i) {
+      const int qi = i * BWD_NT + lane;
+      if (qi < p.Lq) {
+        const int64_t li = ((int64_t)b * p.H + h) * p.Lq + qi;
+        lse_n = p.lse[li]; delta_n = p.delta[li]; mq_n = p.mask_q[(int64_t)b * p.Lq + qi];
+      } else { lse_n = INFINITY; delta_n = 0.f; mq_n = 0; }
+    };
+    fetch(0);
     for (int i = 0; i < T; ++i) {
       const int st = i & (KV_STAGES - 1);
+      const float lse_c = lse_n, delta_c = delta_n;
+      const bool mq_c = mq_n != 0;
+      if (i + 1 < T) fetch(i + 1);
       if (lane == 0) mbar_wait(&bars->kv_empty[st], ((i / KV_STAGES) & 1) ^ 1);
       __syncwarp();
-      // per-query vectors of this tile (one query per lane), published with the TMA barrier below
-      const int qi = i * BWD_NT + lane;
-      const bool in = qi < p.Lq;
-      const int64_t li = ((int64_t)b * p.H + h) * p.Lq + qi;
-      qv[st].nlse2[lane] = in ? -p.lse[li] * kLog2e : -INFINITY;
-      qv[st].nds[lane] = in ? -p.delta[li] * p.scale : 0.f;
-      const uint32_t mqb = __ballot_sync(0xffffffffu, in && p.mask_q[(int64_t)b * p.Lq + (in ? qi : 0)] != 0);
+      qv[st].nlse2[lane] = -lse_c * kLog2e;              // queries past Lq: -inf => P = 0
+      qv[st].nds[lane] = -delta_c * p.scale;
+      const uint32_t mqb = __ballot_sync(0xffffffffu, mq_c);
       if (lane == 0) qv[st].mq = mqb;
       __syncwarp();
       if (lane == 0) {
@@ -710,7 +738,7 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
   }
   if (a->nblk == 1) { p.Lk[1] = 0; p.mask_k[1] = p.mask_k[0]; }
   const int64_t q_rows = (int64_t)a->B * a->Lq;
-  static bool cfg_done[3] = {false, false, false};
+  static size_t cfg_bytes[3] = {0, 0, 0};   // largest dynamic shared-memory size configured so far, per kernel
   const size_t bar_bytes = sizeof(Bars) + 1024 /*align*/;
   if (kind == 0 || kind == 1) {
     const uint32_t kbox = kind == 0 ? FWD_NT : BWD_NT;
@@ -724,15 +752,17 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     }
     dim3 grid((a->Lq + QT - 1) / QT, a->H, a->B);
     if (kind == 0) {
-      const size_t smem = 2 * TILE128 + KV_STAGES * 2 * TILE64 + 2 * PBYTES + bar_bytes;
-      if (!cfg_done[0]) { int rc = set_smem(attn_fwd_tc_kernel, smem); if (rc) return rc; cfg_done[0] = true; }
+      const size_t T = (a->blk[0].Lk + FWD_NT - 1) / FWD_NT + (a->nblk > 1 ? (a->blk[1].Lk + FWD_NT - 1) / FWD_NT : 0);
+      const size_t smem = 2 * TILE128 + KV_STAGES * 2 * TILE64 + 2 * PBYTES + bar_bytes + T * (FWD_NT / 32) * 4;
+      if (smem > cfg_bytes[0]) { int rc = set_smem(attn_fwd_tc_kernel, smem); if (rc) return rc; cfg_bytes[0] = smem; }
       attn_fwd_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
     } else {
       MMI_CHECK_ARG(a->dout && a->delta, "attn_tc bwd: null dout/delta");
       MMI_CHECK_ARG(a->lddo % 8 == 0, "attn_tc: lddo must be a multiple of 8");
       if (!map_rows(a->dout, a->lddo, q_rows, width, QT, &mdO)) return MMI_ECUDA;
-      const size_t smem = 3 * TILE128 + KV_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes;
-      if (!cfg_done[1]) { int rc = set_smem(attn_bwd_dq_tc_kernel, smem); if (rc) return rc; cfg_done[1] = true; }
+      const size_t T = (a->blk[0].Lk + BWD_NT - 1) / BWD_NT + (a->nblk > 1 ? (a->blk[1].Lk + BWD_NT - 1) / BWD_NT : 0);
+      const size_t smem = 3 * TILE128 + KV_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes + T * 4;
+      if (smem > cfg_bytes[1]) { int rc = set_smem(attn_bwd_dq_tc_kernel, smem); if (rc) return rc; cfg_bytes[1] = smem; }
       attn_bwd_dq_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p);
     }
   } else {
@@ -750,7 +780,7 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     if (!map_rows(s.v, s.ldv, k_rows, width, QT, &mV)) return MMI_ECUDA;
     dim3 grid((s.Lk + QT - 1) / QT, a->H, a->B);
     const size_t smem = 2 * TILE128 + KV_STAGES * 2 * TILE32 + 4 * TILE128 + KV_STAGES * sizeof(QVec) + bar_bytes;
-    if (!cfg_done[2]) { int rc = set_smem(attn_bwd_dkv_tc_kernel, smem); if (rc) return rc; cfg_done[2] = true; }
+    if (smem > cfg_bytes[2]) { int rc = set_smem(attn_bwd_dkv_tc_kernel, smem); if (rc) return rc; cfg_bytes[2] = smem; }
     attn_bwd_dkv_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ, mK, mV, mdO, p);
   }
   MMI_CHECK_LAUNCH();

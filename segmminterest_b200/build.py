@@ -40,6 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                "-Xcompiler", "-fPIC", "-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
+        cmd[1:1] = os.environ.get("MMI_NVCC_EXTRA", "").split()
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for s, p in procs:

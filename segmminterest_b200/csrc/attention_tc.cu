@@ -61,6 +61,15 @@ struct AttnTcParams {
   float fill_log2;    // -10000 * scale * log2(e)
 };
 
+#ifdef MMI_ATTN_TRACE
+// debug build only: clock64 stamps of one CTA (blockIdx.z == gridDim.z / 2, x == 0, y == 0), read back by mmi_debug_trace
+__device__ long long g_trace[8192];
+#define TRACE_ON (blockIdx.z == gridDim.z / 2 && blockIdx.x == 0 && blockIdx.y == 0)
+#define TRACE(slot) do { if (TRACE_ON && lane == 0) g_trace[(slot)] = clock64(); } while (0)
+#else
+#define TRACE(slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -167,8 +176,17 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint3
 }
 
 // ====================================================================================== forward
-// smem: Q [2][8 KB] | K,V ring [4][4 KB + 4 KB] | P [2][16 KB] | barriers
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+// smem: Q [2][8 KB] | K,V ring [4][4 KB + 4 KB] | P [2][16 KB] | barriers | row exchange | key bits
+// 10 warps: 0 TMA, 1 MMA, 2-9 softmax.  Softmax warp w owns TMEM lane quarter (w & 3) -- the hardware rule -- and
+// the 32-column half ((w - 2) >> 2) of every 64-key tile, so a row's max / sum live in two threads and are
+// combined through shared memory once per pass.  Four softmax warps per scheduler (two resident CTAs) hide the
+// TMEM-load, barrier and MUFU latencies that two could not.
+constexpr int FWD_THREADS = 64 + 256;
+struct RowXch { float v[2][QT]; uint32_t f[2][QT]; float l[2][QT]; };
+
+__device__ __forceinline__ void softmax_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+__global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
                    const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
                    const __grid_constant__ CUtensorMap tmVa, const __grid_constant__ CUtensorMap tmVb, const AttnTcParams p) {
@@ -178,108 +196,130 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
   uint8_t* sKV = sQ + 2 * TILE128;
   uint8_t* sP = sKV + KV_STAGES * 2 * TILE64;
   Bars* bars = reinterpret_cast<Bars*>(sP + 2 * PBYTES);
-  uint32_t* kbits = reinterpret_cast<uint32_t*>(bars + 1);
+  RowXch* xch = reinterpret_cast<RowXch*>(bars + 1);
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(xch + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp index in a uniform register
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
   const int nt0 = (p.Lk[0] + FWD_NT - 1) / FWD_NT, nt1 = p.nblk > 1 ? (p.Lk[1] + FWD_NT - 1) / FWD_NT : 0;
   const int T = nt0 + nt1;
   const int rows_valid = min(QT, p.Lq - q0);
-  const int nact = (rows_valid + 31) >> 5;                  // softmax warps with at least one real query
+  const int nact = (rows_valid + 31) >> 5;                  // TMEM lane quarters with at least one real query
 
-  if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
-  build_key_bits<FWD_NT>(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
+  if (warp == 0 && lane == 0) init_bars(bars, 64 * nact);
+  build_key_bits<FWD_NT>(kbits, p, b, nt0, T, warp, lane, FWD_THREADS / 32);
+  if (warp == 4) TRACE(4090);
   const uint32_t tmem = tmem_setup(bars, warp);
   const uint32_t tO = tmem + 2 * FWD_NT;
+  if (warp == 4) TRACE(4091);
 
   if (warp == 0) {
-    if (lane == 0) {
+    // warp-uniform producer loop: all lanes wait for the free stage, one elected lane issues the TMA
+    if (elect_one()) {
       mbar_expect_tx(&bars->once, (p.nblk > 1 ? 2 : 1) * TILE128);
       tma_load_2d(&tmQa, &bars->once, sQ, h * DH, b * p.Lq + q0);
       if (p.nblk > 1) tma_load_2d(&tmQb, &bars->once, sQ + TILE128, h * DH, b * p.Lq + q0);
-      for (int jj = 0; jj < 2 * T; ++jj) {
-        const bool pass2 = jj >= T;
-        const int j = pass2 ? jj - T : jj, blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = jj & (KV_STAGES - 1);
-        mbar_wait(&bars->kv_empty[st], ((jj / KV_STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int jj = 0; jj < 2 * T; ++jj) {
+      const bool pass2 = jj >= T;
+      const int j = pass2 ? jj - T : jj, blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = jj & (KV_STAGES - 1);
+      mbar_wait(&bars->kv_empty[st], ((jj / KV_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&bars->kv_full[st], pass2 ? 2 * TILE64 : TILE64);
         uint8_t* dst = sKV + st * 2 * TILE64;
         const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * FWD_NT;
         tma_load_2d(blk ? &tmKb : &tmKa, &bars->kv_full[st], dst, h * DH, row);
         if (pass2) tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[st], dst + TILE64, h * DH, row);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(&bars->once, 0);
-      auto issue_pv = [&](int u, int st) {               // O += P(u) V(u)
-        const int pb = u & 1;
-        mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
-        tcgen05_fence_after();
+    // warp-uniform MMA loop: all lanes wait, one elected lane issues
+    const uint32_t tS = uniform(tmem), tOu = uniform(tO);
+    mbar_wait(&bars->once, 0);
+    auto issue_pv = [&](int u, int st) {               // O += P(u) V(u)
+      const int pb = u & 1;
+      mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
         const uint32_t aP = smem_u32(sP + pb * PBYTES), aV = smem_u32(sKV + st * 2 * TILE64 + TILE64);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tO, desc_p128(aP, k), desc_mn64(aV, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_f16(tOu, desc_p128(aP, k), desc_mn64(aV, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);
         umma_commit(&bars->p_free[pb]);
         umma_commit(&bars->kv_empty[st]);
-      };
-      for (int jj = 0; jj < 2 * T; ++jj) {
-        const int j = jj >= T ? jj - T : jj, blk = j < nt0 ? 0 : 1, st = jj & (KV_STAGES - 1), sb = jj & 1;
-        mbar_wait(&bars->kv_full[st], (jj / KV_STAGES) & 1);
-        if (jj >= 2) mbar_wait(&bars->s_free[sb], ((jj >> 1) - 1) & 1);
-        tcgen05_fence_after();
+      }
+      __syncwarp();
+    };
+    for (int jj = 0; jj < 2 * T; ++jj) {
+      const int j = jj >= T ? jj - T : jj, blk = j < nt0 ? 0 : 1, st = jj & (KV_STAGES - 1), sb = jj & 1;
+      TRACE(2048 + jj * 8 + 0);
+      mbar_wait(&bars->kv_full[st], (jj / KV_STAGES) & 1);
+      TRACE(2048 + jj * 8 + 1);
+      if (jj >= 2) mbar_wait(&bars->s_free[sb], ((jj >> 1) - 1) & 1);
+      TRACE(2048 + jj * 8 + 2);
+      tcgen05_fence_after();
+      TRACE(2048 + jj * 8 + 5);
+      if (elect_one()) {
         const uint32_t aQ = smem_u32(sQ + blk * TILE128), aK = smem_u32(sKV + st * 2 * TILE64);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tmem + sb * FWD_NT, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S64, k);
+        for (int k = 0; k < 2; ++k) umma_f16(tS + sb * FWD_NT, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S64, k);
         umma_commit(&bars->a_ready[sb]);
         if (jj < T) umma_commit(&bars->kv_empty[st]);     // pass 1 needs K only
-        if (jj - 1 >= T) issue_pv(jj - 1 - T, (jj - 1) & (KV_STAGES - 1));
       }
-      issue_pv(T - 1, (2 * T - 1) & (KV_STAGES - 1));
-      umma_commit(&bars->done);
+      __syncwarp();
+      TRACE(2048 + jj * 8 + 3);
+      if (jj - 1 >= T) issue_pv(jj - 1 - T, (jj - 1) & (KV_STAGES - 1));
+      TRACE(2048 + jj * 8 + 4);
     }
+    issue_pv(T - 1, (2 * T - 1) & (KV_STAGES - 1));
+    if (elect_one()) umma_commit(&bars->done);
     __syncwarp();
   } else if ((warp & 3) < nact) {
-    const int qd = warp & 3, row = qd * 32 + lane;
+    const int qd = warp & 3, wg = (warp - 2) >> 2, row = qd * 32 + lane;
     const int qi = q0 + row;
     const bool q_in = qi < p.Lq;
     // rows past Lq compute on whatever the TMA box held (finite) and are never stored
     const bool mq = q_in ? (p.mask_q[(int64_t)b * p.Lq + qi] != 0) : true;
     const bool warp_all_mq = __all_sync(0xffffffffu, mq);
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t my_cols = lane_addr + wg * 32;          // this warp's half of every S tile
+    const int nsm = 64 * nact;                             // softmax threads of this CTA
     // ---- pass 1: exact row maximum of the masked logits
     float mx = -INFINITY;
     bool any_masked = false;
     for (int j = 0; j < T; ++j) {
       const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, sb = j & 1;
-      const int k0 = kt * FWD_NT, nvalid = min(FWD_NT, (blk ? p.Lk[1] : p.Lk[0]) - k0);
-      const uint32_t wv[2] = {kbits[2 * j], kbits[2 * j + 1]};
-      const uint32_t wr[2] = {range_bits32(0, nvalid), range_bits32(32, nvalid)};
-      any_masked |= ((wr[0] & ~wv[0]) | (wr[1] & ~wv[1])) != 0u;
+      const int nvalid = min(FWD_NT, (blk ? p.Lk[1] : p.Lk[0]) - kt * FWD_NT) - wg * 32;   // valid columns of my half (may be <= 0)
+      const uint32_t wv = kbits[2 * j + wg];
+      any_masked |= (range_bits32(0, nvalid) & ~wv) != 0u;
+      if (warp == 4) TRACE(j * 8 + 0);
       mbar_wait(&bars->a_ready[sb], (j >> 1) & 1);
+      if (warp == 4) TRACE(j * 8 + 1);
       tcgen05_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(tmem + lane_addr + sb * FWD_NT, r0);
-      if (nvalid > 32) tmem_ld_32x32(tmem + lane_addr + sb * FWD_NT + 32, r1);
-      tmem_ld_wait();
+      uint32_t r[32];
+      if (nvalid > 0) {
+        tmem_ld_32x32(tmem + my_cols + sb * FWD_NT, r);
+        tmem_ld_wait();
+      }
       tcgen05_fence_before();
       mbar_arrive(&bars->s_free[sb]);
-      if (wv[0] == 0xffffffffu) {
+      if (warp == 4) TRACE(j * 8 + 2);
+      if (nvalid > 0) {
+        if (wv == 0xffffffffu) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r0[c]));
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) if ((wv[0] >> c) & 1u) mx = fmaxf(mx, __uint_as_float(r0[c]));
-      }
-      if (nvalid > 32) {
-        if (wv[1] == 0xffffffffu) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r1[c]));
+          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
         } else {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) if ((wv[1] >> c) & 1u) mx = fmaxf(mx, __uint_as_float(r1[c]));
+          for (int c = 0; c < 32; ++c) if ((wv >> c) & 1u) mx = fmaxf(mx, __uint_as_float(r[c]));
         }
       }
     }
+    xch->v[wg][row] = mx;
+    xch->f[wg][row] = any_masked ? 1u : 0u;
+    softmax_bar(nsm);
+    mx = fmaxf(mx, xch->v[wg ^ 1][row]);
+    any_masked |= xch->f[wg ^ 1][row] != 0u;
     // log2-domain maximum of x = valid ? s * scale : fill  (a padded query sees fill everywhere)
     float m;
     if (!mq) m = p.fill_log2;
@@ -294,25 +334,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
     float l = 0.f;
     for (int j = 0; j < T; ++j) {
       const int jj = T + j, blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, sb = jj & 1, pb = j & 1;
-      const int k0 = kt * FWD_NT, nvalid = min(FWD_NT, (blk ? p.Lk[1] : p.Lk[0]) - k0);
-      const uint32_t wv[2] = {kbits[2 * j], kbits[2 * j + 1]};
-      const uint32_t wr[2] = {range_bits32(0, nvalid), range_bits32(32, nvalid)};
+      const int nvalid = min(FWD_NT, (blk ? p.Lk[1] : p.Lk[0]) - kt * FWD_NT) - wg * 32;
+      const uint32_t wv = kbits[2 * j + wg];
+      const uint32_t wr = range_bits32(0, nvalid);
+      if (warp == 4) TRACE(jj * 8 + 0);
       mbar_wait(&bars->a_ready[sb], (jj >> 1) & 1);
+      if (warp == 4) TRACE(jj * 8 + 1);
       tcgen05_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32(tmem + lane_addr + sb * FWD_NT, r0);
-      if (nvalid > 32) tmem_ld_32x32(tmem + lane_addr + sb * FWD_NT + 32, r1);
-      tmem_ld_wait();
+      uint32_t r[32];
+      if (nvalid > 0) {
+        tmem_ld_32x32(tmem + my_cols + sb * FWD_NT, r);
+        tmem_ld_wait();
+      }
       tcgen05_fence_before();
       mbar_arrive(&bars->s_free[sb]);
-      uint32_t pk0[16], pk1[16];
+      if (warp == 4) TRACE(jj * 8 + 2);
+      uint32_t pk[16];
       float sum0 = 0.f, sum1 = 0.f;
-      if (warp_all_mq && wv[0] == 0xffffffffu) {
+      if (nvalid <= 0) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) pk[c] = 0u;
+      } else if (warp_all_mq && wv == 0xffffffffu) {
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
-          const float e0 = ex2(fmaf(__uint_as_float(r0[c]), scale_t, nb_t)), e1 = ex2(fmaf(__uint_as_float(r0[c + 1]), scale_t, nb_t));
+          const float e0 = ex2(fmaf(__uint_as_float(r[c]), scale_t, nb_t)), e1 = ex2(fmaf(__uint_as_float(r[c + 1]), scale_t, nb_t));
           sum0 += e0; sum1 += e1;
-          pk0[c >> 1] = pack_bf16x2(e0, e1);
+          pk[c >> 1] = pack_bf16x2(e0, e1);
         }
       } else {
 #pragma unroll
@@ -321,55 +368,42 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             const int cc = c + t;
-            const float ev = ex2(fmaf(__uint_as_float(r0[cc]), scale_t, nb_t));
-            e[t] = ((wv[0] >> cc) & 1u) ? ev : (((wr[0] >> cc) & 1u) ? pm : 0.f);
+            const float ev = ex2(fmaf(__uint_as_float(r[cc]), scale_t, nb_t));
+            e[t] = ((wv >> cc) & 1u) ? ev : (((wr >> cc) & 1u) ? pm : 0.f);
           }
           sum0 += e[0]; sum1 += e[1];
-          pk0[c >> 1] = pack_bf16x2(e[0], e[1]);
+          pk[c >> 1] = pack_bf16x2(e[0], e[1]);
         }
-      }
-      if (nvalid > 32) {
-        if (warp_all_mq && wv[1] == 0xffffffffu) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            const float e0 = ex2(fmaf(__uint_as_float(r1[c]), scale_t, nb_t)), e1 = ex2(fmaf(__uint_as_float(r1[c + 1]), scale_t, nb_t));
-            sum0 += e0; sum1 += e1;
-            pk1[c >> 1] = pack_bf16x2(e0, e1);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 32; c += 2) {
-            float e[2];
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const int cc = c + t;
-              const float ev = ex2(fmaf(__uint_as_float(r1[cc]), scale_t, nb_t));
-              e[t] = ((wv[1] >> cc) & 1u) ? ev : (((wr[1] >> cc) & 1u) ? pm : 0.f);
-            }
-            sum0 += e[0]; sum1 += e[1];
-            pk1[c >> 1] = pack_bf16x2(e[0], e[1]);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) pk1[c] = 0u;
       }
       l += sum0 + sum1;
+      if (warp == 4) TRACE(jj * 8 + 3);
       if (j >= 2) mbar_wait(&bars->p_free[pb], ((j >> 1) - 1) & 1);   // P V of tile j-2 has consumed this buffer
-      write_row_sw128_half(sP + pb * PBYTES, row, 0, pk0);
-      write_row_sw128_half(sP + pb * PBYTES, row, 1, pk1);
+      if (warp == 4) TRACE(jj * 8 + 4);
+      write_row_sw128_half(sP + pb * PBYTES, row, wg, pk);
       fence_proxy_async_smem();
       mbar_arrive(&bars->p_ready[pb]);
+      if (warp == 4) TRACE(jj * 8 + 5);
     }
+    xch->l[wg][row] = l;
+    softmax_bar(nsm);
+    l += xch->l[wg ^ 1][row];
     mbar_wait(&bars->done, 0);
     tcgen05_fence_after();
-    uint32_t ro[32];
-    tmem_ld_32x32(tO + lane_addr, ro);
+    // each warpgroup normalises and stores 16 of the 32 output columns
+    uint32_t ro[16];
+    tmem_ld_32x32b_x16(tO + lane_addr + wg * 16, ro);
     tmem_ld_wait();
     if (q_in) {
-      store_row32_bf16(p.out + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH, ro, 1.0f / l);
-      p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = m * kLn2 + logf(l);
+      const float inv = 1.0f / l;
+      __nv_bfloat16* dst = p.out + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH + wg * 16;
+#pragma unroll
+      for (int d = 0; d < 16; d += 8)
+        *reinterpret_cast<uint4*>(dst + d) =
+            make_uint4(pack_bf16x2(__uint_as_float(ro[d]) * inv, __uint_as_float(ro[d + 1]) * inv), pack_bf16x2(__uint_as_float(ro[d + 2]) * inv, __uint_as_float(ro[d + 3]) * inv),
+                       pack_bf16x2(__uint_as_float(ro[d + 4]) * inv, __uint_as_float(ro[d + 5]) * inv), pack_bf16x2(__uint_as_float(ro[d + 6]) * inv, __uint_as_float(ro[d + 7]) * inv));
+      if (wg == 0) p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = m * kLn2 + logf(l);
     }
+    if (warp == 4) TRACE(4092);
   }
   tmem_teardown(tmem, warp);
 }
@@ -391,7 +425,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
   Bars* bars = reinterpret_cast<Bars*>(sdS + 2 * TILE128);
   uint32_t* kbits = reinterpret_cast<uint32_t*>(bars + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp index in a uniform register
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
   const int nt0 = (p.Lk[0] + BWD_NT - 1) / BWD_NT, nt1 = p.nblk > 1 ? (p.Lk[1] + BWD_NT - 1) / BWD_NT : 0;
   const int T = nt0 + nt1;
@@ -404,52 +438,60 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
   const uint32_t tdP = tmem + 2 * BWD_NT, tdQ = tmem + 4 * BWD_NT;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&bars->once, (p.nblk > 1 ? 3 : 2) * TILE128);
       tma_load_2d(&tmQa, &bars->once, sQ, h * DH, b * p.Lq + q0);
       if (p.nblk > 1) tma_load_2d(&tmQb, &bars->once, sQ + TILE128, h * DH, b * p.Lq + q0);
       tma_load_2d(&tmdO, &bars->once, sdO, h * DH, b * p.Lq + q0);
-      for (int j = 0; j < T; ++j) {
-        const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j & (KV_STAGES - 1);
-        mbar_wait(&bars->kv_empty[st], ((j / KV_STAGES) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < T; ++j) {
+      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j & (KV_STAGES - 1);
+      mbar_wait(&bars->kv_empty[st], ((j / KV_STAGES) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
         uint8_t* dst = sKV + st * 2 * TILE32;
         const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * BWD_NT;
         tma_load_2d(blk ? &tmKb : &tmKa, &bars->kv_full[st], dst, h * DH, row);
         tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[st], dst + TILE32, h * DH, row);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(&bars->once, 0);
-      const uint32_t adO = smem_u32(sdO);
-      auto issue_dq = [&](int u) {                       // dQ[blk(u)] += dS(u) K(u)
-        const int pb = u & 1, st = u & (KV_STAGES - 1), blk = u < nt0 ? 0 : 1, kt = blk ? u - nt0 : u;
-        mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
-        tcgen05_fence_after();
+    const uint32_t tS = uniform(tmem), tdPu = uniform(tdP), tdQu = uniform(tdQ);
+    mbar_wait(&bars->once, 0);
+    const uint32_t adO = smem_u32(sdO);
+    auto issue_dq = [&](int u) {                       // dQ[blk(u)] += dS(u) K(u)
+      const int pb = u & 1, st = u & (KV_STAGES - 1), blk = u < nt0 ? 0 : 1, kt = blk ? u - nt0 : u;
+      mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
         const uint32_t adS = smem_u32(sdS + pb * TILE128), aK = smem_u32(sKV + st * 2 * TILE32);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tdQ + blk * DH, desc_k64(adS, k), desc_mn64(aK, k), IDESC_O, (kt > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 2; ++k) umma_f16(tdQu + blk * DH, desc_k64(adS, k), desc_mn64(aK, k), IDESC_O, (kt > 0 || k > 0) ? 1u : 0u);
         umma_commit(&bars->p_free[pb]);
         umma_commit(&bars->kv_empty[st]);
-      };
-      for (int j = 0; j < T; ++j) {
-        const int blk = j < nt0 ? 0 : 1, st = j & (KV_STAGES - 1), sb = j & 1;
-        mbar_wait(&bars->kv_full[st], (j / KV_STAGES) & 1);
-        if (j >= 2) mbar_wait(&bars->s_free[sb], ((j >> 1) - 1) & 1);
-        tcgen05_fence_after();
+      }
+      __syncwarp();
+    };
+    for (int j = 0; j < T; ++j) {
+      const int blk = j < nt0 ? 0 : 1, st = j & (KV_STAGES - 1), sb = j & 1;
+      mbar_wait(&bars->kv_full[st], (j / KV_STAGES) & 1);
+      if (j >= 2) mbar_wait(&bars->s_free[sb], ((j >> 1) - 1) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
         const uint32_t aQ = smem_u32(sQ + blk * TILE128), aK = smem_u32(sKV + st * 2 * TILE32), aV = aK + TILE32;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tmem + sb * BWD_NT, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S32, k);
+        for (int k = 0; k < 2; ++k) umma_f16(tS + sb * BWD_NT, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S32, k);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tdP + sb * BWD_NT, desc_k64(adO, k), desc_k64(aV, k), IDESC_S32, k);
+        for (int k = 0; k < 2; ++k) umma_f16(tdPu + sb * BWD_NT, desc_k64(adO, k), desc_k64(aV, k), IDESC_S32, k);
         umma_commit(&bars->a_ready[sb]);
-        if (j >= 1) issue_dq(j - 1);
       }
-      issue_dq(T - 1);
-      umma_commit(&bars->done);
+      __syncwarp();
+      if (j >= 1) issue_dq(j - 1);
     }
+    issue_dq(T - 1);
+    if (elect_one()) umma_commit(&bars->done);
     __syncwarp();
   } else if ((warp & 3) < nact) {
     const int qd = warp & 3, row = qd * 32 + lane;
@@ -547,7 +589,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   QVec* qv = reinterpret_cast<QVec*>(sdST + 2 * TILE128);
   Bars* bars = reinterpret_cast<Bars*>(qv + KV_STAGES);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp index in a uniform register
   const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * QT;
   const int blk = p.which;
   const int Lk = (blk ? p.Lk[1] : p.Lk[0]);
@@ -560,11 +602,12 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t tdPT = tmem + 2 * BWD_NT, tdK = tmem + 4 * BWD_NT, tdV = tmem + 4 * BWD_NT + DH;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(&bars->once, 2 * TILE128);
       tma_load_2d(&tmK, &bars->once, sK, h * DH, b * Lk + k0);
       tma_load_2d(&tmV, &bars->once, sV, h * DH, b * Lk + k0);
     }
+    __syncwarp();
     // per-query vectors (one query per lane) are fetched one tile AHEAD so that their global-load latency
     // overlaps the wait for a free stage instead of pacing the whole pipeline
     float lse_n = 0.f, delta_n = 0.f;
@@ -582,55 +625,59 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const float lse_c = lse_n, delta_c = delta_n;
       const bool mq_c = mq_n != 0;
       if (i + 1 < T) fetch(i + 1);
-      if (lane == 0) mbar_wait(&bars->kv_empty[st], ((i / KV_STAGES) & 1) ^ 1);
-      __syncwarp();
+      mbar_wait(&bars->kv_empty[st], ((i / KV_STAGES) & 1) ^ 1);
       qv[st].nlse2[lane] = -lse_c * kLog2e;              // queries past Lq: -inf => P = 0
       qv[st].nds[lane] = -delta_c * p.scale;
       const uint32_t mqb = __ballot_sync(0xffffffffu, mq_c);
       if (lane == 0) qv[st].mq = mqb;
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
         uint8_t* dst = sQdO + st * 2 * TILE32;
         const int row = b * p.Lq + i * BWD_NT;
         tma_load_2d(&tmQ, &bars->kv_full[st], dst, h * DH, row);
         tma_load_2d(&tmdO, &bars->kv_full[st], dst + TILE32, h * DH, row);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(&bars->once, 0);
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-      auto issue_dkv = [&](int u) {
-        const int pb = u & 1, st = u & (KV_STAGES - 1);
-        mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
-        tcgen05_fence_after();
+    const uint32_t tS = uniform(tmem), tdPTu = uniform(tdPT), tdKu = uniform(tdK), tdVu = uniform(tdV);
+    mbar_wait(&bars->once, 0);
+    const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+    auto issue_dkv = [&](int u) {
+      const int pb = u & 1, st = u & (KV_STAGES - 1);
+      mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
         const uint32_t aPT = smem_u32(sPT + pb * TILE128), adST = smem_u32(sdST + pb * TILE128);
         const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE32), adO = aQ + TILE32;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tdV, desc_k64(aPT, k), desc_mn64(adO, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);   // dV += P^T dO
+        for (int k = 0; k < 2; ++k) umma_f16(tdVu, desc_k64(aPT, k), desc_mn64(adO, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);   // dV += P^T dO
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tdK, desc_k64(adST, k), desc_mn64(aQ, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);   // dK += dS^T Q
+        for (int k = 0; k < 2; ++k) umma_f16(tdKu, desc_k64(adST, k), desc_mn64(aQ, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);   // dK += dS^T Q
         umma_commit(&bars->p_free[pb]);
         umma_commit(&bars->kv_empty[st]);
-      };
-      for (int i = 0; i < T; ++i) {
-        const int st = i & (KV_STAGES - 1), sb = i & 1;
-        mbar_wait(&bars->kv_full[st], (i / KV_STAGES) & 1);
-        if (i >= 2) mbar_wait(&bars->s_free[sb], ((i >> 1) - 1) & 1);
-        tcgen05_fence_after();
+      }
+      __syncwarp();
+    };
+    for (int i = 0; i < T; ++i) {
+      const int st = i & (KV_STAGES - 1), sb = i & 1;
+      mbar_wait(&bars->kv_full[st], (i / KV_STAGES) & 1);
+      if (i >= 2) mbar_wait(&bars->s_free[sb], ((i >> 1) - 1) & 1);
+      tcgen05_fence_after();
+      if (elect_one()) {
         const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE32), adO = aQ + TILE32;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tmem + sb * BWD_NT, desc_k64(aK, k), desc_k64(aQ, k), IDESC_S32, k);      // S^T  = K Q^T
+        for (int k = 0; k < 2; ++k) umma_f16(tS + sb * BWD_NT, desc_k64(aK, k), desc_k64(aQ, k), IDESC_S32, k);      // S^T  = K Q^T
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tdPT + sb * BWD_NT, desc_k64(aV, k), desc_k64(adO, k), IDESC_S32, k);    // dP^T = V dO^T
+        for (int k = 0; k < 2; ++k) umma_f16(tdPTu + sb * BWD_NT, desc_k64(aV, k), desc_k64(adO, k), IDESC_S32, k);    // dP^T = V dO^T
         umma_commit(&bars->a_ready[sb]);
-        if (i >= 1) issue_dkv(i - 1);
       }
-      issue_dkv(T - 1);
-      umma_commit(&bars->done);
+      __syncwarp();
+      if (i >= 1) issue_dkv(i - 1);
     }
+    issue_dkv(T - 1);
+    if (elect_one()) umma_commit(&bars->done);
     __syncwarp();
   } else if ((warp & 3) < nact) {
     const int qd = warp & 3, row = qd * 32 + lane;
@@ -715,6 +762,12 @@ static int set_smem(K kernel, size_t bytes) {
 
 }  // namespace tc
 
+#ifdef MMI_ATTN_TRACE
+extern "C" int mmi_debug_trace(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, tc::g_trace, sizeof(long long) * n);
+}
+#endif
+
 int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
   using namespace tc;
   MMI_CHECK_ARG(a->dtype == MMI_BF16 && a->dh == DH, "attn_tc: bf16 with head dim 32 only (got dtype %d, dh %d)", a->dtype, a->dh);
@@ -753,9 +806,9 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     dim3 grid((a->Lq + QT - 1) / QT, a->H, a->B);
     if (kind == 0) {
       const size_t T = (a->blk[0].Lk + FWD_NT - 1) / FWD_NT + (a->nblk > 1 ? (a->blk[1].Lk + FWD_NT - 1) / FWD_NT : 0);
-      const size_t smem = 2 * TILE128 + KV_STAGES * 2 * TILE64 + 2 * PBYTES + bar_bytes + T * (FWD_NT / 32) * 4;
+      const size_t smem = 2 * TILE128 + KV_STAGES * 2 * TILE64 + 2 * PBYTES + bar_bytes + sizeof(RowXch) + T * (FWD_NT / 32) * 4;
       if (smem > cfg_bytes[0]) { int rc = set_smem(attn_fwd_tc_kernel, smem); if (rc) return rc; cfg_bytes[0] = smem; }
-      attn_fwd_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
+      attn_fwd_tc_kernel<<<grid, FWD_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
     } else {
       MMI_CHECK_ARG(a->dout && a->delta, "attn_tc bwd: null dout/delta");
       MMI_CHECK_ARG(a->lddo % 8 == 0, "attn_tc: lddo must be a multiple of 8");

@@ -80,7 +80,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(aux_bars + 2 * EPI_WARPS);
   uint8_t* stg_base = smem + STAGES * STAGE_BYTES + 256;   // 1024-aligned: STAGE_BYTES is a multiple of 1024
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp index in a uniform register
   const int total_tiles = m_tiles * n_tiles * split;
 
   if (warp == 0 && lane == 0) {
@@ -103,12 +103,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileInfo ti = get_tile(t, m_tiles, n_tiles, num_kb, split);
-        for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // warp-uniform loop: every lane waits on the mbarrier, one elected lane issues (operands stay in uniform
+    // registers; a lane-0-only loop makes ptxas wrap every UTMALDG / UTCHMMA in a waterfall loop)
+    uint32_t stage = 0, phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const TileInfo ti = get_tile(t, m_tiles, n_tiles, num_kb, split);
+      for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
@@ -123,25 +125,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int j = 0; j < BN / 64; ++j)
               tma_load_2d(&tma_b, &full_bar[stage], sb + j * (64 * BK * 2), ti.n_blk * BN + j * 64, kb * BK);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, MN_MAJOR, MN_MAJOR);
-      uint32_t stage = 0, phase = 0, it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const TileInfo ti = get_tile(t, m_tiles, n_tiles, num_kb, split);
-        const uint32_t buf = it & 1, use = it >> 1;
-        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);   // epilogue drained this accumulator
+    // ===================================================================== MMA issuer (warp-uniform, elected lane issues)
+    constexpr uint32_t idesc = make_idesc(BM, BN, MN_MAJOR, MN_MAJOR);
+    const uint32_t tbase = uniform(tmem_base);
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const TileInfo ti = get_tile(t, m_tiles, n_tiles, num_kb, split);
+      const uint32_t buf = it & 1, use = it >> 1;
+      mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);   // epilogue drained this accumulator
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tbase + buf * BN;
+      for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
@@ -157,12 +160,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             umma_f16(d_tmem, ad, bd, idesc, (kb > ti.kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);             // smem slot free once these MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (kb == ti.kb1 - 1) umma_commit(&tmem_full[buf]);   // accumulator complete -> epilogue
         }
-        umma_commit(&tmem_full[buf]);                 // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    __syncwarp();
   } else if constexpr (TMA_EPI) {
     // ===================================================================== TMA epilogue (8 warps)
     // warp = 32 accumulator rows (its TMEM lane quarter) x every other 64-column chunk of the tile.
@@ -186,7 +189,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tma_load_2d(&em.aux, &aux_bar[k], ebuf + k * EBUF_BYTES, ti.n_blk * BN + (half + 2 * k) * 64, ti.m_blk * BM + q * 32);
       }
     };
-    if (has_aux && lane == 0 && (int)blockIdx.x < total_tiles) issue_aux(blockIdx.x);
+    if (has_aux && (int)blockIdx.x < total_tiles && elect_one()) issue_aux(blockIdx.x);
+    __syncwarp();
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const TileInfo ti = get_tile(t, m_tiles, n_tiles, num_kb, split);
@@ -225,8 +229,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           *reinterpret_cast<float2*>(sbias + 2 * lane) = b;
         }
         __syncwarp();
-        uint8_t* row1 = ebuf + (second ? 0 : k * EBUF_BYTES) + lane * 128;
-        uint8_t* row2 = ebuf + EBUF_BYTES + lane * 128;
+        uint8_t* tile1 = ebuf + (second ? 0 : k * EBUF_BYTES);          // warp-uniform staging tiles
+        uint8_t* tile2 = ebuf + EBUF_BYTES;
+        uint8_t* row1 = tile1 + lane * 128;
+        uint8_t* row2 = tile2 + lane * 128;
         if (has_aux) mbar_wait(&aux_bar[k], it & 1);
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
@@ -272,14 +278,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&em.c, row1 - lane * 128, n0, m0);
-          if (second) tma_store_2d(&em.c2, row2 - lane * 128, n0, m0);
+        if (elect_one()) {                               // lane 0: owns this warp's bulk async-groups
+          tma_store_2d(&em.c, tile1, n0, m0);
+          if (second) tma_store_2d(&em.c2, tile2, n0, m0);
           bulk_commit();
         }
       }
       if (has_aux) {                                   // recycle the buffers: prefetch the next tile's operand
-        if (lane == 0) {
+        if (elect_one()) {
           bulk_wait_read0();
           if (t + (int)gridDim.x < total_tiles) issue_aux(t + gridDim.x);
         }

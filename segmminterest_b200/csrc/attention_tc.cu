@@ -31,17 +31,15 @@ namespace tc {
 
 constexpr int DH = 32;
 constexpr int QT = 128;                 // rows per CTA (TMEM lanes)
-constexpr int FWD_NT = 64;              // key columns per forward tile
-constexpr int BWD_NT = 32;              // columns per backward tile
+constexpr int NT = 32;                  // key / query columns per score tile
+constexpr int BWD_NT = NT;
 constexpr int KV_STAGES = 4;
 constexpr int ATT_THREADS = 192;        // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 softmax
 constexpr int ATT_TMEM_COLS = 256;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr uint32_t TILE32 = 32 * DH * 2;     // 2 KB : 32 rows x 64 B
-constexpr uint32_t TILE64 = 64 * DH * 2;     // 4 KB : 64 rows x 64 B
 constexpr uint32_t TILE128 = QT * DH * 2;    // 8 KB : 128 rows x 64 B
-constexpr uint32_t PBYTES = QT * FWD_NT * 2; // 16 KB: 128 rows x 128 B (SWIZZLE_128B, K-major)
 
 struct AttnTcParams {
   int B, H, Lq, nblk;
@@ -74,14 +72,6 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-// 32 bf16 (16 packed words) = columns [32*half, 32*half+32) of row `row` of a [rows x 128 B] SWIZZLE_128B K-major tile
-__device__ __forceinline__ void write_row_sw128_half(uint8_t* tile, int row, int half, const uint32_t (&w)[16]) {
-#pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    const int chunk = half * 4 + v;
-    *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
-  }
 }
 // 32 bf16 = the whole row `row` of a [rows x 64 B] SWIZZLE_64B K-major tile (address bits [4,6) ^= bits [7,9))
 __device__ __forceinline__ void write_row_sw64(uint8_t* tile, int row, const uint32_t (&w)[16]) {
@@ -116,13 +106,11 @@ __device__ __forceinline__ void build_key_bits(uint32_t* kb, const AttnTcParams&
   }
 }
 
-constexpr uint32_t IDESC_S64 = make_idesc(QT, FWD_NT, false, false);   // 128 x 64, A/B K-major
 constexpr uint32_t IDESC_S32 = make_idesc(QT, BWD_NT, false, false);   // 128 x 32, A/B K-major
 constexpr uint32_t IDESC_O = make_idesc(QT, DH, false, true);          // 128 x 32, A K-major, B MN-major
 
 __device__ __forceinline__ uint64_t desc_k64(uint32_t addr, int kstep) { return make_smem_desc(addr + kstep * 32, 16, 512, 4); }      // K-major SW64
 __device__ __forceinline__ uint64_t desc_mn64(uint32_t addr, int kstep) { return make_smem_desc(addr + kstep * 1024, 512, 512, 4); }  // MN-major SW64, 16 rows/step
-__device__ __forceinline__ uint64_t desc_p128(uint32_t addr, int kstep) { return make_smem_desc(addr + kstep * 32, 16, 1024, 2); }   // K-major SW128
 
 // barrier slots shared by the three kernels
 struct Bars {
@@ -149,9 +137,9 @@ __device__ __forceinline__ void init_bars(Bars* bars, int softmax_threads) {
   mbar_init(&bars->done, 1);
   fence_barrier_init();
 }
-__device__ __forceinline__ uint32_t tmem_setup(Bars* bars, int warp) {
+__device__ __forceinline__ uint32_t tmem_setup(Bars* bars, int warp, uint32_t cols = ATT_TMEM_COLS) {
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "r"(ATT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "r"(cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -159,12 +147,12 @@ __device__ __forceinline__ uint32_t tmem_setup(Bars* bars, int warp) {
   tcgen05_fence_after();
   return bars->tmem_slot;
 }
-__device__ __forceinline__ void tmem_teardown(uint32_t tmem, int warp) {
+__device__ __forceinline__ void tmem_teardown(uint32_t tmem, int warp, uint32_t cols = ATT_TMEM_COLS) {
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(ATT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols) : "memory");
   }
 }
 __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint32_t (&r)[32], float mul) {
@@ -176,17 +164,23 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint3
 }
 
 // ====================================================================================== forward
-// smem: Q [2][8 KB] | K,V ring [4][4 KB + 4 KB] | P [2][16 KB] | barriers | row exchange | key bits
-// 10 warps: 0 TMA, 1 MMA, 2-9 softmax.  Softmax warp w owns TMEM lane quarter (w & 3) -- the hardware rule -- and
-// the 32-column half ((w - 2) >> 2) of every 64-key tile, so a row's max / sum live in two threads and are
-// combined through shared memory once per pass.  Four softmax warps per scheduler (two resident CTAs) hide the
-// TMEM-load, barrier and MUFU latencies that two could not.
-constexpr int FWD_THREADS = 64 + 256;
-struct RowXch { float v[2][QT]; uint32_t f[2][QT]; float l[2][QT]; };
+// smem: Q [2][8 KB] | K,V ring [4][2 KB + 2 KB] | P [2][8 KB] | barriers | key bits      (~50 KB: four CTAs per SM)
+// TMEM: S[2] @0,32 | O @64                                                             (128 columns allocated)
+//
+// Small CTAs on purpose: with dh = 32 every hand-off (mbarrier wait ~100+ cycles even when already complete,
+// tcgen05.ld, fence.proxy.async) costs about as much as the arithmetic of a tile, so the kernel is bound by the
+// latency of ONE CTA's softmax -> MMA -> softmax chain, not by a pipe.  Four resident CTAs (16 softmax warps, 4 per
+// scheduler) overlap those chains and each other's prologue / epilogue.
+//
+// Single pass over the 32-key tiles with a LAZY running maximum: thread = query row keeps a reference maximum m
+// (log2 domain) taken from its first tile and only moves it when a later tile exceeds it by more than kTau;
+// P = exp2(x - m) <= 2^kTau is exact in bf16's exponent range, so the result equals the two-pass softmax up to
+// rounding.  When m moves, the warp rescales its rows of O in TMEM (tcgen05.ld / .st) after the P V products
+// issued so far have retired -- rare on real data, never on the critical path.
+constexpr float kTau = 8.0f;
+constexpr int FWD_STAGES = 4;
 
-__device__ __forceinline__ void softmax_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
-
-__global__ void __launch_bounds__(FWD_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
                    const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
                    const __grid_constant__ CUtensorMap tmVa, const __grid_constant__ CUtensorMap tmVb, const AttnTcParams p) {
@@ -194,24 +188,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + 2 * TILE128;
-  uint8_t* sP = sKV + KV_STAGES * 2 * TILE64;
-  Bars* bars = reinterpret_cast<Bars*>(sP + 2 * PBYTES);
-  RowXch* xch = reinterpret_cast<RowXch*>(bars + 1);
-  uint32_t* kbits = reinterpret_cast<uint32_t*>(xch + 1);
+  uint8_t* sP = sKV + FWD_STAGES * 2 * TILE32;
+  Bars* bars = reinterpret_cast<Bars*>(sP + 2 * TILE128);
+  uint32_t* kbits = reinterpret_cast<uint32_t*>(bars + 1);
 
   const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp index in a uniform register
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
-  const int nt0 = (p.Lk[0] + FWD_NT - 1) / FWD_NT, nt1 = p.nblk > 1 ? (p.Lk[1] + FWD_NT - 1) / FWD_NT : 0;
+  const int nt0 = (p.Lk[0] + NT - 1) / NT, nt1 = p.nblk > 1 ? (p.Lk[1] + NT - 1) / NT : 0;
   const int T = nt0 + nt1;
   const int rows_valid = min(QT, p.Lq - q0);
-  const int nact = (rows_valid + 31) >> 5;                  // TMEM lane quarters with at least one real query
+  const int nact = (rows_valid + 31) >> 5;                  // softmax warps with at least one real query
 
-  if (warp == 0 && lane == 0) init_bars(bars, 64 * nact);
-  build_key_bits<FWD_NT>(kbits, p, b, nt0, T, warp, lane, FWD_THREADS / 32);
-  if (warp == 4) TRACE(4090);
-  const uint32_t tmem = tmem_setup(bars, warp);
-  const uint32_t tO = tmem + 2 * FWD_NT;
-  if (warp == 4) TRACE(4091);
+  if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
+  build_key_bits<NT>(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
+  const uint32_t tmem = tmem_setup(bars, warp, 128);
+  const uint32_t tO = tmem + 2 * NT;
 
   if (warp == 0) {
     // warp-uniform producer loop: all lanes wait for the free stage, one elected lane issues the TMA
@@ -221,16 +212,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
       if (p.nblk > 1) tma_load_2d(&tmQb, &bars->once, sQ + TILE128, h * DH, b * p.Lq + q0);
     }
     __syncwarp();
-    for (int jj = 0; jj < 2 * T; ++jj) {
-      const bool pass2 = jj >= T;
-      const int j = pass2 ? jj - T : jj, blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = jj & (KV_STAGES - 1);
-      mbar_wait(&bars->kv_empty[st], ((jj / KV_STAGES) & 1) ^ 1);
+    for (int j = 0; j < T; ++j) {
+      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j % FWD_STAGES;
+      mbar_wait(&bars->kv_empty[st], ((j / FWD_STAGES) & 1) ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&bars->kv_full[st], pass2 ? 2 * TILE64 : TILE64);
-        uint8_t* dst = sKV + st * 2 * TILE64;
-        const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * FWD_NT;
+        mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
+        uint8_t* dst = sKV + st * 2 * TILE32;
+        const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * NT;
         tma_load_2d(blk ? &tmKb : &tmKa, &bars->kv_full[st], dst, h * DH, row);
-        if (pass2) tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[st], dst + TILE64, h * DH, row);
+        tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[st], dst + TILE32, h * DH, row);
       }
       __syncwarp();
     }
@@ -238,74 +228,62 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
     // warp-uniform MMA loop: all lanes wait, one elected lane issues
     const uint32_t tS = uniform(tmem), tOu = uniform(tO);
     mbar_wait(&bars->once, 0);
-    auto issue_pv = [&](int u, int st) {               // O += P(u) V(u)
-      const int pb = u & 1;
+    auto issue_pv = [&](int u) {                         // O += P(u) V(u)
+      const int pb = u & 1, st = u % FWD_STAGES;
       mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
       tcgen05_fence_after();
       if (elect_one()) {
-        const uint32_t aP = smem_u32(sP + pb * PBYTES), aV = smem_u32(sKV + st * 2 * TILE64 + TILE64);
+        const uint32_t aP = smem_u32(sP + pb * TILE128), aV = smem_u32(sKV + st * 2 * TILE32 + TILE32);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tOu, desc_p128(aP, k), desc_mn64(aV, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 2; ++k) umma_f16(tOu, desc_k64(aP, k), desc_mn64(aV, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);
         umma_commit(&bars->p_free[pb]);
         umma_commit(&bars->kv_empty[st]);
       }
       __syncwarp();
     };
-    for (int jj = 0; jj < 2 * T; ++jj) {
-      const int j = jj >= T ? jj - T : jj, blk = j < nt0 ? 0 : 1, st = jj & (KV_STAGES - 1), sb = jj & 1;
-      TRACE(2048 + jj * 8 + 0);
-      mbar_wait(&bars->kv_full[st], (jj / KV_STAGES) & 1);
-      TRACE(2048 + jj * 8 + 1);
-      if (jj >= 2) mbar_wait(&bars->s_free[sb], ((jj >> 1) - 1) & 1);
-      TRACE(2048 + jj * 8 + 2);
+    for (int j = 0; j < T; ++j) {
+      const int blk = j < nt0 ? 0 : 1, st = j % FWD_STAGES, sb = j & 1;
+      mbar_wait(&bars->kv_full[st], (j / FWD_STAGES) & 1);
+      if (j >= 2) mbar_wait(&bars->s_free[sb], ((j >> 1) - 1) & 1);
       tcgen05_fence_after();
-      TRACE(2048 + jj * 8 + 5);
       if (elect_one()) {
-        const uint32_t aQ = smem_u32(sQ + blk * TILE128), aK = smem_u32(sKV + st * 2 * TILE64);
+        const uint32_t aQ = smem_u32(sQ + blk * TILE128), aK = smem_u32(sKV + st * 2 * TILE32);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tS + sb * FWD_NT, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S64, k);
-        umma_commit(&bars->a_ready[sb]);
-        if (jj < T) umma_commit(&bars->kv_empty[st]);     // pass 1 needs K only
+        for (int k = 0; k < 2; ++k) umma_f16(tS + sb * NT, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S32, k);
+        umma_commit(&bars->a_ready[sb]);                 // also covers P V (j-2): P buffer sb is free once this fires
       }
       __syncwarp();
-      TRACE(2048 + jj * 8 + 3);
-      if (jj - 1 >= T) issue_pv(jj - 1 - T, (jj - 1) & (KV_STAGES - 1));
-      TRACE(2048 + jj * 8 + 4);
+      if (j >= 1) issue_pv(j - 1);
     }
-    issue_pv(T - 1, (2 * T - 1) & (KV_STAGES - 1));
+    issue_pv(T - 1);
     if (elect_one()) umma_commit(&bars->done);
     __syncwarp();
   } else if ((warp & 3) < nact) {
-    const int qd = warp & 3, wg = (warp - 2) >> 2, row = qd * 32 + lane;
+    const int qd = warp & 3, row = qd * 32 + lane;
     const int qi = q0 + row;
     const bool q_in = qi < p.Lq;
     // rows past Lq compute on whatever the TMA box held (finite) and are never stored
     const bool mq = q_in ? (p.mask_q[(int64_t)b * p.Lq + qi] != 0) : true;
     const bool warp_all_mq = __all_sync(0xffffffffu, mq);
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t my_cols = lane_addr + wg * 32;          // this warp's half of every S tile
-    const int nsm = 64 * nact;                             // softmax threads of this CTA
-    // ---- pass 1: exact row maximum of the masked logits
-    float mx = -INFINITY;
-    bool any_masked = false;
+    const float scale_t = mq ? p.scale_log2 : 0.f;       // x = s * scale_t + base_t  (a padded query sees `fill` everywhere)
+    const float base_t = mq ? 0.f : p.fill_log2;
+    float m = 0.f, l0 = 0.f, l1 = 0.f;
     for (int j = 0; j < T; ++j) {
       const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, sb = j & 1;
-      const int nvalid = min(FWD_NT, (blk ? p.Lk[1] : p.Lk[0]) - kt * FWD_NT) - wg * 32;   // valid columns of my half (may be <= 0)
-      const uint32_t wv = kbits[2 * j + wg];
-      any_masked |= (range_bits32(0, nvalid) & ~wv) != 0u;
-      if (warp == 4) TRACE(j * 8 + 0);
-      mbar_wait(&bars->a_ready[sb], (j >> 1) & 1);
-      if (warp == 4) TRACE(j * 8 + 1);
+      const int nvalid = min(NT, (blk ? p.Lk[1] : p.Lk[0]) - kt * NT);
+      const uint32_t wv = kbits[j], wr = range_bits32(0, nvalid);
+      mbar_wait(&bars->a_ready[sb], (j >> 1) & 1);       // S(j) ready; P buffer sb consumed by P V (j-2)
       tcgen05_fence_after();
       uint32_t r[32];
-      if (nvalid > 0) {
-        tmem_ld_32x32(tmem + my_cols + sb * FWD_NT, r);
-        tmem_ld_wait();
-      }
+      tmem_ld_32x32(tmem + lane_addr + sb * NT, r);
+      tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(&bars->s_free[sb]);
-      if (warp == 4) TRACE(j * 8 + 2);
-      if (nvalid > 0) {
+      // ---- tile maximum in the log2 domain
+      float t;
+      {
+        float mx = -INFINITY;
         if (wv == 0xffffffffu) {
 #pragma unroll
           for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
@@ -313,99 +291,69 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
 #pragma unroll
           for (int c = 0; c < 32; ++c) if ((wv >> c) & 1u) mx = fmaxf(mx, __uint_as_float(r[c]));
         }
+        t = (wr & ~wv) != 0u ? p.fill_log2 : -INFINITY;  // a masked key inside the tile sits at `fill`
+        if (mx > -INFINITY) t = fmaxf(t, mx * p.scale_log2);
+        if (!mq) t = p.fill_log2;
       }
-    }
-    xch->v[wg][row] = mx;
-    xch->f[wg][row] = any_masked ? 1u : 0u;
-    softmax_bar(nsm);
-    mx = fmaxf(mx, xch->v[wg ^ 1][row]);
-    any_masked |= xch->f[wg ^ 1][row] != 0u;
-    // log2-domain maximum of x = valid ? s * scale : fill  (a padded query sees fill everywhere)
-    float m;
-    if (!mq) m = p.fill_log2;
-    else {
-      m = any_masked ? p.fill_log2 : -INFINITY;
-      if (mx > -INFINITY) m = fmaxf(m, mx * p.scale_log2);
-    }
-    const float scale_t = mq ? p.scale_log2 : 0.f;
-    const float nb_t = (mq ? 0.f : p.fill_log2) - m;     // x - m = s * scale_t + nb_t
-    const float pm = ex2(p.fill_log2 - m);               // probability weight of a masked key
-    // ---- pass 2: P = exp2(x - m) -> bf16 -> swizzled smem, O accumulates in TMEM
-    float l = 0.f;
-    for (int j = 0; j < T; ++j) {
-      const int jj = T + j, blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, sb = jj & 1, pb = j & 1;
-      const int nvalid = min(FWD_NT, (blk ? p.Lk[1] : p.Lk[0]) - kt * FWD_NT) - wg * 32;
-      const uint32_t wv = kbits[2 * j + wg];
-      const uint32_t wr = range_bits32(0, nvalid);
-      if (warp == 4) TRACE(jj * 8 + 0);
-      mbar_wait(&bars->a_ready[sb], (jj >> 1) & 1);
-      if (warp == 4) TRACE(jj * 8 + 1);
-      tcgen05_fence_after();
-      uint32_t r[32];
-      if (nvalid > 0) {
-        tmem_ld_32x32(tmem + my_cols + sb * FWD_NT, r);
+      if (j == 0) m = t;
+      const bool move = j > 0 && t > m + kTau;
+      if (__any_sync(0xffffffffu, move)) {
+        // move the reference maximum of some rows: rescale l and the warp's rows of O once P V (0..j-1) have retired
+        // (tcgen05.ld / .st are warp-collective, so every lane takes part; lanes that keep m multiply by 1)
+        mbar_wait(&bars->p_free[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tcgen05_fence_after();
+        const float f = move ? ex2(m - t) : 1.0f;
+        uint32_t ro[32];
+        tmem_ld_32x32(tO + lane_addr, ro);
         tmem_ld_wait();
-      }
-      tcgen05_fence_before();
-      mbar_arrive(&bars->s_free[sb]);
-      if (warp == 4) TRACE(jj * 8 + 2);
-      uint32_t pk[16];
-      float sum0 = 0.f, sum1 = 0.f;
-      if (nvalid <= 0) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) pk[c] = 0u;
-      } else if (warp_all_mq && wv == 0xffffffffu) {
+        for (int c = 0; c < 32; ++c) ro[c] = __float_as_uint(__uint_as_float(ro[c]) * f);
+        tmem_st_32x32(tO + lane_addr, ro);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        l0 *= f; l1 *= f;
+        if (move) m = t;
+      }
+      const float nb_t = base_t - m;                     // x - m = s * scale_t + nb_t
+      uint32_t pk[16];
+      if (warp_all_mq && wv == 0xffffffffu) {
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           const float e0 = ex2(fmaf(__uint_as_float(r[c]), scale_t, nb_t)), e1 = ex2(fmaf(__uint_as_float(r[c + 1]), scale_t, nb_t));
-          sum0 += e0; sum1 += e1;
+          l0 += e0; l1 += e1;
           pk[c >> 1] = pack_bf16x2(e0, e1);
         }
       } else {
+        const float pm = ex2(p.fill_log2 - m);           // probability weight of a masked key
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           float e[2];
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int cc = c + t;
+          for (int u = 0; u < 2; ++u) {
+            const int cc = c + u;
             const float ev = ex2(fmaf(__uint_as_float(r[cc]), scale_t, nb_t));
-            e[t] = ((wv >> cc) & 1u) ? ev : (((wr >> cc) & 1u) ? pm : 0.f);
+            e[u] = ((wv >> cc) & 1u) ? ev : (((wr >> cc) & 1u) ? pm : 0.f);
           }
-          sum0 += e[0]; sum1 += e[1];
+          l0 += e[0]; l1 += e[1];
           pk[c >> 1] = pack_bf16x2(e[0], e[1]);
         }
       }
-      l += sum0 + sum1;
-      if (warp == 4) TRACE(jj * 8 + 3);
-      if (j >= 2) mbar_wait(&bars->p_free[pb], ((j >> 1) - 1) & 1);   // P V of tile j-2 has consumed this buffer
-      if (warp == 4) TRACE(jj * 8 + 4);
-      write_row_sw128_half(sP + pb * PBYTES, row, wg, pk);
+      write_row_sw64(sP + sb * TILE128, row, pk);
       fence_proxy_async_smem();
-      mbar_arrive(&bars->p_ready[pb]);
-      if (warp == 4) TRACE(jj * 8 + 5);
+      mbar_arrive(&bars->p_ready[sb]);
     }
-    xch->l[wg][row] = l;
-    softmax_bar(nsm);
-    l += xch->l[wg ^ 1][row];
     mbar_wait(&bars->done, 0);
     tcgen05_fence_after();
-    // each warpgroup normalises and stores 16 of the 32 output columns
-    uint32_t ro[16];
-    tmem_ld_32x32b_x16(tO + lane_addr + wg * 16, ro);
+    uint32_t ro[32];
+    tmem_ld_32x32(tO + lane_addr, ro);
     tmem_ld_wait();
     if (q_in) {
-      const float inv = 1.0f / l;
-      __nv_bfloat16* dst = p.out + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH + wg * 16;
-#pragma unroll
-      for (int d = 0; d < 16; d += 8)
-        *reinterpret_cast<uint4*>(dst + d) =
-            make_uint4(pack_bf16x2(__uint_as_float(ro[d]) * inv, __uint_as_float(ro[d + 1]) * inv), pack_bf16x2(__uint_as_float(ro[d + 2]) * inv, __uint_as_float(ro[d + 3]) * inv),
-                       pack_bf16x2(__uint_as_float(ro[d + 4]) * inv, __uint_as_float(ro[d + 5]) * inv), pack_bf16x2(__uint_as_float(ro[d + 6]) * inv, __uint_as_float(ro[d + 7]) * inv));
-      if (wg == 0) p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = m * kLn2 + logf(l);
+      const float l = l0 + l1;
+      store_row32_bf16(p.out + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH, ro, 1.0f / l);
+      p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = m * kLn2 + logf(l);
     }
-    if (warp == 4) TRACE(4092);
   }
-  tmem_teardown(tmem, warp);
+  tmem_teardown(tmem, warp, 128);
 }
 
 // ====================================================================================== backward: dQ
@@ -794,7 +742,7 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
   static size_t cfg_bytes[3] = {0, 0, 0};   // largest dynamic shared-memory size configured so far, per kernel
   const size_t bar_bytes = sizeof(Bars) + 1024 /*align*/;
   if (kind == 0 || kind == 1) {
-    const uint32_t kbox = kind == 0 ? FWD_NT : BWD_NT;
+    const uint32_t kbox = NT;
     CUtensorMap mQ[2], mK[2], mV[2], mdO;
     for (int i = 0; i < 2; ++i) {
       const mmi_attn_block& s = a->blk[i < a->nblk ? i : 0];
@@ -805,10 +753,10 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     }
     dim3 grid((a->Lq + QT - 1) / QT, a->H, a->B);
     if (kind == 0) {
-      const size_t T = (a->blk[0].Lk + FWD_NT - 1) / FWD_NT + (a->nblk > 1 ? (a->blk[1].Lk + FWD_NT - 1) / FWD_NT : 0);
-      const size_t smem = 2 * TILE128 + KV_STAGES * 2 * TILE64 + 2 * PBYTES + bar_bytes + sizeof(RowXch) + T * (FWD_NT / 32) * 4;
+      const size_t T = (a->blk[0].Lk + NT - 1) / NT + (a->nblk > 1 ? (a->blk[1].Lk + NT - 1) / NT : 0);
+      const size_t smem = 2 * TILE128 + FWD_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes + T * 4;
       if (smem > cfg_bytes[0]) { int rc = set_smem(attn_fwd_tc_kernel, smem); if (rc) return rc; cfg_bytes[0] = smem; }
-      attn_fwd_tc_kernel<<<grid, FWD_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
+      attn_fwd_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
     } else {
       MMI_CHECK_ARG(a->dout && a->delta, "attn_tc bwd: null dout/delta");
       MMI_CHECK_ARG(a->lddo % 8 == 0, "attn_tc: lddo must be a multiple of 8");

@@ -200,7 +200,14 @@ def test_attention_tc_unmasked_fast_path(dev, shape):
     _check_attention(dev, 32, torch.bfloat16, "tc", shape, ragged=False)
 
 
-def _check_attention(dev, dh, dtype, impl, shape, ragged):
+@pytest.mark.parametrize("ragged", [False, True])
+def test_attention_tc_running_max_rescale(dev, ragged):
+    """Keys whose logits grow tile after tile: the forward kernel's lazy running maximum has to move several
+    times (O rescaled in TMEM), and must still equal the exact two-pass softmax."""
+    _check_attention(dev, 32, torch.bfloat16, "tc", (2, 4, 200, 100, 700), ragged=ragged, key_ramp=0.012)
+
+
+def _check_attention(dev, dh, dtype, impl, shape, ragged, key_ramp=0.0):
     from segmminterest_b200 import ops
     torch.manual_seed(4)
     B, H, Lq, La, Lb = shape
@@ -214,6 +221,10 @@ def _check_attention(dev, dh, dtype, impl, shape, ragged):
     mq, mka, mkb = mk(Lq), mk(La), mk(Lb)
     mq[0, :] = True
     t = [torch.randn(B, L, d) * 0.7 for L in (Lq, La, La, Lq, Lb, Lb)]
+    if key_ramp:   # |k_j| grows with j: later key tiles hold much larger logits than the first one
+        t[0] *= 3.0; t[3] *= 3.0
+        t[1] *= (1.0 + key_ramp * torch.arange(La))[None, :, None] ** 2
+        t[4] *= (1.0 + key_ramp * (La + torch.arange(Lb)))[None, :, None] ** 2
     t = [x.to(dtype).to(dev) for x in t]
     qa, ka, va, qb, kb, vb = t
     ref_in = [x.double().cpu().requires_grad_(True) for x in t]

@@ -32,7 +32,6 @@ namespace tc {
 constexpr int DH = 32;
 constexpr int QT = 128;                 // rows per CTA (TMEM lanes)
 constexpr int NT = 32;                  // key / query columns per score tile
-constexpr int BWD_NT = NT;
 constexpr int KV_STAGES = 4;
 constexpr int ATT_THREADS = 192;        // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 softmax
 constexpr int ATT_TMEM_COLS = 256;
@@ -106,7 +105,7 @@ __device__ __forceinline__ void build_key_bits(uint32_t* kb, const AttnTcParams&
   }
 }
 
-constexpr uint32_t IDESC_S32 = make_idesc(QT, BWD_NT, false, false);   // 128 x 32, A/B K-major
+constexpr uint32_t IDESC_S32 = make_idesc(QT, NT, false, false);   // 128 x 32, A/B K-major
 constexpr uint32_t IDESC_O = make_idesc(QT, DH, false, true);          // 128 x 32, A K-major, B MN-major
 
 __device__ __forceinline__ uint64_t desc_k64(uint32_t addr, int kstep) { return make_smem_desc(addr + kstep * 32, 16, 512, 4); }      // K-major SW64
@@ -357,9 +356,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
 }
 
 // ====================================================================================== backward: dQ
-// smem: Q [2][8 KB] | dO 8 KB | K,V ring [4][2 KB + 2 KB] | dS [2][8 KB] | barriers
-// TMEM: S[2] @0,32 | dP[2] @64,96 | dQa @128 | dQb @160
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+// smem: Q [2][8 KB] | dO 8 KB | K,V ring [3][2 KB + 2 KB] | dS [2][8 KB] | barriers | key bits   (~53 KB: four CTAs / SM)
+// TMEM: S @0 | dP @32 | dQa @64 | dQb @96                                                      (128 columns)
+// S / dP are single-buffered: the softmax threads pull a tile into registers first thing (s_free), so the MMA warp
+// refills the buffer while they compute.  dS staging is double-buffered; buffer (j & 1) is known to be free when
+// a_ready(j) fires because that commit also covers the dQ product of tile j - 2.
+constexpr int BWD_STAGES = 3;
+
+__global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
                       const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
                       const __grid_constant__ CUtensorMap tmVa, const __grid_constant__ CUtensorMap tmVb,
@@ -369,21 +373,21 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + 2 * TILE128;
   uint8_t* sKV = sdO + TILE128;
-  uint8_t* sdS = sKV + KV_STAGES * 2 * TILE32;
+  uint8_t* sdS = sKV + BWD_STAGES * 2 * TILE32;           // 36 KB from the base: still 1024-aligned
   Bars* bars = reinterpret_cast<Bars*>(sdS + 2 * TILE128);
   uint32_t* kbits = reinterpret_cast<uint32_t*>(bars + 1);
 
   const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp index in a uniform register
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
-  const int nt0 = (p.Lk[0] + BWD_NT - 1) / BWD_NT, nt1 = p.nblk > 1 ? (p.Lk[1] + BWD_NT - 1) / BWD_NT : 0;
+  const int nt0 = (p.Lk[0] + NT - 1) / NT, nt1 = p.nblk > 1 ? (p.Lk[1] + NT - 1) / NT : 0;
   const int T = nt0 + nt1;
   const int rows_valid = min(QT, p.Lq - q0);
   const int nact = (rows_valid + 31) >> 5;
 
   if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
-  build_key_bits<BWD_NT>(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
-  const uint32_t tmem = tmem_setup(bars, warp);
-  const uint32_t tdP = tmem + 2 * BWD_NT, tdQ = tmem + 4 * BWD_NT;
+  build_key_bits<NT>(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
+  const uint32_t tmem = tmem_setup(bars, warp, 128);
+  const uint32_t tdP = tmem + NT, tdQ = tmem + 2 * NT;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -394,12 +398,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
     }
     __syncwarp();
     for (int j = 0; j < T; ++j) {
-      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j & (KV_STAGES - 1);
-      mbar_wait(&bars->kv_empty[st], ((j / KV_STAGES) & 1) ^ 1);
+      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j % BWD_STAGES;
+      mbar_wait(&bars->kv_empty[st], ((j / BWD_STAGES) & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
         uint8_t* dst = sKV + st * 2 * TILE32;
-        const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * BWD_NT;
+        const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * NT;
         tma_load_2d(blk ? &tmKb : &tmKa, &bars->kv_full[st], dst, h * DH, row);
         tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[st], dst + TILE32, h * DH, row);
       }
@@ -410,30 +414,29 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
     mbar_wait(&bars->once, 0);
     const uint32_t adO = smem_u32(sdO);
     auto issue_dq = [&](int u) {                       // dQ[blk(u)] += dS(u) K(u)
-      const int pb = u & 1, st = u & (KV_STAGES - 1), blk = u < nt0 ? 0 : 1, kt = blk ? u - nt0 : u;
+      const int pb = u & 1, st = u % BWD_STAGES, blk = u < nt0 ? 0 : 1, kt = blk ? u - nt0 : u;
       mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint32_t adS = smem_u32(sdS + pb * TILE128), aK = smem_u32(sKV + st * 2 * TILE32);
 #pragma unroll
         for (int k = 0; k < 2; ++k) umma_f16(tdQu + blk * DH, desc_k64(adS, k), desc_mn64(aK, k), IDESC_O, (kt > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&bars->p_free[pb]);
         umma_commit(&bars->kv_empty[st]);
       }
       __syncwarp();
     };
     for (int j = 0; j < T; ++j) {
-      const int blk = j < nt0 ? 0 : 1, st = j & (KV_STAGES - 1), sb = j & 1;
-      mbar_wait(&bars->kv_full[st], (j / KV_STAGES) & 1);
-      if (j >= 2) mbar_wait(&bars->s_free[sb], ((j >> 1) - 1) & 1);
+      const int blk = j < nt0 ? 0 : 1, st = j % BWD_STAGES;
+      mbar_wait(&bars->kv_full[st], (j / BWD_STAGES) & 1);
+      if (j >= 1) mbar_wait(&bars->s_free[0], (j - 1) & 1);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint32_t aQ = smem_u32(sQ + blk * TILE128), aK = smem_u32(sKV + st * 2 * TILE32), aV = aK + TILE32;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tS + sb * BWD_NT, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S32, k);
+        for (int k = 0; k < 2; ++k) umma_f16(tS, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S32, k);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tdPu + sb * BWD_NT, desc_k64(adO, k), desc_k64(aV, k), IDESC_S32, k);
-        umma_commit(&bars->a_ready[sb]);
+        for (int k = 0; k < 2; ++k) umma_f16(tdPu, desc_k64(adO, k), desc_k64(aV, k), IDESC_S32, k);
+        umma_commit(&bars->a_ready[0]);                  // also covers dQ (j-2): dS buffer (j & 1) is free once this fires
       }
       __syncwarp();
       if (j >= 1) issue_dq(j - 1);
@@ -463,68 +466,77 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
     }
     const float nds = -delta * p.scale;                  // dS = P * (dP * scale + nds)
     for (int j = 0; j < T; ++j) {
-      const int sb = j & 1;
+      const int pb = j & 1;
       const uint32_t wv = kbits[j];
-      mbar_wait(&bars->a_ready[sb], (j >> 1) & 1);
+      const bool fast = warp_all_mq && wv == 0xffffffffu;
+      mbar_wait(&bars->a_ready[0], j & 1);               // S(j), dP(j) ready; dS buffer pb consumed by dQ (j-2)
       tcgen05_fence_after();
-      uint32_t rs[32], rp[32];
-      tmem_ld_32x32(tmem + lane_addr + sb * BWD_NT, rs);
-      tmem_ld_32x32(tdP + lane_addr + sb * BWD_NT, rp);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      mbar_arrive(&bars->s_free[sb]);
       uint32_t pk[16];
-      if (warp_all_mq && wv == 0xffffffffu) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(rs[c]), p.scale_log2, nlse2)), p1 = ex2(fmaf(__uint_as_float(rs[c + 1]), p.scale_log2, nlse2));
-          pk[c >> 1] = pack_bf16x2(p0 * fmaf(__uint_as_float(rp[c]), p.scale, nds), p1 * fmaf(__uint_as_float(rp[c + 1]), p.scale, nds));
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t rs[16], rp[16];
+        tmem_ld_32x32b_x16(tmem + lane_addr + hf * 16, rs);
+        tmem_ld_32x32b_x16(tdP + lane_addr + hf * 16, rp);
+        tmem_ld_wait();
+        if (hf == 1) {                                   // the whole tile is in registers: hand the buffers back
+          tcgen05_fence_before();
+          mbar_arrive(&bars->s_free[0]);
         }
-      } else {
+        if (fast) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float ds[2];
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int cc = c + t;
-            const bool valid = mq && (((wv >> cc) & 1u) != 0);   // overwritten (masked) logits pass no gradient
-            const float pr = ex2(fmaf(__uint_as_float(rs[cc]), p.scale_log2, nlse2));
-            ds[t] = valid ? pr * fmaf(__uint_as_float(rp[cc]), p.scale, nds) : 0.f;
+          for (int c = 0; c < 16; c += 2) {
+            const float p0 = ex2(fmaf(__uint_as_float(rs[c]), p.scale_log2, nlse2)), p1 = ex2(fmaf(__uint_as_float(rs[c + 1]), p.scale_log2, nlse2));
+            pk[hf * 8 + (c >> 1)] = pack_bf16x2(p0 * fmaf(__uint_as_float(rp[c]), p.scale, nds), p1 * fmaf(__uint_as_float(rp[c + 1]), p.scale, nds));
           }
-          pk[c >> 1] = pack_bf16x2(ds[0], ds[1]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            float ds[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const int cc = c + t;
+              const bool valid = mq && (((wv >> (hf * 16 + cc)) & 1u) != 0);   // overwritten (masked) logits pass no gradient
+              const float pr = ex2(fmaf(__uint_as_float(rs[cc]), p.scale_log2, nlse2));
+              ds[t] = valid ? pr * fmaf(__uint_as_float(rp[cc]), p.scale, nds) : 0.f;
+            }
+            pk[hf * 8 + (c >> 1)] = pack_bf16x2(ds[0], ds[1]);
+          }
         }
       }
-      if (j >= 2) mbar_wait(&bars->p_free[sb], ((j >> 1) - 1) & 1);
-      write_row_sw64(sdS + sb * TILE128, row, pk);
+      write_row_sw64(sdS + pb * TILE128, row, pk);
       fence_proxy_async_smem();
-      mbar_arrive(&bars->p_ready[sb]);
+      mbar_arrive(&bars->p_ready[pb]);
     }
     mbar_wait(&bars->done, 0);
     tcgen05_fence_after();
-    uint32_t ra[32], rb[32];
+    uint32_t ra[32];
     tmem_ld_32x32(tdQ + lane_addr, ra);
-    if (p.nblk > 1) tmem_ld_32x32(tdQ + DH + lane_addr, rb);
     tmem_ld_wait();
-    if (q_in) {
-      if (p.dq[0] != nullptr) store_row32_bf16(p.dq[0] + ((int64_t)b * p.Lq + qi) * p.lddq[0] + h * DH, ra, 1.0f);
-      if (p.nblk > 1 && p.dq[1] != nullptr) store_row32_bf16(p.dq[1] + ((int64_t)b * p.Lq + qi) * p.lddq[1] + h * DH, rb, 1.0f);
+    if (q_in && p.dq[0] != nullptr) store_row32_bf16(p.dq[0] + ((int64_t)b * p.Lq + qi) * p.lddq[0] + h * DH, ra, 1.0f);
+    if (p.nblk > 1) {
+      tmem_ld_32x32(tdQ + DH + lane_addr, ra);
+      tmem_ld_wait();
+      if (q_in && p.dq[1] != nullptr) store_row32_bf16(p.dq[1] + ((int64_t)b * p.Lq + qi) * p.lddq[1] + h * DH, ra, 1.0f);
     }
   }
-  tmem_teardown(tmem, warp);
+  tmem_teardown(tmem, warp, 128);
 }
 
 // ====================================================================================== backward: dK, dV
 // CTA = 128 keys of one key block; loops over 32-query tiles.  thread = key row.
-// smem: K 8 KB | V 8 KB | Q,dO ring [4][2 KB + 2 KB] | P^T [2][8 KB] | dS^T [2][8 KB] | per-query vectors | barriers
-// TMEM: S^T[2] @0,32 | dP^T[2] @64,96 | dK @128 | dV @160
+// smem: K 8 KB | V 8 KB | Q,dO ring [3][2 KB + 2 KB] | P^T 8 KB | dS^T 8 KB | per-query vectors | barriers   (~46 KB)
+// TMEM: S^T @0 | dP^T @32 | dK @64 | dV @96                                                                (128 columns)
+// Everything single-buffered: S^T / dP^T are pulled into registers at the top of a tile (s_free) and refilled
+// while the threads compute; P^T / dS^T are rewritten only after the dK / dV products of the previous tile have
+// retired (p_free), which happened long before in steady state.
 struct QVec {
-  float nlse2[BWD_NT];     // -lse * log2(e)          (+/-inf tricks: -inf for queries past Lq => P = 0)
-  float nds[BWD_NT];       // -delta * scale
+  float nlse2[NT];         // -lse * log2(e)          (+/-inf tricks: -inf for queries past Lq => P = 0)
+  float nds[NT];           // -delta * scale
   uint32_t mq;             // valid-query bits
   uint32_t pad[3];
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -532,22 +544,22 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint8_t* sK = smem;
   uint8_t* sV = sK + TILE128;
   uint8_t* sQdO = sV + TILE128;
-  uint8_t* sPT = sQdO + KV_STAGES * 2 * TILE32;
-  uint8_t* sdST = sPT + 2 * TILE128;
-  QVec* qv = reinterpret_cast<QVec*>(sdST + 2 * TILE128);
-  Bars* bars = reinterpret_cast<Bars*>(qv + KV_STAGES);
+  uint8_t* sPT = sQdO + 4 * 2 * TILE32;                   // ring region sized for 4 stages keeps the tiles 1024-aligned
+  uint8_t* sdST = sPT + TILE128;
+  QVec* qv = reinterpret_cast<QVec*>(sdST + TILE128);
+  Bars* bars = reinterpret_cast<Bars*>(qv + BWD_STAGES);
 
   const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp index in a uniform register
   const int b = blockIdx.z, h = blockIdx.y, k0 = blockIdx.x * QT;
   const int blk = p.which;
   const int Lk = (blk ? p.Lk[1] : p.Lk[0]);
-  const int T = (p.Lq + BWD_NT - 1) / BWD_NT;
+  const int T = (p.Lq + NT - 1) / NT;
   const int rows_valid = min(QT, Lk - k0);
   const int nact = (rows_valid + 31) >> 5;
 
   if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
-  const uint32_t tmem = tmem_setup(bars, warp);
-  const uint32_t tdPT = tmem + 2 * BWD_NT, tdK = tmem + 4 * BWD_NT, tdV = tmem + 4 * BWD_NT + DH;
+  const uint32_t tmem = tmem_setup(bars, warp, 128);
+  const uint32_t tdPT = tmem + NT, tdK = tmem + 2 * NT, tdV = tmem + 2 * NT + DH;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -561,7 +573,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     float lse_n = 0.f, delta_n = 0.f;
     uint8_t mq_n = 0;
     auto fetch = [&](int i) {
-      const int qi = i * BWD_NT + lane;
+      const int qi = i * NT + lane;
       if (qi < p.Lq) {
         const int64_t li = ((int64_t)b * p.H + h) * p.Lq + qi;
         lse_n = p.lse[li]; delta_n = p.delta[li]; mq_n = p.mask_q[(int64_t)b * p.Lq + qi];
@@ -569,11 +581,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     };
     fetch(0);
     for (int i = 0; i < T; ++i) {
-      const int st = i & (KV_STAGES - 1);
+      const int st = i % BWD_STAGES;
       const float lse_c = lse_n, delta_c = delta_n;
       const bool mq_c = mq_n != 0;
       if (i + 1 < T) fetch(i + 1);
-      mbar_wait(&bars->kv_empty[st], ((i / KV_STAGES) & 1) ^ 1);
+      mbar_wait(&bars->kv_empty[st], ((i / BWD_STAGES) & 1) ^ 1);
       qv[st].nlse2[lane] = -lse_c * kLog2e;              // queries past Lq: -inf => P = 0
       qv[st].nds[lane] = -delta_c * p.scale;
       const uint32_t mqb = __ballot_sync(0xffffffffu, mq_c);
@@ -582,7 +594,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (elect_one()) {
         mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
         uint8_t* dst = sQdO + st * 2 * TILE32;
-        const int row = b * p.Lq + i * BWD_NT;
+        const int row = b * p.Lq + i * NT;
         tma_load_2d(&tmQ, &bars->kv_full[st], dst, h * DH, row);
         tma_load_2d(&tmdO, &bars->kv_full[st], dst + TILE32, h * DH, row);
       }
@@ -592,34 +604,34 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t tS = uniform(tmem), tdPTu = uniform(tdPT), tdKu = uniform(tdK), tdVu = uniform(tdV);
     mbar_wait(&bars->once, 0);
     const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+    const uint32_t aPT = smem_u32(sPT), adST = smem_u32(sdST);
     auto issue_dkv = [&](int u) {
-      const int pb = u & 1, st = u & (KV_STAGES - 1);
-      mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
+      const int st = u % BWD_STAGES;
+      mbar_wait(&bars->p_ready[0], u & 1);
       tcgen05_fence_after();
       if (elect_one()) {
-        const uint32_t aPT = smem_u32(sPT + pb * TILE128), adST = smem_u32(sdST + pb * TILE128);
         const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE32), adO = aQ + TILE32;
 #pragma unroll
         for (int k = 0; k < 2; ++k) umma_f16(tdVu, desc_k64(aPT, k), desc_mn64(adO, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);   // dV += P^T dO
 #pragma unroll
         for (int k = 0; k < 2; ++k) umma_f16(tdKu, desc_k64(adST, k), desc_mn64(aQ, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);   // dK += dS^T Q
-        umma_commit(&bars->p_free[pb]);
+        umma_commit(&bars->p_free[0]);
         umma_commit(&bars->kv_empty[st]);
       }
       __syncwarp();
     };
     for (int i = 0; i < T; ++i) {
-      const int st = i & (KV_STAGES - 1), sb = i & 1;
-      mbar_wait(&bars->kv_full[st], (i / KV_STAGES) & 1);
-      if (i >= 2) mbar_wait(&bars->s_free[sb], ((i >> 1) - 1) & 1);
+      const int st = i % BWD_STAGES;
+      mbar_wait(&bars->kv_full[st], (i / BWD_STAGES) & 1);
+      if (i >= 1) mbar_wait(&bars->s_free[0], (i - 1) & 1);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE32), adO = aQ + TILE32;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tS + sb * BWD_NT, desc_k64(aK, k), desc_k64(aQ, k), IDESC_S32, k);      // S^T  = K Q^T
+        for (int k = 0; k < 2; ++k) umma_f16(tS, desc_k64(aK, k), desc_k64(aQ, k), IDESC_S32, k);        // S^T  = K Q^T
 #pragma unroll
-        for (int k = 0; k < 2; ++k) umma_f16(tdPTu + sb * BWD_NT, desc_k64(aV, k), desc_k64(adO, k), IDESC_S32, k);    // dP^T = V dO^T
-        umma_commit(&bars->a_ready[sb]);
+        for (int k = 0; k < 2; ++k) umma_f16(tdPTu, desc_k64(aV, k), desc_k64(adO, k), IDESC_S32, k);    // dP^T = V dO^T
+        umma_commit(&bars->a_ready[0]);
       }
       __syncwarp();
       if (i >= 1) issue_dkv(i - 1);
@@ -635,65 +647,73 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const bool warp_all_mk = __all_sync(0xffffffffu, mk);
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     for (int i = 0; i < T; ++i) {
-      const int st = i & (KV_STAGES - 1), sb = i & 1;
-      mbar_wait(&bars->a_ready[sb], (i >> 1) & 1);
+      const int st = i % BWD_STAGES;
+      mbar_wait(&bars->kv_full[st], (i / BWD_STAGES) & 1);   // acquire the loader's per-query vectors
+      const uint32_t qva = smem_u32(&qv[st]);
+      const uint32_t wq = qv[st].mq;
+      const bool fast = warp_all_mk && wq == 0xffffffffu;
+      mbar_wait(&bars->a_ready[0], i & 1);
       tcgen05_fence_after();
-      uint32_t rs[32], rp[32];
-      tmem_ld_32x32(tmem + lane_addr + sb * BWD_NT, rs);
-      tmem_ld_32x32(tdPT + lane_addr + sb * BWD_NT, rp);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      mbar_arrive(&bars->s_free[sb]);
-      mbar_wait(&bars->kv_full[st], (i / KV_STAGES) & 1);   // acquire the loader's per-query vectors (already complete)
-      const QVec& v = qv[st];
-      const uint32_t wq = v.mq;
       uint32_t pp[16], pd[16];
-      if (warp_all_mk && wq == 0xffffffffu) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 nl = *reinterpret_cast<const float4*>(&v.nlse2[c]);
-          const float4 nd = *reinterpret_cast<const float4*>(&v.nds[c]);
-          const float p0 = ex2(fmaf(__uint_as_float(rs[c]), p.scale_log2, nl.x)), p1 = ex2(fmaf(__uint_as_float(rs[c + 1]), p.scale_log2, nl.y));
-          const float p2 = ex2(fmaf(__uint_as_float(rs[c + 2]), p.scale_log2, nl.z)), p3 = ex2(fmaf(__uint_as_float(rs[c + 3]), p.scale_log2, nl.w));
-          pp[c >> 1] = pack_bf16x2(p0, p1);
-          pp[(c >> 1) + 1] = pack_bf16x2(p2, p3);
-          pd[c >> 1] = pack_bf16x2(p0 * fmaf(__uint_as_float(rp[c]), p.scale, nd.x), p1 * fmaf(__uint_as_float(rp[c + 1]), p.scale, nd.y));
-          pd[(c >> 1) + 1] = pack_bf16x2(p2 * fmaf(__uint_as_float(rp[c + 2]), p.scale, nd.z), p3 * fmaf(__uint_as_float(rp[c + 3]), p.scale, nd.w));
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t rs[16], rp[16];
+        tmem_ld_32x32b_x16(tmem + lane_addr + hf * 16, rs);
+        tmem_ld_32x32b_x16(tdPT + lane_addr + hf * 16, rp);
+        tmem_ld_wait();
+        if (hf == 1) {
+          tcgen05_fence_before();
+          mbar_arrive(&bars->s_free[0]);
         }
-      } else {
+        if (fast) {                                      // branch hoisted out of the element loops: straight-line FFMA / EX2 code
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float pr[2], ds[2];
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int cc = c + t;
-            const bool valid = mk && (((wq >> cc) & 1u) != 0);
-            const float x = valid ? __uint_as_float(rs[cc]) * p.scale_log2 : p.fill_log2;
-            pr[t] = ex2(x + v.nlse2[cc]);                // queries past Lq: nlse2 = -inf => 0
-            ds[t] = valid ? pr[t] * fmaf(__uint_as_float(rp[cc]), p.scale, v.nds[cc]) : 0.f;
+          for (int c = 0; c < 16; c += 4) {
+            const float4 nl = lds_f4(qva + (hf * 16 + c) * 4), nd = lds_f4(qva + (NT + hf * 16 + c) * 4);
+            const float p0 = ex2(fmaf(__uint_as_float(rs[c]), p.scale_log2, nl.x)), p1 = ex2(fmaf(__uint_as_float(rs[c + 1]), p.scale_log2, nl.y));
+            const float p2 = ex2(fmaf(__uint_as_float(rs[c + 2]), p.scale_log2, nl.z)), p3 = ex2(fmaf(__uint_as_float(rs[c + 3]), p.scale_log2, nl.w));
+            pp[hf * 8 + (c >> 1)] = pack_bf16x2(p0, p1);
+            pp[hf * 8 + (c >> 1) + 1] = pack_bf16x2(p2, p3);
+            pd[hf * 8 + (c >> 1)] = pack_bf16x2(p0 * fmaf(__uint_as_float(rp[c]), p.scale, nd.x), p1 * fmaf(__uint_as_float(rp[c + 1]), p.scale, nd.y));
+            pd[hf * 8 + (c >> 1) + 1] = pack_bf16x2(p2 * fmaf(__uint_as_float(rp[c + 2]), p.scale, nd.z), p3 * fmaf(__uint_as_float(rp[c + 3]), p.scale, nd.w));
           }
-          pp[c >> 1] = pack_bf16x2(pr[0], pr[1]);
-          pd[c >> 1] = pack_bf16x2(ds[0], ds[1]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) {
+            const float4 nl = lds_f4(qva + (hf * 16 + c) * 4), nd = lds_f4(qva + (NT + hf * 16 + c) * 4);
+            const float nlv[4] = {nl.x, nl.y, nl.z, nl.w}, ndv[4] = {nd.x, nd.y, nd.z, nd.w};
+            float pr[4], ds[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int cc = c + t;
+              const bool valid = mk && (((wq >> (hf * 16 + cc)) & 1u) != 0);
+              const float x = valid ? __uint_as_float(rs[cc]) * p.scale_log2 : p.fill_log2;
+              pr[t] = ex2(x + nlv[t]);                   // queries past Lq: nlse2 = -inf => 0
+              ds[t] = valid ? pr[t] * fmaf(__uint_as_float(rp[cc]), p.scale, ndv[t]) : 0.f;
+            }
+            pp[hf * 8 + (c >> 1)] = pack_bf16x2(pr[0], pr[1]);
+            pp[hf * 8 + (c >> 1) + 1] = pack_bf16x2(pr[2], pr[3]);
+            pd[hf * 8 + (c >> 1)] = pack_bf16x2(ds[0], ds[1]);
+            pd[hf * 8 + (c >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
+          }
         }
       }
-      if (i >= 2) mbar_wait(&bars->p_free[sb], ((i >> 1) - 1) & 1);
-      write_row_sw64(sPT + sb * TILE128, row, pp);
-      write_row_sw64(sdST + sb * TILE128, row, pd);
+      if (i >= 1) mbar_wait(&bars->p_free[0], (i - 1) & 1);   // dK / dV products of tile i-1 have consumed the staging tiles
+      write_row_sw64(sPT, row, pp);
+      write_row_sw64(sdST, row, pd);
       fence_proxy_async_smem();
-      mbar_arrive(&bars->p_ready[sb]);
+      mbar_arrive(&bars->p_ready[0]);
     }
     mbar_wait(&bars->done, 0);
     tcgen05_fence_after();
-    uint32_t rk[32], rv[32];
+    uint32_t rk[32];
     tmem_ld_32x32(tdK + lane_addr, rk);
-    tmem_ld_32x32(tdV + lane_addr, rv);
     tmem_ld_wait();
-    if (k_in) {
-      if (p.dk != nullptr) store_row32_bf16(p.dk + ((int64_t)b * Lk + kj) * p.lddk + h * DH, rk, 1.0f);
-      if (p.dv != nullptr) store_row32_bf16(p.dv + ((int64_t)b * Lk + kj) * p.lddv + h * DH, rv, 1.0f);
-    }
+    if (k_in && p.dk != nullptr) store_row32_bf16(p.dk + ((int64_t)b * Lk + kj) * p.lddk + h * DH, rk, 1.0f);
+    tmem_ld_32x32(tdV + lane_addr, rk);
+    tmem_ld_wait();
+    if (k_in && p.dv != nullptr) store_row32_bf16(p.dv + ((int64_t)b * Lk + kj) * p.lddv + h * DH, rk, 1.0f);
   }
-  tmem_teardown(tmem, warp);
+  tmem_teardown(tmem, warp, 128);
 }
 
 // ====================================================================================== host
@@ -761,8 +781,8 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
       MMI_CHECK_ARG(a->dout && a->delta, "attn_tc bwd: null dout/delta");
       MMI_CHECK_ARG(a->lddo % 8 == 0, "attn_tc: lddo must be a multiple of 8");
       if (!map_rows(a->dout, a->lddo, q_rows, width, QT, &mdO)) return MMI_ECUDA;
-      const size_t T = (a->blk[0].Lk + BWD_NT - 1) / BWD_NT + (a->nblk > 1 ? (a->blk[1].Lk + BWD_NT - 1) / BWD_NT : 0);
-      const size_t smem = 3 * TILE128 + KV_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes + T * 4;
+      const size_t T = (a->blk[0].Lk + NT - 1) / NT + (a->nblk > 1 ? (a->blk[1].Lk + NT - 1) / NT : 0);
+      const size_t smem = 3 * TILE128 + BWD_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes + T * 4;
       if (smem > cfg_bytes[1]) { int rc = set_smem(attn_bwd_dq_tc_kernel, smem); if (rc) return rc; cfg_bytes[1] = smem; }
       attn_bwd_dq_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p);
     }
@@ -775,12 +795,12 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     p.dv = reinterpret_cast<__nv_bfloat16*>(s.dv); p.lddv = s.lddv;
     const int64_t k_rows = (int64_t)a->B * s.Lk;
     CUtensorMap mQ, mK, mV, mdO;
-    if (!map_rows(s.q, s.ldq, q_rows, width, BWD_NT, &mQ)) return MMI_ECUDA;
-    if (!map_rows(a->dout, a->lddo, q_rows, width, BWD_NT, &mdO)) return MMI_ECUDA;
+    if (!map_rows(s.q, s.ldq, q_rows, width, NT, &mQ)) return MMI_ECUDA;
+    if (!map_rows(a->dout, a->lddo, q_rows, width, NT, &mdO)) return MMI_ECUDA;
     if (!map_rows(s.k, s.ldk, k_rows, width, QT, &mK)) return MMI_ECUDA;
     if (!map_rows(s.v, s.ldv, k_rows, width, QT, &mV)) return MMI_ECUDA;
     dim3 grid((s.Lk + QT - 1) / QT, a->H, a->B);
-    const size_t smem = 2 * TILE128 + KV_STAGES * 2 * TILE32 + 4 * TILE128 + KV_STAGES * sizeof(QVec) + bar_bytes;
+    const size_t smem = 2 * TILE128 + 4 * 2 * TILE32 + 2 * TILE128 + BWD_STAGES * sizeof(QVec) + bar_bytes;
     if (smem > cfg_bytes[2]) { int rc = set_smem(attn_bwd_dkv_tc_kernel, smem); if (rc) return rc; cfg_bytes[2] = smem; }
     attn_bwd_dkv_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ, mK, mV, mdO, p);
   }

@@ -27,9 +27,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // suspend-time hint: sleep in hardware, do not spin
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) break;
     if (++spins > SPIN_LIMIT) __trap();  // a protocol bug must fail the launch, not hang the GPU
   }

@@ -112,12 +112,13 @@ int mmi_colsum_acc(const void* x, int dtype, int64_t M, int N, int64_t ldx, floa
  * stats[row] = (mean, rstd).                                                          */
 int mmi_layernorm_fwd(const void* x, int dtype, int64_t rows, int d, const float* gamma,
                       const float* beta, float eps, void* y, float* stats, mmi_stream_t stream);
-/* dx = LN'(dy) (+ add); dgamma += sum dy*xhat; dbeta += sum dy.
+/* dx = LN'(dy) (+ add); dgamma += sum dy*xhat; dbeta += sum dy; if dxsum: dxsum[c] += sum_rows dx[row, c]
+ * (the bias gradient of the Linear that produced the LayerNorm input, fused so dx is not read again).
  * workspace: at least mmi_layernorm_bwd_workspace(d) floats.                          */
 int64_t mmi_layernorm_bwd_workspace(int d);
 int mmi_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int d,
                       const float* gamma, const float* stats, const void* add, void* dx,
-                      float* dgamma, float* dbeta, float* workspace, mmi_stream_t stream);
+                      float* dgamma, float* dbeta, float* dxsum, float* workspace, mmi_stream_t stream);
 
 /* ---- a-5/a-6: candidate x history attention -----------------------------------------
  * replaces models/encoder.py:44-73 (get_attn_logits: QK^T, outer-product mask,

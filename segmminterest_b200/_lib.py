@@ -51,7 +51,7 @@ _SIGS = {
     "mmi_colsum_acc": (C.c_int, [c_p, C.c_int, i64, C.c_int, i64, c_p, c_p, i64, c_p]),
     "mmi_layernorm_fwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, C.c_float, c_p, c_p, c_p]),
     "mmi_layernorm_bwd_workspace": (i64, [C.c_int]),
-    "mmi_layernorm_bwd": (C.c_int, [c_p, c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "mmi_layernorm_bwd": (C.c_int, [c_p, c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmi_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), c_p]),
     "mmi_attn_bwd_dq": (C.c_int, [C.POINTER(AttnArgs), c_p]),
     "mmi_attn_bwd_dkv": (C.c_int, [C.POINTER(AttnArgs), C.c_int, c_p]),

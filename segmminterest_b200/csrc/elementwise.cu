@@ -137,17 +137,155 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
   }
 }
 
-// out[c] += sum_b partial[b][c]   (c < ncols); out2 takes the second half when split_at > 0
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int ncols, float* __restrict__ out_a,
-                                       float* __restrict__ out_b, int split_at) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncols) return;
+// bf16 fast path (d = 256 * NV): lane owns 8 consecutive columns per 16-byte vector, two rows per warp iteration so
+// that 128 B per lane are in flight; optionally also accumulates the column sums of dx (the bias gradient of the
+// Linear that produced the LayerNorm input -- saves a separate pass over dx).
+// partial layout: [gridDim.x][3][d]  (dgamma, dbeta, dxsum)
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& r, float* f) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint4 f32_to_bf16x8(const float* f) {
+  __nv_bfloat162 p[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return make_uint4(*reinterpret_cast<uint32_t*>(&p[0]), *reinterpret_cast<uint32_t*>(&p[1]), *reinterpret_cast<uint32_t*>(&p[2]), *reinterpret_cast<uint32_t*>(&p[3]));
+}
+
+template <int NV, bool WITH_DXSUM>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                                    int64_t rows, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ stats, const __nv_bfloat16* __restrict__ add,
+                                                                    __nv_bfloat16* __restrict__ dx, float* __restrict__ partial) {
+  extern __shared__ float sm[];  // [8 warps][3][d]
+  constexpr int d = 256 * NV;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * 8;
+  float gm[NV][8], dg[NV][8], db[NV][8], ds[WITH_DXSUM ? NV : 1][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 a = *reinterpret_cast<const float4*>(gamma + (lane + 32 * i) * 8), b = *reinterpret_cast<const float4*>(gamma + (lane + 32 * i) * 8 + 4);
+    gm[i][0] = a.x; gm[i][1] = a.y; gm[i][2] = a.z; gm[i][3] = a.w; gm[i][4] = b.x; gm[i][5] = b.y; gm[i][6] = b.z; gm[i][7] = b.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; if (WITH_DXSUM) ds[i][j] = 0.f; }
+  }
+  for (int64_t row0 = (int64_t)blockIdx.x * 8 + warp; row0 < rows; row0 += 2 * wstride) {
+    const int64_t rr[2] = {row0, row0 + wstride};
+    const bool in1 = rr[1] < rows;
+    uint4 xv[2][NV], dv[2][NV];
+    float2 st[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const bool in = r == 0 || in1;
+      const int64_t base = (in ? rr[r] : row0) * (int64_t)d;
+      st[r] = *reinterpret_cast<const float2*>(stats + 2 * (in ? rr[r] : row0));
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        xv[r][i] = ldg_stream(reinterpret_cast<const uint4*>(x + base) + lane + 32 * i);
+        dv[r][i] = ldg_stream(reinterpret_cast<const uint4*>(dy + base) + lane + 32 * i);
+      }
+    }
+    float c1[2] = {0.f, 0.f}, c2[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float xf[8], df[8];
+        bf16x8_to_f32(xv[r][i], xf);
+        bf16x8_to_f32(dv[r][i], df);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xf[j] - st[r].x) * st[r].y, g = df[j] * gm[i][j];
+          c1[r] += g;
+          c2[r] = fmaf(g, xh, c2[r]);
+          if (r == 0 || in1) { dg[i][j] = fmaf(df[j], xh, dg[i][j]); db[i][j] += df[j]; }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      c1[0] += __shfl_xor_sync(0xffffffffu, c1[0], o); c2[0] += __shfl_xor_sync(0xffffffffu, c2[0], o);
+      c1[1] += __shfl_xor_sync(0xffffffffu, c1[1], o); c2[1] += __shfl_xor_sync(0xffffffffu, c2[1], o);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (r == 1 && !in1) break;
+      const float m1 = c1[r] * (1.0f / d), m2 = c2[r] * (1.0f / d);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float xf[8], df[8], o[8];
+        bf16x8_to_f32(xv[r][i], xf);
+        bf16x8_to_f32(dv[r][i], df);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (xf[j] - st[r].x) * st[r].y;
+          o[j] = st[r].y * (df[j] * gm[i][j] - m1 - xh * m2);
+        }
+        if (add != nullptr) {
+          float af[8];
+          bf16x8_to_f32(*(reinterpret_cast<const uint4*>(add + rr[r] * (int64_t)d) + lane + 32 * i), af);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += af[j];
+        }
+        const uint4 packed = f32_to_bf16x8(o);
+        if (WITH_DXSUM) {                                  // sum what the next kernel will read (the rounded values)
+          float of[8];
+          bf16x8_to_f32(packed, of);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ds[i][j] += of[j];
+        }
+        stg_stream(reinterpret_cast<uint4*>(dx + rr[r] * (int64_t)d) + lane + 32 * i, packed);
+      }
+    }
+  }
+  // CTA reduction of the per-warp column sums (fixed order)
+  constexpr int NQ = WITH_DXSUM ? 3 : 2;
+  float* mine = sm + (size_t)warp * NQ * d;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mine[c + j] = dg[i][j];
+      mine[d + c + j] = db[i][j];
+      if (WITH_DXSUM) mine[2 * d + c + j] = ds[i][j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < NQ * d; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sm[(size_t)w * NQ * d + c];
+    partial[(size_t)blockIdx.x * NQ * d + c] = s;
+  }
+}
+
+// out_k[c'] += sum_b partial[b][c]  for column c = k * seg + c' (k-th output pointer, may be null).
+// block (32, 8): 8 row groups per column reduce through shared memory (fixed order => deterministic).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int ncols, int seg,
+                                                              float* __restrict__ out0, float* __restrict__ out1, float* __restrict__ out2) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * ncols + c];
-  if (split_at > 0 && c >= split_at) {
-    if (out_b) out_b[c - split_at] += s;
-  } else if (out_a) {
-    out_a[c] += s;
+  if (c < ncols) {
+    int b = threadIdx.y;
+    float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (; b + 24 < nblocks; b += 32) {
+      s += partial[(size_t)b * ncols + c]; s1 += partial[(size_t)(b + 8) * ncols + c];
+      s2 += partial[(size_t)(b + 16) * ncols + c]; s3 += partial[(size_t)(b + 24) * ncols + c];
+    }
+    for (; b < nblocks; b += 8) s += partial[(size_t)b * ncols + c];
+    s = (s + s1) + (s2 + s3);
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < ncols) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) s += red[w][threadIdx.x];
+    const int k = c / seg, cc = c - k * seg;
+    float* out = k == 0 ? out0 : (k == 1 ? out1 : out2);
+    if (out) out[cc] += s;
   }
 }
 
@@ -460,14 +598,39 @@ extern "C" int mmi_layernorm_fwd(const void* x, int dtype, int64_t rows, int d, 
   return MMI_OK;
 }
 
-extern "C" int64_t mmi_layernorm_bwd_workspace(int d) { return (int64_t)kRedCtas * 2 * d; }
+extern "C" int64_t mmi_layernorm_bwd_workspace(int d) { return (int64_t)kRedCtas * 3 * d; }
 
 extern "C" int mmi_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int d, const float* gamma, const float* stats,
-                                 const void* add, void* dx, float* dgamma, float* dbeta, float* workspace, mmi_stream_t stream) {
+                                 const void* add, void* dx, float* dgamma, float* dbeta, float* dxsum, float* workspace,
+                                 mmi_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MMI_CHECK_ARG(dy && x && gamma && stats && dx && workspace, "layernorm_bwd: null pointer");
   MMI_CHECK_ARG(d % 4 == 0 && d <= 128 * kMaxVecPerLane && d > 0, "layernorm: d=%d must be a multiple of 4 and <= %d", d, 128 * kMaxVecPerLane);
   if (rows == 0) return MMI_OK;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
+                      reinterpret_cast<uintptr_t>(add)) & 15) == 0;
+  if (dtype == MMI_BF16 && (d == 256 || d == 512 || d == 768 || d == 1024) && al16) {
+    // bandwidth path: 16-byte vectors, two rows per warp in flight, dx column sums fused
+    const int grid = grid_for_rows((rows + 1) / 2, 8, kNumSMs * 2);
+    const int nq = dxsum ? 3 : 2;
+    const size_t smem = (size_t)8 * nq * d * sizeof(float);
+#define MMI_LN_BWD16(NV_)                                                                                                     \
+  do {                                                                                                                        \
+    if (dxsum) {                                                                                                              \
+      if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_bf16_kernel<NV_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      layernorm_bwd_bf16_kernel<NV_, true><<<grid, 256, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, rows, gamma, stats, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, workspace); \
+    } else {                                                                                                                  \
+      if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_bf16_kernel<NV_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      layernorm_bwd_bf16_kernel<NV_, false><<<grid, 256, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, rows, gamma, stats, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, workspace); \
+    }                                                                                                                         \
+  } while (0)
+    if (d == 256) MMI_LN_BWD16(1); else if (d == 512) MMI_LN_BWD16(2); else if (d == 768) MMI_LN_BWD16(3); else MMI_LN_BWD16(4);
+#undef MMI_LN_BWD16
+    MMI_CHECK_LAUNCH();
+    reduce_partials_kernel<<<(nq * d + 31) / 32, dim3(32, 8), 0, st>>>(workspace, grid, nq * d, d, dgamma, dbeta, dxsum);
+    MMI_CHECK_LAUNCH();
+    return MMI_OK;
+  }
   const int grid = grid_for_rows(rows, 8, kRedCtas);
   const size_t smem = (size_t)8 * 2 * d * sizeof(float);
   const int nv = d <= 128 ? 1 : (d <= 256 ? 2 : (d <= 512 ? 4 : 8));
@@ -483,9 +646,11 @@ extern "C" int mmi_layernorm_bwd(const void* dy, const void* x, int dtype, int64
 #undef MMI_LN_BWD_NV
 #undef MMI_LN_BWD
   MMI_CHECK_LAUNCH();
-  if (dgamma || dbeta) {
-    reduce_partials_kernel<<<(2 * d + 255) / 256, 256, 0, st>>>(workspace, grid, 2 * d, dgamma, dbeta, d);
-    MMI_CHECK_LAUNCH();
+  reduce_partials_kernel<<<(2 * d + 31) / 32, dim3(32, 8), 0, st>>>(workspace, grid, 2 * d, d, dgamma, dbeta, nullptr);
+  MMI_CHECK_LAUNCH();
+  if (dxsum) {   // generic path: separate column-sum pass over dx
+    const int rc = mmi_colsum_acc(dx, dtype, rows, d, d, dxsum, workspace, mmi_layernorm_bwd_workspace(d), stream);
+    if (rc) return rc;
   }
   return MMI_OK;
 }
@@ -507,7 +672,7 @@ extern "C" int mmi_colsum_acc(const void* x, int dtype, int64_t M, int N, int64_
   else if (dtype == MMI_BF16) colsum_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, M, N, ldx, workspace);
   else { set_error("colsum: bad dtype %d", dtype); return MMI_EINVAL; }
   MMI_CHECK_LAUNCH();
-  reduce_partials_kernel<<<(N + 255) / 256, 256, 0, st>>>(workspace, (int)gy, N, out, nullptr, 0);
+  reduce_partials_kernel<<<(N + 31) / 32, dim3(32, 8), 0, st>>>(workspace, (int)gy, N, N, out, nullptr, nullptr);
   MMI_CHECK_LAUNCH();
   return MMI_OK;
 }
@@ -544,7 +709,7 @@ extern "C" int mmi_head_bwd(const void* x, int dtype, int64_t rows, int d, const
     else head_bwd_kernel<__nv_bfloat16, 8><<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, rows, d, w, dlogits, gscale, (__nv_bfloat16*)dx, workspace);
   } else { set_error("head_bwd: bad dtype %d", dtype); return MMI_EINVAL; }
   MMI_CHECK_LAUNCH();
-  reduce_partials_kernel<<<(d + 1 + 255) / 256, 256, 0, st>>>(workspace, grid, d + 1, dw, db, d);
+  reduce_partials_kernel<<<(d + 1 + 31) / 32, dim3(32, 8), 0, st>>>(workspace, grid, d + 1, d, dw, db, nullptr);
   MMI_CHECK_LAUNCH();
   return MMI_OK;
 }

@@ -226,10 +226,12 @@ class Engine:
         ops.gemm(GEMM_NT, self._impl(M, N, K, GEMM_NT), x, K, W, K, out, N, M, N, K, bias=self.w(bkey), act=act,
                  preact=preact, add=add, add_mod=add_mod, ld_add=ld_add, save_act_grad=self.use_tc and preact is not None)
 
-    def _linear_bwd(self, dy, x, M, N, K, wkey, bkey, dx, *, mul_gelu_grad=None, add=None, need_dx=True):
-        """dW += dy^T x ; db += colsum(dy) ; dx = dy W (* gelu'(mul)) (+ add)."""
+    def _linear_bwd(self, dy, x, M, N, K, wkey, bkey, dx, *, mul_gelu_grad=None, add=None, need_dx=True, bias_done=False):
+        """dW += dy^T x ; db += colsum(dy) ; dx = dy W (* gelu'(mul)) (+ add).  bias_done: the kernel that produced dy
+        (LayerNorm backward) already accumulated the bias gradient."""
         lp = self.cfg.precision == "bf16"
-        ops.colsum_acc(dy, M, N, N, self.g(bkey), self.red_ws)
+        if not bias_done:
+            ops.colsum_acc(dy, M, N, N, self.g(bkey), self.red_ws)
         impl_w = self._impl(N, K, M, GEMM_TN)
         if impl_w == IMPL_TC:
             split = 0  # auto: fill the SMs
@@ -381,16 +383,16 @@ class Engine:
                 pre = f"L{i}.{s}."
                 dp2 = scratch("dp2", s)
                 ops.layernorm_bwd(dX[s], a["p2"], Ts[s], d, self.w(pre + "ln2.g"), a["st2"], None, dp2, self.g(pre + "ln2.g"),
-                                  self.g(pre + "ln2.b"), self.red_ws)
+                                  self.g(pre + "ln2.b"), self.red_ws, dxsum=self.g(pre + "b2"))
                 dz1 = scratch("dz1", s)
-                self._linear_bwd(dp2, a["g1"], Ts[s], d, d, pre + "w2", pre + "b2", dz1, mul_gelu_grad=a["z1"])
+                self._linear_bwd(dp2, a["g1"], Ts[s], d, d, pre + "w2", pre + "b2", dz1, mul_gelu_grad=a["z1"], bias_done=True)
                 dx1 = scratch("dx1", s)
                 self._linear_bwd(dz1, a["x1"], Ts[s], d, d, pre + "w1", pre + "b1", dx1, add=dp2)
                 dp1 = scratch("dp1", s)
                 ops.layernorm_bwd(dx1, a["p1"], Ts[s], d, self.w(pre + "ln1.g"), a["st1"], None, dp1, self.g(pre + "ln1.g"),
-                                  self.g(pre + "ln1.b"), self.red_ws)
+                                  self.g(pre + "ln1.b"), self.red_ws, dxsum=self.g(pre + "bo"))
                 da = scratch("da", s)
-                self._linear_bwd(dp1, lay["attn"][s][1], Ts[s], d, d, pre + "wo", pre + "bo", da)
+                self._linear_bwd(dp1, lay["attn"][s][1], Ts[s], d, d, pre + "wo", pre + "bo", da, bias_done=True)
                 dP1[s], dA[s] = dp1, da
             dqkv = {s: scratch("dqkv", s, nq[s] * d) for s in ("vid", "usr")}
             esz = dqkv["vid"].element_size()
@@ -426,11 +428,11 @@ class Engine:
             if dX[s] is None:
                 continue
             ops.layernorm_bwd(dX[s], sv[f"emb_pre.{s}"], Ts[s], d, self.w(f"{s}_ln.g"), sv[f"emb_st.{s}"], None, de,
-                              self.g(f"{s}_ln.g"), self.g(f"{s}_ln.b"), self.red_ws)
+                              self.g(f"{s}_ln.g"), self.g(f"{s}_ln.b"), self.red_ws, dxsum=self.g(f"{s}_proj.b"))
             if cfg.use_pe:
                 # d pe[l,:] = sum_b dE[b,l,:]  -> column sums of dE viewed as [B, L*d]
                 ops.colsum_acc(de, B, Ls[s] * d, Ls[s] * d, self.g(f"{s}_pe")[: Ls[s] * d], self.red_ws)
-            self._linear_bwd(de, sv["x_in"][s], Ts[s], d, din[s], f"{s}_proj.w", f"{s}_proj.b", None, need_dx=False)
+            self._linear_bwd(de, sv["x_in"][s], Ts[s], d, din[s], f"{s}_proj.w", f"{s}_proj.b", None, need_dx=False, bias_done=True)
         if on_ready is not None:
             on_ready(0)
         self._saved = None

@@ -98,12 +98,13 @@ def layernorm_fwd(x, rows, d, gamma, beta, y, stats, eps=1e-12):
     LaunchCounter.n += 1
 
 
-def layernorm_bwd(dy, x, rows, d, gamma, stats, add, dx, dgamma, dbeta, ws):
+def layernorm_bwd(dy, x, rows, d, gamma, stats, add, dx, dgamma, dbeta, ws, dxsum=None):
+    """dxsum (optional, fp32 [d]) += column sums of dx: the bias gradient of the Linear feeding this LayerNorm."""
     lib = _lib.load()
     assert ws.numel() >= lib.mmi_layernorm_bwd_workspace(d)
     with TIMER.region("ln_bwd"):
         rc = lib.mmi_layernorm_bwd(dy.data_ptr(), x.data_ptr(), dt(x), rows, d, gamma.data_ptr(), stats.data_ptr(), _ptr(add),
-                                   dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), ws.data_ptr(), _stream())
+                                   dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), ws.data_ptr(), _stream())
     _lib.check(rc, "mmi_layernorm_bwd")
     LaunchCounter.n += 2
 

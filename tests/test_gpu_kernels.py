@@ -121,12 +121,11 @@ def test_gemm_simt_epilogue(dev):
 
 
 # ----------------------------------------------------------------------------- LayerNorm, colsum, head
-@pytest.mark.parametrize("d", [64, 512])
+@pytest.mark.parametrize("d,rows", [(64, 777), (512, 777), (256, 5001), (768, 130), (1024, 33)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_layernorm_fwd_bwd(dev, d, dtype):
+def test_layernorm_fwd_bwd(dev, d, rows, dtype):
     from segmminterest_b200 import _lib, ops
     torch.manual_seed(2)
-    rows = 777
     x = (torch.randn(rows, d, device=dev) * 2 + 0.5).to(dtype)
     g, b = torch.randn(d, device=dev), torch.randn(d, device=dev)
     dy, add = torch.randn(rows, d, device=dev).to(dtype), torch.randn(rows, d, device=dev).to(dtype)
@@ -145,6 +144,13 @@ def test_layernorm_fwd_bwd(dev, d, dtype):
     ops.layernorm_bwd(dy, x, rows, d, g, st, add, dx, dg, db, ws)
     assert _rel(dx, xr.grad + add.double()) < tol
     assert _rel(dg - 1, gr.grad) < tol and _rel(db - 1, br.grad) < tol
+    # fused column sums of dx (bias gradient of the Linear feeding the LayerNorm), accumulate semantics, no residual
+    dx2, dxs = torch.empty_like(x), torch.full((d,), 2.0, device=dev)
+    dg2, db2 = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    ops.layernorm_bwd(dy, x, rows, d, g, st, None, dx2, dg2, db2, ws, dxsum=dxs)
+    assert _rel(dx2, xr.grad) < tol
+    assert _rel(dg2, gr.grad) < tol and _rel(db2, br.grad) < tol
+    assert _rel(dxs - 2, dx2.double().sum(0)) < 1e-5
 
 
 def test_colsum_and_head(dev):

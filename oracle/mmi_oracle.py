@@ -266,3 +266,23 @@ def clip_and_adamw(params, grads, exp_avg, exp_avg_sq, step, lr=1e-3, wd=1e-4, b
         denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
         p.addcdiv_(m, denom, value=-lr / bc1)
     return total
+
+
+# --------------------------------------------------------------------------
+# a-15  parity metric: per-segment skip AUC
+# --------------------------------------------------------------------------
+def prob_auc_batch(logits, gt, exposure_prob=None):
+    """models/my_evaluation.py:73-80 (ProbAUC_batch) fed as main_eval_batch does (:264-284) from
+    main_for_seq_leave_earlystop_SegMM.py:402-403: interests = sigmoid(logits) * exposure_prob,
+    survival = exp(cumsum(log interests)); positions with gt != -2; label -1 -> 0;
+    sklearn.metrics.roc_auc_score on the flattened batch."""
+    from sklearn.metrics import roc_auc_score
+    logits = torch.as_tensor(logits, dtype=torch.float32)
+    gt = torch.as_tensor(gt)
+    ep = torch.ones(logits.shape[1]) if exposure_prob is None else torch.as_tensor(exposure_prob, dtype=torch.float32)
+    interests = torch.sigmoid(logits) * ep[None, :]
+    survival = torch.exp(torch.cumsum(torch.log(interests), dim=1))
+    mask = gt != -2
+    labels = gt[mask]
+    labels = torch.where(labels == -1, torch.zeros_like(labels), labels)
+    return float(roc_auc_score(labels.numpy().ravel(), survival[mask].numpy().ravel()))

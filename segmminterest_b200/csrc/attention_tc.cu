@@ -200,8 +200,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
 
   if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
   build_key_bits<NT>(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
+  if (warp == 4) TRACE(4090);
   const uint32_t tmem = tmem_setup(bars, warp, 128);
   const uint32_t tO = tmem + 2 * NT;
+  if (warp == 4) TRACE(4091);
 
   if (warp == 0) {
     // warp-uniform producer loop: all lanes wait for the free stage, one elected lane issues the TMA
@@ -213,7 +215,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
     __syncwarp();
     for (int j = 0; j < T; ++j) {
       const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j % FWD_STAGES;
-      mbar_wait(&bars->kv_empty[st], ((j / FWD_STAGES) & 1) ^ 1);
+      mbar_wait_bg(&bars->kv_empty[st], ((j / FWD_STAGES) & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
         uint8_t* dst = sKV + st * 2 * TILE32;
@@ -229,7 +231,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
     mbar_wait(&bars->once, 0);
     auto issue_pv = [&](int u) {                         // O += P(u) V(u)
       const int pb = u & 1, st = u % FWD_STAGES;
-      mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
+      mbar_wait_bg(&bars->p_ready[pb], (u >> 1) & 1);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint32_t aP = smem_u32(sP + pb * TILE128), aV = smem_u32(sKV + st * 2 * TILE32 + TILE32);
@@ -242,8 +244,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
     };
     for (int j = 0; j < T; ++j) {
       const int blk = j < nt0 ? 0 : 1, st = j % FWD_STAGES, sb = j & 1;
-      mbar_wait(&bars->kv_full[st], (j / FWD_STAGES) & 1);
-      if (j >= 2) mbar_wait(&bars->s_free[sb], ((j >> 1) - 1) & 1);
+      mbar_wait_bg(&bars->kv_full[st], (j / FWD_STAGES) & 1);
+      if (j >= 2) mbar_wait_bg(&bars->s_free[sb], ((j >> 1) - 1) & 1);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint32_t aQ = smem_u32(sQ + blk * TILE128), aK = smem_u32(sKV + st * 2 * TILE32);
@@ -272,13 +274,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
       const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, sb = j & 1;
       const int nvalid = min(NT, (blk ? p.Lk[1] : p.Lk[0]) - kt * NT);
       const uint32_t wv = kbits[j], wr = range_bits32(0, nvalid);
+      if (warp == 4) TRACE(j * 8 + 0);
       mbar_wait(&bars->a_ready[sb], (j >> 1) & 1);       // S(j) ready; P buffer sb consumed by P V (j-2)
+      if (warp == 4) TRACE(j * 8 + 1);
       tcgen05_fence_after();
       uint32_t r[32];
       tmem_ld_32x32(tmem + lane_addr + sb * NT, r);
       tmem_ld_wait();
       tcgen05_fence_before();
       mbar_arrive(&bars->s_free[sb]);
+      if (warp == 4) TRACE(j * 8 + 2);
       // ---- tile maximum in the log2 domain
       float t;
       {
@@ -337,10 +342,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
           pk[c >> 1] = pack_bf16x2(e[0], e[1]);
         }
       }
+      if (warp == 4) TRACE(j * 8 + 3);
       write_row_sw64(sP + sb * TILE128, row, pk);
       fence_proxy_async_smem();
       mbar_arrive(&bars->p_ready[sb]);
+      if (warp == 4) TRACE(j * 8 + 4);
     }
+    if (warp == 4) TRACE(4093);
     mbar_wait(&bars->done, 0);
     tcgen05_fence_after();
     uint32_t ro[32];
@@ -351,6 +359,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
       store_row32_bf16(p.out + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH, ro, 1.0f / l);
       p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = m * kLn2 + logf(l);
     }
+    if (warp == 4) TRACE(4092);
   }
   tmem_teardown(tmem, warp, 128);
 }
@@ -399,7 +408,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
     __syncwarp();
     for (int j = 0; j < T; ++j) {
       const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j % BWD_STAGES;
-      mbar_wait(&bars->kv_empty[st], ((j / BWD_STAGES) & 1) ^ 1);
+      mbar_wait_bg(&bars->kv_empty[st], ((j / BWD_STAGES) & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
         uint8_t* dst = sKV + st * 2 * TILE32;
@@ -415,7 +424,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
     const uint32_t adO = smem_u32(sdO);
     auto issue_dq = [&](int u) {                       // dQ[blk(u)] += dS(u) K(u)
       const int pb = u & 1, st = u % BWD_STAGES, blk = u < nt0 ? 0 : 1, kt = blk ? u - nt0 : u;
-      mbar_wait(&bars->p_ready[pb], (u >> 1) & 1);
+      mbar_wait_bg(&bars->p_ready[pb], (u >> 1) & 1);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint32_t adS = smem_u32(sdS + pb * TILE128), aK = smem_u32(sKV + st * 2 * TILE32);
@@ -427,8 +436,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
     };
     for (int j = 0; j < T; ++j) {
       const int blk = j < nt0 ? 0 : 1, st = j % BWD_STAGES;
-      mbar_wait(&bars->kv_full[st], (j / BWD_STAGES) & 1);
-      if (j >= 1) mbar_wait(&bars->s_free[0], (j - 1) & 1);
+      mbar_wait_bg(&bars->kv_full[st], (j / BWD_STAGES) & 1);
+      if (j >= 1) mbar_wait_bg(&bars->s_free[0], (j - 1) & 1);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint32_t aQ = smem_u32(sQ + blk * TILE128), aK = smem_u32(sKV + st * 2 * TILE32), aV = aK + TILE32;
@@ -585,7 +594,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const float lse_c = lse_n, delta_c = delta_n;
       const bool mq_c = mq_n != 0;
       if (i + 1 < T) fetch(i + 1);
-      mbar_wait(&bars->kv_empty[st], ((i / BWD_STAGES) & 1) ^ 1);
+      mbar_wait_bg(&bars->kv_empty[st], ((i / BWD_STAGES) & 1) ^ 1);
       qv[st].nlse2[lane] = -lse_c * kLog2e;              // queries past Lq: -inf => P = 0
       qv[st].nds[lane] = -delta_c * p.scale;
       const uint32_t mqb = __ballot_sync(0xffffffffu, mq_c);
@@ -607,7 +616,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t aPT = smem_u32(sPT), adST = smem_u32(sdST);
     auto issue_dkv = [&](int u) {
       const int st = u % BWD_STAGES;
-      mbar_wait(&bars->p_ready[0], u & 1);
+      mbar_wait_bg(&bars->p_ready[0], u & 1);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE32), adO = aQ + TILE32;
@@ -622,8 +631,8 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     };
     for (int i = 0; i < T; ++i) {
       const int st = i % BWD_STAGES;
-      mbar_wait(&bars->kv_full[st], (i / BWD_STAGES) & 1);
-      if (i >= 1) mbar_wait(&bars->s_free[0], (i - 1) & 1);
+      mbar_wait_bg(&bars->kv_full[st], (i / BWD_STAGES) & 1);
+      if (i >= 1) mbar_wait_bg(&bars->s_free[0], (i - 1) & 1);
       tcgen05_fence_after();
       if (elect_one()) {
         const uint32_t aQ = smem_u32(sQdO + st * 2 * TILE32), adO = aQ + TILE32;

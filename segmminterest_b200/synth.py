@@ -86,6 +86,30 @@ def make_indices(batch: int, lt: int, nv_max: int, n_rows: int, seed: int = 2025
     return usr_idx, vid_idx, gt
 
 
+def make_teacher_batch(table: np.ndarray, batch: int, lt: int, nv_max: int, seed: int, w_seed: int = 7, quantile: float = 0.25):
+    """Planted-teacher labels for the AUC parity check: the viewer skips at the first candidate
+    segment whose <w*, e_seg> + <w*, mean(history rows)> falls below a threshold (fixed w*, seed 7), so the
+    per-segment skip AUC of a trained model is well above 0.5.  Ragged histories and candidates."""
+    n_rows, din = table.shape
+    usr_idx, vid_idx, _ = make_indices(batch, lt, nv_max, n_rows, seed=seed, ragged=True)
+    w = np.random.default_rng(w_seed).standard_normal(din).astype(np.float32) / np.sqrt(din)
+    proj = table.astype(np.float32) @ w                              # teacher score of every table row
+    thr = np.quantile(proj, quantile)
+    gt = np.full((batch, PHOTO_MAX), PAD_LABEL, dtype=np.int64)
+    for b in range(batch):
+        hist = usr_idx[b][usr_idx[b] >= 0]
+        bias = 0.5 * (proj[hist].mean() if hist.size else 0.0)
+        rows = vid_idx[b][vid_idx[b] >= 0]
+        n = rows.size
+        below = np.nonzero(proj[rows] + bias < thr)[0]
+        v = int(below[0]) if below.size else n                     # first skipped segment (n = watched to the end)
+        gt[b, :v] = 1
+        if v < n:
+            gt[b, v] = 0
+            gt[b, v + 1:n] = -1
+    return usr_idx, vid_idx, gt
+
+
 def make_dense_batch(rng: np.random.Generator, B: int, Lt: int, din: int, full: bool = False):
     """Dense, already L1-normalised inputs in the form the reference driver hands
     to the model (main_for_seq_leave_earlystop_SegMM.py:271-284), ragged lengths."""

@@ -28,17 +28,10 @@ lib = _lib.load()
 lib.mmi_debug_trace.argtypes = [C.c_void_p, C.c_int]
 print("rc", lib.mmi_debug_trace(buf, 8192))
 t = list(buf)
-T = 9
+T = 17
 base = t[4090]
-print("cta: before tmem_setup 0, after", t[4091] - base, "end", t[4092] - base)
-print("softmax warp 4 (rows 0-31, cols 0-31): per tile [wait_a_ready, ld+arrive, compute, wait_p_free, write+arrive] start@")
-for jj in range(2 * T):
-    s = t[jj * 8: jj * 8 + 6]
-    if jj < T:
-        print(f"  p1 jj={jj:2d} start@{s[0]-base:6d}  wait {s[1]-s[0]:5d}  ld {s[2]-s[1]:5d}")
-    else:
-        print(f"  p2 jj={jj:2d} start@{s[0]-base:6d}  wait {s[1]-s[0]:5d}  ld {s[2]-s[1]:5d}  compute {s[3]-s[2]:5d}  pfree {s[4]-s[3]:5d}  write {s[5]-s[4]:5d}")
-print("mma thread: per jj [wait kv_full, wait s_free, issue S, issue_pv(wait p_ready + PV)]")
-for jj in range(2 * T):
-    s = t[2048 + jj * 8: 2048 + jj * 8 + 8]
-    print(f"  jj={jj:2d} start@{s[0]-base:6d}  kv_full {s[1]-s[0]:5d}  s_free {s[2]-s[1]:5d}  fence {s[5]-s[2]:4d} umma2 {s[6]-s[5]:4d} commit {s[7]-s[6]:4d} commit2 {s[3]-s[7]:4d}  pv {s[4]-s[3]:5d}")
+print("cta: tmem_setup done @", t[4091] - base, " last tile done @", t[4093] - base, " end @", t[4092] - base)
+print("softmax warp 4 per tile: start@, wait a_ready, ld+arrive, max+exp, write+arrive")
+for j in range(T):
+    s = t[j * 8: j * 8 + 5]
+    print(f"  j={j:2d} start@{s[0]-base:6d}  wait {s[1]-s[0]:5d}  ld {s[2]-s[1]:5d}  compute {s[3]-s[2]:5d}  write {s[4]-s[3]:5d}")

@@ -259,38 +259,64 @@ def main():
     e2e_val = K * B * world / (ms_e2e * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
-    # ---- per-kernel CUDA-event pass for the roofline -------------------------------------------------
+    # ---- per-kernel CUDA-event pass for the roofline (one category per kernel AND launch shape) ----------------
     TIMER.enabled = True
+    TIMER.detail = True
     TIMER.reset()
     barrier()
     for i in range(K):
         ts.step(*devb[i % n_batches])
     summ = TIMER.summary()
     TIMER.enabled = False
+    TIMER.detail = False
     pk = peaks()
     tot_ms = sum(v["ms"] for v in summ.values())
     dom = max(summ, key=lambda k: summ[k]["ms"])
     d = summ[dom]
-    if dom == "gather":
+    traffic_db = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic_db = json.load(open(tp))
+    tr = traffic_db.get(dom)
+    if dom.startswith("gather"):
         ach = d["work"] / (d["ms"] * 1e-3) / 1e9
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None}
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
     else:
         ach = d["work"] / (d["ms"] * 1e-3) / 1e12
-        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                "traffic": None}
+        roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"]}
+    roof["traffic"] = tr["dram_bytes_per_launch"] if tr else None
+    if tr:
+        roof["traffic_source"] = tr.get("source")
     roof["peak_source"] = pk["src"] + (" (sustained bf16, kernel timed inside a long step)" if roof["bound"] == "tensor" else "")
     roof["share_of_step"] = d["ms"] / tot_ms
     roof["avg_launch_ms"] = d["ms"] / d["launches"]
+    roof["launches_per_step"] = d["launches"] // K
+    if dom.startswith("attn"):
+        roof["note"] = ("head dim 32: one ex2 per score against 128 tensor FLOPs, so this kernel is bounded by the MUFU / issue "
+                        "pipes (16 ex2/clk/SM), not by the tensor pipe the FLOP count is divided by")
+
+    def family(k):
+        return k.split(" ")[0]
+    fam = {}
+    for k, v in summ.items():
+        f = fam.setdefault(family(k), {"ms": 0.0, "launches": 0, "work": 0.0})
+        f["ms"] += v["ms"]; f["launches"] += v["launches"]; f["work"] += v["work"]
     breakdown = {k: {"ms_per_step": round(v["ms"] / K, 3), "launches_per_step": v["launches"] // K,
                      "achieved": (round(v["work"] / (v["ms"] * 1e-3) / (1e9 if k == "gather" else 1e12), 2) if v["work"] else None)}
-                 for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
+                 for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
     # gather roofline is always reported too (HBM-bound stage the north star names)
-    if "gather" in summ:
-        gsum = summ["gather"]
+    if "gather" in fam:
+        gsum = fam["gather"]
         gbs = gsum["work"] / (gsum["ms"] * 1e-3) / 1e9
         gather_roof = {"achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}
     else:
         gather_roof = None
+    # tensor-pipe utilisation of all GEMM launches together (north star: >= 50 %)
+    gemm_roof = None
+    if "gemm_tc" in fam:
+        gs = fam["gemm_tc"]
+        tf = gs["work"] / (gs["ms"] * 1e-3) / 1e12
+        gemm_roof = {"achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"], "ms_per_step": gs["ms"] / K}
 
     line = {"metric": "train_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -301,7 +327,7 @@ def main():
                        "dropout": "off (parity mode)", "l2": "activations/step >> 126 MB L2 (inputs larger than L2, no flush needed)"},
             "e2e": {"value": e2e_val, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "gather_roofline": gather_roof,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "gather_roofline": gather_roof, "gemm_roofline": gemm_roof,
             "kernel_breakdown": breakdown, "loss_last": loss_last, "use_tc": bool(ts.engine.use_tc)}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -134,8 +134,15 @@ class AttnSide:
         lk = sum(a.blk[i].Lk for i in range(a.nblk)) if which is None else a.blk[which].Lk
         return 4.0 * a.B * a.H * a.Lq * lk * a.dh
 
+    def _cat(self, name, which=None):
+        if not TIMER.detail:
+            return name
+        a = self.a
+        lk = "+".join(str(a.blk[i].Lk) for i in range(a.nblk)) if which is None else str(a.blk[which].Lk)
+        return f"{name} B={a.B} H={a.H} Lq={a.Lq} Lk={lk}"
+
     def fwd(self):
-        with TIMER.region("attn_fwd", self.flops()):
+        with TIMER.region(self._cat("attn_fwd"), self.flops()):
             rc = _lib.load().mmi_attn_fwd(C.byref(self.a), _stream())
         _lib.check(rc, "mmi_attn_fwd")
         LaunchCounter.n += 1
@@ -150,13 +157,13 @@ class AttnSide:
             k.dv, k.lddv = g["dv"]
 
     def bwd_dq(self):
-        with TIMER.region("attn_bwd_dq", 1.5 * self.flops()):
+        with TIMER.region(self._cat("attn_bwd_dq"), 1.5 * self.flops()):
             rc = _lib.load().mmi_attn_bwd_dq(C.byref(self.a), _stream())
         _lib.check(rc, "mmi_attn_bwd_dq")
         LaunchCounter.n += 1
 
     def bwd_dkv(self, which):
-        with TIMER.region("attn_bwd_dkv", 2.0 * self.flops(which)):
+        with TIMER.region(self._cat("attn_bwd_dkv", which), 2.0 * self.flops(which)):
             rc = _lib.load().mmi_attn_bwd_dkv(C.byref(self.a), which, _stream())
         _lib.check(rc, "mmi_attn_bwd_dkv")
         LaunchCounter.n += 1

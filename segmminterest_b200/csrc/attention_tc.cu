@@ -73,10 +73,10 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 // 32 bf16 = the whole row `row` of a [rows x 64 B] SWIZZLE_64B K-major tile (address bits [4,6) ^= bits [7,9))
-__device__ __forceinline__ void write_row_sw64(uint8_t* tile, int row, const uint32_t (&w)[16]) {
+// row_addr = shared-space address of the row (tile + row * 64); swz = (row >> 1) & 3
+__device__ __forceinline__ void write_row_sw64(uint32_t row_addr, uint32_t swz, const uint32_t (&w)[16]) {
 #pragma unroll
-  for (int v = 0; v < 4; ++v)
-    *reinterpret_cast<uint4*>(tile + row * 64 + ((v ^ ((row >> 1) & 3)) << 4)) = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+  for (uint32_t v = 0; v < 4; ++v) sts_u4(row_addr + ((v ^ swz) << 4), w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
 }
 // bit c of the result = mask[base + off + c] != 0 for off + c < count, whole warp participates
 __device__ __forceinline__ uint32_t mask_bits32(const uint8_t* mask, int64_t base, int off, int count, int lane) {
@@ -92,16 +92,13 @@ __device__ __forceinline__ uint32_t range_bits32(int off, int count) {   // bit 
 // Key-validity bit words of every key tile of the CTA, built ONCE (all warps, before the role split) so that the
 // softmax loop reads them from shared memory instead of paying a global-load latency per tile.
 // words_per_tile = tile_cols / 32; word w of tile j covers keys [j_k0 + 32 w, +32); bits past Lk are 0.
-template <int TILE_COLS>
-__device__ __forceinline__ void build_key_bits(uint32_t* kb, const AttnTcParams& p, int b, int nt0, int T, int warp, int lane, int nwarps) {
-  constexpr int WPT = TILE_COLS / 32;
-  for (int w = warp; w < T * WPT; w += nwarps) {
-    const int j = w / WPT, sub = w % WPT;
+// entry j = {valid bits, in-range bits} of the 32 keys of tile j
+__device__ __forceinline__ void build_key_bits(uint2* kb, const AttnTcParams& p, int b, int nt0, int T, int warp, int lane, int nwarps) {
+  for (int j = warp; j < T; j += nwarps) {
     const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
     const int Lk = blk ? p.Lk[1] : p.Lk[0];
-    const int k0 = kt * TILE_COLS + sub * 32;
-    const uint32_t bits = mask_bits32(blk ? p.mask_k[1] : p.mask_k[0], (int64_t)b * Lk, k0, Lk, lane);
-    if (lane == 0) kb[w] = bits;
+    const uint32_t bits = mask_bits32(blk ? p.mask_k[1] : p.mask_k[0], (int64_t)b * Lk, kt * NT, Lk, lane);
+    if (lane == 0) kb[j] = make_uint2(bits, range_bits32(kt * NT, Lk));
   }
 }
 
@@ -189,7 +186,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
   uint8_t* sKV = sQ + 2 * TILE128;
   uint8_t* sP = sKV + FWD_STAGES * 2 * TILE32;
   Bars* bars = reinterpret_cast<Bars*>(sP + 2 * TILE128);
-  uint32_t* kbits = reinterpret_cast<uint32_t*>(bars + 1);
+  uint2* kbits = reinterpret_cast<uint2*>(bars + 1);
 
   const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp index in a uniform register
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
@@ -199,7 +196,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
   const int nact = (rows_valid + 31) >> 5;                  // softmax warps with at least one real query
 
   if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
-  build_key_bits<NT>(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
+  build_key_bits(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
   if (warp == 4) TRACE(4090);
   const uint32_t tmem = tmem_setup(bars, warp, 128);
   const uint32_t tO = tmem + 2 * NT;
@@ -270,19 +267,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
     const float scale_t = mq ? p.scale_log2 : 0.f;       // x = s * scale_t + base_t  (a padded query sees `fill` everywhere)
     const float base_t = mq ? 0.f : p.fill_log2;
     float m = 0.f, l0 = 0.f, l1 = 0.f;
+    // shared-space addresses of everything the loop touches, computed once
+    const uint32_t a_ready_a = smem_u32(&bars->a_ready[0]), s_free_a = smem_u32(&bars->s_free[0]), p_ready_a = smem_u32(&bars->p_ready[0]);
+    const uint32_t kb_a = smem_u32(kbits), prow_a = smem_u32(sP) + row * 64, swz = (row >> 1) & 3;
+    const uint32_t tS_row = tmem + lane_addr;
     for (int j = 0; j < T; ++j) {
-      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, sb = j & 1;
-      const int nvalid = min(NT, (blk ? p.Lk[1] : p.Lk[0]) - kt * NT);
-      const uint32_t wv = kbits[j], wr = range_bits32(0, nvalid);
+      const uint32_t sb = j & 1;
+      const uint2 kb = lds_u2(kb_a + j * 8);
+      const uint32_t wv = kb.x, wr = kb.y;
       if (warp == 4) TRACE(j * 8 + 0);
-      mbar_wait(&bars->a_ready[sb], (j >> 1) & 1);       // S(j) ready; P buffer sb consumed by P V (j-2)
+      mbar_wait_a(a_ready_a + sb * 8, (j >> 1) & 1);     // S(j) ready; P buffer sb consumed by P V (j-2)
       if (warp == 4) TRACE(j * 8 + 1);
       tcgen05_fence_after();
       uint32_t r[32];
-      tmem_ld_32x32(tmem + lane_addr + sb * NT, r);
+      tmem_ld_32x32(tS_row + sb * NT, r);
       tmem_ld_wait();
       tcgen05_fence_before();
-      mbar_arrive(&bars->s_free[sb]);
+      mbar_arrive_a(s_free_a + sb * 8);
       if (warp == 4) TRACE(j * 8 + 2);
       // ---- tile maximum in the log2 domain
       float t;
@@ -343,9 +344,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
         }
       }
       if (warp == 4) TRACE(j * 8 + 3);
-      write_row_sw64(sP + sb * TILE128, row, pk);
+      write_row_sw64(prow_a + sb * TILE128, swz, pk);
       fence_proxy_async_smem();
-      mbar_arrive(&bars->p_ready[sb]);
+      mbar_arrive_a(p_ready_a + sb * 8);
       if (warp == 4) TRACE(j * 8 + 4);
     }
     if (warp == 4) TRACE(4093);
@@ -384,7 +385,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
   uint8_t* sKV = sdO + TILE128;
   uint8_t* sdS = sKV + BWD_STAGES * 2 * TILE32;           // 36 KB from the base: still 1024-aligned
   Bars* bars = reinterpret_cast<Bars*>(sdS + 2 * TILE128);
-  uint32_t* kbits = reinterpret_cast<uint32_t*>(bars + 1);
+  uint2* kbits = reinterpret_cast<uint2*>(bars + 1);
 
   const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp index in a uniform register
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
@@ -394,7 +395,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
   const int nact = (rows_valid + 31) >> 5;
 
   if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
-  build_key_bits<NT>(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
+  build_key_bits(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
   const uint32_t tmem = tmem_setup(bars, warp, 128);
   const uint32_t tdP = tmem + NT, tdQ = tmem + 2 * NT;
 
@@ -474,11 +475,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
       p.delta[li] = delta;
     }
     const float nds = -delta * p.scale;                  // dS = P * (dP * scale + nds)
+    const uint32_t a_ready_a = smem_u32(&bars->a_ready[0]), s_free_a = smem_u32(&bars->s_free[0]), p_ready_a = smem_u32(&bars->p_ready[0]);
+    const uint32_t kb_a = smem_u32(kbits), dsrow_a = smem_u32(sdS) + row * 64, swz = (row >> 1) & 3;
     for (int j = 0; j < T; ++j) {
-      const int pb = j & 1;
-      const uint32_t wv = kbits[j];
+      const uint32_t pb = j & 1;
+      const uint32_t wv = lds_u1(kb_a + j * 8);
       const bool fast = warp_all_mq && wv == 0xffffffffu;
-      mbar_wait(&bars->a_ready[0], j & 1);               // S(j), dP(j) ready; dS buffer pb consumed by dQ (j-2)
+      mbar_wait_a(a_ready_a, j & 1);                     // S(j), dP(j) ready; dS buffer pb consumed by dQ (j-2)
       tcgen05_fence_after();
       uint32_t pk[16];
 #pragma unroll
@@ -489,7 +492,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
         tmem_ld_wait();
         if (hf == 1) {                                   // the whole tile is in registers: hand the buffers back
           tcgen05_fence_before();
-          mbar_arrive(&bars->s_free[0]);
+          mbar_arrive_a(s_free_a);
         }
         if (fast) {
 #pragma unroll
@@ -512,9 +515,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
           }
         }
       }
-      write_row_sw64(sdS + pb * TILE128, row, pk);
+      write_row_sw64(dsrow_a + pb * TILE128, swz, pk);
       fence_proxy_async_smem();
-      mbar_arrive(&bars->p_ready[pb]);
+      mbar_arrive_a(p_ready_a + pb * 8);
     }
     mbar_wait(&bars->done, 0);
     tcgen05_fence_after();
@@ -655,13 +658,17 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const bool mk = k_in ? ((blk ? p.mask_k[1] : p.mask_k[0])[(int64_t)b * Lk + kj] != 0) : false;
     const bool warp_all_mk = __all_sync(0xffffffffu, mk);
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t a_ready_a = smem_u32(&bars->a_ready[0]), s_free_a = smem_u32(&bars->s_free[0]), p_ready_a = smem_u32(&bars->p_ready[0]);
+    const uint32_t p_free_a = smem_u32(&bars->p_free[0]), kv_full_a = smem_u32(&bars->kv_full[0]), qv_a = smem_u32(qv);
+    const uint32_t ptrow_a = smem_u32(sPT) + row * 64, dstrow_a = smem_u32(sdST) + row * 64, swz = (row >> 1) & 3;
+    int st = 0, st_phase = 0;
     for (int i = 0; i < T; ++i) {
-      const int st = i % BWD_STAGES;
-      mbar_wait(&bars->kv_full[st], (i / BWD_STAGES) & 1);   // acquire the loader's per-query vectors
-      const uint32_t qva = smem_u32(&qv[st]);
-      const uint32_t wq = qv[st].mq;
+      mbar_wait_a(kv_full_a + st * 8, st_phase);         // acquire the loader's per-query vectors
+      const uint32_t qva = qv_a + st * (uint32_t)sizeof(QVec);
+      const uint32_t wq = lds_u1(qva + 2 * NT * 4);
       const bool fast = warp_all_mk && wq == 0xffffffffu;
-      mbar_wait(&bars->a_ready[0], i & 1);
+      if (++st == BWD_STAGES) { st = 0; st_phase ^= 1; }
+      mbar_wait_a(a_ready_a, i & 1);
       tcgen05_fence_after();
       uint32_t pp[16], pd[16];
 #pragma unroll
@@ -672,7 +679,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tmem_ld_wait();
         if (hf == 1) {
           tcgen05_fence_before();
-          mbar_arrive(&bars->s_free[0]);
+          mbar_arrive_a(s_free_a);
         }
         if (fast) {                                      // branch hoisted out of the element loops: straight-line FFMA / EX2 code
 #pragma unroll
@@ -706,11 +713,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           }
         }
       }
-      if (i >= 1) mbar_wait(&bars->p_free[0], (i - 1) & 1);   // dK / dV products of tile i-1 have consumed the staging tiles
-      write_row_sw64(sPT, row, pp);
-      write_row_sw64(sdST, row, pd);
+      if (i >= 1) mbar_wait_a(p_free_a, (i - 1) & 1);    // dK / dV products of tile i-1 have consumed the staging tiles
+      write_row_sw64(ptrow_a, swz, pp);
+      write_row_sw64(dstrow_a, swz, pd);
       fence_proxy_async_smem();
-      mbar_arrive(&bars->p_ready[0]);
+      mbar_arrive_a(p_ready_a);
     }
     mbar_wait(&bars->done, 0);
     tcgen05_fence_after();
@@ -783,7 +790,7 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     dim3 grid((a->Lq + QT - 1) / QT, a->H, a->B);
     if (kind == 0) {
       const size_t T = (a->blk[0].Lk + NT - 1) / NT + (a->nblk > 1 ? (a->blk[1].Lk + NT - 1) / NT : 0);
-      const size_t smem = 2 * TILE128 + FWD_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes + T * 4;
+      const size_t smem = 2 * TILE128 + FWD_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes + T * 8;
       if (smem > cfg_bytes[0]) { int rc = set_smem(attn_fwd_tc_kernel, smem); if (rc) return rc; cfg_bytes[0] = smem; }
       attn_fwd_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
     } else {
@@ -791,7 +798,7 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
       MMI_CHECK_ARG(a->lddo % 8 == 0, "attn_tc: lddo must be a multiple of 8");
       if (!map_rows(a->dout, a->lddo, q_rows, width, QT, &mdO)) return MMI_ECUDA;
       const size_t T = (a->blk[0].Lk + NT - 1) / NT + (a->nblk > 1 ? (a->blk[1].Lk + NT - 1) / NT : 0);
-      const size_t smem = 3 * TILE128 + BWD_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes + T * 4;
+      const size_t smem = 3 * TILE128 + BWD_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes + T * 8;
       if (smem > cfg_bytes[1]) { int rc = set_smem(attn_bwd_dq_tc_kernel, smem); if (rc) return rc; cfg_bytes[1] = smem; }
       attn_bwd_dq_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p);
     }

@@ -200,7 +200,7 @@ def test_attention_fwd_bwd(dev, dh, dtype, impl, shape):
     _check_attention(dev, dh, dtype, impl, shape, ragged=True)
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 500, 40, 500), (2, 4, 40, 40, 100), (1, 2, 128, 64, 256), (1, 2, 300, 33, 1030)])
+@pytest.mark.parametrize("shape", [(2, 16, 500, 40, 500), (2, 4, 40, 40, 100), (1, 2, 128, 64, 256), (1, 2, 300, 33, 1030), (1, 2, 1000, 40, 4000)])
 def test_attention_tc_unmasked_fast_path(dev, shape):
     """Full histories (no masked key, no padded query): the mask-free fast path of the tcgen05 kernels."""
     _check_attention(dev, 32, torch.bfloat16, "tc", shape, ragged=False)

@@ -175,6 +175,25 @@ int mmi_focal_loss_fwd_bwd(const float* logits, int64_t* gt, int B, int L,
                            const float* exposure_prob, float inv_bsz, float weight,
                            int rewrite_gt, float* scalars, float* dlogits, mmi_stream_t stream);
 
+/* General form: optional learnable position bias (models/decoder_leave_focal.py:442-444,497-504:
+ * logits += (pos+1) * bias_weight + bias_bias, both [L]) and the default loss `interestBPR`
+ * (compute_interest_BPR_all :163-221: rows with view_len < L; pos = logits[row, view_len], the other L-1 logits --
+ * pad positions included -- are negatives; -log(clamp(sum_k softmax_k(neg) * sigmoid(neg_k - pos), 1e-8, 1-1e-8)),
+ * mean over those rows, times bpr_scale (1 / world size under data parallelism)).
+ * loss = w_focal * focal + w_bpr * interestBPR over the losses switched on.
+ * scalars (fp32[8]): 0 focal, 1 mse, 2 mse2, 3 loss, 4 interestBPR.
+ * logits_out (optional) receives logits + bias; dbias_* (optional) are accumulated (+=).             */
+typedef struct {
+  const float* logits; int64_t* gt; int B; int L;
+  const float* exposure_prob;
+  const float* bias_weight; const float* bias_bias;
+  float inv_bsz; float w_focal; float w_bpr; float bpr_scale;
+  int use_focal; int use_bpr; int rewrite_gt;
+  float* logits_out; float* scalars; float* dlogits;
+  float* dbias_weight; float* dbias_bias;
+} mmi_loss_args;
+int mmi_loss_fwd_bwd(const mmi_loss_args* args, mmi_stream_t stream);
+
 /* ---- a-14: global-norm clip + AdamW on flat fp32 buffers ----------------------------
  * replaces main_for_seq_leave_earlystop_SegMM.py:298-299 (clip_grad_norm_(10.0),
  * torch.optim.AdamW.step).  norm_out[0] = pre-clip global L2 norm, norm_out[1] = clip

@@ -131,7 +131,7 @@ def head_logits(sd, x):
     logits = F.linear(x, sd["stage_mlp1.weight"], sd["stage_mlp1.bias"]).squeeze(-1)
     if "bias_weight" in sd:
         pos = torch.arange(logits.shape[1], dtype=logits.dtype)
-        logits = logits + (pos + 1) * sd["bias_weight"] + sd["bias_bias"]
+        logits = logits + (pos + 1) * sd["bias_weight"].reshape(1, -1) + sd["bias_bias"].reshape(1, -1)
     return logits
 
 
@@ -213,7 +213,7 @@ def compute_loss(logits, gt, exposure_prob, loss_type_list=("focal",), loss_weig
 # full forward (image modality, single backbone)
 # --------------------------------------------------------------------------
 def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_layers,
-            exposure_prob=None, loss_type_list=("focal",), use_pe=True, mode="train"):
+            exposure_prob=None, loss_type_list=("focal",), use_pe=True, mode="train", loss_weight=None):
     """models/decoder_leave_focal.py:574-658 for input_type image/image,
     backbone2=None, head=None."""
     x = backbone(sd, "backbone1.", usr_image, usr_mask.bool(), vid_image, vid_mask.bool(),
@@ -222,7 +222,7 @@ def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_laye
     if mode == "inference":
         return dict(logits=logits, gt=gt)
     exposure_prob = exposure_prob if exposure_prob is not None else [1.0] * logits.shape[1]
-    return compute_loss(logits, gt, exposure_prob, loss_type_list)
+    return compute_loss(logits, gt, exposure_prob, loss_type_list, loss_weight)
 
 
 def live_param_names(sd_keys, num_layers):

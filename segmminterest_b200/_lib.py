@@ -42,6 +42,14 @@ class AttnArgs(C.Structure):
                 ("dout", c_p), ("lddo", i64), ("delta", c_p)]
 
 
+class LossArgs(C.Structure):
+    _fields_ = [("logits", c_p), ("gt", c_p), ("B", C.c_int), ("L", C.c_int), ("exposure_prob", c_p),
+                ("bias_weight", c_p), ("bias_bias", c_p),
+                ("inv_bsz", C.c_float), ("w_focal", C.c_float), ("w_bpr", C.c_float), ("bpr_scale", C.c_float),
+                ("use_focal", C.c_int), ("use_bpr", C.c_int), ("rewrite_gt", C.c_int),
+                ("logits_out", c_p), ("scalars", c_p), ("dlogits", c_p), ("dbias_weight", c_p), ("dbias_bias", c_p)]
+
+
 _SIGS = {
     "mmi_version": (C.c_int, []),
     "mmi_last_error": (C.c_char_p, []),
@@ -59,6 +67,7 @@ _SIGS = {
     "mmi_head_bwd_workspace": (i64, [C.c_int]),
     "mmi_head_bwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmi_focal_loss_fwd_bwd": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, C.c_float, C.c_float, C.c_int, c_p, c_p, c_p]),
+    "mmi_loss_fwd_bwd": (C.c_int, [C.POINTER(LossArgs), c_p]),
     "mmi_clip_adamw_workspace": (i64, [i64]),
     "mmi_clip_adamw": (C.c_int, [c_p, c_p, c_p, c_p, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int, c_p, c_p, c_p, c_p]),

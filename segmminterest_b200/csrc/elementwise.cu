@@ -3,6 +3,7 @@
 // AdamW, and the fp32->bf16 parameter cast.  Reductions use warp shuffles; cross-CTA
 // reductions are two-stage (fixed order => run-to-run deterministic).
 #include "common.cuh"
+#include <string.h>
 
 namespace mmi {
 
@@ -390,16 +391,45 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const T* __restrict__ x, 
   }
 }
 
-// ------------------------------------------------------------------ focal loss + diagnostics
-// One CTA (<= 32 warps), one warp per row, L <= 64.  models/decoder_leave_focal.py:490-572.
-__global__ void __launch_bounds__(1024) focal_loss_kernel(const float* __restrict__ logits, int64_t* __restrict__ gt, int B, int L,
-                                                          const float* __restrict__ ep, float inv_bsz, float weight, int rewrite_gt,
-                                                          float* __restrict__ scalars, float* __restrict__ dlogits) {
-  __shared__ double red[32][9];
+// ------------------------------------------------------------------ loss (focal / interestBPR) + diagnostics
+// One CTA (<= 32 warps), one warp per row, L <= 64.  models/decoder_leave_focal.py:490-572:
+//   logits = stage_logits (+ (pos+1) * bias_weight + bias_bias)                      :497-504
+//   focal       : my_sigmoid_focal_loss (alpha .5, gamma 2), masked sum / bsz        :35-59, 533-538
+//   interestBPR : compute_interest_BPR_all, rows with view_len < L, mean over rows   :163-221
+//   mse / mse2 diagnostics (incl. the [B] vs [B,1] broadcast of the reference)        :552-558
+// dlogits = d loss / d logits for loss = w_focal * focal + w_bpr * interestBPR.
+struct LossParams {
+  const float* logits_in; int64_t* gt; int B, L;
+  const float* ep; const float* bias_w; const float* bias_b;
+  float inv_bsz, w_focal, w_bpr, bpr_scale;
+  int use_focal, use_bpr, rewrite_gt;
+  float* logits_out; float* scalars; float* dlogits; float* dbias_w; float* dbias_b;
+};
+
+__global__ void __launch_bounds__(1024) loss_kernel(const LossParams q) {
+  __shared__ double red[32][10];
+  __shared__ int n_bpr_rows_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  double acc[9];
+  const int B = q.B, L = q.L;
+  // ---- number of rows that take part in interestBPR (view_len < L), needed for its mean before any gradient
+  if (threadIdx.x == 0) n_bpr_rows_s = 0;
+  __syncthreads();
+  if (q.use_bpr) {
+    int cnt = 0;
+    for (int row = warp; row < B; row += nw) {
+      const bool v0 = lane < L && q.gt[(size_t)row * L + lane] == 1;
+      const bool v1 = lane + 32 < L && q.gt[(size_t)row * L + lane + 32] == 1;
+      const int n_view = __popc(__ballot_sync(0xffffffffu, v0)) + __popc(__ballot_sync(0xffffffffu, v1));
+      cnt += n_view < L ? 1 : 0;
+    }
+    if (lane == 0 && cnt) atomicAdd(&n_bpr_rows_s, cnt);
+  }
+  __syncthreads();
+  const int n_bpr = n_bpr_rows_s;
+  const float inv_nbpr = 1.0f / (float)n_bpr;            // 0 rows: inf -> loss = 0 * inf = NaN like torch's empty mean
+  double acc[10];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) acc[i] = 0.0;
+  for (int i = 0; i < 10; ++i) acc[i] = 0.0;
   for (int row = warp; row < B; row += nw) {
     float x[2], sig[2], logp[2];
     long long g[2];
@@ -408,8 +438,10 @@ __global__ void __launch_bounds__(1024) focal_loss_kernel(const float* __restric
     for (int h = 0; h < 2; ++h) {
       const int l = lane + 32 * h;
       in[h] = l < L;
-      x[h] = in[h] ? logits[(size_t)row * L + l] : 0.f;
-      g[h] = in[h] ? gt[(size_t)row * L + l] : -2;
+      x[h] = in[h] ? q.logits_in[(size_t)row * L + l] : 0.f;
+      if (in[h] && q.bias_w != nullptr) x[h] += (float)(l + 1) * q.bias_w[l] + q.bias_b[l];
+      if (in[h] && q.logits_out != nullptr) q.logits_out[(size_t)row * L + l] = x[h];
+      g[h] = in[h] ? q.gt[(size_t)row * L + l] : -2;
       valid[h] = in[h] && g[h] != -2;
       sig[h] = 1.0f / (1.0f + expf(-x[h]));
       logp[h] = in[h] ? logf(sig[h]) : 0.f;
@@ -440,56 +472,114 @@ __global__ void __launch_bounds__(1024) focal_loss_kernel(const float* __restric
     const float at_pos = (pos < 32) ? __shfl_sync(0xffffffffu, sm0, pos) : __shfl_sync(0xffffffffu, sm1, pos - 32);
     const float s2_row = s_row - at_pos + 1.0f;
     // after the in-place rewrite gt in {1,0,-2}: (gt>=0).sum() == n_valid; otherwise count of {1,0}
-    const float v2 = rewrite_gt ? (float)n_valid : (float)n_nonneg_orig;
+    const float v2 = (q.use_focal && q.rewrite_gt) ? (float)n_valid : (float)n_nonneg_orig;
+    float dl[2] = {0.f, 0.f};
     float lsum = 0.f;
+    if (q.use_focal) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int l = lane + 32 * h;
-      if (!in[h]) continue;
-      const long long gn = (g[h] > 0) ? 1 : (g[h] == -1 ? 0 : g[h]);
-      if (rewrite_gt) gt[(size_t)row * L + l] = gn;
-      float dl = 0.f;
-      if (valid[h]) {
-        const float t = (float)gn;
-        const float e = ep[l];
-        const float p = sig[h] * e;
-        const float ce = fmaxf(x[h], 0.f) - x[h] * t + log1pf(expf(-fabsf(x[h])));
-        const float pt = p * t + (1.f - p) * (1.f - t);
-        const float om = 1.f - pt;
-        lsum += 0.5f * ce * om * om;
-        const float dp = e * sig[h] * (1.f - sig[h]);
-        dl = 0.5f * ((sig[h] - t) * om * om - ce * 2.f * om * (2.f * t - 1.f) * dp);
+      for (int h = 0; h < 2; ++h) {
+        const int l = lane + 32 * h;
+        if (!in[h]) continue;
+        const long long gn = (g[h] > 0) ? 1 : (g[h] == -1 ? 0 : g[h]);
+        if (q.rewrite_gt) q.gt[(size_t)row * L + l] = gn;
+        if (valid[h]) {
+          const float t = (float)gn;
+          const float e = q.ep[l];
+          const float p = sig[h] * e;
+          const float ce = fmaxf(x[h], 0.f) - x[h] * t + log1pf(expf(-fabsf(x[h])));
+          const float pt = p * t + (1.f - p) * (1.f - t);
+          const float om = 1.f - pt;
+          lsum += 0.5f * ce * om * om;
+          const float dp = e * sig[h] * (1.f - sig[h]);
+          dl[h] = 0.5f * ((sig[h] - t) * om * om - ce * 2.f * om * (2.f * t - 1.f) * dp) * q.w_focal * q.inv_bsz;
+        }
       }
-      dlogits[(size_t)row * L + l] = dl * weight * inv_bsz;
+      lsum = warp_sum(lsum);
     }
-    lsum = warp_sum(lsum);
+    // ---- interestBPR (:163-221): pos = logits[row, view_len]; the other L-1 logits (pad positions included) are negatives
+    float bpr_row = 0.f;
+    if (q.use_bpr && n_view < L) {                       // warp-uniform
+      const float xpos = (n_view < 32) ? __shfl_sync(0xffffffffu, x[0], n_view) : __shfl_sync(0xffffffffu, x[1], n_view - 32);
+      bool neg[2];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        neg[h] = in[h] && (lane + 32 * h) != n_view;
+        if (neg[h]) mx = fmaxf(mx, x[h]);
+      }
+      mx = warp_max(mx);
+      float e[2], gsig[2], se = 0.f, sa = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        e[h] = neg[h] ? expf(x[h] - mx) : 0.f;
+        gsig[h] = neg[h] ? 1.0f / (1.0f + expf(-(x[h] - xpos))) : 0.f;
+        se += e[h];
+        sa += e[h] * gsig[h];
+      }
+      se = warp_sum(se);
+      sa = warp_sum(sa);
+      const float A = sa / se;                           // sum_k softmax_k * sigmoid(neg_k - pos)
+      const float Ac = fminf(fmaxf(A, 1e-8f), 1.0f - 1e-8f);
+      bpr_row = -logf(Ac);
+      const float dA = (A > 1e-8f && A < 1.0f - 1e-8f) ? -1.0f / A : 0.f;   // clamp passes no gradient outside its range
+      const float coef = dA * q.w_bpr * q.bpr_scale * inv_nbpr;
+      float dpos = 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (neg[h]) {
+          const float sk = e[h] / se, gg = gsig[h] * (1.0f - gsig[h]);
+          dl[h] += coef * (sk * gg + sk * (gsig[h] - A));
+          dpos -= sk * gg;
+        }
+      }
+      dpos = warp_sum(dpos) * coef;
+      if (n_view < 32) { if (lane == n_view) dl[0] += dpos; }
+      else if (lane == n_view - 32) dl[1] += dpos;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (in[h]) q.dlogits[(size_t)row * L + lane + 32 * h] = dl[h];
     if (lane == 0) {
       acc[0] += lsum;
       acc[1] += s_row; acc[2] += (double)s_row * s_row;
       acc[3] += n_view; acc[4] += (double)n_view * n_view;
       acc[5] += s2_row; acc[6] += (double)s2_row * s2_row;
       acc[7] += v2; acc[8] += (double)v2 * v2;
+      acc[9] += bpr_row;
     }
   }
   if (lane == 0)
 #pragma unroll
-    for (int i = 0; i < 9; ++i) red[warp][i] = acc[i];
+    for (int i = 0; i < 10; ++i) red[warp][i] = acc[i];
   __syncthreads();
   if (threadIdx.x == 0) {
-    double t[9];
-    for (int i = 0; i < 9; ++i) {
+    double t[10];
+    for (int i = 0; i < 10; ++i) {
       t[i] = 0.0;
       for (int w = 0; w < nw; ++w) t[i] += red[w][i];
     }
     const double b = (double)B;
-    const double focal = t[0] * (double)inv_bsz;
+    const double focal = t[0] * (double)q.inv_bsz;
+    const double bpr = q.use_bpr ? t[9] * (double)q.bpr_scale / (double)n_bpr : 0.0;
     // nn.MSELoss()([B], [B,1]) broadcasts to [B,B]: mean_ij (s_j - v_i)^2  (:552)
     const double mse = t[2] / b - 2.0 * (t[1] / b) * (t[3] / b) + t[4] / b;
     const double mse2 = t[6] / b - 2.0 * (t[5] / b) * (t[7] / b) + t[8] / b;
-    scalars[0] = (float)focal;
-    scalars[1] = (float)mse;
-    scalars[2] = (float)mse2;
-    scalars[3] = (float)(focal * (double)weight);
+    q.scalars[0] = (float)focal;
+    q.scalars[1] = (float)mse;
+    q.scalars[2] = (float)mse2;
+    q.scalars[3] = (float)((q.use_focal ? focal * (double)q.w_focal : 0.0) + (q.use_bpr ? bpr * (double)q.w_bpr : 0.0));
+    q.scalars[4] = (float)bpr;
+  }
+  // ---- learnable position bias gradients: d bias_bias[l] = sum_b dlogits[b,l], d bias_weight[l] = (l+1) * that
+  if (q.dbias_w != nullptr || q.dbias_b != nullptr) {
+    __threadfence_block();
+    __syncthreads();
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+      float s = 0.f;
+      for (int r = 0; r < B; ++r) s += q.dlogits[(size_t)r * L + l];
+      if (q.dbias_b) q.dbias_b[l] += s;
+      if (q.dbias_w) q.dbias_w[l] += s * (float)(l + 1);
+    }
   }
 }
 
@@ -714,15 +804,32 @@ extern "C" int mmi_head_bwd(const void* x, int dtype, int64_t rows, int d, const
   return MMI_OK;
 }
 
-extern "C" int mmi_focal_loss_fwd_bwd(const float* logits, int64_t* gt, int B, int L, const float* exposure_prob, float inv_bsz,
-                                      float weight, int rewrite_gt, float* scalars, float* dlogits, mmi_stream_t stream) {
+extern "C" int mmi_loss_fwd_bwd(const mmi_loss_args* a, mmi_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  MMI_CHECK_ARG(logits && gt && exposure_prob && scalars && dlogits, "focal_loss: null pointer");
-  MMI_CHECK_ARG(L > 0 && L <= 64 && B > 0, "focal_loss: need 0 < L <= 64 (got %d), B > 0 (got %d)", L, B);
-  int threads = B >= 32 ? 1024 : 32 * B;
-  focal_loss_kernel<<<1, threads, 0, st>>>(logits, (int64_t*)gt, B, L, exposure_prob, inv_bsz, weight, rewrite_gt, scalars, dlogits);
+  MMI_CHECK_ARG(a && a->logits && a->gt && a->scalars && a->dlogits, "loss: null pointer");
+  MMI_CHECK_ARG(a->L > 0 && a->L <= 64 && a->B > 0, "loss: need 0 < L <= 64 (got %d), B > 0 (got %d)", a->L, a->B);
+  MMI_CHECK_ARG(!a->use_focal || a->exposure_prob, "loss: focal needs exposure_prob");
+  MMI_CHECK_ARG((a->bias_weight == nullptr) == (a->bias_bias == nullptr), "loss: bias_weight and bias_bias go together");
+  LossParams q;
+  q.logits_in = a->logits; q.gt = a->gt; q.B = a->B; q.L = a->L;
+  q.ep = a->exposure_prob; q.bias_w = a->bias_weight; q.bias_b = a->bias_bias;
+  q.inv_bsz = a->inv_bsz; q.w_focal = a->w_focal; q.w_bpr = a->w_bpr; q.bpr_scale = a->bpr_scale;
+  q.use_focal = a->use_focal; q.use_bpr = a->use_bpr; q.rewrite_gt = a->rewrite_gt;
+  q.logits_out = a->logits_out; q.scalars = a->scalars; q.dlogits = a->dlogits; q.dbias_w = a->dbias_weight; q.dbias_b = a->dbias_bias;
+  const int threads = a->B >= 32 ? 1024 : 32 * a->B;
+  loss_kernel<<<1, threads, 0, st>>>(q);
   MMI_CHECK_LAUNCH();
   return MMI_OK;
+}
+
+extern "C" int mmi_focal_loss_fwd_bwd(const float* logits, int64_t* gt, int B, int L, const float* exposure_prob, float inv_bsz,
+                                      float weight, int rewrite_gt, float* scalars, float* dlogits, mmi_stream_t stream) {
+  mmi_loss_args a;
+  memset(&a, 0, sizeof(a));
+  a.logits = logits; a.gt = gt; a.B = B; a.L = L; a.exposure_prob = exposure_prob;
+  a.inv_bsz = inv_bsz; a.w_focal = weight; a.use_focal = 1; a.rewrite_gt = rewrite_gt; a.bpr_scale = 1.0f;
+  a.scalars = scalars; a.dlogits = dlogits;
+  return mmi_loss_fwd_bwd(&a, stream);
 }
 
 extern "C" int64_t mmi_clip_adamw_workspace(int64_t n) { (void)n; return 2 * (int64_t)kRedCtas + 4; }

@@ -127,6 +127,9 @@ class Engine:
                 group(f"L{i}.{side}.ln2.b", [(f"{q}ln_{side}.bias", ln2.bias)])
         group("head.w", [("stage_mlp1.weight", self.model.stage_mlp1.weight)])
         group("head.b", [("stage_mlp1.bias", self.model.stage_mlp1.bias)])
+        if getattr(self.model, "bias_weight", None) is not None:   # learnable position bias (decoder_leave_focal.py:442-444)
+            group("bias_weight", [("bias_weight", self.model.bias_weight)])
+            group("bias_bias", [("bias_bias", self.model.bias_bias)])
         self.n_flat = (off + ALIGN - 1) // ALIGN * ALIGN
         self.live_names = [s.name for s in self.slots]
 
@@ -332,21 +335,40 @@ class Engine:
         return logits
 
     # ------------------------------------------------------------------ loss
-    def loss(self, logits, gt, exposure_prob, inv_bsz, weight=1.0):
-        """Fused focal loss + diagnostics + dlogits (models/decoder_leave_focal.py:490-572).
-        `gt` is rewritten in place like the reference (:534-535).  Returns the scalars tensor
-        [focal, mse, mse2, loss, ...] (device, no sync)."""
+    def loss(self, logits, gt, exposure_prob, inv_bsz, loss_cfg=None, bpr_scale=1.0, need_grad=True):
+        """Fused loss (focal and / or interestBPR) + learnable position bias + diagnostics + dlogits
+        (models/decoder_leave_focal.py:490-572).  `gt` is rewritten in place like the reference (:534-535) when
+        focal is on.  Returns (scalars [focal, mse, mse2, loss, interestBPR, ...], logits incl. bias): device
+        tensors, no sync.  loss_cfg: dict(use_focal, w_focal, use_bpr, w_bpr); None = focal with weight 1."""
         B, L = logits.shape
         if gt.dtype != torch.int64 or not gt.is_contiguous() or not gt.is_cuda:
             raise ValueError("gt must be a contiguous CUDA int64 tensor (it is rewritten in place, like the reference)")
+        cfg = loss_cfg or dict(use_focal=True, w_focal=1.0, use_bpr=False, w_bpr=0.0)
         ep = self._ws.get("ep")
         if ep is None or self._ws.get("ep_src") != tuple(exposure_prob[:L]):
             ep = torch.tensor(list(exposure_prob[:L]), device=self.device, dtype=torch.float32)
             self._ws["ep"], self._ws["ep_src"] = ep, tuple(exposure_prob[:L])
         dlogits = self._buf("dlogits", (B, L), torch.float32)
-        ops.focal_loss(logits, gt, ep, inv_bsz, weight, True, self.scalars, dlogits)
-        self._saved["dlogits"] = dlogits
-        return self.scalars
+        has_bias = "bias_weight" in self.groups
+        logits_out = self._buf("logits_b", (B, L), torch.float32) if has_bias else None
+        if has_bias and need_grad:
+            self.bind_grads()
+        ops.loss_fwd_bwd(logits, gt, ep, inv_bsz=inv_bsz, scalars=self.scalars, dlogits=dlogits, use_focal=cfg["use_focal"],
+                         w_focal=cfg["w_focal"], use_bpr=cfg["use_bpr"], w_bpr=cfg["w_bpr"], bpr_scale=bpr_scale, rewrite_gt=True,
+                         bias_weight=self.w("bias_weight") if has_bias else None, bias_bias=self.w("bias_bias") if has_bias else None,
+                         logits_out=logits_out, dbias_weight=self._pending_bias_grad(0) if has_bias and need_grad else None,
+                         dbias_bias=self._pending_bias_grad(1) if has_bias and need_grad else None)
+        if self._saved is not None:
+            self._saved["dlogits"] = dlogits
+        return self.scalars, (logits_out if has_bias else logits)
+
+    def _pending_bias_grad(self, which):
+        """The loss kernel produces d loss / d bias directly; it lands in a scratch buffer and is added to the flat
+        gradient in backward() scaled by the upstream gradient (so autograd's grad_out is honoured)."""
+        t = self._buf("dbias", (2, self.groups["bias_weight"][1]), torch.float32)
+        if which == 0:
+            t.zero_()
+        return t[which]
 
     # ------------------------------------------------------------------ backward
     def backward(self, gscale=None, on_ready=None):
@@ -368,6 +390,11 @@ class Engine:
         def scratch(name, s, width=d):
             return self._buf(f"bw.{name}.{s}", (Ts[s], width), T)
 
+        if "bias_weight" in self.groups:   # d loss / d (bias_weight, bias_bias) from the loss kernel, times the upstream gradient
+            db = self._buf("dbias", (2, self.groups["bias_weight"][1]), torch.float32)
+            gs = gscale if gscale is not None else 1.0
+            self.g("bias_weight").add_(db[0] * gs)
+            self.g("bias_bias").add_(db[1] * gs)
         dX = {"vid": scratch("dx", "vid"), "usr": None}
         ops.head_bwd(sv["x_out"], Ts["vid"], d, self.w("head.w"), sv["dlogits"], gscale, dX["vid"], self.g("head.w"),
                      self.g("head.b"), self.red_ws)

@@ -174,11 +174,10 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
         it = getattr(model_cfg, "input_type", {"user": "image", "photo": "image"})
         if it.get("user") != "image" or it.get("photo") != "image":
             raise NotImplementedError("only input_type image/image is built (ID inputs: SURVEY 8f-1)")
-        if getattr(model_cfg, "learnable_bias", 0):
-            raise NotImplementedError("learnable_bias=1 is not built yet")
         for lt in model_cfg.loss_type_list:
-            if lt != "focal":
-                raise NotImplementedError(f"loss_type {lt!r}: only 'focal' (the BCE family the path names) is built")
+            if lt not in ("focal", "interestBPR"):
+                raise NotImplementedError(f"loss_type {lt!r}: 'focal' (the BCE family the path names) and 'interestBPR' "
+                                          "(the reference default) are built")
         self.backbone1 = backbone1
         self.backbone2 = None
         self.model_cfg = model_cfg
@@ -188,6 +187,9 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
         self.input_type = it
         self.bias_weight = None
         self.bias_bias = None
+        if getattr(model_cfg, "learnable_bias", 0):   # models/decoder_leave_focal.py:442-444
+            self.bias_weight = nn.Parameter(torch.ones(1, PHOTO_MAX), requires_grad=True)
+            self.bias_bias = nn.Parameter(torch.ones(1, PHOTO_MAX), requires_grad=True)
         self.exposure_prob = model_cfg.exposure_prob
         d_model = model_cfg.d_model
         self.stage_mlp1 = nn.Linear(d_model, 1)
@@ -211,21 +213,37 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
         self._engine.ensure_bound()
         return self._engine
 
+    def loss_cfg(self):
+        lw = self.model_cfg.loss_weight
+        names = list(self.model_cfg.loss_type_list)
+        return dict(use_focal="focal" in names, w_focal=float(lw.get("focal", 1.0)) if "focal" in names else 0.0,
+                    use_bpr="interestBPR" in names, w_bpr=float(lw.get("interestBPR", 1.0)) if "interestBPR" in names else 0.0)
+
     def forward(self, usr_image, usr_id, usr_mask, vid_image, vid_id, vid_mask, gt=None, mode="train", **kwargs):
         eng = self.engine()
         B = usr_id.shape[0]
         logits = eng.forward(usr_image, usr_mask, vid_image, vid_mask)
         if mode == "inference":
-            return dict(logits=logits.clone(), gt=gt)
+            if self.bias_weight is None:
+                return dict(logits=logits.clone(), gt=gt)
+            # logits + (pos+1) * bias_weight + bias_bias (models/decoder_leave_focal.py:650-658): the loss kernel adds it
+            g = gt if gt is not None else torch.full((B, PHOTO_MAX), -2, dtype=torch.int64, device=logits.device)
+            _, lb = eng.loss(logits, g.clone().contiguous(), self.exposure_prob, 1.0 / B,
+                             dict(use_focal=False, w_focal=0.0, use_bpr=False, w_bpr=0.0), need_grad=False)
+            return dict(logits=lb.clone(), gt=gt)
         if mode not in ("train", "test"):
             return None
-        weight = float(self.model_cfg.loss_weight["focal"])
-        scal = eng.loss(logits, gt, self.exposure_prob, inv_bsz=1.0 / B, weight=weight)
+        cfg = self.loss_cfg()
+        scal, lb = eng.loss(logits, gt, self.exposure_prob, 1.0 / B, cfg, need_grad=torch.is_grad_enabled())
         loss = scal[3]
         if torch.is_grad_enabled():
             loss = _EngineStep.apply(eng.anchor, loss, eng)
-        out = {"focal": scal[0].clone(), "mse": scal[1].clone(), "mse2": scal[2].clone(), "loss": loss,
-               "logits": logits.clone(), "gt": gt}
+        out = {}
+        if cfg["use_focal"]:
+            out["focal"] = scal[0].clone()
+        if cfg["use_bpr"]:
+            out["interestBPR"] = scal[4].clone()
+        out.update({"mse": scal[1].clone(), "mse2": scal[2].clone(), "loss": loss, "logits": lb.clone(), "gt": gt})
         return out
 
 

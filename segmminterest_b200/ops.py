@@ -196,6 +196,26 @@ def focal_loss(logits, gt, exposure_prob, inv_bsz, weight, rewrite_gt, scalars, 
     LaunchCounter.n += 1
 
 
+def loss_fwd_bwd(logits, gt, exposure_prob, *, inv_bsz, scalars, dlogits, use_focal=True, w_focal=1.0, use_bpr=False, w_bpr=1.0,
+                 bpr_scale=1.0, rewrite_gt=True, bias_weight=None, bias_bias=None, logits_out=None, dbias_weight=None,
+                 dbias_bias=None):
+    """Fused loss (focal and / or interestBPR) + learnable position bias + diagnostics + dlogits."""
+    B, L = logits.shape
+    assert gt.dtype == torch.int64 and gt.is_contiguous() and logits.is_contiguous() and logits.dtype == torch.float32
+    a = _lib.LossArgs()
+    a.logits, a.gt, a.B, a.L = logits.data_ptr(), gt.data_ptr(), B, L
+    a.exposure_prob = _ptr(exposure_prob)
+    a.bias_weight, a.bias_bias = _ptr(bias_weight), _ptr(bias_bias)
+    a.inv_bsz, a.w_focal, a.w_bpr, a.bpr_scale = inv_bsz, w_focal, w_bpr, bpr_scale
+    a.use_focal, a.use_bpr, a.rewrite_gt = int(use_focal), int(use_bpr), int(rewrite_gt)
+    a.logits_out, a.scalars, a.dlogits = _ptr(logits_out), scalars.data_ptr(), dlogits.data_ptr()
+    a.dbias_weight, a.dbias_bias = _ptr(dbias_weight), _ptr(dbias_bias)
+    with TIMER.region("loss"):
+        rc = _lib.load().mmi_loss_fwd_bwd(C.byref(a), _stream())
+    _lib.check(rc, "mmi_loss_fwd_bwd")
+    LaunchCounter.n += 1
+
+
 def clip_adamw(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, wd, max_norm, step, norm_out, bf16_out, ws):
     lib = _lib.load()
     n = params.numel()

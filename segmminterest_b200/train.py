@@ -50,7 +50,7 @@ class TrainStep:
         self.step_no = 0
         self.buckets = GradBuckets(eng.flat_grad, process_group, bucket_bytes)
         self.global_batch = global_batch
-        self.weight = float(model.model_cfg.loss_weight["focal"])
+        self.loss_cfg = model.loss_cfg()
 
     def step(self, usr_idx: torch.Tensor, vid_idx: torch.Tensor, gt: torch.Tensor):
         """One training step on device-resident int32 indices [B,Lt], [B,40] and int64 labels
@@ -62,9 +62,10 @@ class TrainStep:
         vid, vm = self.gather(vid_idx, "vid")
         logits = eng.forward(usr, um, vid, vm)
         gb = self.global_batch or B * self.buckets.world
-        scal = eng.loss(logits, gt, self.model.exposure_prob, inv_bsz=1.0 / gb, weight=self.weight)
         eng.bind_grads()           # Parameters' .grad alias the flat gradient buffer
         eng.flat_grad.zero_()
+        # focal is a sum / B_global; interestBPR is a mean over this rank's rows, averaged over ranks (DDP semantics)
+        scal, _ = eng.loss(logits, gt, self.model.exposure_prob, 1.0 / gb, self.loss_cfg, bpr_scale=1.0 / self.buckets.world)
         self.buckets.begin()
         eng.backward(None, on_ready=self.buckets.ready)
         self.buckets.finish()

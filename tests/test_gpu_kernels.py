@@ -275,6 +275,49 @@ def test_focal_loss_matches_reference_golden(dev):
     assert _rel(dl, torch.from_numpy(z["grad_focal"])) < 5e-6
 
 
+def test_interest_bpr_and_position_bias_match_reference_golden(dev):
+    """mmi_loss_fwd_bwd with the reference's default loss `interestBPR` (+ focal) against the fixture produced by the
+    unmodified reference (value and gradient), and the learnable position bias against autograd of the oracle."""
+    from oracle import mmi_oracle
+    from segmminterest_b200 import ops
+    z = np.load(os.path.join(GOLDEN, "loss_cases.npz"))
+    logits = torch.from_numpy(z["logits"]).to(dev)
+    B, L = logits.shape
+    ep = torch.from_numpy(z["exposure_prob"].astype(np.float32)).to(dev)
+    for use_focal, use_bpr in ((False, True), (True, True)):
+        gt = torch.from_numpy(z["gt_in"].copy()).to(dev)
+        scal, dl = torch.zeros(8, device=dev), torch.empty_like(logits)
+        ops.loss_fwd_bwd(logits, gt, ep, inv_bsz=1.0 / B, scalars=scal, dlogits=dl, use_focal=use_focal, w_focal=1.0, use_bpr=use_bpr,
+                         w_bpr=1.0, rewrite_gt=True)
+        s = scal.cpu().numpy()
+        assert abs(s[4] - float(z["interestBPR"])) < 5e-6 * abs(float(z["interestBPR"]))
+        want = z["grad_bpr"] + (z["grad_focal"] if use_focal else 0.0)
+        assert _rel(dl, torch.from_numpy(want)) < 1e-5
+        if use_focal:
+            assert abs(s[3] - float(z["loss"])) < 5e-6 * abs(float(z["loss"]))
+            assert np.array_equal(gt.cpu().numpy(), z["gt_out"])
+        else:
+            assert np.array_equal(gt.cpu().numpy(), z["gt_in"])   # no focal in the list: gt is left alone
+    # learnable position bias: logits + (pos+1) * w + b, gradients of w and b (accumulate semantics)
+    torch.manual_seed(11)
+    bw, bb = (1 + 0.1 * torch.randn(L)).to(dev), (1 + 0.1 * torch.randn(L)).to(dev)
+    gt = torch.from_numpy(z["gt_in"].copy()).to(dev)
+    scal, dl, lo = torch.zeros(8, device=dev), torch.empty_like(logits), torch.empty_like(logits)
+    dbw, dbb = torch.full((L,), 3.0, device=dev), torch.full((L,), -1.0, device=dev)
+    ops.loss_fwd_bwd(logits, gt, ep, inv_bsz=1.0 / B, scalars=scal, dlogits=dl, use_focal=True, w_focal=0.7, use_bpr=True, w_bpr=1.3,
+                     rewrite_gt=True, bias_weight=bw, bias_bias=bb, logits_out=lo, dbias_weight=dbw, dbias_bias=dbb)
+    lr = torch.from_numpy(z["logits"]).double().requires_grad_(True)
+    bwr, bbr = bw.double().cpu().requires_grad_(True), bb.double().cpu().requires_grad_(True)
+    full = lr + (torch.arange(L, dtype=torch.float64) + 1) * bwr + bbr
+    out = mmi_oracle.compute_loss(full, torch.from_numpy(z["gt_in"]), list(z["exposure_prob"]), ("focal", "interestBPR"),
+                                  {"focal": 0.7, "interestBPR": 1.3})
+    out["loss"].backward()
+    assert _rel(lo, full.detach()) < 1e-6
+    assert abs(scal[3].item() - out["loss"].item()) < 1e-5 * abs(out["loss"].item())
+    assert _rel(dl, lr.grad) < 1e-5
+    assert _rel(dbw - 3.0, bwr.grad) < 1e-4 and _rel(dbb + 1.0, bbr.grad) < 1e-4
+
+
 # ----------------------------------------------------------------------------- clip + AdamW
 def test_clip_adamw_matches_torch(dev):
     from segmminterest_b200 import _lib, ops

@@ -159,6 +159,45 @@ def test_drop_in_training_loop_matches_oracle_adamw():
             assert torch.equal(got[k].cpu(), sd0[k]), f"{k}: dead parameter must stay untouched"
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_default_loss_and_learnable_bias_vs_oracle(precision):
+    """`--loss_type interestBPR` (the reference default) with `learnable_bias 1`: logits (incl. position
+    bias), loss and every gradient (incl. bias_weight / bias_bias) against the oracle."""
+    from oracle import mmi_oracle
+    from segmminterest_b200 import synth
+    from segmminterest_b200.model import build_model
+    dev = torch.device("cuda:0")
+    args = make_args(d_model=128, nhead=4, num_layers_enc=3, learnable_bias=1, loss_type_list=["interestBPR", "focal"],
+                     loss_weight={"focal": 0.5, "interestBPR": 1.0}, mmi_precision=precision)
+    torch.manual_seed(3)
+    model = build_model(args, din=64, max_usr_len=24).cuda().eval()
+    with torch.no_grad():
+        model.bias_weight.add_(0.05 * torch.randn_like(model.bias_weight))
+        model.bias_bias.add_(0.05 * torch.randn_like(model.bias_bias))
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    assert "bias_weight" in sd and "bias_bias" in sd
+    rng = np.random.default_rng(5)
+    usr, um, vid, vm, gt = synth.make_dense_batch(rng, 16, 24, 64)
+    out = _run(model, usr, um, vid, vm, gt, dev)
+    assert set(out) >= {"interestBPR", "focal", "mse", "mse2", "loss", "logits", "gt"}
+    out["loss"].backward()
+    live = mmi_oracle.live_param_names(list(sd.keys()), 3)
+    osd = {k: v.requires_grad_(k in live) for k, v in sd.items()}
+    ref = mmi_oracle.forward(osd, torch.from_numpy(usr), torch.from_numpy(um), torch.from_numpy(vid), torch.from_numpy(vm),
+                             torch.from_numpy(gt), nhead=4, num_layers=3, loss_type_list=("interestBPR", "focal"),
+                             loss_weight={"focal": 0.5, "interestBPR": 1.0})
+    ref["loss"].backward()
+    tol = FP32_TOL if precision == "fp32" else BF16_TOL
+    assert _rel(out["logits"].cpu().numpy(), ref["logits"].detach().numpy()) < tol
+    assert abs(out["loss"].item() - ref["loss"].item()) < tol * abs(ref["loss"].item())
+    assert abs(out["interestBPR"].item() - ref["interestBPR"].item()) < tol * abs(ref["interestBPR"].item()) + 2e-6
+    for k, p in model.named_parameters():
+        if k in live:
+            assert _rel(p.grad.cpu().numpy(), osd[k].grad.numpy()) < 3 * tol, k
+    inf = _run(model, usr, um, vid, vm, gt, dev, mode="inference")
+    assert _rel(inf["logits"].cpu().numpy(), ref["logits"].detach().numpy()) < tol
+
+
 def test_cpu_call_fails_loudly():
     from segmminterest_b200 import _lib
     from segmminterest_b200.model import build_model

@@ -79,7 +79,9 @@ def test_cpu_forward_fails_loudly():
 def test_unsupported_configs_raise():
     from segmminterest_b200.model import SegFormerX, build_model
     with pytest.raises(NotImplementedError):
-        build_model(make_args(loss_type_list=["interestBPR"]), din=16, max_usr_len=4)
+        build_model(make_args(loss_type_list=["surviveCE"]), din=16, max_usr_len=4)
+    m = build_model(make_args(loss_type_list=["interestBPR"], learnable_bias=1), din=16, max_usr_len=4)   # 8f-1: built
+    assert tuple(m.bias_weight.shape) == (1, 40) and tuple(m.bias_bias.shape) == (1, 40)
     with pytest.raises(NotImplementedError):
         SegFormerX(d_model_in=64, d_model_lvls=[64], num_head_lvls=[2], ff_dim_lvls=[64], sr_ratio_lvls=[1],
                    use_patch_merge=[False], output_layers=[-1], model_cfg=make_args(), user_id_max=10)

@@ -92,6 +92,55 @@ def run_model_case(name, d_model, nhead, nlayers, din, Lt, B, seed, store_sd=Tru
     print(name, "loss", save["loss"], "n_dead", len(dead))
 
 
+def run_general_case(name, input_type, d_model, nhead, nlayers, din, B, seed, loss_types, n_users=23, n_items=57):
+    """SURVEY 8f-1: ID inputs / two backbones + InteractionAggregation (the reference's default 'both' config), history
+    padded to the reference's 100 tokens.  Stores the full state_dict, inputs, outputs and gradients."""
+    args = ref_shim.make_args(d_model=d_model, nhead=nhead, num_layers_enc=nlayers, loss_type_list=list(loss_types),
+                              input_type=input_type, fusion_heads=2)
+    model = ref_shim.build_reference_model_general(args, din=din, n_users=n_users, n_items=n_items, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if p.ndim == 1:
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+            if k in ("stage_mlp1.weight", "fusion_module.w_x.weight", "fusion_module.w_y.weight", "fusion_module.w_xy"):
+                p.mul_(3.0)
+    model.eval()
+    rng = np.random.default_rng(seed + 7)
+    Lt = 100
+    usr, usr_mask, vid, vid_mask, gt = synth.make_dense_batch(rng, B, Lt, din)
+    usr_id = rng.integers(0, n_users + 1, size=B)
+    vid_id = rng.integers(0, n_items + 1, size=B)
+    vid_id[1] = vid_id[0]          # two interactions with the same video: embedding gradients must add up
+    batch = dict(usr_image=torch.from_numpy(usr), usr_id=torch.from_numpy(usr_id), usr_mask=torch.from_numpy(usr_mask),
+                 vid_image=torch.from_numpy(vid), vid_id=torch.from_numpy(vid_id), vid_mask=torch.from_numpy(vid_mask),
+                 gt=torch.from_numpy(gt.copy()))
+    out = ref_shim.run_reference(model, batch, mode="train")
+    out["loss"].backward()
+    save = dict(cfg=json.dumps(dict(d_model=d_model, nhead=nhead, num_layers_enc=nlayers, din=din, Lt=Lt, B=B, seed=seed,
+                                    loss_types=list(loss_types), input_type=input_type, n_users=n_users, n_items=n_items,
+                                    fusion_heads=2)),
+                usr_image=usr, vid_image=vid, usr_id=usr_id, vid_id=vid_id, usr_mask=usr_mask, vid_mask=vid_mask, gt_in=gt,
+                logits=out["logits"].detach().numpy(), gt_out=out["gt"].numpy(), loss=np.float64(out["loss"].item()),
+                mse=np.float64(out["mse"].item()), mse2=np.float64(out["mse2"].item()))
+    for lt_ in loss_types:
+        save[lt_] = np.float64(out[lt_].item())
+    with torch.no_grad():
+        batch["gt"] = torch.from_numpy(gt.copy())
+        save["logits_inference"] = ref_shim.run_reference(model, batch, mode="inference")["logits"].numpy()
+    dead = []
+    for k, v in model.state_dict().items():
+        save["sd/" + k] = v.numpy()
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            dead.append(k)
+        else:
+            save["grad/" + k] = p.grad.numpy()
+    save["dead_params"] = json.dumps(dead)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print(name, "loss", save["loss"], "n_dead", len(dead), "n_params", sum(p.numel() for p in model.parameters()))
+
+
 def run_loss_cases():
     """compute_loss alone (decoder_leave_focal.py:490-572) on hand-made edge cases."""
     args = ref_shim.make_args(d_model=32, nhead=2, num_layers_enc=2, loss_type_list=["focal", "interestBPR"])
@@ -185,7 +234,18 @@ def main():
     run_model_case("model_small_dh16", d_model=64, nhead=4, nlayers=4, din=40, Lt=20, B=4, seed=12)
     run_model_case("model_full_b4", d_model=512, nhead=16, nlayers=6, din=1024, Lt=100, B=4, seed=13,
                    store_sd=False, fill_seed=42)
+    run_general_cases()
+
+
+def run_general_cases():
+    run_general_case("model_both_small", {"user": "both", "photo": "both"}, d_model=64, nhead=2, nlayers=3, din=24, B=4, seed=21,
+                     loss_types=("interestBPR",))
+    run_general_case("model_id_small", {"user": "id", "photo": "id"}, d_model=64, nhead=2, nlayers=3, din=24, B=4, seed=22,
+                     loss_types=("focal",))
 
 
 if __name__ == "__main__":
-    main()
+    if "--general-only" in sys.argv:
+        run_general_cases()
+    else:
+        main()

@@ -32,10 +32,23 @@ def l1_normalise(x: torch.Tensor) -> torch.Tensor:
 # a-4  embedding: Linear(Din->d) + PE + LN(eps 1e-12)
 # --------------------------------------------------------------------------
 def embed(sd, prefix, usr, vid, use_pe=True):
-    """models/encoder.py:425-473 (image inputs, dropout off)."""
+    """models/encoder.py:425-473 (dropout off).  Image inputs are [B,L,Din] floats (Linear projections); ID inputs
+    are int64 [B] (encoder.py:352-362,426-435,478-488): the video id is repeated over the 40 segments
+    and embedded into d/2 columns, the other d/2 come from Linear(1 -> d/2) of the segment position; the user id
+    becomes ONE token (the caller then uses an all-ones user mask)."""
     d = sd[prefix + "vid_ln.weight"].shape[0]
-    v = F.linear(vid, sd[prefix + "vid_proj.weight"], sd[prefix + "vid_proj.bias"])
-    u = F.linear(usr, sd[prefix + "usr_proj.weight"], sd[prefix + "usr_proj.bias"])
+    if vid.ndim == 1:
+        B, Lv = vid.shape[0], 40
+        emb = sd[prefix + "vid_proj.weight"][vid][:, None, :].expand(B, Lv, -1)
+        pos = torch.arange(Lv, dtype=emb.dtype)[None, :, None].expand(B, Lv, 1)
+        fr = F.linear(pos, sd[prefix + "frameid_proj.weight"], sd[prefix + "frameid_proj.bias"])
+        v = torch.cat([emb, fr], -1)
+    else:
+        v = F.linear(vid, sd[prefix + "vid_proj.weight"], sd[prefix + "vid_proj.bias"])
+    if usr.ndim == 1:
+        u = sd[prefix + "usr_proj.weight"][usr][:, None, :]
+    else:
+        u = F.linear(usr, sd[prefix + "usr_proj.weight"], sd[prefix + "usr_proj.bias"])
     if use_pe:
         v = v + sd[prefix + "vid_pe.weight"][None, : v.shape[1]]
         u = u + sd[prefix + "usr_pe.weight"][None, : u.shape[1]]
@@ -113,6 +126,8 @@ def backbone(sd, prefix, usr, usr_mask, vid, vid_mask, nhead, num_layers, use_pe
     BEFORE each layer and the caller takes [-1], so layer N-1 never reaches the
     output, nor does the history side of layer N-2."""
     v, u = embed(sd, prefix, usr, vid, use_pe)
+    if usr.ndim == 1:   # ID user: one token, mask of ones (encoder.py:478-481)
+        usr_mask = torch.ones(usr.shape[0], 1, dtype=torch.bool)
     for i in range(num_layers - 1):
         p = f"{prefix}encoder.layers.{i}."
         need_usr = i < num_layers - 2
@@ -126,13 +141,31 @@ def backbone(sd, prefix, usr, usr_mask, vid, vid_mask, nhead, num_layers, use_pe
 # --------------------------------------------------------------------------
 # a-9/a-10  head (+ optional learnable position bias)
 # --------------------------------------------------------------------------
-def head_logits(sd, x):
-    """models/decoder_leave_focal.py:451,596 and :497-504."""
-    logits = F.linear(x, sd["stage_mlp1.weight"], sd["stage_mlp1.bias"]).squeeze(-1)
+def _position_bias(sd, logits):
     if "bias_weight" in sd:
         pos = torch.arange(logits.shape[1], dtype=logits.dtype)
         logits = logits + (pos + 1) * sd["bias_weight"].reshape(1, -1) + sd["bias_bias"].reshape(1, -1)
     return logits
+
+
+def head_logits(sd, x):
+    """models/decoder_leave_focal.py:451,596 and :497-504."""
+    logits = F.linear(x, sd["stage_mlp1.weight"], sd["stage_mlp1.bias"]).squeeze(-1)
+    return _position_bias(sd, logits)
+
+
+def fusion_logits(sd, x, y, num_heads):
+    """InteractionAggregation.forward, models/decoder_leave_focal.py:411-423 (output_dim 1):
+    w_x.x + w_y.y + sum_h x_h^T W_h y_h with W stored flat [H*dx*dy, 1] viewed [H, dx, dy]."""
+    B, L, d = x.shape
+    out = F.linear(x, sd["fusion_module.w_x.weight"], sd["fusion_module.w_x.bias"]) + \
+        F.linear(y, sd["fusion_module.w_y.weight"], sd["fusion_module.w_y.bias"])
+    dx = d // num_heads
+    W = sd["fusion_module.w_xy"].view(num_heads, dx, dx)
+    xh = x.reshape(B * L, num_heads, dx)
+    yh = y.reshape(B * L, num_heads, dx)
+    xy = torch.einsum("rhi,hij,rhj->r", xh, W, yh)
+    return _position_bias(sd, out.squeeze(-1) + xy.view(B, L))
 
 
 # --------------------------------------------------------------------------
@@ -213,12 +246,28 @@ def compute_loss(logits, gt, exposure_prob, loss_type_list=("focal",), loss_weig
 # full forward (image modality, single backbone)
 # --------------------------------------------------------------------------
 def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_layers,
-            exposure_prob=None, loss_type_list=("focal",), use_pe=True, mode="train", loss_weight=None):
-    """models/decoder_leave_focal.py:574-658 for input_type image/image,
-    backbone2=None, head=None."""
-    x = backbone(sd, "backbone1.", usr_image, usr_mask.bool(), vid_image, vid_mask.bool(),
-                 nhead, num_layers, use_pe)
-    logits = head_logits(sd, x)
+            exposure_prob=None, loss_type_list=("focal",), use_pe=True, mode="train", loss_weight=None,
+            usr_id=None, vid_id=None, input_type=None, fusion_heads=2):
+    """models/decoder_leave_focal.py:574-658.  input_type {'user': image|id|both, 'photo': image|id|both}
+    (default image/image, single backbone, Linear head); with a 'both' entry there are two backbones
+    (main...SegMM.py:63-106: backbone1 takes the image side of a 'both' input, backbone2 the id side) fused by
+    InteractionAggregation (fusion_heads > 0)."""
+    it = input_type or {"user": "image", "photo": "image"}
+    two = it["user"] == "both" or it["photo"] == "both"
+
+    def pick(kind, image, ident, which):
+        if kind == "both":
+            return image if which == 1 else ident
+        return image if kind == "image" else ident
+
+    x1 = backbone(sd, "backbone1.", pick(it["user"], usr_image, usr_id, 1), usr_mask.bool(),
+                  pick(it["photo"], vid_image, vid_id, 1), vid_mask.bool(), nhead, num_layers, use_pe)
+    if two:
+        x2 = backbone(sd, "backbone2.", pick(it["user"], usr_image, usr_id, 2), usr_mask.bool(),
+                      pick(it["photo"], vid_image, vid_id, 2), vid_mask.bool(), nhead, num_layers, use_pe)
+        logits = fusion_logits(sd, x1, x2, fusion_heads)
+    else:
+        logits = head_logits(sd, x1)
     if mode == "inference":
         return dict(logits=logits, gt=gt)
     exposure_prob = exposure_prob if exposure_prob is not None else [1.0] * logits.shape[1]

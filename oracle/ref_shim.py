@@ -129,6 +129,34 @@ def build_reference_model(args, din=1024, max_usr_len=100, max_vid_len=40, seed=
     return model
 
 
+def build_reference_model_general(args, din=1024, n_users=0, n_items=0, max_vid_len=40, seed=42):
+    """init_model() of main_for_seq_leave_earlystop_SegMM.py:60-130 for any input_type (image / id / both);
+    n_users / n_items stand for reader.n_users / reader.n_items."""
+    import torch
+    import torch.nn as nn
+    ref = load()
+    torch.manual_seed(seed)
+    n = args.num_layers_enc
+    it = args.input_type
+
+    def bb(user_id_max, video_id_max, max_usr_len):
+        return ref.SegFormerX(d_model_in=args.d_model, d_model_lvls=[args.d_model] * n, num_head_lvls=[args.nhead] * n,
+                              ff_dim_lvls=[args.d_model] * n, input_vid_dim=din, input_usr_dim=din, max_vid_len=max_vid_len,
+                              max_usr_len=max_usr_len, sr_ratio_lvls=[1] * n, use_patch_merge=[False] * n, output_layers=[-1],
+                              model_cfg=args, user_id_max=user_id_max, video_id_max=video_id_max, use_pe=args.use_pe)
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        if it["user"] == "both" or it["photo"] == "both":
+            u1, l1, u2, l2 = {"both": (-1, 100, n_users, 1), "id": (n_users, 1, n_users, 1), "image": (-1, 100, -1, 100)}[it["user"]]
+            v1, v2 = {"both": (-1, n_items), "id": (n_items, n_items), "image": (-1, -1)}[it["photo"]]
+            model = ref.MultiScaleTemporalDetrLeaveFocal(bb(u1, v1, l1), bb(u2, v2, l2), None, nn.Identity(), args)
+        else:
+            u1, l1 = (n_users, 1) if it["user"] == "id" else (-1, 100)
+            v1 = n_items if it["photo"] == "id" else -1
+            model = ref.MultiScaleTemporalDetrLeaveFocal(bb(u1, v1, l1), None, None, nn.Identity(), args)
+    return model
+
+
 def run_reference(model, batch, mode="train"):
     """Calls the reference forward with stdout swallowed (it prints each call)."""
     with contextlib.redirect_stdout(io.StringIO()):

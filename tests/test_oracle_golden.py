@@ -54,6 +54,42 @@ def test_model_small_matches_reference(name):
     assert _rel(inf["logits"].numpy(), z["logits_inference"]) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["model_both_small", "model_id_small"])
+def test_general_config_matches_reference(name):
+    """ID-embedding inputs, two backbones + InteractionAggregation (the reference default 'both'),
+    interestBPR: the oracle against the unmodified reference."""
+    z = _load(name)
+    cfg = json.loads(str(z["cfg"]))
+    sd = {k[3:]: torch.from_numpy(z[k]).clone() for k in z.files if k.startswith("sd/")}
+    for k, v in sd.items():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    kw = dict(nhead=cfg["nhead"], num_layers=cfg["num_layers_enc"], loss_type_list=tuple(cfg["loss_types"]),
+              usr_id=torch.from_numpy(z["usr_id"]), vid_id=torch.from_numpy(z["vid_id"]), input_type=cfg["input_type"],
+              fusion_heads=cfg["fusion_heads"])
+    args = (torch.from_numpy(z["usr_image"]), torch.from_numpy(z["usr_mask"]), torch.from_numpy(z["vid_image"]),
+            torch.from_numpy(z["vid_mask"]), torch.from_numpy(z["gt_in"]))
+    out = mmi_oracle.forward(sd, *args, **kw)
+    assert _rel(out["logits"].detach().numpy(), z["logits"]) < 1e-5
+    assert abs(out["loss"].item() - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    for lt in cfg["loss_types"]:
+        assert abs(out[lt].item() - float(z[lt])) <= 1e-5 * abs(float(z[lt]))
+    out["loss"].backward()
+    dead = set(json.loads(str(z["dead_params"])))
+    live = set(mmi_oracle.live_param_names([k for k in sd if ("grad/" + k) in z.files or k in dead], cfg["num_layers_enc"]))
+    assert live == {k for k in sd if ("grad/" + k) in z.files}
+    for k in sorted(live):
+        assert sd[k].grad is not None, k
+        ref = z["grad/" + k].astype(np.float64)
+        # interestBPR is invariant to a common shift of the logits: the head biases get an analytically zero
+        # gradient (1e-10 rounding noise in both implementations), hence the absolute term
+        assert np.linalg.norm(sd[k].grad.numpy() - ref) < 5e-5 * np.linalg.norm(ref) + 1e-8, k
+    for k in dead:
+        assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+    inf = mmi_oracle.forward({k: v.detach() for k, v in sd.items()}, *args, mode="inference", **kw)
+    assert _rel(inf["logits"].numpy(), z["logits_inference"]) < 1e-5
+
+
 def test_model_full_matches_reference():
     z = _load("model_full_b4")
     cfg = json.loads(str(z["cfg"]))

@@ -194,6 +194,23 @@ typedef struct {
 } mmi_loss_args;
 int mmi_loss_fwd_bwd(const mmi_loss_args* args, mmi_stream_t stream);
 
+/* ---- ID-embedding inputs and the bilinear fusion head ------------------------------------
+ * mmi_id_embed_fwd: models/encoder.py:352-362,426-435,478-488.  out[b,l,c] = (c < tw ? table[ids[b], c]
+ *   : l * frame_w[c-tw] + frame_b[c-tw]) + pe[l,c]   (video: tw = d/2, L = 40; user: tw = d, L = 1, no frame
+ *   projection).  table fp32 [n_rows, tw], ids int64 [B], pe fp32 [L, d] or NULL, out [B*L, d].
+ * mmi_id_embed_bwd: dtable[ids[b], c] += sum_l de[b,l,c]; dframe_w += sum_{b,l} l*de; dframe_b += sum de (atomics). */
+int mmi_id_embed_fwd(const float* table, int64_t n_rows, int tw, const int64_t* ids, int B, int L, int d,
+                     const float* frame_w, const float* frame_b, const float* pe, void* out, int out_dtype,
+                     mmi_stream_t stream);
+int mmi_id_embed_bwd(const void* de, int dtype, const int64_t* ids, int64_t n_rows, int tw, int B, int L, int d,
+                     float* dtable, float* dframe_w, float* dframe_b, mmi_stream_t stream);
+/* InteractionAggregation (models/decoder_leave_focal.py:411-423) after the two X_h W_h GEMMs:
+ *   out[r] = sum_c T[r,c] * Y[r,c] (+ add1[r]) (+ add2[r]);   backward: dT = g*Y, dY = g*T (+ dy_add), g *= gscale[0]. */
+int mmi_rowdot_fwd(const void* t, int64_t ldt, const void* y, int64_t ldy, int dtype, int64_t R, int C,
+                   const float* add1, const float* add2, float* out, mmi_stream_t stream);
+int mmi_rowdot_bwd(const float* g, const float* gscale, const void* t, int64_t ldt, const void* y, int64_t ldy,
+                   int dtype, int64_t R, int C, const void* dy_add, void* dt, void* dy, mmi_stream_t stream);
+
 /* ---- a-14: global-norm clip + AdamW on flat fp32 buffers ----------------------------
  * replaces main_for_seq_leave_earlystop_SegMM.py:298-299 (clip_grad_norm_(10.0),
  * torch.optim.AdamW.step).  norm_out[0] = pre-clip global L2 norm, norm_out[1] = clip

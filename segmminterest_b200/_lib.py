@@ -68,6 +68,10 @@ _SIGS = {
     "mmi_head_bwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmi_focal_loss_fwd_bwd": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, C.c_float, C.c_float, C.c_int, c_p, c_p, c_p]),
     "mmi_loss_fwd_bwd": (C.c_int, [C.POINTER(LossArgs), c_p]),
+    "mmi_id_embed_fwd": (C.c_int, [c_p, i64, C.c_int, c_p, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, c_p, C.c_int, c_p]),
+    "mmi_id_embed_bwd": (C.c_int, [c_p, C.c_int, c_p, i64, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, c_p]),
+    "mmi_rowdot_fwd": (C.c_int, [c_p, i64, c_p, i64, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p]),
+    "mmi_rowdot_bwd": (C.c_int, [c_p, c_p, c_p, i64, c_p, i64, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p]),
     "mmi_clip_adamw_workspace": (i64, [i64]),
     "mmi_clip_adamw": (C.c_int, [c_p, c_p, c_p, c_p, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int, c_p, c_p, c_p, c_p]),

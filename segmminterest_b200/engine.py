@@ -37,12 +37,38 @@ class EngineConfig:
     precision: str = "fp32"   # 'fp32' (FFMA, strict parity) | 'bf16' (tcgen05 tensor cores)
 
 
+class _View:
+    """A column window of a workspace tensor (pointer + dtype only; the leading dimension is passed separately)."""
+    __slots__ = ("_ptr", "dtype")
+
+    def __init__(self, ptr, like):
+        self._ptr, self.dtype = ptr, like.dtype
+
+    def data_ptr(self):
+        return self._ptr
+
+
 class _Slot:
     __slots__ = ("name", "param", "off", "numel", "shape")
 
     def __init__(self, name, param, off):
         self.name, self.param, self.off = name, param, off
         self.numel, self.shape = param.numel(), tuple(param.shape)
+
+
+class _Tower:
+    """One backbone (SegFormerX parameter container) and how its two inputs arrive: 'image' = [B,L,Din] features through a
+    Linear projection, 'id' = int64 ids through an embedding table (models/encoder.py:352-362,426-435)."""
+
+    def __init__(self, tag, prefix, module):
+        import torch.nn as nn
+        self.tag, self.prefix, self.m = tag, prefix, module
+        self.vid_kind = "id" if isinstance(module.vid_proj, nn.Embedding) else "image"
+        self.usr_kind = "id" if isinstance(module.usr_proj, nn.Embedding) else "image"
+
+    def k(self, name):
+        """group key: bare for backbone1 (kept from the single-backbone engine), 'b2/...' for backbone2"""
+        return name if self.tag == "b1" else f"{self.tag}/{name}"
 
 
 class Engine:
@@ -56,6 +82,10 @@ class Engine:
         if cfg.d_model % 4 or cfg.d_model > 1024:
             raise NotImplementedError("d_model must be a multiple of 4 and <= 1024")
         self.act_dtype = torch.float32 if cfg.precision == "fp32" else torch.bfloat16
+        self.towers = [_Tower("b1", "backbone1.", model.backbone1)]
+        if getattr(model, "backbone2", None) is not None:
+            self.towers.append(_Tower("b2", "backbone2.", model.backbone2))
+        self.fusion = getattr(model, "fusion_module", None)
         self.slots: list[_Slot] = []
         self.groups = {}
         self._layout()
@@ -74,7 +104,7 @@ class Engine:
 
     # ------------------------------------------------------------------ parameter layout
     def _layout(self):
-        cfg, bb = self.cfg, self.model.backbone1
+        cfg = self.cfg
         N = cfg.num_layers
         off = 0
 
@@ -87,46 +117,60 @@ class Engine:
                 off += p.numel()
             self.groups[key] = (start, off - start)
 
-        P = "backbone1."
-        group("vid_proj.w", [(P + "vid_proj.weight", bb.vid_proj.weight)])
-        group("vid_proj.b", [(P + "vid_proj.bias", bb.vid_proj.bias)])
-        group("usr_proj.w", [(P + "usr_proj.weight", bb.usr_proj.weight)])
-        group("usr_proj.b", [(P + "usr_proj.bias", bb.usr_proj.bias)])
-        if cfg.use_pe:
-            group("vid_pe", [(P + "vid_pe.weight", bb.vid_pe.weight)])
-            group("usr_pe", [(P + "usr_pe.weight", bb.usr_pe.weight)])
-        for s in ("vid", "usr"):
-            ln = getattr(bb, s + "_ln")
-            group(f"{s}_ln.g", [(f"{P}{s}_ln.weight", ln.weight)])
-            group(f"{s}_ln.b", [(f"{P}{s}_ln.bias", ln.bias)])
-        for i in range(N - 1):
-            L = bb.encoder.layers[i]
-            ca = L.cross_attn
-            full = i < N - 2
-            q = f"{P}encoder.layers.{i}."
-            # six projections of the candidate tokens / of the history tokens, adjacent
-            vid6 = [("v2v", 0), ("v2v", 1), ("v2v", 2), ("t2v", 0), ("v2t", 1), ("v2t", 2)]
-            usr6 = [("t2v", 1), ("t2v", 2), ("v2t", 0), ("t2t", 0), ("t2t", 1), ("t2t", 2)]
-            if not full:
-                vid6, usr6 = vid6[:4], usr6[:2]
-            for side, six in (("vid", vid6), ("usr", usr6)):
-                group(f"L{i}.{side}.w6", [(f"{q}cross_attn.{b}_proj.{j}.weight", getattr(ca, b + "_proj")[j].weight) for b, j in six])
-                group(f"L{i}.{side}.b6", [(f"{q}cross_attn.{b}_proj.{j}.bias", getattr(ca, b + "_proj")[j].bias) for b, j in six])
-            for side in (("vid", "usr") if full else ("vid",)):
-                ff, ln = getattr(ca, "ff_" + side), getattr(ca, "ln_" + side)
-                group(f"L{i}.{side}.wo", [(f"{q}cross_attn.ff_{side}.weight", ff.weight)])
-                group(f"L{i}.{side}.bo", [(f"{q}cross_attn.ff_{side}.bias", ff.bias)])
-                group(f"L{i}.{side}.ln1.g", [(f"{q}cross_attn.ln_{side}.weight", ln.weight)])
-                group(f"L{i}.{side}.ln1.b", [(f"{q}cross_attn.ln_{side}.bias", ln.bias)])
-                mlp, ln2 = getattr(L, "ff_" + side), getattr(L, "ln_" + side)
-                group(f"L{i}.{side}.w1", [(f"{q}ff_{side}.layers.0.weight", mlp.layers[0].weight)])
-                group(f"L{i}.{side}.b1", [(f"{q}ff_{side}.layers.0.bias", mlp.layers[0].bias)])
-                group(f"L{i}.{side}.w2", [(f"{q}ff_{side}.layers.1.weight", mlp.layers[1].weight)])
-                group(f"L{i}.{side}.b2", [(f"{q}ff_{side}.layers.1.bias", mlp.layers[1].bias)])
-                group(f"L{i}.{side}.ln2.g", [(f"{q}ln_{side}.weight", ln2.weight)])
-                group(f"L{i}.{side}.ln2.b", [(f"{q}ln_{side}.bias", ln2.bias)])
-        group("head.w", [("stage_mlp1.weight", self.model.stage_mlp1.weight)])
-        group("head.b", [("stage_mlp1.bias", self.model.stage_mlp1.bias)])
+        for tw in self.towers:
+            bb, P, k = tw.m, tw.prefix, tw.k
+            group(k("vid_proj.w"), [(P + "vid_proj.weight", bb.vid_proj.weight)])
+            if tw.vid_kind == "id":
+                group(k("frameid.w"), [(P + "frameid_proj.weight", bb.frameid_proj.weight)])
+                group(k("frameid.b"), [(P + "frameid_proj.bias", bb.frameid_proj.bias)])
+            else:
+                group(k("vid_proj.b"), [(P + "vid_proj.bias", bb.vid_proj.bias)])
+            group(k("usr_proj.w"), [(P + "usr_proj.weight", bb.usr_proj.weight)])
+            if tw.usr_kind == "image":
+                group(k("usr_proj.b"), [(P + "usr_proj.bias", bb.usr_proj.bias)])
+            if cfg.use_pe:
+                group(k("vid_pe"), [(P + "vid_pe.weight", bb.vid_pe.weight)])
+                group(k("usr_pe"), [(P + "usr_pe.weight", bb.usr_pe.weight)])
+            for s in ("vid", "usr"):
+                ln = getattr(bb, s + "_ln")
+                group(k(f"{s}_ln.g"), [(f"{P}{s}_ln.weight", ln.weight)])
+                group(k(f"{s}_ln.b"), [(f"{P}{s}_ln.bias", ln.bias)])
+            for i in range(N - 1):
+                L = bb.encoder.layers[i]
+                ca = L.cross_attn
+                full = i < N - 2
+                q = f"{P}encoder.layers.{i}."
+                # six projections of the candidate tokens / of the history tokens, adjacent
+                vid6 = [("v2v", 0), ("v2v", 1), ("v2v", 2), ("t2v", 0), ("v2t", 1), ("v2t", 2)]
+                usr6 = [("t2v", 1), ("t2v", 2), ("v2t", 0), ("t2t", 0), ("t2t", 1), ("t2t", 2)]
+                if not full:
+                    vid6, usr6 = vid6[:4], usr6[:2]
+                for side, six in (("vid", vid6), ("usr", usr6)):
+                    group(k(f"L{i}.{side}.w6"), [(f"{q}cross_attn.{b}_proj.{j}.weight", getattr(ca, b + "_proj")[j].weight) for b, j in six])
+                    group(k(f"L{i}.{side}.b6"), [(f"{q}cross_attn.{b}_proj.{j}.bias", getattr(ca, b + "_proj")[j].bias) for b, j in six])
+                for side in (("vid", "usr") if full else ("vid",)):
+                    ff, ln = getattr(ca, "ff_" + side), getattr(ca, "ln_" + side)
+                    group(k(f"L{i}.{side}.wo"), [(f"{q}cross_attn.ff_{side}.weight", ff.weight)])
+                    group(k(f"L{i}.{side}.bo"), [(f"{q}cross_attn.ff_{side}.bias", ff.bias)])
+                    group(k(f"L{i}.{side}.ln1.g"), [(f"{q}cross_attn.ln_{side}.weight", ln.weight)])
+                    group(k(f"L{i}.{side}.ln1.b"), [(f"{q}cross_attn.ln_{side}.bias", ln.bias)])
+                    mlp, ln2 = getattr(L, "ff_" + side), getattr(L, "ln_" + side)
+                    group(k(f"L{i}.{side}.w1"), [(f"{q}ff_{side}.layers.0.weight", mlp.layers[0].weight)])
+                    group(k(f"L{i}.{side}.b1"), [(f"{q}ff_{side}.layers.0.bias", mlp.layers[0].bias)])
+                    group(k(f"L{i}.{side}.w2"), [(f"{q}ff_{side}.layers.1.weight", mlp.layers[1].weight)])
+                    group(k(f"L{i}.{side}.b2"), [(f"{q}ff_{side}.layers.1.bias", mlp.layers[1].bias)])
+                    group(k(f"L{i}.{side}.ln2.g"), [(f"{q}ln_{side}.weight", ln2.weight)])
+                    group(k(f"L{i}.{side}.ln2.b"), [(f"{q}ln_{side}.bias", ln2.bias)])
+        if self.fusion is not None:    # InteractionAggregation (models/decoder_leave_focal.py:392-423)
+            fm = self.fusion
+            group("fusion.wxy", [("fusion_module.w_xy", fm.w_xy)])
+            group("fusion.wx", [("fusion_module.w_x.weight", fm.w_x.weight)])
+            group("fusion.bx", [("fusion_module.w_x.bias", fm.w_x.bias)])
+            group("fusion.wy", [("fusion_module.w_y.weight", fm.w_y.weight)])
+            group("fusion.by", [("fusion_module.w_y.bias", fm.w_y.bias)])
+        else:
+            group("head.w", [("stage_mlp1.weight", self.model.stage_mlp1.weight)])
+            group("head.b", [("stage_mlp1.bias", self.model.stage_mlp1.bias)])
         if getattr(self.model, "bias_weight", None) is not None:   # learnable position bias (decoder_leave_focal.py:442-444)
             group("bias_weight", [("bias_weight", self.model.bias_weight)])
             group("bias_bias", [("bias_bias", self.model.bias_bias)])
@@ -198,6 +242,14 @@ class Engine:
                 if key.endswith((".w6", ".wo", ".w1", ".w2")):
                     rows = n // d
                     ops.cast_bf16(self.flat[off:off + n], self.flat_lpT[off:off + n], rows, d, transpose=True)
+            if self.fusion is not None:     # W_h [dx, dy] -> W_h^T [dy, dx] per head (B operand of X_h W_h)
+                off, n = self.groups["fusion.wxy"]
+                H = self.fusion.num_heads
+                per = n // H
+                dxh = d // H
+                for h in range(H):
+                    ops.cast_bf16(self.flat[off + h * per:off + (h + 1) * per], self.flat_lpT[off + h * per:off + (h + 1) * per], dxh, dxh,
+                                  transpose=True)
 
     # ------------------------------------------------------------------ workspace
     def _buf(self, name, shape, dtype):
@@ -251,35 +303,101 @@ class Engine:
                          add=add, add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=self.use_tc)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, usr_image, usr_mask, vid_image, vid_mask):
+    def forward(self, usr_image, usr_mask, vid_image, vid_mask, usr_id=None, vid_id=None):
         """usr_image [B,Lt,Din] / vid_image [B,Lv,Din] already L1-normalised (the driver does it,
-        main...SegMM.py:272-273; our own data path fuses it into the gather).  Returns fp32
-        logits [B, Lv] (a workspace tensor: clone before the next call)."""
+        main...SegMM.py:272-273; our own data path fuses it into the gather); usr_id / vid_id int64 [B] for towers with
+        ID inputs.  Returns fp32 logits [B, Lv] before the position bias (a workspace tensor: clone before the next call)."""
         cfg = self.cfg
-        ops._need_cuda(usr_image, vid_image, usr_mask, vid_mask)
         self.ensure_bound()
-        B, Lt, _ = usr_image.shape
-        Lv = vid_image.shape[1]
-        if Lt > cfg.max_usr_len or Lv > cfg.max_vid_len:
-            raise ValueError(f"sequence longer than the position table: Lt={Lt} (max {cfg.max_usr_len}), Lv={Lv} (max {cfg.max_vid_len})")
+        self.refresh_low_precision()
+        d = cfg.d_model
+        sv = {"towers": {}}
+        outs = []
+        B = Lv = None
+        for tw in self.towers:
+            x_out, B, Lv = self._tower_forward(tw, sv, usr_image, usr_mask, vid_image, vid_mask, usr_id, vid_id)
+            outs.append(x_out)
+        sv["B"], sv["Lv"] = B, Lv
+        R = B * Lv
+        logits = self._buf("logits", (B, Lv), torch.float32)
+        if self.fusion is None:
+            ops.head_fwd(outs[0], R, d, self.w("head.w"), self.w("head.b"), logits)
+        else:
+            # InteractionAggregation: w_x.x + w_y.y + sum_h x_h^T W_h y_h  (decoder_leave_focal.py:411-423)
+            T = self.act_dtype
+            H = self.fusion.num_heads
+            dxh = d // H
+            x, y = outs
+            t = self._buf("fusion.t", (R, d), T)
+            esz = x.element_size()
+            lp = cfg.precision == "bf16"
+            off, n = self.groups["fusion.wxy"]
+            per = n // H
+            for h in range(H):
+                xa = _View(x.data_ptr() + h * dxh * esz, x)
+                tc = _View(t.data_ptr() + h * dxh * esz, t)
+                if self._impl(R, dxh, dxh, GEMM_NT) == IMPL_TC:
+                    ops.gemm(GEMM_NT, IMPL_TC, xa, d, self.flat_lpT[off + h * per:off + (h + 1) * per], dxh, tc, d, R, dxh, dxh)
+                else:
+                    wsrc = (self.flat_lp if lp else self.flat)[off + h * per:off + (h + 1) * per]
+                    ops.gemm(GEMM_NN, IMPL_SIMT, xa, d, wsrc, dxh, tc, d, R, dxh, dxh)
+            lin_x = self._buf("fusion.linx", (R,), torch.float32)
+            lin_y = self._buf("fusion.liny", (R,), torch.float32)
+            ops.head_fwd(x, R, d, self.w("fusion.wx"), self.w("fusion.bx"), lin_x)
+            ops.head_fwd(y, R, d, self.w("fusion.wy"), self.w("fusion.by"), lin_y)
+            ops.rowdot_fwd(t, d, y, d, R, d, logits, add1=lin_x, add2=lin_y)
+            sv["fusion.t"] = t
+        sv["x_out"] = outs
+        self._saved = sv
+        return logits
+
+    def _tower_forward(self, tw, sv, usr_image, usr_mask, vid_image, vid_mask, usr_id, vid_id):
+        cfg, k, bb = self.cfg, tw.k, tw.m
         T = self.act_dtype
         d, H, N = cfg.d_model, cfg.nhead, cfg.num_layers
-        self.refresh_low_precision()
-        x_in = {"usr": usr_image.to(T).contiguous().view(B * Lt, -1), "vid": vid_image.to(T).contiguous().view(B * Lv, -1)}
-        mask = {"usr": usr_mask.to(torch.bool).contiguous().view(torch.uint8), "vid": vid_mask.to(torch.bool).contiguous().view(torch.uint8)}
+        B = (vid_id if tw.vid_kind == "id" else vid_image).shape[0]
+        Lv = bb.max_vid_len if tw.vid_kind == "id" else vid_image.shape[1]
+        Lt = 1 if tw.usr_kind == "id" else usr_image.shape[1]
+        if Lt > bb.max_usr_len or Lv > bb.max_vid_len:
+            raise ValueError(f"sequence longer than the position table: Lt={Lt} (max {bb.max_usr_len}), Lv={Lv} (max {bb.max_vid_len})")
+        ops._need_cuda(vid_mask, usr_mask if tw.usr_kind == "image" else None)
         Ls = {"usr": Lt, "vid": Lv}
         Ts = {"usr": B * Lt, "vid": B * Lv}
-        din = {"usr": cfg.din_usr, "vid": cfg.din_vid}
-        sv = {"B": B, "Lt": Lt, "Lv": Lv, "x_in": x_in, "mask": mask, "layers": []}
+        mask = {"vid": vid_mask.to(torch.bool).contiguous().view(torch.uint8)}
+        if tw.usr_kind == "id":       # one token per user, mask of ones (encoder.py:478-481)
+            mask["usr"] = self._buf(k("ones_mask"), (B, 1), torch.uint8)
+            mask["usr"].fill_(1)
+        else:
+            mask["usr"] = usr_mask.to(torch.bool).contiguous().view(torch.uint8)
+        ts = {"B": B, "Lt": Lt, "Lv": Lv, "mask": mask, "layers": [], "x_in": {}, "ids": {}}
         X = {}
         for s in ("vid", "usr"):
-            e = self._buf(f"emb_pre.{s}", (Ts[s], d), T)
-            st = self._buf(f"emb_st.{s}", (Ts[s], 2), torch.float32)
-            x0 = self._buf(f"x0.{s}", (Ts[s], d), T)
-            pe = self.w(f"{s}_pe") if cfg.use_pe else None
-            self._linear(x_in[s], Ts[s], din[s], f"{s}_proj.w", f"{s}_proj.b", d, e, add=pe, add_mod=Ls[s] if pe is not None else 0, ld_add=d)
-            ops.layernorm_fwd(e, Ts[s], d, self.w(f"{s}_ln.g"), self.w(f"{s}_ln.b"), x0, st)
-            sv[f"emb_pre.{s}"], sv[f"emb_st.{s}"] = e, st
+            kind = tw.vid_kind if s == "vid" else tw.usr_kind
+            e = self._buf(k(f"emb_pre.{s}"), (Ts[s], d), T)
+            st = self._buf(k(f"emb_st.{s}"), (Ts[s], 2), torch.float32)
+            x0 = self._buf(k(f"x0.{s}"), (Ts[s], d), T)
+            pe = self.w(k(f"{s}_pe")) if cfg.use_pe else None
+            if kind == "image":
+                img = vid_image if s == "vid" else usr_image
+                ops._need_cuda(img)
+                xin = img.to(T).contiguous().view(Ts[s], -1)
+                ts["x_in"][s] = xin
+                self._linear(xin, Ts[s], xin.shape[1], k(f"{s}_proj.w"), k(f"{s}_proj.b"), d, e, add=pe,
+                             add_mod=Ls[s] if pe is not None else 0, ld_add=d)
+            else:
+                ids = (vid_id if s == "vid" else usr_id)
+                if ids is None:
+                    raise ValueError(f"{tw.prefix[:-1]} takes {s} ids but none were passed")
+                ids = ids.to(torch.int64).contiguous()
+                ops._need_cuda(ids)
+                ts["ids"][s] = ids
+                table = self.w(k(f"{s}_proj.w"))
+                tw_cols = d // 2 if s == "vid" else d
+                table = table.view(-1, tw_cols)
+                ops.id_embed_fwd(table, ids, B, Ls[s], d, e, frame_w=self.w(k("frameid.w")) if s == "vid" else None,
+                                 frame_b=self.w(k("frameid.b")) if s == "vid" else None, pe=pe)
+            ops.layernorm_fwd(e, Ts[s], d, self.w(k(f"{s}_ln.g")), self.w(k(f"{s}_ln.b")), x0, st)
+            ts[f"emb_pre.{s}"], ts[f"emb_st.{s}"] = e, st
             X[s] = x0
         esz = x0.element_size()
         for i in range(N - 1):
@@ -288,8 +406,8 @@ class Engine:
             lay = {"full": full, "nq": nq, "x": dict(X)}
             qkv = {}
             for s in ("vid", "usr"):
-                qkv[s] = self._buf(f"qkv.{i}.{s}", (Ts[s], nq[s] * d), T)
-                self._linear(X[s], Ts[s], d, f"L{i}.{s}.w6", f"L{i}.{s}.b6", nq[s] * d, qkv[s])
+                qkv[s] = self._buf(k(f"qkv.{i}.{s}"), (Ts[s], nq[s] * d), T)
+                self._linear(X[s], Ts[s], d, k(f"L{i}.{s}.w6"), k(f"L{i}.{s}.b6"), nq[s] * d, qkv[s])
             lay["qkv"] = qkv
 
             def col(s, j):
@@ -298,8 +416,8 @@ class Engine:
             sides = ("vid", "usr") if full else ("vid",)
             attn = {}
             for s in sides:
-                a_out = self._buf(f"attn.{i}.{s}", (Ts[s], d), T)
-                lse = self._buf(f"lse.{i}.{s}", (B, H, Ls[s]), torch.float32)
+                a_out = self._buf(k(f"attn.{i}.{s}"), (Ts[s], d), T)
+                lse = self._buf(k(f"lse.{i}.{s}"), (B, H, Ls[s]), torch.float32)
                 if s == "vid":
                     blocks = [dict(q=col("vid", 0), k=col("vid", 1), v=col("vid", 2), mask_k=mask["vid"], Lk=Lv),
                               dict(q=col("vid", 3), k=col("usr", 0), v=col("usr", 1), mask_k=mask["usr"], Lk=Lt)]
@@ -312,27 +430,24 @@ class Engine:
                 attn[s] = (side, a_out, lse)
             lay["attn"] = attn
             for s in sides:
-                p1 = self._buf(f"p1.{i}.{s}", (Ts[s], d), T)
-                st1 = self._buf(f"st1.{i}.{s}", (Ts[s], 2), torch.float32)
-                x1 = self._buf(f"x1.{i}.{s}", (Ts[s], d), T)
-                z1 = self._buf(f"z1.{i}.{s}", (Ts[s], d), T)
-                g1 = self._buf(f"g1.{i}.{s}", (Ts[s], d), T)
-                p2 = self._buf(f"p2.{i}.{s}", (Ts[s], d), T)
-                st2 = self._buf(f"st2.{i}.{s}", (Ts[s], 2), torch.float32)
-                x2 = self._buf(f"x2.{i}.{s}", (Ts[s], d), T)
-                self._linear(attn[s][1], Ts[s], d, f"L{i}.{s}.wo", f"L{i}.{s}.bo", d, p1, add=X[s], add_mod=Ts[s], ld_add=d)
-                ops.layernorm_fwd(p1, Ts[s], d, self.w(f"L{i}.{s}.ln1.g"), self.w(f"L{i}.{s}.ln1.b"), x1, st1)
-                self._linear(x1, Ts[s], d, f"L{i}.{s}.w1", f"L{i}.{s}.b1", d, g1, act=ACT_GELU, preact=z1)
-                self._linear(g1, Ts[s], d, f"L{i}.{s}.w2", f"L{i}.{s}.b2", d, p2, add=x1, add_mod=Ts[s], ld_add=d)
-                ops.layernorm_fwd(p2, Ts[s], d, self.w(f"L{i}.{s}.ln2.g"), self.w(f"L{i}.{s}.ln2.b"), x2, st2)
+                p1 = self._buf(k(f"p1.{i}.{s}"), (Ts[s], d), T)
+                st1 = self._buf(k(f"st1.{i}.{s}"), (Ts[s], 2), torch.float32)
+                x1 = self._buf(k(f"x1.{i}.{s}"), (Ts[s], d), T)
+                z1 = self._buf(k(f"z1.{i}.{s}"), (Ts[s], d), T)
+                g1 = self._buf(k(f"g1.{i}.{s}"), (Ts[s], d), T)
+                p2 = self._buf(k(f"p2.{i}.{s}"), (Ts[s], d), T)
+                st2 = self._buf(k(f"st2.{i}.{s}"), (Ts[s], 2), torch.float32)
+                x2 = self._buf(k(f"x2.{i}.{s}"), (Ts[s], d), T)
+                self._linear(attn[s][1], Ts[s], d, k(f"L{i}.{s}.wo"), k(f"L{i}.{s}.bo"), d, p1, add=X[s], add_mod=Ts[s], ld_add=d)
+                ops.layernorm_fwd(p1, Ts[s], d, self.w(k(f"L{i}.{s}.ln1.g")), self.w(k(f"L{i}.{s}.ln1.b")), x1, st1)
+                self._linear(x1, Ts[s], d, k(f"L{i}.{s}.w1"), k(f"L{i}.{s}.b1"), d, g1, act=ACT_GELU, preact=z1)
+                self._linear(g1, Ts[s], d, k(f"L{i}.{s}.w2"), k(f"L{i}.{s}.b2"), d, p2, add=x1, add_mod=Ts[s], ld_add=d)
+                ops.layernorm_fwd(p2, Ts[s], d, self.w(k(f"L{i}.{s}.ln2.g")), self.w(k(f"L{i}.{s}.ln2.b")), x2, st2)
                 lay[s] = dict(p1=p1, st1=st1, x1=x1, z1=z1, g1=g1, p2=p2, st2=st2)
                 X[s] = x2
-            sv["layers"].append(lay)
-        sv["x_out"] = X["vid"]
-        logits = self._buf("logits", (B, Lv), torch.float32)
-        ops.head_fwd(X["vid"], Ts["vid"], d, self.w("head.w"), self.w("head.b"), logits)
-        self._saved = sv
-        return logits
+            ts["layers"].append(lay)
+        sv["towers"][tw.tag] = ts
+        return X["vid"], B, Lv
 
     # ------------------------------------------------------------------ loss
     def loss(self, logits, gt, exposure_prob, inv_bsz, loss_cfg=None, bpr_scale=1.0, need_grad=True):
@@ -373,41 +488,85 @@ class Engine:
     # ------------------------------------------------------------------ backward
     def backward(self, gscale=None, on_ready=None):
         """Accumulates d(loss)/d(param) into the flat gradient buffer.  `gscale` is the upstream
-        gradient of the loss (device scalar) -- never read on the host."""
+        gradient of the loss (device scalar) -- never read on the host.  on_ready(lo): every gradient at flat
+        offsets >= lo is final (the layout is forward order, backward walks it from the top)."""
         sv = self._saved
         if sv is None or "dlogits" not in sv:
             raise RuntimeError("backward() called before forward()+loss()")
         self.bind_grads()
         cfg = self.cfg
         T = self.act_dtype
-        d, H, N = cfg.d_model, cfg.nhead, cfg.num_layers
-        B, Lt, Lv = sv["B"], sv["Lt"], sv["Lv"]
-        Ls = {"usr": Lt, "vid": Lv}
-        Ts = {"usr": B * Lt, "vid": B * Lv}
-        din = {"usr": cfg.din_usr, "vid": cfg.din_vid}
-        mask = sv["mask"]
-
-        def scratch(name, s, width=d):
-            return self._buf(f"bw.{name}.{s}", (Ts[s], width), T)
-
+        d = cfg.d_model
+        B, Lv = sv["B"], sv["Lv"]
+        R = B * Lv
         if "bias_weight" in self.groups:   # d loss / d (bias_weight, bias_bias) from the loss kernel, times the upstream gradient
             db = self._buf("dbias", (2, self.groups["bias_weight"][1]), torch.float32)
             gs = gscale if gscale is not None else 1.0
             self.g("bias_weight").add_(db[0] * gs)
             self.g("bias_bias").add_(db[1] * gs)
-        dX = {"vid": scratch("dx", "vid"), "usr": None}
-        ops.head_bwd(sv["x_out"], Ts["vid"], d, self.w("head.w"), sv["dlogits"], gscale, dX["vid"], self.g("head.w"),
-                     self.g("head.b"), self.red_ws)
-        if on_ready is not None:
-            on_ready(self.groups["head.w"][0])
+        dX_out = []
+        if self.fusion is None:
+            dx = self._buf("bw.dx.b1.vid", (R, d), T)
+            ops.head_bwd(sv["x_out"][0], R, d, self.w("head.w"), sv["dlogits"], gscale, dx, self.g("head.w"), self.g("head.b"), self.red_ws)
+            dX_out.append(dx)
+            if on_ready is not None:
+                on_ready(self.groups["head.w"][0])
+        else:
+            H = self.fusion.num_heads
+            dxh = d // H
+            x, y = sv["x_out"]
+            t = sv["fusion.t"]
+            esz = x.element_size()
+            lp = cfg.precision == "bf16"
+            dx_lin = self._buf("bw.fusion.dxlin", (R, d), T)
+            dy_lin = self._buf("bw.fusion.dylin", (R, d), T)
+            ops.head_bwd(x, R, d, self.w("fusion.wx"), sv["dlogits"], gscale, dx_lin, self.g("fusion.wx"), self.g("fusion.bx"), self.red_ws)
+            ops.head_bwd(y, R, d, self.w("fusion.wy"), sv["dlogits"], gscale, dy_lin, self.g("fusion.wy"), self.g("fusion.by"), self.red_ws)
+            dt_ = self._buf("bw.fusion.dt", (R, d), T)
+            dy = self._buf("bw.dx.b2.vid", (R, d), T)
+            ops.rowdot_bwd(sv["dlogits"], gscale, t, d, y, d, R, d, dt_, dy, dy_add=dy_lin)
+            dx = self._buf("bw.dx.b1.vid", (R, d), T)
+            off, n = self.groups["fusion.wxy"]
+            per = n // H
+            for h in range(H):
+                xa = _View(x.data_ptr() + h * dxh * esz, x)
+                dta = _View(dt_.data_ptr() + h * dxh * esz, dt_)
+                dxa = _View(dx.data_ptr() + h * dxh * esz, dx)
+                adda = _View(dx_lin.data_ptr() + h * dxh * esz, dx_lin)
+                gw = self.flat_grad[off + h * per:off + (h + 1) * per]
+                # dW_h += X_h^T dT_h ; dX_h = dT_h W_h^T + g w_x
+                impl_w = self._impl(dxh, dxh, R, GEMM_TN)
+                ops.gemm(GEMM_TN, impl_w, xa, d, dta, d, gw, dxh, dxh, dxh, R, accumulate=True, split_k=0 if impl_w == IMPL_TC else 1,
+                         out_dtype=_lib.F32)
+                wsrc = (self.flat_lp if lp else self.flat)[off + h * per:off + (h + 1) * per]
+                ops.gemm(GEMM_NT, self._impl(R, dxh, dxh, GEMM_NT), dta, d, wsrc, dxh, dxa, d, R, dxh, dxh, add=adda, add_mod=R, ld_add=d)
+            dX_out = [dx, dy]
+            if on_ready is not None:
+                on_ready(self.groups["fusion.wxy"][0])
+        for tw, dxo in reversed(list(zip(self.towers, dX_out))):
+            self._tower_backward(tw, sv["towers"][tw.tag], dxo, on_ready)
+        self._saved = None
+
+    def _tower_backward(self, tw, ts, dx_out, on_ready):
+        cfg, k = self.cfg, tw.k
+        T = self.act_dtype
+        d, H, N = cfg.d_model, cfg.nhead, cfg.num_layers
+        B, Lt, Lv = ts["B"], ts["Lt"], ts["Lv"]
+        Ls = {"usr": Lt, "vid": Lv}
+        Ts = {"usr": B * Lt, "vid": B * Lv}
+
+        def scratch(name, s, width=d):
+            return self._buf(f"bw.{name}.{tw.tag}.{s}.{width}", (Ts[s], width), T)
+
+        dX = {"vid": dx_out, "usr": None}
         for i in reversed(range(N - 1)):
-            lay = sv["layers"][i]
+            lay = ts["layers"][i]
             full, nq, Xin = lay["full"], lay["nq"], lay["x"]
             sides = ("vid", "usr") if full else ("vid",)
             dP1, dA = {}, {}
             for s in sides:
                 a = lay[s]
-                pre = f"L{i}.{s}."
+                pre = k(f"L{i}.{s}.")
                 dp2 = scratch("dp2", s)
                 ops.layernorm_bwd(dX[s], a["p2"], Ts[s], d, self.w(pre + "ln2.g"), a["st2"], None, dp2, self.g(pre + "ln2.g"),
                                   self.g(pre + "ln2.b"), self.red_ws, dxsum=self.g(pre + "b2"))
@@ -429,7 +588,7 @@ class Engine:
 
             for s in sides:
                 side = lay["attn"][s][0]
-                delta = self._buf(f"delta.{s}", (B, H, Ls[s]), torch.float32)
+                delta = self._buf(f"delta.{tw.tag}.{s}", (B, H, Ls[s]), torch.float32)
                 if s == "vid":
                     grads = [dict(dq=gcol("vid", 0), dk=gcol("vid", 1), dv=gcol("vid", 2)),
                              dict(dq=gcol("vid", 3), dk=gcol("usr", 0), dv=gcol("usr", 1))]
@@ -442,24 +601,36 @@ class Engine:
                 side.bwd_dkv(1)
             new_dX = {}
             for s in ("vid", "usr"):
-                pre = f"L{i}.{s}."
-                out = scratch("dx", s) if dX[s] is None or True else None
+                pre = k(f"L{i}.{s}.")
+                out = scratch("dxl", s)
                 # dX[s] (the grad w.r.t. this layer's OUTPUT) is dead by now: dp2 consumed it
                 self._linear_bwd(dqkv[s], Xin[s], Ts[s], nq[s] * d, d, pre + "w6", pre + "b6", out, add=dP1.get(s))
                 new_dX[s] = out
             dX = new_dX
             if on_ready is not None:
-                on_ready(self.groups[f"L{i}.vid.w6"][0])  # first group of layer i in the flat layout
+                on_ready(self.groups[k(f"L{i}.vid.w6")][0])  # first group of layer i in the flat layout
         for s in ("vid", "usr"):
-            de = self._buf(f"bw.de.{s}", (Ts[s], d), T)
             if dX[s] is None:
                 continue
-            ops.layernorm_bwd(dX[s], sv[f"emb_pre.{s}"], Ts[s], d, self.w(f"{s}_ln.g"), sv[f"emb_st.{s}"], None, de,
-                              self.g(f"{s}_ln.g"), self.g(f"{s}_ln.b"), self.red_ws, dxsum=self.g(f"{s}_proj.b"))
+            kind = tw.vid_kind if s == "vid" else tw.usr_kind
+            de = self._buf(f"bw.de.{tw.tag}.{s}", (Ts[s], d), T)
+            if kind == "image":
+                ops.layernorm_bwd(dX[s], ts[f"emb_pre.{s}"], Ts[s], d, self.w(k(f"{s}_ln.g")), ts[f"emb_st.{s}"], None, de,
+                                  self.g(k(f"{s}_ln.g")), self.g(k(f"{s}_ln.b")), self.red_ws, dxsum=self.g(k(f"{s}_proj.b")))
+            else:
+                ops.layernorm_bwd(dX[s], ts[f"emb_pre.{s}"], Ts[s], d, self.w(k(f"{s}_ln.g")), ts[f"emb_st.{s}"], None, de,
+                                  self.g(k(f"{s}_ln.g")), self.g(k(f"{s}_ln.b")), self.red_ws)
             if cfg.use_pe:
                 # d pe[l,:] = sum_b dE[b,l,:]  -> column sums of dE viewed as [B, L*d]
-                ops.colsum_acc(de, B, Ls[s] * d, Ls[s] * d, self.g(f"{s}_pe")[: Ls[s] * d], self.red_ws)
-            self._linear_bwd(de, sv["x_in"][s], Ts[s], d, din[s], f"{s}_proj.w", f"{s}_proj.b", None, need_dx=False, bias_done=True)
+                ops.colsum_acc(de, B, Ls[s] * d, Ls[s] * d, self.g(k(f"{s}_pe"))[: Ls[s] * d], self.red_ws)
+            if kind == "image":
+                xin = ts["x_in"][s]
+                self._linear_bwd(de, xin, Ts[s], d, xin.shape[1], k(f"{s}_proj.w"), k(f"{s}_proj.b"), None, need_dx=False, bias_done=True)
+            else:
+                tw_cols = d // 2 if s == "vid" else d
+                gtab = self.g(k(f"{s}_proj.w"))
+                ops.id_embed_bwd(de, ts["ids"][s], gtab.numel() // tw_cols, tw_cols, B, Ls[s], d, gtab,
+                                 dframe_w=self.g(k("frameid.w")) if s == "vid" else None,
+                                 dframe_b=self.g(k("frameid.b")) if s == "vid" else None)
         if on_ready is not None:
-            on_ready(0)
-        self._saved = None
+            on_ready(self.groups[k("vid_proj.w")][0])

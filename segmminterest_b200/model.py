@@ -109,9 +109,6 @@ class SegFormerX(_Container):
                  use_patch_merge=[True, False, True, False], output_layers=None, model_cfg=None, user_id_max=-1,
                  video_id_max=-1, use_pe=1):
         super().__init__()
-        if user_id_max != -1 or video_id_max != -1:
-            raise NotImplementedError("ID-embedding backbone (user_id_max/video_id_max != -1) is SURVEY section 8f-1 "
-                                      "('next'); only the image modality is built")
         abl = getattr(model_cfg, "ablation_type", "ours") if model_cfg is not None else "ours"
         if abl != "ours":
             raise NotImplementedError(f"ablation_type={abl!r}: only 'ours' is built")
@@ -122,8 +119,16 @@ class SegFormerX(_Container):
             raise NotImplementedError("all levels must share d_model / ff_dim / nhead (main...SegMM.py:89-91)")
         if output_layers not in ([-1], (-1,)):
             raise NotImplementedError("output_layers must be [-1] (main...SegMM.py:95)")
-        self.vid_proj = nn.Linear(input_vid_dim, d_model_in)
-        self.usr_proj = nn.Linear(input_usr_dim, d_model_in)
+        # models/encoder.py:352-362: an id_max != -1 turns the projection into an embedding table
+        if video_id_max != -1:
+            self.vid_proj = nn.Embedding(video_id_max + 1, d_model_in // 2)
+            self.frameid_proj = nn.Linear(1, d_model_in // 2)
+        else:
+            self.vid_proj = nn.Linear(input_vid_dim, d_model_in)
+        if user_id_max != -1:
+            self.usr_proj = nn.Embedding(user_id_max + 1, d_model_in)
+        else:
+            self.usr_proj = nn.Linear(input_usr_dim, d_model_in)
         self.debug = getattr(model_cfg, "debug", 0)
         self.num_layers_enc = len(d_model_lvls)
         self.use_pe = use_pe
@@ -159,27 +164,44 @@ class _EngineStep(torch.autograd.Function):
         return None, None, None
 
 
+class InteractionAggregation(_Container):
+    """Parameters of models/decoder_leave_focal.py:392-410 (output_dim 1): w_x, w_y Linear(d, 1) and the bilinear
+    weight stored flat [H * dx * dy, 1]."""
+
+    def __init__(self, x_dim, y_dim, output_dim=1, num_heads=1):
+        super().__init__()
+        if output_dim != 1 or x_dim != y_dim or num_heads <= 0 or x_dim % num_heads:
+            raise NotImplementedError("InteractionAggregation: output_dim 1, x_dim == y_dim divisible by num_heads > 0")
+        self.num_heads, self.output_dim = num_heads, output_dim
+        self.w_x = nn.Linear(x_dim, output_dim)
+        self.w_y = nn.Linear(y_dim, output_dim)
+        for lin in (self.w_x, self.w_y):                      # kn_util/nn_utils/init.py:52-62
+            nn.init.xavier_uniform_(lin.weight.data)
+            lin.bias.data.zero_()
+        self.head_x_dim = x_dim // num_heads
+        self.head_y_dim = y_dim // num_heads
+        self.w_xy = nn.Parameter(torch.empty(num_heads * self.head_x_dim * self.head_y_dim, output_dim))
+        nn.init.xavier_normal_(self.w_xy)
+
+
 class MultiScaleTemporalDetrLeaveFocal(nn.Module):
-    """models/decoder_leave_focal.py:425-658, image modality, single backbone, `focal`
-    loss: ctor (backbone1, backbone2, head, frame_pooler, model_cfg); forward keywords and
-    return dict unchanged.  `precision` ('fp32' strict parity | 'bf16' tensor-core) is read
+    """models/decoder_leave_focal.py:425-658: ctor (backbone1, backbone2, head, frame_pooler, model_cfg); forward
+    keywords and return dict unchanged.  One backbone + Linear head, or two backbones (the reference's default
+    'both' configuration: image features + ID embeddings) fused by InteractionAggregation; losses `focal` and
+    `interestBPR`; optional learnable position bias.  `precision` ('fp32' strict parity | 'bf16' tensor-core) is read
     from model_cfg.mmi_precision when present (default 'fp32')."""
 
     def __init__(self, backbone1, backbone2, head, frame_pooler, model_cfg) -> None:
         super().__init__()
-        if backbone2 is not None:
-            raise NotImplementedError("two-backbone ('both') fusion is SURVEY section 8f-1 ('next')")
         if head is not None:
             raise NotImplementedError("head must be None (main...SegMM.py:106,129)")
         it = getattr(model_cfg, "input_type", {"user": "image", "photo": "image"})
-        if it.get("user") != "image" or it.get("photo") != "image":
-            raise NotImplementedError("only input_type image/image is built (ID inputs: SURVEY 8f-1)")
         for lt in model_cfg.loss_type_list:
             if lt not in ("focal", "interestBPR"):
                 raise NotImplementedError(f"loss_type {lt!r}: 'focal' (the BCE family the path names) and 'interestBPR' "
                                           "(the reference default) are built")
         self.backbone1 = backbone1
-        self.backbone2 = None
+        self.backbone2 = backbone2
         self.model_cfg = model_cfg
         self.head = head
         self.frame_pooler = frame_pooler
@@ -192,15 +214,22 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
             self.bias_bias = nn.Parameter(torch.ones(1, PHOTO_MAX), requires_grad=True)
         self.exposure_prob = model_cfg.exposure_prob
         d_model = model_cfg.d_model
-        self.stage_mlp1 = nn.Linear(d_model, 1)
-        nn.init.xavier_uniform_(self.stage_mlp1.weight.data)  # kn_util/nn_utils/init.py:52-62
-        self.stage_mlp1.bias.data.zero_()
+        if backbone2 is None:
+            self.stage_mlp1 = nn.Linear(d_model, 1)
+            nn.init.xavier_uniform_(self.stage_mlp1.weight.data)  # kn_util/nn_utils/init.py:52-62
+            self.stage_mlp1.bias.data.zero_()
+        else:
+            fh = getattr(model_cfg, "fusion_heads", 2)
+            if fh <= 0:
+                raise NotImplementedError(f"fusion_heads={fh}: only the InteractionAggregation fusion (fusion_heads > 0, the "
+                                          "reference default 2) is built")
+            self.fusion_module = InteractionAggregation(d_model, d_model, output_dim=1, num_heads=fh)
         self._engine = None
         self.precision = getattr(model_cfg, "mmi_precision", "fp32")
 
     # -- engine plumbing ---------------------------------------------------------------
     def engine(self) -> Engine:
-        dev = self.stage_mlp1.weight.device
+        dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise _lib.MMIError("MultiScaleTemporalDetrLeaveFocal (b200) needs the model on a CUDA device: "
                                 "there is no CPU fallback")
@@ -222,7 +251,7 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
     def forward(self, usr_image, usr_id, usr_mask, vid_image, vid_id, vid_mask, gt=None, mode="train", **kwargs):
         eng = self.engine()
         B = usr_id.shape[0]
-        logits = eng.forward(usr_image, usr_mask, vid_image, vid_mask)
+        logits = eng.forward(usr_image, usr_mask, vid_image, vid_mask, usr_id=usr_id, vid_id=vid_id)
         if mode == "inference":
             if self.bias_weight is None:
                 return dict(logits=logits.clone(), gt=gt)
@@ -289,11 +318,23 @@ def reference_state_shapes(d_model=512, num_layers=6, din=1024, max_usr_len=100,
     return s
 
 
-def build_model(args, din=1024, max_usr_len=100, max_vid_len=40, dropout=0.1):
-    """init_model() of main_for_seq_leave_earlystop_SegMM.py:60-130, image/image branch."""
+def build_model(args, din=1024, max_usr_len=100, max_vid_len=40, dropout=0.1, n_users=0, n_items=0):
+    """init_model() of main_for_seq_leave_earlystop_SegMM.py:60-130 for every input_type (image / id / both);
+    n_users / n_items stand for reader.n_users / reader.n_items."""
     n = args.num_layers_enc
-    bb = SegFormerX(d_model_in=args.d_model, d_model_lvls=[args.d_model] * n, num_head_lvls=[args.nhead] * n,
-                    ff_dim_lvls=[args.d_model] * n, input_vid_dim=din, input_usr_dim=din, max_vid_len=max_vid_len,
-                    max_usr_len=max_usr_len, sr_ratio_lvls=[1] * n, use_patch_merge=[False] * n, output_layers=[-1],
-                    model_cfg=args, user_id_max=-1, video_id_max=-1, use_pe=args.use_pe, dropout=dropout)
-    return MultiScaleTemporalDetrLeaveFocal(bb, None, None, nn.Identity(), args)
+    it = getattr(args, "input_type", {"user": "image", "photo": "image"})
+
+    def bb(user_id_max, video_id_max, usr_len):
+        return SegFormerX(d_model_in=args.d_model, d_model_lvls=[args.d_model] * n, num_head_lvls=[args.nhead] * n,
+                          ff_dim_lvls=[args.d_model] * n, input_vid_dim=din, input_usr_dim=din, max_vid_len=max_vid_len,
+                          max_usr_len=usr_len, sr_ratio_lvls=[1] * n, use_patch_merge=[False] * n, output_layers=[-1],
+                          model_cfg=args, user_id_max=user_id_max, video_id_max=video_id_max, use_pe=args.use_pe, dropout=dropout)
+
+    if it["user"] == "both" or it["photo"] == "both":
+        u1, l1, u2, l2 = {"both": (-1, max_usr_len, n_users, 1), "id": (n_users, 1, n_users, 1),
+                          "image": (-1, max_usr_len, -1, max_usr_len)}[it["user"]]
+        v1, v2 = {"both": (-1, n_items), "id": (n_items, n_items), "image": (-1, -1)}[it["photo"]]
+        return MultiScaleTemporalDetrLeaveFocal(bb(u1, v1, l1), bb(u2, v2, l2), None, nn.Identity(), args)
+    u1, l1 = (n_users, 1) if it["user"] == "id" else (-1, max_usr_len)
+    v1 = n_items if it["photo"] == "id" else -1
+    return MultiScaleTemporalDetrLeaveFocal(bb(u1, v1, l1), None, None, nn.Identity(), args)

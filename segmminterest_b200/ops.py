@@ -216,6 +216,38 @@ def loss_fwd_bwd(logits, gt, exposure_prob, *, inv_bsz, scalars, dlogits, use_fo
     LaunchCounter.n += 1
 
 
+def id_embed_fwd(table, ids, B, L, d, out, frame_w=None, frame_b=None, pe=None):
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and table.dtype == torch.float32
+    with TIMER.region("id_embed"):
+        rc = _lib.load().mmi_id_embed_fwd(table.data_ptr(), table.shape[0], table.shape[1], ids.data_ptr(), B, L, d, _ptr(frame_w),
+                                          _ptr(frame_b), _ptr(pe), out.data_ptr(), dt(out), _stream())
+    _lib.check(rc, "mmi_id_embed_fwd")
+    LaunchCounter.n += 1
+
+
+def id_embed_bwd(de, ids, n_rows, tw, B, L, d, dtable, dframe_w=None, dframe_b=None):
+    with TIMER.region("id_embed"):
+        rc = _lib.load().mmi_id_embed_bwd(de.data_ptr(), dt(de), ids.data_ptr(), n_rows, tw, B, L, d, dtable.data_ptr(), _ptr(dframe_w),
+                                          _ptr(dframe_b), _stream())
+    _lib.check(rc, "mmi_id_embed_bwd")
+    LaunchCounter.n += 1
+
+
+def rowdot_fwd(t, ldt, y, ldy, R, C_, out, add1=None, add2=None):
+    with TIMER.region("head"):
+        rc = _lib.load().mmi_rowdot_fwd(t.data_ptr(), ldt, y.data_ptr(), ldy, dt(t), R, C_, _ptr(add1), _ptr(add2), out.data_ptr(), _stream())
+    _lib.check(rc, "mmi_rowdot_fwd")
+    LaunchCounter.n += 1
+
+
+def rowdot_bwd(g, gscale, t, ldt, y, ldy, R, C_, dt_out, dy_out, dy_add=None):
+    with TIMER.region("head"):
+        rc = _lib.load().mmi_rowdot_bwd(g.data_ptr(), _ptr(gscale), t.data_ptr(), ldt, y.data_ptr(), ldy, dt(t), R, C_, _ptr(dy_add),
+                                        dt_out.data_ptr(), dy_out.data_ptr(), _stream())
+    _lib.check(rc, "mmi_rowdot_bwd")
+    LaunchCounter.n += 1
+
+
 def clip_adamw(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, wd, max_norm, step, norm_out, bf16_out, ws):
     lib = _lib.load()
     n = params.numel()

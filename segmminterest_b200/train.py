@@ -52,7 +52,7 @@ class TrainStep:
         self.global_batch = global_batch
         self.loss_cfg = model.loss_cfg()
 
-    def step(self, usr_idx: torch.Tensor, vid_idx: torch.Tensor, gt: torch.Tensor):
+    def step(self, usr_idx: torch.Tensor, vid_idx: torch.Tensor, gt: torch.Tensor, usr_id=None, vid_id=None):
         """One training step on device-resident int32 indices [B,Lt], [B,40] and int64 labels
         [B,40] (rewritten in place like the reference).  Returns the device scalars
         [focal, mse, mse2, loss]; nothing is synchronised."""
@@ -60,7 +60,7 @@ class TrainStep:
         B = usr_idx.shape[0]
         usr, um = self.gather(usr_idx, "usr")
         vid, vm = self.gather(vid_idx, "vid")
-        logits = eng.forward(usr, um, vid, vm)
+        logits = eng.forward(usr, um, vid, vm, usr_id=usr_id, vid_id=vid_id)
         gb = self.global_batch or B * self.buckets.world
         eng.bind_grads()           # Parameters' .grad alias the flat gradient buffer
         eng.flat_grad.zero_()

@@ -83,8 +83,23 @@ def test_unsupported_configs_raise():
     m = build_model(make_args(loss_type_list=["interestBPR"], learnable_bias=1), din=16, max_usr_len=4)   # 8f-1: built
     assert tuple(m.bias_weight.shape) == (1, 40) and tuple(m.bias_bias.shape) == (1, 40)
     with pytest.raises(NotImplementedError):
-        SegFormerX(d_model_in=64, d_model_lvls=[64], num_head_lvls=[2], ff_dim_lvls=[64], sr_ratio_lvls=[1],
-                   use_patch_merge=[False], output_layers=[-1], model_cfg=make_args(), user_id_max=10)
+        SegFormerX(d_model_in=64, d_model_lvls=[64], num_head_lvls=[2], ff_dim_lvls=[64], sr_ratio_lvls=[2],
+                   use_patch_merge=[False], output_layers=[-1], model_cfg=make_args())
+    with pytest.raises(NotImplementedError):      # only the InteractionAggregation fusion (fusion_heads > 0) is built
+        build_model(make_args(input_type={"user": "both", "photo": "both"}, fusion_heads=0), din=16, max_usr_len=4, n_users=3, n_items=5)
+
+
+def test_both_config_state_dict_matches_reference_golden_keys():
+    import json
+    import numpy as np
+    from segmminterest_b200.model import build_model
+    z = np.load(os.path.join(ROOT, "tests", "golden", "model_both_small.npz"))
+    cfg = json.loads(str(z["cfg"]))
+    m = build_model(make_args(d_model=cfg["d_model"], nhead=cfg["nhead"], num_layers_enc=cfg["num_layers_enc"], input_type=cfg["input_type"],
+                              loss_type_list=cfg["loss_types"], loss_weight={"interestBPR": 1.0}), din=cfg["din"], max_usr_len=100,
+                    n_users=cfg["n_users"], n_items=cfg["n_items"])
+    want = [(k[3:], tuple(z[k].shape)) for k in z.files if k.startswith("sd/")]
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == want
 
 
 def test_product_never_imports_oracle():

@@ -83,7 +83,7 @@ def test_general_config_matches_reference(name):
         ref = z["grad/" + k].astype(np.float64)
         # interestBPR is invariant to a common shift of the logits: the head biases get an analytically zero
         # gradient (1e-10 rounding noise in both implementations), hence the absolute term
-        assert np.linalg.norm(sd[k].grad.numpy() - ref) < 5e-5 * np.linalg.norm(ref) + 1e-8, k
+        assert np.linalg.norm(sd[k].grad.numpy() - ref) < 5e-5 * np.linalg.norm(ref) + 1e-7, k
     for k in dead:
         assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
     inf = mmi_oracle.forward({k: v.detach() for k, v in sd.items()}, *args, mode="inference", **kw)

@@ -1,0 +1,79 @@
+"""the vectorised line-id index against the restated reference loader (oracle/gather_oracle.py, itself
+pinned to the unmodified FrameDatasetSeq_SegMM by tests/golden/gather_small.npz) and against that fixture directly."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gather_oracle
+from segmminterest_b200.index import PHOTO_MAX, USER_MAX, SegmentIndex, n_segments, parse_label
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _parse_list(s):
+    return gather_oracle.parse_int_list(s)
+
+
+def test_index_reproduces_reference_loader_fixture():
+    z = np.load(os.path.join(GOLDEN, "gather_small.npz"))
+    lineid = json.loads(str(z["lineid_json"]))
+    uin = json.loads(str(z["user_input_json"]))
+    rows = json.loads(str(z["rows_json"]))
+    table = z["table"]
+    idx = SegmentIndex(lineid, uin)
+    b = idx.batch(user_id=[r[0] for r in rows], video_id=[r[1] for r in rows], duration_ms=[r[3] for r in rows],
+                  history_items=[_parse_list(r[6]) for r in rows], history_playing=[_parse_list(r[7]) for r in rows],
+                  label_1d=[r[5] for r in rows])
+    photo, pmask = gather_oracle.gather_dense(table, b["vid_idx"])
+    user, umask = gather_oracle.gather_dense(table, b["usr_idx"])
+    assert np.array_equal(photo, z["out/photo"]) and np.array_equal(pmask, z["out/photo_mask"])     # bit-exact rows
+    assert np.array_equal(user, z["out/user"]) and np.array_equal(umask, z["out/user_mask"])
+    assert np.array_equal(b["label"], z["out/label"])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_index_matches_oracle_on_random_corpora(seed):
+    rng = np.random.default_rng(seed)
+    n_vid = 60
+    nseg = rng.integers(1, 41, size=n_vid)
+    pids = rng.choice(np.arange(1000, 5000), size=n_vid, replace=False)
+    lineid, r = {}, 0
+    for p, n in zip(pids, nseg):
+        for i in range(n):
+            if rng.random() < 0.95:                      # some segments are missing from the map
+                lineid[f"{p}-{i}"] = r
+                r += 1
+    users = list(range(1, 9))
+    uin = {str(u): [f"{rng.choice(pids)}_{rng.integers(0, 45)}" for _ in range(rng.integers(0, 6))] for u in users}
+    idx = SegmentIndex(lineid, uin)
+    B = 40
+    uid = rng.choice(users, size=B)
+    hist_items = [list(rng.choice(pids, size=rng.integers(0, 6))) + ([99999] if rng.random() < 0.2 else []) for _ in range(B)]
+    hist_play = [[int(rng.integers(0, 120000)) for _ in h] for h in hist_items]
+    got = idx.history_idx(uid, hist_items, hist_play)
+    for b in range(B):
+        want = gather_oracle.history_rows(uid[b], hist_items[b], hist_play[b], lineid, uin)
+        if len(want) <= USER_MAX:
+            assert list(got[b][: len(want)]) == want and np.all(got[b][len(want):] == -1)
+        else:                                            # reference: random.sample of 100 (order not preserved)
+            assert np.all(got[b] >= 0) and set(got[b]) <= set(want) and len(set(got[b])) == USER_MAX
+    # candidates: videos whose segments are all present
+    full = [p for p, n in zip(pids, nseg) if all(f"{p}-{i}" in lineid for i in range(n))]
+    dur = [int(5000 * (nseg[list(pids).index(p)] - 1) + rng.integers(1, 5001)) for p in full]
+    cand = idx.candidate_idx(full, dur)
+    for j, p in enumerate(full):
+        want = gather_oracle.candidate_rows(p, dur[j], lineid)
+        assert list(cand[j][: len(want)]) == want and np.all(cand[j][len(want):] == -1)
+    missing = [p for p in pids if p not in full]
+    if missing:
+        with pytest.raises(ValueError):
+            idx.candidate_idx([missing[0]], [5000 * 40])
+
+
+def test_segment_count_and_label_parsing():
+    for ms in (0, 1, 4999, 5000, 5001, 14999, 200000):
+        assert int(n_segments(ms)) == gather_oracle.n_segments(ms)
+    assert np.array_equal(parse_label("[ 1 1 0 -1]"), gather_oracle.pad_labels("[ 1 1 0 -1]"))
+    assert parse_label("[" + " ".join(["1"] * 50) + "]").shape == (PHOTO_MAX,)

@@ -169,7 +169,7 @@ int mmi_head_bwd(const void* x, int dtype, int64_t rows, int d, const float* w,
  * (my_sigmoid_focal_loss :35-59, alpha 0.5, gamma 2, masked sum / bsz) plus the
  * diagnostics mse / mse2 (:552-558).  gt int64 [B,L] in {1,0,-1,-2}; gt is rewritten in
  * place exactly as the reference does (:534-535) when rewrite_gt != 0.
- * scalars (fp32[8]): 0 focal, 1 mse, 2 mse2, 3 loss(=weight*focal).
+ * scalars (fp32[16], layout under mmi_loss_fwd_bwd): 0 focal, 1 mse, 2 mse2, 3 loss(=weight*focal).
  * dlogits[B,L] = d loss / d logits (already includes weight and inv_bsz).             */
 int mmi_focal_loss_fwd_bwd(const float* logits, int64_t* gt, int B, int L,
                            const float* exposure_prob, float inv_bsz, float weight,
@@ -180,8 +180,17 @@ int mmi_focal_loss_fwd_bwd(const float* logits, int64_t* gt, int B, int L,
  * (compute_interest_BPR_all :163-221: rows with view_len < L; pos = logits[row, view_len], the other L-1 logits --
  * pad positions included -- are negatives; -log(clamp(sum_k softmax_k(neg) * sigmoid(neg_k - pos), 1e-8, 1-1e-8)),
  * mean over those rows, times bpr_scale (1 / world size under data parallelism)).
- * loss = w_focal * focal + w_bpr * interestBPR over the losses switched on.
- * scalars (fp32[8]): 0 focal, 1 mse, 2 mse2, 3 loss, 4 interestBPR.
+ * The other selectable losses of compute_loss (:539-551) ride in the same launch:
+ *   huber      huber_loss(sum hazard_masked [B], view_lengths [B,1], delta 1) -- broadcasts to [B,B] like `mse` (:61-66)
+ *   hazard     compute_partial_likelihood_loss (:273-286), rows with view_len == L skipped, / B
+ *   surviveCE  compute_leave_prob_CE (:68-97): BCE-with-logits fed exp(h_t), sum over valid / number of valid positions
+ *   interestCE / interestKL  compute_interest_leave_CE (:99-161) with use_mask = mask_loss; `*_after_focal` != 0 when
+ *              'focal' precedes the loss in loss_type_list (it then sees focal's in-place rewrite of gt, :534-535).
+ * loss = sum over the losses switched on of w_* x value  (w_huber is loss_weight['mse'], :563-564).  Batch means over a
+ * data-dependent count (interestBPR, surviveCE) and huber's [B,B] mean are taken over this call's rows and scaled by
+ * bpr_scale (1 / world size under data parallelism); focal, hazard, interestCE/KL use inv_bsz (1 / global batch).
+ * scalars (fp32[16]): 0 focal, 1 mse, 2 mse2, 3 loss, 4 interestBPR, 5 huber, 6 hazard, 7 surviveCE, 8 interestCE,
+ * 9 interestKL (10..15 reserved).
  * logits_out (optional) receives logits + bias; dbias_* (optional) are accumulated (+=).             */
 typedef struct {
   const float* logits; int64_t* gt; int B; int L;
@@ -191,6 +200,9 @@ typedef struct {
   int use_focal; int use_bpr; int rewrite_gt;
   float* logits_out; float* scalars; float* dlogits;
   float* dbias_weight; float* dbias_bias;
+  int use_huber; int use_hazard; int use_surviveCE; int use_interestCE; int use_interestKL;
+  int mask_loss; int ce_after_focal; int kl_after_focal;
+  float w_huber; float w_hazard; float w_surviveCE; float w_interestCE; float w_interestKL;
 } mmi_loss_args;
 int mmi_loss_fwd_bwd(const mmi_loss_args* args, mmi_stream_t stream);
 

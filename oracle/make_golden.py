@@ -172,6 +172,48 @@ def run_loss_cases():
     print("loss_cases focal", out["focal"].item(), "bpr", out["interestBPR"].item())
 
 
+ALL_LOSS_VARIANTS = [  # (tag, loss_type_list, mask_loss): order matters -- focal rewrites gt in place before later losses see it
+    ("huber", ["huber"], 0), ("hazard", ["hazard"], 0), ("surviveCE", ["surviveCE"], 0),
+    ("interestCE", ["interestCE"], 0), ("interestCE_m", ["interestCE"], 1),
+    ("interestKL", ["interestKL"], 0), ("interestKL_m", ["interestKL"], 1),
+    ("focal_then_CE_KL", ["focal", "interestCE", "interestKL"], 0),
+    ("CE_then_focal_KL_m", ["interestCE", "focal", "interestKL"], 1),
+    ("all", ["interestBPR", "huber", "hazard", "surviveCE", "focal", "interestCE", "interestKL"], 0),
+]
+
+
+def run_loss_cases_all():
+    """Every other selectable loss of compute_loss (decoder_leave_focal.py:528-551: huber, hazard, surviveCE,
+    interestCE, interestKL, each alone and mixed with focal / interestBPR) on the inputs of loss_cases.npz."""
+    base = np.load(os.path.join(OUT, "loss_cases.npz"))
+    logits, gt, ep = base["logits"], base["gt_in"], list(base["exposure_prob"])
+    save = {}
+    weights = {"focal": 0.7, "mse": 0.3, "hazard": 0.9, "surviveCE": 1.1, "interestBPR": 1.3, "interestCE": 0.8, "interestKL": 1.7}
+    for tag, lst, mask_loss in ALL_LOSS_VARIANTS:
+        args = ref_shim.make_args(d_model=32, nhead=2, num_layers_enc=2, loss_type_list=list(lst), mask_loss=mask_loss,
+                                  loss_weight=dict(weights))
+        model = ref_shim.build_reference_model(args, din=8, max_usr_len=4)
+        model.exposure_prob = ep
+        lg = logits.copy()
+        if any(n.startswith("interestCE") or n.startswith("interestKL") for n in lst):
+            # the reference takes log(softmax(x)) literally (:102,112): the +-60 logits of row 5 underflow it to -inf
+            lg[5, :4] = [8.0, -8.0, 12.0, -12.0]
+        lt = torch.from_numpy(lg).requires_grad_(True)
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = model.compute_loss(stage_logits=lt[..., None], gt=torch.from_numpy(gt.copy()))
+        (g,) = torch.autograd.grad(out["loss"], lt, retain_graph=True)
+        save[f"{tag}/logits"] = lg
+        save[f"{tag}/loss"] = np.float64(out["loss"].item())
+        save[f"{tag}/grad"] = g.numpy()
+        save[f"{tag}/gt_out"] = out["gt"].numpy()
+        for name in lst + ["mse", "mse2"]:
+            save[f"{tag}/{name}"] = np.float64(out[name].item())
+        print("loss_cases_all", tag, {n: round(float(out[n].item()), 6) for n in lst}, "loss", out["loss"].item())
+    save["variants"] = json.dumps(ALL_LOSS_VARIANTS)
+    save["weights"] = json.dumps(weights)
+    np.savez_compressed(os.path.join(OUT, "loss_cases_all.npz"), **save)
+
+
 def run_gather_case():
     """FrameDatasetSeq_SegMM + DataCollator (utils/dataloader_SegMM.py:186-382) on a
     5-video fixture; stores the inputs in index form plus the dense outputs."""
@@ -232,6 +274,7 @@ def main():
     assert ref_shim.available(), "reference tree missing"
     run_gather_case()
     run_loss_cases()
+    run_loss_cases_all()
     run_model_case("model_small_dh32", d_model=64, nhead=2, nlayers=3, din=48, Lt=12, B=5, seed=11)
     run_model_case("model_small_dh16", d_model=64, nhead=4, nlayers=4, din=40, Lt=20, B=4, seed=12)
     run_model_case("model_full_b4", d_model=512, nhead=16, nlayers=6, din=1024, Lt=100, B=4, seed=13,
@@ -249,5 +292,7 @@ def run_general_cases():
 if __name__ == "__main__":
     if "--general-only" in sys.argv:
         run_general_cases()
+    elif "--losses-only" in sys.argv:
+        run_loss_cases_all()
     else:
         main()

@@ -202,7 +202,53 @@ def interest_bpr_all(logits, gt):
     return -(soft.sum(1)).clamp(min=1e-8, max=1 - 1e-8).log().mean()
 
 
-def compute_loss(logits, gt, exposure_prob, loss_type_list=("focal",), loss_weight=None):
+def huber_broadcast(hazard_masked, view_lengths, delta=1.0):
+    """`huber` (models/decoder_leave_focal.py:61-66, call :539-540): the prediction is [B] (expected leave position =
+    sum of masked hazards) and the target [B,1], so -- like `mse` -- the error broadcasts to [B,B]: err[i,j] = H_j - v_i."""
+    err = hazard_masked.sum(1)[None, :] - view_lengths
+    a = err.abs()
+    return torch.where(a < delta, 0.5 * err * err, delta * (a - 0.5 * delta)).mean()
+
+
+def partial_likelihood(hazard_masked, view_lengths):
+    """`hazard` (compute_partial_likelihood_loss :273-286): rows whose observed time (= number of watched segments)
+    equals 40 are skipped; -(log(h[ot]+1e-6) - log(sum_{t>=ot} h[t] + 1e-6)) summed, / n_samples (all rows)."""
+    B, L = hazard_masked.shape
+    ot = view_lengths.view(-1).long()
+    rows = ot != 40
+    idx = torch.arange(L)[None, :]
+    at = (hazard_masked * (idx == ot[:, None])).sum(1)
+    risk = (hazard_masked * (idx >= ot[:, None])).sum(1)
+    ll = torch.log(at + 1e-6) - torch.log(risk + 1e-6)
+    return -(ll * rows.to(ll.dtype)).sum() / B
+
+
+def leave_prob_ce(h_t, gt_binary, mask):
+    """`surviveCE` (compute_leave_prob_CE :68-97): BCE-with-logits fed exp(h_t) -- the survival probability -- as the
+    *logit*, masked, sum / number of valid positions in the batch."""
+    ce = F.binary_cross_entropy_with_logits(torch.exp(h_t), gt_binary, reduction="none")
+    m = mask.to(ce.dtype)
+    return (ce * m).sum() / m.sum()
+
+
+def interest_leave_ce(logits, gt_cur, mask, kind, use_mask):
+    """`interestCE` / `interestKL` (compute_interest_leave_CE :99-161).  gt_cur is gt *as it is when the loss runs*
+    (after focal's in-place rewrite if 'focal' precedes it in loss_type_list)."""
+    nonleave = (gt_cur != 0).to(logits.dtype)
+    log_q = torch.log(logits.softmax(1))
+    tgt = nonleave.softmax(1)
+    m = mask.to(logits.dtype)
+    if kind == "CE":
+        if use_mask:
+            return (-(m * tgt * log_q).sum(1) / m.sum(1)).mean()
+        return (-(tgt * log_q).sum(1)).mean()
+    kl = tgt * (torch.log(tgt) - log_q)
+    if use_mask:
+        return ((kl * m).sum(1) / m.sum(1)).mean()
+    return kl.sum() / logits.shape[0]
+
+
+def compute_loss(logits, gt, exposure_prob, loss_type_list=("focal",), loss_weight=None, mask_loss=0):
     """models/decoder_leave_focal.py:490-572.  Returns the same dict (tensors).
     ``gt`` is NOT modified here; the returned ``gt`` is the rewritten copy the
     reference leaves behind when 'focal' is in the list."""
@@ -215,6 +261,7 @@ def compute_loss(logits, gt, exposure_prob, loss_type_list=("focal",), loss_weig
     view_lengths = (gt == 1).to(logits.dtype).sum(1, keepdim=True)
     durations = mask.sum(1)
     survival_masked = torch.where(mask, survival, torch.zeros_like(survival))
+    hazard_masked = torch.where(mask, 1 - survival, torch.zeros_like(survival))
     out = {}
     gt_cur = gt.clone()
     for name in loss_type_list:
@@ -224,6 +271,14 @@ def compute_loss(logits, gt, exposure_prob, loss_type_list=("focal",), loss_weig
             out["focal"] = focal_loss_sum(logits, gt_cur, mask, exposure_prob, B)
         elif name == "interestBPR":
             out["interestBPR"] = interest_bpr_all(logits, gt)
+        elif name == "huber":
+            out["huber"] = huber_broadcast(hazard_masked, view_lengths)
+        elif name == "hazard":
+            out["hazard"] = partial_likelihood(hazard_masked, view_lengths)
+        elif name == "surviveCE":
+            out["surviveCE"] = leave_prob_ce(h_t, (gt == 1).to(logits.dtype), mask)
+        elif name in ("interestCE", "interestKL"):
+            out[name] = interest_leave_ce(logits, gt_cur, mask, name[-2:], mask_loss)
         else:
             raise NotImplementedError(name)
     s = survival_masked.sum(1)  # [B]
@@ -235,7 +290,7 @@ def compute_loss(logits, gt, exposure_prob, loss_type_list=("focal",), loss_weig
     out["mse2"] = ((sm2.sum(1)[None, :] - view_lengths2) ** 2).mean()
     loss = 0.0
     for name in loss_type_list:
-        loss = loss + out[name] * loss_weight.get(name, 1.0)
+        loss = loss + out[name] * loss_weight.get("mse" if name == "huber" else name, 1.0)   # :563-564
     out["loss"] = loss
     out["logits"] = logits
     out["gt"] = gt_cur
@@ -247,7 +302,7 @@ def compute_loss(logits, gt, exposure_prob, loss_type_list=("focal",), loss_weig
 # --------------------------------------------------------------------------
 def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_layers,
             exposure_prob=None, loss_type_list=("focal",), use_pe=True, mode="train", loss_weight=None,
-            usr_id=None, vid_id=None, input_type=None, fusion_heads=2):
+            usr_id=None, vid_id=None, input_type=None, fusion_heads=2, mask_loss=0):
     """models/decoder_leave_focal.py:574-658.  input_type {'user': image|id|both, 'photo': image|id|both}
     (default image/image, single backbone, Linear head); with a 'both' entry there are two backbones
     (main...SegMM.py:63-106: backbone1 takes the image side of a 'both' input, backbone2 the id side) fused by
@@ -271,7 +326,7 @@ def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_laye
     if mode == "inference":
         return dict(logits=logits, gt=gt)
     exposure_prob = exposure_prob if exposure_prob is not None else [1.0] * logits.shape[1]
-    return compute_loss(logits, gt, exposure_prob, loss_type_list, loss_weight)
+    return compute_loss(logits, gt, exposure_prob, loss_type_list, loss_weight, mask_loss=mask_loss)
 
 
 def live_param_names(sd_keys, num_layers):

@@ -47,7 +47,11 @@ class LossArgs(C.Structure):
                 ("bias_weight", c_p), ("bias_bias", c_p),
                 ("inv_bsz", C.c_float), ("w_focal", C.c_float), ("w_bpr", C.c_float), ("bpr_scale", C.c_float),
                 ("use_focal", C.c_int), ("use_bpr", C.c_int), ("rewrite_gt", C.c_int),
-                ("logits_out", c_p), ("scalars", c_p), ("dlogits", c_p), ("dbias_weight", c_p), ("dbias_bias", c_p)]
+                ("logits_out", c_p), ("scalars", c_p), ("dlogits", c_p), ("dbias_weight", c_p), ("dbias_bias", c_p),
+                ("use_huber", C.c_int), ("use_hazard", C.c_int), ("use_surviveCE", C.c_int), ("use_interestCE", C.c_int),
+                ("use_interestKL", C.c_int), ("mask_loss", C.c_int), ("ce_after_focal", C.c_int), ("kl_after_focal", C.c_int),
+                ("w_huber", C.c_float), ("w_hazard", C.c_float), ("w_surviveCE", C.c_float), ("w_interestCE", C.c_float),
+                ("w_interestKL", C.c_float)]
 
 
 _SIGS = {

@@ -397,39 +397,59 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const T* __restrict__ x, 
 //   focal       : my_sigmoid_focal_loss (alpha .5, gamma 2), masked sum / bsz        :35-59, 533-538
 //   interestBPR : compute_interest_BPR_all, rows with view_len < L, mean over rows   :163-221
 //   mse / mse2 diagnostics (incl. the [B] vs [B,1] broadcast of the reference)        :552-558
-// dlogits = d loss / d logits for loss = w_focal * focal + w_bpr * interestBPR.
+//   huber       : huber_loss(sum hazard_masked [B], view_lengths [B,1]) -> [B,B] mean  :61-66, 539-540
+//   hazard      : compute_partial_likelihood_loss (rows with view_len == L skipped)   :273-286
+//   surviveCE   : BCE-with-logits fed exp(h_t) as the logit, masked batch mean        :68-97
+//   interestCE / interestKL : softmax(logits) vs softmax(gt != 0), optional mask      :99-161
+// The three survival-chain losses share one gradient path: c_t = d loss / d S_t, then
+//   d loss / d x_l = (1 - sigmoid(x_l)) * sum_{t >= l} c_t S_t     (S_t = exp(cumsum log sigmoid)).
+// dlogits = d loss / d logits for loss = sum over the losses switched on of weight * value.
 struct LossParams {
   const float* logits_in; int64_t* gt; int B, L;
   const float* ep; const float* bias_w; const float* bias_b;
   float inv_bsz, w_focal, w_bpr, bpr_scale;
   int use_focal, use_bpr, rewrite_gt;
   float* logits_out; float* scalars; float* dlogits; float* dbias_w; float* dbias_b;
+  int use_huber, use_hazard, use_sce, use_ice, use_ikl, mask_loss, ce_after_focal, kl_after_focal;
+  float w_huber, w_hazard, w_sce, w_ice, w_ikl;
 };
 
+// huber(e), delta 1 (models/decoder_leave_focal.py:61-66) and its derivative
+__device__ __forceinline__ float huber1(float e) { const float a = fabsf(e); return a < 1.f ? 0.5f * e * e : a - 0.5f; }
+__device__ __forceinline__ float huber1_grad(float e) { return fabsf(e) < 1.f ? e : (e > 0.f ? 1.f : -1.f); }
+
 __global__ void __launch_bounds__(1024) loss_kernel(const LossParams q) {
-  __shared__ double red[32][10];
-  __shared__ int n_bpr_rows_s;
+  constexpr int NACC = 15;
+  __shared__ double red[32][NACC];
+  __shared__ int n_bpr_rows_s, n_valid_total_s;
+  __shared__ int view_hist_s[66];                        // rows per view length (huber's [B,B] broadcast)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int B = q.B, L = q.L;
-  // ---- number of rows that take part in interestBPR (view_len < L), needed for its mean before any gradient
-  if (threadIdx.x == 0) n_bpr_rows_s = 0;
+  // ---- batch-wide counts that the means need before any gradient: rows in interestBPR (view_len < L), valid
+  //      positions (surviveCE), rows per view length (huber)
+  if (threadIdx.x == 0) { n_bpr_rows_s = 0; n_valid_total_s = 0; }
+  for (int i = threadIdx.x; i < 66; i += blockDim.x) view_hist_s[i] = 0;
   __syncthreads();
-  if (q.use_bpr) {
-    int cnt = 0;
+  if (q.use_bpr || q.use_sce || q.use_huber) {
+    int cnt = 0, nval = 0;
     for (int row = warp; row < B; row += nw) {
-      const bool v0 = lane < L && q.gt[(size_t)row * L + lane] == 1;
-      const bool v1 = lane + 32 < L && q.gt[(size_t)row * L + lane + 32] == 1;
-      const int n_view = __popc(__ballot_sync(0xffffffffu, v0)) + __popc(__ballot_sync(0xffffffffu, v1));
+      const long long g0 = lane < L ? q.gt[(size_t)row * L + lane] : -2;
+      const long long g1 = lane + 32 < L ? q.gt[(size_t)row * L + lane + 32] : -2;
+      const int n_view = __popc(__ballot_sync(0xffffffffu, g0 == 1)) + __popc(__ballot_sync(0xffffffffu, g1 == 1));
+      nval += __popc(__ballot_sync(0xffffffffu, g0 != -2)) + __popc(__ballot_sync(0xffffffffu, g1 != -2));
       cnt += n_view < L ? 1 : 0;
+      if (lane == 0 && q.use_huber) atomicAdd(&view_hist_s[n_view], 1);
     }
     if (lane == 0 && cnt) atomicAdd(&n_bpr_rows_s, cnt);
+    if (lane == 0 && nval) atomicAdd(&n_valid_total_s, nval);
   }
   __syncthreads();
   const int n_bpr = n_bpr_rows_s;
+  const float inv_nvalid_total = 1.0f / (float)n_valid_total_s;
   const float inv_nbpr = 1.0f / (float)n_bpr;            // 0 rows: inf -> loss = 0 * inf = NaN like torch's empty mean
-  double acc[10];
+  double acc[NACC];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) acc[i] = 0.0;
+  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
   for (int row = warp; row < B; row += nw) {
     float x[2], sig[2], logp[2];
     long long g[2];
@@ -536,10 +556,99 @@ __global__ void __launch_bounds__(1024) loss_kernel(const LossParams q) {
       if (n_view < 32) { if (lane == n_view) dl[0] += dpos; }
       else if (lane == n_view - 32) dl[1] += dpos;
     }
+    // ---- survival-chain losses: c[h] = d loss / d S_t at this lane's positions (zero where gt == -2)
+    float c[2] = {0.f, 0.f};
+    float huber_row = 0.f, hazard_row = 0.f, sce_row = 0.f;
+    if (q.use_huber) {                                   // mean_ij huber(H_j - v_i): row j against the histogram of v
+      const float H = warp_sum((valid[0] ? 1.f - surv[0] : 0.f) + (valid[1] ? 1.f - surv[1] : 0.f));
+      float hv = 0.f, hg = 0.f;
+      for (int v = lane; v <= L; v += 32) {
+        const float n = (float)view_hist_s[v];
+        hv += n * huber1(H - (float)v);
+        hg += n * huber1_grad(H - (float)v);
+      }
+      huber_row = warp_sum(hv);
+      const float gH = warp_sum(hg) * q.w_huber * q.bpr_scale / ((float)B * (float)B);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) if (valid[h]) c[h] -= gH;          // H = sum_valid (1 - S_t)
+    }
+    if (q.use_hazard && n_view < L) {                    // reference: `if observed_time==40: continue` (L = 40)
+      const float hm[2] = {valid[0] ? 1.f - surv[0] : 0.f, valid[1] ? 1.f - surv[1] : 0.f};
+      const float at = (n_view < 32) ? __shfl_sync(0xffffffffu, hm[0], n_view) : __shfl_sync(0xffffffffu, hm[1], n_view - 32);
+      const float risk = warp_sum((lane >= n_view ? hm[0] : 0.f) + (lane + 32 >= n_view ? hm[1] : 0.f));
+      hazard_row = -(logf(at + 1e-6f) - logf(risk + 1e-6f));
+      const float coef = q.w_hazard * q.inv_bsz;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int l = lane + 32 * h;
+        if (valid[h]) c[h] += coef * ((l == n_view ? 1.f / (at + 1e-6f) : 0.f) - (l >= n_view ? 1.f / (risk + 1e-6f) : 0.f));
+      }
+    }
+    if (q.use_sce) {
+      const float coef = q.w_sce * q.bpr_scale * inv_nvalid_total;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (!valid[h]) continue;
+        const float S = surv[h], y = (g[h] == 1) ? 1.f : 0.f;
+        sce_row += fmaxf(S, 0.f) - S * y + log1pf(expf(-fabsf(S)));
+        c[h] += coef * (1.0f / (1.0f + expf(-S)) - y);
+      }
+      sce_row = warp_sum(sce_row);
+    }
+    if (q.use_huber || q.use_hazard || q.use_sce) {      // suffix sums of c_t S_t over t >= l
+      float u0 = c[0] * surv[0], u1 = c[1] * surv[1];
+      if (!in[0]) u0 = 0.f;
+      if (!in[1]) u1 = 0.f;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float a0 = __shfl_down_sync(0xffffffffu, u0, o), a1 = __shfl_down_sync(0xffffffffu, u1, o);
+        if (lane + o < 32) { u0 += a0; u1 += a1; }
+      }
+      u0 += __shfl_sync(0xffffffffu, u1, 0);
+      dl[0] += (1.f - sig[0]) * u0;
+      dl[1] += (1.f - sig[1]) * u1;
+    }
+    // ---- interestCE / interestKL (:99-161): q = softmax(x) over all L positions, target = softmax(gt != 0)
+    float ice_row = 0.f, ikl_row = 0.f;
+    if (q.use_ice || q.use_ikl) {
+      float mx = warp_max(fmaxf(in[0] ? x[0] : -INFINITY, in[1] ? x[1] : -INFINITY));
+      float e[2] = {in[0] ? expf(x[0] - mx) : 0.f, in[1] ? expf(x[1] - mx) : 0.f};
+      const float se = warp_sum(e[0] + e[1]);
+      float qs[2], logq[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) { qs[h] = e[h] / se; logq[h] = in[h] ? logf(qs[h]) : 0.f; }   // log(softmax), as written
+      const float inv_nvalid_row = 1.0f / (float)n_valid;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        if (!(which == 0 ? q.use_ice : q.use_ikl)) continue;
+        const bool rewritten = which == 0 ? q.ce_after_focal : q.kl_after_focal;   // focal earlier in the list rewrote gt
+        bool nl[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) nl[h] = in[h] && (rewritten ? (g[h] > 0 || (g[h] < 0 && g[h] != -1)) : (g[h] != 0));
+        const int n1 = __popc(__ballot_sync(0xffffffffu, nl[0])) + __popc(__ballot_sync(0xffffffffu, nl[1]));
+        const float t_hi = n1 > 0 ? 1.f : 0.f;                                       // softmax subtracts the row max first
+        const float Z = (float)n1 * expf(1.f - t_hi) + (float)(L - n1) * expf(0.f - t_hi);
+        float w[2], W = 0.f, A = 0.f, T = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float t = in[h] ? expf((nl[h] ? 1.f : 0.f) - t_hi) / Z : 0.f;
+          w[h] = q.mask_loss ? (valid[h] ? t * inv_nvalid_row : 0.f) : t;
+          W += w[h];
+          A += w[h] * logq[h];
+          T += in[h] ? w[h] * logf(t) : 0.f;
+        }
+        W = warp_sum(W); A = warp_sum(A); T = warp_sum(T);
+        const float coef = (which == 0 ? q.w_ice : q.w_ikl) * q.inv_bsz;
+        if (which == 0) ice_row = -A; else ikl_row = T - A;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) if (in[h]) dl[h] += coef * (W * qs[h] - w[h]);
+      }
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h)
       if (in[h]) q.dlogits[(size_t)row * L + lane + 32 * h] = dl[h];
     if (lane == 0) {
+      acc[10] += huber_row; acc[11] += hazard_row; acc[12] += sce_row; acc[13] += ice_row; acc[14] += ikl_row;
       acc[0] += lsum;
       acc[1] += s_row; acc[2] += (double)s_row * s_row;
       acc[3] += n_view; acc[4] += (double)n_view * n_view;
@@ -550,11 +659,11 @@ __global__ void __launch_bounds__(1024) loss_kernel(const LossParams q) {
   }
   if (lane == 0)
 #pragma unroll
-    for (int i = 0; i < 10; ++i) red[warp][i] = acc[i];
+    for (int i = 0; i < NACC; ++i) red[warp][i] = acc[i];
   __syncthreads();
   if (threadIdx.x == 0) {
-    double t[10];
-    for (int i = 0; i < 10; ++i) {
+    double t[NACC];
+    for (int i = 0; i < NACC; ++i) {
       t[i] = 0.0;
       for (int w = 0; w < nw; ++w) t[i] += red[w][i];
     }
@@ -567,8 +676,17 @@ __global__ void __launch_bounds__(1024) loss_kernel(const LossParams q) {
     q.scalars[0] = (float)focal;
     q.scalars[1] = (float)mse;
     q.scalars[2] = (float)mse2;
-    q.scalars[3] = (float)((q.use_focal ? focal * (double)q.w_focal : 0.0) + (q.use_bpr ? bpr * (double)q.w_bpr : 0.0));
+    const double huber = q.use_huber ? t[10] * (double)q.bpr_scale / (b * b) : 0.0;
+    const double hazard = q.use_hazard ? t[11] * (double)q.inv_bsz : 0.0;
+    const double sce = q.use_sce ? t[12] * (double)q.bpr_scale / (double)n_valid_total_s : 0.0;
+    const double ice = q.use_ice ? t[13] * (double)q.inv_bsz : 0.0;
+    const double ikl = q.use_ikl ? t[14] * (double)q.inv_bsz : 0.0;
+    q.scalars[3] = (float)((q.use_focal ? focal * (double)q.w_focal : 0.0) + (q.use_bpr ? bpr * (double)q.w_bpr : 0.0) +
+                           huber * (double)q.w_huber + hazard * (double)q.w_hazard + sce * (double)q.w_sce +
+                           ice * (double)q.w_ice + ikl * (double)q.w_ikl);
     q.scalars[4] = (float)bpr;
+    q.scalars[5] = (float)huber; q.scalars[6] = (float)hazard; q.scalars[7] = (float)sce;
+    q.scalars[8] = (float)ice; q.scalars[9] = (float)ikl;
   }
   // ---- learnable position bias gradients: d bias_bias[l] = sum_b dlogits[b,l], d bias_weight[l] = (l+1) * that
   if (q.dbias_w != nullptr || q.dbias_b != nullptr) {
@@ -816,6 +934,9 @@ extern "C" int mmi_loss_fwd_bwd(const mmi_loss_args* a, mmi_stream_t stream) {
   q.inv_bsz = a->inv_bsz; q.w_focal = a->w_focal; q.w_bpr = a->w_bpr; q.bpr_scale = a->bpr_scale;
   q.use_focal = a->use_focal; q.use_bpr = a->use_bpr; q.rewrite_gt = a->rewrite_gt;
   q.logits_out = a->logits_out; q.scalars = a->scalars; q.dlogits = a->dlogits; q.dbias_w = a->dbias_weight; q.dbias_b = a->dbias_bias;
+  q.use_huber = a->use_huber; q.use_hazard = a->use_hazard; q.use_sce = a->use_surviveCE; q.use_ice = a->use_interestCE;
+  q.use_ikl = a->use_interestKL; q.mask_loss = a->mask_loss; q.ce_after_focal = a->ce_after_focal; q.kl_after_focal = a->kl_after_focal;
+  q.w_huber = a->w_huber; q.w_hazard = a->w_hazard; q.w_sce = a->w_surviveCE; q.w_ice = a->w_interestCE; q.w_ikl = a->w_interestKL;
   const int threads = a->B >= 32 ? 1024 : 32 * a->B;
   loss_kernel<<<1, threads, 0, st>>>(q);
   MMI_CHECK_LAUNCH();

@@ -100,7 +100,7 @@ class Engine:
         n_red = max(_lib.load().mmi_layernorm_bwd_workspace(cfg.d_model), _lib.load().mmi_head_bwd_workspace(cfg.d_model),
                     4 * cfg.d_model * max(cfg.max_usr_len, cfg.max_vid_len), 1 << 20)
         self.red_ws = torch.empty(int(n_red), device=device, dtype=torch.float32)
-        self.scalars = torch.zeros(8, device=device, dtype=torch.float32)
+        self.scalars = torch.zeros(16, device=device, dtype=torch.float32)
 
     # ------------------------------------------------------------------ parameter layout
     def _layout(self):
@@ -453,8 +453,9 @@ class Engine:
     def loss(self, logits, gt, exposure_prob, inv_bsz, loss_cfg=None, bpr_scale=1.0, need_grad=True):
         """Fused loss (focal and / or interestBPR) + learnable position bias + diagnostics + dlogits
         (models/decoder_leave_focal.py:490-572).  `gt` is rewritten in place like the reference (:534-535) when
-        focal is on.  Returns (scalars [focal, mse, mse2, loss, interestBPR, ...], logits incl. bias): device
-        tensors, no sync.  loss_cfg: dict(use_focal, w_focal, use_bpr, w_bpr); None = focal with weight 1."""
+        focal is on.  Returns (scalars [focal, mse, mse2, loss, interestBPR, huber, hazard, surviveCE, interestCE,
+        interestKL, ...], logits incl. bias): device tensors, no sync.  loss_cfg: dict(use_focal, w_focal, use_bpr, w_bpr
+        [, others={name: weight}, mask_loss, ce_after_focal, kl_after_focal]); None = focal with weight 1."""
         B, L = logits.shape
         if gt.dtype != torch.int64 or not gt.is_contiguous() or not gt.is_cuda:
             raise ValueError("gt must be a contiguous CUDA int64 tensor (it is rewritten in place, like the reference)")
@@ -470,6 +471,8 @@ class Engine:
             self.bind_grads()
         ops.loss_fwd_bwd(logits, gt, ep, inv_bsz=inv_bsz, scalars=self.scalars, dlogits=dlogits, use_focal=cfg["use_focal"],
                          w_focal=cfg["w_focal"], use_bpr=cfg["use_bpr"], w_bpr=cfg["w_bpr"], bpr_scale=bpr_scale, rewrite_gt=True,
+                         others=cfg.get("others"), mask_loss=cfg.get("mask_loss", 0), ce_after_focal=cfg.get("ce_after_focal", False),
+                         kl_after_focal=cfg.get("kl_after_focal", False),
                          bias_weight=self.w("bias_weight") if has_bias else None, bias_bias=self.w("bias_bias") if has_bias else None,
                          logits_out=logits_out, dbias_weight=self._pending_bias_grad(0) if has_bias and need_grad else None,
                          dbias_bias=self._pending_bias_grad(1) if has_bias and need_grad else None)

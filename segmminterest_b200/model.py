@@ -19,6 +19,8 @@ from . import _lib
 from .engine import Engine, EngineConfig
 
 PHOTO_MAX = 40
+# loss name -> slot of the fused loss kernel's scalar vector (include/mmi_b200.h, mmi_loss_fwd_bwd)
+LOSS_SLOT = {"focal": 0, "interestBPR": 4, "huber": 5, "hazard": 6, "surviveCE": 7, "interestCE": 8, "interestKL": 9}
 
 
 def _init_bert(module):
@@ -196,10 +198,9 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
         if head is not None:
             raise NotImplementedError("head must be None (main...SegMM.py:106,129)")
         it = getattr(model_cfg, "input_type", {"user": "image", "photo": "image"})
-        for lt in model_cfg.loss_type_list:
-            if lt not in ("focal", "interestBPR"):
-                raise NotImplementedError(f"loss_type {lt!r}: 'focal' (the BCE family the path names) and 'interestBPR' "
-                                          "(the reference default) are built")
+        for lt in model_cfg.loss_type_list:     # names the reference's compute_loss does not know are silently skipped there
+            if lt not in LOSS_SLOT:             # (and then KeyError in the weighted sum, :561-566); fail early instead
+                raise ValueError(f"unknown loss_type {lt!r}; the reference knows {sorted(LOSS_SLOT)}")
         self.backbone1 = backbone1
         self.backbone2 = backbone2
         self.model_cfg = model_cfg
@@ -245,8 +246,16 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
     def loss_cfg(self):
         lw = self.model_cfg.loss_weight
         names = list(self.model_cfg.loss_type_list)
-        return dict(use_focal="focal" in names, w_focal=float(lw.get("focal", 1.0)) if "focal" in names else 0.0,
-                    use_bpr="interestBPR" in names, w_bpr=float(lw.get("interestBPR", 1.0)) if "interestBPR" in names else 0.0)
+        # like the reference (:561-566) a missing weight is a KeyError; huber is weighted by loss_weight['mse']
+        others = {n: float(lw["mse" if n == "huber" else n]) for n in names if n not in ("focal", "interestBPR")}
+
+        def after_focal(n):
+            return n in names and "focal" in names and names.index("focal") < names.index(n)
+
+        return dict(use_focal="focal" in names, w_focal=float(lw["focal"]) if "focal" in names else 0.0,
+                    use_bpr="interestBPR" in names, w_bpr=float(lw["interestBPR"]) if "interestBPR" in names else 0.0,
+                    others=others, mask_loss=int(getattr(self.model_cfg, "mask_loss", 0)),
+                    ce_after_focal=after_focal("interestCE"), kl_after_focal=after_focal("interestKL"))
 
     def forward(self, usr_image, usr_id, usr_mask, vid_image, vid_id, vid_mask, gt=None, mode="train", **kwargs):
         eng = self.engine()
@@ -267,11 +276,7 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
         loss = scal[3]
         if torch.is_grad_enabled():
             loss = _EngineStep.apply(eng.anchor, loss, eng)
-        out = {}
-        if cfg["use_focal"]:
-            out["focal"] = scal[0].clone()
-        if cfg["use_bpr"]:
-            out["interestBPR"] = scal[4].clone()
+        out = {name: scal[LOSS_SLOT[name]].clone() for name in self.model_cfg.loss_type_list}
         out.update({"mse": scal[1].clone(), "mse2": scal[2].clone(), "loss": loss, "logits": lb.clone(), "gt": gt})
         return out
 

@@ -198,9 +198,12 @@ def focal_loss(logits, gt, exposure_prob, inv_bsz, weight, rewrite_gt, scalars, 
 
 def loss_fwd_bwd(logits, gt, exposure_prob, *, inv_bsz, scalars, dlogits, use_focal=True, w_focal=1.0, use_bpr=False, w_bpr=1.0,
                  bpr_scale=1.0, rewrite_gt=True, bias_weight=None, bias_bias=None, logits_out=None, dbias_weight=None,
-                 dbias_bias=None):
-    """Fused loss (focal and / or interestBPR) + learnable position bias + diagnostics + dlogits."""
+                 dbias_bias=None, others=None, mask_loss=0, ce_after_focal=False, kl_after_focal=False):
+    """Fused loss (any mix of focal, interestBPR and -- `others` = {name: weight} -- huber, hazard, surviveCE, interestCE,
+    interestKL) + learnable position bias + diagnostics + dlogits.  scalars: fp32[16] (layout in include/mmi_b200.h)."""
     B, L = logits.shape
+    if scalars.numel() < 16:
+        raise ValueError("loss scalars buffer must hold 16 floats")
     assert gt.dtype == torch.int64 and gt.is_contiguous() and logits.is_contiguous() and logits.dtype == torch.float32
     a = _lib.LossArgs()
     a.logits, a.gt, a.B, a.L = logits.data_ptr(), gt.data_ptr(), B, L
@@ -210,6 +213,12 @@ def loss_fwd_bwd(logits, gt, exposure_prob, *, inv_bsz, scalars, dlogits, use_fo
     a.use_focal, a.use_bpr, a.rewrite_gt = int(use_focal), int(use_bpr), int(rewrite_gt)
     a.logits_out, a.scalars, a.dlogits = _ptr(logits_out), scalars.data_ptr(), dlogits.data_ptr()
     a.dbias_weight, a.dbias_bias = _ptr(dbias_weight), _ptr(dbias_bias)
+    for name, wt in (others or {}).items():
+        if name not in ("huber", "hazard", "surviveCE", "interestCE", "interestKL"):
+            raise ValueError(f"unknown loss {name!r}")
+        setattr(a, "use_" + name, 1)
+        setattr(a, "w_" + name, float(wt))
+    a.mask_loss, a.ce_after_focal, a.kl_after_focal = int(bool(mask_loss)), int(bool(ce_after_focal)), int(bool(kl_after_focal))
     with TIMER.region("loss"):
         rc = _lib.load().mmi_loss_fwd_bwd(C.byref(a), _stream())
     _lib.check(rc, "mmi_loss_fwd_bwd")

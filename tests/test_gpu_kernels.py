@@ -265,7 +265,7 @@ def test_focal_loss_matches_reference_golden(dev):
     gt = torch.from_numpy(z["gt_in"]).to(dev)
     B = logits.shape[0]
     ep = torch.from_numpy(z["exposure_prob"]).float().to(dev)
-    scal, dl = torch.zeros(8, device=dev), torch.empty_like(logits)
+    scal, dl = torch.zeros(16, device=dev), torch.empty_like(logits)
     ops.focal_loss(logits, gt, ep, 1.0 / B, 1.0, True, scal, dl)
     s = scal.cpu().numpy()
     assert abs(s[0] - float(z["focal"])) < 2e-6 * abs(float(z["focal"]))
@@ -286,7 +286,7 @@ def test_interest_bpr_and_position_bias_match_reference_golden(dev):
     ep = torch.from_numpy(z["exposure_prob"].astype(np.float32)).to(dev)
     for use_focal, use_bpr in ((False, True), (True, True)):
         gt = torch.from_numpy(z["gt_in"].copy()).to(dev)
-        scal, dl = torch.zeros(8, device=dev), torch.empty_like(logits)
+        scal, dl = torch.zeros(16, device=dev), torch.empty_like(logits)
         ops.loss_fwd_bwd(logits, gt, ep, inv_bsz=1.0 / B, scalars=scal, dlogits=dl, use_focal=use_focal, w_focal=1.0, use_bpr=use_bpr,
                          w_bpr=1.0, rewrite_gt=True)
         s = scal.cpu().numpy()
@@ -302,7 +302,7 @@ def test_interest_bpr_and_position_bias_match_reference_golden(dev):
     torch.manual_seed(11)
     bw, bb = (1 + 0.1 * torch.randn(L)).to(dev), (1 + 0.1 * torch.randn(L)).to(dev)
     gt = torch.from_numpy(z["gt_in"].copy()).to(dev)
-    scal, dl, lo = torch.zeros(8, device=dev), torch.empty_like(logits), torch.empty_like(logits)
+    scal, dl, lo = torch.zeros(16, device=dev), torch.empty_like(logits), torch.empty_like(logits)
     dbw, dbb = torch.full((L,), 3.0, device=dev), torch.full((L,), -1.0, device=dev)
     ops.loss_fwd_bwd(logits, gt, ep, inv_bsz=1.0 / B, scalars=scal, dlogits=dl, use_focal=True, w_focal=0.7, use_bpr=True, w_bpr=1.3,
                      rewrite_gt=True, bias_weight=bw, bias_bias=bb, logits_out=lo, dbias_weight=dbw, dbias_bias=dbb)
@@ -316,6 +316,42 @@ def test_interest_bpr_and_position_bias_match_reference_golden(dev):
     assert abs(scal[3].item() - out["loss"].item()) < 1e-5 * abs(out["loss"].item())
     assert _rel(dl, lr.grad) < 1e-5
     assert _rel(dbw - 3.0, bwr.grad) < 1e-4 and _rel(dbb + 1.0, bbr.grad) < 1e-4
+
+
+@pytest.mark.parametrize("i", range(10))
+def test_every_selectable_loss_matches_reference_golden(dev, i):
+    """huber / hazard / surviveCE / interestCE / interestKL alone and mixed with focal (whose in-place gt rewrite the
+    later losses see) and interestBPR: values, weighted total, d loss / d logits and the rewritten gt against the
+    fixture produced by the unmodified reference (models/decoder_leave_focal.py:528-566)."""
+    import json
+    from segmminterest_b200 import ops
+    from segmminterest_b200.model import LOSS_SLOT
+    z = np.load(os.path.join(GOLDEN, "loss_cases_all.npz"))
+    base = np.load(os.path.join(GOLDEN, "loss_cases.npz"))
+    tag, lst, mask_loss = json.loads(str(z["variants"]))[i]
+    wts = json.loads(str(z["weights"]))
+    logits = torch.from_numpy(z[f"{tag}/logits"]).to(dev)
+    gt = torch.from_numpy(base["gt_in"].copy()).to(dev)
+    B = logits.shape[0]
+    ep = torch.from_numpy(base["exposure_prob"].astype(np.float32)).to(dev)
+    scal, dl = torch.zeros(16, device=dev), torch.empty_like(logits)
+    others = {n: wts["mse" if n == "huber" else n] for n in lst if n not in ("focal", "interestBPR")}
+
+    def after_focal(n):
+        return n in lst and "focal" in lst and lst.index("focal") < lst.index(n)
+
+    ops.loss_fwd_bwd(logits, gt, ep, inv_bsz=1.0 / B, scalars=scal, dlogits=dl, use_focal="focal" in lst, w_focal=wts["focal"],
+                     use_bpr="interestBPR" in lst, w_bpr=wts["interestBPR"], rewrite_gt=True, others=others, mask_loss=mask_loss,
+                     ce_after_focal=after_focal("interestCE"), kl_after_focal=after_focal("interestKL"))
+    s = scal.cpu().numpy()
+    for n in lst:
+        want = float(z[f"{tag}/{n}"])
+        assert abs(s[LOSS_SLOT[n]] - want) < 2e-5 * abs(want), (tag, n, s[LOSS_SLOT[n]], want)
+    for n, slot in (("mse", 1), ("mse2", 2), ("loss", 3)):
+        want = float(z[f"{tag}/{n}"])
+        assert abs(s[slot] - want) < 2e-5 * abs(want), (tag, n, s[slot], want)
+    assert np.array_equal(gt.cpu().numpy(), z[f"{tag}/gt_out"])
+    assert _rel(dl, torch.from_numpy(z[f"{tag}/grad"])) < 2e-5, tag
 
 
 # ----------------------------------------------------------------------------- clip + AdamW

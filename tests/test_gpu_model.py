@@ -198,6 +198,42 @@ def test_default_loss_and_learnable_bias_vs_oracle(precision):
     assert _rel(inf["logits"].cpu().numpy(), ref["logits"].detach().numpy()) < tol
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_all_selectable_losses_through_the_model_vs_oracle(precision):
+    """`--loss_type surviveCE,hazard,huber,interestCE,focal,interestKL,interestBPR --mask_loss 1` through the
+    drop-in model: every entry of the output dict, the logits and every parameter gradient against the oracle (which is
+    pinned to the unmodified reference by tests/golden/loss_cases_all.npz)."""
+    from oracle import mmi_oracle
+    from segmminterest_b200 import synth
+    from segmminterest_b200.model import build_model
+    dev = torch.device("cuda:0")
+    names = ["surviveCE", "hazard", "huber", "interestCE", "focal", "interestKL", "interestBPR"]
+    lw = {"focal": 0.5, "mse": 0.05, "hazard": 0.7, "surviveCE": 1.2, "interestBPR": 1.0, "interestCE": 0.9, "interestKL": 1.1}
+    args = make_args(d_model=128, nhead=4, num_layers_enc=3, loss_type_list=list(names), loss_weight=dict(lw), mask_loss=1,
+                     mmi_precision=precision)
+    torch.manual_seed(4)
+    model = build_model(args, din=64, max_usr_len=24).cuda().eval()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    rng = np.random.default_rng(6)
+    usr, um, vid, vm, gt = synth.make_dense_batch(rng, 16, 24, 64)
+    out = _run(model, usr, um, vid, vm, gt, dev)
+    assert set(out) == set(names) | {"mse", "mse2", "loss", "logits", "gt"}
+    out["loss"].backward()
+    live = mmi_oracle.live_param_names(list(sd.keys()), 3)
+    osd = {k: v.requires_grad_(k in live) for k, v in sd.items()}
+    ref = mmi_oracle.forward(osd, torch.from_numpy(usr), torch.from_numpy(um), torch.from_numpy(vid), torch.from_numpy(vm),
+                             torch.from_numpy(gt), nhead=4, num_layers=3, loss_type_list=tuple(names), loss_weight=lw, mask_loss=1)
+    ref["loss"].backward()
+    tol = FP32_TOL if precision == "fp32" else BF16_TOL
+    assert _rel(out["logits"].cpu().numpy(), ref["logits"].detach().numpy()) < tol
+    for n in names + ["loss"]:
+        assert abs(out[n].item() - ref[n].item()) < tol * abs(ref[n].item()) + 2e-6, n
+    assert np.array_equal(out["gt"].cpu().numpy(), ref["gt"].numpy())
+    for k, p in model.named_parameters():
+        if k in live:
+            assert _rel(p.grad.cpu().numpy(), osd[k].grad.numpy()) < 3 * tol, k
+
+
 @pytest.mark.parametrize("name", ["model_both_small", "model_id_small"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_general_config_vs_reference_golden(name, precision):

@@ -78,8 +78,15 @@ def test_cpu_forward_fails_loudly():
 
 def test_unsupported_configs_raise():
     from segmminterest_b200.model import SegFormerX, build_model
-    with pytest.raises(NotImplementedError):
-        build_model(make_args(loss_type_list=["surviveCE"]), din=16, max_usr_len=4)
+    with pytest.raises(ValueError):              # every loss the reference knows is built; anything else is a typo
+        build_model(make_args(loss_type_list=["surviveCE", "harzard"]), din=16, max_usr_len=4)
+    lw = {"focal": 1.0, "mse": 1.0, "hazard": 1.0, "surviveCE": 1.0, "interestBPR": 1.0, "interestCE": 1.0, "interestKL": 1.0}
+    m = build_model(make_args(loss_type_list=["surviveCE", "hazard", "huber", "interestCE", "interestKL"], loss_weight=lw), din=16,
+                    max_usr_len=4)
+    cfg = m.loss_cfg()
+    assert cfg["others"] == {"surviveCE": 1.0, "hazard": 1.0, "huber": 1.0, "interestCE": 1.0, "interestKL": 1.0}
+    assert not cfg["ce_after_focal"] and not cfg["use_focal"]
+    assert build_model(make_args(loss_type_list=["focal", "interestKL"], loss_weight=lw), din=16, max_usr_len=4).loss_cfg()["kl_after_focal"]
     m = build_model(make_args(loss_type_list=["interestBPR"], learnable_bias=1), din=16, max_usr_len=4)   # 8f-1: built
     assert tuple(m.bias_weight.shape) == (1, 40) and tuple(m.bias_bias.shape) == (1, 40)
     with pytest.raises(NotImplementedError):

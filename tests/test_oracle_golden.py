@@ -129,6 +129,28 @@ def test_loss_cases_match_reference():
     assert _rel(gb.numpy(), z["grad_bpr"]) < 1e-5
 
 
+def _loss_variants():
+    z = _load("loss_cases_all")
+    return z, json.loads(str(z["variants"])), json.loads(str(z["weights"]))
+
+
+@pytest.mark.parametrize("i", range(10))
+def test_every_selectable_loss_matches_reference(i):
+    """huber / hazard / surviveCE / interestCE / interestKL (models/decoder_leave_focal.py:528-551), alone and mixed
+    with focal (whose in-place gt rewrite later losses see) and interestBPR, against the unmodified reference."""
+    z, variants, weights = _loss_variants()
+    base = _load("loss_cases")
+    tag, lst, mask_loss = variants[i]
+    logits = torch.from_numpy(z[f"{tag}/logits"]).requires_grad_(True)
+    out = mmi_oracle.compute_loss(logits, torch.from_numpy(base["gt_in"]), list(base["exposure_prob"]), tuple(lst), weights,
+                                  mask_loss=mask_loss)
+    for k in lst + ["mse", "mse2", "loss"]:
+        assert abs(out[k].item() - float(z[f"{tag}/{k}"])) <= 2e-5 * abs(float(z[f"{tag}/{k}"])), (tag, k)
+    assert np.array_equal(out["gt"].numpy(), z[f"{tag}/gt_out"])
+    (g,) = torch.autograd.grad(out["loss"], logits)
+    assert _rel(g.numpy(), z[f"{tag}/grad"]) < 1e-5, tag
+
+
 def test_gather_oracle_matches_reference_dataloader():
     z = _load("gather_small")
     table = z["table"]

@@ -195,7 +195,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
   const int rows_valid = min(QT, p.Lq - q0);
   const int nact = (rows_valid + 31) >> 5;                  // softmax warps with at least one real query
 
-  if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
+  auto load_kv = [&](int j) {                            // one elected lane: K, V of tile j into ring stage j % FWD_STAGES
+    const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j % FWD_STAGES;
+    mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
+    uint8_t* dst = sKV + st * 2 * TILE32;
+    const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * NT;
+    tma_load_2d(blk ? &tmKb : &tmKa, &bars->kv_full[st], dst, h * DH, row);
+    tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[st], dst + TILE32, h * DH, row);
+  };
+  // The thread that initialises the barriers also launches the first loads (Q and the whole K/V ring) right away:
+  // their latency overlaps the mask reads and the TMEM allocation below instead of following them.
+  if (warp == 0 && elect_one()) {
+    init_bars(bars, 32 * nact);
+    mbar_expect_tx(&bars->once, (p.nblk > 1 ? 2 : 1) * TILE128);
+    tma_load_2d(&tmQa, &bars->once, sQ, h * DH, b * p.Lq + q0);
+    if (p.nblk > 1) tma_load_2d(&tmQb, &bars->once, sQ + TILE128, h * DH, b * p.Lq + q0);
+    for (int j = 0; j < min(T, FWD_STAGES); ++j) load_kv(j);
+  }
   build_key_bits(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
   if (warp == 4) TRACE(4090);
   const uint32_t tmem = tmem_setup(bars, warp, 128);
@@ -204,22 +220,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
 
   if (warp == 0) {
     // warp-uniform producer loop: all lanes wait for the free stage, one elected lane issues the TMA
-    if (elect_one()) {
-      mbar_expect_tx(&bars->once, (p.nblk > 1 ? 2 : 1) * TILE128);
-      tma_load_2d(&tmQa, &bars->once, sQ, h * DH, b * p.Lq + q0);
-      if (p.nblk > 1) tma_load_2d(&tmQb, &bars->once, sQ + TILE128, h * DH, b * p.Lq + q0);
-    }
-    __syncwarp();
-    for (int j = 0; j < T; ++j) {
-      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j % FWD_STAGES;
-      mbar_wait_bg(&bars->kv_empty[st], ((j / FWD_STAGES) & 1) ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
-        uint8_t* dst = sKV + st * 2 * TILE32;
-        const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * NT;
-        tma_load_2d(blk ? &tmKb : &tmKa, &bars->kv_full[st], dst, h * DH, row);
-        tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[st], dst + TILE32, h * DH, row);
-      }
+    for (int j = FWD_STAGES; j < T; ++j) {
+      mbar_wait_bg(&bars->kv_empty[j % FWD_STAGES], ((j / FWD_STAGES) & 1) ^ 1);
+      if (elect_one()) load_kv(j);
       __syncwarp();
     }
   } else if (warp == 1) {
@@ -394,29 +397,30 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
   const int rows_valid = min(QT, p.Lq - q0);
   const int nact = (rows_valid + 31) >> 5;
 
-  if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
+  auto load_kv = [&](int j) {                            // one elected lane: K, V of tile j into ring stage j % BWD_STAGES
+    const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j % BWD_STAGES;
+    mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
+    uint8_t* dst = sKV + st * 2 * TILE32;
+    const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * NT;
+    tma_load_2d(blk ? &tmKb : &tmKa, &bars->kv_full[st], dst, h * DH, row);
+    tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[st], dst + TILE32, h * DH, row);
+  };
+  if (warp == 0 && elect_one()) {                        // first loads leave before the mask reads / TMEM allocation
+    init_bars(bars, 32 * nact);
+    mbar_expect_tx(&bars->once, (p.nblk > 1 ? 3 : 2) * TILE128);
+    tma_load_2d(&tmQa, &bars->once, sQ, h * DH, b * p.Lq + q0);
+    if (p.nblk > 1) tma_load_2d(&tmQb, &bars->once, sQ + TILE128, h * DH, b * p.Lq + q0);
+    tma_load_2d(&tmdO, &bars->once, sdO, h * DH, b * p.Lq + q0);
+    for (int j = 0; j < min(T, BWD_STAGES); ++j) load_kv(j);
+  }
   build_key_bits(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
   const uint32_t tmem = tmem_setup(bars, warp, 128);
   const uint32_t tdP = tmem + NT, tdQ = tmem + 2 * NT;
 
   if (warp == 0) {
-    if (elect_one()) {
-      mbar_expect_tx(&bars->once, (p.nblk > 1 ? 3 : 2) * TILE128);
-      tma_load_2d(&tmQa, &bars->once, sQ, h * DH, b * p.Lq + q0);
-      if (p.nblk > 1) tma_load_2d(&tmQb, &bars->once, sQ + TILE128, h * DH, b * p.Lq + q0);
-      tma_load_2d(&tmdO, &bars->once, sdO, h * DH, b * p.Lq + q0);
-    }
-    __syncwarp();
-    for (int j = 0; j < T; ++j) {
-      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j % BWD_STAGES;
-      mbar_wait_bg(&bars->kv_empty[st], ((j / BWD_STAGES) & 1) ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
-        uint8_t* dst = sKV + st * 2 * TILE32;
-        const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * NT;
-        tma_load_2d(blk ? &tmKb : &tmKa, &bars->kv_full[st], dst, h * DH, row);
-        tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[st], dst + TILE32, h * DH, row);
-      }
+    for (int j = BWD_STAGES; j < T; ++j) {
+      mbar_wait_bg(&bars->kv_empty[j % BWD_STAGES], ((j / BWD_STAGES) & 1) ^ 1);
+      if (elect_one()) load_kv(j);
       __syncwarp();
     }
   } else if (warp == 1) {
@@ -569,17 +573,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const int rows_valid = min(QT, Lk - k0);
   const int nact = (rows_valid + 31) >> 5;
 
-  if (warp == 0 && lane == 0) init_bars(bars, 32 * nact);
+  if (warp == 0 && elect_one()) {                        // K, V of the CTA's rows leave before the TMEM allocation
+    init_bars(bars, 32 * nact);
+    mbar_expect_tx(&bars->once, 2 * TILE128);
+    tma_load_2d(&tmK, &bars->once, sK, h * DH, b * Lk + k0);
+    tma_load_2d(&tmV, &bars->once, sV, h * DH, b * Lk + k0);
+  }
   const uint32_t tmem = tmem_setup(bars, warp, 128);
   const uint32_t tdPT = tmem + NT, tdK = tmem + 2 * NT, tdV = tmem + 2 * NT + DH;
 
   if (warp == 0) {
-    if (elect_one()) {
-      mbar_expect_tx(&bars->once, 2 * TILE128);
-      tma_load_2d(&tmK, &bars->once, sK, h * DH, b * Lk + k0);
-      tma_load_2d(&tmV, &bars->once, sV, h * DH, b * Lk + k0);
-    }
-    __syncwarp();
     // per-query vectors (one query per lane) are fetched one tile AHEAD so that their global-load latency
     // overlaps the wait for a free stage instead of pacing the whole pipeline
     float lse_n = 0.f, delta_n = 0.f;

@@ -96,9 +96,11 @@ __device__ __forceinline__ void store2(__nv_bfloat16* p, float2 v) { *reinterpre
 // Columns n, n+1 of row m; consecutive lanes own consecutive column pairs of the SAME row, so
 // every global access below is a fully coalesced 128 B (bf16) / 256 B (fp32) row segment.
 // b0/b1: bias of the two columns (already zero when there is no bias or this is not the lead split).
+// add_row: row of the `add` operand that belongs to output row m (m for a residual, m mod add_mod for the position
+// table); the caller walks it incrementally -- a 64-bit modulo per element made the position-embedding GEMM 5x slower.
 template <typename TIN, typename TOUT>
 __device__ __forceinline__ void gemm_epilogue2(const GemmParams& p, int64_t m, int64_t n, float v0, float v1, float b0, float b1,
-                                               bool lead) {
+                                               bool lead, int64_t add_row) {
   v0 += b0; v1 += b1;
   if (p.preact != nullptr)
     store2(reinterpret_cast<TIN*>(p.preact) + m * p.ld_preact + n,
@@ -110,10 +112,9 @@ __device__ __forceinline__ void gemm_epilogue2(const GemmParams& p, int64_t m, i
     else { v0 *= gelu_grad_fast(z.x); v1 *= gelu_grad_fast(z.y); }
   }
   if (lead && p.add != nullptr) {
-    const int64_t r = (m < p.add_mod) ? m : m % p.add_mod;  // residual: add_mod == M (no division)
     float2 a;
-    if (p.add_dtype == MMI_F32) a = load2(reinterpret_cast<const float*>(p.add) + r * p.ld_add + n);
-    else a = load2(reinterpret_cast<const __nv_bfloat16*>(p.add) + r * p.ld_add + n);
+    if (p.add_dtype == MMI_F32) a = load2(reinterpret_cast<const float*>(p.add) + add_row * p.ld_add + n);
+    else a = load2(reinterpret_cast<const __nv_bfloat16*>(p.add) + add_row * p.ld_add + n);
     v0 += a.x; v1 += a.y;
   }
   TOUT* c = reinterpret_cast<TOUT*>(p.C) + m * p.ldc + n;

@@ -177,7 +177,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint8_t* ebuf = epi_base + ew * (2 * EBUF_BYTES);
     float* sbias = reinterpret_cast<float*>(epi_base + EPI_WARPS * 2 * EBUF_BYTES) + ew * 64;
     uint64_t* aux_bar = aux_bars + 2 * ew;
-    const bool aux_add = p.add != nullptr, aux_mul = p.mul_gelu_grad != nullptr;
+    // position-embedding add (fp32 table [add_mod, N], row = m mod add_mod): read straight from L1/L2 by the thread
+    // that owns the accumulator row -- the table is ~1 MB and shared by every batch item, so it never leaves cache
+    const bool pe_add = p.add != nullptr && p.add_mod < p.M;
+    const bool aux_add = p.add != nullptr && !pe_add, aux_mul = p.mul_gelu_grad != nullptr;
     const bool has_aux = aux_add || aux_mul;
     const bool second = p.preact != nullptr;           // host: never together with an aux operand
     const bool do_gelu = p.act == MMI_ACT_GELU;
@@ -234,6 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         uint8_t* row1 = tile1 + lane * 128;
         uint8_t* row2 = tile2 + lane * 128;
         if (has_aux) mbar_wait(&aux_bar[k], it & 1);
+        const float* pe_row = pe_add ? reinterpret_cast<const float*>(p.add) + ((int64_t)(m0 + lane) % p.add_mod) * p.ld_add + n0 : nullptr;
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
           const int phys = (v ^ (lane & 7)) << 4;
@@ -245,6 +249,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             x[j + 1] = __uint_as_float(acc[8 * v + j + 1]) + b.y;
             x[j + 2] = __uint_as_float(acc[8 * v + j + 2]) + b.z;
             x[j + 3] = __uint_as_float(acc[8 * v + j + 3]) + b.w;
+          }
+          if (pe_add) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(pe_row + 8 * v + j));
+              x[j] += a.x; x[j + 1] += a.y; x[j + 2] += a.z; x[j + 3] += a.w;
+            }
           }
           if (has_aux) {
             const uint4 a = *reinterpret_cast<const uint4*>(row1 + phys);
@@ -331,10 +342,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (n < p.N) {
           float b0 = 0.f, b1 = 0.f;
           if (ti.lead && p.bias != nullptr) { const float2 b = *reinterpret_cast<const float2*>(p.bias + n); b0 = b.x; b1 = b.y; }
+          int64_t add_row = (p.add != nullptr && m_base >= p.add_mod) ? m_base % p.add_mod : m_base;   // once per 32-row block
 #pragma unroll 4
           for (int rr = 0; rr < rows; ++rr) {
             const float2 x = *reinterpret_cast<const float2*>(stg + rr * STG_COLS + (((lane >> 1) ^ (rr & 7)) << 2) + ((lane & 1) << 1));
-            gemm_epilogue2<__nv_bfloat16, TOUT>(p, m_base + rr, n, x.x, x.y, b0, b1, ti.lead);
+            gemm_epilogue2<__nv_bfloat16, TOUT>(p, m_base + rr, n, x.x, x.y, b0, b1, ti.lead, add_row);
+            if (++add_row == p.add_mod) add_row = 0;
           }
         }
         __syncwarp();
@@ -429,11 +442,15 @@ int gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   memset(&em, 0, sizeof(em));
   // TMA epilogue: bf16 output tiles leave through shared memory; at most one tile-shaped bf16 side operand
   bool tma_epi = !mn && !f32out && !p.accumulate && split == 1 && tma_ok(p.C, p.ldc) && !(p.add && p.mul_gelu_grad);
-  if (tma_epi && p.add) tma_epi = p.add_dtype == MMI_BF16 && p.add_mod >= p.M && tma_ok(p.add, p.ld_add);
+  const bool pe_add = p.add != nullptr && p.add_mod < p.M;   // position table: fp32 rows read directly, no TMA box
+  if (tma_epi && p.add)
+    tma_epi = pe_add ? (p.add_dtype == MMI_F32 && p.add_mod > 0 && p.ld_add % 4 == 0 && (reinterpret_cast<uintptr_t>(p.add) & 15) == 0 && !p.mul_gelu_grad)
+                     : (p.add_dtype == MMI_BF16 && tma_ok(p.add, p.ld_add));
   if (tma_epi && p.mul_gelu_grad) tma_epi = tma_ok(p.mul_gelu_grad, p.ld_mul);
   if (tma_epi && p.preact) tma_epi = !p.add && !p.mul_gelu_grad && tma_ok(p.preact, p.ld_preact);
+  if (tma_epi && pe_add && p.N % 64 != 0) tma_epi = false;  // the direct table reads cover whole 64-column chunks
   if (tma_epi) {
-    const void* aux = p.add ? p.add : p.mul_gelu_grad;
+    const void* aux = pe_add ? nullptr : (p.add ? p.add : p.mul_gelu_grad);
     const int64_t ld_aux = p.add ? p.ld_add : p.ld_mul;
     if (!get_tensor_map(p.C, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldc, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &em.c)) return MMI_ECUDA;
     em.aux = em.c; em.c2 = em.c;

@@ -233,6 +233,22 @@ int mmi_clip_adamw(float* params, const float* grads, float* exp_avg, float* exp
                    float max_norm, int step, float* norm_out, void* bf16_out,
                    float* workspace, mmi_stream_t stream);
 
+/* ---- a-15 / 8f-4: validation metrics on the device -------------------------------------------------
+ * replaces models/my_evaluation.py: ProbAUC_batch (:73-80) and the per-row metrics of main_eval_batch (:264-357:
+ * LeaveMSE's predict_view_length :82-85, LeaveCTR / LeaveCTR_view :87-90, JaccardSim = IoU_Sim length_aware :37-57),
+ * fed with interests = sigmoid(logits) * exposure_prob (main...SegMM.py:402-403) and
+ * survival = exp(cumsum(log interests)) (my_evaluation.py:273-274).
+ * input_kind 0: `logits` are logits (interests formed here); 1: `logits` already holds the interests (exposure_prob
+ * unused, may be NULL) -- what main_eval_batch receives.
+ * logits fp32 [B,L], gt int64 [B,L] in {1,0,-1,-2} (or the {1,0,-2} focal leaves behind), L <= 64.
+ * rows fp32 [B,6]: pred_view_length, view_length, duration, LeaveCTR, LeaveCTR_view, JaccardSim.
+ * out fp32[4]: 0 ProbAUC over all positions with gt != -2 (label gt==-1 -> 0; exact Mann-Whitney statistic with
+ * ties 1/2 == sklearn.roc_auc_score; NaN when one class is missing, where sklearn raises), 1 n_pos, 2 n_neg.
+ * workspace: mmi_eval_metrics_workspace(B, L) bytes, 8-byte aligned.                                            */
+int64_t mmi_eval_metrics_workspace(int B, int L);
+int mmi_eval_metrics(const float* logits, const int64_t* gt, int B, int L, const float* exposure_prob,
+                     int input_kind, void* workspace, float* rows, float* out, mmi_stream_t stream);
+
 /* fp32 -> bf16 cast, optionally transposed: src [rows, cols] -> dst [cols, rows]      */
 int mmi_cast_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int transpose,
                   mmi_stream_t stream);

@@ -214,6 +214,26 @@ def run_loss_cases_all():
     np.savez_compressed(os.path.join(OUT, "loss_cases_all.npz"), **save)
 
 
+def run_eval_case():
+    """main_eval_batch of models/my_evaluation.py (:264-357) on the loss_cases inputs: ProbAUC of the batch and the
+    per-row JaccardSim / LeaveMSE / LeaveCTR / LeaveCTR_view lists, exactly as the driver's validation loop collects them
+    (main...SegMM.py:396-432)."""
+    ev = ref_shim.load_evaluation()
+    base = np.load(os.path.join(OUT, "loss_cases.npz"))
+    logits = torch.from_numpy(base["logits"])
+    gt = torch.from_numpy(base["gt_in"])
+    ep = torch.tensor(base["exposure_prob"], dtype=torch.float32)
+    interests = torch.sigmoid(logits) * ep                     # main...SegMM.py:402-403
+    results = {k: [] for k in ("ProbAUC", "JaccardSim", "LeaveMSE", "view_lengths", "duration_lengths", "LeaveCTR", "LeaveCTR_view")}
+    args = ref_shim.make_args(TOP_K_mask=0, TOP_K_permutation=1, draw_case=0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        results = ev.main_eval_batch(args, interests, gt, torch.zeros_like(gt), results, type="inference")
+    save = {k: np.asarray(v, dtype=np.float64) for k, v in results.items()}
+    save["interests"] = interests.numpy()
+    np.savez_compressed(os.path.join(OUT, "eval_cases.npz"), **save)
+    print("eval_cases", {k: (len(v), float(np.mean(v))) for k, v in results.items()})
+
+
 def run_gather_case():
     """FrameDatasetSeq_SegMM + DataCollator (utils/dataloader_SegMM.py:186-382) on a
     5-video fixture; stores the inputs in index form plus the dense outputs."""
@@ -275,6 +295,7 @@ def main():
     run_gather_case()
     run_loss_cases()
     run_loss_cases_all()
+    run_eval_case()
     run_model_case("model_small_dh32", d_model=64, nhead=2, nlayers=3, din=48, Lt=12, B=5, seed=11)
     run_model_case("model_small_dh16", d_model=64, nhead=4, nlayers=4, din=40, Lt=20, B=4, seed=12)
     run_model_case("model_full_b4", d_model=512, nhead=16, nlayers=6, din=1024, Lt=100, B=4, seed=13,
@@ -294,5 +315,7 @@ if __name__ == "__main__":
         run_general_cases()
     elif "--losses-only" in sys.argv:
         run_loss_cases_all()
+    elif "--eval-only" in sys.argv:
+        run_eval_case()
     else:
         main()

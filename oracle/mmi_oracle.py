@@ -390,3 +390,24 @@ def prob_auc_batch(logits, gt, exposure_prob=None):
     labels = gt[mask]
     labels = torch.where(labels == -1, torch.zeros_like(labels), labels)
     return float(roc_auc_score(labels.numpy().ravel(), survival[mask].numpy().ravel()))
+
+
+def eval_rows(interests, gt):
+    """Per-row validation metrics of main_eval_batch (models/my_evaluation.py:264-357, test_type 'new'):
+    columns pred_view_length (predict_view_length :82-85), view_length, duration, LeaveCTR, LeaveCTR_view (:87-90;
+    index view_length - 1 wraps for view_length 0), JaccardSim (IoU_Sim length_aware :37-57)."""
+    interests = torch.as_tensor(interests, dtype=torch.float32)
+    gt = torch.as_tensor(gt)
+    B, L = gt.shape
+    survival = torch.exp(torch.cumsum(torch.log(interests), dim=1))
+    mask = gt != -2
+    view = (gt == 1).sum(1)
+    dur = mask.sum(1)
+    pred = (survival * mask).sum(1)
+    at = (view - 1) % L
+    idx = torch.arange(B)
+    ctr, ctr_view = 1 - interests[idx, at], 1 - survival[idx, at]
+    watched = torch.arange(L)[None, :] < view[:, None]
+    inter = ((1 - (gt.to(torch.float32) - survival).abs()) * watched).sum(1)
+    jac = (inter + (dur - view).to(torch.float32)) / dur.to(torch.float32)
+    return torch.stack([pred, view.float(), dur.float(), ctr, ctr_view, jac], dim=1)

@@ -97,6 +97,22 @@ def load_dataloader():
         return _load_by_path(name, os.path.join(_MM, "utils", "dataloader_SegMM.py"))
 
 
+def load_evaluation():
+    """Loads the reference's models/my_evaluation.py by path; matplotlib (absent here, only used by draw_hotmap) is
+    replaced by empty stubs."""
+    name = "_ref_my_evaluation"
+    if name in sys.modules:
+        return sys.modules[name]
+    for m in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors"):
+        if m not in sys.modules:
+            try:
+                importlib.import_module(m)
+            except ImportError:
+                _stub(m, Normalize=object)
+    with contextlib.redirect_stdout(io.StringIO()):
+        return _load_by_path(name, os.path.join(_MM, "models", "my_evaluation.py"))
+
+
 def make_args(**over):
     """The argparse namespace fields the reference model reads."""
     a = dict(debug=0, input_type={"user": "image", "photo": "image"}, d_model=512, nhead=16,

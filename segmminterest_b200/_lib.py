@@ -77,6 +77,8 @@ _SIGS = {
     "mmi_rowdot_fwd": (C.c_int, [c_p, i64, c_p, i64, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p]),
     "mmi_rowdot_bwd": (C.c_int, [c_p, c_p, c_p, i64, c_p, i64, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p]),
     "mmi_clip_adamw_workspace": (i64, [i64]),
+    "mmi_eval_metrics_workspace": (i64, [C.c_int, C.c_int]),
+    "mmi_eval_metrics": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, C.c_int, c_p, c_p, c_p, c_p]),
     "mmi_clip_adamw": (C.c_int, [c_p, c_p, c_p, c_p, i64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int, c_p, c_p, c_p, c_p]),
     "mmi_cast_bf16": (C.c_int, [c_p, c_p, i64, i64, C.c_int, c_p]),

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmmi_b200.so")
-SOURCES = ["api.cu", "gather.cu", "gemm_simt.cu", "gemm_tc.cu", "tc_host.cu", "elementwise.cu", "attention_simt.cu", "attention_tc.cu", "idfusion.cu"]
+SOURCES = ["api.cu", "gather.cu", "gemm_simt.cu", "gemm_tc.cu", "tc_host.cu", "elementwise.cu", "attention_simt.cu", "attention_tc.cu", "idfusion.cu", "metrics.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false"]
 

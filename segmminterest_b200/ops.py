@@ -273,3 +273,18 @@ def cast_bf16(src, dst, rows, cols, transpose=False):
         rc = _lib.load().mmi_cast_bf16(src.data_ptr(), dst.data_ptr(), rows, cols, 1 if transpose else 0, _stream())
     _lib.check(rc, "mmi_cast_bf16")
     LaunchCounter.n += 1
+
+
+def eval_metrics(logits, gt, exposure_prob, rows, out, workspace, interests=False):
+    """Device validation metrics (mmi_eval_metrics): rows [B,6] = pred_view_length, view_length, duration, LeaveCTR,
+    LeaveCTR_view, JaccardSim; out[0] = ProbAUC of the batch."""
+    B, L = logits.shape
+    _need_cuda(logits, gt, exposure_prob, rows, out, workspace)
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and gt.dtype == torch.int64 and gt.is_contiguous()
+    assert rows.numel() >= B * 6 and out.numel() >= 4
+    assert workspace.numel() * workspace.element_size() >= _lib.load().mmi_eval_metrics_workspace(B, L)
+    with TIMER.region("eval_metrics"):
+        rc = _lib.load().mmi_eval_metrics(logits.data_ptr(), gt.data_ptr(), B, L, _ptr(exposure_prob), 1 if interests else 0,
+                                          workspace.data_ptr(), rows.data_ptr(), out.data_ptr(), _stream())
+    _lib.check(rc, "mmi_eval_metrics")
+    LaunchCounter.n += 3

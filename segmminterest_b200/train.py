@@ -52,22 +52,42 @@ class TrainStep:
         self.global_batch = global_batch
         self.loss_cfg = model.loss_cfg()
 
-    def step(self, usr_idx: torch.Tensor, vid_idx: torch.Tensor, gt: torch.Tensor, usr_id=None, vid_id=None):
+    def step(self, usr_idx: torch.Tensor, vid_idx: torch.Tensor, gt: torch.Tensor, usr_id=None, vid_id=None, micro_batch: int = 0):
         """One training step on device-resident int32 indices [B,Lt], [B,40] and int64 labels
         [B,40] (rewritten in place like the reference).  Returns the device scalars
-        [focal, mse, mse2, loss]; nothing is synchronised."""
+        [focal, mse, mse2, loss, ...]; nothing is synchronised.
+
+        micro_batch > 0 runs the batch in slices of that many interactions with gradient accumulation (the saved
+        activations of one slice are all that lives in HBM: config 3 / 4 histories do not fit otherwise); the gradient
+        all-reduce overlaps the backward of the LAST slice.  Exact for losses that are sums over interactions / B_global
+        (focal, hazard, interestCE/KL); losses whose mean runs over a data-dependent count (interestBPR, surviveCE) or
+        over pairs of rows (huber, the mse diagnostics) are evaluated per slice and averaged."""
         eng = self.engine
         B = usr_idx.shape[0]
-        usr, um = self.gather(usr_idx, "usr")
-        vid, vm = self.gather(vid_idx, "vid")
-        logits = eng.forward(usr, um, vid, vm, usr_id=usr_id, vid_id=vid_id)
         gb = self.global_batch or B * self.buckets.world
         eng.bind_grads()           # Parameters' .grad alias the flat gradient buffer
         eng.flat_grad.zero_()
-        # focal is a sum / B_global; interestBPR is a mean over this rank's rows, averaged over ranks (DDP semantics)
-        scal, _ = eng.loss(logits, gt, self.model.exposure_prob, 1.0 / gb, self.loss_cfg, bpr_scale=1.0 / self.buckets.world)
-        self.buckets.begin()
-        eng.backward(None, on_ready=self.buckets.ready)
+        mb = int(micro_batch) if micro_batch and micro_batch < B else B
+        n_slices = (B + mb - 1) // mb
+        total = None
+        for si, a in enumerate(range(0, B, mb)):
+            b = min(B, a + mb)
+            usr, um = self.gather(usr_idx[a:b], "usr")
+            vid, vm = self.gather(vid_idx[a:b], "vid")
+            logits = eng.forward(usr, um, vid, vm, usr_id=None if usr_id is None else usr_id[a:b],
+                                 vid_id=None if vid_id is None else vid_id[a:b])
+            # focal is a sum / B_global; interestBPR is a mean over this slice's rows, averaged over slices and ranks (DDP semantics)
+            scal, _ = eng.loss(logits, gt[a:b], self.model.exposure_prob, 1.0 / gb, self.loss_cfg,
+                               bpr_scale=1.0 / (self.buckets.world * n_slices))
+            last = si == n_slices - 1
+            if last:
+                self.buckets.begin()
+            eng.backward(None, on_ready=self.buckets.ready if last else None)
+            if n_slices > 1:
+                total = scal.clone() if total is None else total.add_(scal)
+        if n_slices > 1:
+            total[1:3].div_(n_slices)          # mse / mse2 diagnostics: mean of the per-slice values
+            scal = total
         self.buckets.finish()
         self.step_no += 1
         ops.clip_adamw(eng.flat, eng.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,

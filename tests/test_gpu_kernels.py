@@ -354,6 +354,41 @@ def test_every_selectable_loss_matches_reference_golden(dev, i):
     assert _rel(dl, torch.from_numpy(z[f"{tag}/grad"])) < 2e-5, tag
 
 
+# ----------------------------------------------------------------------------- validation metrics (a-15 / 8f-4)
+def test_eval_metrics_match_reference_golden_and_oracle(dev):
+    """mmi_eval_metrics: ProbAUC (exact Mann-Whitney == sklearn.roc_auc_score) and the per-row metrics against the lists
+    the unmodified reference's main_eval_batch collected, then the drop-in main_eval_batch protocol, then a larger
+    random batch (with exact ties) against the oracle."""
+    from oracle import mmi_oracle
+    from segmminterest_b200.evaluation import DeviceMetrics, main_eval_batch
+    from types import SimpleNamespace
+    z = np.load(os.path.join(GOLDEN, "eval_cases.npz"))
+    base = np.load(os.path.join(GOLDEN, "loss_cases.npz"))
+    logits = torch.from_numpy(base["logits"]).to(dev)
+    gt = torch.from_numpy(base["gt_in"]).to(dev)
+    rows, out = DeviceMetrics()(logits, gt, list(base["exposure_prob"]))
+    r = rows.cpu().numpy()
+    for name, col in (("LeaveMSE", 0), ("view_lengths", 1), ("duration_lengths", 2), ("LeaveCTR", 3), ("LeaveCTR_view", 4), ("JaccardSim", 5)):
+        assert np.allclose(r[:, col], z[name], rtol=2e-5, atol=2e-6, equal_nan=True), name
+    assert abs(out[0].item() - float(z["ProbAUC"][0])) < 1e-6
+    # the driver protocol: results_list keys select the metrics; same lists as the reference
+    res = {k: [] for k in ("ProbAUC", "JaccardSim", "LeaveMSE", "view_lengths", "duration_lengths", "LeaveCTR", "LeaveCTR_view")}
+    res = main_eval_batch(SimpleNamespace(TOP_K_mask=0, draw_case=0), torch.from_numpy(z["interests"]).to(dev), gt, None, res)
+    for k in res:
+        assert np.allclose(np.asarray(res[k]), z[k], rtol=2e-5, atol=2e-6, equal_nan=True), k
+    # larger batch, quantised logits => many exact ties
+    rng = np.random.default_rng(17)
+    from segmminterest_b200 import synth
+    B = 700
+    gt2 = synth.make_labels(rng, rng.integers(1, 41, size=B))
+    lg2 = (np.round(rng.standard_normal((B, 40)) * 4) / 4).astype(np.float32)
+    rows2, out2 = DeviceMetrics()(torch.from_numpy(lg2).to(dev), torch.from_numpy(gt2).to(dev), [1.0] * 40)
+    want = mmi_oracle.prob_auc_batch(lg2, gt2)
+    assert abs(out2[0].item() - want) < 2e-6, (out2[0].item(), want)
+    wrows = mmi_oracle.eval_rows(torch.sigmoid(torch.from_numpy(lg2)), torch.from_numpy(gt2)).numpy()
+    assert np.allclose(rows2.cpu().numpy(), wrows, rtol=3e-5, atol=3e-6, equal_nan=True)
+
+
 # ----------------------------------------------------------------------------- clip + AdamW
 def test_clip_adamw_matches_torch(dev):
     from segmminterest_b200 import _lib, ops

@@ -336,3 +336,58 @@ def test_bf16_training_auc_matches_fp32_oracle():
     print(f"per-segment skip AUC after {steps} steps: bf16 CUDA path {a:.4f}  fp32 oracle {r:.4f}")
     assert r > 0.6, "teacher signal not learned: the AUC comparison would be uninformative"
     assert abs(a - r) < 0.002
+
+
+def test_micro_batched_step_equals_full_batch_step():
+    """TrainStep.step(micro_batch=m): gradient accumulation over slices of the batch (what configs 3 / 4 need to fit their
+    saved activations) gives the same parameters after clip + AdamW as the full-batch step (focal: a sum over
+    interactions / B, so the split is exact up to fp32 summation order)."""
+    from segmminterest_b200 import synth
+    from segmminterest_b200.model import build_model
+    from segmminterest_b200.train import TrainStep
+    dev = torch.device("cuda:0")
+    din, Lt, B, n_rows = 64, 24, 16, 512
+    table = torch.from_numpy(synth.make_table(n_rows, din, seed=3)).to(dev)
+    ui, vi, gt = synth.make_teacher_batch(table.cpu().numpy(), B, Lt, 12, seed=77)
+    flats, losses = [], []
+    for mb in (0, 4):
+        torch.manual_seed(0)
+        model = build_model(make_args(d_model=128, nhead=4, num_layers_enc=3), din=din, max_usr_len=Lt).cuda().eval()
+        ts = TrainStep(model, table, global_batch=B)
+        for _ in range(2):
+            scal = ts.step(torch.from_numpy(ui).to(dev), torch.from_numpy(vi).to(dev), torch.from_numpy(gt.copy()).to(dev), micro_batch=mb)
+        flats.append(ts.engine.flat.detach().cpu().clone())
+        losses.append(float(scal[3].item()))
+    assert abs(losses[0] - losses[1]) < 1e-5 * abs(losses[0])
+    assert _rel(flats[1].numpy(), flats[0].numpy()) < 1e-5
+
+
+def test_inference_scorer_packs_the_reference_logit_dump():
+    """SURVEY 8f-3 (inference/save_logits_for_all_leave_SegMM.py:97-148): chunked forward-only scoring from row ids equals
+    the model's own mode="inference" call on the gathered features (bit-exact: same kernels), matches the oracle, and
+    `to_dict` rebuilds the reference's {"uid-pid-time_ms": [40 floats]} mapping."""
+    from oracle import gather_oracle, mmi_oracle
+    from segmminterest_b200 import InferenceScorer, synth
+    from segmminterest_b200.model import build_model
+    dev = torch.device("cuda:0")
+    din, Lt, n, n_rows = 64, 24, 13, 512
+    table = synth.make_table(n_rows, din, seed=5)
+    torch.manual_seed(1)
+    model = build_model(make_args(d_model=128, nhead=4, num_layers_enc=3, learnable_bias=1), din=din, max_usr_len=Lt).cuda().eval()
+    ui, vi, gt = synth.make_teacher_batch(table, n, Lt, 12, seed=78)
+    scorer = InferenceScorer(model, torch.from_numpy(table).to(dev), max_batch=5)
+    logits = scorer.score_host(torch.from_numpy(ui).pin_memory(), torch.from_numpy(vi).pin_memory())
+    assert tuple(logits.shape) == (n, 40) and logits.dtype == torch.float32 and not logits.is_cuda
+    u, um = gather_oracle.gather_dense(table, ui)
+    c, cm = gather_oracle.gather_dense(table, vi)
+    u, c = torch.from_numpy(gather_oracle.l1_normalise(u)), torch.from_numpy(gather_oracle.l1_normalise(c))
+    zeros = torch.zeros(n, dtype=torch.long, device=dev)
+    with torch.no_grad():
+        whole = model(usr_image=u.to(dev), usr_id=zeros, usr_mask=torch.from_numpy(um).to(dev), vid_image=c.to(dev), vid_id=zeros,
+                      vid_mask=torch.from_numpy(cm).to(dev), gt=None, mode="inference")["logits"].cpu()
+    assert _rel(logits.numpy(), whole.numpy()) < 1e-6
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref = mmi_oracle.forward(sd, u, torch.from_numpy(um), c, torch.from_numpy(cm), None, nhead=4, num_layers=3, mode="inference")
+    assert _rel(logits.numpy(), ref["logits"].detach().numpy()) < FP32_TOL
+    d = InferenceScorer.to_dict(logits, range(100, 100 + n), range(7, 7 + n), [5000 * i for i in range(n)])
+    assert list(d)[0] == "100-7-0" and len(d) == n and d["101-8-5000"] == logits[1].tolist()

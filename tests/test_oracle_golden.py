@@ -151,6 +151,17 @@ def test_every_selectable_loss_matches_reference(i):
     assert _rel(g.numpy(), z[f"{tag}/grad"]) < 1e-5, tag
 
 
+def test_eval_metrics_match_reference_main_eval_batch():
+    """oracle restatement of main_eval_batch's metrics vs the lists the unmodified reference collected"""
+    z = _load("eval_cases")
+    base = _load("loss_cases")
+    rows = mmi_oracle.eval_rows(torch.from_numpy(z["interests"]), torch.from_numpy(base["gt_in"])).numpy()
+    for name, col in (("LeaveMSE", 0), ("view_lengths", 1), ("duration_lengths", 2), ("LeaveCTR", 3), ("LeaveCTR_view", 4), ("JaccardSim", 5)):
+        assert np.allclose(rows[:, col], z[name], rtol=1e-5, atol=1e-6, equal_nan=True), name
+    auc = mmi_oracle.prob_auc_batch(base["logits"], base["gt_in"], base["exposure_prob"])
+    assert abs(auc - float(z["ProbAUC"][0])) < 1e-9
+
+
 def test_gather_oracle_matches_reference_dataloader():
     z = _load("gather_small")
     table = z["table"]

@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=list(synth.WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--micro-batch", type=int, default=0, help="gradient-accumulation slice (configs 3 / 4: saved activations of a slice must fit in HBM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     args = ap.parse_args()
@@ -225,8 +226,9 @@ def main():
             return float(t.item())
         return ms
 
+    mb = args.micro_batch
     for i in range(W):
-        ts.step(*devb[i % n_batches])
+        ts.step(*devb[i % n_batches], micro_batch=mb)
     barrier()
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------
@@ -238,7 +240,7 @@ def main():
     barrier()
     e0.record()
     for i in range(K):
-        scal = ts.step(*devb[i % n_batches])
+        scal = ts.step(*devb[i % n_batches], micro_batch=mb)
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -248,11 +250,11 @@ def main():
     value = K * B * world / (ms_total * 1e-3)
 
     # ---- timed region 2: end to end from pinned host buffers, loss read back every step -----------
-    ts.step_host(*host[0], staging)
+    ts.step_host(*host[0], staging, micro_batch=mb)
     barrier()
     e0.record()
     for i in range(K):
-        ts.step_host(*host[i % n_batches], staging)
+        ts.step_host(*host[i % n_batches], staging, micro_batch=mb)
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
@@ -265,7 +267,7 @@ def main():
     TIMER.reset()
     barrier()
     for i in range(K):
-        ts.step(*devb[i % n_batches])
+        ts.step(*devb[i % n_batches], micro_batch=mb)
     summ = TIMER.summary()
     TIMER.enabled = False
     TIMER.detail = False
@@ -321,7 +323,7 @@ def main():
     line = {"metric": "train_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": wl.name, "per_gpu_batch": B, "global_batch": B * world, "hist_len": Lt, "cand_pad": 40,
+            "config": {"workload": wl.name, "per_gpu_batch": B, "micro_batch": mb or B, "global_batch": B * world, "hist_len": Lt, "cand_pad": 40,
                        "cand_valid": wl.segs_per_video, "din": wl.din, "d_model": 512, "heads": 16, "layers": 6,
                        "table_rows": wl.n_rows, "parallelism": f"dp{world}", "optimizer": "AdamW lr1e-3 wd1e-4 clip10",
                        "dropout": "off (parity mode)", "l2": "activations/step >> 126 MB L2 (inputs larger than L2, no flush needed)"},

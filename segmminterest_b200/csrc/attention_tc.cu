@@ -72,6 +72,56 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2: two results per FMA-pipe issue slot) and a polynomial exp2.
+// Measured on B200 (tools/micro/pipe_rates.cu): MUFU.EX2 16 results/clk/SM, FFMA2 126 results/clk/SM.  With one ex2 per
+// score the softmax loops are MUFU-bound while the warps compute, so a fixed share of the scores of every tile takes
+// its exponential on the FMA / ALU pipes instead: round-to-nearest split x = n + f (magic-number add), 2^f by a
+// degree-3 minimax polynomial on [-1/2, 1/2] (relative error 7.5e-5, bf16 keeps 3.9e-3), 2^n added into the exponent.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 ex2_mufu2(float2 x) { return make_float2(ex2(x.x), ex2(x.y)); }
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  constexpr float kMagic = 12582912.0f;                        // 1.5 * 2^23: x + kMagic holds round(x) in its low mantissa bits
+  x.x = fmaxf(x.x, -126.0f); x.y = fmaxf(x.y, -126.0f);        // keep the biased exponent non-negative (2^-126 ~ 0)
+  const float2 t = add2(x, splat2(kMagic));
+  const float2 n = add2(t, splat2(-kMagic));
+  const float2 f = fma2(n, splat2(-1.0f), x);
+  float2 q = fma2(f, splat2(0.0551716685295105f), splat2(0.2426111251115799f));
+  q = fma2(q, f, splat2(0.6932609677314758f));
+  q = fma2(q, f, splat2(0.9999280571937561f));
+  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
+                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
+}
+// which score pairs of a 32-score tile take the polynomial: 6 of 16 (3 of every 8), spread so both pipes stay busy
+#ifndef MMI_POLY
+#define MMI_POLY 0   // measured (tools/attn_bench.py, c2 usr fwd): 0 -> 1.99 ms, 3 of 8 -> 2.02 ms, 4 of 8 -> 2.06 ms: the loops are
+#endif               // not MUFU-bound end to end (hand-off latency is), so the polynomial's extra issue slots cost more than they free
+__device__ __forceinline__ constexpr bool poly_pair(int pair) {
+  return MMI_POLY == 0 ? false
+       : MMI_POLY == 2 ? ((pair & 7) == 2 || (pair & 7) == 6)
+       : MMI_POLY == 3 ? ((pair & 7) == 2 || (pair & 7) == 5 || (pair & 7) == 7)
+       : MMI_POLY == 4 ? ((pair & 1) == 1)
+       : ((pair & 7) != 0 && (pair & 7) != 4 && (pair & 7) != 6);   // 5 of 8
+}
+
 // 32 bf16 = the whole row `row` of a [rows x 64 B] SWIZZLE_64B K-major tile (address bits [4,6) ^= bits [7,9))
 // row_addr = shared-space address of the row (tile + row * 64); swz = (row >> 1) & 3
 __device__ __forceinline__ void write_row_sw64(uint32_t row_addr, uint32_t swz, const uint32_t (&w)[16]) {
@@ -325,12 +375,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
       const float nb_t = base_t - m;                     // x - m = s * scale_t + nb_t
       uint32_t pk[16];
       if (warp_all_mq && wv == 0xffffffffu) {
+        float2 l2 = make_float2(l0, l1);
+        const float2 sc2 = splat2(scale_t), nb2 = splat2(nb_t);
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
-          const float e0 = ex2(fmaf(__uint_as_float(r[c]), scale_t, nb_t)), e1 = ex2(fmaf(__uint_as_float(r[c + 1]), scale_t, nb_t));
-          l0 += e0; l1 += e1;
-          pk[c >> 1] = pack_bf16x2(e0, e1);
+          const float2 x = fma2(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), sc2, nb2);
+          const float2 e = poly_pair(c >> 1) ? ex2_poly2(x) : ex2_mufu2(x);
+          l2 = add2(l2, e);
+          pk[c >> 1] = pack_bf16x2(e.x, e.y);
         }
+        l0 = l2.x; l1 = l2.y;
       } else {
         const float pm = ex2(p.fill_log2 - m);           // probability weight of a masked key
 #pragma unroll
@@ -499,10 +553,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
           mbar_arrive_a(s_free_a);
         }
         if (fast) {
+          const float2 sl2 = splat2(p.scale_log2), nl2 = splat2(nlse2), sc2 = splat2(p.scale), nd2 = splat2(nds);
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(rs[c]), p.scale_log2, nlse2)), p1 = ex2(fmaf(__uint_as_float(rs[c + 1]), p.scale_log2, nlse2));
-            pk[hf * 8 + (c >> 1)] = pack_bf16x2(p0 * fmaf(__uint_as_float(rp[c]), p.scale, nds), p1 * fmaf(__uint_as_float(rp[c + 1]), p.scale, nds));
+            const float2 x = fma2(make_float2(__uint_as_float(rs[c]), __uint_as_float(rs[c + 1])), sl2, nl2);
+            const float2 pr = poly_pair(c >> 1) ? ex2_poly2(x) : ex2_mufu2(x);
+            const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, nd2));
+            pk[hf * 8 + (c >> 1)] = pack_bf16x2(ds.x, ds.y);
           }
         } else {
 #pragma unroll
@@ -688,12 +745,16 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
           for (int c = 0; c < 16; c += 4) {
             const float4 nl = lds_f4(qva + (hf * 16 + c) * 4), nd = lds_f4(qva + (NT + hf * 16 + c) * 4);
-            const float p0 = ex2(fmaf(__uint_as_float(rs[c]), p.scale_log2, nl.x)), p1 = ex2(fmaf(__uint_as_float(rs[c + 1]), p.scale_log2, nl.y));
-            const float p2 = ex2(fmaf(__uint_as_float(rs[c + 2]), p.scale_log2, nl.z)), p3 = ex2(fmaf(__uint_as_float(rs[c + 3]), p.scale_log2, nl.w));
-            pp[hf * 8 + (c >> 1)] = pack_bf16x2(p0, p1);
-            pp[hf * 8 + (c >> 1) + 1] = pack_bf16x2(p2, p3);
-            pd[hf * 8 + (c >> 1)] = pack_bf16x2(p0 * fmaf(__uint_as_float(rp[c]), p.scale, nd.x), p1 * fmaf(__uint_as_float(rp[c + 1]), p.scale, nd.y));
-            pd[hf * 8 + (c >> 1) + 1] = pack_bf16x2(p2 * fmaf(__uint_as_float(rp[c + 2]), p.scale, nd.z), p3 * fmaf(__uint_as_float(rp[c + 3]), p.scale, nd.w));
+            const float2 sl2 = splat2(p.scale_log2), sc2 = splat2(p.scale);
+            const float2 xa = fma2(make_float2(__uint_as_float(rs[c]), __uint_as_float(rs[c + 1])), sl2, make_float2(nl.x, nl.y));
+            const float2 xb = fma2(make_float2(__uint_as_float(rs[c + 2]), __uint_as_float(rs[c + 3])), sl2, make_float2(nl.z, nl.w));
+            const float2 pa = poly_pair(c >> 1) ? ex2_poly2(xa) : ex2_mufu2(xa), pb = poly_pair((c >> 1) + 1) ? ex2_poly2(xb) : ex2_mufu2(xb);
+            const float2 da = mul2(pa, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, make_float2(nd.x, nd.y)));
+            const float2 db = mul2(pb, fma2(make_float2(__uint_as_float(rp[c + 2]), __uint_as_float(rp[c + 3])), sc2, make_float2(nd.z, nd.w)));
+            pp[hf * 8 + (c >> 1)] = pack_bf16x2(pa.x, pa.y);
+            pp[hf * 8 + (c >> 1) + 1] = pack_bf16x2(pb.x, pb.y);
+            pd[hf * 8 + (c >> 1)] = pack_bf16x2(da.x, da.y);
+            pd[hf * 8 + (c >> 1) + 1] = pack_bf16x2(db.x, db.y);
           }
         } else {
 #pragma unroll

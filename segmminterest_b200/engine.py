@@ -303,13 +303,14 @@ class Engine:
                          add=add, add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=self.use_tc)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, usr_image, usr_mask, vid_image, vid_mask, usr_id=None, vid_id=None):
+    def forward(self, usr_image, usr_mask, vid_image, vid_mask, usr_id=None, vid_id=None, refresh=True):
         """usr_image [B,Lt,Din] / vid_image [B,Lv,Din] already L1-normalised (the driver does it,
         main...SegMM.py:272-273; our own data path fuses it into the gather); usr_id / vid_id int64 [B] for towers with
         ID inputs.  Returns fp32 logits [B, Lv] before the position bias (a workspace tensor: clone before the next call)."""
         cfg = self.cfg
         self.ensure_bound()
-        self.refresh_low_precision()
+        if refresh:                      # bf16 weight shadows; a micro-batched step refreshes them once, not per slice
+            self.refresh_low_precision()
         d = cfg.d_model
         sv = {"towers": {}}
         outs = []

@@ -75,7 +75,7 @@ class TrainStep:
             usr, um = self.gather(usr_idx[a:b], "usr")
             vid, vm = self.gather(vid_idx[a:b], "vid")
             logits = eng.forward(usr, um, vid, vm, usr_id=None if usr_id is None else usr_id[a:b],
-                                 vid_id=None if vid_id is None else vid_id[a:b])
+                                 vid_id=None if vid_id is None else vid_id[a:b], refresh=si == 0)
             # focal is a sum / B_global; interestBPR is a mean over this slice's rows, averaged over slices and ranks (DDP semantics)
             scal, _ = eng.loss(logits, gt[a:b], self.model.exposure_prob, 1.0 / gb, self.loss_cfg,
                                bpr_scale=1.0 / (self.buckets.world * n_slices))
@@ -94,12 +94,12 @@ class TrainStep:
                        self.wd, self.max_norm if self.max_norm else 0.0, self.step_no, self.norm, None, self.ws)
         return scal
 
-    def step_host(self, usr_idx_h, vid_idx_h, gt_h, dev_bufs):
+    def step_host(self, usr_idx_h, vid_idx_h, gt_h, dev_bufs, micro_batch: int = 0):
         """End-to-end variant: pinned host index/label buffers -> H2D inside the call, loss read
         back to the host (one D2H + sync), as the reference loop's `loss.item()` does."""
         u, v, g = dev_bufs
         u.copy_(usr_idx_h, non_blocking=True)
         v.copy_(vid_idx_h, non_blocking=True)
         g.copy_(gt_h, non_blocking=True)
-        scal = self.step(u, v, g)
+        scal = self.step(u, v, g, micro_batch=micro_batch)
         return float(scal[3].item())

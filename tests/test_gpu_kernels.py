@@ -418,3 +418,37 @@ def test_cast_bf16_transpose(dev):
     y = torch.empty(130, 70, device=dev, dtype=torch.bfloat16)
     ops.cast_bf16(x, y, 70, 130, transpose=True)
     assert torch.equal(y, x.T.contiguous().bfloat16())
+
+
+# ----------------------------------------------------------------------------- loader drop-in (a-1 / a-2)
+def test_device_frame_loader_reproduces_reference_batch(dev):
+    """DeviceFrameLoader against the batch the unmodified FrameDatasetSeq_SegMM + DataCollator produced
+    (tests/golden/gather_small.npz): all twelve keys, bit-exact, in the reference's key order; then the fused
+    L1 normalisation against main...SegMM.py:272-273."""
+    import json
+    import pandas as pd
+    from segmminterest_b200 import DeviceFrameLoader
+    z = np.load(os.path.join(GOLDEN, "gather_small.npz"))
+    rows = json.loads(str(z["rows_json"]))
+    df = pd.DataFrame(rows, columns=["user_id", "video_id", "time_ms", "duration_ms", "playing_time_x", "label_1D", "history_items",
+                                     "history_playing", "history_lengths"])
+
+    class Corpus:
+        data_df = {"test": df}
+        user_input_dict = json.loads(str(z["user_input_json"]))
+
+    table = torch.from_numpy(z["table"]).to(dev)
+    kw = dict(phase="test", batch_size=3, user2id=json.loads(str(z["user2id_json"])), item2id=json.loads(str(z["item2id_json"])))
+    ld = DeviceFrameLoader(Corpus(), json.loads(str(z["lineid_json"])), table, **kw)
+    batches = list(ld)
+    assert len(batches) == len(ld) == 2
+    ref_keys = [k[4:] for k in z.files if k.startswith("out/")]
+    assert [k for k in batches[0] if k not in ("usr_idx", "vid_idx")] == ref_keys       # DataCollator's key order
+    for k in ref_keys:
+        got = torch.cat([b[k] for b in batches]).cpu().numpy()
+        assert got.dtype == z["out/" + k].dtype and np.array_equal(got, z["out/" + k]), k
+    ldn = DeviceFrameLoader(Corpus(), json.loads(str(z["lineid_json"])), table, normalise=True, **kw)
+    user = torch.cat([b["user"] for b in ldn]).cpu()
+    ref = torch.from_numpy(z["out/user"])
+    ref = ref / (ref.norm(p=1, dim=-1, keepdim=True) + 1e-6)
+    assert _rel(user, ref) < 1e-6

@@ -23,6 +23,8 @@
 //              S^T = K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q.  TMEM: S^T[2] | dP^T[2] | dK | dV.
 // Operands arrive by TMA (64 B rows, SWIZZLE_64B) straight from the fused-projection buffers:
 // head h of a [tokens, ld] tensor is the 32-column box at column h*32.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -418,6 +420,260 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_consta
       p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = m * kLn2 + logf(l);
     }
     if (warp == 4) TRACE(4092);
+  }
+  tmem_teardown(tmem, warp, 128);
+}
+
+// ====================================================================================== forward, 64-key tiles
+// Same algorithm with HALF the hand-offs per score: one barrier round trip (a_ready wait, s_free / p_ready arrivals,
+// fence.proxy.async) now covers 64 keys.  The CUDA-event trace of the 32-key kernel (tools/attn_trace.py) shows ~550 of
+// the ~1350 cycles a softmax warp spends per tile going to those hand-offs, not to arithmetic.  TMEM stays at 128
+// columns per CTA (S single-buffered 64 | O 32) and shared memory at ~49 KB, so four CTAs still fit on an SM:
+//   * S is single-buffered: the softmax thread pulls the tile into registers in two 32-column halves and frees the
+//     buffer after the second pull; the MMA warp refills it while the second half is being exponentiated;
+//   * K and V ride in separate 2-stage rings: a K stage is free as soon as its S product retired (early), a V stage
+//     once its P V product retired, so the next K tile is always in flight one whole tile ahead;
+//   * P (bf16, 128 B rows, SWIZZLE_128B) is single-buffered: half 0 is written ~a half tile after p_ready of the
+//     previous tile, by which time its P V product has long retired.
+// smem: Q [2][8 KB] | K [2][4 KB] | V [2][4 KB] | P 16 KB | barriers | key bits
+#ifndef MMI_NS_TMA
+#define MMI_NS_TMA 64
+#endif
+#ifndef MMI_NS_MMA
+#define MMI_NS_MMA 32
+#endif
+constexpr int NT64 = 64;
+constexpr uint32_t TILE64 = NT64 * DH * 2;       // 4 KB : 64 rows x 64 B
+constexpr uint32_t PTILE64 = QT * NT64 * 2;      // 16 KB: 128 rows x 128 B
+constexpr uint32_t IDESC_S64 = make_idesc(QT, NT64, false, false);
+__device__ __forceinline__ uint64_t desc_k128(uint32_t addr, int kstep) { return make_smem_desc(addr + kstep * 32, 16, 1024, 2); }   // K-major SW128
+
+// entry j = {valid bits of keys 0-31, 32-63, in-range bits of keys 0-31, 32-63} of 64-key tile j
+__device__ __forceinline__ void build_key_bits64(uint4* kb, const AttnTcParams& p, int b, int nt0, int T, int warp, int lane, int nwarps) {
+  for (int j = warp; j < T; j += nwarps) {
+    const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
+    const int Lk = blk ? p.Lk[1] : p.Lk[0];
+    const uint8_t* mk = blk ? p.mask_k[1] : p.mask_k[0];
+    const uint32_t lo = mask_bits32(mk, (int64_t)b * Lk, kt * NT64, Lk, lane), hi = mask_bits32(mk, (int64_t)b * Lk, kt * NT64 + 32, Lk, lane);
+    if (lane == 0) kb[j] = make_uint4(lo, hi, range_bits32(kt * NT64, Lk), range_bits32(kt * NT64 + 32, Lk));
+  }
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 4)
+attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
+                     const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
+                     const __grid_constant__ CUtensorMap tmVa, const __grid_constant__ CUtensorMap tmVb, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 2 * TILE128;
+  uint8_t* sV = sK + 2 * TILE64;
+  uint8_t* sP = sV + 2 * TILE64;                          // 32 KB from the base: 1024-aligned
+  Bars* bars = reinterpret_cast<Bars*>(sP + PTILE64);
+  uint4* kbits = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(bars + 1) + 15) & ~static_cast<uintptr_t>(15));
+
+  const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
+  const int nt0 = (p.Lk[0] + NT64 - 1) / NT64, nt1 = p.nblk > 1 ? (p.Lk[1] + NT64 - 1) / NT64 : 0;
+  const int T = nt0 + nt1;
+  const int rows_valid = min(QT, p.Lq - q0);
+  const int nact = (rows_valid + 31) >> 5;
+  // barrier slots: kv_full / kv_empty [0,1] = K ring, [2,3] = V ring; a_ready[0], s_free[0], p_ready[0], p_free[0]
+  auto load_k = [&](int j) {
+    const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j & 1;
+    mbar_expect_tx(&bars->kv_full[st], TILE64);
+    tma_load_2d(blk ? &tmKb : &tmKa, &bars->kv_full[st], sK + st * TILE64, h * DH, b * (blk ? p.Lk[1] : p.Lk[0]) + kt * NT64);
+  };
+  auto load_v = [&](int j) {
+    const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j, st = j & 1;
+    mbar_expect_tx(&bars->kv_full[2 + st], TILE64);
+    tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[2 + st], sV + st * TILE64, h * DH, b * (blk ? p.Lk[1] : p.Lk[0]) + kt * NT64);
+  };
+  if (warp == 0 && elect_one()) {
+    init_bars(bars, 32 * nact);
+    mbar_expect_tx(&bars->once, (p.nblk > 1 ? 2 : 1) * TILE128);
+    tma_load_2d(&tmQa, &bars->once, sQ, h * DH, b * p.Lq + q0);
+    if (p.nblk > 1) tma_load_2d(&tmQb, &bars->once, sQ + TILE128, h * DH, b * p.Lq + q0);
+    for (int j = 0; j < min(T, 2); ++j) { load_k(j); load_v(j); }
+  }
+  build_key_bits64(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
+  const uint32_t tmem = tmem_setup(bars, warp, 128);
+  const uint32_t tO = tmem + NT64;
+
+  if (warp == 0) {
+    for (int j = 2; j < T; ++j) {
+      const uint32_t par = ((j >> 1) & 1) ^ 1;
+      mbar_wait_bg(&bars->kv_empty[j & 1], par, MMI_NS_TMA);
+      if (elect_one()) load_k(j);
+      __syncwarp();
+      mbar_wait_bg(&bars->kv_empty[2 + (j & 1)], par, MMI_NS_TMA);
+      if (elect_one()) load_v(j);
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t tS = uniform(tmem), tOu = uniform(tO);
+    mbar_wait(&bars->once, 0);
+    const uint32_t aP = smem_u32(sP);
+    auto issue_pv = [&](int u) {                         // O += P(u) V(u)
+      const int st = u & 1;
+      mbar_wait_bg(&bars->kv_full[2 + st], (u >> 1) & 1, MMI_NS_MMA);
+      mbar_wait_bg(&bars->p_ready[0], u & 1, MMI_NS_MMA);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t aV = smem_u32(sV + st * TILE64);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tOu, desc_k128(aP, k), desc_mn64(aV, k), IDESC_O, (u > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&bars->p_free[0]);
+        umma_commit(&bars->kv_empty[2 + st]);
+      }
+      __syncwarp();
+    };
+    for (int j = 0; j < T; ++j) {
+      const int blk = j < nt0 ? 0 : 1, st = j & 1;
+      mbar_wait_bg(&bars->kv_full[st], (j >> 1) & 1, MMI_NS_MMA);
+      if (j >= 1) mbar_wait_bg(&bars->s_free[0], (j - 1) & 1, MMI_NS_MMA);
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t aQ = smem_u32(sQ + blk * TILE128), aK = smem_u32(sK + st * TILE64);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) umma_f16(tS, desc_k64(aQ, k), desc_k64(aK, k), IDESC_S64, k);
+        umma_commit(&bars->kv_empty[st]);
+        umma_commit(&bars->a_ready[0]);
+      }
+      __syncwarp();
+      if (j >= 1) issue_pv(j - 1);
+    }
+    issue_pv(T - 1);
+    if (elect_one()) umma_commit(&bars->done);
+    __syncwarp();
+  } else if ((warp & 3) < nact) {
+    const int qd = warp & 3, row = qd * 32 + lane;
+    const int qi = q0 + row;
+    const bool q_in = qi < p.Lq;
+    const bool mq = q_in ? (p.mask_q[(int64_t)b * p.Lq + qi] != 0) : true;
+    const bool warp_all_mq = __all_sync(0xffffffffu, mq);
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const float scale_t = mq ? p.scale_log2 : 0.f;
+    const float base_t = mq ? 0.f : p.fill_log2;
+    float m = 0.f, l0 = 0.f, l1 = 0.f;
+    const uint32_t a_ready_a = smem_u32(&bars->a_ready[0]), s_free_a = smem_u32(&bars->s_free[0]), p_ready_a = smem_u32(&bars->p_ready[0]);
+    const uint32_t p_free_a = smem_u32(&bars->p_free[0]);
+    const uint32_t kb_a = smem_u32(kbits), prow_a = smem_u32(sP) + row * 128, swz = row & 7;
+    const uint32_t tS_row = tmem + lane_addr;
+    for (int j = 0; j < T; ++j) {
+      const uint4 kb = lds_u4(kb_a + j * 16);
+      mbar_wait_a(a_ready_a, j & 1);
+      tcgen05_fence_after();
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const uint32_t wv = hf ? kb.y : kb.x, wr = hf ? kb.w : kb.z;
+        uint32_t r[32];
+        tmem_ld_32x32(tS_row + hf * 32, r);
+        tmem_ld_wait();
+        if (hf == 1) {                                   // the whole tile is in registers: the MMA warp may refill S
+          tcgen05_fence_before();
+          mbar_arrive_a(s_free_a);
+        }
+        // ---- maximum of this half in the log2 domain
+        float t;
+        {
+          float mx = -INFINITY;
+          if (wv == 0xffffffffu) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) if ((wv >> c) & 1u) mx = fmaxf(mx, __uint_as_float(r[c]));
+          }
+          t = (wr & ~wv) != 0u ? p.fill_log2 : -INFINITY;
+          if (mx > -INFINITY) t = fmaxf(t, mx * p.scale_log2);
+          if (!mq) t = p.fill_log2;
+        }
+        const bool first = j == 0 && hf == 0;
+        if (first) m = t;
+        const bool move = !first && t > m + kTau;
+        if (__any_sync(0xffffffffu, move)) {
+          // rare: move the reference maximum of some rows -- rescale l, the rows of O (once every P V product issued so
+          // far has retired) and, in the second half, the half-0 probabilities this thread already staged
+          if (j >= 1) mbar_wait(&bars->p_free[0], (j - 1) & 1);
+          tcgen05_fence_after();
+          const float f = move ? ex2(m - t) : 1.0f;
+          if (j >= 1) {
+            uint32_t ro[32];
+            tmem_ld_32x32(tO + lane_addr, ro);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) ro[c] = __float_as_uint(__uint_as_float(ro[c]) * f);
+            tmem_st_32x32(tO + lane_addr, ro);
+            tmem_st_wait();
+            tcgen05_fence_before();
+          }
+          if (hf == 1) {
+#pragma unroll
+            for (uint32_t v = 0; v < 4; ++v) {
+              const uint32_t a = prow_a + ((v ^ swz) << 4);
+              uint4 w = lds_u4(a);
+              uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                ww[i] = pack_bf16x2(__uint_as_float(ww[i] << 16) * f, __uint_as_float(ww[i] & 0xffff0000u) * f);
+              sts_u4(a, ww[0], ww[1], ww[2], ww[3]);
+            }
+          }
+          l0 *= f; l1 *= f;
+          if (move) m = t;
+        }
+        const float nb_t = base_t - m;
+        uint32_t pk[16];
+        if (warp_all_mq && wv == 0xffffffffu) {
+          float2 l2 = make_float2(l0, l1);
+          const float2 sc2 = splat2(scale_t), nb2 = splat2(nb_t);
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            const float2 x = fma2(make_float2(__uint_as_float(r[c]), __uint_as_float(r[c + 1])), sc2, nb2);
+            const float2 e = poly_pair(c >> 1) ? ex2_poly2(x) : ex2_mufu2(x);
+            l2 = add2(l2, e);
+            pk[c >> 1] = pack_bf16x2(e.x, e.y);
+          }
+          l0 = l2.x; l1 = l2.y;
+        } else {
+          const float pm = ex2(p.fill_log2 - m);
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float e[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int cc = c + u;
+              const float ev = ex2(fmaf(__uint_as_float(r[cc]), scale_t, nb_t));
+              e[u] = ((wv >> cc) & 1u) ? ev : (((wr >> cc) & 1u) ? pm : 0.f);
+            }
+            l0 += e[0]; l1 += e[1];
+            pk[c >> 1] = pack_bf16x2(e[0], e[1]);
+          }
+        }
+        if (hf == 0 && j >= 1) mbar_wait_a(p_free_a, (j - 1) & 1);      // P V (j-1) has consumed the staging tile
+#pragma unroll
+        for (uint32_t v = 0; v < 4; ++v)
+          sts_u4(prow_a + (((hf * 4 + v) ^ swz) << 4), pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive_a(p_ready_a);
+    }
+    mbar_wait(&bars->done, 0);
+    tcgen05_fence_after();
+    uint32_t ro[32];
+    tmem_ld_32x32(tO + lane_addr, ro);
+    tmem_ld_wait();
+    if (q_in) {
+      const float l = l0 + l1;
+      store_row32_bf16(p.out + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH, ro, 1.0f / l);
+      p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = m * kLn2 + logf(l);
+    }
   }
   tmem_teardown(tmem, warp, 128);
 }
@@ -841,8 +1097,9 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
   const int64_t q_rows = (int64_t)a->B * a->Lq;
   static size_t cfg_bytes[3] = {0, 0, 0};   // largest dynamic shared-memory size configured so far, per kernel
   const size_t bar_bytes = sizeof(Bars) + 1024 /*align*/;
+  static const bool fwd64 = []() { const char* e = getenv("MMI_ATTN_FWD64"); return e == nullptr || e[0] != '0'; }();
   if (kind == 0 || kind == 1) {
-    const uint32_t kbox = NT;
+    const uint32_t kbox = (kind == 0 && fwd64) ? NT64 : NT;
     CUtensorMap mQ[2], mK[2], mV[2], mdO;
     for (int i = 0; i < 2; ++i) {
       const mmi_attn_block& s = a->blk[i < a->nblk ? i : 0];
@@ -852,7 +1109,13 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
       if (!map_rows(s.v, s.ldv, k_rows, width, kbox, &mV[i])) return MMI_ECUDA;
     }
     dim3 grid((a->Lq + QT - 1) / QT, a->H, a->B);
-    if (kind == 0) {
+    if (kind == 0 && fwd64) {
+      static size_t cfg64 = 0;
+      const size_t T = (a->blk[0].Lk + NT64 - 1) / NT64 + (a->nblk > 1 ? (a->blk[1].Lk + NT64 - 1) / NT64 : 0);
+      const size_t smem = 2 * TILE128 + 4 * TILE64 + PTILE64 + bar_bytes + 16 + T * 16;
+      if (smem > cfg64) { int rc = set_smem(attn_fwd_tc64_kernel, smem); if (rc) return rc; cfg64 = smem; }
+      attn_fwd_tc64_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
+    } else if (kind == 0) {
       const size_t T = (a->blk[0].Lk + NT - 1) / NT + (a->nblk > 1 ? (a->blk[1].Lk + NT - 1) / NT : 0);
       const size_t smem = 2 * TILE128 + FWD_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes + T * 8;
       if (smem > cfg_bytes[0]) { int rc = set_smem(attn_fwd_tc_kernel, smem); if (rc) return rc; cfg_bytes[0] = smem; }

@@ -73,6 +73,19 @@ __device__ __forceinline__ uint32_t lds_u1(uint32_t saddr) {
 __device__ __forceinline__ void mbar_wait_bg(uint64_t* bar, uint32_t parity, uint32_t ns = 64) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0, spins = 0;
+#ifdef MMI_WAIT_HINT
+  // suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint expires) instead of polling
+  (void)ns;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity), "r"((uint32_t)MMI_WAIT_HINT) : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+#else
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -83,6 +96,7 @@ __device__ __forceinline__ void mbar_wait_bg(uint64_t* bar, uint32_t parity, uin
     __nanosleep(ns);
     if (++spins > SPIN_LIMIT) __trap();
   }
+#endif
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -138,6 +138,10 @@ typedef struct {
   void* dq; int64_t lddq;
   void* dk; int64_t lddk;
   void* dv; int64_t lddv;
+  /* optional (NULL = off; MMI_IMPL_TC only): fp32 [H*dh] accumulators that receive (+=, atomics) the column sums of dq /
+   * dk / dv taken in fp32 BEFORE rounding to the output dtype -- the bias gradients of the three projections
+   * (autograd's dY.sum(0) for models/encoder.py:50-62,95-98), so no separate pass re-reads the gradients.        */
+  float* dbq; float* dbk; float* dbv;
 } mmi_attn_block;
 typedef struct {
   int dtype; int impl;

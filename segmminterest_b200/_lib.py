@@ -31,7 +31,8 @@ class GemmArgs(C.Structure):
 class AttnBlock(C.Structure):
     _fields_ = [("q", c_p), ("ldq", i64), ("k", c_p), ("ldk", i64), ("v", c_p), ("ldv", i64),
                 ("mask_k", c_p), ("Lk", C.c_int),
-                ("dq", c_p), ("lddq", i64), ("dk", c_p), ("lddk", i64), ("dv", c_p), ("lddv", i64)]
+                ("dq", c_p), ("lddq", i64), ("dk", c_p), ("lddk", i64), ("dv", c_p), ("lddv", i64),
+                ("dbq", c_p), ("dbk", c_p), ("dbv", c_p)]
 
 
 class AttnArgs(C.Structure):

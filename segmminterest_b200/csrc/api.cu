@@ -63,6 +63,8 @@ static int attn_dispatch(int kind, const mmi_attn_args* a, int which, mmi_stream
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MMI_CHECK_ARG(a != nullptr, "attn: null args");
   if (a->impl == MMI_IMPL_TC) return attn_tc(kind, a, which, st);
+  for (int i = 0; i < a->nblk && i < 2; ++i)
+    MMI_CHECK_ARG(kind == 0 || (!a->blk[i].dbq && !a->blk[i].dbk && !a->blk[i].dbv), "attn: fused bias-gradient sums (dbq/dbk/dbv) need MMI_IMPL_TC");
   return attn_simt(kind, a, which, st);
 }
 

@@ -54,6 +54,7 @@ struct AttnTcParams {
   __nv_bfloat16* dq[2]; int64_t lddq[2];
   __nv_bfloat16* dk; int64_t lddk;
   __nv_bfloat16* dv; int64_t lddv;
+  float* dbq[2]; float* dbk; float* dbv;   // optional fused bias-gradient accumulators [H*dh]
   int which;
   float scale;        // 1/sqrt(dh)
   float scale_log2;   // scale * log2(e)
@@ -209,6 +210,29 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const uint3
     *reinterpret_cast<uint4*>(dst + d) =
         make_uint4(pack_bf16x2(__uint_as_float(r[d]) * mul, __uint_as_float(r[d + 1]) * mul), pack_bf16x2(__uint_as_float(r[d + 2]) * mul, __uint_as_float(r[d + 3]) * mul),
                    pack_bf16x2(__uint_as_float(r[d + 4]) * mul, __uint_as_float(r[d + 5]) * mul), pack_bf16x2(__uint_as_float(r[d + 6]) * mul, __uint_as_float(r[d + 7]) * mul));
+}
+
+// Column sums of a [32 lanes x 32 values] register tile by a transposing butterfly (31 shuffles instead of 160):
+// lane i ends with sum over lanes of v[i].  Used by the backward epilogues for the fused bias gradients.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? v[i] : v[i + o];
+      const float keep = up ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0];
+}
+__device__ __forceinline__ void add_bias_grad(float* db, const uint32_t (&r)[32], bool row_in, int lane) {
+  float f[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) f[c] = row_in ? __uint_as_float(r[c]) : 0.f;
+  const float s = warp_colsum32(f, lane);
+  atomicAdd(db + lane, s);
 }
 
 // ====================================================================================== forward
@@ -842,10 +866,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
     tmem_ld_32x32(tdQ + lane_addr, ra);
     tmem_ld_wait();
     if (q_in && p.dq[0] != nullptr) store_row32_bf16(p.dq[0] + ((int64_t)b * p.Lq + qi) * p.lddq[0] + h * DH, ra, 1.0f);
+    if (p.dbq[0] != nullptr) add_bias_grad(p.dbq[0] + h * DH, ra, q_in, lane);
     if (p.nblk > 1) {
       tmem_ld_32x32(tdQ + DH + lane_addr, ra);
       tmem_ld_wait();
       if (q_in && p.dq[1] != nullptr) store_row32_bf16(p.dq[1] + ((int64_t)b * p.Lq + qi) * p.lddq[1] + h * DH, ra, 1.0f);
+      if (p.dbq[1] != nullptr) add_bias_grad(p.dbq[1] + h * DH, ra, q_in, lane);
     }
   }
   tmem_teardown(tmem, warp, 128);
@@ -1045,9 +1071,11 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tmem_ld_32x32(tdK + lane_addr, rk);
     tmem_ld_wait();
     if (k_in && p.dk != nullptr) store_row32_bf16(p.dk + ((int64_t)b * Lk + kj) * p.lddk + h * DH, rk, 1.0f);
+    if (p.dbk != nullptr) add_bias_grad(p.dbk + h * DH, rk, k_in, lane);
     tmem_ld_32x32(tdV + lane_addr, rk);
     tmem_ld_wait();
     if (k_in && p.dv != nullptr) store_row32_bf16(p.dv + ((int64_t)b * Lk + kj) * p.lddv + h * DH, rk, 1.0f);
+    if (p.dbv != nullptr) add_bias_grad(p.dbv + h * DH, rk, k_in, lane);
   }
   tmem_teardown(tmem, warp, 128);
 }
@@ -1092,6 +1120,7 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     MMI_CHECK_ARG(s.ldq % 8 == 0 && s.ldk % 8 == 0 && s.ldv % 8 == 0, "attn_tc: leading dims must be multiples of 8 (TMA)");
     p.Lk[i] = s.Lk; p.mask_k[i] = s.mask_k;
     p.dq[i] = reinterpret_cast<__nv_bfloat16*>(s.dq); p.lddq[i] = s.lddq;
+    p.dbq[i] = kind == 1 ? s.dbq : nullptr;
   }
   if (a->nblk == 1) { p.Lk[1] = 0; p.mask_k[1] = p.mask_k[0]; }
   const int64_t q_rows = (int64_t)a->B * a->Lq;
@@ -1136,6 +1165,7 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     p.which = which;
     p.dk = reinterpret_cast<__nv_bfloat16*>(s.dk); p.lddk = s.lddk;
     p.dv = reinterpret_cast<__nv_bfloat16*>(s.dv); p.lddv = s.lddv;
+    p.dbk = s.dbk; p.dbv = s.dbv;
     const int64_t k_rows = (int64_t)a->B * s.Lk;
     CUtensorMap mQ, mK, mV, mdO;
     if (!map_rows(s.q, s.ldq, q_rows, width, NT, &mQ)) return MMI_ECUDA;

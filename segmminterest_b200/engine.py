@@ -303,7 +303,7 @@ class Engine:
                          add=add, add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=self.use_tc)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, usr_image, usr_mask, vid_image, vid_mask, usr_id=None, vid_id=None, refresh=True):
+    def forward(self, usr_image, usr_mask, vid_image, vid_mask, usr_id=None, vid_id=None, refresh=True, need_bwd=True):
         """usr_image [B,Lt,Din] / vid_image [B,Lv,Din] already L1-normalised (the driver does it,
         main...SegMM.py:272-273; our own data path fuses it into the gather); usr_id / vid_id int64 [B] for towers with
         ID inputs.  Returns fp32 logits [B, Lv] before the position bias (a workspace tensor: clone before the next call)."""
@@ -312,6 +312,7 @@ class Engine:
         if refresh:                      # bf16 weight shadows; a micro-batched step refreshes them once, not per slice
             self.refresh_low_precision()
         d = cfg.d_model
+        self._need_bwd = need_bwd        # forward-only calls (mode="inference") skip the saved GELU' tensor
         sv = {"towers": {}}
         outs = []
         B = Lv = None
@@ -441,7 +442,7 @@ class Engine:
                 x2 = self._buf(k(f"x2.{i}.{s}"), (Ts[s], d), T)
                 self._linear(attn[s][1], Ts[s], d, k(f"L{i}.{s}.wo"), k(f"L{i}.{s}.bo"), d, p1, add=X[s], add_mod=Ts[s], ld_add=d)
                 ops.layernorm_fwd(p1, Ts[s], d, self.w(k(f"L{i}.{s}.ln1.g")), self.w(k(f"L{i}.{s}.ln1.b")), x1, st1)
-                self._linear(x1, Ts[s], d, k(f"L{i}.{s}.w1"), k(f"L{i}.{s}.b1"), d, g1, act=ACT_GELU, preact=z1)
+                self._linear(x1, Ts[s], d, k(f"L{i}.{s}.w1"), k(f"L{i}.{s}.b1"), d, g1, act=ACT_GELU, preact=z1 if self._need_bwd else None)
                 self._linear(g1, Ts[s], d, k(f"L{i}.{s}.w2"), k(f"L{i}.{s}.b2"), d, p2, add=x1, add_mod=Ts[s], ld_add=d)
                 ops.layernorm_fwd(p2, Ts[s], d, self.w(k(f"L{i}.{s}.ln2.g")), self.w(k(f"L{i}.{s}.ln2.b")), x2, st2)
                 lay[s] = dict(p1=p1, st1=st1, x1=x1, z1=z1, g1=g1, p2=p2, st2=st2)
@@ -590,15 +591,24 @@ class Engine:
             def gcol(s, j):
                 return (dqkv[s].data_ptr() + j * d * esz, nq[s] * d)
 
+            # tensor-core attention: the backward kernels add the fp32 column sums of dq / dk / dv (= the bias gradients of
+            # the six fused projections) straight into the flat gradient buffer, so dqkv is not re-read by a colsum pass
+            fused_bias = all(lay["attn"][s][0].a.impl == IMPL_TC for s in sides)
+            gb6 = {s: self.g(k(f"L{i}.{s}.b6")) for s in ("vid", "usr")}
+
+            def bcol(s, j):
+                return gb6[s].data_ptr() + 4 * j * d if fused_bias else None
+
+            def gset(qs, ks, vs):
+                return dict(dq=gcol(*qs), dk=gcol(*ks), dv=gcol(*vs), dbq=bcol(*qs), dbk=bcol(*ks), dbv=bcol(*vs))
+
             for s in sides:
                 side = lay["attn"][s][0]
                 delta = self._buf(f"delta.{tw.tag}.{s}", (B, H, Ls[s]), torch.float32)
                 if s == "vid":
-                    grads = [dict(dq=gcol("vid", 0), dk=gcol("vid", 1), dv=gcol("vid", 2)),
-                             dict(dq=gcol("vid", 3), dk=gcol("usr", 0), dv=gcol("usr", 1))]
+                    grads = [gset(("vid", 0), ("vid", 1), ("vid", 2)), gset(("vid", 3), ("usr", 0), ("usr", 1))]
                 else:
-                    grads = [dict(dq=gcol("usr", 2), dk=gcol("vid", 4), dv=gcol("vid", 5)),
-                             dict(dq=gcol("usr", 3), dk=gcol("usr", 4), dv=gcol("usr", 5))]
+                    grads = [gset(("usr", 2), ("vid", 4), ("vid", 5)), gset(("usr", 3), ("usr", 4), ("usr", 5))]
                 side.set_bwd(dA[s], d, delta, grads)
                 side.bwd_dq()
                 side.bwd_dkv(0)
@@ -608,7 +618,7 @@ class Engine:
                 pre = k(f"L{i}.{s}.")
                 out = scratch("dxl", s)
                 # dX[s] (the grad w.r.t. this layer's OUTPUT) is dead by now: dp2 consumed it
-                self._linear_bwd(dqkv[s], Xin[s], Ts[s], nq[s] * d, d, pre + "w6", pre + "b6", out, add=dP1.get(s))
+                self._linear_bwd(dqkv[s], Xin[s], Ts[s], nq[s] * d, d, pre + "w6", pre + "b6", out, add=dP1.get(s), bias_done=fused_bias)
                 new_dX[s] = out
             dX = new_dX
             if on_ready is not None:

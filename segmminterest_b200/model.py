@@ -260,7 +260,8 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
     def forward(self, usr_image, usr_id, usr_mask, vid_image, vid_id, vid_mask, gt=None, mode="train", **kwargs):
         eng = self.engine()
         B = usr_id.shape[0]
-        logits = eng.forward(usr_image, usr_mask, vid_image, vid_mask, usr_id=usr_id, vid_id=vid_id)
+        logits = eng.forward(usr_image, usr_mask, vid_image, vid_mask, usr_id=usr_id, vid_id=vid_id,
+                             need_bwd=mode != "inference" and torch.is_grad_enabled())
         if mode == "inference":
             if self.bias_weight is None:
                 return dict(logits=logits.clone(), gt=gt)

@@ -155,6 +155,7 @@ class AttnSide:
             k.dq, k.lddq = g["dq"]
             k.dk, k.lddk = g["dk"]
             k.dv, k.lddv = g["dv"]
+            k.dbq, k.dbk, k.dbv = g.get("dbq"), g.get("dbk"), g.get("dbv")   # fused bias-gradient sums (TC path), None = off
 
     def bwd_dq(self):
         with TIMER.region(self._cat("attn_bwd_dq"), 1.5 * self.flops()):

@@ -248,13 +248,25 @@ def _check_attention(dev, dh, dtype, impl, shape, ragged, key_ramp=0.0):
     ref.backward(dO.double().cpu())
     grads = [torch.zeros_like(x) for x in t]
     delta = torch.empty(B, H, Lq, device=dev)
-    side.set_bwd(dO, d, delta, [dict(dq=(grads[0].data_ptr(), d), dk=(grads[1].data_ptr(), d), dv=(grads[2].data_ptr(), d)),
-                                dict(dq=(grads[3].data_ptr(), d), dk=(grads[4].data_ptr(), d), dv=(grads[5].data_ptr(), d))])
+    fused = impl == ops.IMPL_TC          # tensor-core kernels also accumulate the projections' bias gradients (column sums)
+    db = [torch.full((d,), 0.25, device=dev) for _ in range(6)] if fused else [None] * 6
+    ptr = [x.data_ptr() if x is not None else None for x in db]
+    side.set_bwd(dO, d, delta, [dict(dq=(grads[0].data_ptr(), d), dk=(grads[1].data_ptr(), d), dv=(grads[2].data_ptr(), d),
+                                     dbq=ptr[0], dbk=ptr[1], dbv=ptr[2]),
+                                dict(dq=(grads[3].data_ptr(), d), dk=(grads[4].data_ptr(), d), dv=(grads[5].data_ptr(), d),
+                                     dbq=ptr[3], dbk=ptr[4], dbv=ptr[5])])
     side.bwd_dq()
     side.bwd_dkv(0)
     side.bwd_dkv(1)
     for g, r, name in zip(grads, ref_in, ["dqa", "dka", "dva", "dqb", "dkb", "dvb"]):
         assert _rel(g, r.grad) < (5e-5 if dtype == torch.float32 else 1.5e-2), name
+    if fused:                            # += semantics (buffers started at 0.25), fp32 sums taken before the bf16 rounding
+        for x, r, name in zip(db, ref_in, ["dbqa", "dbka", "dbva", "dbqb", "dbkb", "dbvb"]):
+            want = r.grad.sum((0, 1))
+            # a column sum cancels heavily, so the bar is relative to the gradient it sums (random element errors of
+            # relative size e give ||sum error|| ~ e * ||grad||_F), the same 1.5e-2 the gradients themselves are held to
+            err = float((x.double().cpu() - 0.25 - want).norm())
+            assert err < 1.5e-2 * float(r.grad.norm()) + 1e-20, (name, err, float(r.grad.norm()), float(want.norm()))
 
 
 # ----------------------------------------------------------------------------- loss

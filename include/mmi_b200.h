@@ -160,9 +160,12 @@ int mmi_attn_bwd_dq(const mmi_attn_args* a, mmi_stream_t stream);
 /* writes dk, dv of block `which` (needs lse and delta from the calls above) */
 int mmi_attn_bwd_dkv(const mmi_attn_args* a, int which, mmi_stream_t stream);
 
-/* ---- a-9: head Linear(d -> 1)  (models/decoder_leave_focal.py:451,596) ---------------*/
+/* ---- a-9: head Linear(d -> 1)  (models/decoder_leave_focal.py:451,596) ---------------
+ * logits[r] = w . x[r] (+ b[0]) (+ add[r]);  b and add may be NULL.  `add` chains two heads for the two-backbone
+ * fusions without InteractionAggregation (:624-631: Linear over the sum / the concatenation, or two Linear heads).
+ * head_bwd: db may be NULL when another call owns the bias gradient.                                   */
 int mmi_head_fwd(const void* x, int dtype, int64_t rows, int d, const float* w,
-                 const float* b, float* logits, mmi_stream_t stream);
+                 const float* b, const float* add, float* logits, mmi_stream_t stream);
 int64_t mmi_head_bwd_workspace(int d);
 int mmi_head_bwd(const void* x, int dtype, int64_t rows, int d, const float* w,
                  const float* dlogits, const float* gscale /* device scalar or NULL */,

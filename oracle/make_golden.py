@@ -92,18 +92,18 @@ def run_model_case(name, d_model, nhead, nlayers, din, Lt, B, seed, store_sd=Tru
     print(name, "loss", save["loss"], "n_dead", len(dead))
 
 
-def run_general_case(name, input_type, d_model, nhead, nlayers, din, B, seed, loss_types, n_users=23, n_items=57):
+def run_general_case(name, input_type, d_model, nhead, nlayers, din, B, seed, loss_types, n_users=23, n_items=57, fusion_heads=2):
     """SURVEY 8f-1: ID inputs / two backbones + InteractionAggregation (the reference's default 'both' config), history
     padded to the reference's 100 tokens.  Stores the full state_dict, inputs, outputs and gradients."""
     args = ref_shim.make_args(d_model=d_model, nhead=nhead, num_layers_enc=nlayers, loss_type_list=list(loss_types),
-                              input_type=input_type, fusion_heads=2)
+                              input_type=input_type, fusion_heads=fusion_heads)
     model = ref_shim.build_reference_model_general(args, din=din, n_users=n_users, n_items=n_items, seed=seed)
     g = torch.Generator().manual_seed(seed + 1)
     with torch.no_grad():
         for k, p in model.named_parameters():
             if p.ndim == 1:
                 p.add_(torch.randn(p.shape, generator=g) * 0.05)
-            if k == "stage_mlp1.weight":
+            if k in ("stage_mlp1.weight", "stage_mlp2.weight"):
                 p.mul_(3.0)
             # the fusion head keeps its init scale: interestBPR = -log(A) must stay away from A ~ 1, where the loss
             # amplifies any logit noise by 1 / (1 - A) and a bf16 comparison would only measure that amplification
@@ -121,7 +121,7 @@ def run_general_case(name, input_type, d_model, nhead, nlayers, din, B, seed, lo
     out["loss"].backward()
     save = dict(cfg=json.dumps(dict(d_model=d_model, nhead=nhead, num_layers_enc=nlayers, din=din, Lt=Lt, B=B, seed=seed,
                                     loss_types=list(loss_types), input_type=input_type, n_users=n_users, n_items=n_items,
-                                    fusion_heads=2)),
+                                    fusion_heads=fusion_heads)),
                 usr_image=usr, vid_image=vid, usr_id=usr_id, vid_id=vid_id, usr_mask=usr_mask, vid_mask=vid_mask, gt_in=gt,
                 logits=out["logits"].detach().numpy(), gt_out=out["gt"].numpy(), loss=np.float64(out["loss"].item()),
                 mse=np.float64(out["mse"].item()), mse2=np.float64(out["mse2"].item()))
@@ -308,6 +308,15 @@ def run_general_cases():
                      loss_types=("interestBPR",))
     run_general_case("model_id_small", {"user": "id", "photo": "id"}, d_model=64, nhead=2, nlayers=3, din=24, B=4, seed=22,
                      loss_types=("focal",))
+    run_fusion_variants()
+
+
+def run_fusion_variants():
+    """the other fusions of forward (decoder_leave_focal.py:624-634): fusion_heads 0 (two Linear heads summed), -1 (one
+    Linear(2d, 1) over the concatenation), -2 (one Linear head over the sum of the two backbones)"""
+    for fh in (0, -1, -2):
+        run_general_case(f"model_both_fh{fh}", {"user": "both", "photo": "both"}, d_model=64, nhead=2, nlayers=3, din=24, B=4,
+                         seed=30 - fh, loss_types=("focal",), fusion_heads=fh)
 
 
 if __name__ == "__main__":
@@ -317,5 +326,7 @@ if __name__ == "__main__":
         run_loss_cases_all()
     elif "--eval-only" in sys.argv:
         run_eval_case()
+    elif "--fusion-only" in sys.argv:
+        run_fusion_variants()
     else:
         main()

@@ -320,7 +320,17 @@ def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_laye
     if two:
         x2 = backbone(sd, "backbone2.", pick(it["user"], usr_image, usr_id, 2), usr_mask.bool(),
                       pick(it["photo"], vid_image, vid_id, 2), vid_mask.bool(), nhead, num_layers, use_pe)
-        logits = fusion_logits(sd, x1, x2, fusion_heads)
+        if fusion_heads > 0:
+            logits = fusion_logits(sd, x1, x2, fusion_heads)
+        elif fusion_heads == 0:      # models/decoder_leave_focal.py:630-631: stage_mlp1(x1) + stage_mlp2(x2)
+            logits = _position_bias(sd, (F.linear(x1, sd["stage_mlp1.weight"], sd["stage_mlp1.bias"]) +
+                                         F.linear(x2, sd["stage_mlp2.weight"], sd["stage_mlp2.bias"])).squeeze(-1))
+        elif fusion_heads == -1:     # :627-629: Linear(2d, 1) over cat([x1, x2], -1)
+            logits = head_logits(sd, torch.cat([x1, x2], dim=-1))
+        elif fusion_heads == -2:     # :624-626: Linear(d, 1) over x1 + x2
+            logits = head_logits(sd, x1 + x2)
+        else:
+            raise NotImplementedError(f"fusion_heads={fusion_heads}")
     else:
         logits = head_logits(sd, x1)
     if mode == "inference":

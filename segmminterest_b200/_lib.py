@@ -68,7 +68,7 @@ _SIGS = {
     "mmi_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), c_p]),
     "mmi_attn_bwd_dq": (C.c_int, [C.POINTER(AttnArgs), c_p]),
     "mmi_attn_bwd_dkv": (C.c_int, [C.POINTER(AttnArgs), C.c_int, c_p]),
-    "mmi_head_fwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p]),
+    "mmi_head_fwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p]),
     "mmi_head_bwd_workspace": (i64, [C.c_int]),
     "mmi_head_bwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmi_focal_loss_fwd_bwd": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, C.c_float, C.c_float, C.c_int, c_p, c_p, c_p]),

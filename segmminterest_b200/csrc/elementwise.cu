@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
 // ------------------------------------------------------------------ head Linear(d -> 1)
 template <typename T>
 __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ x, int64_t rows, int d, const float* __restrict__ w,
-                                                       const float* __restrict__ b, float* __restrict__ logits) {
+                                                       const float* __restrict__ b, const float* __restrict__ add, float* __restrict__ logits) {
   const int lane = threadIdx.x & 31;
   const int nvec = d >> 2;
   const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const T* __restrict__ x, 
       s += v.x * ww.x + v.y * ww.y + v.z * ww.z + v.w * ww.w;
     }
     s = warp_sum(s);
-    if (lane == 0) logits[row] = s + b[0];
+    if (lane == 0) logits[row] = s + (b ? b[0] : 0.f) + (add ? add[row] : 0.f);
   }
 }
 
@@ -885,15 +885,15 @@ extern "C" int mmi_colsum_acc(const void* x, int dtype, int64_t M, int N, int64_
   return MMI_OK;
 }
 
-extern "C" int mmi_head_fwd(const void* x, int dtype, int64_t rows, int d, const float* w, const float* b, float* logits,
-                            mmi_stream_t stream) {
+extern "C" int mmi_head_fwd(const void* x, int dtype, int64_t rows, int d, const float* w, const float* b, const float* add,
+                            float* logits, mmi_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  MMI_CHECK_ARG(x && w && b && logits, "head_fwd: null pointer");
+  MMI_CHECK_ARG(x && w && logits, "head_fwd: null pointer");
   MMI_CHECK_ARG(d % 4 == 0 && d > 0, "head: d=%d must be a multiple of 4", d);
   if (rows == 0) return MMI_OK;
   const int grid = grid_for_rows(rows, 8, kNumSMs * 8);
-  if (dtype == MMI_F32) head_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, rows, d, w, b, logits);
-  else if (dtype == MMI_BF16) head_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, rows, d, w, b, logits);
+  if (dtype == MMI_F32) head_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, rows, d, w, b, add, logits);
+  else if (dtype == MMI_BF16) head_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, rows, d, w, b, add, logits);
   else { set_error("head_fwd: bad dtype %d", dtype); return MMI_EINVAL; }
   MMI_CHECK_LAUNCH();
   return MMI_OK;
@@ -904,7 +904,7 @@ extern "C" int64_t mmi_head_bwd_workspace(int d) { return (int64_t)kRedCtas * (d
 extern "C" int mmi_head_bwd(const void* x, int dtype, int64_t rows, int d, const float* w, const float* dlogits, const float* gscale,
                             void* dx, float* dw, float* db, float* workspace, mmi_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  MMI_CHECK_ARG(x && w && dlogits && dx && dw && db && workspace, "head_bwd: null pointer");
+  MMI_CHECK_ARG(x && w && dlogits && dx && dw && workspace, "head_bwd: null pointer");   // db may be NULL (bias owned by another head)
   MMI_CHECK_ARG(d % 4 == 0 && d <= 128 * kMaxVecPerLane && d > 0, "head: d=%d must be a multiple of 4 and <= %d", d, 128 * kMaxVecPerLane);
   if (rows == 0) return MMI_OK;
   const int grid = grid_for_rows(rows, 8, kRedCtas);

@@ -171,6 +171,9 @@ class Engine:
         else:
             group("head.w", [("stage_mlp1.weight", self.model.stage_mlp1.weight)])
             group("head.b", [("stage_mlp1.bias", self.model.stage_mlp1.bias)])
+            if getattr(self.model, "stage_mlp2", None) is not None:      # fusion_heads == 0: a second Linear head
+                group("head2.w", [("stage_mlp2.weight", self.model.stage_mlp2.weight)])
+                group("head2.b", [("stage_mlp2.bias", self.model.stage_mlp2.bias)])
         if getattr(self.model, "bias_weight", None) is not None:   # learnable position bias (decoder_leave_focal.py:442-444)
             group("bias_weight", [("bias_weight", self.model.bias_weight)])
             group("bias_bias", [("bias_bias", self.model.bias_bias)])
@@ -322,8 +325,14 @@ class Engine:
         sv["B"], sv["Lv"] = B, Lv
         R = B * Lv
         logits = self._buf("logits", (B, Lv), torch.float32)
-        if self.fusion is None:
+        if self.fusion is None and len(outs) == 1:
             ops.head_fwd(outs[0], R, d, self.w("head.w"), self.w("head.b"), logits)
+        elif self.fusion is None:
+            # two backbones without InteractionAggregation (decoder_leave_focal.py:624-631): two chained Linear(d, 1) passes
+            (w1, b1), (w2, b2) = self._two_head_params()
+            part = self._buf("head.part", (R,), torch.float32)
+            ops.head_fwd(outs[0], R, d, w1, b1, part)
+            ops.head_fwd(outs[1], R, d, w2, b2, logits, add=part)
         else:
             # InteractionAggregation: w_x.x + w_y.y + sum_h x_h^T W_h y_h  (decoder_leave_focal.py:411-423)
             T = self.act_dtype
@@ -352,6 +361,18 @@ class Engine:
         sv["x_out"] = outs
         self._saved = sv
         return logits
+
+    def _two_head_params(self, grad=False):
+        """((w1, b1), (w2, b2)) of the two chained Linear(d, 1) passes for fusion_heads 0 / -1 / -2; b2 is None when the
+        bias belongs to the first pass (grad=True: the matching views of the flat gradient buffer)."""
+        d = self.cfg.d_model
+        buf = self.g if grad else self.w
+        fh = self.model.fusion_heads
+        if fh == 0:        # stage_mlp1(x1) + stage_mlp2(x2)
+            return (buf("head.w"), buf("head.b")), (buf("head2.w"), buf("head2.b"))
+        if fh == -1:       # Linear(2d, 1)(cat([x1, x2]))
+            return (buf("head.w")[:d], buf("head.b")), (buf("head.w")[d:], None)
+        return (buf("head.w"), buf("head.b")), (buf("head.w"), None)     # -2: Linear(d, 1)(x1 + x2)
 
     def _tower_forward(self, tw, sv, usr_image, usr_mask, vid_image, vid_mask, usr_id, vid_id):
         cfg, k, bb = self.cfg, tw.k, tw.m
@@ -510,10 +531,19 @@ class Engine:
             self.g("bias_weight").add_(db[0] * gs)
             self.g("bias_bias").add_(db[1] * gs)
         dX_out = []
-        if self.fusion is None:
+        if self.fusion is None and len(sv["x_out"]) == 1:
             dx = self._buf("bw.dx.b1.vid", (R, d), T)
             ops.head_bwd(sv["x_out"][0], R, d, self.w("head.w"), sv["dlogits"], gscale, dx, self.g("head.w"), self.g("head.b"), self.red_ws)
             dX_out.append(dx)
+            if on_ready is not None:
+                on_ready(self.groups["head.w"][0])
+        elif self.fusion is None:
+            (w1, _), (w2, _) = self._two_head_params()
+            (g1, gb1), (g2, gb2) = self._two_head_params(grad=True)
+            dx1, dx2 = self._buf("bw.dx.b1.vid", (R, d), T), self._buf("bw.dx.b2.vid", (R, d), T)
+            ops.head_bwd(sv["x_out"][0], R, d, w1, sv["dlogits"], gscale, dx1, g1, gb1, self.red_ws)
+            ops.head_bwd(sv["x_out"][1], R, d, w2, sv["dlogits"], gscale, dx2, g2, gb2, self.red_ws)
+            dX_out = [dx1, dx2]
             if on_ready is not None:
                 on_ready(self.groups["head.w"][0])
         else:

@@ -219,12 +219,23 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
             self.stage_mlp1 = nn.Linear(d_model, 1)
             nn.init.xavier_uniform_(self.stage_mlp1.weight.data)  # kn_util/nn_utils/init.py:52-62
             self.stage_mlp1.bias.data.zero_()
-        else:
+        else:                                          # models/decoder_leave_focal.py:457-470
             fh = getattr(model_cfg, "fusion_heads", 2)
-            if fh <= 0:
-                raise NotImplementedError(f"fusion_heads={fh}: only the InteractionAggregation fusion (fusion_heads > 0, the "
-                                          "reference default 2) is built")
-            self.fusion_module = InteractionAggregation(d_model, d_model, output_dim=1, num_heads=fh)
+            if fh > 0:
+                self.fusion_module = InteractionAggregation(d_model, d_model, output_dim=1, num_heads=fh)
+            elif fh in (0, -1, -2):
+                self.stage_mlp1 = nn.Linear(2 * d_model if fh == -1 else d_model, 1)
+                heads = [self.stage_mlp1]
+                if fh == 0:
+                    self.stage_mlp2 = nn.Linear(d_model, 1)
+                    heads.append(self.stage_mlp2)
+                for lin in heads:
+                    nn.init.xavier_uniform_(lin.weight.data)
+                    lin.bias.data.zero_()
+            else:
+                raise NotImplementedError(f"fusion_heads={fh}: -3 concatenates the two output LISTS and so scores backbone2 alone "
+                                          "(decoder_leave_focal.py:621-623); not built")
+            self.fusion_heads = fh
         self._engine = None
         self.precision = getattr(model_cfg, "mmi_precision", "fp32")
 

@@ -170,9 +170,10 @@ class AttnSide:
         LaunchCounter.n += 1
 
 
-def head_fwd(x, rows, d, w, b, logits):
+def head_fwd(x, rows, d, w, b, logits, add=None):
+    """logits[r] = w . x[r] (+ b) (+ add[r])"""
     with TIMER.region("head"):
-        rc = _lib.load().mmi_head_fwd(x.data_ptr(), dt(x), rows, d, w.data_ptr(), b.data_ptr(), logits.data_ptr(), _stream())
+        rc = _lib.load().mmi_head_fwd(x.data_ptr(), dt(x), rows, d, w.data_ptr(), _ptr(b), _ptr(add), logits.data_ptr(), _stream())
     _lib.check(rc, "mmi_head_fwd")
     LaunchCounter.n += 1
 
@@ -182,7 +183,7 @@ def head_bwd(x, rows, d, w, dlogits, gscale, dx, dw, db, ws):
     assert ws.numel() >= lib.mmi_head_bwd_workspace(d)
     with TIMER.region("head"):
         rc = lib.mmi_head_bwd(x.data_ptr(), dt(x), rows, d, w.data_ptr(), dlogits.data_ptr(), _ptr(gscale), dx.data_ptr(),
-                              dw.data_ptr(), db.data_ptr(), ws.data_ptr(), _stream())
+                              dw.data_ptr(), _ptr(db), ws.data_ptr(), _stream())
     _lib.check(rc, "mmi_head_bwd")
     LaunchCounter.n += 2
 

@@ -234,7 +234,7 @@ def test_all_selectable_losses_through_the_model_vs_oracle(precision):
             assert _rel(p.grad.cpu().numpy(), osd[k].grad.numpy()) < 3 * tol, k
 
 
-@pytest.mark.parametrize("name", ["model_both_small", "model_id_small"])
+@pytest.mark.parametrize("name", ["model_both_small", "model_id_small", "model_both_fh0", "model_both_fh-1", "model_both_fh-2"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_general_config_vs_reference_golden(name, precision):
     """ID-embedding inputs and the reference's default 'both' configuration (image backbone + ID backbone

@@ -54,7 +54,7 @@ def test_model_small_matches_reference(name):
     assert _rel(inf["logits"].numpy(), z["logits_inference"]) < 1e-5
 
 
-@pytest.mark.parametrize("name", ["model_both_small", "model_id_small"])
+@pytest.mark.parametrize("name", ["model_both_small", "model_id_small", "model_both_fh0", "model_both_fh-1", "model_both_fh-2"])
 def test_general_config_matches_reference(name):
     """ID-embedding inputs, two backbones + InteractionAggregation (the reference default 'both'),
     interestBPR: the oracle against the unmodified reference."""

@@ -29,9 +29,9 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 
 def run_model_case(name, d_model, nhead, nlayers, din, Lt, B, seed, store_sd=True, loss_types=("focal",),
-                   fill_seed=None):
+                   fill_seed=None, ablation_type="ours"):
     args = ref_shim.make_args(d_model=d_model, nhead=nhead, num_layers_enc=nlayers,
-                              loss_type_list=list(loss_types))
+                              loss_type_list=list(loss_types), ablation_type=ablation_type)
     model = ref_shim.build_reference_model(args, din=din, max_usr_len=Lt, seed=seed)
     if fill_seed is not None:
         shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
@@ -56,7 +56,7 @@ def run_model_case(name, d_model, nhead, nlayers, din, Lt, B, seed, store_sd=Tru
     out = ref_shim.run_reference(model, batch, mode="train")
     out["loss"].backward()
     save = dict(cfg=json.dumps(dict(d_model=d_model, nhead=nhead, num_layers_enc=nlayers, din=din, Lt=Lt, B=B,
-                                    seed=seed, loss_types=list(loss_types), fill_seed=fill_seed)),
+                                    seed=seed, loss_types=list(loss_types), fill_seed=fill_seed, ablation_type=ablation_type)),
                 usr_mask=usr_mask, vid_mask=vid_mask, gt_in=gt,
                 logits=out["logits"].detach().numpy(), gt_out=out["gt"].numpy(),
                 loss=np.float64(out["loss"].item()), mse=np.float64(out["mse"].item()),
@@ -311,6 +311,12 @@ def run_general_cases():
     run_fusion_variants()
 
 
+def run_ablation_cases():
+    """encoder ablations that select one attention block per query side (encoder.py:108-135,172-175)"""
+    run_model_case("model_small_crossatt", d_model=64, nhead=2, nlayers=4, din=48, Lt=12, B=5, seed=41, ablation_type="CrossAtt")
+    run_model_case("model_small_selfatt", d_model=64, nhead=2, nlayers=3, din=48, Lt=12, B=5, seed=42, ablation_type="SelfAtt")
+
+
 def run_fusion_variants():
     """the other fusions of forward (decoder_leave_focal.py:624-634): fusion_heads 0 (two Linear heads summed), -1 (one
     Linear(2d, 1) over the concatenation), -2 (one Linear head over the sum of the two backbones)"""
@@ -328,5 +334,7 @@ if __name__ == "__main__":
         run_eval_case()
     elif "--fusion-only" in sys.argv:
         run_fusion_variants()
+    elif "--ablation-only" in sys.argv:
+        run_ablation_cases()
     else:
         main()

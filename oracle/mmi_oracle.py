@@ -77,31 +77,40 @@ def attn_logits(sd, p, feat_k, mask_k, feat_q, mask_q, nhead):
 # --------------------------------------------------------------------------
 # a-6  four-way attention + output projection + residual LN
 # --------------------------------------------------------------------------
-def cross_attention(sd, p, vid, vid_mask, usr, usr_mask, nhead, need_usr=True):
-    """models/encoder.py:75-175 with sr_ratio=1, ablation 'ours', dropout off.
-    Joint softmax over [v2v | t2v] for candidate queries and [v2t | t2t] for
-    history queries; scale 1/sqrt(dh) is applied AFTER the mask fill."""
+# which attention blocks feed the candidate ("vid") / history ("usr") queries per ablation (encoder.py:108-161,172-175)
+ATTN_BLOCKS = {"ours": (("v2v", "t2v"), ("v2t", "t2t")), "CrossAtt": (("t2v",), ("v2t",)), "SelfAtt": (("v2v",), None)}
+
+
+def attn_ablation(ablation_type):
+    """the reference tests `'CrossAtt' in ablation_type` / `'SelfAtt' in ablation_type` (substring, so 'noUser_SelfAtt' is
+    SelfAtt for the model; the 'noUser' half lives in the driver, main...SegMM.py:275-277)"""
+    a = ablation_type or "ours"
+    return "CrossAtt" if "CrossAtt" in a else ("SelfAtt" if "SelfAtt" in a else "ours")
+
+
+def cross_attention(sd, p, vid, vid_mask, usr, usr_mask, nhead, need_usr=True, ablation="ours"):
+    """models/encoder.py:75-175 with sr_ratio=1, dropout off.  'ours': joint softmax over [v2v | t2v] for candidate
+    queries and [v2t | t2t] for history queries; 'CrossAtt' keeps t2v / v2t only, 'SelfAtt' keeps v2v only and returns
+    no history update (:172-173).  The scale 1/sqrt(dh) is applied AFTER the mask fill."""
     B, Lv, d = vid.shape
     dh = d // nhead
     scale = 1.0 / math.sqrt(dh)
+    key_side = {"v2v": (vid, vid_mask), "t2v": (usr, usr_mask), "v2t": (vid, vid_mask), "t2t": (usr, usr_mask)}
+    names_v, names_t = ATTN_BLOCKS[ablation]
 
     def val(name, x):
         return F.linear(x, sd[p + name + "_proj.2.weight"], sd[p + name + "_proj.2.bias"])
 
-    v_logits = torch.cat([attn_logits(sd, p + "v2v_proj.", vid, vid_mask, vid, vid_mask, nhead),
-                          attn_logits(sd, p + "t2v_proj.", usr, usr_mask, vid, vid_mask, nhead)], -1) * scale
-    v_value = torch.cat([val("v2v", vid), val("t2v", usr)], 1).view(B, -1, nhead, dh)
-    vid_ = torch.einsum("bhqk,bkhd->bqhd", F.softmax(v_logits, -1), v_value).reshape(B, Lv, d)
-    vid_ = F.linear(vid_, sd[p + "ff_vid.weight"], sd[p + "ff_vid.bias"])
+    def attend(names, q, q_mask):
+        logits = torch.cat([attn_logits(sd, p + n + "_proj.", key_side[n][0], key_side[n][1], q, q_mask, nhead) for n in names], -1) * scale
+        value = torch.cat([val(n, key_side[n][0]) for n in names], 1).view(B, -1, nhead, dh)
+        return torch.einsum("bhqk,bkhd->bqhd", F.softmax(logits, -1), value).reshape(B, q.shape[1], d)
+
+    vid_ = F.linear(attend(names_v, vid, vid_mask), sd[p + "ff_vid.weight"], sd[p + "ff_vid.bias"])
     vid_out = F.layer_norm(vid + vid_, (d,), sd[p + "ln_vid.weight"], sd[p + "ln_vid.bias"], 1e-12)
-    if not need_usr:
+    if not need_usr or names_t is None:
         return vid_out, None
-    Lt = usr.shape[1]
-    t_logits = torch.cat([attn_logits(sd, p + "v2t_proj.", vid, vid_mask, usr, usr_mask, nhead),
-                          attn_logits(sd, p + "t2t_proj.", usr, usr_mask, usr, usr_mask, nhead)], -1) * scale
-    t_value = torch.cat([val("v2t", vid), val("t2t", usr)], 1).view(B, -1, nhead, dh)
-    usr_ = torch.einsum("bhqk,bkhd->bqhd", F.softmax(t_logits, -1), t_value).reshape(B, Lt, d)
-    usr_ = F.linear(usr_, sd[p + "ff_usr.weight"], sd[p + "ff_usr.bias"])
+    usr_ = F.linear(attend(names_t, usr, usr_mask), sd[p + "ff_usr.weight"], sd[p + "ff_usr.bias"])
     usr_out = F.layer_norm(usr + usr_, (d,), sd[p + "ln_usr.weight"], sd[p + "ln_usr.bias"], 1e-12)
     return vid_out, usr_out
 
@@ -121,7 +130,7 @@ def ffn(sd, p, side, x):
 # --------------------------------------------------------------------------
 # a-8  encoder stack; output = INPUT of the last layer
 # --------------------------------------------------------------------------
-def backbone(sd, prefix, usr, usr_mask, vid, vid_mask, nhead, num_layers, use_pe=True):
+def backbone(sd, prefix, usr, usr_mask, vid, vid_mask, nhead, num_layers, use_pe=True, ablation="ours"):
     """models/encoder.py:302-324,475-520.  intermediate_states records vid_feat
     BEFORE each layer and the caller takes [-1], so layer N-1 never reaches the
     output, nor does the history side of layer N-2."""
@@ -131,9 +140,9 @@ def backbone(sd, prefix, usr, usr_mask, vid, vid_mask, nhead, num_layers, use_pe
     for i in range(num_layers - 1):
         p = f"{prefix}encoder.layers.{i}."
         need_usr = i < num_layers - 2
-        v, u2 = cross_attention(sd, p + "cross_attn.", v, vid_mask, u, usr_mask, nhead, need_usr)
+        v, u2 = cross_attention(sd, p + "cross_attn.", v, vid_mask, u, usr_mask, nhead, need_usr, ablation)
         v = ffn(sd, p, "vid", v)
-        if need_usr:
+        if u2 is not None:          # SelfAtt: the history tokens are never updated (encoder.py:320-321)
             u = ffn(sd, p, "usr", u2)
     return v
 
@@ -302,7 +311,7 @@ def compute_loss(logits, gt, exposure_prob, loss_type_list=("focal",), loss_weig
 # --------------------------------------------------------------------------
 def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_layers,
             exposure_prob=None, loss_type_list=("focal",), use_pe=True, mode="train", loss_weight=None,
-            usr_id=None, vid_id=None, input_type=None, fusion_heads=2, mask_loss=0):
+            usr_id=None, vid_id=None, input_type=None, fusion_heads=2, mask_loss=0, ablation_type="ours"):
     """models/decoder_leave_focal.py:574-658.  input_type {'user': image|id|both, 'photo': image|id|both}
     (default image/image, single backbone, Linear head); with a 'both' entry there are two backbones
     (main...SegMM.py:63-106: backbone1 takes the image side of a 'both' input, backbone2 the id side) fused by
@@ -315,11 +324,12 @@ def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_laye
             return image if which == 1 else ident
         return image if kind == "image" else ident
 
+    abl = attn_ablation(ablation_type)
     x1 = backbone(sd, "backbone1.", pick(it["user"], usr_image, usr_id, 1), usr_mask.bool(),
-                  pick(it["photo"], vid_image, vid_id, 1), vid_mask.bool(), nhead, num_layers, use_pe)
+                  pick(it["photo"], vid_image, vid_id, 1), vid_mask.bool(), nhead, num_layers, use_pe, abl)
     if two:
         x2 = backbone(sd, "backbone2.", pick(it["user"], usr_image, usr_id, 2), usr_mask.bool(),
-                      pick(it["photo"], vid_image, vid_id, 2), vid_mask.bool(), nhead, num_layers, use_pe)
+                      pick(it["photo"], vid_image, vid_id, 2), vid_mask.bool(), nhead, num_layers, use_pe, abl)
         if fusion_heads > 0:
             logits = fusion_logits(sd, x1, x2, fusion_heads)
         elif fusion_heads == 0:      # models/decoder_leave_focal.py:630-631: stage_mlp1(x1) + stage_mlp2(x2)
@@ -339,15 +349,21 @@ def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_laye
     return compute_loss(logits, gt, exposure_prob, loss_type_list, loss_weight, mask_loss=mask_loss)
 
 
-def live_param_names(sd_keys, num_layers):
+def live_param_names(sd_keys, num_layers, ablation_type="ours"):
     """Names of parameters that receive a gradient in the reference (SURVEY
     section 0 fact 5): everything except layer N-1, the history side of layer
     N-2 (its v2t/t2t projections, ff_usr, ln_usr), and the never-called
-    pe_lns / txt_lvl_projs / patch_merge."""
+    pe_lns / txt_lvl_projs / patch_merge.  Ablations: 'CrossAtt' never uses v2v / t2t; 'SelfAtt' never uses the history
+    tokens at all (t2v / v2t / t2t, every *_usr module, usr_proj / usr_pe / usr_ln)."""
     live = []
     N = num_layers
+    abl = attn_ablation(ablation_type)
     for k in sd_keys:
         if any(s in k for s in ("pe_lns", "txt_lvl_projs", "patch_merge")):
+            continue
+        if abl == "SelfAtt" and any(s in k for s in ("usr_proj", "usr_pe", "usr_ln", "t2v_proj", "v2t_proj", "t2t_proj", "ff_usr", "ln_usr")):
+            continue
+        if abl == "CrossAtt" and any(s in k for s in ("v2v_proj", "t2t_proj")):
             continue
         if ".encoder.layers." in k:
             i = int(k.split(".encoder.layers.")[1].split(".")[0])
@@ -359,9 +375,6 @@ def live_param_names(sd_keys, num_layers):
     return live
 
 
-# --------------------------------------------------------------------------
-# a-14  step tail: global-norm clip + AdamW
-# --------------------------------------------------------------------------
 def clip_and_adamw(params, grads, exp_avg, exp_avg_sq, step, lr=1e-3, wd=1e-4, betas=(0.9, 0.999),
                    eps=1e-8, max_norm=10.0):
     """main_for_seq_leave_earlystop_SegMM.py:298-299: clip_grad_norm_(10.0) then

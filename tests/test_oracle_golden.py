@@ -23,14 +23,15 @@ def _rel(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
 
 
-@pytest.mark.parametrize("name", ["model_small_dh32", "model_small_dh16"])
+@pytest.mark.parametrize("name", ["model_small_dh32", "model_small_dh16", "model_small_crossatt", "model_small_selfatt"])
 def test_model_small_matches_reference(name):
     z = _load(name)
     cfg = json.loads(str(z["cfg"]))
+    abl = cfg.get("ablation_type", "ours")
     sd = {k[3:]: torch.from_numpy(z[k]).clone().requires_grad_(True) for k in z.files if k.startswith("sd/")}
     out = mmi_oracle.forward(sd, torch.from_numpy(z["usr_image"]), torch.from_numpy(z["usr_mask"]),
                              torch.from_numpy(z["vid_image"]), torch.from_numpy(z["vid_mask"]),
-                             torch.from_numpy(z["gt_in"]), nhead=cfg["nhead"], num_layers=cfg["num_layers_enc"])
+                             torch.from_numpy(z["gt_in"]), nhead=cfg["nhead"], num_layers=cfg["num_layers_enc"], ablation_type=abl)
     assert _rel(out["logits"].detach().numpy(), z["logits"]) < 1e-5
     assert abs(out["loss"].item() - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
     assert abs(out["mse"].item() - float(z["mse"])) <= 1e-5 * abs(float(z["mse"]))
@@ -38,19 +39,21 @@ def test_model_small_matches_reference(name):
     assert np.array_equal(out["gt"].numpy(), z["gt_out"])
     out["loss"].backward()
     dead = set(json.loads(str(z["dead_params"])))
-    live = set(mmi_oracle.live_param_names(list(sd.keys()), cfg["num_layers_enc"]))
+    live = set(mmi_oracle.live_param_names(list(sd.keys()), cfg["num_layers_enc"], abl))
     named_params = {k for k in sd if ("grad/" + k) in z.files} | dead
     assert live == {k for k in named_params if k not in dead}
     for k in sorted(live):
         g = sd[k].grad
         assert g is not None, k
-        assert _rel(g.numpy(), z["grad/" + k]) < 2e-5, k
+        # single-block ablations: a key-projection bias shifts every logit of a query row by the same amount, so its
+        # gradient is exactly zero in exact arithmetic -- both sides hold ~1e-9 rounding noise there (absolute floor)
+        assert np.linalg.norm(g.numpy() - z["grad/" + k]) < 2e-5 * np.linalg.norm(z["grad/" + k]) + 1e-8, k
     for k in dead:
         assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
     inf = mmi_oracle.forward({k: v.detach() for k, v in sd.items()}, torch.from_numpy(z["usr_image"]),
                              torch.from_numpy(z["usr_mask"]), torch.from_numpy(z["vid_image"]),
                              torch.from_numpy(z["vid_mask"]), torch.from_numpy(z["gt_in"]), nhead=cfg["nhead"],
-                             num_layers=cfg["num_layers_enc"], mode="inference")
+                             num_layers=cfg["num_layers_enc"], mode="inference", ablation_type=abl)
     assert _rel(inf["logits"].numpy(), z["logits_inference"]) < 1e-5
 
 

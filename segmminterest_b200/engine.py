@@ -23,6 +23,24 @@ from .ops import ACT_GELU, ACT_NONE, GEMM_NN, GEMM_NT, GEMM_TN, IMPL_SIMT, IMPL_
 
 ALIGN = 64  # floats (256 B): every parameter group starts on a TMA-friendly boundary
 
+# The four attention blocks of SegFormerXAttention (models/encoder.py:17-24): projection j of block n (0 = query, 1 = key,
+# 2 = value).  Q_SIDE / KEY_SIDE: which tokens the query / the key+value projections read.  PROJ_ORDER: the order in which
+# the projections of one token side sit in the flat parameter buffer, so that the ones in use form ONE fused GEMM.
+Q_SIDE = {"v2v": "vid", "t2v": "vid", "v2t": "usr", "t2t": "usr"}
+KEY_SIDE = {"v2v": "vid", "t2v": "usr", "v2t": "vid", "t2t": "usr"}
+PROJ_ORDER = {"vid": [("v2v", 0), ("v2v", 1), ("v2v", 2), ("t2v", 0), ("v2t", 1), ("v2t", 2)],
+              "usr": [("t2v", 1), ("t2v", 2), ("v2t", 0), ("t2t", 0), ("t2t", 1), ("t2t", 2)]}
+# blocks that feed the candidate / history queries per ablation (encoder.py:108-161; 'SelfAtt' returns no history update)
+ATTN_BLOCKS = {"ours": {"vid": ("v2v", "t2v"), "usr": ("v2t", "t2t")},
+               "CrossAtt": {"vid": ("t2v",), "usr": ("v2t",)},
+               "SelfAtt": {"vid": ("v2v",), "usr": ()}}
+
+
+def attn_ablation(ablation_type):
+    """the reference tests substrings ('noUser_SelfAtt' is SelfAtt for the model; 'noUser' lives in the driver)"""
+    a = ablation_type or "ours"
+    return "CrossAtt" if "CrossAtt" in a else ("SelfAtt" if "SelfAtt" in a else "ours")
+
 
 @dataclass
 class EngineConfig:
@@ -35,6 +53,7 @@ class EngineConfig:
     max_vid_len: int = 40
     use_pe: bool = True
     precision: str = "fp32"   # 'fp32' (FFMA, strict parity) | 'bf16' (tcgen05 tensor cores)
+    ablation: str = "ours"    # 'ours' | 'CrossAtt' | 'SelfAtt'
 
 
 class _View:
@@ -102,6 +121,18 @@ class Engine:
         self.red_ws = torch.empty(int(n_red), device=device, dtype=torch.float32)
         self.scalars = torch.zeros(16, device=device, dtype=torch.float32)
 
+    def layer_plan(self, i):
+        """(query sides that are computed in layer i, {token side: [(block, j), ...] projections in buffer order})."""
+        blocks = ATTN_BLOCKS[self.cfg.ablation]
+        full = i < self.cfg.num_layers - 2          # the history side of layer N-2 never reaches the output
+        qsides = tuple(s for s in ("vid", "usr") if blocks[s] and (s == "vid" or full))
+        active = {n for s in qsides for n in blocks[s]}
+        return qsides, {side: [(n, j) for n, j in PROJ_ORDER[side] if n in active] for side in ("vid", "usr")}
+
+    @property
+    def uses_history(self):
+        return self.cfg.ablation != "SelfAtt"
+
     # ------------------------------------------------------------------ parameter layout
     def _layout(self):
         cfg = self.cfg
@@ -125,30 +156,29 @@ class Engine:
                 group(k("frameid.b"), [(P + "frameid_proj.bias", bb.frameid_proj.bias)])
             else:
                 group(k("vid_proj.b"), [(P + "vid_proj.bias", bb.vid_proj.bias)])
-            group(k("usr_proj.w"), [(P + "usr_proj.weight", bb.usr_proj.weight)])
-            if tw.usr_kind == "image":
-                group(k("usr_proj.b"), [(P + "usr_proj.bias", bb.usr_proj.bias)])
+            token_sides = ("vid", "usr") if self.uses_history else ("vid",)   # SelfAtt never reads the history tokens
+            if "usr" in token_sides:
+                group(k("usr_proj.w"), [(P + "usr_proj.weight", bb.usr_proj.weight)])
+                if tw.usr_kind == "image":
+                    group(k("usr_proj.b"), [(P + "usr_proj.bias", bb.usr_proj.bias)])
             if cfg.use_pe:
-                group(k("vid_pe"), [(P + "vid_pe.weight", bb.vid_pe.weight)])
-                group(k("usr_pe"), [(P + "usr_pe.weight", bb.usr_pe.weight)])
-            for s in ("vid", "usr"):
+                for s in token_sides:
+                    group(k(f"{s}_pe"), [(f"{P}{s}_pe.weight", getattr(bb, s + "_pe").weight)])
+            for s in token_sides:
                 ln = getattr(bb, s + "_ln")
                 group(k(f"{s}_ln.g"), [(f"{P}{s}_ln.weight", ln.weight)])
                 group(k(f"{s}_ln.b"), [(f"{P}{s}_ln.bias", ln.bias)])
             for i in range(N - 1):
                 L = bb.encoder.layers[i]
                 ca = L.cross_attn
-                full = i < N - 2
+                qsides, projs = self.layer_plan(i)
                 q = f"{P}encoder.layers.{i}."
-                # six projections of the candidate tokens / of the history tokens, adjacent
-                vid6 = [("v2v", 0), ("v2v", 1), ("v2v", 2), ("t2v", 0), ("v2t", 1), ("v2t", 2)]
-                usr6 = [("t2v", 1), ("t2v", 2), ("v2t", 0), ("t2t", 0), ("t2t", 1), ("t2t", 2)]
-                if not full:
-                    vid6, usr6 = vid6[:4], usr6[:2]
-                for side, six in (("vid", vid6), ("usr", usr6)):
-                    group(k(f"L{i}.{side}.w6"), [(f"{q}cross_attn.{b}_proj.{j}.weight", getattr(ca, b + "_proj")[j].weight) for b, j in six])
-                    group(k(f"L{i}.{side}.b6"), [(f"{q}cross_attn.{b}_proj.{j}.bias", getattr(ca, b + "_proj")[j].bias) for b, j in six])
-                for side in (("vid", "usr") if full else ("vid",)):
+                # the projections in use of the candidate tokens / of the history tokens, adjacent (one fused GEMM each)
+                for side in ("vid", "usr"):
+                    if projs[side]:
+                        group(k(f"L{i}.{side}.w6"), [(f"{q}cross_attn.{b}_proj.{j}.weight", getattr(ca, b + "_proj")[j].weight) for b, j in projs[side]])
+                        group(k(f"L{i}.{side}.b6"), [(f"{q}cross_attn.{b}_proj.{j}.bias", getattr(ca, b + "_proj")[j].bias) for b, j in projs[side]])
+                for side in qsides:
                     ff, ln = getattr(ca, "ff_" + side), getattr(ca, "ln_" + side)
                     group(k(f"L{i}.{side}.wo"), [(f"{q}cross_attn.ff_{side}.weight", ff.weight)])
                     group(k(f"L{i}.{side}.bo"), [(f"{q}cross_attn.ff_{side}.bias", ff.bias)])
@@ -387,14 +417,17 @@ class Engine:
         Ls = {"usr": Lt, "vid": Lv}
         Ts = {"usr": B * Lt, "vid": B * Lv}
         mask = {"vid": vid_mask.to(torch.bool).contiguous().view(torch.uint8)}
-        if tw.usr_kind == "id":       # one token per user, mask of ones (encoder.py:478-481)
+        token_sides = ("vid", "usr") if self.uses_history else ("vid",)
+        if "usr" not in token_sides:
+            pass
+        elif tw.usr_kind == "id":       # one token per user, mask of ones (encoder.py:478-481)
             mask["usr"] = self._buf(k("ones_mask"), (B, 1), torch.uint8)
             mask["usr"].fill_(1)
         else:
             mask["usr"] = usr_mask.to(torch.bool).contiguous().view(torch.uint8)
         ts = {"B": B, "Lt": Lt, "Lv": Lv, "mask": mask, "layers": [], "x_in": {}, "ids": {}}
         X = {}
-        for s in ("vid", "usr"):
+        for s in token_sides:
             kind = tw.vid_kind if s == "vid" else tw.usr_kind
             e = self._buf(k(f"emb_pre.{s}"), (Ts[s], d), T)
             st = self._buf(k(f"emb_st.{s}"), (Ts[s], 2), torch.float32)
@@ -424,29 +457,28 @@ class Engine:
             X[s] = x0
         esz = x0.element_size()
         for i in range(N - 1):
-            full = i < N - 2
-            nq = {"vid": 6 if full else 4, "usr": 6 if full else 2}
-            lay = {"full": full, "nq": nq, "x": dict(X)}
+            sides, projs = self.layer_plan(i)
+            nq = {s: len(projs[s]) for s in ("vid", "usr")}
+            cols = {s: {pj: c for c, pj in enumerate(projs[s])} for s in ("vid", "usr")}
+            lay = {"sides": sides, "nq": nq, "cols": cols, "x": dict(X)}
             qkv = {}
-            for s in ("vid", "usr"):
-                qkv[s] = self._buf(k(f"qkv.{i}.{s}"), (Ts[s], nq[s] * d), T)
-                self._linear(X[s], Ts[s], d, k(f"L{i}.{s}.w6"), k(f"L{i}.{s}.b6"), nq[s] * d, qkv[s])
+            for s in token_sides:
+                if nq[s]:
+                    qkv[s] = self._buf(k(f"qkv.{i}.{s}"), (Ts[s], nq[s] * d), T)
+                    self._linear(X[s], Ts[s], d, k(f"L{i}.{s}.w6"), k(f"L{i}.{s}.b6"), nq[s] * d, qkv[s])
             lay["qkv"] = qkv
 
-            def col(s, j):
-                return (qkv[s].data_ptr() + j * d * esz, nq[s] * d)
+            def col(n, j):
+                """(pointer, leading dimension) of projection j of block n inside the fused projection buffer of its side"""
+                s_ = Q_SIDE[n] if j == 0 else KEY_SIDE[n]
+                return (qkv[s_].data_ptr() + cols[s_][(n, j)] * d * esz, nq[s_] * d)
 
-            sides = ("vid", "usr") if full else ("vid",)
             attn = {}
             for s in sides:
                 a_out = self._buf(k(f"attn.{i}.{s}"), (Ts[s], d), T)
                 lse = self._buf(k(f"lse.{i}.{s}"), (B, H, Ls[s]), torch.float32)
-                if s == "vid":
-                    blocks = [dict(q=col("vid", 0), k=col("vid", 1), v=col("vid", 2), mask_k=mask["vid"], Lk=Lv),
-                              dict(q=col("vid", 3), k=col("usr", 0), v=col("usr", 1), mask_k=mask["usr"], Lk=Lt)]
-                else:
-                    blocks = [dict(q=col("usr", 2), k=col("vid", 4), v=col("vid", 5), mask_k=mask["vid"], Lk=Lv),
-                              dict(q=col("usr", 3), k=col("usr", 4), v=col("usr", 5), mask_k=mask["usr"], Lk=Lt)]
+                blocks = [dict(q=col(n, 0), k=col(n, 1), v=col(n, 2), mask_k=mask[KEY_SIDE[n]], Lk=Ls[KEY_SIDE[n]])
+                          for n in ATTN_BLOCKS[cfg.ablation][s]]
                 attn_impl = IMPL_TC if (self.use_tc and d // H == 32 and d % 8 == 0) else IMPL_SIMT
                 side = ops.AttnSide(ops.dt(a_out), attn_impl, B, H, d // H, Ls[s], mask[s], a_out, d, lse, blocks)
                 side.fwd()
@@ -594,10 +626,10 @@ class Engine:
             return self._buf(f"bw.{name}.{tw.tag}.{s}.{width}", (Ts[s], width), T)
 
         dX = {"vid": dx_out, "usr": None}
+        token_sides = ("vid", "usr") if self.uses_history else ("vid",)
         for i in reversed(range(N - 1)):
             lay = ts["layers"][i]
-            full, nq, Xin = lay["full"], lay["nq"], lay["x"]
-            sides = ("vid", "usr") if full else ("vid",)
+            sides, nq, cols, Xin = lay["sides"], lay["nq"], lay["cols"], lay["x"]
             dP1, dA = {}, {}
             for s in sides:
                 a = lay[s]
@@ -615,46 +647,48 @@ class Engine:
                 da = scratch("da", s)
                 self._linear_bwd(dp1, lay["attn"][s][1], Ts[s], d, d, pre + "wo", pre + "bo", da, bias_done=True)
                 dP1[s], dA[s] = dp1, da
-            dqkv = {s: scratch("dqkv", s, nq[s] * d) for s in ("vid", "usr")}
+            dqkv = {s: scratch("dqkv", s, nq[s] * d) for s in token_sides if nq[s]}
             esz = dqkv["vid"].element_size()
-
-            def gcol(s, j):
-                return (dqkv[s].data_ptr() + j * d * esz, nq[s] * d)
-
             # tensor-core attention: the backward kernels add the fp32 column sums of dq / dk / dv (= the bias gradients of
-            # the six fused projections) straight into the flat gradient buffer, so dqkv is not re-read by a colsum pass
+            # the fused projections) straight into the flat gradient buffer, so dqkv is not re-read by a colsum pass
             fused_bias = all(lay["attn"][s][0].a.impl == IMPL_TC for s in sides)
-            gb6 = {s: self.g(k(f"L{i}.{s}.b6")) for s in ("vid", "usr")}
+            gb6 = {s: self.g(k(f"L{i}.{s}.b6")) for s in dqkv}
 
-            def bcol(s, j):
-                return gb6[s].data_ptr() + 4 * j * d if fused_bias else None
-
-            def gset(qs, ks, vs):
-                return dict(dq=gcol(*qs), dk=gcol(*ks), dv=gcol(*vs), dbq=bcol(*qs), dbk=bcol(*ks), dbv=bcol(*vs))
+            def gset(n):
+                out = {}
+                for j, (kp, kb) in enumerate((("dq", "dbq"), ("dk", "dbk"), ("dv", "dbv"))):
+                    s_ = Q_SIDE[n] if j == 0 else KEY_SIDE[n]
+                    c = cols[s_][(n, j)]
+                    out[kp] = (dqkv[s_].data_ptr() + c * d * esz, nq[s_] * d)
+                    out[kb] = gb6[s_].data_ptr() + 4 * c * d if fused_bias else None
+                return out
 
             for s in sides:
                 side = lay["attn"][s][0]
                 delta = self._buf(f"delta.{tw.tag}.{s}", (B, H, Ls[s]), torch.float32)
-                if s == "vid":
-                    grads = [gset(("vid", 0), ("vid", 1), ("vid", 2)), gset(("vid", 3), ("usr", 0), ("usr", 1))]
-                else:
-                    grads = [gset(("usr", 2), ("vid", 4), ("vid", 5)), gset(("usr", 3), ("usr", 4), ("usr", 5))]
-                side.set_bwd(dA[s], d, delta, grads)
+                names = ATTN_BLOCKS[cfg.ablation][s]
+                side.set_bwd(dA[s], d, delta, [gset(n) for n in names])
                 side.bwd_dq()
-                side.bwd_dkv(0)
-                side.bwd_dkv(1)
+                for w_ in range(len(names)):
+                    side.bwd_dkv(w_)
             new_dX = {}
-            for s in ("vid", "usr"):
+            for s in token_sides:
                 pre = k(f"L{i}.{s}.")
+                if not nq[s]:          # no projection of these tokens is live in this layer: the gradient passes through
+                    new_dX[s] = dP1.get(s, dX.get(s))
+                    continue
                 out = scratch("dxl", s)
                 # dX[s] (the grad w.r.t. this layer's OUTPUT) is dead by now: dp2 consumed it
-                self._linear_bwd(dqkv[s], Xin[s], Ts[s], nq[s] * d, d, pre + "w6", pre + "b6", out, add=dP1.get(s), bias_done=fused_bias)
+                resid = dP1.get(s)
+                if resid is None and dX.get(s) is not None and s not in sides:
+                    resid = dX[s]      # tokens that are only keys here but were updated by a LATER layer: add that path
+                self._linear_bwd(dqkv[s], Xin[s], Ts[s], nq[s] * d, d, pre + "w6", pre + "b6", out, add=resid, bias_done=fused_bias)
                 new_dX[s] = out
             dX = new_dX
             if on_ready is not None:
                 on_ready(self.groups[k(f"L{i}.vid.w6")][0])  # first group of layer i in the flat layout
-        for s in ("vid", "usr"):
-            if dX[s] is None:
+        for s in token_sides:
+            if dX.get(s) is None:
                 continue
             kind = tw.vid_kind if s == "vid" else tw.usr_kind
             de = self._buf(f"bw.de.{tw.tag}.{s}", (Ts[s], d), T)

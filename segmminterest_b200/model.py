@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .engine import Engine, EngineConfig
+from .engine import Engine, EngineConfig, attn_ablation
 
 PHOTO_MAX = 40
 # loss name -> slot of the fused loss kernel's scalar vector (include/mmi_b200.h, mmi_loss_fwd_bwd)
@@ -112,8 +112,11 @@ class SegFormerX(_Container):
                  video_id_max=-1, use_pe=1):
         super().__init__()
         abl = getattr(model_cfg, "ablation_type", "ours") if model_cfg is not None else "ours"
-        if abl != "ours":
-            raise NotImplementedError(f"ablation_type={abl!r}: only 'ours' is built")
+        if abl not in ("ours", "CrossAtt", "SelfAtt", "noUser", "noUser_SelfAtt"):
+            # 'noUser*' only changes what the DRIVER feeds (random user features, main...SegMM.py:275-277); the MLP ablations
+            # ('SelfMLP', 'CrossMLP', 'w/oAtt') replace the encoder by an MLP_Block and 'noPos' draws a random permutation
+            # of the frame positions per call (encoder.py:392-400,428-429): not built
+            raise NotImplementedError(f"ablation_type={abl!r}: 'ours', 'CrossAtt', 'SelfAtt' (and the driver-side 'noUser' variants) are built")
         if any(use_patch_merge) or any(s != 1 for s in sr_ratio_lvls):
             raise NotImplementedError("patch_merge / sr_ratio>1 are never enabled by the reference drivers")
         if any(d != d_model_in for d in d_model_lvls) or any(f != d_model_in for f in ff_dim_lvls) \
@@ -249,7 +252,8 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
         if self._engine is None or self._engine.device != dev or self._engine.cfg.precision != self.precision:
             cfg = EngineConfig(d_model=bb.d_model, nhead=bb.nhead, num_layers=bb.num_layers_enc,
                                din_vid=bb.input_vid_dim, din_usr=bb.input_usr_dim, max_usr_len=bb.max_usr_len,
-                               max_vid_len=bb.max_vid_len, use_pe=bool(bb.use_pe), precision=self.precision)
+                               max_vid_len=bb.max_vid_len, use_pe=bool(bb.use_pe), precision=self.precision,
+                               ablation=attn_ablation(bb.ablation_type))
             self._engine = Engine(cfg, self, dev)
         self._engine.ensure_bound()
         return self._engine

@@ -39,14 +39,15 @@ def _run(model, usr, usr_mask, vid, vid_mask, gt, dev, mode="train"):
                  gt=torch.from_numpy(gt.copy()).to(dev), mode=mode)
 
 
-@pytest.mark.parametrize("name", ["model_small_dh32", "model_small_dh16"])
+@pytest.mark.parametrize("name", ["model_small_dh32", "model_small_dh16", "model_small_crossatt", "model_small_selfatt"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_small_model_vs_reference_golden(name, precision):
     from segmminterest_b200.model import build_model
     dev = torch.device("cuda:0")
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     cfg = json.loads(str(z["cfg"]))
-    args = make_args(d_model=cfg["d_model"], nhead=cfg["nhead"], num_layers_enc=cfg["num_layers_enc"], mmi_precision=precision)
+    args = make_args(d_model=cfg["d_model"], nhead=cfg["nhead"], num_layers_enc=cfg["num_layers_enc"], mmi_precision=precision,
+                     ablation_type=cfg.get("ablation_type", "ours"))   # CrossAtt / SelfAtt: one attention block per query side
     model = build_model(args, din=cfg["din"], max_usr_len=cfg["Lt"])
     sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
     assert list(model.state_dict().keys()) == list(sd.keys())          # same schema, same order
@@ -65,14 +66,23 @@ def test_small_model_vs_reference_golden(name, precision):
     out["loss"].backward()
     dead = set(json.loads(str(z["dead_params"])))
     worst = 0.0
+    gmax = max(float(np.linalg.norm(z[k])) for k in z.files if k.startswith("grad/"))
+    # bf16 noise floor of the backward pass: a tensor whose gradient is > 4 orders of magnitude below the largest one
+    # (CrossAtt: q/k projections of history queries over 2..10 candidate keys, ||g|| ~ 3e-4 against 12) is compared
+    # against that floor instead of its own norm; fp32 has no floor
+    floor = 0.0 if precision == "fp32" else 2e-5 * gmax
     for k, p in model.named_parameters():
         if k in dead:
             assert p.grad is None, f"{k} must not receive a gradient (dead in the reference)"
         else:
             assert p.grad is not None, k
-            r = _rel(p.grad.cpu().numpy(), z["grad/" + k])
-            worst = max(worst, r)
-            assert r < (tol if precision == "fp32" else 3 * tol), (k, r)
+            ref = z["grad/" + k]
+            if np.linalg.norm(ref) < 1e-7:      # key-projection biases of a single-block softmax: exactly zero in exact
+                assert float(p.grad.abs().max()) < 1e-5, k          # arithmetic, rounding noise on both sides
+                continue
+            err = float(np.linalg.norm(p.grad.double().cpu().numpy() - ref))
+            worst = max(worst, err / float(np.linalg.norm(ref)))
+            assert err < (tol if precision == "fp32" else 3 * tol) * float(np.linalg.norm(ref)) + floor, (k, err, float(np.linalg.norm(ref)))
     inf = _run(model, z["usr_image"], z["usr_mask"], z["vid_image"], z["vid_mask"], z["gt_in"], dev, mode="inference")
     assert _rel(inf["logits"].cpu().numpy(), z["logits_inference"]) < tol
     assert valid.any()

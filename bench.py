@@ -7,6 +7,9 @@
 
 One JSON line on stdout (rank 0).  A "step" = gather+pad+mask+L1-normalise -> forward -> focal loss
 -> backward -> (gradient all-reduce) -> clip + AdamW over one batch of synthetic interactions.
+Both arms run the reference's TRAINING semantics by default: nn.Dropout(0.1) live at every site (--dropout 0.1; the
+driver never overrides SegFormerX's default).  `dropout_off` in the JSON line is the same step with every site off
+(the eval()-mode arithmetic the bit-level parity tests use); --dropout 0 makes that the headline.
 """
 from __future__ import annotations
 
@@ -91,7 +94,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_step_builder(wl, b_cpu, seed=0, threads=None):
+def cpu_step_builder(wl, b_cpu, seed=0, threads=None, dropout=0.0):
     """The reference's training step on host cores, restated by oracle/mmi_oracle.py (the reference
     is pure Python and does not travel to the GPU box; the port is pinned to it by tests/golden)."""
     from oracle import gather_oracle, mmi_oracle
@@ -117,7 +120,8 @@ def cpu_step_builder(wl, b_cpu, seed=0, threads=None):
         c = torch.from_numpy(gather_oracle.l1_normalise(c))
         for p in params:
             p.grad = None
-        out = mmi_oracle.forward(sd, u, torch.from_numpy(um), c, torch.from_numpy(cm), torch.from_numpy(gt), nhead=16, num_layers=6)
+        out = mmi_oracle.forward(sd, u, torch.from_numpy(um), c, torch.from_numpy(cm), torch.from_numpy(gt), nhead=16, num_layers=6,
+                                 drop=mmi_oracle.torch_dropout(dropout) if dropout > 0 else None)
         out["loss"].backward()
         state["step"] += 1
         with torch.no_grad():
@@ -127,13 +131,13 @@ def cpu_step_builder(wl, b_cpu, seed=0, threads=None):
     return step
 
 
-def run_cpu_sample(wl, budget_s, steps, warmup):
+def run_cpu_sample(wl, budget_s, steps, warmup, dropout=0.0):
     """Sizes the sample so (steps+warmup) CPU steps fit in ~budget_s; returns (interactions/s, B, cores, ms/step)."""
-    probe = cpu_step_builder(wl, 2)
+    probe = cpu_step_builder(wl, 2, dropout=dropout)
     t0 = time.perf_counter(); probe(); t1 = time.perf_counter(); probe(); t2 = time.perf_counter()
     per_inter = max((t2 - t1) / 2, 1e-3)
     b = int(max(1, min(32, budget_s / ((steps + warmup) * per_inter))))
-    step = cpu_step_builder(wl, b)
+    step = cpu_step_builder(wl, b, dropout=dropout)
     for _ in range(warmup):
         step()
     ts = []
@@ -148,12 +152,13 @@ def reference_arm(args, wl):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    val, b, cores, ms = run_cpu_sample(wl, 150.0, steps, warmup)
+    val, b, cores, ms = run_cpu_sample(wl, 150.0, steps, warmup, dropout=args.dropout)
+    dnote = f"dropout {args.dropout} (torch generator)" if args.dropout > 0 else "dropout off"
     line = {"impl": "reference", "metric": "train_interactions_per_s", "value": val, "unit": "interactions/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": wl.name, "cpu_batch": b},
+            "dtype": "f32", "data": "synthetic", "config": {"workload": wl.name, "cpu_batch": b, "dropout": args.dropout},
             "cpu_baseline": {"value": val, "unit": "interactions/s", "cores": cores, "kind": "port",
-                             "sample": f"{b} interactions/step of {wl.name} (oracle port of the reference's eager PyTorch step, fp32, dropout off)"},
+                             "sample": f"{b} interactions/step of {wl.name} (oracle port of the reference's eager PyTorch step, fp32, {dnote})"},
             "e2e": {"value": val, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -171,6 +176,8 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=0, help="gradient-accumulation slice (configs 3 / 4: saved activations of a slice must fit in HBM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--dropout", type=float, default=0.1,
+                    help="dropout probability of every nn.Dropout site (reference training default 0.1); 0 = eval()-mode arithmetic")
     args = ap.parse_args()
     wl = synth.WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -200,10 +207,10 @@ def main():
 
     torch.manual_seed(42)
     model = build_model(model_args(args.precision), din=wl.din, max_usr_len=Lt).to(dev)
-    model.eval()  # dropout is not applied by the engine in this round (parity mode, p=0)
+    model.train(args.dropout > 0)   # train(): every nn.Dropout site of the reference is live (counter-based masks, csrc/dropout.cuh)
     g = torch.Generator(device=dev).manual_seed(1234)
     table = torch.randn(wl.n_rows, wl.din, generator=g, device=dev, dtype=torch.float32)
-    ts = TrainStep(model, table, lr=1e-3, weight_decay=1e-4, max_norm=10.0, global_batch=B * world)
+    ts = TrainStep(model, table, lr=1e-3, weight_decay=1e-4, max_norm=10.0, global_batch=B * world, dropout=args.dropout)
 
     n_batches = 4
     host, devb = [], []
@@ -260,6 +267,21 @@ def main():
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_val = K * B * world / (ms_e2e * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    # ---- the same step with every dropout site off (eval()-mode arithmetic of the parity tests) ---------------------------
+    drop_off = None
+    if args.dropout > 0:
+        ts.dropout = 0.0
+        ts.step(*devb[0], micro_batch=mb)
+        barrier()
+        e0.record()
+        for i in range(K):
+            ts.step(*devb[i % n_batches], micro_batch=mb)
+        e1.record()
+        barrier()
+        ms_off = max_over_ranks(e0.elapsed_time(e1))
+        drop_off = {"value": K * B * world / (ms_off * 1e-3), "unit": "interactions/s", "ms_per_step": ms_off / K}
+        ts.dropout = args.dropout
 
     # ---- per-kernel CUDA-event pass for the roofline (one category per kernel AND launch shape) ----------------
     TIMER.enabled = True
@@ -326,17 +348,19 @@ def main():
             "config": {"workload": wl.name, "per_gpu_batch": B, "micro_batch": mb or B, "global_batch": B * world, "hist_len": Lt, "cand_pad": 40,
                        "cand_valid": wl.segs_per_video, "din": wl.din, "d_model": 512, "heads": 16, "layers": 6,
                        "table_rows": wl.n_rows, "parallelism": f"dp{world}", "optimizer": "AdamW lr1e-3 wd1e-4 clip10",
-                       "dropout": "off (parity mode)", "l2": "activations/step >> 126 MB L2 (inputs larger than L2, no flush needed)"},
+                       "dropout": (f"{args.dropout} at every reference site (train() mode; counter-based masks, realised drop probability "
+                                   f"{round(args.dropout * 256) / 256:.4f})" if args.dropout > 0 else "off (eval()-mode arithmetic)"), "l2": "activations/step >> 126 MB L2 (inputs larger than L2, no flush needed)"},
             "e2e": {"value": e2e_val, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "gather_roofline": gather_roof, "gemm_roofline": gemm_roof,
-            "kernel_breakdown": breakdown, "loss_last": loss_last, "use_tc": bool(ts.engine.use_tc)}
+            "kernel_breakdown": breakdown, "loss_last": loss_last, "use_tc": bool(ts.engine.use_tc), "dropout_off": drop_off}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            val, b, cores, ms = run_cpu_sample(wl, args.cpu_budget, 2, 1)
+            val, b, cores, ms = run_cpu_sample(wl, args.cpu_budget, 2, 1, dropout=args.dropout)
             line["cpu_baseline"] = {"value": val, "unit": "interactions/s", "cores": cores, "kind": "port",
                                     "sample": f"{b} interactions/step of {wl.name}, median of 2 steps after 1 warm-up "
-                                              f"({ms:.0f} ms/step; oracle port of the reference's eager PyTorch step, fp32, dropout off)"}
+                                              f"({ms:.0f} ms/step; oracle port of the reference's eager PyTorch step, fp32, "
+                                              + (f"dropout {args.dropout})" if args.dropout > 0 else "dropout off)")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -46,6 +46,21 @@ extern "C" {
 
 typedef void* mmi_stream_t; /* cudaStream_t */
 
+/* ---- dropout (every nn.Dropout(0.1) site of the path: models/encoder.py:386,472 embedding; :145-150 attention logits,
+ * BEFORE the 1/sqrt(dh) scale; :163-164 attention output projection; kn_util/nn_utils/layers/mlp.py:21-22 after the FFN's
+ * GELU; models/encoder.py:198-202 FFN output).  Counter-based: element (row, col) of a site is kept iff
+ * bit (col & 31) of keep_word(key, row, col >> 5) is set (segmminterest_b200/csrc/dropout.cuh; numpy twin in
+ * oracle/dropout_ref.py), so forward and backward regenerate the same mask and none is stored.  thr8 = 0 switches the
+ * site off; otherwise the drop probability is thr8 / 256 and scale must be 256 / (256 - thr8).                      */
+typedef struct {
+  uint32_t key;    /* per site and per step (host: segmminterest_b200/dropout.py site_key)  */
+  uint32_t thr8;   /* 0 = off                                                                */
+  float scale;     /* 1 / realised keep probability                                          */
+} mmi_dropout;
+/* test hook: mask[r * cols + c] = 1 iff element (row0 + r, c) is kept (group of column c = group0 + (c >> 5)).       */
+int mmi_dropout_mask(const mmi_dropout* drop, int64_t row0, int64_t rows, int cols, uint32_t group0, uint8_t* mask,
+                     mmi_stream_t stream);
+
 int mmi_version(void);
 const char* mmi_last_error(void);
 /* 1 if the tcgen05 GEMM path was compiled in and the device is sm_100 */
@@ -68,6 +83,8 @@ int mmi_gather_l1norm_fwd(const void* table, int table_dtype, int64_t n_rows, in
  *   if preact: preact[m,n] = z                           (saved for GELU backward; save_act_grad = 0)
  *              preact[m,n] = gelu'(z)                    (save_act_grad = 1: backward needs no erf)
  *   y    = act(z)
+ *   if drop.thr8: y = dropout(y) (and the gelu'(z) written to preact gets the same mask and scale, so the backward
+ *                 epilogue's y *= preact applies the dropout gradient for free); element index (m, n), BEFORE `add`
  *   if mul_gelu_grad: y *= gelu'(mul_gelu_grad[m,n])     (dgrad through GELU; mul_is_grad = 0)
  *                     y *= mul_gelu_grad[m,n]            (mul_is_grad = 1: operand saved by save_act_grad)
  *   if add:  y += add[(m % add_mod) * ld_add + n]        (residual / position embedding)
@@ -100,6 +117,7 @@ typedef struct {
   int split_k;
   int save_act_grad;   /* 1: preact receives gelu'(z) instead of z */
   int mul_is_grad;     /* 1: mul_gelu_grad already holds gelu'(z)  */
+  mmi_dropout drop;    /* applied to act(z) before `add`; thr8 = 0: off (not with accumulate / split-K) */
 } mmi_gemm_args;
 int mmi_gemm(const mmi_gemm_args* args, mmi_stream_t stream);
 
@@ -120,6 +138,19 @@ int mmi_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, in
                       const float* gamma, const float* stats, const void* add, void* dx,
                       float* dgamma, float* dbeta, float* dxsum, float* workspace, mmi_stream_t stream);
 
+/* Dropout variants (NULL pointers = that part off; with all three NULL they equal the calls above):
+ * fwd:  y = dropout(LN(x))                                   -- the embedding dropout, models/encoder.py:386,472
+ * bwd:  dy_drop:  dy is read as dropout'(dy) = mask * scale * dy (backward of the forward variant);
+ *       dx_drop + dx_dropped: additionally writes dx_dropped = mask * scale * dx, the gradient that flows into the
+ *       Linear whose dropped-out output was added to the residual (encoder.py:163-171,198-202), and dxsum then sums
+ *       dx_dropped (that Linear's bias gradient); dx itself stays the residual-branch gradient.                      */
+int mmi_layernorm_fwd_drop(const void* x, int dtype, int64_t rows, int d, const float* gamma, const float* beta,
+                           float eps, void* y, float* stats, const mmi_dropout* drop, mmi_stream_t stream);
+int mmi_layernorm_bwd_drop(const void* dy, const void* x, int dtype, int64_t rows, int d, const float* gamma,
+                           const float* stats, const void* add, void* dx, float* dgamma, float* dbeta, float* dxsum,
+                           float* workspace, const mmi_dropout* dy_drop, const mmi_dropout* dx_drop, void* dx_dropped,
+                           mmi_stream_t stream);
+
 /* ---- a-5/a-6: candidate x history attention -----------------------------------------
  * replaces models/encoder.py:44-73 (get_attn_logits: QK^T, outer-product mask,
  * "set to -10000"), :138-161 (concat of two key blocks, /sqrt(dh), joint softmax, PV).
@@ -127,6 +158,9 @@ int mmi_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, in
  * with different query projections:
  *     S = [ Qa Ka^T | Qb Kb^T ],  S[!(mq_i & mk_j)] = -10000,  P = softmax(S / sqrt(dh)),
  *     O = P [Va ; Vb]
+ * With drop.thr8 != 0 the reference's logits dropout (encoder.py:145-150) sits between the fill and the scale:
+ *     S <- dropout(S)  (dropped logits become 0 -- a dropped masked logit is therefore VISIBLE to the softmax, exactly
+ *     like the reference), mask row = (b*H + h)*Lq + q, column group of key k of block i = (i << 20) + (k >> 5).
  * Tensors are [B*L, ld] with head h at columns [h*dh, (h+1)*dh).  nblk may be 1.      */
 typedef struct {
   const void* q; int64_t ldq;      /* query projection used against this key block */
@@ -153,6 +187,7 @@ typedef struct {
   /* backward only */
   const void* dout; int64_t lddo;
   float* delta;                    /* [B, H, Lq] scratch: rowsum(dO * O) */
+  mmi_dropout drop;                /* logits dropout; thr8 = 0: off */
 } mmi_attn_args;
 int mmi_attn_fwd(const mmi_attn_args* a, mmi_stream_t stream);
 /* writes dq for both blocks and delta */

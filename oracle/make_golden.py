@@ -29,7 +29,9 @@ OUT = os.path.join(ROOT, "tests", "golden")
 
 
 def run_model_case(name, d_model, nhead, nlayers, din, Lt, B, seed, store_sd=True, loss_types=("focal",),
-                   fill_seed=None, ablation_type="ours"):
+                   fill_seed=None, ablation_type="ours", train_seed=None):
+    """train_seed: run the training forward in train() mode (nn.Dropout(0.1) live at every site) right after
+    torch.manual_seed(train_seed); the oracle replays the same generator stream (tests/test_oracle_golden.py)."""
     args = ref_shim.make_args(d_model=d_model, nhead=nhead, num_layers_enc=nlayers,
                               loss_type_list=list(loss_types), ablation_type=ablation_type)
     model = ref_shim.build_reference_model(args, din=din, max_usr_len=Lt, seed=seed)
@@ -53,10 +55,15 @@ def run_model_case(name, d_model, nhead, nlayers, din, Lt, B, seed, store_sd=Tru
                  usr_mask=torch.from_numpy(usr_mask), vid_image=torch.from_numpy(vid),
                  vid_id=torch.zeros(B, dtype=torch.long), vid_mask=torch.from_numpy(vid_mask),
                  gt=torch.from_numpy(gt.copy()))
+    if train_seed is not None:
+        model.train()
+        torch.manual_seed(train_seed)
     out = ref_shim.run_reference(model, batch, mode="train")
     out["loss"].backward()
+    model.eval()
     save = dict(cfg=json.dumps(dict(d_model=d_model, nhead=nhead, num_layers_enc=nlayers, din=din, Lt=Lt, B=B,
-                                    seed=seed, loss_types=list(loss_types), fill_seed=fill_seed, ablation_type=ablation_type)),
+                                    seed=seed, loss_types=list(loss_types), fill_seed=fill_seed, ablation_type=ablation_type,
+                                    train_seed=train_seed)),
                 usr_mask=usr_mask, vid_mask=vid_mask, gt_in=gt,
                 logits=out["logits"].detach().numpy(), gt_out=out["gt"].numpy(),
                 loss=np.float64(out["loss"].item()), mse=np.float64(out["mse"].item()),
@@ -301,6 +308,8 @@ def main():
     run_model_case("model_full_b4", d_model=512, nhead=16, nlayers=6, din=1024, Lt=100, B=4, seed=13,
                    store_sd=False, fill_seed=42)
     run_general_cases()
+    run_ablation_cases()
+    run_dropout_cases()
 
 
 def run_general_cases():
@@ -315,6 +324,13 @@ def run_ablation_cases():
     """encoder ablations that select one attention block per query side (encoder.py:108-135,172-175)"""
     run_model_case("model_small_crossatt", d_model=64, nhead=2, nlayers=4, din=48, Lt=12, B=5, seed=41, ablation_type="CrossAtt")
     run_model_case("model_small_selfatt", d_model=64, nhead=2, nlayers=3, din=48, Lt=12, B=5, seed=42, ablation_type="SelfAtt")
+
+
+def run_dropout_cases():
+    """train() mode: nn.Dropout(0.1) live at every site, torch generator seeded right before the forward"""
+    run_model_case("model_small_dropout", d_model=64, nhead=2, nlayers=4, din=48, Lt=12, B=5, seed=51, train_seed=1234)
+    run_model_case("model_small_dropout_crossatt", d_model=64, nhead=2, nlayers=3, din=48, Lt=12, B=5, seed=52, train_seed=99,
+                   ablation_type="CrossAtt")
 
 
 def run_fusion_variants():
@@ -336,5 +352,7 @@ if __name__ == "__main__":
         run_fusion_variants()
     elif "--ablation-only" in sys.argv:
         run_ablation_cases()
+    elif "--dropout-only" in sys.argv:
+        run_dropout_cases()
     else:
         main()

@@ -31,8 +31,28 @@ def l1_normalise(x: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------
 # a-4  embedding: Linear(Din->d) + PE + LN(eps 1e-12)
 # --------------------------------------------------------------------------
-def embed(sd, prefix, usr, vid, use_pe=True):
-    """models/encoder.py:425-473 (dropout off).  Image inputs are [B,L,Din] floats (Linear projections); ID inputs
+# Dropout hook.  The reference's five kinds of nn.Dropout sites are restated with an optional callable
+#     drop(kind, tower, layer, side, x, blocks=None) -> dropout(x)
+# (kind: DROP_* below; tower 0/1 = backbone1/2; layer 63 = the embedding; side 0 = candidate, 1 = history; blocks = key
+# block widths of a concatenated logits tensor).  None = eval mode.  torch's own generator cannot be replayed by any other
+# implementation, so the parity tests pass a callable that applies the masks of oracle/dropout_ref.py -- the counter-based
+# generator of the CUDA path -- which makes "training with dropout" a deterministic comparison.
+DROP_EMB, DROP_ATTN, DROP_ATTN_OUT, DROP_MLP1, DROP_MLP2 = range(5)
+
+
+def _tower(prefix):
+    return 1 if prefix.startswith("backbone2.") else 0
+
+
+def torch_dropout(p=0.1):
+    """the reference's own behaviour (F.dropout from torch's global generator) as a drop callable: CPU baseline timing"""
+    def drop(kind, tower, layer, side, x, blocks=None):
+        return F.dropout(x, p, True)
+    return drop
+
+
+def embed(sd, prefix, usr, vid, use_pe=True, drop=None):
+    """models/encoder.py:425-473.  Image inputs are [B,L,Din] floats (Linear projections); ID inputs
     are int64 [B] (encoder.py:352-362,426-435,478-488): the video id is repeated over the 40 segments
     and embedded into d/2 columns, the other d/2 come from Linear(1 -> d/2) of the segment position; the user id
     becomes ONE token (the caller then uses an all-ones user mask)."""
@@ -54,6 +74,9 @@ def embed(sd, prefix, usr, vid, use_pe=True):
         u = u + sd[prefix + "usr_pe.weight"][None, : u.shape[1]]
     v = F.layer_norm(v, (d,), sd[prefix + "vid_ln.weight"], sd[prefix + "vid_ln.bias"], 1e-12)
     u = F.layer_norm(u, (d,), sd[prefix + "usr_ln.weight"], sd[prefix + "usr_ln.bias"], 1e-12)
+    if drop is not None:            # encoder.py:458,470: self.do on both embeddings
+        v = drop(DROP_EMB, _tower(prefix), 63, 0, v)
+        u = drop(DROP_EMB, _tower(prefix), 63, 1, u)
     return v, u
 
 
@@ -88,8 +111,10 @@ def attn_ablation(ablation_type):
     return "CrossAtt" if "CrossAtt" in a else ("SelfAtt" if "SelfAtt" in a else "ours")
 
 
-def cross_attention(sd, p, vid, vid_mask, usr, usr_mask, nhead, need_usr=True, ablation="ours"):
-    """models/encoder.py:75-175 with sr_ratio=1, dropout off.  'ours': joint softmax over [v2v | t2v] for candidate
+def cross_attention(sd, p, vid, vid_mask, usr, usr_mask, nhead, need_usr=True, ablation="ours", drop=None, where=(0, 0)):
+    """models/encoder.py:75-175 with sr_ratio=1; drop: the logits dropout (:145-150, on the concatenated logits AFTER the
+    -10000 fill and BEFORE the scale -- a dropped masked logit becomes 0 and is visible to the softmax) and the dropout of
+    the output projections (:163-164); where = (tower, layer).  'ours': joint softmax over [v2v | t2v] for candidate
     queries and [v2t | t2t] for history queries; 'CrossAtt' keeps t2v / v2t only, 'SelfAtt' keeps v2v only and returns
     no history update (:172-173).  The scale 1/sqrt(dh) is applied AFTER the mask fill."""
     B, Lv, d = vid.shape
@@ -101,49 +126,71 @@ def cross_attention(sd, p, vid, vid_mask, usr, usr_mask, nhead, need_usr=True, a
     def val(name, x):
         return F.linear(x, sd[p + name + "_proj.2.weight"], sd[p + name + "_proj.2.bias"])
 
-    def attend(names, q, q_mask):
-        logits = torch.cat([attn_logits(sd, p + n + "_proj.", key_side[n][0], key_side[n][1], q, q_mask, nhead) for n in names], -1) * scale
-        value = torch.cat([val(n, key_side[n][0]) for n in names], 1).view(B, -1, nhead, dh)
-        return torch.einsum("bhqk,bkhd->bqhd", F.softmax(logits, -1), value).reshape(B, q.shape[1], d)
+    def scaled_logits(names, q, q_mask, side):
+        blocks = [attn_logits(sd, p + n + "_proj.", key_side[n][0], key_side[n][1], q, q_mask, nhead) for n in names]
+        logits = torch.cat(blocks, -1)
+        if drop is not None:
+            logits = drop(DROP_ATTN, where[0], where[1], side, logits, blocks=[b.shape[-1] for b in blocks])
+        return logits * scale
 
-    vid_ = F.linear(attend(names_v, vid, vid_mask), sd[p + "ff_vid.weight"], sd[p + "ff_vid.bias"])
+    def attend(names, logits, Lq):
+        value = torch.cat([val(n, key_side[n][0]) for n in names], 1).view(B, -1, nhead, dh)
+        return torch.einsum("bhqk,bkhd->bqhd", F.softmax(logits, -1), value).reshape(B, Lq, d)
+
+    # the reference's order of dropout draws (:145-150,163-164): candidate logits, history logits, history output
+    # projection, candidate output projection -- kept so that torch_dropout() replays the reference's generator stream
+    want_usr = need_usr and names_t is not None
+    lv = scaled_logits(names_v, vid, vid_mask, 0)
+    lt = scaled_logits(names_t, usr, usr_mask, 1) if want_usr else None
+    usr_out = None
+    if want_usr:
+        usr_ = F.linear(attend(names_t, lt, usr.shape[1]), sd[p + "ff_usr.weight"], sd[p + "ff_usr.bias"])
+        if drop is not None:
+            usr_ = drop(DROP_ATTN_OUT, where[0], where[1], 1, usr_)
+        usr_out = F.layer_norm(usr + usr_, (d,), sd[p + "ln_usr.weight"], sd[p + "ln_usr.bias"], 1e-12)
+    vid_ = F.linear(attend(names_v, lv, Lv), sd[p + "ff_vid.weight"], sd[p + "ff_vid.bias"])
+    if drop is not None:
+        vid_ = drop(DROP_ATTN_OUT, where[0], where[1], 0, vid_)
     vid_out = F.layer_norm(vid + vid_, (d,), sd[p + "ln_vid.weight"], sd[p + "ln_vid.bias"], 1e-12)
-    if not need_usr or names_t is None:
-        return vid_out, None
-    usr_ = F.linear(attend(names_t, usr, usr_mask), sd[p + "ff_usr.weight"], sd[p + "ff_usr.bias"])
-    usr_out = F.layer_norm(usr + usr_, (d,), sd[p + "ln_usr.weight"], sd[p + "ln_usr.bias"], 1e-12)
     return vid_out, usr_out
 
 
 # --------------------------------------------------------------------------
 # a-7  FFN + residual LN
 # --------------------------------------------------------------------------
-def ffn(sd, p, side, x):
-    """models/encoder.py:202-206 + kn_util/nn_utils/layers/mlp.py:17-24:
-    LN(x + W2 gelu_erf(W1 x)), eps 1e-12."""
+def ffn(sd, p, side, x, drop=None, where=(0, 0)):
+    """models/encoder.py:198-206 + kn_util/nn_utils/layers/mlp.py:17-24:
+    LN(x + do(W2 do(gelu_erf(W1 x)))), eps 1e-12."""
     d = x.shape[-1]
+    si = 0 if side == "vid" else 1
     h = F.gelu(F.linear(x, sd[p + f"ff_{side}.layers.0.weight"], sd[p + f"ff_{side}.layers.0.bias"]))
+    if drop is not None:
+        h = drop(DROP_MLP1, where[0], where[1], si, h)
     h = F.linear(h, sd[p + f"ff_{side}.layers.1.weight"], sd[p + f"ff_{side}.layers.1.bias"])
+    if drop is not None:
+        h = drop(DROP_MLP2, where[0], where[1], si, h)
     return F.layer_norm(x + h, (d,), sd[p + f"ln_{side}.weight"], sd[p + f"ln_{side}.bias"], 1e-12)
 
 
 # --------------------------------------------------------------------------
 # a-8  encoder stack; output = INPUT of the last layer
 # --------------------------------------------------------------------------
-def backbone(sd, prefix, usr, usr_mask, vid, vid_mask, nhead, num_layers, use_pe=True, ablation="ours"):
+def backbone(sd, prefix, usr, usr_mask, vid, vid_mask, nhead, num_layers, use_pe=True, ablation="ours", drop=None, full_usr=False):
     """models/encoder.py:302-324,475-520.  intermediate_states records vid_feat
     BEFORE each layer and the caller takes [-1], so layer N-1 never reaches the
     output, nor does the history side of layer N-2."""
-    v, u = embed(sd, prefix, usr, vid, use_pe)
+    v, u = embed(sd, prefix, usr, vid, use_pe, drop)
+    tw = _tower(prefix)
     if usr.ndim == 1:   # ID user: one token, mask of ones (encoder.py:478-481)
         usr_mask = torch.ones(usr.shape[0], 1, dtype=torch.bool)
     for i in range(num_layers - 1):
         p = f"{prefix}encoder.layers.{i}."
-        need_usr = i < num_layers - 2
-        v, u2 = cross_attention(sd, p + "cross_attn.", v, vid_mask, u, usr_mask, nhead, need_usr, ablation)
-        v = ffn(sd, p, "vid", v)
+        need_usr = full_usr or i < num_layers - 2      # full_usr: also the dead history side of layer N-2 (its dropout DRAWS
+                                                       # precede live ones in the reference's generator stream)
+        v, u2 = cross_attention(sd, p + "cross_attn.", v, vid_mask, u, usr_mask, nhead, need_usr, ablation, drop, (tw, i))
+        v = ffn(sd, p, "vid", v, drop, (tw, i))
         if u2 is not None:          # SelfAtt: the history tokens are never updated (encoder.py:320-321)
-            u = ffn(sd, p, "usr", u2)
+            u = ffn(sd, p, "usr", u2, drop, (tw, i))
     return v
 
 
@@ -311,7 +358,8 @@ def compute_loss(logits, gt, exposure_prob, loss_type_list=("focal",), loss_weig
 # --------------------------------------------------------------------------
 def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_layers,
             exposure_prob=None, loss_type_list=("focal",), use_pe=True, mode="train", loss_weight=None,
-            usr_id=None, vid_id=None, input_type=None, fusion_heads=2, mask_loss=0, ablation_type="ours"):
+            usr_id=None, vid_id=None, input_type=None, fusion_heads=2, mask_loss=0, ablation_type="ours", drop=None,
+            full_usr=False):
     """models/decoder_leave_focal.py:574-658.  input_type {'user': image|id|both, 'photo': image|id|both}
     (default image/image, single backbone, Linear head); with a 'both' entry there are two backbones
     (main...SegMM.py:63-106: backbone1 takes the image side of a 'both' input, backbone2 the id side) fused by
@@ -326,10 +374,10 @@ def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_laye
 
     abl = attn_ablation(ablation_type)
     x1 = backbone(sd, "backbone1.", pick(it["user"], usr_image, usr_id, 1), usr_mask.bool(),
-                  pick(it["photo"], vid_image, vid_id, 1), vid_mask.bool(), nhead, num_layers, use_pe, abl)
+                  pick(it["photo"], vid_image, vid_id, 1), vid_mask.bool(), nhead, num_layers, use_pe, abl, drop, full_usr)
     if two:
         x2 = backbone(sd, "backbone2.", pick(it["user"], usr_image, usr_id, 2), usr_mask.bool(),
-                      pick(it["photo"], vid_image, vid_id, 2), vid_mask.bool(), nhead, num_layers, use_pe, abl)
+                      pick(it["photo"], vid_image, vid_id, 2), vid_mask.bool(), nhead, num_layers, use_pe, abl, drop, full_usr)
         if fusion_heads > 0:
             logits = fusion_logits(sd, x1, x2, fusion_heads)
         elif fusion_heads == 0:      # models/decoder_leave_focal.py:630-631: stage_mlp1(x1) + stage_mlp2(x2)

@@ -17,6 +17,11 @@ c_p = C.c_void_p
 i64 = C.c_int64
 
 
+class Dropout(C.Structure):
+    """mmi_dropout: one dropout site (csrc/dropout.cuh); thr8 = 0 is off"""
+    _fields_ = [("key", C.c_uint32), ("thr8", C.c_uint32), ("scale", C.c_float)]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [("layout", C.c_int), ("impl", C.c_int), ("in_dtype", C.c_int), ("out_dtype", C.c_int),
                 ("M", i64), ("N", i64), ("K", i64),
@@ -25,7 +30,8 @@ class GemmArgs(C.Structure):
                 ("preact", c_p), ("ld_preact", i64),
                 ("mul_gelu_grad", c_p), ("ld_mul", i64),
                 ("add", c_p), ("ld_add", i64), ("add_mod", i64), ("add_dtype", C.c_int),
-                ("accumulate", C.c_int), ("split_k", C.c_int), ("save_act_grad", C.c_int), ("mul_is_grad", C.c_int)]
+                ("accumulate", C.c_int), ("split_k", C.c_int), ("save_act_grad", C.c_int), ("mul_is_grad", C.c_int),
+                ("drop", Dropout)]
 
 
 class AttnBlock(C.Structure):
@@ -40,7 +46,8 @@ class AttnArgs(C.Structure):
                 ("B", C.c_int), ("H", C.c_int), ("dh", C.c_int), ("Lq", C.c_int),
                 ("mask_q", c_p), ("nblk", C.c_int), ("blk", AttnBlock * 2),
                 ("out", c_p), ("ldo", i64), ("lse", c_p),
-                ("dout", c_p), ("lddo", i64), ("delta", c_p)]
+                ("dout", c_p), ("lddo", i64), ("delta", c_p),
+                ("drop", Dropout)]
 
 
 class LossArgs(C.Structure):
@@ -63,6 +70,10 @@ _SIGS = {
     "mmi_gemm": (C.c_int, [C.POINTER(GemmArgs), c_p]),
     "mmi_colsum_acc": (C.c_int, [c_p, C.c_int, i64, C.c_int, i64, c_p, c_p, i64, c_p]),
     "mmi_layernorm_fwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, C.c_float, c_p, c_p, c_p]),
+    "mmi_layernorm_fwd_drop": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, C.c_float, c_p, c_p, C.POINTER(Dropout), c_p]),
+    "mmi_layernorm_bwd_drop": (C.c_int, [c_p, c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                                         C.POINTER(Dropout), C.POINTER(Dropout), c_p, c_p]),
+    "mmi_dropout_mask": (C.c_int, [C.POINTER(Dropout), i64, i64, C.c_int, C.c_uint32, c_p, c_p]),
     "mmi_layernorm_bwd_workspace": (i64, [C.c_int]),
     "mmi_layernorm_bwd": (C.c_int, [c_p, c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmi_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), c_p]),

@@ -47,6 +47,10 @@ extern "C" int mmi_gemm(const mmi_gemm_args* a, mmi_stream_t stream) {
   p.add = a->add; p.ld_add = a->ld_add; p.add_mod = a->add_mod; p.add_dtype = a->add_dtype;
   p.accumulate = a->accumulate; p.split_k = a->split_k;
   p.save_act_grad = a->save_act_grad; p.mul_is_grad = a->mul_is_grad;
+  p.drop = make_drop(a->drop);
+  MMI_CHECK_ARG(p.drop.thr8 < 256u, "gemm: dropout thr8 must be < 256");
+  MMI_CHECK_ARG(!(p.drop.thr8 && (a->accumulate || a->split_k > 1)), "gemm: dropout cannot be combined with accumulate / split-K");
+  MMI_CHECK_ARG(!(p.drop.thr8 && a->mul_gelu_grad && a->act != MMI_ACT_NONE), "gemm: dropout with both act and mul_gelu_grad is undefined");
   if (a->impl != MMI_IMPL_TC && p.split_k == 0) p.split_k = 1;
   if (a->impl == MMI_IMPL_TC) {
     if (!tc_available()) { set_error("gemm: tcgen05 path requested but not available on this device/build"); return MMI_ENOSUP; }

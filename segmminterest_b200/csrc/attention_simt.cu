@@ -9,6 +9,7 @@
 // uniform softmax over all keys (pads included) and gradients do not flow through the
 // overwritten logits.
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace mmi {
 
@@ -30,7 +31,10 @@ struct AttnParams {
   const void* dout; int64_t lddo;
   float* delta;
   float scale;
+  DropParams drop;   // logits dropout (models/encoder.py:145-150): after the -10000 fill, before the scale
 };
+// keep-word group of key k of key block blk (include/mmi_b200.h)
+__device__ __forceinline__ uint32_t attn_group(int blk, int k) { return (static_cast<uint32_t>(blk) << 20) + (static_cast<uint32_t>(k) >> 5); }
 
 constexpr int kQThreads = 128;
 constexpr int kKT = 64;   // keys per smem tile (fwd / dq)
@@ -87,6 +91,8 @@ __global__ void __launch_bounds__(kQThreads) attn_fwd_simt_kernel(AttnParams a) 
   float m = -INFINITY, l = 0.f, o[DH];
 #pragma unroll
   for (int d = 0; d < DH; ++d) o[d] = 0.f;
+  const bool drop_on = a.drop.thr8 != 0u;
+  const uint32_t rowh = drop_on ? drop_rowhash(a.drop.key, (uint64_t)(((int64_t)b * a.H + h) * a.Lq + qi)) : 0u;
 
   for (int bi = 0; bi < a.nblk; ++bi) {
     const AttnBlk& kb = a.blk[bi];
@@ -105,15 +111,19 @@ __global__ void __launch_bounds__(kQThreads) attn_fwd_simt_kernel(AttnParams a) 
       if (tid < kKT) Mk[tid] = (k0 + tid < kb.Lk) ? kb.mask_k[(int64_t)b * kb.Lk + k0 + tid] : 0;
       __syncthreads();
       const int nk = min(kKT, kb.Lk - k0);
+      uint32_t kw = 0xffffffffu;
       for (int j0 = 0; j0 < nk; j0 += 8) {
         float s[8];
         float mx = -INFINITY;
+        if (drop_on && (j0 & 31) == 0) kw = drop_keep_word(rowh, attn_group(bi, k0 + j0), a.drop.thr8);   // k0 is a multiple of 64
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
           const int j = j0 + jj;
           if (j < nk) {
             const float dt = dot_smem<DH>(q, &Ks[j][0]);
-            s[jj] = ((mq && Mk[j]) ? dt : kMaskFill) * a.scale;
+            float raw = (mq && Mk[j]) ? dt : kMaskFill;
+            if (drop_on) raw = ((kw >> (j & 31)) & 1u) ? raw * a.drop.scale : 0.f;    // a dropped logit is 0, masked or not
+            s[jj] = raw * a.scale;
           } else {
             s[jj] = -INFINITY;
           }
@@ -174,6 +184,9 @@ __global__ void __launch_bounds__(kQThreads) attn_bwd_dq_simt_kernel(AttnParams 
 #pragma unroll
     for (int d = 0; d < DH; ++d) dO[d] = 0.f;
   }
+  const bool drop_on = a.drop.thr8 != 0u;
+  const uint32_t rowh = drop_on ? drop_rowhash(a.drop.key, (uint64_t)(((int64_t)b * a.H + h) * a.Lq + qi)) : 0u;
+  const float gscale = drop_on ? a.scale * a.drop.scale : a.scale;      // d logit / d (q.k) for a surviving valid logit
   for (int bi = 0; bi < a.nblk; ++bi) {
     const AttnBlk& kb = a.blk[bi];
     float q[DH], dq[DH];
@@ -189,13 +202,15 @@ __global__ void __launch_bounds__(kQThreads) attn_bwd_dq_simt_kernel(AttnParams 
       if (tid < kKT) Mk[tid] = (k0 + tid < kb.Lk) ? kb.mask_k[(int64_t)b * kb.Lk + k0 + tid] : 0;
       __syncthreads();
       const int nk = min(kKT, kb.Lk - k0);
-      if (mq) {  // an overwritten (masked) logit passes no gradient to q/k
+      if (mq) {  // an overwritten (masked) or dropped logit passes no gradient to q/k
+        uint32_t kw = 0xffffffffu;
         for (int j = 0; j < nk; ++j) {
-          if (!Mk[j]) continue;
-          const float s = dot_smem<DH>(q, &Ks[j][0]) * a.scale;
+          if (drop_on && (j & 31) == 0) kw = drop_keep_word(rowh, attn_group(bi, k0 + j), a.drop.thr8);
+          if (!Mk[j] || !((kw >> (j & 31)) & 1u)) continue;
+          const float s = dot_smem<DH>(q, &Ks[j][0]) * gscale;
           const float p = expf(s - lse);
           const float dp = dot_smem<DH>(dO, &Vs[j][0]);
-          const float ds = p * (dp - delta) * a.scale;
+          const float ds = p * (dp - delta) * gscale;
 #pragma unroll
           for (int d = 0; d < DH; d += 4) {
             const float4 kv = *reinterpret_cast<const float4*>(&Ks[j][d]);
@@ -216,6 +231,8 @@ __global__ void __launch_bounds__(kQThreads) attn_bwd_dkv_simt_kernel(AttnParams
   __shared__ __align__(16) float dOs[kQT][DH];
   __shared__ float Ls[kQT], Ds[kQT];
   __shared__ uint8_t Mq[kQT];
+  __shared__ uint32_t Rh[kQT];     // dropout row hashes of the tile's queries
+  const bool drop_on = a.drop.thr8 != 0u;
   const AttnBlk& kb = a.blk[which];
   const int b = blockIdx.z, h = blockIdx.y, tid = threadIdx.x;
   const int kj = blockIdx.x * kQThreads + tid;
@@ -241,16 +258,25 @@ __global__ void __launch_bounds__(kQThreads) attn_bwd_dkv_simt_kernel(AttnParams
       Ls[tid] = in ? lse[q0 + tid] : 0.f;
       Ds[tid] = in ? del[q0 + tid] : 0.f;
       Mq[tid] = in ? a.mask_q[(int64_t)b * a.Lq + q0 + tid] : 0;
+      Rh[tid] = drop_on ? drop_rowhash(a.drop.key, (uint64_t)(((int64_t)b * a.H + h) * a.Lq + q0 + tid)) : 0u;
     }
     __syncthreads();
     const int nq = min(kQT, a.Lq - q0);
     for (int i = 0; i < nq; ++i) {
-      const bool valid = mk && Mq[i];
+      bool valid = mk && Mq[i];
       const float dt = dot_smem<DH>(k, &Qs[i][0]);
-      const float s = (valid ? dt : kMaskFill) * a.scale;
+      float raw = valid ? dt : kMaskFill;
+      float gscale = a.scale;
+      if (drop_on) {                 // same keep bit the forward used for (query q0 + i, key kj of block `which`)
+        const bool keep = (drop_keep_word(Rh[i], attn_group(which, kj), a.drop.thr8) >> (kj & 31)) & 1u;
+        raw = keep ? raw * a.drop.scale : 0.f;
+        valid = valid && keep;
+        gscale *= a.drop.scale;
+      }
+      const float s = raw * a.scale;
       const float p = expf(s - Ls[i]);
       const float dp = dot_smem<DH>(v, &dOs[i][0]);
-      const float ds = valid ? p * (dp - Ds[i]) * a.scale : 0.f;
+      const float ds = valid ? p * (dp - Ds[i]) * gscale : 0.f;
 #pragma unroll
       for (int d = 0; d < DH; d += 4) {
         const float4 dov = *reinterpret_cast<const float4*>(&dOs[i][d]);
@@ -277,6 +303,8 @@ static int to_params(const mmi_attn_args* a, AttnParams& p, bool bwd) {
   p.mask_q = a->mask_q; p.out = a->out; p.ldo = a->ldo; p.lse = a->lse;
   p.dout = a->dout; p.lddo = a->lddo; p.delta = a->delta;
   p.scale = 1.0f / sqrtf((float)a->dh);
+  p.drop = make_drop(a->drop);
+  MMI_CHECK_ARG(p.drop.thr8 < 256u, "attn: dropout thr8 must be < 256");
   const int al = a->dtype == MMI_F32 ? 4 : 4;  // 4-element vector accesses
   for (int i = 0; i < a->nblk; ++i) {
     const mmi_attn_block& s = a->blk[i];

@@ -26,6 +26,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "dropout.cuh"
 #include "tc_common.cuh"
 
 namespace mmi {
@@ -59,7 +60,15 @@ struct AttnTcParams {
   float scale;        // 1/sqrt(dh)
   float scale_log2;   // scale * log2(e)
   float fill_log2;    // -10000 * scale * log2(e)
+  DropParams drop;    // logits dropout (kernels instantiated with DROP = true): after the -10000 fill, before the scale
 };
+// Logits dropout (models/encoder.py:145-150) in the three kernels, DROP = true instantiations only:
+//   raw logit v = valid ? q.k : -10000;  v <- keep ? v * drop.scale : 0;  softmax over v / sqrt(dh)
+// so a dropped logit is 0 whether it was masked or not (the reference's order of operations), and only logits that are
+// both valid and kept pass a gradient (times drop.scale).  keep(query row, key) comes from the keep word of
+// (row = (b*H + h)*Lq + q, group = (blk << 20) + (k >> 5)): fwd / dq threads own a query row and generate one word per
+// 32 keys; dk/dv threads own a key, so lane c generates the word of query c of the tile and the warp shuffles them.
+__device__ __forceinline__ uint32_t attn_group(int blk, int k32) { return (static_cast<uint32_t>(blk) << 20) + static_cast<uint32_t>(k32); }
 
 #ifdef MMI_ATTN_TRACE
 // debug build only: clock64 stamps of one CTA (blockIdx.z == gridDim.z / 2, x == 0, y == 0), read back by mmi_debug_trace
@@ -488,6 +497,7 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
   return v;
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
                      const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
@@ -582,8 +592,12 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_cons
     const bool mq = q_in ? (p.mask_q[(int64_t)b * p.Lq + qi] != 0) : true;
     const bool warp_all_mq = __all_sync(0xffffffffu, mq);
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-    const float scale_t = mq ? p.scale_log2 : 0.f;
-    const float base_t = mq ? 0.f : p.fill_log2;
+    // DROP: the fill and the dropout are applied to the raw scores in registers, after which every in-range key is an
+    // ordinary logit with scale scale_log2 * drop.scale (padded query rows included)
+    const float scale_d = p.scale_log2 * p.drop.scale;
+    const float scale_t = DROP ? scale_d : (mq ? p.scale_log2 : 0.f);
+    const float base_t = DROP ? 0.f : (mq ? 0.f : p.fill_log2);
+    const uint32_t rowh = DROP ? drop_rowhash(p.drop.key, (uint64_t)(((int64_t)b * p.H + h) * p.Lq + qi)) : 0u;
     float m = 0.f, l0 = 0.f, l1 = 0.f;
     const uint32_t a_ready_a = smem_u32(&bars->a_ready[0]), s_free_a = smem_u32(&bars->s_free[0]), p_ready_a = smem_u32(&bars->p_ready[0]);
     const uint32_t p_free_a = smem_u32(&bars->p_free[0]);
@@ -595,13 +609,29 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_cons
       tcgen05_fence_after();
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        const uint32_t wv = hf ? kb.y : kb.x, wr = hf ? kb.w : kb.z;
+        const uint32_t wr = hf ? kb.w : kb.z;
+        const uint32_t wv = DROP ? wr : (hf ? kb.y : kb.x);              // DROP: every in-range key carries a logit
         uint32_t r[32];
         tmem_ld_32x32(tS_row + hf * 32, r);
         tmem_ld_wait();
         if (hf == 1) {                                   // the whole tile is in registers: the MMA warp may refill S
           tcgen05_fence_before();
           mbar_arrive_a(s_free_a);
+        }
+        if constexpr (DROP) {
+          const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
+          const uint32_t kw = drop_keep_word(rowh, attn_group(blk, kt * 2 + hf), p.drop.thr8);
+          const uint32_t vb = mq ? (hf ? kb.y : kb.x) : 0u;             // logits that are not overwritten with -10000
+          if (vb == 0xffffffffu) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) r[c] = ((kw >> c) & 1u) ? r[c] : 0u;
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const uint32_t v = ((vb >> c) & 1u) ? r[c] : __float_as_uint(-10000.0f);
+              r[c] = ((kw >> c) & 1u) ? v : 0u;
+            }
+          }
         }
         // ---- maximum of this half in the log2 domain
         float t;
@@ -614,9 +644,13 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_cons
 #pragma unroll
             for (int c = 0; c < 32; ++c) if ((wv >> c) & 1u) mx = fmaxf(mx, __uint_as_float(r[c]));
           }
-          t = (wr & ~wv) != 0u ? p.fill_log2 : -INFINITY;
-          if (mx > -INFINITY) t = fmaxf(t, mx * p.scale_log2);
-          if (!mq) t = p.fill_log2;
+          if constexpr (DROP) {
+            t = mx > -INFINITY ? mx * scale_d : -INFINITY;
+          } else {
+            t = (wr & ~wv) != 0u ? p.fill_log2 : -INFINITY;
+            if (mx > -INFINITY) t = fmaxf(t, mx * p.scale_log2);
+            if (!mq) t = p.fill_log2;
+          }
         }
         const bool first = j == 0 && hf == 0;
         if (first) m = t;
@@ -654,7 +688,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_cons
         }
         const float nb_t = base_t - m;
         uint32_t pk[16];
-        if (warp_all_mq && wv == 0xffffffffu) {
+        if ((DROP || warp_all_mq) && wv == 0xffffffffu) {
           float2 l2 = make_float2(l0, l1);
           const float2 sc2 = splat2(scale_t), nb2 = splat2(nb_t);
 #pragma unroll
@@ -666,7 +700,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_cons
           }
           l0 = l2.x; l1 = l2.y;
         } else {
-          const float pm = ex2(p.fill_log2 - m);
+          const float pm = ex2(p.fill_log2 - m);         // (DROP: wv == wr, never selected)
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
             float e[2];
@@ -710,6 +744,7 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_cons
 // a_ready(j) fires because that commit also covers the dQ product of tile j - 2.
 constexpr int BWD_STAGES = 3;
 
+template <bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
                       const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
@@ -815,10 +850,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
     const float nds = -delta * p.scale;                  // dS = P * (dP * scale + nds)
     const uint32_t a_ready_a = smem_u32(&bars->a_ready[0]), s_free_a = smem_u32(&bars->s_free[0]), p_ready_a = smem_u32(&bars->p_ready[0]);
     const uint32_t kb_a = smem_u32(kbits), dsrow_a = smem_u32(sdS) + row * 64, swz = (row >> 1) & 3;
+    const uint32_t rowh = DROP ? drop_rowhash(p.drop.key, (uint64_t)(((int64_t)b * p.H + h) * p.Lq + qi)) : 0u;
     for (int j = 0; j < T; ++j) {
       const uint32_t pb = j & 1;
       const uint32_t wv = lds_u1(kb_a + j * 8);
-      const bool fast = warp_all_mq && wv == 0xffffffffu;
+      const bool fast = !DROP && warp_all_mq && wv == 0xffffffffu;
+      uint32_t ve = 0u;                                  // DROP: logits of this row that are valid AND kept (the only ones with a gradient)
+      if constexpr (DROP) {
+        const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
+        ve = (mq ? wv : 0u) & drop_keep_word(rowh, attn_group(blk, kt), p.drop.thr8);
+      }
       mbar_wait_a(a_ready_a, j & 1);                     // S(j), dP(j) ready; dS buffer pb consumed by dQ (j-2)
       tcgen05_fence_after();
       uint32_t pk[16];
@@ -832,7 +873,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
           tcgen05_fence_before();
           mbar_arrive_a(s_free_a);
         }
-        if (fast) {
+        if constexpr (DROP) {
+          // surviving logit = q.k * drop.scale * scale; every other entry gets dS = 0 by a SELECT (its P may be inf / NaN)
+          const float ds_ = p.drop.scale;
+          const float2 sl2 = splat2(p.scale_log2 * ds_), nl2 = splat2(nlse2), sc2 = splat2(p.scale * ds_), nd2 = splat2(nds * ds_);
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            const float2 x = fma2(make_float2(__uint_as_float(rs[c]), __uint_as_float(rs[c + 1])), sl2, nl2);
+            const float2 pr = ex2_mufu2(x);
+            const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, nd2));
+            const float d0 = ((ve >> (hf * 16 + c)) & 1u) ? ds.x : 0.f, d1 = ((ve >> (hf * 16 + c + 1)) & 1u) ? ds.y : 0.f;
+            pk[hf * 8 + (c >> 1)] = pack_bf16x2(d0, d1);
+          }
+        } else if (fast) {
           const float2 sl2 = splat2(p.scale_log2), nl2 = splat2(nlse2), sc2 = splat2(p.scale), nd2 = splat2(nds);
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
@@ -889,8 +942,11 @@ struct QVec {
   float nds[NT];           // -delta * scale
   uint32_t mq;             // valid-query bits
   uint32_t pad[3];
+  uint32_t rh[NT];         // DROP: dropout row hash of each query (drop_rowhash of (b*H + h)*Lq + q)
 };
+constexpr uint32_t QVEC_RH_OFF = 2 * NT * 4 + 16;
 
+template <bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO, const AttnTcParams p) {
@@ -942,6 +998,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_wait_bg(&bars->kv_empty[st], ((i / BWD_STAGES) & 1) ^ 1);
       qv[st].nlse2[lane] = -lse_c * kLog2e;              // queries past Lq: -inf => P = 0
       qv[st].nds[lane] = -delta_c * p.scale;
+      if constexpr (DROP) qv[st].rh[lane] = drop_rowhash(p.drop.key, (uint64_t)(((int64_t)b * p.H + h) * p.Lq + i * NT + lane));
       const uint32_t mqb = __ballot_sync(0xffffffffu, mq_c);
       if (lane == 0) qv[st].mq = mqb;
       __syncwarp();
@@ -1008,7 +1065,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_wait_a(kv_full_a + st * 8, st_phase);         // acquire the loader's per-query vectors
       const uint32_t qva = qv_a + st * (uint32_t)sizeof(QVec);
       const uint32_t wq = lds_u1(qva + 2 * NT * 4);
-      const bool fast = warp_all_mk && wq == 0xffffffffu;
+      const bool fast = !DROP && warp_all_mk && wq == 0xffffffffu;
+      uint32_t Wq = 0u;                                  // DROP: keep word of (query `lane` of this tile, this warp's 32 keys)
+      if constexpr (DROP) Wq = drop_keep_word(lds_u1(qva + QVEC_RH_OFF + lane * 4), attn_group(blk, (k0 >> 5) + qd), p.drop.thr8);
       if (++st == BWD_STAGES) { st = 0; st_phase ^= 1; }
       mbar_wait_a(a_ready_a, i & 1);
       tcgen05_fence_after();
@@ -1023,7 +1082,23 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           tcgen05_fence_before();
           mbar_arrive_a(s_free_a);
         }
-        if (fast) {                                      // branch hoisted out of the element loops: straight-line FFMA / EX2 code
+        if constexpr (DROP) {
+          // column cc = query cc of the tile; this thread's key is bit `lane` of that query's keep word (shuffled in)
+          const float ds_ = p.drop.scale;
+          const float2 sl2 = splat2(p.scale_log2 * ds_), sc2 = splat2(p.scale * ds_), dsc2 = splat2(ds_);
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            const int cc = hf * 16 + c;
+            const float2 nl = lds_f2(qva + cc * 4), nd = lds_f2(qva + (NT + cc) * 4);
+            const bool k0_ = (__shfl_sync(0xffffffffu, Wq, cc) >> lane) & 1u, k1_ = (__shfl_sync(0xffffffffu, Wq, cc + 1) >> lane) & 1u;
+            const bool v0 = mk && ((wq >> cc) & 1u), v1 = mk && ((wq >> (cc + 1)) & 1u);
+            const float s0 = k0_ ? (v0 ? __uint_as_float(rs[c]) : -10000.0f) : 0.f, s1 = k1_ ? (v1 ? __uint_as_float(rs[c + 1]) : -10000.0f) : 0.f;
+            const float2 pr = ex2_mufu2(fma2(make_float2(s0, s1), sl2, nl));
+            const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, mul2(nd, dsc2)));
+            pp[hf * 8 + (c >> 1)] = pack_bf16x2(pr.x, pr.y);
+            pd[hf * 8 + (c >> 1)] = pack_bf16x2((k0_ && v0) ? ds.x : 0.f, (k1_ && v1) ? ds.y : 0.f);
+          }
+        } else if (fast) {                               // branch hoisted out of the element loops: straight-line FFMA / EX2 code
 #pragma unroll
           for (int c = 0; c < 16; c += 4) {
             const float4 nl = lds_f4(qva + (hf * 16 + c) * 4), nd = lds_f4(qva + (NT + hf * 16 + c) * 4);
@@ -1114,6 +1189,9 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
   p.scale = 1.0f / sqrtf((float)DH);
   p.scale_log2 = p.scale * kLog2e;
   p.fill_log2 = -10000.0f * p.scale * kLog2e;
+  p.drop = make_drop(a->drop);
+  MMI_CHECK_ARG(p.drop.thr8 < 256u, "attn_tc: dropout thr8 must be < 256");
+  const bool drop_on = p.drop.thr8 != 0u;
   for (int i = 0; i < a->nblk; ++i) {
     const mmi_attn_block& s = a->blk[i];
     MMI_CHECK_ARG(s.q && s.k && s.v && s.mask_k && s.Lk > 0, "attn_tc: block %d has null pointer / Lk<=0", i);
@@ -1126,7 +1204,8 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
   const int64_t q_rows = (int64_t)a->B * a->Lq;
   static size_t cfg_bytes[3] = {0, 0, 0};   // largest dynamic shared-memory size configured so far, per kernel
   const size_t bar_bytes = sizeof(Bars) + 1024 /*align*/;
-  static const bool fwd64 = []() { const char* e = getenv("MMI_ATTN_FWD64"); return e == nullptr || e[0] != '0'; }();
+  static const bool fwd64_env = []() { const char* e = getenv("MMI_ATTN_FWD64"); return e == nullptr || e[0] != '0'; }();
+  const bool fwd64 = fwd64_env || drop_on;    // the 32-key forward kernel (A/B only) has no dropout instantiation
   if (kind == 0 || kind == 1) {
     const uint32_t kbox = (kind == 0 && fwd64) ? NT64 : NT;
     CUtensorMap mQ[2], mK[2], mV[2], mdO;
@@ -1142,8 +1221,13 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
       static size_t cfg64 = 0;
       const size_t T = (a->blk[0].Lk + NT64 - 1) / NT64 + (a->nblk > 1 ? (a->blk[1].Lk + NT64 - 1) / NT64 : 0);
       const size_t smem = 2 * TILE128 + 4 * TILE64 + PTILE64 + bar_bytes + 16 + T * 16;
-      if (smem > cfg64) { int rc = set_smem(attn_fwd_tc64_kernel, smem); if (rc) return rc; cfg64 = smem; }
-      attn_fwd_tc64_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
+      if (smem > cfg64) {
+        int rc = set_smem(attn_fwd_tc64_kernel<false>, smem); if (rc) return rc;
+        rc = set_smem(attn_fwd_tc64_kernel<true>, smem); if (rc) return rc;
+        cfg64 = smem;
+      }
+      if (drop_on) attn_fwd_tc64_kernel<true><<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
+      else attn_fwd_tc64_kernel<false><<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
     } else if (kind == 0) {
       const size_t T = (a->blk[0].Lk + NT - 1) / NT + (a->nblk > 1 ? (a->blk[1].Lk + NT - 1) / NT : 0);
       const size_t smem = 2 * TILE128 + FWD_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes + T * 8;
@@ -1155,8 +1239,13 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
       if (!map_rows(a->dout, a->lddo, q_rows, width, QT, &mdO)) return MMI_ECUDA;
       const size_t T = (a->blk[0].Lk + NT - 1) / NT + (a->nblk > 1 ? (a->blk[1].Lk + NT - 1) / NT : 0);
       const size_t smem = 3 * TILE128 + BWD_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes + T * 8;
-      if (smem > cfg_bytes[1]) { int rc = set_smem(attn_bwd_dq_tc_kernel, smem); if (rc) return rc; cfg_bytes[1] = smem; }
-      attn_bwd_dq_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p);
+      if (smem > cfg_bytes[1]) {
+        int rc = set_smem(attn_bwd_dq_tc_kernel<false>, smem); if (rc) return rc;
+        rc = set_smem(attn_bwd_dq_tc_kernel<true>, smem); if (rc) return rc;
+        cfg_bytes[1] = smem;
+      }
+      if (drop_on) attn_bwd_dq_tc_kernel<true><<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p);
+      else attn_bwd_dq_tc_kernel<false><<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p);
     }
   } else {
     MMI_CHECK_ARG(which >= 0 && which < a->nblk, "attn_tc dkv: bad block index %d", which);
@@ -1174,8 +1263,13 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     if (!map_rows(s.v, s.ldv, k_rows, width, QT, &mV)) return MMI_ECUDA;
     dim3 grid((s.Lk + QT - 1) / QT, a->H, a->B);
     const size_t smem = 2 * TILE128 + 4 * 2 * TILE32 + 2 * TILE128 + BWD_STAGES * sizeof(QVec) + bar_bytes;
-    if (smem > cfg_bytes[2]) { int rc = set_smem(attn_bwd_dkv_tc_kernel, smem); if (rc) return rc; cfg_bytes[2] = smem; }
-    attn_bwd_dkv_tc_kernel<<<grid, ATT_THREADS, smem, st>>>(mQ, mK, mV, mdO, p);
+    if (smem > cfg_bytes[2]) {
+      int rc = set_smem(attn_bwd_dkv_tc_kernel<false>, smem); if (rc) return rc;
+      rc = set_smem(attn_bwd_dkv_tc_kernel<true>, smem); if (rc) return rc;
+      cfg_bytes[2] = smem;
+    }
+    if (drop_on) attn_bwd_dkv_tc_kernel<true><<<grid, ATT_THREADS, smem, st>>>(mQ, mK, mV, mdO, p);
+    else attn_bwd_dkv_tc_kernel<false><<<grid, ATT_THREADS, smem, st>>>(mQ, mK, mV, mdO, p);
   }
   MMI_CHECK_LAUNCH();
   return MMI_OK;

@@ -3,6 +3,7 @@
 // AdamW, and the fp32->bf16 parameter cast.  Reductions use warp shuffles; cross-CTA
 // reductions are two-stage (fixed order => run-to-run deterministic).
 #include "common.cuh"
+#include "dropout.cuh"
 #include <string.h>
 
 namespace mmi {
@@ -14,7 +15,8 @@ constexpr int kRedCtas = kNumSMs * 4;
 template <typename T, int NV>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, int64_t rows, int d,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            float eps, T* __restrict__ y, float* __restrict__ stats) {
+                                                            float eps, T* __restrict__ y, float* __restrict__ stats,
+                                                            const DropParams drop) {
   const int lane = threadIdx.x & 31;
   const int nvec = d >> 2;
   const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -45,6 +47,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
       stats[2 * row + 1] = rstd;
     }
     T* yr = y + row * (int64_t)d;
+    const uint32_t rowh = drop.thr8 ? drop_rowhash(drop.key, (uint64_t)row) : 0u;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
@@ -56,6 +59,11 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
         o.y = (v[i].y - mean) * rstd * g.y + b.y;
         o.z = (v[i].z - mean) * rstd * g.z + b.z;
         o.w = (v[i].w - mean) * rstd * g.w + b.w;
+        if (drop.thr8) {                                   // y = dropout(LN(x)): lane owns columns 4c .. 4c+3
+          const uint32_t w = drop_keep_word(rowh, (uint32_t)c >> 3, drop.thr8) >> ((c & 7) * 4);
+          o.x *= (w & 1u) ? drop.scale : 0.f; o.y *= (w & 2u) ? drop.scale : 0.f;
+          o.z *= (w & 4u) ? drop.scale : 0.f; o.w *= (w & 8u) ? drop.scale : 0.f;
+        }
         store4(yr + c * 4, o);
       }
     }
@@ -68,7 +76,8 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, int64_t rows, int d,
                                                             const float* __restrict__ gamma, const float* __restrict__ stats,
                                                             const T* __restrict__ add, T* __restrict__ dx,
-                                                            float* __restrict__ partial) {
+                                                            float* __restrict__ partial, const DropParams dy_drop,
+                                                            const DropParams dx_drop, T* __restrict__ dx_dropped) {
   extern __shared__ float sm[];  // [8 warps][2][d]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = d >> 2;
@@ -82,12 +91,19 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
     const T* dyr = dy + row * (int64_t)d;
     float4 xh[NV], g[NV];
     float c1 = 0.f, c2 = 0.f;
+    const uint32_t rowh_y = dy_drop.thr8 ? drop_rowhash(dy_drop.key, (uint64_t)row) : 0u;
+    const uint32_t rowh_x = dx_drop.thr8 ? drop_rowhash(dx_drop.key, (uint64_t)row) : 0u;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < nvec) {
         const float4 xv = load4(xr + c * 4);
-        const float4 dv = load4(dyr + c * 4);
+        float4 dv = load4(dyr + c * 4);
+        if (dy_drop.thr8) {                                // backward of y = dropout(LN(x)): dy <- mask * scale * dy
+          const uint32_t w = drop_keep_word(rowh_y, (uint32_t)c >> 3, dy_drop.thr8) >> ((c & 7) * 4);
+          dv.x *= (w & 1u) ? dy_drop.scale : 0.f; dv.y *= (w & 2u) ? dy_drop.scale : 0.f;
+          dv.z *= (w & 4u) ? dy_drop.scale : 0.f; dv.w *= (w & 8u) ? dy_drop.scale : 0.f;
+        }
         const float4 gm = *reinterpret_cast<const float4*>(gamma + c * 4);
         xh[i] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
         g[i] = make_float4(dv.x * gm.x, dv.y * gm.y, dv.z * gm.z, dv.w * gm.w);
@@ -116,6 +132,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
           o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
         }
         store4(dxr + c * 4, o);
+        if (dx_drop.thr8) {                                // gradient into the Linear behind the residual's dropout
+          const uint32_t w = drop_keep_word(rowh_x, (uint32_t)c >> 3, dx_drop.thr8) >> ((c & 7) * 4);
+          o.x *= (w & 1u) ? dx_drop.scale : 0.f; o.y *= (w & 2u) ? dx_drop.scale : 0.f;
+          o.z *= (w & 4u) ? dx_drop.scale : 0.f; o.w *= (w & 8u) ? dx_drop.scale : 0.f;
+          store4(dx_dropped + row * (int64_t)d + c * 4, o);
+        }
       }
     }
   }
@@ -154,11 +176,20 @@ __device__ __forceinline__ uint4 f32_to_bf16x8(const float* f) {
   return make_uint4(*reinterpret_cast<uint32_t*>(&p[0]), *reinterpret_cast<uint32_t*>(&p[1]), *reinterpret_cast<uint32_t*>(&p[2]), *reinterpret_cast<uint32_t*>(&p[3]));
 }
 
-template <int NV, bool WITH_DXSUM>
+// keep factors of the 8 consecutive columns (lane + 32 i) * 8 .. + 7 of one row: byte (lane & 3) of keep word (lane + 32 i) >> 2
+__device__ __forceinline__ void drop_factors8(const DropParams& dp, uint32_t rowh, int vec, float* kf) {
+  const uint32_t w = (drop_keep_word(rowh, (uint32_t)vec >> 2, dp.thr8) >> ((vec & 3) * 8)) & 0xffu;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) kf[j] = ((w >> j) & 1u) ? dp.scale : 0.f;
+}
+
+template <int NV, bool WITH_DXSUM, bool DROP>
 __global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                                     int64_t rows, const float* __restrict__ gamma,
                                                                     const float* __restrict__ stats, const __nv_bfloat16* __restrict__ add,
-                                                                    __nv_bfloat16* __restrict__ dx, float* __restrict__ partial) {
+                                                                    __nv_bfloat16* __restrict__ dx, float* __restrict__ partial,
+                                                                    const DropParams dy_drop, const DropParams dx_drop,
+                                                                    __nv_bfloat16* __restrict__ dx_dropped) {
   extern __shared__ float sm[];  // [8 warps][3][d]
   constexpr int d = 256 * NV;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -187,6 +218,21 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_b
         dv[r][i] = ldg_stream(reinterpret_cast<const uint4*>(dy + base) + lane + 32 * i);
       }
     }
+    if (DROP && dy_drop.thr8) {                            // backward of y = dropout(LN(x)): dy <- mask * scale * dy, in registers
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const uint32_t rowh = drop_rowhash(dy_drop.key, (uint64_t)((r == 0 || in1) ? rr[r] : row0));
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          float df[8], kf[8];
+          bf16x8_to_f32(dv[r][i], df);
+          drop_factors8(dy_drop, rowh, lane + 32 * i, kf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) df[j] *= kf[j];
+          dv[r][i] = f32_to_bf16x8(df);
+        }
+      }
+    }
     float c1[2] = {0.f, 0.f}, c2[2] = {0.f, 0.f};
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -213,6 +259,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_b
     for (int r = 0; r < 2; ++r) {
       if (r == 1 && !in1) break;
       const float m1 = c1[r] * (1.0f / d), m2 = c2[r] * (1.0f / d);
+      const uint32_t rowh_x = (DROP && dx_drop.thr8) ? drop_rowhash(dx_drop.key, (uint64_t)rr[r]) : 0u;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         float xf[8], df[8], o[8];
@@ -230,9 +277,18 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_b
           for (int j = 0; j < 8; ++j) o[j] += af[j];
         }
         const uint4 packed = f32_to_bf16x8(o);
+        uint4 summed = packed;
+        if (DROP && dx_drop.thr8) {                        // second output: the gradient behind the residual's dropout
+          float kf[8];
+          drop_factors8(dx_drop, rowh_x, lane + 32 * i, kf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] *= kf[j];
+          summed = f32_to_bf16x8(o);
+          stg_stream(reinterpret_cast<uint4*>(dx_dropped + rr[r] * (int64_t)d) + lane + 32 * i, summed);
+        }
         if (WITH_DXSUM) {                                  // sum what the next kernel will read (the rounded values)
           float of[8];
-          bf16x8_to_f32(packed, of);
+          bf16x8_to_f32(summed, of);
 #pragma unroll
           for (int j = 0; j < 8; ++j) ds[i][j] += of[j];
         }
@@ -783,19 +839,48 @@ static int grid_for_rows(int64_t rows, int warps_per_cta, int cap) {
   return (int)ctas;
 }
 
+
+// ------------------------------------------------------------------ dropout test hook
+__global__ void dropout_mask_kernel(const DropParams dp, int64_t row0, int64_t rows, int cols, uint32_t group0, uint8_t* __restrict__ mask) {
+  const int64_t n = rows * (int64_t)cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    const uint32_t w = dp.thr8 ? drop_keep_word(drop_rowhash(dp.key, (uint64_t)(row0 + r)), group0 + ((uint32_t)c >> 5), dp.thr8) : 0xffffffffu;
+    mask[i] = (w >> (c & 31)) & 1u;
+  }
+}
+
 }  // namespace mmi
 
 using namespace mmi;
 
+extern "C" int mmi_dropout_mask(const mmi_dropout* drop, int64_t row0, int64_t rows, int cols, uint32_t group0, uint8_t* mask,
+                                mmi_stream_t stream) {
+  MMI_CHECK_ARG(drop && mask && rows >= 0 && cols > 0, "dropout_mask: bad arguments");
+  MMI_CHECK_ARG(drop->thr8 < 256u, "dropout_mask: thr8 must be < 256");
+  if (rows == 0) return MMI_OK;
+  dropout_mask_kernel<<<kNumSMs * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(make_drop(*drop), row0, rows, cols, group0, mask);
+  MMI_CHECK_LAUNCH();
+  return MMI_OK;
+}
+
 extern "C" int mmi_layernorm_fwd(const void* x, int dtype, int64_t rows, int d, const float* gamma, const float* beta, float eps,
                                  void* y, float* stats, mmi_stream_t stream) {
+  return mmi_layernorm_fwd_drop(x, dtype, rows, d, gamma, beta, eps, y, stats, nullptr, stream);
+}
+
+extern "C" int mmi_layernorm_fwd_drop(const void* x, int dtype, int64_t rows, int d, const float* gamma, const float* beta, float eps,
+                                      void* y, float* stats, const mmi_dropout* drop, mmi_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const DropParams dp = drop ? make_drop(*drop) : drop_off();
+  MMI_CHECK_ARG(dp.thr8 < 256u, "layernorm_fwd: dropout thr8 must be < 256");
   MMI_CHECK_ARG(x && y && gamma && beta, "layernorm_fwd: null pointer");
   MMI_CHECK_ARG(d % 4 == 0 && d <= 128 * kMaxVecPerLane && d > 0, "layernorm: d=%d must be a multiple of 4 and <= %d", d, 128 * kMaxVecPerLane);
   if (rows == 0) return MMI_OK;
   const int grid = grid_for_rows(rows, 8, kNumSMs * 8);
   const int nv = d <= 128 ? 1 : (d <= 256 ? 2 : (d <= 512 ? 4 : 8));
-#define MMI_LN_FWD(T_, NV_) layernorm_fwd_kernel<T_, NV_><<<grid, 256, 0, st>>>((const T_*)x, rows, d, gamma, beta, eps, (T_*)y, stats)
+#define MMI_LN_FWD(T_, NV_) layernorm_fwd_kernel<T_, NV_><<<grid, 256, 0, st>>>((const T_*)x, rows, d, gamma, beta, eps, (T_*)y, stats, dp)
 #define MMI_LN_FWD_NV(T_) do { if (nv == 1) MMI_LN_FWD(T_, 1); else if (nv == 2) MMI_LN_FWD(T_, 2); else if (nv == 4) MMI_LN_FWD(T_, 4); else MMI_LN_FWD(T_, 8); } while (0)
   if (dtype == MMI_F32) MMI_LN_FWD_NV(float);
   else if (dtype == MMI_BF16) MMI_LN_FWD_NV(__nv_bfloat16);
@@ -811,28 +896,45 @@ extern "C" int64_t mmi_layernorm_bwd_workspace(int d) { return (int64_t)kRedCtas
 extern "C" int mmi_layernorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int d, const float* gamma, const float* stats,
                                  const void* add, void* dx, float* dgamma, float* dbeta, float* dxsum, float* workspace,
                                  mmi_stream_t stream) {
+  return mmi_layernorm_bwd_drop(dy, x, dtype, rows, d, gamma, stats, add, dx, dgamma, dbeta, dxsum, workspace, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int mmi_layernorm_bwd_drop(const void* dy, const void* x, int dtype, int64_t rows, int d, const float* gamma,
+                                      const float* stats, const void* add, void* dx, float* dgamma, float* dbeta, float* dxsum,
+                                      float* workspace, const mmi_dropout* dy_drop, const mmi_dropout* dx_drop, void* dx_dropped,
+                                      mmi_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MMI_CHECK_ARG(dy && x && gamma && stats && dx && workspace, "layernorm_bwd: null pointer");
+  const DropParams dyd = dy_drop ? make_drop(*dy_drop) : drop_off();
+  DropParams dxd = dx_drop ? make_drop(*dx_drop) : drop_off();
+  MMI_CHECK_ARG(dyd.thr8 < 256u && dxd.thr8 < 256u, "layernorm_bwd: dropout thr8 must be < 256");
+  MMI_CHECK_ARG(!(dx_drop && !dx_dropped), "layernorm_bwd: dx_drop needs the dx_dropped output");
+  if (dx_drop && dxd.thr8 == 0u) {   // site switched off: the dropped gradient IS dx (keep the two-output contract with thr8 = 1 .. 255 only)
+    set_error("layernorm_bwd: dx_drop with thr8 = 0; pass NULL and use dx");
+    return MMI_EINVAL;
+  }
+  const bool any_drop = dyd.thr8 != 0u || dxd.thr8 != 0u;
   MMI_CHECK_ARG(d % 4 == 0 && d <= 128 * kMaxVecPerLane && d > 0, "layernorm: d=%d must be a multiple of 4 and <= %d", d, 128 * kMaxVecPerLane);
   if (rows == 0) return MMI_OK;
   const bool al16 = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
-                      reinterpret_cast<uintptr_t>(add)) & 15) == 0;
+                      reinterpret_cast<uintptr_t>(add) | reinterpret_cast<uintptr_t>(dx_dropped)) & 15) == 0;
   if (dtype == MMI_BF16 && (d == 256 || d == 512 || d == 768 || d == 1024) && al16) {
     // bandwidth path: 16-byte vectors, two rows per warp in flight, dx column sums fused
     const int grid = grid_for_rows((rows + 1) / 2, 8, kNumSMs * 2);
     const int nq = dxsum ? 3 : 2;
     const size_t smem = (size_t)8 * nq * d * sizeof(float);
+#define MMI_LN_BWD16_K(NV_, DS_, DR_)                                                                                          \
+  do {                                                                                                                        \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_bf16_kernel<NV_, DS_, DR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    layernorm_bwd_bf16_kernel<NV_, DS_, DR_><<<grid, 256, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, rows, gamma, stats, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, workspace, dyd, dxd, (__nv_bfloat16*)dx_dropped); \
+  } while (0)
 #define MMI_LN_BWD16(NV_)                                                                                                     \
   do {                                                                                                                        \
-    if (dxsum) {                                                                                                              \
-      if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_bf16_kernel<NV_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      layernorm_bwd_bf16_kernel<NV_, true><<<grid, 256, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, rows, gamma, stats, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, workspace); \
-    } else {                                                                                                                  \
-      if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_bf16_kernel<NV_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      layernorm_bwd_bf16_kernel<NV_, false><<<grid, 256, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, rows, gamma, stats, (const __nv_bfloat16*)add, (__nv_bfloat16*)dx, workspace); \
-    }                                                                                                                         \
+    if (dxsum) { if (any_drop) MMI_LN_BWD16_K(NV_, true, true); else MMI_LN_BWD16_K(NV_, true, false); }                      \
+    else { if (any_drop) MMI_LN_BWD16_K(NV_, false, true); else MMI_LN_BWD16_K(NV_, false, false); }                          \
   } while (0)
     if (d == 256) MMI_LN_BWD16(1); else if (d == 512) MMI_LN_BWD16(2); else if (d == 768) MMI_LN_BWD16(3); else MMI_LN_BWD16(4);
+#undef MMI_LN_BWD16_K
 #undef MMI_LN_BWD16
     MMI_CHECK_LAUNCH();
     reduce_partials_kernel<<<(nq * d + 31) / 32, dim3(32, 8), 0, st>>>(workspace, grid, nq * d, d, dgamma, dbeta, dxsum);
@@ -845,7 +947,7 @@ extern "C" int mmi_layernorm_bwd(const void* dy, const void* x, int dtype, int64
 #define MMI_LN_BWD(T_, NV_)                                                                                                   \
   do {                                                                                                                        \
     if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_kernel<T_, NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    layernorm_bwd_kernel<T_, NV_><<<grid, 256, smem, st>>>((const T_*)dy, (const T_*)x, rows, d, gamma, stats, (const T_*)add, (T_*)dx, workspace); \
+    layernorm_bwd_kernel<T_, NV_><<<grid, 256, smem, st>>>((const T_*)dy, (const T_*)x, rows, d, gamma, stats, (const T_*)add, (T_*)dx, workspace, dyd, dxd, (T_*)dx_dropped); \
   } while (0)
 #define MMI_LN_BWD_NV(T_) do { if (nv == 1) MMI_LN_BWD(T_, 1); else if (nv == 2) MMI_LN_BWD(T_, 2); else if (nv == 4) MMI_LN_BWD(T_, 4); else MMI_LN_BWD(T_, 8); } while (0)
   if (dtype == MMI_F32) MMI_LN_BWD_NV(float);
@@ -857,7 +959,7 @@ extern "C" int mmi_layernorm_bwd(const void* dy, const void* x, int dtype, int64
   reduce_partials_kernel<<<(2 * d + 31) / 32, dim3(32, 8), 0, st>>>(workspace, grid, 2 * d, d, dgamma, dbeta, nullptr);
   MMI_CHECK_LAUNCH();
   if (dxsum) {   // generic path: separate column-sum pass over dx
-    const int rc = mmi_colsum_acc(dx, dtype, rows, d, d, dxsum, workspace, mmi_layernorm_bwd_workspace(d), stream);
+    const int rc = mmi_colsum_acc(dxd.thr8 ? dx_dropped : dx, dtype, rows, d, d, dxsum, workspace, mmi_layernorm_bwd_workspace(d), stream);
     if (rc) return rc;
   }
   return MMI_OK;

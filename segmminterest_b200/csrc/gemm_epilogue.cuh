@@ -2,6 +2,7 @@
 // include/mmi_b200.h for the op order).
 #pragma once
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace mmi {
 
@@ -20,6 +21,7 @@ struct GemmParams {
   int split_k;
   int save_act_grad;
   int mul_is_grad;
+  DropParams drop;     // dropout of act(z) before `add` (and of the saved gelu'(z)); thr8 = 0: off
 };
 
 // 4 consecutive columns n..n+3 of row m.  `lead` = this CTA owns the bias/add terms
@@ -30,14 +32,25 @@ __device__ __forceinline__ void gemm_epilogue4(const GemmParams& p, int64_t m, i
     const float4 b = *reinterpret_cast<const float4*>(p.bias + n);
     v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
   }
+  float keep[4] = {1.f, 1.f, 1.f, 1.f};   // dropout factor of the four columns (0 or scale)
+  if (p.drop.thr8 != 0u) {
+    const uint32_t w = drop_keep_word(drop_rowhash(p.drop.key, (uint64_t)m), (uint32_t)(n >> 5), p.drop.thr8) >> (n & 31);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) keep[j] = ((w >> j) & 1u) ? p.drop.scale : 0.f;
+  }
   if (p.preact != nullptr) {
     float4 z = make_float4(v[0], v[1], v[2], v[3]);
-    if (p.save_act_grad) z = make_float4(gelu_grad_f(v[0]), gelu_grad_f(v[1]), gelu_grad_f(v[2]), gelu_grad_f(v[3]));
+    if (p.save_act_grad)   // the saved derivative carries the dropout factor: the backward epilogue multiplies by it
+      z = make_float4(gelu_grad_f(v[0]) * keep[0], gelu_grad_f(v[1]) * keep[1], gelu_grad_f(v[2]) * keep[2], gelu_grad_f(v[3]) * keep[3]);
     store4(reinterpret_cast<TIN*>(p.preact) + m * p.ld_preact + n, z);
   }
   if (p.act == MMI_ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = gelu_f(v[j]);
+  }
+  if (p.drop.thr8 != 0u) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] *= keep[j];
   }
   if (p.mul_gelu_grad != nullptr) {
     const float4 z = load4(reinterpret_cast<const TIN*>(p.mul_gelu_grad) + m * p.ld_mul + n);
@@ -102,10 +115,17 @@ template <typename TIN, typename TOUT>
 __device__ __forceinline__ void gemm_epilogue2(const GemmParams& p, int64_t m, int64_t n, float v0, float v1, float b0, float b1,
                                                bool lead, int64_t add_row) {
   v0 += b0; v1 += b1;
+  float k0 = 1.f, k1 = 1.f;                  // dropout factors (generic register epilogue: one keep word per call)
+  if (p.drop.thr8 != 0u) {
+    const uint32_t w = drop_keep_word(drop_rowhash(p.drop.key, (uint64_t)m), (uint32_t)(n >> 5), p.drop.thr8) >> (n & 31);
+    k0 = (w & 1u) ? p.drop.scale : 0.f;
+    k1 = (w & 2u) ? p.drop.scale : 0.f;
+  }
   if (p.preact != nullptr)
     store2(reinterpret_cast<TIN*>(p.preact) + m * p.ld_preact + n,
-           p.save_act_grad ? make_float2(gelu_grad_fast(v0), gelu_grad_fast(v1)) : make_float2(v0, v1));
+           p.save_act_grad ? make_float2(gelu_grad_fast(v0) * k0, gelu_grad_fast(v1) * k1) : make_float2(v0, v1));
   if (p.act == MMI_ACT_GELU) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); }
+  v0 *= k0; v1 *= k1;
   if (p.mul_gelu_grad != nullptr) {
     const float2 z = load2(reinterpret_cast<const TIN*>(p.mul_gelu_grad) + m * p.ld_mul + n);
     if (p.mul_is_grad) { v0 *= z.x; v1 *= z.y; }

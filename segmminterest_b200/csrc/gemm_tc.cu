@@ -184,6 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const bool has_aux = aux_add || aux_mul;
     const bool second = p.preact != nullptr;           // host: never together with an aux operand
     const bool do_gelu = p.act == MMI_ACT_GELU;
+    const bool drop_on = p.drop.thr8 != 0u;
     auto issue_aux = [&](int t) {                      // lane 0 only
       const TileInfo ti = get_tile(t, m_tiles, n_tiles, num_kb, split);
 #pragma unroll
@@ -238,10 +239,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         uint8_t* row2 = tile2 + lane * 128;
         if (has_aux) mbar_wait(&aux_bar[k], it & 1);
         const float* pe_row = pe_add ? reinterpret_cast<const float*>(p.add) + ((int64_t)(m0 + lane) % p.add_mod) * p.ld_add + n0 : nullptr;
+        // dropout: the two keep words of this row's 64 columns (dropout.cuh); bit c of kw[w] = column n0 + 32 w + c survives
+        uint32_t kw0 = 0xffffffffu, kw1 = 0xffffffffu;
+        if (drop_on) {
+          const uint32_t rowh = drop_rowhash(p.drop.key, (uint64_t)(m0 + lane));
+          kw0 = drop_keep_word(rowh, (uint32_t)(n0 >> 5), p.drop.thr8);
+          kw1 = drop_keep_word(rowh, (uint32_t)(n0 >> 5) + 1u, p.drop.thr8);
+        }
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
           const int phys = (v ^ (lane & 7)) << 4;
           float x[8];
+          float kf[8];
+          if (drop_on) {
+            const uint32_t kb8 = ((v < 4 ? kw0 : kw1) >> ((8 * v) & 31)) & 0xffu;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) kf[j] = ((kb8 >> j) & 1u) ? p.drop.scale : 0.f;
+          }
 #pragma unroll
           for (int j = 0; j < 8; j += 4) {
             const float4 b = *reinterpret_cast<const float4*>(sbias + 8 * v + j);
@@ -256,6 +270,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               const float4 a = __ldg(reinterpret_cast<const float4*>(pe_row + 8 * v + j));
               x[j] += a.x; x[j + 1] += a.y; x[j + 2] += a.z; x[j + 3] += a.w;
             }
+          }
+          if (drop_on && !do_gelu) {                     // dropout(x W^T + b) BEFORE the residual is added
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] *= kf[j];
           }
           if (has_aux) {
             const uint4 a = *reinterpret_cast<const uint4*>(row1 + phys);
@@ -279,11 +297,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 if (p.save_act_grad) z[j] = fmaf(x[j] * 0.39894228040143267794f, e, cdf);
                 if (do_gelu) x[j] *= cdf;
               }
+              if (drop_on && do_gelu) {                  // dropout(gelu(z)); the saved gelu'(z) carries the same factor
+                x[j] *= kf[j];
+                if (p.save_act_grad) z[j] *= kf[j];
+              }
             }
             *reinterpret_cast<uint4*>(row2 + phys) = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
           } else if (do_gelu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = gelu_fast(x[j]);
+            for (int j = 0; j < 8; ++j) x[j] = drop_on ? gelu_fast(x[j]) * kf[j] : gelu_fast(x[j]);
           }
           *reinterpret_cast<uint4*>(row1 + phys) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
         }

@@ -16,6 +16,7 @@ class GradBuckets:
         self.group = group
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._hi = flat_grad.numel()      # everything at or above _hi has been handed to NCCL
         self._ready_lo = flat_grad.numel()
         self._works = []

@@ -19,6 +19,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib, ops
+from .dropout import DropSite, quantise, site_key
 from .ops import ACT_GELU, ACT_NONE, GEMM_NN, GEMM_NT, GEMM_TN, IMPL_SIMT, IMPL_TC
 
 ALIGN = 64  # floats (256 B): every parameter group starts on a TMA-friendly boundary
@@ -113,6 +114,12 @@ class Engine:
         self.flat_lp = None    # bf16 shadow of `flat` (bf16 mode)
         self.flat_lpT = None   # per-matrix transposed bf16 shadow (dgrad operand of the TC path)
         self.anchor = torch.zeros((), device=device, requires_grad=True)
+        # dropout (dropout.py): probability of the next forward (0 = off), run seed, forward-call counter
+        self.drop_p = 0.0
+        self.drop_p_mlp = None     # None: the FFN's inner dropout follows drop_p (the reference's 0.1 / 0.1)
+        self.drop_seed = int(torch.initial_seed())
+        self._drop_call = 0
+        self._drop_cur = None      # (thr8, scale, call) of the forward in flight, None = off
         self._ws = {}
         self._saved = None
         self.use_tc = cfg.precision == "bf16" and bool(_lib.load().mmi_has_tc())
@@ -304,19 +311,39 @@ class Engine:
             ok = M % 8 == 0 and N % 8 == 0
         return IMPL_TC if ok else IMPL_SIMT
 
+    # ------------------------------------------------------------------ dropout sites
+    DROP_EMB, DROP_ATTN, DROP_ATTN_OUT, DROP_MLP1, DROP_MLP2 = range(5)
+
+    def _site(self, tw, layer, side, kind):
+        """DropSite of one nn.Dropout call of the reference in the forward in flight (None when dropout is off):
+        kind DROP_EMB encoder.py:472/386, DROP_ATTN :145-150, DROP_ATTN_OUT :163-164, DROP_MLP1 mlp.py:21-22,
+        DROP_MLP2 encoder.py:198-202.  The key depends on (seed, forward-call counter, tower, layer, side, kind)."""
+        if self._drop_cur is None:
+            return None
+        thr8, scale, call = self._drop_cur
+        if kind == self.DROP_MLP1 and self.drop_p_mlp is not None:
+            thr8, scale = quantise(self.drop_p_mlp)
+            if not thr8:
+                return None
+        sid = (((0 if tw.tag == "b1" else 1) * 64 + layer) * 2 + (0 if side == "vid" else 1)) * 8 + kind
+        return DropSite(site_key(self.drop_seed, call, sid), thr8, scale)
+
     # ------------------------------------------------------------------ building blocks
     def _linear(self, x, M, K, wkey, bkey, N, out, *, act=ACT_NONE, preact=None, add=None, add_mod=0, ld_add=0,
-                n_prefix=None):
+                n_prefix=None, drop=None):
         """out[M,N] = act(x[M,K] W[N,K]^T + b) (+ add).  On the tensor-core path `preact` receives
         gelu'(z) instead of z (the backward epilogue then needs no erf; see mmi_gemm save_act_grad)."""
         lp = self.cfg.precision == "bf16"
         W = self.w(wkey, lp)
         ops.gemm(GEMM_NT, self._impl(M, N, K, GEMM_NT), x, K, W, K, out, N, M, N, K, bias=self.w(bkey), act=act,
-                 preact=preact, add=add, add_mod=add_mod, ld_add=ld_add, save_act_grad=self.use_tc and preact is not None)
+                 preact=preact, add=add, add_mod=add_mod, ld_add=ld_add, save_act_grad=self.use_tc and preact is not None,
+                 drop=drop)
 
-    def _linear_bwd(self, dy, x, M, N, K, wkey, bkey, dx, *, mul_gelu_grad=None, add=None, need_dx=True, bias_done=False):
+    def _linear_bwd(self, dy, x, M, N, K, wkey, bkey, dx, *, mul_gelu_grad=None, add=None, need_dx=True, bias_done=False,
+                    drop=None):
         """dW += dy^T x ; db += colsum(dy) ; dx = dy W (* gelu'(mul)) (+ add).  bias_done: the kernel that produced dy
-        (LayerNorm backward) already accumulated the bias gradient."""
+        (LayerNorm backward) already accumulated the bias gradient.  drop: dropout of the site that FOLLOWED the GELU whose
+        derivative is multiplied in (strict-parity path only: the tensor-core path folds it into the saved gelu')."""
         lp = self.cfg.precision == "bf16"
         if not bias_done:
             ops.colsum_acc(dy, M, N, N, self.g(bkey), self.red_ws)
@@ -330,10 +357,10 @@ class Engine:
         if need_dx:
             if self._impl(M, K, N, GEMM_NT) == IMPL_TC:
                 ops.gemm(GEMM_NT, IMPL_TC, dy, N, self.wT(wkey), N, dx, K, M, K, N, mul_gelu_grad=mul_gelu_grad, add=add,
-                         add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=self.use_tc)
+                         add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=self.use_tc, drop=drop)
             else:
                 ops.gemm(GEMM_NN, IMPL_SIMT, dy, N, self.w(wkey, lp), K, dx, K, M, K, N, mul_gelu_grad=mul_gelu_grad,
-                         add=add, add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=self.use_tc)
+                         add=add, add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=self.use_tc, drop=drop)
 
     # ------------------------------------------------------------------ forward
     def forward(self, usr_image, usr_mask, vid_image, vid_mask, usr_id=None, vid_id=None, refresh=True, need_bwd=True):
@@ -346,6 +373,12 @@ class Engine:
             self.refresh_low_precision()
         d = cfg.d_model
         self._need_bwd = need_bwd        # forward-only calls (mode="inference") skip the saved GELU' tensor
+        if self.drop_p > 0.0:            # a fresh set of masks per forward call: the counter goes into every site key
+            thr8, scale = quantise(self.drop_p)
+            self._drop_call += 1
+            self._drop_cur = (thr8, scale, self._drop_call) if thr8 else None
+        else:
+            self._drop_cur = None
         sv = {"towers": {}}
         outs = []
         B = Lv = None
@@ -452,7 +485,8 @@ class Engine:
                 table = table.view(-1, tw_cols)
                 ops.id_embed_fwd(table, ids, B, Ls[s], d, e, frame_w=self.w(k("frameid.w")) if s == "vid" else None,
                                  frame_b=self.w(k("frameid.b")) if s == "vid" else None, pe=pe)
-            ops.layernorm_fwd(e, Ts[s], d, self.w(k(f"{s}_ln.g")), self.w(k(f"{s}_ln.b")), x0, st)
+            ts[f"drop.emb.{s}"] = self._site(tw, 63, s, self.DROP_EMB)
+            ops.layernorm_fwd(e, Ts[s], d, self.w(k(f"{s}_ln.g")), self.w(k(f"{s}_ln.b")), x0, st, drop=ts[f"drop.emb.{s}"])
             ts[f"emb_pre.{s}"], ts[f"emb_st.{s}"] = e, st
             X[s] = x0
         esz = x0.element_size()
@@ -480,7 +514,8 @@ class Engine:
                 blocks = [dict(q=col(n, 0), k=col(n, 1), v=col(n, 2), mask_k=mask[KEY_SIDE[n]], Lk=Ls[KEY_SIDE[n]])
                           for n in ATTN_BLOCKS[cfg.ablation][s]]
                 attn_impl = IMPL_TC if (self.use_tc and d // H == 32 and d % 8 == 0) else IMPL_SIMT
-                side = ops.AttnSide(ops.dt(a_out), attn_impl, B, H, d // H, Ls[s], mask[s], a_out, d, lse, blocks)
+                side = ops.AttnSide(ops.dt(a_out), attn_impl, B, H, d // H, Ls[s], mask[s], a_out, d, lse, blocks,
+                                    drop=self._site(tw, i, s, self.DROP_ATTN))
                 side.fwd()
                 attn[s] = (side, a_out, lse)
             lay["attn"] = attn
@@ -493,12 +528,16 @@ class Engine:
                 p2 = self._buf(k(f"p2.{i}.{s}"), (Ts[s], d), T)
                 st2 = self._buf(k(f"st2.{i}.{s}"), (Ts[s], 2), torch.float32)
                 x2 = self._buf(k(f"x2.{i}.{s}"), (Ts[s], d), T)
-                self._linear(attn[s][1], Ts[s], d, k(f"L{i}.{s}.wo"), k(f"L{i}.{s}.bo"), d, p1, add=X[s], add_mod=Ts[s], ld_add=d)
+                dr = {kind: self._site(tw, i, s, kind) for kind in (self.DROP_ATTN_OUT, self.DROP_MLP1, self.DROP_MLP2)}
+                self._linear(attn[s][1], Ts[s], d, k(f"L{i}.{s}.wo"), k(f"L{i}.{s}.bo"), d, p1, add=X[s], add_mod=Ts[s], ld_add=d,
+                             drop=dr[self.DROP_ATTN_OUT])
                 ops.layernorm_fwd(p1, Ts[s], d, self.w(k(f"L{i}.{s}.ln1.g")), self.w(k(f"L{i}.{s}.ln1.b")), x1, st1)
-                self._linear(x1, Ts[s], d, k(f"L{i}.{s}.w1"), k(f"L{i}.{s}.b1"), d, g1, act=ACT_GELU, preact=z1 if self._need_bwd else None)
-                self._linear(g1, Ts[s], d, k(f"L{i}.{s}.w2"), k(f"L{i}.{s}.b2"), d, p2, add=x1, add_mod=Ts[s], ld_add=d)
+                self._linear(x1, Ts[s], d, k(f"L{i}.{s}.w1"), k(f"L{i}.{s}.b1"), d, g1, act=ACT_GELU, preact=z1 if self._need_bwd else None,
+                             drop=dr[self.DROP_MLP1])
+                self._linear(g1, Ts[s], d, k(f"L{i}.{s}.w2"), k(f"L{i}.{s}.b2"), d, p2, add=x1, add_mod=Ts[s], ld_add=d,
+                             drop=dr[self.DROP_MLP2])
                 ops.layernorm_fwd(p2, Ts[s], d, self.w(k(f"L{i}.{s}.ln2.g")), self.w(k(f"L{i}.{s}.ln2.b")), x2, st2)
-                lay[s] = dict(p1=p1, st1=st1, x1=x1, z1=z1, g1=g1, p2=p2, st2=st2)
+                lay[s] = dict(p1=p1, st1=st1, x1=x1, z1=z1, g1=g1, p2=p2, st2=st2, drop=dr)
                 X[s] = x2
             ts["layers"].append(lay)
         sv["towers"][tw.tag] = ts
@@ -634,18 +673,26 @@ class Engine:
             for s in sides:
                 a = lay[s]
                 pre = k(f"L{i}.{s}.")
+                dr = a["drop"]
+                # with dropout the LayerNorm backward writes two tensors: dp (residual branch) and dpm = dropout'(dp), the
+                # gradient into the Linear whose dropped-out output was added to the residual (its bias gradient sums dpm)
                 dp2 = scratch("dp2", s)
+                dp2m = scratch("dp2m", s) if dr[self.DROP_MLP2] is not None else dp2
                 ops.layernorm_bwd(dX[s], a["p2"], Ts[s], d, self.w(pre + "ln2.g"), a["st2"], None, dp2, self.g(pre + "ln2.g"),
-                                  self.g(pre + "ln2.b"), self.red_ws, dxsum=self.g(pre + "b2"))
+                                  self.g(pre + "ln2.b"), self.red_ws, dxsum=self.g(pre + "b2"), dx_drop=dr[self.DROP_MLP2],
+                                  dx_dropped=dp2m)
                 dz1 = scratch("dz1", s)
-                self._linear_bwd(dp2, a["g1"], Ts[s], d, d, pre + "w2", pre + "b2", dz1, mul_gelu_grad=a["z1"], bias_done=True)
+                self._linear_bwd(dp2m, a["g1"], Ts[s], d, d, pre + "w2", pre + "b2", dz1, mul_gelu_grad=a["z1"], bias_done=True,
+                                 drop=None if self.use_tc else dr[self.DROP_MLP1])
                 dx1 = scratch("dx1", s)
                 self._linear_bwd(dz1, a["x1"], Ts[s], d, d, pre + "w1", pre + "b1", dx1, add=dp2)
                 dp1 = scratch("dp1", s)
+                dp1m = scratch("dp1m", s) if dr[self.DROP_ATTN_OUT] is not None else dp1
                 ops.layernorm_bwd(dx1, a["p1"], Ts[s], d, self.w(pre + "ln1.g"), a["st1"], None, dp1, self.g(pre + "ln1.g"),
-                                  self.g(pre + "ln1.b"), self.red_ws, dxsum=self.g(pre + "bo"))
+                                  self.g(pre + "ln1.b"), self.red_ws, dxsum=self.g(pre + "bo"), dx_drop=dr[self.DROP_ATTN_OUT],
+                                  dx_dropped=dp1m)
                 da = scratch("da", s)
-                self._linear_bwd(dp1, lay["attn"][s][1], Ts[s], d, d, pre + "wo", pre + "bo", da, bias_done=True)
+                self._linear_bwd(dp1m, lay["attn"][s][1], Ts[s], d, d, pre + "wo", pre + "bo", da, bias_done=True)
                 dP1[s], dA[s] = dp1, da
             dqkv = {s: scratch("dqkv", s, nq[s] * d) for s in token_sides if nq[s]}
             esz = dqkv["vid"].element_size()
@@ -694,10 +741,11 @@ class Engine:
             de = self._buf(f"bw.de.{tw.tag}.{s}", (Ts[s], d), T)
             if kind == "image":
                 ops.layernorm_bwd(dX[s], ts[f"emb_pre.{s}"], Ts[s], d, self.w(k(f"{s}_ln.g")), ts[f"emb_st.{s}"], None, de,
-                                  self.g(k(f"{s}_ln.g")), self.g(k(f"{s}_ln.b")), self.red_ws, dxsum=self.g(k(f"{s}_proj.b")))
+                                  self.g(k(f"{s}_ln.g")), self.g(k(f"{s}_ln.b")), self.red_ws, dxsum=self.g(k(f"{s}_proj.b")),
+                                  dy_drop=ts[f"drop.emb.{s}"])
             else:
                 ops.layernorm_bwd(dX[s], ts[f"emb_pre.{s}"], Ts[s], d, self.w(k(f"{s}_ln.g")), ts[f"emb_st.{s}"], None, de,
-                                  self.g(k(f"{s}_ln.g")), self.g(k(f"{s}_ln.b")), self.red_ws)
+                                  self.g(k(f"{s}_ln.g")), self.g(k(f"{s}_ln.b")), self.red_ws, dy_drop=ts[f"drop.emb.{s}"])
             if cfg.use_pe:
                 # d pe[l,:] = sum_b dE[b,l,:]  -> column sums of dE viewed as [B, L*d]
                 ops.colsum_acc(de, B, Ls[s] * d, Ls[s] * d, self.g(k(f"{s}_pe"))[: Ls[s] * d], self.red_ws)

@@ -272,8 +272,16 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
                     others=others, mask_loss=int(getattr(self.model_cfg, "mask_loss", 0)),
                     ce_after_focal=after_focal("interestCE"), kl_after_focal=after_focal("interestKL"))
 
+    def dropout_p(self):
+        """Dropout probability of the next forward: nn.Module semantics -- the constructor value of the backbone
+        (the reference driver never passes one, so 0.1: models/encoder.py:342, main...SegMM.py:88-104) under train(), 0
+        under eval().  The FFN's inner dropout is MLP's own default 0.1 whatever the backbone was given
+        (kn_util/nn_utils/layers/mlp.py:8; models/encoder.py:183-184) -- it only differs when a caller overrides p."""
+        return float(self.backbone1.dropout_p) if self.training else 0.0
+
     def forward(self, usr_image, usr_id, usr_mask, vid_image, vid_id, vid_mask, gt=None, mode="train", **kwargs):
         eng = self.engine()
+        eng.drop_p = self.dropout_p()
         B = usr_id.shape[0]
         logits = eng.forward(usr_image, usr_mask, vid_image, vid_mask, usr_id=usr_id, vid_id=vid_id,
                              need_bwd=mode != "inference" and torch.is_grad_enabled())

@@ -31,6 +31,30 @@ def _need_cuda(*ts):
             raise _lib.MMIError("segmminterest_b200 kernels need CUDA tensors; there is no CPU fallback")
 
 
+def _drop(site):
+    """DropSite (dropout.py) or None -> mmi_dropout (thr8 = 0: off)"""
+    d = _lib.Dropout()
+    if site is not None and site.thr8:
+        d.key, d.thr8, d.scale = site.key, site.thr8, site.scale
+    else:
+        d.key, d.thr8, d.scale = 0, 0, 1.0
+    return d
+
+
+def _drop_ptr(site):
+    return C.byref(_drop(site)) if (site is not None and site.thr8) else None
+
+
+def dropout_mask(site, row0, rows, cols, mask, group0=0):
+    """test hook: mask[r, c] = 1 iff element (row0 + r, c) of the site survives"""
+    _need_cuda(mask)
+    assert mask.dtype == torch.uint8 and mask.is_contiguous() and mask.numel() == rows * cols
+    d = _drop(site)
+    rc = _lib.load().mmi_dropout_mask(C.byref(d), row0, rows, cols, group0, mask.data_ptr(), _stream())
+    _lib.check(rc, "mmi_dropout_mask")
+    LaunchCounter.n += 1
+
+
 class LaunchCounter:
     """Counts kernel launches issued through this module (bench.py `gpu_launches`)."""
     n = 0
@@ -51,7 +75,7 @@ def gather_l1norm(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor, mas
 
 def gemm(layout, impl, A, lda, B, ldb, Cm, ldc, M, N, K, *, bias=None, act=ACT_NONE, preact=None, mul_gelu_grad=None,
          add=None, add_mod=0, ld_add=0, accumulate=False, split_k=1, in_dtype=None, out_dtype=None, save_act_grad=False,
-         mul_is_grad=False):
+         mul_is_grad=False, drop=None):
     lib = _lib.load()
     a = _lib.GemmArgs()
     a.layout, a.impl = layout, impl
@@ -73,10 +97,11 @@ def gemm(layout, impl, A, lda, B, ldb, Cm, ldc, M, N, K, *, bias=None, act=ACT_N
     a.split_k = split_k
     a.save_act_grad = 1 if save_act_grad else 0
     a.mul_is_grad = 1 if mul_is_grad else 0
+    a.drop = _drop(drop)
     cat = "gemm_tc" if impl == IMPL_TC else "gemm_simt"
     if TIMER.detail:
         cat += f" {('NT', 'NN', 'TN')[layout]} M={M} N={N} K={K}" + (" gelu" if act else "") + (" mulgelu" if mul_gelu_grad is not None else "") \
-            + (" add" if add is not None else "") + (" acc" if accumulate else "")
+            + (" add" if add is not None else "") + (" acc" if accumulate else "") + (" drop" if a.drop.thr8 else "")
     with TIMER.region(cat, 2.0 * M * N * K):
         rc = lib.mmi_gemm(C.byref(a), _stream())
     _lib.check(rc, "mmi_gemm")
@@ -90,21 +115,28 @@ def colsum_acc(x, M, N, ldx, out, ws):
     LaunchCounter.n += 2
 
 
-def layernorm_fwd(x, rows, d, gamma, beta, y, stats, eps=1e-12):
+def layernorm_fwd(x, rows, d, gamma, beta, y, stats, eps=1e-12, drop=None):
+    """drop (DropSite): y = dropout(LN(x)) -- the embedding dropout (encoder.py:386,472)"""
     with TIMER.region("ln_fwd"):
-        rc = _lib.load().mmi_layernorm_fwd(x.data_ptr(), dt(x), rows, d, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(),
-                                           _ptr(stats), _stream())
+        rc = _lib.load().mmi_layernorm_fwd_drop(x.data_ptr(), dt(x), rows, d, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(),
+                                                _ptr(stats), _drop_ptr(drop), _stream())
     _lib.check(rc, "mmi_layernorm_fwd")
     LaunchCounter.n += 1
 
 
-def layernorm_bwd(dy, x, rows, d, gamma, stats, add, dx, dgamma, dbeta, ws, dxsum=None):
-    """dxsum (optional, fp32 [d]) += column sums of dx: the bias gradient of the Linear feeding this LayerNorm."""
+def layernorm_bwd(dy, x, rows, d, gamma, stats, add, dx, dgamma, dbeta, ws, dxsum=None, dy_drop=None, dx_drop=None,
+                  dx_dropped=None):
+    """dxsum (optional, fp32 [d]) += column sums of dx: the bias gradient of the Linear feeding this LayerNorm.
+    dy_drop: dy is read through the dropout mask of that site (backward of y = dropout(LN(x))).
+    dx_drop + dx_dropped: also writes mask * scale * dx, the gradient into the Linear whose dropped-out output was added to
+    the residual; dxsum then sums that tensor."""
     lib = _lib.load()
     assert ws.numel() >= lib.mmi_layernorm_bwd_workspace(d)
+    dxp = _drop_ptr(dx_drop)
     with TIMER.region("ln_bwd"):
-        rc = lib.mmi_layernorm_bwd(dy.data_ptr(), x.data_ptr(), dt(x), rows, d, gamma.data_ptr(), stats.data_ptr(), _ptr(add),
-                                   dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), ws.data_ptr(), _stream())
+        rc = lib.mmi_layernorm_bwd_drop(dy.data_ptr(), x.data_ptr(), dt(x), rows, d, gamma.data_ptr(), stats.data_ptr(), _ptr(add),
+                                        dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(dxsum), ws.data_ptr(), _drop_ptr(dy_drop),
+                                        dxp, _ptr(dx_dropped) if dxp is not None else None, _stream())
     _lib.check(rc, "mmi_layernorm_bwd")
     LaunchCounter.n += 2
 
@@ -112,8 +144,9 @@ def layernorm_bwd(dy, x, rows, d, gamma, stats, add, dx, dgamma, dbeta, ws, dxsu
 class AttnSide:
     """One query side of the 4-way attention: two key blocks sharing a softmax."""
 
-    def __init__(self, dtype, impl, B, H, dh, Lq, mask_q, out, ldo, lse, blocks):
+    def __init__(self, dtype, impl, B, H, dh, Lq, mask_q, out, ldo, lse, blocks, drop=None):
         a = _lib.AttnArgs()
+        a.drop = _drop(drop)           # logits dropout (encoder.py:145-150); the backward calls reuse it
         a.dtype, a.impl, a.B, a.H, a.dh, a.Lq = dtype, impl, B, H, dh, Lq
         a.mask_q = mask_q.data_ptr()
         a.nblk = len(blocks)

@@ -37,10 +37,13 @@ class DeviceGather:
 
 class TrainStep:
     def __init__(self, model, table: torch.Tensor, lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
-                 max_norm=10.0, process_group=None, global_batch=None, bucket_bytes=25 << 20):
+                 max_norm=10.0, process_group=None, global_batch=None, bucket_bytes=25 << 20, dropout=None):
+        """dropout: None follows the module (model.dropout_p(): the backbone's p under train(), 0 under eval()); a float
+        overrides it.  Every rank and every forward call draws its own masks (seed mixes torch.initial_seed() and the rank)."""
         self.model = model
         self.engine = model.engine()
         eng = self.engine
+        self.dropout = dropout
         self.gather = DeviceGather(table, eng.act_dtype)
         self.lr, self.wd, self.betas, self.eps, self.max_norm = lr, weight_decay, betas, eps, max_norm
         self.exp_avg = torch.zeros_like(eng.flat)
@@ -49,6 +52,7 @@ class TrainStep:
         self.ws = torch.empty(int(_lib.load().mmi_clip_adamw_workspace(eng.n_flat)), device=eng.device)
         self.step_no = 0
         self.buckets = GradBuckets(eng.flat_grad, process_group, bucket_bytes)
+        eng.drop_seed = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * self.buckets.rank) & 0xFFFFFFFFFFFFFFFF
         self.global_batch = global_batch
         self.loss_cfg = model.loss_cfg()
 
@@ -67,6 +71,7 @@ class TrainStep:
         gb = self.global_batch or B * self.buckets.world
         eng.bind_grads()           # Parameters' .grad alias the flat gradient buffer
         eng.flat_grad.zero_()
+        eng.drop_p = self.model.dropout_p() if self.dropout is None else float(self.dropout)
         mb = int(micro_batch) if micro_batch and micro_batch < B else B
         n_slices = (B + mb - 1) // mb
         total = None

@@ -135,8 +135,8 @@ def test_drop_in_training_loop_matches_oracle_adamw():
     dev = torch.device("cuda:0")
     args = make_args(d_model=64, nhead=2, num_layers_enc=3)
     torch.manual_seed(0)
-    model = build_model(args, din=48, max_usr_len=16).cuda()
-    model.train()  # NB: dropout is not applied by the engine yet (p=0 semantics)
+    model = build_model(args, din=48, max_usr_len=16, dropout=0.0).cuda()   # p = 0: the oracle side of this test has no masks
+    model.train()                                                           # (train()-mode dropout: tests/test_gpu_dropout.py)
     sd0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     live = mmi_oracle.live_param_names(list(sd0.keys()), 3)
     osd = {k: v.clone().requires_grad_(k in live) for k, v in sd0.items()}

@@ -57,6 +57,44 @@ def test_model_small_matches_reference(name):
     assert _rel(inf["logits"].numpy(), z["logits_inference"]) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["model_small_dropout", "model_small_dropout_crossatt"])
+def test_dropout_sites_match_reference_generator_stream(name):
+    """train() mode of the UNMODIFIED reference (nn.Dropout(0.1) at every site, torch generator seeded right before the
+    forward) against the oracle drawing from the same generator through its dropout hook: identical only if every site
+    sits at the same place, sees the same tensor shape and is drawn in the same order as in the reference -- including
+    the logits dropout between the -10000 fill and the scale.  This pins the PLACEMENT of the oracle's dropout sites;
+    the CUDA path is then compared with the oracle under its own counter-based masks (tests/test_gpu_dropout.py)."""
+    z = _load(name)
+    cfg = json.loads(str(z["cfg"]))
+    abl = cfg.get("ablation_type", "ours")
+    sd = {k[3:]: torch.from_numpy(z[k]).clone().requires_grad_(True) for k in z.files if k.startswith("sd/")}
+    torch.manual_seed(cfg["train_seed"])
+    out = mmi_oracle.forward(sd, torch.from_numpy(z["usr_image"]), torch.from_numpy(z["usr_mask"]),
+                             torch.from_numpy(z["vid_image"]), torch.from_numpy(z["vid_mask"]),
+                             torch.from_numpy(z["gt_in"]), nhead=cfg["nhead"], num_layers=cfg["num_layers_enc"], ablation_type=abl,
+                             drop=mmi_oracle.torch_dropout(0.1), full_usr=True)
+    assert _rel(out["logits"].detach().numpy(), z["logits"]) < 1e-5
+    assert abs(out["loss"].item() - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    out["loss"].backward()
+    dead = set(json.loads(str(z["dead_params"])))
+    n = 0
+    for k in sd:
+        if ("grad/" + k) not in z.files:
+            continue
+        assert k not in dead
+        g = sd[k].grad
+        assert g is not None, k
+        assert np.linalg.norm(g.numpy() - z["grad/" + k]) < 2e-5 * np.linalg.norm(z["grad/" + k]) + 1e-8, k
+        n += 1
+    assert n > 20
+    # and the masks matter: the eval-mode forward of the same weights differs visibly
+    ev = mmi_oracle.forward({k: v.detach() for k, v in sd.items()}, torch.from_numpy(z["usr_image"]), torch.from_numpy(z["usr_mask"]),
+                            torch.from_numpy(z["vid_image"]), torch.from_numpy(z["vid_mask"]), torch.from_numpy(z["gt_in"]),
+                            nhead=cfg["nhead"], num_layers=cfg["num_layers_enc"], mode="inference", ablation_type=abl)
+    assert _rel(ev["logits"].numpy(), z["logits_inference"]) < 1e-5
+    assert _rel(ev["logits"].numpy(), z["logits"]) > 1e-2
+
+
 @pytest.mark.parametrize("name", ["model_both_small", "model_id_small", "model_both_fh0", "model_both_fh-1", "model_both_fh-2"])
 def test_general_config_matches_reference(name):
     """ID-embedding inputs, two backbones + InteractionAggregation (the reference default 'both'),

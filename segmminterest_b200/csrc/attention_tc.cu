@@ -69,6 +69,18 @@ struct AttnTcParams {
 // (row = (b*H + h)*Lq + q, group = (blk << 20) + (k >> 5)): fwd / dq threads own a query row and generate one word per
 // 32 keys; dk/dv threads own a key, so lane c generates the word of query c of the tile and the warp shuffles them.
 __device__ __forceinline__ uint32_t attn_group(int blk, int k32) { return (static_cast<uint32_t>(blk) << 20) + static_cast<uint32_t>(k32); }
+// 32 x 32 bit-matrix transpose across a warp: lane l holds row l on entry and column l on exit (bit c of the result of
+// lane l = bit l of the input of lane c).  Five butterfly stages (one shuffle each) instead of 32 shuffles.
+__device__ __forceinline__ uint32_t warp_bit_transpose32(uint32_t x, int lane) {
+  uint32_t m = 0x0000ffffu;
+#pragma unroll
+  for (int j = 16; j >= 1; j >>= 1) {
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+    x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+    m ^= m << (j >> 1);
+  }
+  return x;
+}
 
 #ifdef MMI_ATTN_TRACE
 // debug build only: clock64 stamps of one CTA (blockIdx.z == gridDim.z / 2, x == 0, y == 0), read back by mmi_debug_trace
@@ -1066,8 +1078,13 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       const uint32_t qva = qv_a + st * (uint32_t)sizeof(QVec);
       const uint32_t wq = lds_u1(qva + 2 * NT * 4);
       const bool fast = !DROP && warp_all_mk && wq == 0xffffffffu;
-      uint32_t Wq = 0u;                                  // DROP: keep word of (query `lane` of this tile, this warp's 32 keys)
-      if constexpr (DROP) Wq = drop_keep_word(lds_u1(qva + QVEC_RH_OFF + lane * 4), attn_group(blk, (k0 >> 5) + qd), p.drop.thr8);
+      uint32_t kq = 0u;                                  // DROP: bit c = this thread's key is kept for query c of the tile
+      if constexpr (DROP) {
+        // lane c generates the keep word of (query c, this warp's 32 keys); the transpose hands every thread (= key) its
+        // own bit of all 32 words
+        const uint32_t Wq = drop_keep_word(lds_u1(qva + QVEC_RH_OFF + lane * 4), attn_group(blk, (k0 >> 5) + qd), p.drop.thr8);
+        kq = warp_bit_transpose32(Wq, lane);
+      }
       if (++st == BWD_STAGES) { st = 0; st_phase ^= 1; }
       mbar_wait_a(a_ready_a, i & 1);
       tcgen05_fence_after();
@@ -1083,20 +1100,34 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           mbar_arrive_a(s_free_a);
         }
         if constexpr (DROP) {
-          // column cc = query cc of the tile; this thread's key is bit `lane` of that query's keep word (shuffled in)
+          // column cc = query cc of the tile.  raw logit: valid ? q.k : -10000, then keep ? * drop.scale : 0; only logits that
+          // are valid AND kept pass a gradient (a SELECT: the P of the others may be anything)
           const float ds_ = p.drop.scale;
           const float2 sl2 = splat2(p.scale_log2 * ds_), sc2 = splat2(p.scale * ds_), dsc2 = splat2(ds_);
+          const uint32_t kqh = kq >> (hf * 16), wqh = wq >> (hf * 16);
+          if (warp_all_mk && wq == 0xffffffffu) {         // no masked key / padded query in this tile: one select per operand
 #pragma unroll
-          for (int c = 0; c < 16; c += 2) {
-            const int cc = hf * 16 + c;
-            const float2 nl = lds_f2(qva + cc * 4), nd = lds_f2(qva + (NT + cc) * 4);
-            const bool k0_ = (__shfl_sync(0xffffffffu, Wq, cc) >> lane) & 1u, k1_ = (__shfl_sync(0xffffffffu, Wq, cc + 1) >> lane) & 1u;
-            const bool v0 = mk && ((wq >> cc) & 1u), v1 = mk && ((wq >> (cc + 1)) & 1u);
-            const float s0 = k0_ ? (v0 ? __uint_as_float(rs[c]) : -10000.0f) : 0.f, s1 = k1_ ? (v1 ? __uint_as_float(rs[c + 1]) : -10000.0f) : 0.f;
-            const float2 pr = ex2_mufu2(fma2(make_float2(s0, s1), sl2, nl));
-            const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, mul2(nd, dsc2)));
-            pp[hf * 8 + (c >> 1)] = pack_bf16x2(pr.x, pr.y);
-            pd[hf * 8 + (c >> 1)] = pack_bf16x2((k0_ && v0) ? ds.x : 0.f, (k1_ && v1) ? ds.y : 0.f);
+            for (int c = 0; c < 16; c += 2) {
+              const float2 nl = lds_f2(qva + (hf * 16 + c) * 4), nd = lds_f2(qva + (NT + hf * 16 + c) * 4);
+              const bool k0_ = (kqh >> c) & 1u, k1_ = (kqh >> (c + 1)) & 1u;
+              const float s0 = k0_ ? __uint_as_float(rs[c]) : 0.f, s1 = k1_ ? __uint_as_float(rs[c + 1]) : 0.f;
+              const float2 pr = ex2_mufu2(fma2(make_float2(s0, s1), sl2, nl));
+              const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, mul2(nd, dsc2)));
+              pp[hf * 8 + (c >> 1)] = pack_bf16x2(pr.x, pr.y);
+              pd[hf * 8 + (c >> 1)] = pack_bf16x2(k0_ ? ds.x : 0.f, k1_ ? ds.y : 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+              const float2 nl = lds_f2(qva + (hf * 16 + c) * 4), nd = lds_f2(qva + (NT + hf * 16 + c) * 4);
+              const bool k0_ = (kqh >> c) & 1u, k1_ = (kqh >> (c + 1)) & 1u;
+              const bool v0 = mk && ((wqh >> c) & 1u), v1 = mk && ((wqh >> (c + 1)) & 1u);
+              const float s0 = k0_ ? (v0 ? __uint_as_float(rs[c]) : -10000.0f) : 0.f, s1 = k1_ ? (v1 ? __uint_as_float(rs[c + 1]) : -10000.0f) : 0.f;
+              const float2 pr = ex2_mufu2(fma2(make_float2(s0, s1), sl2, nl));
+              const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, mul2(nd, dsc2)));
+              pp[hf * 8 + (c >> 1)] = pack_bf16x2(pr.x, pr.y);
+              pd[hf * 8 + (c >> 1)] = pack_bf16x2((k0_ && v0) ? ds.x : 0.f, (k1_ && v1) ? ds.y : 0.f);
+            }
           }
         } else if (fast) {                               // branch hoisted out of the element loops: straight-line FFMA / EX2 code
 #pragma unroll

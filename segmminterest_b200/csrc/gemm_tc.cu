@@ -61,7 +61,9 @@ struct EpiMaps {
 
 constexpr int EBUF_BYTES = 32 * 64 * 2;   // 32 rows x 64 bf16 (one SWIZZLE_128B box per warp and chunk)
 
-template <int BN, bool MN_MAJOR, typename TOUT, bool TMA_EPI>
+// DROP (TMA epilogue only): dropout of act(z) fused into the epilogue.  The no-dropout instantiation is byte-for-byte the
+// kernel that existed before dropout was added; the generic register epilogue handles dropout at run time.
+template <int BN, bool MN_MAJOR, typename TOUT, bool TMA_EPI, bool DROP = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ EpiMaps em, const GemmParams p, int m_tiles, int n_tiles, int num_kb, int split) {
@@ -184,7 +186,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const bool has_aux = aux_add || aux_mul;
     const bool second = p.preact != nullptr;           // host: never together with an aux operand
     const bool do_gelu = p.act == MMI_ACT_GELU;
-    const bool drop_on = p.drop.thr8 != 0u;
+    constexpr bool drop_on = DROP;
+    // Linear -> dropout -> (+ residual): the survivors' scale rides in the bias add (x = acc * s + b * s), the mask is a
+    // select on bits of the row's keep words (compile-time bit positions: ptxas turns a byte of them into one R2P)
+    const float dscale = (drop_on && !do_gelu) ? p.drop.scale : 1.0f;
     auto issue_aux = [&](int t) {                      // lane 0 only
       const TileInfo ti = get_tile(t, m_tiles, n_tiles, num_kb, split);
 #pragma unroll
@@ -200,6 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const TileInfo ti = get_tile(t, m_tiles, n_tiles, num_kb, split);
       const uint32_t buf = it & 1, use = it >> 1;
       const int m0 = ti.m_blk * BM + q * 32;
+      const uint32_t rowh = drop_on ? drop_rowhash(p.drop.key, (uint64_t)(m0 + lane)) : 0u;    // overlaps the wait below
       mbar_wait(&tmem_full[buf], use & 1);
       tcgen05_fence_after();
       if (!has_aux) {                                  // last tile's stores have finished reading the staging buffers
@@ -230,6 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const int n = n0 + 2 * lane;
           float2 b = make_float2(0.f, 0.f);
           if (p.bias != nullptr && n < p.N) b = *reinterpret_cast<const float2*>(p.bias + n);
+          if constexpr (drop_on) { b.x *= dscale; b.y *= dscale; }
           *reinterpret_cast<float2*>(sbias + 2 * lane) = b;
         }
         __syncwarp();
@@ -241,28 +248,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const float* pe_row = pe_add ? reinterpret_cast<const float*>(p.add) + ((int64_t)(m0 + lane) % p.add_mod) * p.ld_add + n0 : nullptr;
         // dropout: the two keep words of this row's 64 columns (dropout.cuh); bit c of kw[w] = column n0 + 32 w + c survives
         uint32_t kw0 = 0xffffffffu, kw1 = 0xffffffffu;
-        if (drop_on) {
-          const uint32_t rowh = drop_rowhash(p.drop.key, (uint64_t)(m0 + lane));
+        if constexpr (drop_on) {
           kw0 = drop_keep_word(rowh, (uint32_t)(n0 >> 5), p.drop.thr8);
           kw1 = drop_keep_word(rowh, (uint32_t)(n0 >> 5) + 1u, p.drop.thr8);
         }
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
           const int phys = (v ^ (lane & 7)) << 4;
+          const uint32_t kb8 = (v < 4 ? kw0 : kw1) >> ((8 * v) & 31);      // bits 0..7: this vector's columns
           float x[8];
-          float kf[8];
-          if (drop_on) {
-            const uint32_t kb8 = ((v < 4 ? kw0 : kw1) >> ((8 * v) & 31)) & 0xffu;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) kf[j] = ((kb8 >> j) & 1u) ? p.drop.scale : 0.f;
-          }
 #pragma unroll
           for (int j = 0; j < 8; j += 4) {
             const float4 b = *reinterpret_cast<const float4*>(sbias + 8 * v + j);
-            x[j] = __uint_as_float(acc[8 * v + j]) + b.x;
-            x[j + 1] = __uint_as_float(acc[8 * v + j + 1]) + b.y;
-            x[j + 2] = __uint_as_float(acc[8 * v + j + 2]) + b.z;
-            x[j + 3] = __uint_as_float(acc[8 * v + j + 3]) + b.w;
+            if constexpr (drop_on) {
+              x[j] = fmaf(__uint_as_float(acc[8 * v + j]), dscale, b.x);
+              x[j + 1] = fmaf(__uint_as_float(acc[8 * v + j + 1]), dscale, b.y);
+              x[j + 2] = fmaf(__uint_as_float(acc[8 * v + j + 2]), dscale, b.z);
+              x[j + 3] = fmaf(__uint_as_float(acc[8 * v + j + 3]), dscale, b.w);
+            } else {
+              x[j] = __uint_as_float(acc[8 * v + j]) + b.x;
+              x[j + 1] = __uint_as_float(acc[8 * v + j + 1]) + b.y;
+              x[j + 2] = __uint_as_float(acc[8 * v + j + 2]) + b.z;
+              x[j + 3] = __uint_as_float(acc[8 * v + j + 3]) + b.w;
+            }
           }
           if (pe_add) {
 #pragma unroll
@@ -273,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           if (drop_on && !do_gelu) {                     // dropout(x W^T + b) BEFORE the residual is added
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] *= kf[j];
+            for (int j = 0; j < 8; ++j) x[j] = ((kb8 >> j) & 1u) ? x[j] : 0.f;
           }
           if (has_aux) {
             const uint4 a = *reinterpret_cast<const uint4*>(row1 + phys);
@@ -298,14 +306,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 if (do_gelu) x[j] *= cdf;
               }
               if (drop_on && do_gelu) {                  // dropout(gelu(z)); the saved gelu'(z) carries the same factor
-                x[j] *= kf[j];
-                if (p.save_act_grad) z[j] *= kf[j];
+                x[j] = ((kb8 >> j) & 1u) ? x[j] * p.drop.scale : 0.f;
+                if (p.save_act_grad) z[j] = ((kb8 >> j) & 1u) ? z[j] * p.drop.scale : 0.f;
               }
             }
             *reinterpret_cast<uint4*>(row2 + phys) = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
           } else if (do_gelu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = drop_on ? gelu_fast(x[j]) * kf[j] : gelu_fast(x[j]);
+            for (int j = 0; j < 8; ++j) x[j] = (drop_on && !((kb8 >> j) & 1u)) ? 0.f : gelu_fast(x[j]) * (drop_on ? p.drop.scale : 1.0f);
           }
           *reinterpret_cast<uint4*>(row1 + phys) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
         }
@@ -393,19 +401,19 @@ constexpr size_t smem_bytes() {
          (TMA_EPI ? 1024 /*barriers*/ + EPI_WARPS * 2 * EBUF_BYTES + EPI_WARPS * 64 * 4 : 256 /*barriers*/ + EPI_WARPS * STG_BYTES);
 }
 
-template <int BN, bool MN_MAJOR, typename TOUT, bool TMA_EPI>
+template <int BN, bool MN_MAJOR, typename TOUT, bool TMA_EPI, bool DROP = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmParams& p, int m_tiles, int n_tiles,
                   int num_kb, int split, cudaStream_t st) {
   constexpr size_t smem = smem_bytes<BN, TMA_EPI>();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MN_MAJOR, TOUT, TMA_EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MN_MAJOR, TOUT, TMA_EPI, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return MMI_ECUDA; }
     configured = true;
   }
   const int total = m_tiles * n_tiles * split;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  gemm_tc_kernel<BN, MN_MAJOR, TOUT, TMA_EPI><<<grid, NUM_THREADS, smem, st>>>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split);
+  gemm_tc_kernel<BN, MN_MAJOR, TOUT, TMA_EPI, DROP><<<grid, NUM_THREADS, smem, st>>>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split);
   MMI_CHECK_LAUNCH();
   return MMI_OK;
 }
@@ -478,6 +486,10 @@ int gemm_tc(const GemmParams& p_in, cudaStream_t st) {
     em.aux = em.c; em.c2 = em.c;
     if (aux && !get_tensor_map(aux, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)ld_aux, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &em.aux)) return MMI_ECUDA;
     if (p.preact && !get_tensor_map(p.preact, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ld_preact, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &em.c2)) return MMI_ECUDA;
+    if (p.drop.thr8 != 0u) {
+      if (bn == 256) return launch<256, false, __nv_bfloat16, true, true>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st);
+      return launch<128, false, __nv_bfloat16, true, true>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st);
+    }
     if (bn == 256) return launch<256, false, __nv_bfloat16, true>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st);
     return launch<128, false, __nv_bfloat16, true>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st);
   }

@@ -25,15 +25,16 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--table", action="store_true")
+    ap.add_argument("--dropout", type=float, default=0.1, help="0 = eval()-mode arithmetic")
     a = ap.parse_args()
     wl = synth.WORKLOADS[a.workload]
     B = a.batch or wl.batch
     dev = torch.device("cuda:0")
     torch.manual_seed(42)
-    model = build_model(model_args(a.precision), din=wl.din, max_usr_len=wl.lt).to(dev).eval()
+    model = build_model(model_args(a.precision), din=wl.din, max_usr_len=wl.lt).to(dev).train(a.dropout > 0)
     g = torch.Generator(device=dev).manual_seed(1234)
     table = torch.randn(wl.n_rows, wl.din, generator=g, device=dev)
-    ts = TrainStep(model, table, global_batch=B)
+    ts = TrainStep(model, table, global_batch=B, dropout=a.dropout)
     u, v, gt = synth.make_indices(B, wl.lt, wl.segs_per_video, wl.n_rows, seed=2025)
     u, v, gt = torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev), torch.from_numpy(gt).to(dev)
     for _ in range(a.warmup):

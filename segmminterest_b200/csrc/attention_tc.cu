@@ -980,49 +980,56 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const int rows_valid = min(QT, Lk - k0);
   const int nact = (rows_valid + 31) >> 5;
 
-  if (warp == 0 && elect_one()) {                        // K, V of the CTA's rows leave before the TMEM allocation
-    init_bars(bars, 32 * nact);
-    mbar_expect_tx(&bars->once, 2 * TILE128);
-    tma_load_2d(&tmK, &bars->once, sK, h * DH, b * Lk + k0);
-    tma_load_2d(&tmV, &bars->once, sV, h * DH, b * Lk + k0);
+  // Producer state (warp 0).  The per-query vectors (one query per lane) are fetched one tile AHEAD so that their
+  // global-load latency overlaps the wait for a free stage instead of pacing the whole pipeline.
+  float lse_n = 0.f, delta_n = 0.f;
+  uint8_t mq_n = 0;
+  auto fetch = [&](int i) {
+    const int qi = i * NT + lane;
+    if (qi < p.Lq) {
+      const int64_t li = ((int64_t)b * p.H + h) * p.Lq + qi;
+      lse_n = p.lse[li]; delta_n = p.delta[li]; mq_n = p.mask_q[(int64_t)b * p.Lq + qi];
+    } else { lse_n = INFINITY; delta_n = 0.f; mq_n = 0; }
+  };
+  auto produce = [&](int i, bool wait) {                 // whole warp 0: per-query vectors + Q, dO of query tile i into stage i % BWD_STAGES
+    const int st = i % BWD_STAGES;
+    const float lse_c = lse_n, delta_c = delta_n;
+    const bool mq_c = mq_n != 0;
+    if (i + 1 < T) fetch(i + 1);
+    if (wait) mbar_wait_bg(&bars->kv_empty[st], ((i / BWD_STAGES) & 1) ^ 1);
+    qv[st].nlse2[lane] = -lse_c * kLog2e;                // queries past Lq: -inf => P = 0
+    qv[st].nds[lane] = -delta_c * p.scale;
+    if constexpr (DROP) qv[st].rh[lane] = drop_rowhash(p.drop.key, (uint64_t)(((int64_t)b * p.H + h) * p.Lq + i * NT + lane));
+    const uint32_t mqb = __ballot_sync(0xffffffffu, mq_c);
+    if (lane == 0) qv[st].mq = mqb;
+    __syncwarp();
+    if (elect_one()) {
+      mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
+      uint8_t* dst = sQdO + st * 2 * TILE32;
+      const int row = b * p.Lq + i * NT;
+      tma_load_2d(&tmQ, &bars->kv_full[st], dst, h * DH, row);
+      tma_load_2d(&tmdO, &bars->kv_full[st], dst + TILE32, h * DH, row);
+    }
+    __syncwarp();
+  };
+  if (warp == 0) {
+    // K, V of the CTA's rows AND the first query tiles (one per ring stage) leave before the TMEM allocation and the
+    // CTA-wide sync: every load of the prologue is in flight at once (candidate-side launches have only 2 query tiles)
+    fetch(0);
+    if (elect_one()) {
+      init_bars(bars, 32 * nact);
+      mbar_expect_tx(&bars->once, 2 * TILE128);
+      tma_load_2d(&tmK, &bars->once, sK, h * DH, b * Lk + k0);
+      tma_load_2d(&tmV, &bars->once, sV, h * DH, b * Lk + k0);
+    }
+    __syncwarp();
+    for (int i = 0; i < min(T, BWD_STAGES); ++i) produce(i, false);     // the ring starts empty: no wait for these stages
   }
   const uint32_t tmem = tmem_setup(bars, warp, 128);
   const uint32_t tdPT = tmem + NT, tdK = tmem + 2 * NT, tdV = tmem + 2 * NT + DH;
 
   if (warp == 0) {
-    // per-query vectors (one query per lane) are fetched one tile AHEAD so that their global-load latency
-    // overlaps the wait for a free stage instead of pacing the whole pipeline
-    float lse_n = 0.f, delta_n = 0.f;
-    uint8_t mq_n = 0;
-    auto fetch = [&](int i) {
-      const int qi = i * NT + lane;
-      if (qi < p.Lq) {
-        const int64_t li = ((int64_t)b * p.H + h) * p.Lq + qi;
-        lse_n = p.lse[li]; delta_n = p.delta[li]; mq_n = p.mask_q[(int64_t)b * p.Lq + qi];
-      } else { lse_n = INFINITY; delta_n = 0.f; mq_n = 0; }
-    };
-    fetch(0);
-    for (int i = 0; i < T; ++i) {
-      const int st = i % BWD_STAGES;
-      const float lse_c = lse_n, delta_c = delta_n;
-      const bool mq_c = mq_n != 0;
-      if (i + 1 < T) fetch(i + 1);
-      mbar_wait_bg(&bars->kv_empty[st], ((i / BWD_STAGES) & 1) ^ 1);
-      qv[st].nlse2[lane] = -lse_c * kLog2e;              // queries past Lq: -inf => P = 0
-      qv[st].nds[lane] = -delta_c * p.scale;
-      if constexpr (DROP) qv[st].rh[lane] = drop_rowhash(p.drop.key, (uint64_t)(((int64_t)b * p.H + h) * p.Lq + i * NT + lane));
-      const uint32_t mqb = __ballot_sync(0xffffffffu, mq_c);
-      if (lane == 0) qv[st].mq = mqb;
-      __syncwarp();
-      if (elect_one()) {
-        mbar_expect_tx(&bars->kv_full[st], 2 * TILE32);
-        uint8_t* dst = sQdO + st * 2 * TILE32;
-        const int row = b * p.Lq + i * NT;
-        tma_load_2d(&tmQ, &bars->kv_full[st], dst, h * DH, row);
-        tma_load_2d(&tmdO, &bars->kv_full[st], dst + TILE32, h * DH, row);
-      }
-      __syncwarp();
-    }
+    for (int i = BWD_STAGES; i < T; ++i) produce(i, true);
   } else if (warp == 1) {
     const uint32_t tS = uniform(tmem), tdPTu = uniform(tdPT), tdKu = uniform(tdK), tdVu = uniform(tdV);
     mbar_wait(&bars->once, 0);

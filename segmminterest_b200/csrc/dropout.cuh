@@ -38,9 +38,8 @@ __host__ __device__ __forceinline__ uint32_t drop_mix32(uint32_t x) {
 __host__ __device__ __forceinline__ uint32_t drop_rowhash(uint32_t key, uint64_t row) {
   return drop_mix32(key + static_cast<uint32_t>(row) * 0x9E3779B1u + static_cast<uint32_t>(row >> 32) * 0x85EBCA77u);
 }
-// bit c of the result = 1 iff element (row, 32 * group + c) is KEPT
-__host__ __device__ __forceinline__ uint32_t drop_keep_word(uint32_t rowh, uint32_t group, uint32_t thr8) {
-  const uint32_t h0 = drop_mix32(rowh + group * 0xC2B2AE3Du);
+// bit c of the result = 1 iff the 8-bit number of position c (bit-sliced over the eight planes of h0) is >= thr8
+__host__ __device__ __forceinline__ uint32_t drop_compare_planes(uint32_t h0, uint32_t thr8) {
   constexpr uint32_t M[8] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
   constexpr uint32_t A[8] = {0x7F4A7C15u, 0x94D049BBu, 0xBF58476Du, 0x1CE4E5B9u, 0x133111EBu, 0x2545F491u, 0x4CF5AD43u, 0x2127599Bu};
   uint32_t lt = 0u, eq = 0xffffffffu;
@@ -53,6 +52,13 @@ __host__ __device__ __forceinline__ uint32_t drop_keep_word(uint32_t rowh, uint3
     eq &= ~(b ^ t);
   }
   return ~lt;
+}
+// bit c of the result = 1 iff element (row, 32 * group + c) is KEPT
+__host__ __device__ __forceinline__ uint32_t drop_keep_word(uint32_t rowh, uint32_t group, uint32_t thr8) {
+  const uint32_t h0 = drop_mix32(rowh + group * 0xC2B2AE3Du);
+  // the reference's p = 0.1 (thr8 = 26 = 0b00011010) gets a constant-folded comparator: 11 logic ops instead of 24
+  if (thr8 == 26u) return drop_compare_planes(h0, 26u);
+  return drop_compare_planes(h0, thr8);
 }
 
 }  // namespace mmi

@@ -795,6 +795,21 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
     for (int j = 0; j < min(T, BWD_STAGES); ++j) load_kv(j);
   }
   build_key_bits(kbits, p, b, nt0, T, warp, lane, ATT_THREADS / 32);
+  // per-row operands of the softmax threads (mask byte, lse, the O and dO rows behind delta) are requested BEFORE the TMEM
+  // allocation / CTA-wide sync and consumed after it, so their global-load latency is not exposed
+  const int qi_pre = q0 + (warp & 3) * 32 + lane;
+  const bool pre_in = warp >= 2 && qi_pre < p.Lq;
+  uint8_t mq_pre = 0;
+  float lse_pre = 0.f;
+  uint2 o_pre[DH / 4], do_pre[DH / 4];
+  if (pre_in) {
+    mq_pre = p.mask_q[(int64_t)b * p.Lq + qi_pre];
+    lse_pre = p.lse[((int64_t)b * p.H + h) * p.Lq + qi_pre];
+    const uint2* orow = reinterpret_cast<const uint2*>(p.out + ((int64_t)b * p.Lq + qi_pre) * p.ldo + h * DH);
+    const uint2* dorow = reinterpret_cast<const uint2*>(p.dout + ((int64_t)b * p.Lq + qi_pre) * p.lddo + h * DH);
+#pragma unroll
+    for (int d = 0; d < DH / 4; ++d) { o_pre[d] = orow[d]; do_pre[d] = dorow[d]; }
+  }
   const uint32_t tmem = tmem_setup(bars, warp, 128);
   const uint32_t tdP = tmem + NT, tdQ = tmem + 2 * NT;
 
@@ -843,21 +858,19 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_con
     const int qd = warp & 3, row = qd * 32 + lane;
     const int qi = q0 + row;
     const bool q_in = qi < p.Lq;
-    const bool mq = q_in ? (p.mask_q[(int64_t)b * p.Lq + qi] != 0) : false;
+    const bool mq = q_in ? (mq_pre != 0) : false;
     const bool warp_all_mq = __all_sync(0xffffffffu, mq);
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     float delta = 0.f, nlse2 = -INFINITY;               // rows past Lq: p = exp2(-inf) = 0
     if (q_in) {
-      const __nv_bfloat16* orow = p.out + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH;
-      const __nv_bfloat16* dorow = p.dout + ((int64_t)b * p.Lq + qi) * p.lddo + h * DH;
 #pragma unroll
-      for (int d = 0; d < DH; d += 4) {
-        const float4 a = load4(orow + d), g = load4(dorow + d);
-        delta += a.x * g.x + a.y * g.y + a.z * g.z + a.w * g.w;
+      for (int d = 0; d < DH / 4; ++d) {
+        const uint2 a = o_pre[d], g = do_pre[d];
+        delta += __uint_as_float(a.x << 16) * __uint_as_float(g.x << 16) + __uint_as_float(a.x & 0xffff0000u) * __uint_as_float(g.x & 0xffff0000u) +
+                 __uint_as_float(a.y << 16) * __uint_as_float(g.y << 16) + __uint_as_float(a.y & 0xffff0000u) * __uint_as_float(g.y & 0xffff0000u);
       }
-      const int64_t li = ((int64_t)b * p.H + h) * p.Lq + qi;
-      nlse2 = -p.lse[li] * kLog2e;
-      p.delta[li] = delta;
+      nlse2 = -lse_pre * kLog2e;
+      p.delta[((int64_t)b * p.H + h) * p.Lq + qi] = delta;
     }
     const float nds = -delta * p.scale;                  // dS = P * (dP * scale + nds)
     const uint32_t a_ready_a = smem_u32(&bars->a_ready[0]), s_free_a = smem_u32(&bars->s_free[0]), p_ready_a = smem_u32(&bars->p_ready[0]);
@@ -995,7 +1008,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int st = i % BWD_STAGES;
     const float lse_c = lse_n, delta_c = delta_n;
     const bool mq_c = mq_n != 0;
-    if (i + 1 < T) fetch(i + 1);
+    if (wait && i + 1 < T) fetch(i + 1);                 // steady state: the next tile's vectors are requested one tile ahead
     if (wait) mbar_wait_bg(&bars->kv_empty[st], ((i / BWD_STAGES) & 1) ^ 1);
     qv[st].nlse2[lane] = -lse_c * kLog2e;                // queries past Lq: -inf => P = 0
     qv[st].nds[lane] = -delta_c * p.scale;
@@ -1023,10 +1036,35 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tma_load_2d(&tmV, &bars->once, sV, h * DH, b * Lk + k0);
     }
     __syncwarp();
-    for (int i = 0; i < min(T, BWD_STAGES); ++i) produce(i, false);     // the ring starts empty: no wait for these stages
+    // the ring starts empty: its first stages are produced without waiting; their per-query vectors are requested back
+    // to back (three load latencies in parallel, not in series) before any of them is consumed
+    float l3[BWD_STAGES], d3[BWD_STAGES];
+    uint8_t m3[BWD_STAGES];
+    l3[0] = lse_n; d3[0] = delta_n; m3[0] = mq_n;
+#pragma unroll
+    for (int i = 1; i < BWD_STAGES; ++i) {
+      if (i < T) fetch(i);
+      l3[i] = lse_n; d3[i] = delta_n; m3[i] = mq_n;
+    }
+    if (BWD_STAGES < T) fetch(BWD_STAGES);               // leaves (lse_n, delta_n, mq_n) = tile BWD_STAGES for the steady-state loop
+    const float l_s = lse_n, d_s = delta_n;
+    const uint8_t m_s = mq_n;
+#pragma unroll
+    for (int i = 0; i < BWD_STAGES; ++i) {
+      if (i < T) {
+        lse_n = l3[i]; delta_n = d3[i]; mq_n = m3[i];
+        produce(i, false);
+      }
+    }
+    lse_n = l_s; delta_n = d_s; mq_n = m_s;
   }
+  // the softmax threads' key-mask byte: requested before the TMEM allocation / CTA-wide sync, consumed after it
+  const int kj_pre = k0 + (warp & 3) * 32 + lane;
+  const uint8_t mk_pre = (warp >= 2 && kj_pre < Lk) ? (blk ? p.mask_k[1] : p.mask_k[0])[(int64_t)b * Lk + kj_pre] : (uint8_t)0;
+  if (warp == 2) TRACE(4090);
   const uint32_t tmem = tmem_setup(bars, warp, 128);
   const uint32_t tdPT = tmem + NT, tdK = tmem + 2 * NT, tdV = tmem + 2 * NT + DH;
+  if (warp == 2) TRACE(4091);
 
   if (warp == 0) {
     for (int i = BWD_STAGES; i < T; ++i) produce(i, true);
@@ -1073,7 +1111,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const int qd = warp & 3, row = qd * 32 + lane;
     const int kj = k0 + row;
     const bool k_in = kj < Lk;
-    const bool mk = k_in ? ((blk ? p.mask_k[1] : p.mask_k[0])[(int64_t)b * Lk + kj] != 0) : false;
+    const bool mk = k_in ? (mk_pre != 0) : false;
     const bool warp_all_mk = __all_sync(0xffffffffu, mk);
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
     const uint32_t a_ready_a = smem_u32(&bars->a_ready[0]), s_free_a = smem_u32(&bars->s_free[0]), p_ready_a = smem_u32(&bars->p_ready[0]);
@@ -1081,7 +1119,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t ptrow_a = smem_u32(sPT) + row * 64, dstrow_a = smem_u32(sdST) + row * 64, swz = (row >> 1) & 3;
     int st = 0, st_phase = 0;
     for (int i = 0; i < T; ++i) {
+      if (warp == 2) TRACE(i * 8 + 0);
       mbar_wait_a(kv_full_a + st * 8, st_phase);         // acquire the loader's per-query vectors
+      if (warp == 2) TRACE(i * 8 + 1);
       const uint32_t qva = qv_a + st * (uint32_t)sizeof(QVec);
       const uint32_t wq = lds_u1(qva + 2 * NT * 4);
       const bool fast = !DROP && warp_all_mk && wq == 0xffffffffu;
@@ -1095,6 +1135,7 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (++st == BWD_STAGES) { st = 0; st_phase ^= 1; }
       mbar_wait_a(a_ready_a, i & 1);
       tcgen05_fence_after();
+      if (warp == 2) TRACE(i * 8 + 2);
       uint32_t pp[16], pd[16];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -1172,14 +1213,17 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           }
         }
       }
+      if (warp == 2) TRACE(i * 8 + 3);
       if (i >= 1) mbar_wait_a(p_free_a, (i - 1) & 1);    // dK / dV products of tile i-1 have consumed the staging tiles
       write_row_sw64(ptrow_a, swz, pp);
       write_row_sw64(dstrow_a, swz, pd);
       fence_proxy_async_smem();
       mbar_arrive_a(p_ready_a);
+      if (warp == 2) TRACE(i * 8 + 4);
     }
     mbar_wait(&bars->done, 0);
     tcgen05_fence_after();
+    if (warp == 2) TRACE(4093);
     uint32_t rk[32];
     tmem_ld_32x32(tdK + lane_addr, rk);
     tmem_ld_wait();
@@ -1189,8 +1233,10 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tmem_ld_wait();
     if (k_in && p.dv != nullptr) store_row32_bf16(p.dv + ((int64_t)b * Lk + kj) * p.lddv + h * DH, rk, 1.0f);
     if (p.dbv != nullptr) add_bias_grad(p.dbv + h * DH, rk, k_in, lane);
+    if (warp == 2) TRACE(4094);
   }
   tmem_teardown(tmem, warp, 128);
+  if (warp == 2) TRACE(4092);
 }
 
 // ====================================================================================== host

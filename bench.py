@@ -316,6 +316,13 @@ def main():
     roof["avg_launch_ms"] = d["ms"] / d["launches"]
     roof["launches_per_step"] = d["launches"] // K
     if dom.startswith("attn"):
+        # second yardstick for the attention kernels: one ex2 per score (dq and dk/dv recompute P, so every launch pays
+        # B*H*Lq*Lk of them) against the measured MUFU rate of 16 ex2 / clk / SM (tools/micro/pipe_rates.cu)
+        per_flop = {"attn_fwd": 1.0 / (4 * 32), "attn_bwd_dq": 1.0 / (6 * 32), "attn_bwd_dkv": 1.0 / (8 * 32)}[dom.split(" ")[0]]
+        ex2_per_s = d["work"] * per_flop / (d["ms"] * 1e-3)
+        sm_hz = ((clocks or {}).get("sm_mhz") or 1800.0) * 1e6
+        roof["mufu"] = {"achieved": ex2_per_s / 1e12, "peak": 16 * 148 * sm_hz / 1e12, "unit": "Tex2/s",
+                        "frac": ex2_per_s / (16 * 148 * sm_hz), "peak_source": "16 ex2/clk/SM x 148 SMs x median SM clock sampled during the timed region"}
         roof["note"] = ("head dim 32: one ex2 per score against 128 tensor FLOPs, so this kernel is bounded by the MUFU / issue "
                         "pipes (16 ex2/clk/SM), not by the tensor pipe the FLOP count is divided by")
 

@@ -8,6 +8,10 @@ out=gpurun_out
 mkdir -p $out
 python bench.py --steps 8 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 python tools/profile_step.py --table --steps 2 --warmup 2 > $out/${tag}_table.txt 2>&1
+python tools/profile_step.py --table --steps 2 --warmup 2 --dropout 0 > $out/${tag}_table_dropout_off.txt 2>&1
+# launch list of the bench command itself (serialised, cold-cache: compare shares with the bench line's kernel_breakdown)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $out/${tag}_bench_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_bench_under_ncu.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/${tag}_launches.csv \
     python tools/profile_step.py --steps 1 --warmup 1 > $out/${tag}_launches.log 2>&1
 # attention launches of step 2 (36 per step): #37 = layer-0 history-side forward; #51..53 = layer-3 history-side dq, dkv(cand keys), dkv(history keys)

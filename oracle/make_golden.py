@@ -335,8 +335,9 @@ def run_dropout_cases():
 
 def run_fusion_variants():
     """the other fusions of forward (decoder_leave_focal.py:624-634): fusion_heads 0 (two Linear heads summed), -1 (one
-    Linear(2d, 1) over the concatenation), -2 (one Linear head over the sum of the two backbones)"""
-    for fh in (0, -1, -2):
+    Linear(2d, 1) over the concatenation), -2 (one Linear head over the sum of the two backbones), -3 (list concatenation:
+    backbone2's output alone through one Linear head; backbone1 is dead)"""
+    for fh in (0, -1, -2, -3):
         run_general_case(f"model_both_fh{fh}", {"user": "both", "photo": "both"}, d_model=64, nhead=2, nlayers=3, din=24, B=4,
                          seed=30 - fh, loss_types=("focal",), fusion_heads=fh)
 

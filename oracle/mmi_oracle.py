@@ -387,6 +387,8 @@ def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_laye
             logits = head_logits(sd, torch.cat([x1, x2], dim=-1))
         elif fusion_heads == -2:     # :624-626: Linear(d, 1) over x1 + x2
             logits = head_logits(sd, x1 + x2)
+        elif fusion_heads == -3:     # :621-623: `vid_feat_lvls1 + vid_feat_lvls2` concatenates two LISTS; [-1] is backbone2's output
+            logits = head_logits(sd, x2)
         else:
             raise NotImplementedError(f"fusion_heads={fusion_heads}")
     else:
@@ -397,17 +399,20 @@ def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_laye
     return compute_loss(logits, gt, exposure_prob, loss_type_list, loss_weight, mask_loss=mask_loss)
 
 
-def live_param_names(sd_keys, num_layers, ablation_type="ours"):
+def live_param_names(sd_keys, num_layers, ablation_type="ours", fusion_heads=2):
     """Names of parameters that receive a gradient in the reference (SURVEY
     section 0 fact 5): everything except layer N-1, the history side of layer
     N-2 (its v2t/t2t projections, ff_usr, ln_usr), and the never-called
     pe_lns / txt_lvl_projs / patch_merge.  Ablations: 'CrossAtt' never uses v2v / t2t; 'SelfAtt' never uses the history
-    tokens at all (t2v / v2t / t2t, every *_usr module, usr_proj / usr_pe / usr_ln)."""
+    tokens at all (t2v / v2t / t2t, every *_usr module, usr_proj / usr_pe / usr_ln).  fusion_heads == -3 scores backbone2
+    alone (decoder_leave_focal.py:621-623), so nothing of backbone1 is trained."""
     live = []
     N = num_layers
     abl = attn_ablation(ablation_type)
     for k in sd_keys:
         if any(s in k for s in ("pe_lns", "txt_lvl_projs", "patch_merge")):
+            continue
+        if fusion_heads == -3 and k.startswith("backbone1."):
             continue
         if abl == "SelfAtt" and any(s in k for s in ("usr_proj", "usr_pe", "usr_ln", "t2v_proj", "v2t_proj", "t2t_proj", "ff_usr", "ln_usr")):
             continue

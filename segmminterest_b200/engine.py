@@ -105,6 +105,11 @@ class Engine:
         self.towers = [_Tower("b1", "backbone1.", model.backbone1)]
         if getattr(model, "backbone2", None) is not None:
             self.towers.append(_Tower("b2", "backbone2.", model.backbone2))
+            if getattr(model, "fusion_heads", None) == -3:
+                # vid_feat_lvls1 + vid_feat_lvls2 is a LIST concatenation and [-1] picks backbone2's output
+                # (decoder_leave_focal.py:621-623): backbone1 never reaches the loss, so it is neither computed nor trained
+                # here (its parameters stay at grad = None, exactly what autograd leaves behind in the reference)
+                self.towers = self.towers[1:]
         self.fusion = getattr(model, "fusion_module", None)
         self.slots: list[_Slot] = []
         self.groups = {}

@@ -226,7 +226,9 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
             fh = getattr(model_cfg, "fusion_heads", 2)
             if fh > 0:
                 self.fusion_module = InteractionAggregation(d_model, d_model, output_dim=1, num_heads=fh)
-            elif fh in (0, -1, -2):
+            elif fh in (0, -1, -2, -3):
+                # -3 concatenates the two backbones' output LISTS and takes [-1] (decoder_leave_focal.py:621-623), i.e. it
+                # scores backbone2 alone with a Linear(d, 1) head; backbone1 runs in the reference but never reaches the loss
                 self.stage_mlp1 = nn.Linear(2 * d_model if fh == -1 else d_model, 1)
                 heads = [self.stage_mlp1]
                 if fh == 0:
@@ -236,8 +238,7 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
                     nn.init.xavier_uniform_(lin.weight.data)
                     lin.bias.data.zero_()
             else:
-                raise NotImplementedError(f"fusion_heads={fh}: -3 concatenates the two output LISTS and so scores backbone2 alone "
-                                          "(decoder_leave_focal.py:621-623); not built")
+                raise NotImplementedError(f"fusion_heads={fh}: the reference defines > 0 (InteractionAggregation), 0, -1, -2, -3")
             self.fusion_heads = fh
         self._engine = None
         self.precision = getattr(model_cfg, "mmi_precision", "fp32")

@@ -259,7 +259,7 @@ def test_all_selectable_losses_through_the_model_vs_oracle(precision):
             assert _rel(p.grad.cpu().numpy(), osd[k].grad.numpy()) < 3 * tol, k
 
 
-@pytest.mark.parametrize("name", ["model_both_small", "model_id_small", "model_both_fh0", "model_both_fh-1", "model_both_fh-2"])
+@pytest.mark.parametrize("name", ["model_both_small", "model_id_small", "model_both_fh0", "model_both_fh-1", "model_both_fh-2", "model_both_fh-3"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_general_config_vs_reference_golden(name, precision):
     """ID-embedding inputs and the reference's default 'both' configuration (image backbone + ID backbone
@@ -287,13 +287,34 @@ def test_general_config_vs_reference_golden(name, precision):
     assert abs(out["loss"].item() - float(z["loss"])) < tol * abs(float(z["loss"])) + (2e-6 if precision == "fp32" else 3e-3)
     out["loss"].backward()
     dead = set(json.loads(str(z["dead_params"])))
-    for k, p in model.named_parameters():
+    # same criteria as test_small_model_vs_reference_golden: the whole gradient at the north-star bar (bf16: max(bar, 0.4 x
+    # amp)), single tensors at 3 x bar in fp32-or-bf16, widened in bf16 to 1.5 x amp where amp = relative error of the
+    # head-bias gradient (the fp32 sum of dlogits: what the loss gradient does to the forward's ~1 % logits error)
+    params = dict(model.named_parameters())
+    amp = 0.0
+    hb = "stage_mlp1.bias"
+    if precision == "bf16" and hb in params and hb not in dead and np.linalg.norm(z["grad/" + hb]) > 1e-6:
+        amp = float(np.linalg.norm(params[hb].grad.double().cpu().numpy() - z["grad/" + hb]) / np.linalg.norm(z["grad/" + hb]))
+    assert amp < 0.15, amp
+    per_tensor = max(3 * tol, 1.5 * amp)
+    # bf16 noise floor: a tensor whose gradient is > 4 orders of magnitude below the largest one (key-projection biases: a
+    # common shift of a query's logits leaves the softmax unchanged) is compared against the floor, not its own norm
+    gmax = max(float(np.linalg.norm(z[k])) for k in z.files if k.startswith("grad/"))
+    floor = 1e-7 if precision == "fp32" else 2e-5 * gmax
+    err2 = ref2 = 0.0
+    bad = []
+    for k, p in params.items():
         if k in dead:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
         else:
             ref = z["grad/" + k].astype(np.float64)
-            diff = np.linalg.norm(p.grad.double().cpu().numpy() - ref)
-            assert diff < 3 * tol * np.linalg.norm(ref) + 1e-7, (k, diff, np.linalg.norm(ref))
+            diff = float(np.linalg.norm(p.grad.double().cpu().numpy() - ref))
+            err2 += diff * diff
+            ref2 += float(np.linalg.norm(ref)) ** 2
+            if not diff < per_tensor * np.linalg.norm(ref) + floor:
+                bad.append((k, diff, float(np.linalg.norm(ref))))
+    assert not bad, (amp, bad[:6])
+    assert err2 ** 0.5 < max(tol, 0.4 * amp) * ref2 ** 0.5, ("whole gradient", err2 ** 0.5, ref2 ** 0.5, amp)
 
 
 def test_cpu_call_fails_loudly():

@@ -93,8 +93,10 @@ def test_unsupported_configs_raise():
         SegFormerX(d_model_in=64, d_model_lvls=[64], num_head_lvls=[2], ff_dim_lvls=[64], sr_ratio_lvls=[2],
                    use_patch_merge=[False], output_layers=[-1], model_cfg=make_args())
     both = {"user": "both", "photo": "both"}
-    with pytest.raises(NotImplementedError):      # -3 scores backbone2 alone (list concatenation in the reference); not built
-        build_model(make_args(input_type=both, fusion_heads=-3), din=16, max_usr_len=4, n_users=3, n_items=5)
+    with pytest.raises(NotImplementedError):      # the reference defines > 0, 0, -1, -2, -3 and nothing else
+        build_model(make_args(input_type=both, fusion_heads=-4), din=16, max_usr_len=4, n_users=3, n_items=5)
+    m3 = build_model(make_args(input_type=both, fusion_heads=-3), din=16, max_usr_len=4, n_users=3, n_items=5)
+    assert tuple(m3.stage_mlp1.weight.shape) == (1, 64) and not hasattr(m3, "stage_mlp2")    # -3: backbone2 alone through Linear(d, 1)
     m0 = build_model(make_args(input_type=both, fusion_heads=0), din=16, max_usr_len=4, n_users=3, n_items=5)
     assert tuple(m0.stage_mlp1.weight.shape) == (1, 64) and tuple(m0.stage_mlp2.weight.shape) == (1, 64)
     m1 = build_model(make_args(input_type=both, fusion_heads=-1), din=16, max_usr_len=4, n_users=3, n_items=5)

@@ -95,7 +95,7 @@ def test_dropout_sites_match_reference_generator_stream(name):
     assert _rel(ev["logits"].numpy(), z["logits"]) > 1e-2
 
 
-@pytest.mark.parametrize("name", ["model_both_small", "model_id_small", "model_both_fh0", "model_both_fh-1", "model_both_fh-2"])
+@pytest.mark.parametrize("name", ["model_both_small", "model_id_small", "model_both_fh0", "model_both_fh-1", "model_both_fh-2", "model_both_fh-3"])
 def test_general_config_matches_reference(name):
     """ID-embedding inputs, two backbones + InteractionAggregation (the reference default 'both'),
     interestBPR: the oracle against the unmodified reference."""
@@ -117,7 +117,8 @@ def test_general_config_matches_reference(name):
         assert abs(out[lt].item() - float(z[lt])) <= 1e-5 * abs(float(z[lt]))
     out["loss"].backward()
     dead = set(json.loads(str(z["dead_params"])))
-    live = set(mmi_oracle.live_param_names([k for k in sd if ("grad/" + k) in z.files or k in dead], cfg["num_layers_enc"]))
+    live = set(mmi_oracle.live_param_names([k for k in sd if ("grad/" + k) in z.files or k in dead], cfg["num_layers_enc"],
+                                           fusion_heads=cfg["fusion_heads"]))
     assert live == {k for k in sd if ("grad/" + k) in z.files}
     for k in sorted(live):
         assert sd[k].grad is not None, k

@@ -152,7 +152,7 @@ def reference_arm(args, wl):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    val, b, cores, ms = run_cpu_sample(wl, 150.0, steps, warmup, dropout=args.dropout)
+    val, b, cores, ms = run_cpu_sample(wl, args.ref_budget, steps, warmup, dropout=args.dropout)
     dnote = f"dropout {args.dropout} (torch generator)" if args.dropout > 0 else "dropout off"
     line = {"impl": "reference", "metric": "train_interactions_per_s", "value": val, "unit": "interactions/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=0, help="gradient-accumulation slice (configs 3 / 4: saved activations of a slice must fit in HBM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work the whole run is sized for")
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="dropout probability of every nn.Dropout site (reference training default 0.1); 0 = eval()-mode arithmetic")
     args = ap.parse_args()

@@ -284,6 +284,52 @@ def test_train_mode_model_vs_oracle_with_the_same_masks(dev, name, precision):
     assert _rel(ev["logits"].detach().cpu().numpy(), z["logits"]) < tol
 
 
+@pytest.mark.parametrize("name", ["model_both_small", "model_id_small"])
+def test_train_mode_two_towers_and_id_inputs_vs_oracle(dev, name):
+    """train() mode of the reference's default multi-modal configuration (image tower + ID tower fused by
+    InteractionAggregation) and of the ID-only configuration: every dropout site of BOTH towers (the ID tower has a
+    one-token history) against the oracle under the kernels' masks, strict fp32 bar."""
+    from oracle import mmi_oracle
+    from segmminterest_b200.model import build_model
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = json.loads(str(z["cfg"]))
+    args = make_args(d_model=cfg["d_model"], nhead=cfg["nhead"], num_layers_enc=cfg["num_layers_enc"], input_type=cfg["input_type"],
+                     fusion_heads=cfg["fusion_heads"], loss_type_list=list(cfg["loss_types"]), mmi_precision="fp32")
+    torch.manual_seed(5)
+    model = build_model(args, din=cfg["din"], max_usr_len=100, n_users=cfg["n_users"], n_items=cfg["n_items"])
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    out = model(usr_image=torch.from_numpy(z["usr_image"]).to(dev), usr_id=torch.from_numpy(z["usr_id"]).to(dev),
+                usr_mask=torch.from_numpy(z["usr_mask"]).to(dev), vid_image=torch.from_numpy(z["vid_image"]).to(dev),
+                vid_id=torch.from_numpy(z["vid_id"]).to(dev), vid_mask=torch.from_numpy(z["vid_mask"]).to(dev),
+                gt=torch.from_numpy(z["gt_in"].copy()).to(dev), mode="train")
+    osd = {k: v.clone() for k, v in sd.items()}
+    for v in osd.values():
+        if v.is_floating_point():
+            v.requires_grad_(True)
+    o = mmi_oracle.forward(osd, torch.from_numpy(z["usr_image"]), torch.from_numpy(z["usr_mask"]), torch.from_numpy(z["vid_image"]),
+                           torch.from_numpy(z["vid_mask"]), torch.from_numpy(z["gt_in"].copy()), nhead=cfg["nhead"],
+                           num_layers=cfg["num_layers_enc"], loss_type_list=tuple(cfg["loss_types"]), usr_id=torch.from_numpy(z["usr_id"]),
+                           vid_id=torch.from_numpy(z["vid_id"]), input_type=cfg["input_type"], fusion_heads=cfg["fusion_heads"],
+                           drop=_oracle_drop(model.engine(), cfg["nhead"]))
+    assert _rel(out["logits"].detach().cpu().numpy(), o["logits"].detach().numpy()) < 1e-4
+    assert _rel(o["logits"].detach().numpy(), z["logits"]) > 1e-3                            # not the eval-mode result
+    assert abs(out["loss"].item() - o["loss"].item()) < 1e-4 * abs(o["loss"].item()) + 2e-6
+    out["loss"].backward()
+    o["loss"].backward()
+    dead = set(json.loads(str(z["dead_params"])))
+    n = 0
+    for k, p in model.named_parameters():
+        if k in dead:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        ref = osd[k].grad.numpy().astype(np.float64)
+        assert np.linalg.norm(p.grad.double().cpu().numpy() - ref) < 3e-4 * np.linalg.norm(ref) + 1e-7, k
+        n += 1
+    assert n > 40
+
+
 def test_train_step_dropout_follows_module_mode(dev):
     """TrainStep: dropout on under train(), off under eval(), overridable; masks differ from step to step."""
     from segmminterest_b200 import synth

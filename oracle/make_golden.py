@@ -310,6 +310,7 @@ def main():
     run_general_cases()
     run_ablation_cases()
     run_dropout_cases()
+    run_mlp_ablation_cases()
 
 
 def run_general_cases():
@@ -331,6 +332,16 @@ def run_dropout_cases():
     run_model_case("model_small_dropout", d_model=64, nhead=2, nlayers=4, din=48, Lt=12, B=5, seed=51, train_seed=1234)
     run_model_case("model_small_dropout_crossatt", d_model=64, nhead=2, nlayers=3, din=48, Lt=12, B=5, seed=52, train_seed=99,
                    ablation_type="CrossAtt")
+
+
+def run_mlp_ablation_cases():
+    """the MLP ablations of the encoder (encoder.py:392-400,503-511): MLP_Block instead of attention; one of them also in
+    train() mode for the dropout placement inside MLP_Block"""
+    run_model_case("model_small_selfmlp", d_model=64, nhead=2, nlayers=6, din=48, Lt=12, B=5, seed=61, ablation_type="SelfMLP")
+    run_model_case("model_small_crossmlp", d_model=64, nhead=2, nlayers=6, din=48, Lt=12, B=5, seed=62, ablation_type="CrossMLP")
+    run_model_case("model_small_woatt", d_model=64, nhead=2, nlayers=6, din=48, Lt=12, B=5, seed=63, ablation_type="w/oAtt")
+    run_model_case("model_small_selfmlp_dropout", d_model=64, nhead=2, nlayers=6, din=48, Lt=12, B=5, seed=64, ablation_type="SelfMLP",
+                   train_seed=777)
 
 
 def run_fusion_variants():
@@ -355,5 +366,7 @@ if __name__ == "__main__":
         run_ablation_cases()
     elif "--dropout-only" in sys.argv:
         run_dropout_cases()
+    elif "--mlp-ablations-only" in sys.argv:
+        run_mlp_ablation_cases()
     else:
         main()

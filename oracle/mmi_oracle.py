@@ -38,6 +38,8 @@ def l1_normalise(x: torch.Tensor) -> torch.Tensor:
 # implementation, so the parity tests pass a callable that applies the masks of oracle/dropout_ref.py -- the counter-based
 # generator of the CUDA path -- which makes "training with dropout" a deterministic comparison.
 DROP_EMB, DROP_ATTN, DROP_ATTN_OUT, DROP_MLP1, DROP_MLP2 = range(5)
+DROP_BLOCK = 5      # hidden layers of the MLP_Block encoder of the SelfMLP / CrossMLP ablations (layer = hidden-layer index)
+MLP_ABLATIONS = ("SelfMLP", "CrossMLP", "w/oAtt")     # compared with == in the reference (encoder.py:392-400,503-511)
 
 
 def _tower(prefix):
@@ -175,12 +177,33 @@ def ffn(sd, p, side, x, drop=None, where=(0, 0)):
 # --------------------------------------------------------------------------
 # a-8  encoder stack; output = INPUT of the last layer
 # --------------------------------------------------------------------------
+def mlp_block(sd, prefix, x, drop=None, tower=0):
+    """MLP_Block (models/encoder.py:210-254, after FuxiCTR) as SegFormerX builds it for the MLP ablations (:392-400):
+    [Linear(d, d) -> ReLU -> Dropout] per hidden unit, then Linear(d, d); nn.Sequential indices 0, 3, 6, ... are the Linears."""
+    idx = sorted(int(k[len(prefix + "encoder_mlp.mlp."):].split(".")[0]) for k in sd if k.startswith(prefix + "encoder_mlp.mlp.") and k.endswith(".weight"))
+    for n, i in enumerate(idx):
+        x = F.linear(x, sd[f"{prefix}encoder_mlp.mlp.{i}.weight"], sd[f"{prefix}encoder_mlp.mlp.{i}.bias"])
+        if n < len(idx) - 1:
+            x = F.relu(x)
+            if drop is not None:
+                x = drop(DROP_BLOCK, tower, n, 0, x)
+    return x
+
+
 def backbone(sd, prefix, usr, usr_mask, vid, vid_mask, nhead, num_layers, use_pe=True, ablation="ours", drop=None, full_usr=False):
     """models/encoder.py:302-324,475-520.  intermediate_states records vid_feat
     BEFORE each layer and the caller takes [-1], so layer N-1 never reaches the
     output, nor does the history side of layer N-2."""
     v, u = embed(sd, prefix, usr, vid, use_pe, drop)
     tw = _tower(prefix)
+    # the MLP ablations replace the attention encoder (encoder.py:503-511); none of them looks at the masks
+    if ablation == "CrossMLP":     # MLP over [history ; candidate] tokens, then AdaptiveAvgPool1d(40) along the token axis
+        x = mlp_block(sd, prefix, torch.cat([u, v], dim=-2), drop, tw)
+        return F.adaptive_avg_pool1d(x.permute(0, 2, 1), 40).permute(0, 2, 1)
+    if ablation == "SelfMLP":      # MLP over the candidate tokens
+        return mlp_block(sd, prefix, v, drop, tw)
+    if ablation == "w/oAtt":       # the embedded candidate tokens go straight to the head (encoder_mlp is built but never called)
+        return v
     if usr.ndim == 1:   # ID user: one token, mask of ones (encoder.py:478-481)
         usr_mask = torch.ones(usr.shape[0], 1, dtype=torch.bool)
     for i in range(num_layers - 1):
@@ -372,7 +395,7 @@ def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_laye
             return image if which == 1 else ident
         return image if kind == "image" else ident
 
-    abl = attn_ablation(ablation_type)
+    abl = ablation_type if ablation_type in MLP_ABLATIONS else attn_ablation(ablation_type)
     x1 = backbone(sd, "backbone1.", pick(it["user"], usr_image, usr_id, 1), usr_mask.bool(),
                   pick(it["photo"], vid_image, vid_id, 1), vid_mask.bool(), nhead, num_layers, use_pe, abl, drop, full_usr)
     if two:
@@ -408,6 +431,14 @@ def live_param_names(sd_keys, num_layers, ablation_type="ours", fusion_heads=2):
     alone (decoder_leave_focal.py:621-623), so nothing of backbone1 is trained."""
     live = []
     N = num_layers
+    if ablation_type in MLP_ABLATIONS:      # no attention encoder: embeddings (+ encoder_mlp) + head; SelfMLP / w/oAtt never read the history
+        for k in sd_keys:
+            if ablation_type != "CrossMLP" and any(s in k for s in ("usr_proj", "usr_pe", "usr_ln")):
+                continue
+            if ablation_type == "w/oAtt" and "encoder_mlp" in k:
+                continue
+            live.append(k)
+        return live
     abl = attn_ablation(ablation_type)
     for k in sd_keys:
         if any(s in k for s in ("pe_lns", "txt_lvl_projs", "patch_merge")):

@@ -57,6 +57,38 @@ def test_model_small_matches_reference(name):
     assert _rel(inf["logits"].numpy(), z["logits_inference"]) < 1e-5
 
 
+@pytest.mark.parametrize("name", ["model_small_selfmlp", "model_small_crossmlp", "model_small_woatt", "model_small_selfmlp_dropout"])
+def test_mlp_ablations_match_reference(name):
+    """the MLP ablations of the encoder (SelfMLP / CrossMLP / w/oAtt, encoder.py:392-400,503-511: MLP_Block over
+    the candidate tokens, over [history ; candidate] tokens + AdaptiveAvgPool1d(40), or no encoder at all) -- oracle only so
+    far: the CUDA path raises NotImplementedError for them.  The `_dropout` fixture is the reference in train() mode; the
+    oracle replays its generator stream (dropout after every hidden ReLU of MLP_Block)."""
+    z = _load(name)
+    cfg = json.loads(str(z["cfg"]))
+    abl = cfg["ablation_type"]
+    sd = {k[3:]: torch.from_numpy(z[k]).clone().requires_grad_(True) for k in z.files if k.startswith("sd/")}
+    kw = dict(nhead=cfg["nhead"], num_layers=cfg["num_layers_enc"], ablation_type=abl)
+    args = (torch.from_numpy(z["usr_image"]), torch.from_numpy(z["usr_mask"]), torch.from_numpy(z["vid_image"]),
+            torch.from_numpy(z["vid_mask"]), torch.from_numpy(z["gt_in"]))
+    if cfg.get("train_seed") is not None:
+        torch.manual_seed(cfg["train_seed"])
+        out = mmi_oracle.forward(sd, *args, drop=mmi_oracle.torch_dropout(0.1), **kw)
+    else:
+        out = mmi_oracle.forward(sd, *args, **kw)
+    assert _rel(out["logits"].detach().numpy(), z["logits"]) < 1e-5
+    assert abs(out["loss"].item() - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    out["loss"].backward()
+    dead = set(json.loads(str(z["dead_params"])))
+    live = set(mmi_oracle.live_param_names(list(sd.keys()), cfg["num_layers_enc"], abl))
+    assert live == {k for k in sd if k not in dead}
+    for k in sorted(live):
+        assert np.linalg.norm(sd[k].grad.numpy() - z["grad/" + k]) < 2e-5 * np.linalg.norm(z["grad/" + k]) + 1e-8, k
+    for k in dead:
+        assert sd[k].grad is None or float(sd[k].grad.abs().max()) == 0.0, k
+    inf = mmi_oracle.forward({k: v.detach() for k, v in sd.items()}, *args, mode="inference", **kw)
+    assert _rel(inf["logits"].numpy(), z["logits_inference"]) < 1e-5
+
+
 @pytest.mark.parametrize("name", ["model_small_dropout", "model_small_dropout_crossatt"])
 def test_dropout_sites_match_reference_generator_stream(name):
     """train() mode of the UNMODIFIED reference (nn.Dropout(0.1) at every site, torch generator seeded right before the

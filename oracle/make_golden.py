@@ -241,6 +241,35 @@ def run_eval_case():
     print("eval_cases", {k: (len(v), float(np.mean(v))) for k, v in results.items()})
 
 
+def run_topk_case():
+    """TOP_K_leave / TOP_K_leave_mask of models/my_evaluation.py (:137-231) as the driver's validation loop calls them
+    (main...SegMM.py:155-167) on the loss_cases inputs, with np.random seeded so the per-row permutations can be replayed."""
+    ev = ref_shim.load_evaluation()
+    base = np.load(os.path.join(OUT, "loss_cases.npz"))
+    logits = torch.from_numpy(base["logits"])
+    gt = torch.from_numpy(base["gt_in"])
+    ep = torch.tensor(base["exposure_prob"], dtype=torch.float32)
+    interests = (torch.sigmoid(logits) * ep).numpy()
+    interests[1, 3] = interests[1, 7]                          # ties: only the permutation decides their order
+    interests[2, :5] = interests[2, 5]
+    view_lengths = (gt == 1).sum(dim=1, keepdim=True).numpy()
+    mask_batch = (gt != -2).numpy()
+    save = dict(interests=interests, view_lengths=view_lengths, mask_batch=mask_batch, seed=np.int64(2024))
+    for fn in ("TOP_K_leave", "TOP_K_leave_mask"):
+        for perm in (1, 0):
+            np.random.seed(2024)
+            with contextlib.redirect_stdout(io.StringIO()):
+                res = getattr(ev, fn)(interests.copy(), view_lengths.copy(), mask_batch.copy(), permutation=perm)
+            for k, v in res.items():
+                save[f"{fn}/{perm}/{k}"] = np.float64(v)
+    np.random.seed(2024)
+    with contextlib.redirect_stdout(io.StringIO()):
+        _, mins = ev.TOP_K_leave(interests.copy(), view_lengths.copy(), mask_batch.copy(), permutation=1, test=1)
+    save["TOP_K_leave/min_indices"] = np.asarray(mins)
+    np.savez_compressed(os.path.join(OUT, "topk_cases.npz"), **save)
+    print("topk_cases", {k: float(v) for k, v in save.items() if k.startswith("TOP_K_leave/1/")})
+
+
 def run_gather_case():
     """FrameDatasetSeq_SegMM + DataCollator (utils/dataloader_SegMM.py:186-382) on a
     5-video fixture; stores the inputs in index form plus the dense outputs."""
@@ -303,6 +332,7 @@ def main():
     run_loss_cases()
     run_loss_cases_all()
     run_eval_case()
+    run_topk_case()
     run_model_case("model_small_dh32", d_model=64, nhead=2, nlayers=3, din=48, Lt=12, B=5, seed=11)
     run_model_case("model_small_dh16", d_model=64, nhead=4, nlayers=4, din=40, Lt=20, B=4, seed=12)
     run_model_case("model_full_b4", d_model=512, nhead=16, nlayers=6, din=1024, Lt=100, B=4, seed=13,
@@ -360,6 +390,8 @@ if __name__ == "__main__":
         run_loss_cases_all()
     elif "--eval-only" in sys.argv:
         run_eval_case()
+    elif "--topk-only" in sys.argv:
+        run_topk_case()
     elif "--fusion-only" in sys.argv:
         run_fusion_variants()
     elif "--ablation-only" in sys.argv:

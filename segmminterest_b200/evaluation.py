@@ -5,8 +5,9 @@
 
 `results_list` keeps the reference's protocol: a dict whose KEYS select the metrics and whose values are lists that get
 one entry per batch (ProbAUC) or per row (JaccardSim, LeaveMSE + view_lengths [+ duration_lengths], LeaveCTR,
-LeaveCTR_view).  The TOP_K family shuffles every row with np.random.permutation (my_evaluation.py:92-231) and stays on
-the host in the reference; it is not built here.
+LeaveCTR_view).  TOP_K_leave / TOP_K_leave_mask -- called by the driver's validation loop on host numpy copies
+(main...SegMM.py:164-167) and shuffling every row with np.random.permutation -- are host numpy functions here as well,
+drawing their permutations in the reference's order (a seeded run reproduces the reference's HR@k / NDCG@k exactly).
 """
 from __future__ import annotations
 
@@ -57,9 +58,6 @@ def main_eval_batch(args, interests, ground_truths, pred_labels, results_list, t
     them (main...SegMM.py:402-403)."""
     if test_type != "new":
         raise NotImplementedError("test_type 'old' (interests already are survival probabilities) is not built")
-    if "TOP_K" in results_list or "TOP1MSE" in results_list:
-        raise NotImplementedError("TOP_K_leave* shuffle every row on the host with np.random.permutation "
-                                  "(my_evaluation.py:92-231); not part of the device path")
     if logits is not None:
         raise NotImplementedError("the `logits=` branch (MAES, my_evaluation.py:309-320) is never taken by the SegMM driver")
     if getattr(args, "draw_case", 0):
@@ -71,8 +69,21 @@ def main_eval_batch(args, interests, ground_truths, pred_labels, results_list, t
         if not (o[1] > 0 and o[2] > 0):
             raise ValueError("Only one class present in y_true. ROC AUC score is not defined in that case.")   # sklearn's error
         results_list["ProbAUC"].append(float(o[0]))
+    if "TOP_K" in results_list:                               # my_evaluation.py:287-303: host metrics on numpy copies, like the reference
+        view_lengths = (ground_truths == 1).sum(dim=1, keepdim=True).cpu().numpy()
+        mask_np = (ground_truths != -2).cpu().numpy()
+        inter_np = interests.detach().float().cpu().numpy()
+        if getattr(args, "TOP_K_mask", 0):
+            evaluations = TOP_K_leave_mask(inter_np, view_lengths, mask_np, permutation=args.TOP_K_permutation)
+        elif "TOP1MSE" in results_list:
+            evaluations, top1 = TOP_K_leave(inter_np, view_lengths, mask_np, permutation=args.TOP_K_permutation, test=1)
+            results_list["TOP1MSE"].append(top1)
+        else:
+            evaluations = TOP_K_leave(inter_np, view_lengths, mask_np, permutation=args.TOP_K_permutation)
+        for name, value in evaluations.items():
+            results_list.setdefault(name, []).append(float(value))
     for i in range(r.shape[0]):                               # per-row appends, in the reference's row-major order (:324-355)
-        for eval_type in results_list:
+        for eval_type in list(results_list):
             if eval_type == "JaccardSim":
                 results_list[eval_type].append(float(r[i, _ROW["JaccardSim"]]))
             elif eval_type == "LeaveMSE":
@@ -87,10 +98,48 @@ def main_eval_batch(args, interests, ground_truths, pred_labels, results_list, t
     return results_list
 
 
-def TOP_K_leave(*a, **k):
-    """Imported by the driver (main...SegMM.py:5); host-side metric with per-row np.random.permutation -- not built."""
-    raise NotImplementedError("TOP_K_leave is a host-side metric (my_evaluation.py:180-231); not part of the device path")
+def _rank_metrics(scores, targets, permutation):
+    """HR@k / NDCG@k (k = 1, 3, 5, 10) of the rank of position `targets[i]` in the ascending order of row i of `scores`.
+    permutation != 0 breaks ties by a fresh np.random.permutation per row, drawn in row order exactly like the reference
+    (so a seeded validation run reproduces the reference's numbers); 0 leaves ties to np.argsort."""
+    import numpy as np
+    n, L = scores.shape
+    if permutation:
+        perms = np.stack([np.random.permutation(L) for _ in range(n)]) if n else np.zeros((0, L), dtype=np.int64)
+        shuffled = np.take_along_axis(scores, perms, axis=1)
+        where = (perms == targets[:, None]).argmax(axis=1)          # where the target went
+        order = np.argsort(shuffled, axis=1)
+    else:
+        where = targets
+        order = np.argsort(scores, axis=1)
+    rank = (order == where[:, None]).argmax(axis=1) + 1
+    out = {}
+    for k in (1, 3, 5, 10):
+        hit = (rank <= k).astype(np.float32)
+        out[f"HR@{k}"] = hit.mean()
+        out[f"NDCG@{k}"] = (hit / np.log2(rank + 1)).mean()
+    return out
 
 
-def TOP_K_leave_mask(*a, **k):
-    raise NotImplementedError("TOP_K_leave_mask is a host-side metric (my_evaluation.py:137-178); not part of the device path")
+def TOP_K_leave(interests, view_lengths, mask_batch, permutation=1, test=0):
+    """models/my_evaluation.py:180-231 -- the metric the driver's validation loop calls on every batch
+    (main...SegMM.py:164-167) with host numpy arrays (`interests.cpu().detach().numpy()`), so it is host numpy here too:
+    among rows that were not watched to the end of the 40 positions, the rank of the skip position (index view_length) in
+    the ascending order of the interests; HR@k and NDCG@k.  test != 0 also returns argmin(interests) per (unfiltered) row."""
+    import numpy as np
+    interests = np.asarray(interests)
+    first_min = np.argmin(interests, axis=1)
+    views = np.asarray(view_lengths).astype(np.int64).reshape(-1)
+    rows = views < 40
+    ev = _rank_metrics(interests[rows], views[rows], permutation)
+    return (ev, first_min) if test else ev
+
+
+def TOP_K_leave_mask(interests, view_lengths, mask_batch, permutation=1):
+    """models/my_evaluation.py:137-178: like TOP_K_leave over the rows whose view length differs from the number of real
+    segments (the video was skipped), with the interests of padded positions replaced by 1.1 so they rank last."""
+    import numpy as np
+    interests, mask_batch = np.asarray(interests), np.asarray(mask_batch)
+    views = np.asarray(view_lengths).astype(np.int64).reshape(-1)
+    rows = views != mask_batch.sum(axis=1)
+    return _rank_metrics(np.where(mask_batch[rows], interests[rows], 1.1), views[rows], permutation)

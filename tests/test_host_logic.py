@@ -5,6 +5,7 @@ import os
 import re
 from types import SimpleNamespace
 
+import numpy as np
 import pytest
 import torch
 
@@ -124,3 +125,47 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "/root/reference" not in src, f
+
+
+def test_topk_validation_metrics_match_reference_golden():
+    """TOP_K_leave / TOP_K_leave_mask (host numpy metrics the driver's validation loop calls on every batch,
+    main...SegMM.py:164-167) against the unmodified reference's functions (tests/golden/topk_cases.npz): with np.random
+    seeded the per-row permutations are drawn in the same order, so HR@k / NDCG@k agree exactly, ties included."""
+    from segmminterest_b200 import TOP_K_leave, TOP_K_leave_mask
+    z = np.load(os.path.join(ROOT, "tests", "golden", "topk_cases.npz"))
+    for name, fn in (("TOP_K_leave", TOP_K_leave), ("TOP_K_leave_mask", TOP_K_leave_mask)):
+        for perm in (1, 0):
+            np.random.seed(int(z["seed"]))
+            got = fn(z["interests"].copy(), z["view_lengths"].copy(), z["mask_batch"].copy(), permutation=perm)
+            assert set(got) == {f"{m}@{k}" for m in ("HR", "NDCG") for k in (1, 3, 5, 10)}
+            for k, v in got.items():
+                assert float(v) == float(z[f"{name}/{perm}/{k}"]), (name, perm, k, float(v), float(z[f"{name}/{perm}/{k}"]))
+    np.random.seed(int(z["seed"]))
+    ev, mins = TOP_K_leave(z["interests"].copy(), z["view_lengths"].copy(), z["mask_batch"].copy(), permutation=1, test=1)
+    assert np.array_equal(mins, z["TOP_K_leave/min_indices"]) and float(ev["HR@1"]) == float(z["TOP_K_leave/1/HR@1"])
+
+
+def test_main_eval_batch_top_k_branch_matches_reference_golden(monkeypatch):
+    """the 'TOP_K' key of main_eval_batch's results protocol (my_evaluation.py:287-303) -- host metrics; the device kernel
+    behind the other keys is stubbed out here (its parity is a GPU test)"""
+    from segmminterest_b200 import evaluation
+    z = np.load(os.path.join(ROOT, "tests", "golden", "topk_cases.npz"))
+    B = z["interests"].shape[0]
+    monkeypatch.setattr(evaluation, "_METRICS", lambda *a, **k: (torch.zeros(B, 6), torch.tensor([0.5, 1.0, 1.0, 0.0])))
+    gt = np.full(z["mask_batch"].shape, -2, dtype=np.int64)          # rebuild labels with the fixture's view lengths and masks
+    for i in range(B):
+        n, v = int(z["mask_batch"][i].sum()), int(z["view_lengths"][i, 0])
+        gt[i, :n] = -1
+        gt[i, :v] = 1
+        if v < n:
+            gt[i, v] = 0
+    for mask_flag, name in ((0, "TOP_K_leave"), (1, "TOP_K_leave_mask")):
+        args = SimpleNamespace(TOP_K_mask=mask_flag, TOP_K_permutation=1, draw_case=0)
+        np.random.seed(int(z["seed"]))
+        res = evaluation.main_eval_batch(args, torch.from_numpy(z["interests"]), torch.from_numpy(gt), None, {"TOP_K": []})
+        for k in ("HR@1", "HR@10", "NDCG@3", "NDCG@10"):
+            assert res[k] == [float(z[f"{name}/1/{k}"])], (name, k)
+    args = SimpleNamespace(TOP_K_mask=0, TOP_K_permutation=1, draw_case=0)
+    np.random.seed(int(z["seed"]))
+    res = evaluation.main_eval_batch(args, torch.from_numpy(z["interests"]), torch.from_numpy(gt), None, {"TOP_K": [], "TOP1MSE": []})
+    assert np.array_equal(res["TOP1MSE"][0], z["TOP_K_leave/min_indices"])

@@ -66,6 +66,26 @@ def test_engine_live_parameters_equal_oracle_live_set():
         assert cnt == (6 if n > 2 else 4) * 64 * 64 and off % 64 == 0
 
 
+def test_engine_live_parameters_follow_ablations_and_fusion_variants():
+    """the parameters the engine lays out in its flat buffer (= the ones that get a gradient) are exactly the oracle's live set
+    for the attention ablations and for every two-backbone fusion, incl. fusion_heads -3 where backbone1 is dead"""
+    from oracle import mmi_oracle
+    from segmminterest_b200.engine import Engine, EngineConfig, attn_ablation
+    from segmminterest_b200.model import build_model
+    for abl in ("CrossAtt", "SelfAtt", "noUser_SelfAtt"):
+        m = build_model(make_args(num_layers_enc=4, ablation_type=abl), din=48, max_usr_len=12)
+        eng = Engine(EngineConfig(d_model=64, nhead=2, num_layers=4, din_vid=48, din_usr=48, max_usr_len=12,
+                                  ablation=attn_ablation(abl)), m, torch.device("cpu"))
+        assert set(eng.live_names) == set(mmi_oracle.live_param_names([k for k, _ in m.named_parameters()], 4, abl)), abl
+    both = {"user": "both", "photo": "both"}
+    for fh in (2, 0, -1, -2, -3):
+        m = build_model(make_args(num_layers_enc=3, input_type=both, fusion_heads=fh), din=16, max_usr_len=100, n_users=3, n_items=5)
+        eng = Engine(EngineConfig(d_model=64, nhead=2, num_layers=3, din_vid=16, din_usr=16, max_usr_len=100), m, torch.device("cpu"))
+        live = set(mmi_oracle.live_param_names([k for k, _ in m.named_parameters()], 3, fusion_heads=fh))
+        assert set(eng.live_names) == live, fh
+        assert any(k.startswith("backbone1.") for k in live) == (fh != -3)
+
+
 def test_cpu_forward_fails_loudly():
     from segmminterest_b200 import _lib
     from segmminterest_b200.model import build_model

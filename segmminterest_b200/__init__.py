@@ -5,6 +5,7 @@ Public surface (mirrors MMinterest/models + the loop in main_for_seq_leave_early
     DeviceGather, TrainStep                                                        (train.py)
     InferenceScorer (forward-only batched scoring, BASELINE config 5)              (inference.py)
     SegmentIndex, DeviceFrameLoader (dataset + DataLoader + DataCollator drop-in)  (index.py, loader.py)
+    load_feature_table (SegMM_feat_memmap.dat, float32 or float64 -> resident table) (table.py)
     main_eval_batch, prob_auc_batch (device ProbAUC / per-row validation metrics)  (evaluation.py)
 Everything computes through libmmi_b200.so (include/mmi_b200.h); no CPU fallback.
 """
@@ -16,4 +17,5 @@ from .train import DeviceGather, TrainStep  # noqa: E402,F401
 from .inference import InferenceScorer  # noqa: E402,F401
 from .loader import DeviceFrameLoader  # noqa: E402,F401
 from .index import SegmentIndex  # noqa: E402,F401
+from .table import load_feature_table  # noqa: E402,F401
 from .evaluation import TOP_K_leave, TOP_K_leave_mask, main_eval_batch, prob_auc_batch  # noqa: E402,F401

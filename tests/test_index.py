@@ -77,3 +77,28 @@ def test_segment_count_and_label_parsing():
         assert int(n_segments(ms)) == gather_oracle.n_segments(ms)
     assert np.array_equal(parse_label("[ 1 1 0 -1]"), gather_oracle.pad_labels("[ 1 1 0 -1]"))
     assert parse_label("[" + " ".join(["1"] * 50) + "]").shape == (PHOTO_MAX,)
+
+
+def test_feature_table_loader_reads_both_file_layouts(tmp_path):
+    """SegMM_feat_memmap.dat is float32 in the driver's code (main...SegMM.py:39) and float64 in the public dump
+    (SegMM.md:22,49): both stream into the same resident table, chunk boundaries included; a wrong row count is an error."""
+    import torch
+    from segmminterest_b200 import load_feature_table
+    from segmminterest_b200.table import infer_row_dtype
+    rng = np.random.default_rng(3)
+    rows, dim = 1000, 64
+    x32 = rng.standard_normal((rows, dim)).astype(np.float32)
+    p32, p64 = str(tmp_path / "f32.dat"), str(tmp_path / "f64.dat")
+    x32.tofile(p32)
+    x32.astype(np.float64).tofile(p64)
+    assert infer_row_dtype(p32, rows, dim) == np.float32 and infer_row_dtype(p64, rows, dim) == np.float64
+    for path in (p32, p64):
+        for chunk in (1, 333, 1 << 16):
+            t = load_feature_table(path, rows, dim, device="cpu", chunk_rows=chunk)
+            assert t.dtype == torch.float32 and np.array_equal(t.numpy(), x32)          # bit-exact rows
+    tb = load_feature_table(p64, rows, dim, dtype=torch.bfloat16, device="cpu", chunk_rows=100)
+    assert tb.dtype == torch.bfloat16 and torch.equal(tb, torch.from_numpy(x32).to(torch.bfloat16))
+    with pytest.raises(ValueError):
+        load_feature_table(p32, rows + 1, dim, device="cpu")
+    with pytest.raises(ValueError):
+        load_feature_table(p32, rows, dim, src_dtype="float64", device="cpu")

@@ -460,12 +460,16 @@ def live_param_names(sd_keys, num_layers, ablation_type="ours", fusion_heads=2):
 
 
 def clip_and_adamw(params, grads, exp_avg, exp_avg_sq, step, lr=1e-3, wd=1e-4, betas=(0.9, 0.999),
-                   eps=1e-8, max_norm=10.0):
-    """main_for_seq_leave_earlystop_SegMM.py:298-299: clip_grad_norm_(10.0) then
+                   eps=1e-8, max_norm=None):
+    """main_for_seq_leave_earlystop_SegMM.py:298-299: clip_grad_norm_(param_dict, 10.0) then
     torch.optim.AdamW(lr, weight_decay).step().  Lists of tensors, updated in
-    place; returns the pre-clip global norm."""
+    place; returns the global gradient norm.
+
+    max_norm=None (default) is what the reference driver actually does: `param_dict = model.parameters()` (:224) is a
+    GENERATOR, AdamW's constructor consumes it (:225), so `clip_grad_norm_(param_dict, 10.0)` (:298) walks an exhausted
+    generator, returns 0 and clips nothing (torch only warns).  A float turns real clipping on (explicit opt-in)."""
     total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).to(grads[0].dtype)
-    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0) if max_norm else torch.ones((), dtype=grads[0].dtype)
     b1, b2 = betas
     for p, g, m, v in zip(params, grads, exp_avg, exp_avg_sq):
         g = g * coef

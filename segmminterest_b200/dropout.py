@@ -8,6 +8,9 @@ train() mode and 0 under eval().  Each site gets its own 32-bit key = mix(seed, 
 regenerate the mask from (key, row, col) in forward and backward, so no mask is ever stored."""
 from __future__ import annotations
 
+import warnings
+
+_WARNED = set()
 _M32 = 0xFFFFFFFF
 
 
@@ -27,6 +30,15 @@ def quantise(p: float):
     if not 0.0 <= p < 1.0:
         raise ValueError(f"dropout probability must be in [0, 1), got {p}")
     thr8 = min(255, int(round(p * 256.0)))
+    if p > 0.0:
+        realised = thr8 / 256.0
+        if thr8 == 0:
+            raise ValueError(f"dropout p={p} is below the 1/512 resolution of the keep words and would silently turn dropout off; "
+                             "use p = 0 or p >= 1/512")
+        if abs(realised - p) > 0.02 * p and p not in _WARNED:
+            _WARNED.add(p)
+            warnings.warn(f"dropout p={p} is realised as {thr8}/256 = {realised:.4f} (keep words quantise p to 1/256; survivors are "
+                          "scaled by the realised keep probability, so the expectation stays exact)", stacklevel=2)
     return thr8, 256.0 / (256.0 - thr8)
 
 

@@ -118,9 +118,12 @@ class SegmentIndex:
         watched segments i < ceil(playing / 5000) that exist in the map, in order, then the user's `user_input_dict`
         rows; more than 100 tokens are sub-sampled WITHOUT order (random.sample in the reference; `rng` here)."""
         B = len(user_id)
-        n_hist = np.array([len(h) for h in history_items], dtype=np.int64)
-        vids = np.concatenate([np.asarray(h, dtype=np.int64).reshape(-1) for h in history_items]) if n_hist.sum() else np.empty(0, np.int64)
-        play = np.concatenate([np.asarray(p).reshape(-1) for p in history_playing]) if n_hist.sum() else np.empty(0, np.int64)
+        # zip(history_items, history_playing) in the reference (:322) stops at the shorter of the two lists
+        n_hist = np.array([min(len(h), len(p)) for h, p in zip(history_items, history_playing)], dtype=np.int64)
+        vids = (np.concatenate([np.asarray(h, dtype=np.int64).reshape(-1)[:n] for h, n in zip(history_items, n_hist)])
+                if n_hist.sum() else np.empty(0, np.int64))
+        play = (np.concatenate([np.asarray(p, dtype=np.int64).reshape(-1)[:n] for p, n in zip(history_playing, n_hist)])
+                if n_hist.sum() else np.empty(0, np.int64))
         nseg = n_segments(play)
         sample_of_vid = np.repeat(np.arange(B), n_hist)
         tok_sample = np.repeat(sample_of_vid, nseg)
@@ -141,7 +144,9 @@ class SegmentIndex:
             if small[b]:
                 out[b, n_tok[b]:n_tok[b] + n_extra[b]] = extras[b]
         if not small.all():
-            rng = rng or np.random.default_rng()
+            # the reference draws with random.sample (:346), which the driver seeds (main...SegMM.py:26-28): derive the default
+            # generator from numpy's seeded global state so that a seeded run stays reproducible here too
+            rng = rng or np.random.default_rng(np.random.randint(2 ** 31))
             starts = np.cumsum(n_tok) - n_tok
             for b in np.nonzero(~small)[0]:
                 allrows = np.concatenate([rows[starts[b]:starts[b] + n_tok[b]], extras[b]])

@@ -36,6 +36,10 @@ class DeviceFrameLoader:
             raise _lib.MMIError("DeviceFrameLoader needs the embedding table in device memory; there is no CPU fallback")
         self.table = table.contiguous()
         self.index = index or SegmentIndex(lineid_map, corpus.user_input_dict)
+        if self.index.n_rows > self.table.shape[0]:
+            # the reference's feat_memmap[line_id] raises IndexError for a row past the table; the gather kernel would read
+            # such an id as padding, so a table loaded with the wrong n_rows must be refused here
+            raise IndexError(f"line-id map refers to row {self.index.n_rows - 1} but the table has {self.table.shape[0]} rows")
         self.batch_size, self.shuffle, self.normalise, self.out_dtype, self.rng = int(batch_size), shuffle, normalise, out_dtype, rng
         df = corpus.data_df[phase]
         self.n = len(df)

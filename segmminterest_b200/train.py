@@ -1,7 +1,7 @@
 """The fused training step behind the reference driver's loop body
 (main_for_seq_leave_earlystop_SegMM.py:270-300): device-side gather + pad + mask +
 L1-normalise -> forward -> focal loss -> hand-written backward -> bucketed gradient
-all-reduce -> global-norm clip + AdamW, all on one stream with no host synchronisation."""
+all-reduce -> (optional global-norm clip) + AdamW, all on one stream with no host synchronisation."""
 from __future__ import annotations
 
 import torch
@@ -37,8 +37,11 @@ class DeviceGather:
 
 class TrainStep:
     def __init__(self, model, table: torch.Tensor, lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
-                 max_norm=10.0, process_group=None, global_batch=None, bucket_bytes=25 << 20, dropout=None):
-        """dropout: None follows the module (model.dropout_p(): the backbone's p under train(), 0 under eval()); a float
+                 max_norm=None, process_group=None, global_batch=None, bucket_bytes=25 << 20, dropout=None):
+        """max_norm: None / 0 (default) applies no gradient clipping -- what the reference driver effectively does: its
+        `clip_grad_norm_(param_dict, 10.0)` (main...SegMM.py:298) receives the generator AdamW already consumed (:224-225),
+        so nothing is clipped; a float opts in to real global-norm clipping (the norm is reported either way).
+        dropout: None follows the module (model.dropout_p(): the backbone's p under train(), 0 under eval()); a float
         overrides it.  Every rank and every forward call draws its own masks (seed mixes torch.initial_seed() and the rank)."""
         self.model = model
         self.engine = model.engine()
@@ -69,6 +72,14 @@ class TrainStep:
         eng = self.engine
         B = usr_idx.shape[0]
         gb = self.global_batch or B * self.buckets.world
+        eng.ensure_bound()
+        if self.buckets.flat.data_ptr() != eng.flat_grad.data_ptr() or self.exp_avg.numel() != eng.flat.numel():
+            # the engine re-bound its flat buffers (.to(), load_state_dict(assign=True), a replaced .data): reducing the old
+            # gradient buffer would silently leave every rank on its local gradients.  The layout is unchanged, so the Adam
+            # moments stay valid; only the bucket views move.
+            if self.exp_avg.numel() != eng.flat.numel():
+                raise _lib.MMIError("the engine's parameter layout changed under a live TrainStep; build a new TrainStep")
+            self.buckets = GradBuckets(eng.flat_grad, self.buckets.group, self.buckets.bucket_elems * 4)
         eng.bind_grads()           # Parameters' .grad alias the flat gradient buffer
         eng.flat_grad.zero_()
         eng.drop_p = self.model.dropout_p() if self.dropout is None else float(self.dropout)
@@ -98,6 +109,14 @@ class TrainStep:
         ops.clip_adamw(eng.flat, eng.flat_grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1], self.eps,
                        self.wd, self.max_norm if self.max_norm else 0.0, self.step_no, self.norm, None, self.ws)
         return scal
+
+    def check_indices(self, *idx):
+        """Debug aid (one sync): raises IndexError when a row id is past the table -- the reference's feat_memmap[line_id]
+        does; the gather kernel treats such an id as padding."""
+        n = self.gather.table.shape[0]
+        for t in idx:
+            if t.numel() and int(t.max()) >= n:
+                raise IndexError(f"row id {int(t.max())} is past the embedding table ({n} rows)")
 
     def step_host(self, usr_idx_h, vid_idx_h, gt_h, dev_bufs, micro_batch: int = 0):
         """End-to-end variant: pinned host index/label buffers -> H2D inside the call, loss read

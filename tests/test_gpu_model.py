@@ -158,15 +158,27 @@ def test_drop_in_training_loop_matches_oracle_adamw():
     oparams = [osd[k] for k in live]
     m = [torch.zeros_like(p) for p in oparams]
     v = [torch.zeros_like(p) for p in oparams]
-    params = list(model.parameters())
-    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4)
+    # exactly the driver's statements (main...SegMM.py:224-225,298): param_dict is a GENERATOR that AdamW consumes, so the
+    # later clip_grad_norm_(param_dict, 10.0) sees nothing and clips nothing -- the oracle's default (max_norm=None)
+    param_dict = model.parameters()
+    opt = torch.optim.AdamW(param_dict, lr=1e-3, weight_decay=1e-4)
+    with torch.no_grad():
+        model.stage_mlp1.weight.mul_(40.0)          # gradient norm well above 10: a working clip would change the result
+    sd0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    osd = {k: v.clone().requires_grad_(k in live) for k, v in sd0.items()}
+    oparams = [osd[k] for k in live]
     rng = np.random.default_rng(1)
+    max_gn = 0.0
     for step in (1, 2, 3):
         usr, usr_mask, vid, vid_mask, gt = synth.make_dense_batch(rng, 6, 16, 48)
         opt.zero_grad()
         out = _run(model, usr, usr_mask, vid, vid_mask, gt, dev)
         out["loss"].backward()
-        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        max_gn = max(max_gn, float(torch.sqrt(sum((p.grad.double() ** 2).sum() for p in model.parameters() if p.grad is not None))))
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert float(torch.nn.utils.clip_grad_norm_(param_dict, 10.0)) == 0.0
         opt.step()
         for p in oparams:
             p.grad = None
@@ -176,6 +188,7 @@ def test_drop_in_training_loop_matches_oracle_adamw():
         assert abs(out["loss"].item() - o["loss"].item()) < 1e-4 * abs(o["loss"].item())
         with torch.no_grad():
             mmi_oracle.clip_and_adamw([p for p in oparams], [p.grad for p in oparams], m, v, step)
+    assert max_gn > 10.0, f"the test must exercise gradients above the clip threshold (max norm {max_gn})"
     got = model.state_dict()
     for k in sd0:
         if k in live:
@@ -352,7 +365,7 @@ def test_bf16_training_auc_matches_fp32_oracle(dropout):
     m = [torch.zeros_like(p) for p in oparams]
     v = [torch.zeros_like(p) for p in oparams]
     table = synth.make_table(n_rows, din, seed=1234)
-    ts = TrainStep(model, torch.from_numpy(table).to(dev), lr=1e-3, weight_decay=1e-4, max_norm=10.0, global_batch=B)
+    ts = TrainStep(model, torch.from_numpy(table).to(dev), lr=1e-3, weight_decay=1e-4, global_batch=B)   # no clip: the reference default
 
     def dense(usr_idx, vid_idx):
         u, um = gather_oracle.gather_dense(table, usr_idx)

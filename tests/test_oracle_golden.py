@@ -283,7 +283,38 @@ def test_clip_adamw_oracle_matches_torch():
             p.grad = g.clone() * step
         n_ref = torch.nn.utils.clip_grad_norm_(ref_p, 10.0)
         opt.step()
-        n = mmi_oracle.clip_and_adamw(mine, [g.clone() * step for g in gs], m, v, step)
+        n = mmi_oracle.clip_and_adamw(mine, [g.clone() * step for g in gs], m, v, step, max_norm=10.0)   # clipping: explicit opt-in
         assert abs(n.item() - n_ref.item()) < 1e-4 * n_ref.item()
         for a, b in zip(mine, ref_p):
             assert torch.allclose(a, b.detach(), rtol=1e-6, atol=1e-7)
+
+
+def test_reference_driver_clip_is_a_no_op_and_the_oracle_default_follows_it():
+    """The driver's own statements (main_for_seq_leave_earlystop_SegMM.py:224-225,298): `param_dict = model.parameters()`
+    is a generator, AdamW's constructor consumes it, so `clip_grad_norm_(param_dict, 10.0)` walks nothing, returns 0 and
+    leaves gradients of norm >> 10 untouched.  mmi_oracle.clip_and_adamw / TrainStep default to exactly that."""
+    import inspect
+    import warnings
+    torch.manual_seed(1)
+    model = torch.nn.Linear(5, 7)
+    param_dict = model.parameters()
+    opt = torch.optim.AdamW(param_dict, lr=1e-3, weight_decay=1e-4)
+    mine = [p.detach().clone() for p in model.parameters()]
+    m = [torch.zeros_like(p) for p in mine]
+    v = [torch.zeros_like(p) for p in mine]
+    for step in (1, 2):
+        gs = [torch.randn_like(p) * 50 for p in model.parameters()]
+        for p, g in zip(model.parameters(), gs):
+            p.grad = g.clone()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert float(torch.nn.utils.clip_grad_norm_(param_dict, 10.0)) == 0.0      # exhausted generator
+        for p, g in zip(model.parameters(), gs):
+            assert torch.equal(p.grad, g)                                            # nothing was clipped
+        opt.step()
+        n = mmi_oracle.clip_and_adamw(mine, [g.clone() for g in gs], m, v, step)      # default: no clipping
+        assert n.item() > 10.0
+        for a, b in zip(mine, model.parameters()):
+            assert torch.allclose(a, b.detach(), rtol=1e-6, atol=1e-7)
+    from segmminterest_b200.train import TrainStep
+    assert inspect.signature(TrainStep.__init__).parameters["max_norm"].default is None

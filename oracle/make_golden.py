@@ -99,15 +99,31 @@ def run_model_case(name, d_model, nhead, nlayers, din, Lt, B, seed, store_sd=Tru
     print(name, "loss", save["loss"], "n_dead", len(dead))
 
 
-def run_general_case(name, input_type, d_model, nhead, nlayers, din, B, seed, loss_types, n_users=23, n_items=57, fusion_heads=2):
+@contextlib.contextmanager
+def _cuda_is_identity():
+    """The position bias hard-codes `.cuda()` on a fresh arange (decoder_leave_focal.py:498,651).  On this CPU-only container
+    the unmodified reference runs with Tensor.cuda patched to the identity -- the arithmetic is untouched."""
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda = orig
+
+
+def run_general_case(name, input_type, d_model, nhead, nlayers, din, B, seed, loss_types, n_users=23, n_items=57, fusion_heads=2,
+                     learnable_bias=0):
     """SURVEY 8f-1: ID inputs / two backbones + InteractionAggregation (the reference's default 'both' config), history
     padded to the reference's 100 tokens.  Stores the full state_dict, inputs, outputs and gradients."""
     args = ref_shim.make_args(d_model=d_model, nhead=nhead, num_layers_enc=nlayers, loss_type_list=list(loss_types),
-                              input_type=input_type, fusion_heads=fusion_heads)
+                              input_type=input_type, fusion_heads=fusion_heads, learnable_bias=learnable_bias)
     model = ref_shim.build_reference_model_general(args, din=din, n_users=n_users, n_items=n_items, seed=seed)
     g = torch.Generator().manual_seed(seed + 1)
     with torch.no_grad():
         for k, p in model.named_parameters():
+            if k in ("bias_weight", "bias_bias"):      # [1, 40], initialised to ones: make every position's pair distinct
+                p.copy_(torch.randn(p.shape, generator=g) * (0.02 if k == "bias_weight" else 0.3))
+                continue
             if p.ndim == 1:
                 p.add_(torch.randn(p.shape, generator=g) * 0.05)
             if k in ("stage_mlp1.weight", "stage_mlp2.weight"):
@@ -124,17 +140,18 @@ def run_general_case(name, input_type, d_model, nhead, nlayers, din, B, seed, lo
     batch = dict(usr_image=torch.from_numpy(usr), usr_id=torch.from_numpy(usr_id), usr_mask=torch.from_numpy(usr_mask),
                  vid_image=torch.from_numpy(vid), vid_id=torch.from_numpy(vid_id), vid_mask=torch.from_numpy(vid_mask),
                  gt=torch.from_numpy(gt.copy()))
-    out = ref_shim.run_reference(model, batch, mode="train")
+    with _cuda_is_identity():
+        out = ref_shim.run_reference(model, batch, mode="train")
     out["loss"].backward()
     save = dict(cfg=json.dumps(dict(d_model=d_model, nhead=nhead, num_layers_enc=nlayers, din=din, Lt=Lt, B=B, seed=seed,
                                     loss_types=list(loss_types), input_type=input_type, n_users=n_users, n_items=n_items,
-                                    fusion_heads=fusion_heads)),
+                                    fusion_heads=fusion_heads, learnable_bias=learnable_bias)),
                 usr_image=usr, vid_image=vid, usr_id=usr_id, vid_id=vid_id, usr_mask=usr_mask, vid_mask=vid_mask, gt_in=gt,
                 logits=out["logits"].detach().numpy(), gt_out=out["gt"].numpy(), loss=np.float64(out["loss"].item()),
                 mse=np.float64(out["mse"].item()), mse2=np.float64(out["mse2"].item()))
     for lt_ in loss_types:
         save[lt_] = np.float64(out[lt_].item())
-    with torch.no_grad():
+    with torch.no_grad(), _cuda_is_identity():
         batch["gt"] = torch.from_numpy(gt.copy())
         save["logits_inference"] = ref_shim.run_reference(model, batch, mode="inference")["logits"].numpy()
     dead = []
@@ -237,6 +254,17 @@ def run_eval_case():
         results = ev.main_eval_batch(args, interests, gt, torch.zeros_like(gt), results, type="inference")
     save = {k: np.asarray(v, dtype=np.float64) for k, v in results.items()}
     save["interests"] = interests.numpy()
+    # test_type 'old' (:270-271: the interests ARE the survival probabilities) and the `logits=` MAES bookkeeping (:309-320)
+    old = {k: [] for k in ("ProbAUC", "JaccardSim", "LeaveMSE", "view_lengths", "LeaveCTR", "LeaveCTR_view")}
+    old["MAES"] = 0.0
+    old["pred_leave"] = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        old = ev.main_eval_batch(args, interests, gt, torch.zeros_like(gt), old, type="inference", test_type="old", logits=logits * 0.125)   # scaled: the +-60 logits of row 5 would turn 1 / softmax into inf
+    for k, v in old.items():
+        if k == "pred_leave":
+            save["old/pred_leave"] = torch.stack(v).numpy()
+        else:
+            save["old/" + k] = np.asarray(v, dtype=np.float64)
     np.savez_compressed(os.path.join(OUT, "eval_cases.npz"), **save)
     print("eval_cases", {k: (len(v), float(np.mean(v))) for k, v in results.items()})
 
@@ -349,6 +377,16 @@ def run_general_cases():
     run_general_case("model_id_small", {"user": "id", "photo": "id"}, d_model=64, nhead=2, nlayers=3, din=24, B=4, seed=22,
                      loss_types=("focal",))
     run_fusion_variants()
+    run_bias_cases()
+
+
+def run_bias_cases():
+    """the learnable position bias (decoder_leave_focal.py:442-444,497-504,650-658) in the reference's default
+    'both' configuration with its default loss, and in the image-only focal configuration"""
+    run_general_case("model_both_bias", {"user": "both", "photo": "both"}, d_model=64, nhead=2, nlayers=3, din=24, B=4, seed=71,
+                     loss_types=("interestBPR",), learnable_bias=1)
+    run_general_case("model_image_bias", {"user": "image", "photo": "image"}, d_model=64, nhead=2, nlayers=3, din=24, B=4, seed=72,
+                     loss_types=("focal", "interestBPR"), learnable_bias=1)
 
 
 def run_ablation_cases():
@@ -392,6 +430,8 @@ if __name__ == "__main__":
         run_eval_case()
     elif "--topk-only" in sys.argv:
         run_topk_case()
+    elif "--bias-only" in sys.argv:
+        run_bias_cases()
     elif "--fusion-only" in sys.argv:
         run_fusion_variants()
     elif "--ablation-only" in sys.argv:

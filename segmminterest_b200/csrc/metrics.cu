@@ -4,6 +4,7 @@
 //
 //   interests = sigmoid(logits) * exposure_prob                       main...SegMM.py:402-403
 //   survival  = exp(cumsum(log interests))                            my_evaluation.py:273-274 (test_type 'new')
+//             = interests themselves                                  my_evaluation.py:270-271 (test_type 'old', input_kind 2)
 //   ProbAUC   = roc_auc_score(label, survival) over positions with gt != -2, label = (gt == -1 ? 0 : gt)   :73-80
 //   per row   : LeaveMSE prediction = sum of survival over valid positions   :82-85
 //               view_length = #(gt == 1), duration = #(gt != -2)
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(256) eval_rows_kernel(const float* __restrict_
     const float x = in[h] ? logits[(size_t)row * L + l] : 0.f;
     g[h] = in[h] ? gt[(size_t)row * L + l] : -2;
     valid[h] = in[h] && g[h] != -2;
-    itr[h] = input_kind == 0 ? (1.0f / (1.0f + expf(-x))) * (in[h] ? ep[l] : 1.f) : (in[h] ? x : 1.f);
+    itr[h] = input_kind == 0 ? (1.0f / (1.0f + expf(-x))) * (in[h] ? ep[l] : 1.f) : (in[h] ? x : 1.f);   // 1, 2: interests given
     logp[h] = in[h] ? logf(itr[h]) : 0.f;
   }
   float sc0 = logp[0], sc1 = logp[1];
@@ -46,7 +47,7 @@ __global__ void __launch_bounds__(256) eval_rows_kernel(const float* __restrict_
     if (lane >= o) { sc0 += a; sc1 += b; }
   }
   sc1 += __shfl_sync(0xffffffffu, sc0, 31);
-  const float surv[2] = {expf(sc0), expf(sc1)};
+  const float surv[2] = {input_kind == 2 ? itr[0] : expf(sc0), input_kind == 2 ? itr[1] : expf(sc1)};   // 2: test_type 'old'
   const int n_view = __popc(__ballot_sync(0xffffffffu, in[0] && g[0] == 1)) + __popc(__ballot_sync(0xffffffffu, in[1] && g[1] == 1));
   const int n_valid = __popc(__ballot_sync(0xffffffffu, valid[0])) + __popc(__ballot_sync(0xffffffffu, valid[1]));
   float pred = 0.f, jac = 0.f;
@@ -144,7 +145,8 @@ extern "C" int mmi_eval_metrics(const float* logits, const int64_t* gt, int B, i
                                 void* workspace, float* rows, float* out, mmi_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MMI_CHECK_ARG(logits && gt && workspace && rows && out, "eval_metrics: null pointer");
-  MMI_CHECK_ARG(input_kind == 1 || (input_kind == 0 && exposure_prob), "eval_metrics: input_kind 0 (logits, needs exposure_prob) or 1 (interests)");
+  MMI_CHECK_ARG(input_kind == 1 || input_kind == 2 || (input_kind == 0 && exposure_prob),
+                "eval_metrics: input_kind 0 (logits, needs exposure_prob), 1 (interests) or 2 (interests that already are survival probabilities)");
   MMI_CHECK_ARG(B > 0 && L > 0 && L <= 64, "eval_metrics: need B > 0 and 0 < L <= 64 (got B %d, L %d)", B, L);
   MMI_CHECK_ARG((int64_t)B * L < (1ll << 30), "eval_metrics: B * L must stay below 2^30");
   MMI_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 7) == 0, "eval_metrics: workspace must be 8-byte aligned");

@@ -24,7 +24,7 @@ class DeviceMetrics:
     def __init__(self):
         self._buf = {}
 
-    def __call__(self, logits: torch.Tensor, gt: torch.Tensor, exposure_prob=None, interests=False):
+    def __call__(self, logits: torch.Tensor, gt: torch.Tensor, exposure_prob=None, interests=False, old=False):
         if not logits.is_cuda:
             raise _lib.MMIError("DeviceMetrics needs CUDA tensors; there is no CPU fallback")
         B, L = logits.shape
@@ -39,7 +39,7 @@ class DeviceMetrics:
         if not interests:
             ep = exposure_prob if torch.is_tensor(exposure_prob) else torch.tensor(list(exposure_prob)[:L], dtype=torch.float32)
             ep = ep.to(logits.device, torch.float32).contiguous()
-        ops.eval_metrics(logits.float().contiguous(), gt.to(torch.int64).contiguous(), ep, rows, out, ws, interests=interests)
+        ops.eval_metrics(logits.float().contiguous(), gt.to(torch.int64).contiguous(), ep, rows, out, ws, interests=interests, old=old)
         return rows, out
 
 
@@ -54,15 +54,12 @@ def prob_auc_batch(logits, gt, exposure_prob) -> torch.Tensor:
 
 
 def main_eval_batch(args, interests, ground_truths, pred_labels, results_list, type="inference", test_type="new", logits=None):
-    """my_evaluation.py:264-357 for test_type 'new'.  `interests` = sigmoid(logits) * exposure_prob as the driver builds
-    them (main...SegMM.py:402-403)."""
-    if test_type != "new":
-        raise NotImplementedError("test_type 'old' (interests already are survival probabilities) is not built")
-    if logits is not None:
-        raise NotImplementedError("the `logits=` branch (MAES, my_evaluation.py:309-320) is never taken by the SegMM driver")
+    """my_evaluation.py:264-357.  `interests` = sigmoid(logits) * exposure_prob as the driver builds them
+    (main...SegMM.py:402-403); test_type 'old' takes them as survival probabilities directly (:270-271), anything else
+    builds exp(cumsum(log interests)) (:273-274).  `logits=` adds the MAES bookkeeping of :309-320."""
     if getattr(args, "draw_case", 0):
         raise NotImplementedError("draw_case needs matplotlib on the host (my_evaluation.py:233-262)")
-    rows, out = _METRICS(interests, ground_truths, interests=True)
+    rows, out = _METRICS(interests, ground_truths, interests=True, old=test_type == "old")
     host = torch.cat([rows.reshape(-1), out]).cpu()          # the one D2H copy (and sync) of the batch
     r, o = host[:-4].view(-1, 6), host[-4:]
     if "ProbAUC" in results_list:
@@ -82,6 +79,17 @@ def main_eval_batch(args, interests, ground_truths, pred_labels, results_list, t
             evaluations = TOP_K_leave(inter_np, view_lengths, mask_np, permutation=args.TOP_K_permutation)
         for name, value in evaluations.items():
             results_list.setdefault(name, []).append(float(value))
+    if logits is not None:
+        # :309-320 -- expected leave position under softmax(1 / softmax(logits)); a [B, 40] host computation in the reference
+        # too (its `pos` lives on the CPU), accumulated as a running sum in results_list['MAES']
+        lg = logits.detach().float().cpu()
+        inv = 1 / torch.nn.functional.softmax(lg, dim=1)
+        leave_p = inv / inv.sum(dim=1).unsqueeze(1)
+        pred_leave = torch.sum(leave_p * torch.linspace(0, 39, 40), dim=1).int()
+        views = (ground_truths == 1).sum(dim=1).cpu()
+        mae = float((views - pred_leave).abs().double().mean())          # sklearn.metrics.mean_absolute_error
+        results_list["MAES"] += mae * interests.shape[0]
+        results_list["pred_leave"].append(pred_leave)
     for i in range(r.shape[0]):                               # per-row appends, in the reference's row-major order (:324-355)
         for eval_type in list(results_list):
             if eval_type == "JaccardSim":

@@ -9,6 +9,8 @@ Host-side index arithmetic only (integers): no embedding row is touched here; th
 """
 from __future__ import annotations
 
+import random as _pyrandom
+
 import numpy as np
 
 PHOTO_MAX = 40    # utils/dataloader_SegMM.py:198
@@ -116,7 +118,8 @@ class SegmentIndex:
     def history_idx(self, user_id, history_items, history_playing, rng: np.random.Generator | None = None) -> np.ndarray:
         """[B, 100] int32 rows of the users' histories (utils/dataloader_SegMM.py:319-350): for each past video the
         watched segments i < ceil(playing / 5000) that exist in the map, in order, then the user's `user_input_dict`
-        rows; more than 100 tokens are sub-sampled WITHOUT order (random.sample in the reference; `rng` here)."""
+        rows; more than 100 tokens are sub-sampled WITHOUT order: `random.sample` on Python's global generator like the
+        reference when rng is None, otherwise from the numpy Generator `rng`."""
         B = len(user_id)
         # zip(history_items, history_playing) in the reference (:322) stops at the shorter of the two lists
         n_hist = np.array([min(len(h), len(p)) for h, p in zip(history_items, history_playing)], dtype=np.int64)
@@ -144,13 +147,17 @@ class SegmentIndex:
             if small[b]:
                 out[b, n_tok[b]:n_tok[b] + n_extra[b]] = extras[b]
         if not small.all():
-            # the reference draws with random.sample (:346), which the driver seeds (main...SegMM.py:26-28): derive the default
-            # generator from numpy's seeded global state so that a seeded run stays reproducible here too
-            rng = rng or np.random.default_rng(np.random.randint(2 ** 31))
+            # the reference draws `random.sample(range(n), 100)` from Python's global generator (:346), which the driver seeds
+            # (main...SegMM.py:26-28); samples are visited in batch order, one draw per over-long user, so with rng=None a
+            # seeded run picks exactly the reference's tokens in the reference's order (tests/test_config1.py)
             starts = np.cumsum(n_tok) - n_tok
             for b in np.nonzero(~small)[0]:
                 allrows = np.concatenate([rows[starts[b]:starts[b] + n_tok[b]], extras[b]])
-                out[b] = allrows[rng.choice(allrows.size, USER_MAX, replace=False)]
+                if rng is None:
+                    pick = np.asarray(_pyrandom.sample(range(allrows.size), USER_MAX), dtype=np.int64)
+                else:
+                    pick = rng.choice(allrows.size, USER_MAX, replace=False)
+                out[b] = allrows[pick]
         return out
 
     def batch(self, user_id, video_id, duration_ms, history_items, history_playing, label_1d, rng=None) -> dict:

@@ -10,7 +10,8 @@ keys, shapes, dtypes and values as `DataCollator` -- directly on the device with
 
 Row order: `shuffle=True` draws the permutation from numpy's global RNG exactly like the reference
 (`np.random.shuffle(samples_BN)`, :278).  Users with more than 100 history tokens are sub-sampled with `random.sample`
-in the reference (:346); here with `rng` (documented deviation: any 100 distinct tokens, order not preserved).
+in the reference (:346); so are they here (Python's global generator, same draw order: a seeded run reproduces the
+reference's batches bit for bit, tests/test_config1.py) unless a numpy Generator is passed as `rng`.
 """
 from __future__ import annotations
 
@@ -28,19 +29,14 @@ def _parse_int_list(s) -> np.ndarray:
     return np.array([int(x) for x in s.strip("[").strip("]").split(" ") if x], dtype=np.int64)
 
 
-class DeviceFrameLoader:
-    def __init__(self, corpus, lineid_map: dict, table: torch.Tensor, phase: str = "train", batch_size: int = 512, shuffle: bool = False,
-                 user2id: dict | None = None, item2id: dict | None = None, normalise: bool = False, out_dtype=torch.float32,
+class HostFrameIndex:
+    """The host half of the loader: the interaction table of one phase parsed once into arrays, and the int32 row-id form
+    of any set of interactions (integers only -- no embedding row is touched, no device needed)."""
+
+    def __init__(self, corpus, lineid_map: dict | None, phase: str = "train", user2id: dict | None = None, item2id: dict | None = None,
                  rng: np.random.Generator | None = None, index: SegmentIndex | None = None):
-        if not table.is_cuda:
-            raise _lib.MMIError("DeviceFrameLoader needs the embedding table in device memory; there is no CPU fallback")
-        self.table = table.contiguous()
         self.index = index or SegmentIndex(lineid_map, corpus.user_input_dict)
-        if self.index.n_rows > self.table.shape[0]:
-            # the reference's feat_memmap[line_id] raises IndexError for a row past the table; the gather kernel would read
-            # such an id as padding, so a table loaded with the wrong n_rows must be refused here
-            raise IndexError(f"line-id map refers to row {self.index.n_rows - 1} but the table has {self.table.shape[0]} rows")
-        self.batch_size, self.shuffle, self.normalise, self.out_dtype, self.rng = int(batch_size), shuffle, normalise, out_dtype, rng
+        self.rng = rng
         df = corpus.data_df[phase]
         self.n = len(df)
         col = {c: df[c].to_numpy() for c in ("user_id", "video_id", "time_ms", "duration_ms", "playing_time_x", "label_1D",
@@ -62,9 +58,6 @@ class DeviceFrameLoader:
         self.user_identity = np.array([int(u2i[str(u)]) for u in self.user_id], dtype=np.int64) if user2id is not None else None
         self.photo_identity = np.array([int(i2i[str(p)]) for p in self.video_id], dtype=np.int64) if item2id is not None else None
 
-    def __len__(self):
-        return (self.n + self.batch_size - 1) // self.batch_size
-
     def index_batch(self, sel: np.ndarray):
         """int32 row ids (-1 = pad) of the interactions `sel`: usr_idx [b,100], vid_idx [b,40] -- the form TrainStep and
         InferenceScorer consume directly."""
@@ -76,6 +69,34 @@ class DeviceFrameLoader:
             raise IndexError("user with no history token and no user_input_dict row (the reference raises IndexError at "
                              "utils/dataloader_SegMM.py:259)")
         return usr, vid
+
+    def scalars(self, sel: np.ndarray) -> dict:
+        """the per-interaction scalars and labels of the reference batch (host arrays, reference dtypes)"""
+        out = {"play_time": self.play_time[sel], "duration": self.duration[sel], "user_id": self.user_id[sel],
+               "photo_id": self.video_id[sel], "time_ms": self.time_ms[sel], "label": self.label[sel]}
+        if self.user_identity is not None:
+            out["user_identity_id"] = self.user_identity[sel]
+        if self.photo_identity is not None:
+            out["photo_identity_id"] = self.photo_identity[sel]
+        return out
+
+
+class DeviceFrameLoader(HostFrameIndex):
+    def __init__(self, corpus, lineid_map: dict, table: torch.Tensor, phase: str = "train", batch_size: int = 512, shuffle: bool = False,
+                 user2id: dict | None = None, item2id: dict | None = None, normalise: bool = False, out_dtype=torch.float32,
+                 rng: np.random.Generator | None = None, index: SegmentIndex | None = None):
+        if not table.is_cuda:
+            raise _lib.MMIError("DeviceFrameLoader needs the embedding table in device memory; there is no CPU fallback")
+        super().__init__(corpus, lineid_map, phase, user2id, item2id, rng, index)
+        self.table = table.contiguous()
+        if self.index.n_rows > self.table.shape[0]:
+            # the reference's feat_memmap[line_id] raises IndexError for a row past the table; the gather kernel would read
+            # such an id as padding, so a table loaded with the wrong n_rows must be refused here
+            raise IndexError(f"line-id map refers to row {self.index.n_rows - 1} but the table has {self.table.shape[0]} rows")
+        self.batch_size, self.shuffle, self.normalise, self.out_dtype = int(batch_size), shuffle, normalise, out_dtype
+
+    def __len__(self):
+        return (self.n + self.batch_size - 1) // self.batch_size
 
     def __iter__(self):
         order = np.arange(self.n)

@@ -310,7 +310,7 @@ def cast_bf16(src, dst, rows, cols, transpose=False):
     LaunchCounter.n += 1
 
 
-def eval_metrics(logits, gt, exposure_prob, rows, out, workspace, interests=False):
+def eval_metrics(logits, gt, exposure_prob, rows, out, workspace, interests=False, old=False):
     """Device validation metrics (mmi_eval_metrics): rows [B,6] = pred_view_length, view_length, duration, LeaveCTR,
     LeaveCTR_view, JaccardSim; out[0] = ProbAUC of the batch."""
     B, L = logits.shape
@@ -319,7 +319,7 @@ def eval_metrics(logits, gt, exposure_prob, rows, out, workspace, interests=Fals
     assert rows.numel() >= B * 6 and out.numel() >= 4
     assert workspace.numel() * workspace.element_size() >= _lib.load().mmi_eval_metrics_workspace(B, L)
     with TIMER.region("eval_metrics"):
-        rc = _lib.load().mmi_eval_metrics(logits.data_ptr(), gt.data_ptr(), B, L, _ptr(exposure_prob), 1 if interests else 0,
+        rc = _lib.load().mmi_eval_metrics(logits.data_ptr(), gt.data_ptr(), B, L, _ptr(exposure_prob), (2 if old else 1) if interests else 0,
                                           workspace.data_ptr(), rows.data_ptr(), out.data_ptr(), _stream())
     _lib.check(rc, "mmi_eval_metrics")
     LaunchCounter.n += 3

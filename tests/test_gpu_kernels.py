@@ -388,6 +388,16 @@ def test_eval_metrics_match_reference_golden_and_oracle(dev):
     res = main_eval_batch(SimpleNamespace(TOP_K_mask=0, draw_case=0), torch.from_numpy(z["interests"]).to(dev), gt, None, res)
     for k in res:
         assert np.allclose(np.asarray(res[k]), z[k], rtol=2e-5, atol=2e-6, equal_nan=True), k
+    # test_type='old' (the interests are the survival probabilities, my_evaluation.py:270-271) + the `logits=` MAES
+    # bookkeeping (:309-320), against the unmodified reference's lists
+    res = {k: [] for k in ("ProbAUC", "JaccardSim", "LeaveMSE", "view_lengths", "LeaveCTR", "LeaveCTR_view")}
+    res["MAES"] = 0.0
+    res["pred_leave"] = []
+    res = main_eval_batch(SimpleNamespace(TOP_K_mask=0, draw_case=0), torch.from_numpy(z["interests"]).to(dev), gt, None, res,
+                          test_type="old", logits=logits * 0.125)
+    for k in ("ProbAUC", "JaccardSim", "LeaveMSE", "view_lengths", "LeaveCTR", "LeaveCTR_view"):
+        assert np.allclose(np.asarray(res[k]), z["old/" + k], rtol=2e-5, atol=2e-6, equal_nan=True), k
+    assert abs(res["MAES"] - float(z["old/MAES"])) < 1e-9 and np.array_equal(torch.stack(res["pred_leave"]).numpy(), z["old/pred_leave"])
     # larger batch, quantised logits => many exact ties
     rng = np.random.default_rng(17)
     from segmminterest_b200 import synth

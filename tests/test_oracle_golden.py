@@ -127,7 +127,8 @@ def test_dropout_sites_match_reference_generator_stream(name):
     assert _rel(ev["logits"].numpy(), z["logits"]) > 1e-2
 
 
-@pytest.mark.parametrize("name", ["model_both_small", "model_id_small", "model_both_fh0", "model_both_fh-1", "model_both_fh-2", "model_both_fh-3"])
+@pytest.mark.parametrize("name", ["model_both_small", "model_id_small", "model_both_fh0", "model_both_fh-1", "model_both_fh-2", "model_both_fh-3",
+                                  "model_both_bias", "model_image_bias"])
 def test_general_config_matches_reference(name):
     """ID-embedding inputs, two backbones + InteractionAggregation (the reference default 'both'),
     interestBPR: the oracle against the unmodified reference."""

@@ -42,7 +42,7 @@ def resident_table(feat_memmap, device=None, chunk_rows: int = 1 << 16) -> torch
     out = torch.empty(n, d, dtype=torch.float32, device=dev)
     for a in range(0, n, chunk_rows):
         b = min(n, a + chunk_rows)
-        out[a:b].copy_(torch.from_numpy(np.ascontiguousarray(feat_memmap[a:b])).to(dev).to(torch.float32))
+        out[a:b].copy_(torch.from_numpy(np.array(feat_memmap[a:b])).to(dev).to(torch.float32))
     _TABLES[key] = (feat_memmap, out)
     return out
 

@@ -188,12 +188,28 @@ typedef struct {
   const void* dout; int64_t lddo;
   float* delta;                    /* [B, H, Lq] scratch: rowsum(dO * O) */
   mmi_dropout drop;                /* logits dropout; thr8 = 0: off */
+  /* mmi_attn_bwd_fused only: fp32 accumulators of the partial dQ tiles of block i, [B*Lq, H*dh] (row-major, leading
+   * dimension H*dh), and one int32 counter per (b, h).  Both must be ZERO on entry and are zero again when the call has
+   * finished (the last key-tile CTA of every (b, h) converts its dQ columns to blk[i].dq and clears what it read).  */
+  float* dq_acc[2];
+  int32_t* dq_count[2];
 } mmi_attn_args;
 int mmi_attn_fwd(const mmi_attn_args* a, mmi_stream_t stream);
 /* writes dq for both blocks and delta */
 int mmi_attn_bwd_dq(const mmi_attn_args* a, mmi_stream_t stream);
 /* writes dk, dv of block `which` (needs lse and delta from the calls above) */
 int mmi_attn_bwd_dkv(const mmi_attn_args* a, int which, mmi_stream_t stream);
+/* MMI_IMPL_TC, bf16, dh 32: the whole backward of key block `which` in ONE kernel -- dk, dv (owned by the CTA's 128 keys)
+ * AND that block's dq (partial tiles reduced through dq_acc[which]) AND their bias-gradient sums; S, dP and the
+ * exponential are computed once per score instead of once in mmi_attn_bwd_dq and once in mmi_attn_bwd_dkv.  Needs out,
+ * lse and dout (delta is recomputed on the fly and not written).  Returns 1 (no error set) when the configuration is
+ * not covered and the caller should use the two-kernel path.                                                         */
+int mmi_attn_bwd_fused(const mmi_attn_args* a, int which, mmi_stream_t stream);
+/* MMI_IMPL_TC, bf16, dh 32, at most 5 key tiles of 128 over both blocks (640 keys): the WHOLE backward of the query side in
+ * one launch, one CTA per (b, h) that owns every key of both blocks -- dq, dk, dv of both blocks and their bias-gradient
+ * sums, nothing accumulated through global memory (models/encoder.py:138-161 backward).  Needs out, lse, dout; delta is
+ * recomputed and not written.  Returns 1 (no error set) when the shapes are not covered.                            */
+int mmi_attn_bwd_all(const mmi_attn_args* a, mmi_stream_t stream);
 
 /* ---- a-9: head Linear(d -> 1)  (models/decoder_leave_focal.py:451,596) ---------------
  * logits[r] = w . x[r] (+ b[0]) (+ add[r]);  b and add may be NULL.  `add` chains two heads for the two-backbone

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmmi_b200.so")
+LIB_PATH = os.environ.get("MMI_LIB_PATH") or os.path.join(HERE, "libmmi_b200.so")   # override: A/B builds of the kernels (tools/)
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
@@ -47,7 +47,8 @@ class AttnArgs(C.Structure):
                 ("mask_q", c_p), ("nblk", C.c_int), ("blk", AttnBlock * 2),
                 ("out", c_p), ("ldo", i64), ("lse", c_p),
                 ("dout", c_p), ("lddo", i64), ("delta", c_p),
-                ("drop", Dropout)]
+                ("drop", Dropout),
+                ("dq_acc", c_p * 2), ("dq_count", c_p * 2)]
 
 
 class LossArgs(C.Structure):
@@ -79,6 +80,8 @@ _SIGS = {
     "mmi_attn_fwd": (C.c_int, [C.POINTER(AttnArgs), c_p]),
     "mmi_attn_bwd_dq": (C.c_int, [C.POINTER(AttnArgs), c_p]),
     "mmi_attn_bwd_dkv": (C.c_int, [C.POINTER(AttnArgs), C.c_int, c_p]),
+    "mmi_attn_bwd_fused": (C.c_int, [C.POINTER(AttnArgs), C.c_int, c_p]),
+    "mmi_attn_bwd_all": (C.c_int, [C.POINTER(AttnArgs), c_p]),
     "mmi_head_fwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p]),
     "mmi_head_bwd_workspace": (i64, [C.c_int]),
     "mmi_head_bwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),

@@ -75,3 +75,13 @@ static int attn_dispatch(int kind, const mmi_attn_args* a, int which, mmi_stream
 extern "C" int mmi_attn_fwd(const mmi_attn_args* a, mmi_stream_t stream) { return attn_dispatch(0, a, 0, stream); }
 extern "C" int mmi_attn_bwd_dq(const mmi_attn_args* a, mmi_stream_t stream) { return attn_dispatch(1, a, 0, stream); }
 extern "C" int mmi_attn_bwd_dkv(const mmi_attn_args* a, int which, mmi_stream_t stream) { return attn_dispatch(2, a, which, stream); }
+extern "C" int mmi_attn_bwd_all(const mmi_attn_args* a, mmi_stream_t stream) {
+  MMI_CHECK_ARG(a != nullptr, "attn: null args");
+  if (a->impl != MMI_IMPL_TC) return 1;          // the strict-parity FFMA path keeps its two kernels
+  return attn_tc(4, a, 0, reinterpret_cast<cudaStream_t>(stream));
+}
+extern "C" int mmi_attn_bwd_fused(const mmi_attn_args* a, int which, mmi_stream_t stream) {
+  MMI_CHECK_ARG(a != nullptr, "attn: null args");
+  if (a->impl != MMI_IMPL_TC) return 1;          // the strict-parity FFMA path keeps its two kernels
+  return attn_tc(3, a, which, reinterpret_cast<cudaStream_t>(stream));
+}

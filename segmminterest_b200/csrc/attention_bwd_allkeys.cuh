@@ -1,0 +1,403 @@
+// Included by attention_tc.cu inside namespace mmi::tc, after attention_bwd_fused.cuh (shares QVec64, dot8_bf16, desc_mn128).
+//
+// ====================================================================================== backward, one CTA per (b, h)
+// The whole attention backward of one query side in ONE launch: the CTA owns every key of BOTH key blocks of its (b, h)
+// (at most 5 tiles of 128 keys: 540 keys at the benchmark's shapes), so
+//   * dK_j / dV_j of every key tile accumulate in TMEM over the whole query loop (5 x 64 columns),
+//   * dQa / dQb of the current 64-query tile accumulate in TMEM over the key tiles of their block and are complete when the
+//     key loop ends: they leave as bf16 rows straight from the accumulator -- no partial tiles, no atomics, no fp32
+//     round trip through HBM (the per-key-block kernel of attention_bwd_fused.cuh needs all three and loses to them),
+//   * Q, dO, lse and delta = rowsum(O * dO) of a query tile are fetched ONCE for all key tiles,
+//   * S^T, dP^T and the exponential are computed once per score (5 MMAs + 1 ex2 instead of 7 + 2 in the dq / dk,dv pair).
+// Per (query tile i, key tile j):  S^T = K_j Q_blk^T,  dP^T = V_j dO^T  (128 keys x 64 queries)  ->  softmax threads
+// (thread = key row x 16-query chunk: 16 warps, per-query constants live in registers across the key tiles)  ->
+// dV_j += P^T dO,  dK_j += dS^T Q_blk,  dQ_blk += dS K_j  (A = the dS^T staging tile read MN-major, M = 64).
+// smem: K,V of all tiles 80 KB | Q ring [2][Qa | Qb | dO] 24 KB | P^T 16 KB | dS^T 16 KB | vectors, barriers   (~140 KB, 1 CTA / SM)
+// TMEM: S^T @0 (64) | dP^T @64 (64) | dQa @128 | dQb @160 | dK_j @192+64j | dV_j @224+64j                        (512 columns)
+constexpr int AK_MAXT = 5;
+constexpr int AK_THREADS = 64 + 16 * 32;
+constexpr uint32_t AK_TMEM_COLS = 512;
+constexpr uint32_t AK_QSTAGE = 3 * TILE64Q;      // Qa | Qb | dO
+
+struct AKBars {
+  uint64_t once, q_full[2], q_empty[2], a_ready, s_free, p_ready, p_free, dq_ready, dq_free, done;
+  uint32_t tmem_slot, pad;
+  float colsum[2][DH];
+};
+
+template <bool DROP>
+__global__ void __launch_bounds__(AK_THREADS, 1)
+attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
+                           const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
+                           const __grid_constant__ CUtensorMap tmVa, const __grid_constant__ CUtensorMap tmVb,
+                           const __grid_constant__ CUtensorMap tmdO, const AttnTcParams p,
+                           __nv_bfloat16* __restrict__ dk0, __nv_bfloat16* __restrict__ dk1, __nv_bfloat16* __restrict__ dv0,
+                           __nv_bfloat16* __restrict__ dv1, int64_t lddk0, int64_t lddk1, int64_t lddv0, int64_t lddv1,
+                           float* dbk0, float* dbk1, float* dbv0, float* dbv1) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sKV = smem;                                    // [AK_MAXT][K 8 KB | V 8 KB]
+  uint8_t* sQ = sKV + AK_MAXT * 2 * TILE128;              // [2][Qa | Qb | dO]
+  uint8_t* sPT = sQ + 2 * AK_QSTAGE;                      // 104 KB from the base: 1024-aligned
+  uint8_t* sdST = sPT + STILE;
+  QVec64* qv = reinterpret_cast<QVec64*>(sdST + STILE);
+  AKBars* bars = reinterpret_cast<AKBars*>(qv + 2);
+
+  const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int nt0 = (p.Lk[0] + QT - 1) / QT, nt1 = p.nblk > 1 ? (p.Lk[1] + QT - 1) / QT : 0;
+  const int NT = nt0 + nt1;                               // <= AK_MAXT (host)
+  const int T = (p.Lq + QN - 1) / QN;
+  const int total = T * NT;
+
+  // ---- producer state (warp 0): per-query scalars of the query tile about to be staged, two queries per lane
+  float nl_n[2] = {0.f, 0.f}, nd_n[2] = {0.f, 0.f};
+  uint32_t rh_n[2] = {0u, 0u};
+  bool mq_n[2] = {false, false};
+  auto fetch = [&](int i) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int qi = i * QN + u * 32 + lane;
+      if (qi < p.Lq) {
+        const int64_t tok = (int64_t)b * p.Lq + qi;
+        const float lse = p.lse[((int64_t)b * p.H + h) * p.Lq + qi];
+        mq_n[u] = p.mask_q[tok] != 0;
+        const uint4* orow = reinterpret_cast<const uint4*>(p.out + tok * p.ldo + h * DH);
+        const uint4* grow = reinterpret_cast<const uint4*>(p.dout + tok * p.lddo + h * DH);
+        uint4 o[4], g[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) { o[d] = orow[d]; g[d] = grow[d]; }
+        float delta = 0.f;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) delta += dot8_bf16(o[d], g[d]);
+        nl_n[u] = -lse * kLog2e;
+        nd_n[u] = -delta * p.scale;
+      } else { nl_n[u] = -INFINITY; nd_n[u] = 0.f; mq_n[u] = false; }
+      rh_n[u] = DROP ? drop_rowhash(p.drop.key, (uint64_t)(((int64_t)b * p.H + h) * p.Lq + qi)) : 0u;
+    }
+  };
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_init(&bars->once, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&bars->q_full[s], 1); mbar_init(&bars->q_empty[s], 1); }
+      mbar_init(&bars->a_ready, 1);
+      mbar_init(&bars->s_free, 512);
+      mbar_init(&bars->p_ready, 512);
+      mbar_init(&bars->p_free, 1);
+      mbar_init(&bars->dq_ready, 1);
+      mbar_init(&bars->dq_free, 512);
+      mbar_init(&bars->done, 1);
+      fence_barrier_init();
+      mbar_expect_tx(&bars->once, NT * 2 * TILE128);
+      for (int j = 0; j < NT; ++j) {
+        const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
+        const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * QT;
+        tma_load_2d(blk ? &tmKb : &tmKa, &bars->once, sKV + j * 2 * TILE128, h * DH, row);
+        tma_load_2d(blk ? &tmVb : &tmVa, &bars->once, sKV + j * 2 * TILE128 + TILE128, h * DH, row);
+      }
+    }
+    __syncwarp();
+    fetch(0);
+  }
+  if (threadIdx.x < 2 * DH) (&bars->colsum[0][0])[threadIdx.x] = 0.f;
+  // ---- softmax threads: which of their key rows (one per key tile) exist / are unmasked
+  uint32_t kin_bits = 0u, mk_bits = 0u;
+  if (warp >= 2) {
+    const int row = (warp & 3) * 32 + lane;
+    for (int j = 0; j < NT; ++j) {
+      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
+      const int Lk = blk ? p.Lk[1] : p.Lk[0];
+      const int kj = kt * QT + row;
+      if (kj < Lk) {
+        kin_bits |= 1u << j;
+        if ((blk ? p.mask_k[1] : p.mask_k[0])[(int64_t)b * Lk + kj] != 0) mk_bits |= 1u << j;
+      }
+    }
+  }
+  if (warp == 2) TRACE(4090);
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "r"(AK_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = bars->tmem_slot;
+  const uint32_t tdPT = tmem + QN, tdQ = tmem + 2 * QN, tdKV = tmem + 3 * QN;
+  if (warp == 2) TRACE(4091);
+
+  if (warp == 0) {
+    // ================================================================= producer
+    for (int i = 0; i < T; ++i) {
+      const int st = i & 1;
+      if (i >= 2) mbar_wait_bg(&bars->q_empty[st], ((i >> 1) & 1) ^ 1);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        qv[st].nlse2[u * 32 + lane] = nl_n[u];
+        qv[st].nds[u * 32 + lane] = nd_n[u];
+        if constexpr (DROP) qv[st].rh[u * 32 + lane] = rh_n[u];
+        const uint32_t bits = __ballot_sync(0xffffffffu, mq_n[u]);
+        if (lane == 0) qv[st].mq[u] = bits;
+      }
+      __syncwarp();
+      if (elect_one()) {
+        mbar_expect_tx(&bars->q_full[st], (p.nblk > 1 ? 3 : 2) * TILE64Q);
+        uint8_t* dst = sQ + st * AK_QSTAGE;
+        const int row = b * p.Lq + i * QN;
+        tma_load_2d(&tmQa, &bars->q_full[st], dst, h * DH, row);
+        if (p.nblk > 1) tma_load_2d(&tmQb, &bars->q_full[st], dst + TILE64Q, h * DH, row);
+        tma_load_2d(&tmdO, &bars->q_full[st], dst + 2 * TILE64Q, h * DH, row);
+      }
+      __syncwarp();
+      if (i + 1 < T) fetch(i + 1);
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    const uint32_t tS = uniform(tmem), tdPTu = uniform(tdPT), tdQu = uniform(tdQ), tdKVu = uniform(tdKV);
+    mbar_wait(&bars->once, 0);
+    const uint32_t aKV = smem_u32(sKV), aQs = smem_u32(sQ), aPT = smem_u32(sPT), adST = smem_u32(sdST);
+    auto issue_back = [&](int u) {
+      const int iu = u / NT, ju = u - iu * NT, su = iu & 1;
+      const int blk = ju < nt0 ? 0 : 1, kt = blk ? ju - nt0 : ju;
+      mbar_wait_bg(&bars->p_ready, u & 1);
+      if (ju == 0 && iu >= 1) mbar_wait_bg(&bars->dq_free, (iu - 1) & 1);      // last query tile's dQ has left the accumulators
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t aQ = aQs + su * AK_QSTAGE + blk * TILE64Q, adO = aQs + su * AK_QSTAGE + 2 * TILE64Q;
+        const uint32_t aK = aKV + ju * 2 * TILE128;
+        const uint32_t tdK = tdKVu + ju * 2 * DH, tdV = tdK + DH;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tdV, desc_k128(aPT, k), desc_mn64(adO, k), IDESC_O, (iu > 0 || k > 0) ? 1u : 0u);    // dV_j += P^T dO
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tdK, desc_k128(adST, k), desc_mn64(aQ, k), IDESC_O, (iu > 0 || k > 0) ? 1u : 0u);    // dK_j += dS^T Q
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_f16(tdQu + blk * DH, desc_mn128(adST, k), desc_mn64(aK, k), IDESC_DQ, (kt > 0 || k > 0) ? 1u : 0u);   // dQ_blk += dS K_j
+        umma_commit(&bars->p_free);
+        if (ju == NT - 1) {
+          umma_commit(&bars->q_empty[su]);
+          umma_commit(&bars->dq_ready);
+        }
+      }
+      __syncwarp();
+    };
+    int t = 0;
+    for (int i = 0; i < T; ++i) {
+      const int st = i & 1;
+      mbar_wait_bg(&bars->q_full[st], (i >> 1) & 1);
+      for (int j = 0; j < NT; ++j, ++t) {
+        const int blk = j < nt0 ? 0 : 1;
+        if (t >= 1) mbar_wait_bg(&bars->s_free, (t - 1) & 1);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t aQ = aQs + st * AK_QSTAGE + blk * TILE64Q, adO = aQs + st * AK_QSTAGE + 2 * TILE64Q;
+          const uint32_t aK = aKV + j * 2 * TILE128, aV = aK + TILE128;
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma_f16(tS, desc_k64(aK, k), desc_k64(aQ, k), IDESC_S64T, k);        // S^T  = K_j Q^T
+#pragma unroll
+          for (int k = 0; k < 2; ++k) umma_f16(tdPTu, desc_k64(aV, k), desc_k64(adO, k), IDESC_S64T, k);    // dP^T = V_j dO^T
+          umma_commit(&bars->a_ready);
+        }
+        __syncwarp();
+        TRACE(t * 8 + 6);
+        if (t >= 1) issue_back(t - 1);
+        TRACE(t * 8 + 7);
+      }
+    }
+    issue_back(total - 1);
+    if (elect_one()) umma_commit(&bars->done);
+    __syncwarp();
+  } else {
+    // ================================================================= softmax + dQ drain + epilogue (16 warps)
+    const int qd = warp & 3, c16 = (warp - 2) >> 2, row = qd * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
+    const uint32_t a_ready_a = smem_u32(&bars->a_ready), s_free_a = smem_u32(&bars->s_free), p_ready_a = smem_u32(&bars->p_ready);
+    const uint32_t p_free_a = smem_u32(&bars->p_free), q_full_a = smem_u32(&bars->q_full[0]), qv_a = smem_u32(qv);
+    const uint32_t dq_ready_a = smem_u32(&bars->dq_ready), dq_free_a = smem_u32(&bars->dq_free);
+    const uint32_t ptrow_a = smem_u32(sPT) + row * 128, dstrow_a = smem_u32(sdST) + row * 128, swz = row & 7;
+    uint32_t act_bits = 0u, allmk_bits = 0u;               // warp-uniform: tile j has a real key in this lane quarter / no masked key
+    for (int j = 0; j < NT; ++j) {
+      if (__any_sync(0xffffffffu, (kin_bits >> j) & 1u)) act_bits |= 1u << j;
+      if (__all_sync(0xffffffffu, (mk_bits >> j) & 1u)) allmk_bits |= 1u << j;
+    }
+    auto drain = [&](int i) {                             // dQ of query tile i: warp (qd, c16) owns rows qd*16 + lane, columns
+      mbar_wait_a(dq_ready_a, i & 1);                     // (c16 & 1) * 16 .. +16 of block c16 >> 1
+      tcgen05_fence_after();
+      const int bq = c16 >> 1, colh = (c16 & 1) * 16;
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tdQ + lane_addr + bq * DH + colh, r);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      mbar_arrive_a(dq_free_a);
+      if (bq < p.nblk) {
+        const int q = i * QN + qd * 16 + lane;            // M = 64 accumulator: row m lives in lane (m & 15) of lane quarter m >> 4
+        const bool ok = lane < 16 && q < p.Lq;
+        if (ok && p.dq[bq] != nullptr) {
+          uint4* dst = reinterpret_cast<uint4*>(p.dq[bq] + ((int64_t)b * p.Lq + q) * p.lddq[bq] + h * DH + colh);
+          uint32_t w[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) w[c] = pack_bf16x2(__uint_as_float(r[2 * c]), __uint_as_float(r[2 * c + 1]));
+          dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+          dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        if (p.dbq[bq] != nullptr) {                       // column sums over the tile's rows -> bias gradient of the query projection
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            float v = ok ? __uint_as_float(r[c]) : 0.f;
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) atomicAdd(&bars->colsum[bq][colh + c], v);
+          }
+        }
+      }
+    };
+    int t = 0;
+    for (int i = 0; i < T; ++i) {
+      const int st = i & 1;
+      mbar_wait_a(q_full_a + st * 8, (i >> 1) & 1);       // acquire the producer's per-query vectors
+      const uint32_t qva = qv_a + st * (uint32_t)sizeof(QVec64) + c16 * 16 * 4;    // this warp's 16 queries
+      const uint32_t wq = (lds_u1(qv_a + st * (uint32_t)sizeof(QVec64) + QV_MQ + (c16 >> 1) * 4) >> ((c16 & 1) * 16)) & 0xffffu;
+      float nl[16], nd[16];                                // per-query constants: in registers across the key tiles
+#pragma unroll
+      for (int c = 0; c < 16; c += 4) {
+        const float4 a = lds_f4(qva + c * 4), d4 = lds_f4(qva + QV_NDS + c * 4);
+        nl[c] = a.x; nl[c + 1] = a.y; nl[c + 2] = a.z; nl[c + 3] = a.w;
+        nd[c] = d4.x; nd[c + 1] = d4.y; nd[c + 2] = d4.z; nd[c + 3] = d4.w;
+      }
+      uint32_t rh = 0u;
+      if constexpr (DROP) rh = lds_u1(qva + QV_RH + (lane & 15) * 4);
+      uint32_t kq2 = 0u;                                   // DROP: keep bits of this thread's key for the 16 queries, tiles j (low half) and j + 1 (high half)
+      for (int j = 0; j < NT; ++j, ++t) {
+        const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
+        const bool act = (act_bits >> j) & 1u;
+        const bool mk = (mk_bits >> j) & 1u;
+        const bool fast = !DROP && ((allmk_bits >> j) & 1u) && wq == 0xffffu;
+        uint32_t kq = 0u;
+        if constexpr (DROP) {
+          if ((j & 1) == 0) {
+            // lanes 0-15 generate the keep words of (query lane, this warp's 32 keys of tile j), lanes 16-31 those of tile
+            // j + 1; one 32 x 32 bit transpose hands every thread (= key) its bits for both tiles
+            const int jj = min(j + (lane >> 4), NT - 1);
+            const int blk2 = jj < nt0 ? 0 : 1, kt2 = blk2 ? jj - nt0 : jj;
+            const uint32_t Wq = drop_keep_word(rh, attn_group(blk2, kt2 * 4 + qd), p.drop.thr8);
+            kq2 = warp_bit_transpose32(Wq, lane);
+          }
+          kq = (j & 1) ? (kq2 >> 16) : (kq2 & 0xffffu);
+        }
+        if (warp == 2) TRACE(t * 8 + 0);
+        mbar_wait_a(a_ready_a, t & 1);
+        tcgen05_fence_after();
+        if (warp == 2) TRACE(t * 8 + 1);
+        uint32_t rs[16], rp[16];
+        if (act) {
+          tmem_ld_32x32b_x16(tmem + lane_addr + c16 * 16, rs);
+          tmem_ld_32x32b_x16(tdPT + lane_addr + c16 * 16, rp);
+          tmem_ld_wait();
+        }
+        tcgen05_fence_before();
+        mbar_arrive_a(s_free_a);
+        if (warp == 2) TRACE(t * 8 + 2);
+        uint32_t pp[8], pd[8];
+        if (!act) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { pp[c] = 0u; pd[c] = 0u; }
+        } else if constexpr (DROP) {
+          const float ds_ = p.drop.scale;
+          const float2 sl2 = splat2(p.scale_log2 * ds_), sc2 = splat2(p.scale * ds_), dsc2 = splat2(ds_);
+          if (((allmk_bits >> j) & 1u) && wq == 0xffffu) {
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+              const bool k0_ = (kq >> c) & 1u, k1_ = (kq >> (c + 1)) & 1u;
+              const float s0 = k0_ ? __uint_as_float(rs[c]) : 0.f, s1 = k1_ ? __uint_as_float(rs[c + 1]) : 0.f;
+              const float2 pr = ex2_mufu2(fma2(make_float2(s0, s1), sl2, make_float2(nl[c], nl[c + 1])));
+              const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, mul2(make_float2(nd[c], nd[c + 1]), dsc2)));
+              pp[c >> 1] = pack_bf16x2(pr.x, pr.y);
+              pd[c >> 1] = pack_bf16x2(k0_ ? ds.x : 0.f, k1_ ? ds.y : 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; c += 2) {
+              const bool k0_ = (kq >> c) & 1u, k1_ = (kq >> (c + 1)) & 1u;
+              const bool v0 = mk && ((wq >> c) & 1u), v1 = mk && ((wq >> (c + 1)) & 1u);
+              const float s0 = k0_ ? (v0 ? __uint_as_float(rs[c]) : -10000.0f) : 0.f, s1 = k1_ ? (v1 ? __uint_as_float(rs[c + 1]) : -10000.0f) : 0.f;
+              const float2 pr = ex2_mufu2(fma2(make_float2(s0, s1), sl2, make_float2(nl[c], nl[c + 1])));
+              const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, mul2(make_float2(nd[c], nd[c + 1]), dsc2)));
+              pp[c >> 1] = pack_bf16x2(pr.x, pr.y);
+              pd[c >> 1] = pack_bf16x2((k0_ && v0) ? ds.x : 0.f, (k1_ && v1) ? ds.y : 0.f);
+            }
+          }
+        } else if (fast) {
+          const float2 sl2 = splat2(p.scale_log2), sc2 = splat2(p.scale);
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            const float2 x = fma2(make_float2(__uint_as_float(rs[c]), __uint_as_float(rs[c + 1])), sl2, make_float2(nl[c], nl[c + 1]));
+            const float2 pr = ex2_mufu2(x);
+            const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, make_float2(nd[c], nd[c + 1])));
+            pp[c >> 1] = pack_bf16x2(pr.x, pr.y);
+            pd[c >> 1] = pack_bf16x2(ds.x, ds.y);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 16; c += 2) {
+            float pr[2], ds[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int cc = c + u;
+              const bool valid = mk && (((wq >> cc) & 1u) != 0);
+              const float x = valid ? __uint_as_float(rs[cc]) * p.scale_log2 : p.fill_log2;
+              pr[u] = ex2(x + nl[cc]);                    // queries past Lq: nlse2 = -inf => 0
+              ds[u] = valid ? pr[u] * fmaf(__uint_as_float(rp[cc]), p.scale, nd[cc]) : 0.f;
+            }
+            pp[c >> 1] = pack_bf16x2(pr[0], pr[1]);
+            pd[c >> 1] = pack_bf16x2(ds[0], ds[1]);
+          }
+        }
+        if (warp == 2) TRACE(t * 8 + 3);
+        if (t >= 1) mbar_wait_a(p_free_a, (t - 1) & 1);    // the products of the previous tile have consumed the staging tiles
+        if (warp == 2) TRACE(t * 8 + 4);
+#pragma unroll
+        for (uint32_t v = 0; v < 2; ++v) {
+          const uint32_t off = ((c16 * 2 + v) ^ swz) << 4;
+          sts_u4(ptrow_a + off, pp[4 * v], pp[4 * v + 1], pp[4 * v + 2], pp[4 * v + 3]);
+          sts_u4(dstrow_a + off, pd[4 * v], pd[4 * v + 1], pd[4 * v + 2], pd[4 * v + 3]);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive_a(p_ready_a);
+        if (warp == 2) TRACE(t * 8 + 5);
+        if (j == 0 && i >= 1) drain(i - 1);               // the previous query tile's dQ: complete long ago, never waited for
+      }
+    }
+    if (warp == 2) TRACE(4093);
+    drain(T - 1);
+    // ---- epilogue: 2 NT accumulators (dK_j, dV_j) spread over the four warps of each lane quarter
+    mbar_wait(&bars->done, 0);
+    tcgen05_fence_after();
+    for (int a = c16; a < 2 * NT; a += 4) {
+      const int j = a >> 1, isv = a & 1;
+      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
+      const int Lk = blk ? p.Lk[1] : p.Lk[0];
+      const int kj = kt * QT + row;
+      const bool k_in = kj < Lk;
+      if (!((act_bits >> j) & 1u)) continue;
+      uint32_t rk[32];
+      tmem_ld_32x32(tdKV + lane_addr + j * 2 * DH + isv * DH, rk);
+      tmem_ld_wait();
+      __nv_bfloat16* dst = isv ? (blk ? dv1 : dv0) : (blk ? dk1 : dk0);
+      const int64_t ldd = isv ? (blk ? lddv1 : lddv0) : (blk ? lddk1 : lddk0);
+      float* db = isv ? (blk ? dbv1 : dbv0) : (blk ? dbk1 : dbk0);
+      if (k_in && dst != nullptr) store_row32_bf16(dst + ((int64_t)b * Lk + kj) * ldd + h * DH, rk, 1.0f);
+      if (db != nullptr) add_bias_grad(db + h * DH, rk, k_in, lane);
+    }
+  }
+  if (warp == 2) TRACE(4094);
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) TRACE(4092);
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(AK_TMEM_COLS) : "memory");
+  }
+  if (threadIdx.x < 2 * DH) {
+    const int bq = threadIdx.x >> 5, c = threadIdx.x & 31;
+    if (bq < p.nblk && p.dbq[bq] != nullptr) atomicAdd(p.dbq[bq] + h * DH + c, bars->colsum[bq][c]);
+  }
+}

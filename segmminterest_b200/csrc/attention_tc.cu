@@ -85,7 +85,7 @@ __device__ __forceinline__ uint32_t warp_bit_transpose32(uint32_t x, int lane) {
 #ifdef MMI_ATTN_TRACE
 // debug build only: clock64 stamps of one CTA (blockIdx.z == gridDim.z / 2, x == 0, y == 0), read back by mmi_debug_trace
 __device__ long long g_trace[8192];
-#define TRACE_ON (blockIdx.z == gridDim.z / 2 && blockIdx.x == 0 && blockIdx.y == 0)
+#define TRACE_ON (blockIdx.z == gridDim.z / 2 && blockIdx.x == 0 && blockIdx.y == (gridDim.z == 1 ? gridDim.y / 2 : 0))
 #define TRACE(slot) do { if (TRACE_ON && lane == 0) g_trace[(slot)] = clock64(); } while (0)
 #else
 #define TRACE(slot) do { } while (0)
@@ -1239,6 +1239,9 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   if (warp == 2) TRACE(4092);
 }
 
+#include "attention_bwd_fused.cuh"
+#include "attention_bwd_allkeys.cuh"
+
 // ====================================================================================== host
 static bool map_rows(const void* ptr, int64_t ld, int64_t rows, int width, uint32_t box_rows, CUtensorMap* m) {
   return get_tensor_map(ptr, (uint64_t)width, (uint64_t)rows, (uint64_t)ld, DH, box_rows, CU_TENSOR_MAP_SWIZZLE_64B, m);
@@ -1282,7 +1285,7 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     MMI_CHECK_ARG(s.ldq % 8 == 0 && s.ldk % 8 == 0 && s.ldv % 8 == 0, "attn_tc: leading dims must be multiples of 8 (TMA)");
     p.Lk[i] = s.Lk; p.mask_k[i] = s.mask_k;
     p.dq[i] = reinterpret_cast<__nv_bfloat16*>(s.dq); p.lddq[i] = s.lddq;
-    p.dbq[i] = kind == 1 ? s.dbq : nullptr;
+    p.dbq[i] = (kind == 1 || kind == 3 || kind == 4) ? s.dbq : nullptr;
   }
   if (a->nblk == 1) { p.Lk[1] = 0; p.mask_k[1] = p.mask_k[0]; }
   const int64_t q_rows = (int64_t)a->B * a->Lq;
@@ -1331,6 +1334,70 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
       if (drop_on) attn_bwd_dq_tc_kernel<true><<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p);
       else attn_bwd_dq_tc_kernel<false><<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p);
     }
+  } else if (kind == 4) {
+    // one CTA per (b, h) owning every key of both blocks (attention_bwd_allkeys.cuh)
+    MMI_CHECK_ARG(a->dout && a->out && a->lse, "attn_tc all-keys bwd: null dout / out / lse");
+    MMI_CHECK_ARG(a->ldo % 8 == 0 && a->lddo % 8 == 0, "attn_tc all-keys bwd: ldo / lddo must be multiples of 8");
+    int nt = 0;
+    for (int i = 0; i < a->nblk; ++i) {
+      nt += (a->blk[i].Lk + QT - 1) / QT;
+      MMI_CHECK_ARG(a->blk[i].lddq % 8 == 0, "attn_tc all-keys bwd: lddq must be a multiple of 8");
+    }
+    if (nt > AK_MAXT) return 1;                 // more keys than one CTA's TMEM holds (5 x 128): the caller uses the other kernels
+    CUtensorMap mQ[2], mK[2], mV[2], mdO;
+    for (int i = 0; i < 2; ++i) {
+      const mmi_attn_block& s = a->blk[i < a->nblk ? i : 0];
+      const int64_t k_rows = (int64_t)a->B * s.Lk;
+      if (!map_rows(s.q, s.ldq, q_rows, width, QN, &mQ[i])) return MMI_ECUDA;
+      if (!map_rows(s.k, s.ldk, k_rows, width, QT, &mK[i])) return MMI_ECUDA;
+      if (!map_rows(s.v, s.ldv, k_rows, width, QT, &mV[i])) return MMI_ECUDA;
+    }
+    if (!map_rows(a->dout, a->lddo, q_rows, width, QN, &mdO)) return MMI_ECUDA;
+    const mmi_attn_block& s0 = a->blk[0];
+    const mmi_attn_block& s1 = a->blk[a->nblk > 1 ? 1 : 0];
+    dim3 grid(a->H, a->B);
+    const size_t smem = AK_MAXT * 2 * TILE128 + 2 * AK_QSTAGE + 2 * STILE + 2 * sizeof(QVec64) + sizeof(AKBars) + 1024;
+    static bool configured = false;
+    if (!configured) {
+      int rc = set_smem(attn_bwd_allkeys_tc_kernel<false>, smem); if (rc) return rc;
+      rc = set_smem(attn_bwd_allkeys_tc_kernel<true>, smem); if (rc) return rc;
+      configured = true;
+    }
+    auto bf = [](void* x) { return reinterpret_cast<__nv_bfloat16*>(x); };
+    if (drop_on)
+      attn_bwd_allkeys_tc_kernel<true><<<grid, AK_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p, bf(s0.dk), bf(s1.dk), bf(s0.dv),
+                                                                        bf(s1.dv), s0.lddk, s1.lddk, s0.lddv, s1.lddv, s0.dbk, s1.dbk, s0.dbv, s1.dbv);
+    else
+      attn_bwd_allkeys_tc_kernel<false><<<grid, AK_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p, bf(s0.dk), bf(s1.dk), bf(s0.dv),
+                                                                         bf(s1.dv), s0.lddk, s1.lddk, s0.lddv, s1.lddv, s0.dbk, s1.dbk, s0.dbv, s1.dbv);
+  } else if (kind == 3) {
+    MMI_CHECK_ARG(which >= 0 && which < a->nblk, "attn_tc fused bwd: bad block index %d", which);
+    MMI_CHECK_ARG(a->dout && a->out && a->lse, "attn_tc fused bwd: null dout / out / lse");
+    if (a->dq_acc[which] == nullptr || a->dq_count[which] == nullptr) return 1;     // caller did not provide the dQ accumulator
+    MMI_CHECK_ARG((reinterpret_cast<uintptr_t>(a->dq_acc[which]) & 15) == 0, "attn_tc fused bwd: dq_acc must be 16-byte aligned");
+    MMI_CHECK_ARG(a->ldo % 8 == 0 && a->lddo % 8 == 0, "attn_tc fused bwd: ldo / lddo must be multiples of 8");
+    const mmi_attn_block& s = a->blk[which];
+    MMI_CHECK_ARG(s.lddq % 4 == 0, "attn_tc fused bwd: lddq must be a multiple of 4");
+    p.which = which;
+    p.dk = reinterpret_cast<__nv_bfloat16*>(s.dk); p.lddk = s.lddk;
+    p.dv = reinterpret_cast<__nv_bfloat16*>(s.dv); p.lddv = s.lddv;
+    p.dbk = s.dbk; p.dbv = s.dbv;
+    const int64_t k_rows = (int64_t)a->B * s.Lk;
+    CUtensorMap mQ, mK, mV, mdO;
+    if (!map_rows(s.q, s.ldq, q_rows, width, QN, &mQ)) return MMI_ECUDA;
+    if (!map_rows(a->dout, a->lddo, q_rows, width, QN, &mdO)) return MMI_ECUDA;
+    if (!map_rows(s.k, s.ldk, k_rows, width, QT, &mK)) return MMI_ECUDA;
+    if (!map_rows(s.v, s.ldv, k_rows, width, QT, &mV)) return MMI_ECUDA;
+    dim3 grid((s.Lk + QT - 1) / QT, a->H, a->B);
+    const size_t smem = 2 * TILE128 + FB_STAGES * 2 * TILE64Q + 2 * STILE + FB_STAGES * sizeof(QVec64) + sizeof(FBars) + 1024;
+    static bool configured = false;
+    if (!configured) {
+      int rc = set_smem(attn_bwd_fused_tc_kernel<false>, smem); if (rc) return rc;
+      rc = set_smem(attn_bwd_fused_tc_kernel<true>, smem); if (rc) return rc;
+      configured = true;
+    }
+    if (drop_on) attn_bwd_fused_tc_kernel<true><<<grid, FB_THREADS, smem, st>>>(mQ, mK, mV, mdO, p, a->dq_acc[which], a->dq_count[which]);
+    else attn_bwd_fused_tc_kernel<false><<<grid, FB_THREADS, smem, st>>>(mQ, mK, mV, mdO, p, a->dq_acc[which], a->dq_count[which]);
   } else {
     MMI_CHECK_ARG(which >= 0 && which < a->nblk, "attn_tc dkv: bad block index %d", which);
     MMI_CHECK_ARG(a->dout && a->delta, "attn_tc bwd: null dout/delta");

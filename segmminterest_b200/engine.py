@@ -14,6 +14,7 @@ Data layout in HBM:
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -128,6 +129,12 @@ class Engine:
         self._ws = {}
         self._saved = None
         self.use_tc = cfg.precision == "bf16" and bool(_lib.load().mmi_has_tc())
+        # attention backward on the tensor-core path: "all" = one CTA per (b, h) owning every key (default, <= 640 keys),
+        # "fused" = one kernel per key block with dQ reduced through an fp32 accumulator (measured slower than the pair it
+        # replaces, kept for A/B runs), anything else = the dq + dk/dv kernel pair (also the fallback for long histories)
+        mode = os.environ.get("MMI_ATTN_BWD", "all")
+        self.allkeys_attn_bwd = mode == "all"
+        self.fused_attn_bwd = mode == "fused"
         n_red = max(_lib.load().mmi_layernorm_bwd_workspace(cfg.d_model), _lib.load().mmi_head_bwd_workspace(cfg.d_model),
                     4 * cfg.d_model * max(cfg.max_usr_len, cfg.max_vid_len), 1 << 20)
         self.red_ws = torch.empty(int(n_red), device=device, dtype=torch.float32)
@@ -302,6 +309,15 @@ class Engine:
         t = self._ws.get(key)
         if t is None:
             t = torch.empty(shape, device=self.device, dtype=dtype)
+            self._ws[key] = t
+        return t
+
+    def _zbuf(self, name, shape, dtype):
+        """workspace tensor that is zero when first handed out (its users leave it zero)"""
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
+            t = torch.zeros(shape, device=self.device, dtype=dtype)
             self._ws[key] = t
         return t
 
@@ -720,6 +736,18 @@ class Engine:
                 delta = self._buf(f"delta.{tw.tag}.{s}", (B, H, Ls[s]), torch.float32)
                 names = ATTN_BLOCKS[cfg.ablation][s]
                 side.set_bwd(dA[s], d, delta, [gset(n) for n in names])
+                if side.a.impl == IMPL_TC and self.allkeys_attn_bwd and side.bwd_all():
+                    continue     # one launch: dq, dk, dv of both key blocks (<= 640 keys per (b, h))
+                if side.a.impl == IMPL_TC and self.fused_attn_bwd:
+                    # one kernel per key block: dK, dV and that block's dQ (partial tiles reduced through an fp32 accumulator
+                    # that the kernel leaves zeroed, so one pair of buffers serves every layer of the tower)
+                    acc = [self._zbuf(f"dqacc.{tw.tag}.{s}.{w_}", (Ts[s], d), torch.float32) for w_ in range(len(names))]
+                    cnt = [self._zbuf(f"dqcnt.{tw.tag}.{s}.{w_}", (B * H,), torch.int32) for w_ in range(len(names))]
+                    side.set_fused(acc, cnt)
+                    done = [side.bwd_fused(w_) for w_ in range(len(names))]
+                    assert all(done) or not any(done)
+                    if all(done):
+                        continue
                 side.bwd_dq()
                 for w_ in range(len(names)):
                     side.bwd_dkv(w_)

@@ -190,6 +190,35 @@ class AttnSide:
             k.dv, k.lddv = g["dv"]
             k.dbq, k.dbk, k.dbv = g.get("dbq"), g.get("dbk"), g.get("dbv")   # fused bias-gradient sums (TC path), None = off
 
+    def set_fused(self, dq_acc, dq_count):
+        """Workspace of mmi_attn_bwd_fused: per key block an fp32 [B*Lq, H*dh] accumulator and B*H int32 counters, all zero
+        on entry (the kernel leaves them zero)."""
+        for i in range(self.a.nblk):
+            self.a.dq_acc[i] = dq_acc[i].data_ptr()
+            self.a.dq_count[i] = dq_count[i].data_ptr()
+
+    def bwd_fused(self, which) -> bool:
+        """dq, dk, dv (+ bias-gradient sums) of key block `which` in one kernel; False when the library asks for the
+        two-kernel path (rc 1)."""
+        with TIMER.region(self._cat("attn_bwd_fused", which), 2.5 * self.flops(which)):
+            rc = _lib.load().mmi_attn_bwd_fused(C.byref(self.a), which, _stream())
+        if rc == 1:
+            return False
+        _lib.check(rc, "mmi_attn_bwd_fused")
+        LaunchCounter.n += 1
+        return True
+
+    def bwd_all(self) -> bool:
+        """dq, dk, dv of BOTH key blocks (+ bias-gradient sums) in one launch, one CTA per (b, h); False when the shapes are
+        not covered (more than 5 key tiles) and the caller has to use the other kernels."""
+        with TIMER.region(self._cat("attn_bwd_all"), 2.5 * self.flops()):
+            rc = _lib.load().mmi_attn_bwd_all(C.byref(self.a), _stream())
+        if rc == 1:
+            return False
+        _lib.check(rc, "mmi_attn_bwd_all")
+        LaunchCounter.n += 1
+        return True
+
     def bwd_dq(self):
         with TIMER.region(self._cat("attn_bwd_dq"), 1.5 * self.flops()):
             rc = _lib.load().mmi_attn_bwd_dq(C.byref(self.a), _stream())

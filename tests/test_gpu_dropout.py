@@ -190,6 +190,21 @@ def test_attention_logits_dropout(dev, dh, dtype, impl, shape, ragged):
     side.bwd_dkv(1)
     for g, r, name in zip(grads, ref_in, ["dqa", "dka", "dva", "dqb", "dkb", "dvb"]):
         assert _rel(g.double().cpu(), r.grad) < (5e-5 if dtype == torch.float32 else 1.5e-2), name
+    if impl == "tc":                     # the one-kernel backward regenerates the same masks (thread = key, 64-query tiles)
+        for g in grads:
+            g.zero_()
+        acc = [torch.zeros(B * Lq, d, device=dev) for _ in range(2)]
+        cnt = [torch.zeros(B * H, device=dev, dtype=torch.int32) for _ in range(2)]
+        side.set_fused(acc, cnt)
+        assert side.bwd_fused(0) and side.bwd_fused(1)
+        for g, r, name in zip(grads, ref_in, ["dqa", "dka", "dva", "dqb", "dkb", "dvb"]):
+            assert _rel(g.double().cpu(), r.grad) < 1.5e-2, ("fused", name)
+        assert all(float(a_.abs().max()) == 0.0 for a_ in acc) and all(int(c_.abs().max()) == 0 for c_ in cnt)
+        for g in grads:
+            g.zero_()
+        if side.bwd_all():               # one CTA per (b, h): keep words of two key tiles per bit transpose
+            for g, r, name in zip(grads, ref_in, ["dqa", "dka", "dva", "dqb", "dkb", "dvb"]):
+                assert _rel(g.double().cpu(), r.grad) < 1.5e-2, ("all-keys", name)
 
 
 # ----------------------------------------------------------------------------- the whole model in train() mode

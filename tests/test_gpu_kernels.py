@@ -255,18 +255,45 @@ def _check_attention(dev, dh, dtype, impl, shape, ragged, key_ramp=0.0):
                                      dbq=ptr[0], dbk=ptr[1], dbv=ptr[2]),
                                 dict(dq=(grads[3].data_ptr(), d), dk=(grads[4].data_ptr(), d), dv=(grads[5].data_ptr(), d),
                                      dbq=ptr[3], dbk=ptr[4], dbv=ptr[5])])
+    def check(tag):
+        for g, r, name in zip(grads, ref_in, ["dqa", "dka", "dva", "dqb", "dkb", "dvb"]):
+            assert _rel(g, r.grad) < (5e-5 if dtype == torch.float32 else 1.5e-2), (tag, name)
+        if fused:                        # += semantics (buffers started at 0.25), fp32 sums taken before the bf16 rounding
+            for x, r, name in zip(db, ref_in, ["dbqa", "dbka", "dbva", "dbqb", "dbkb", "dbvb"]):
+                want = r.grad.sum((0, 1))
+                # a column sum cancels heavily, so the bar is relative to the gradient it sums (random element errors of
+                # relative size e give ||sum error|| ~ e * ||grad||_F), the same 1.5e-2 the gradients themselves are held to
+                err = float((x.double().cpu() - 0.25 - want).norm())
+                assert err < 1.5e-2 * float(r.grad.norm()) + 1e-20, (tag, name, err, float(r.grad.norm()), float(want.norm()))
+
     side.bwd_dq()
     side.bwd_dkv(0)
     side.bwd_dkv(1)
-    for g, r, name in zip(grads, ref_in, ["dqa", "dka", "dva", "dqb", "dkb", "dvb"]):
-        assert _rel(g, r.grad) < (5e-5 if dtype == torch.float32 else 1.5e-2), name
-    if fused:                            # += semantics (buffers started at 0.25), fp32 sums taken before the bf16 rounding
-        for x, r, name in zip(db, ref_in, ["dbqa", "dbka", "dbva", "dbqb", "dbkb", "dbvb"]):
-            want = r.grad.sum((0, 1))
-            # a column sum cancels heavily, so the bar is relative to the gradient it sums (random element errors of
-            # relative size e give ||sum error|| ~ e * ||grad||_F), the same 1.5e-2 the gradients themselves are held to
-            err = float((x.double().cpu() - 0.25 - want).norm())
-            assert err < 1.5e-2 * float(r.grad.norm()) + 1e-20, (name, err, float(r.grad.norm()), float(want.norm()))
+    check("dq + dkv kernels")
+    if fused and dh == 32:
+        # the one-kernel backward (dK, dV and dQ per key block; dQ through the fp32 accumulator): same bars, and the
+        # accumulator / counters are left zero
+        for g in grads:
+            g.zero_()
+        for x in db:
+            x.fill_(0.25)
+        acc = [torch.zeros(B * Lq, d, device=dev) for _ in range(2)]
+        cnt = [torch.zeros(B * H, device=dev, dtype=torch.int32) for _ in range(2)]
+        side.set_fused(acc, cnt)
+        delta.fill_(float("nan"))        # not read by the fused kernel
+        assert side.bwd_fused(0) and side.bwd_fused(1)
+        check("fused kernel")
+        for a_, c_ in zip(acc, cnt):
+            assert float(a_.abs().max()) == 0.0 and int(c_.abs().max()) == 0
+        # the one-launch backward (one CTA per (b, h) owns every key of both blocks): same bars again
+        for g in grads:
+            g.zero_()
+        for x in db:
+            x.fill_(0.25)
+        covered = side.bwd_all()
+        assert covered == ((La + 127) // 128 + (Lb + 127) // 128 <= 5)
+        if covered:
+            check("all-keys kernel")
 
 
 # ----------------------------------------------------------------------------- loss

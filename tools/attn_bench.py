@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--heads", type=int, default=16)
     ap.add_argument("--sides", default="usr,vid")
+    ap.add_argument("--fused", action="store_true", help="also time the per-key-block fused kernel")
+    ap.add_argument("--no-two", action="store_true", help="skip the dq + dk/dv kernel pair")
     ap.add_argument("--valid-cand", type=int, default=-1, help="valid candidate segments (default: workload's S)")
     a = ap.parse_args()
     wl = synth.WORKLOADS[a.workload]
@@ -58,11 +60,15 @@ def main():
         grads = [dict(dq=col(dqkv, *q), dk=col(dqkv, *k), dv=col(dqkv, *v)) for q, k, v in idx]
         side = ops.AttnSide(ops.BF16, ops.IMPL_TC, B, H, dh, Lq, mask[s], out, d, lse, blocks)
         side.set_bwd(dout, d, delta, grads)
+        acc = [torch.zeros(B * Lq, d, device=dev) for _ in range(2)]
+        cnt = [torch.zeros(B * H, device=dev, dtype=torch.int32) for _ in range(2)]
+        side.set_fused(acc, cnt)
         calls = [("fwd", side.fwd, 1.0, None)]
-        if hasattr(side, "bwd"):
-            calls.append(("bwd", side.bwd, 2.5, None))
-        else:
+        if not a.no_two:
             calls += [("bwd_dq", side.bwd_dq, 1.5, None), ("bwd_dkv0", lambda: side.bwd_dkv(0), 2.0, 0), ("bwd_dkv1", lambda: side.bwd_dkv(1), 2.0, 1)]
+        if a.fused:
+            calls += [("bwd_fused0", lambda: side.bwd_fused(0), 2.5, 0), ("bwd_fused1", lambda: side.bwd_fused(1), 2.5, 1)]
+        calls += [("bwd_all", side.bwd_all, 2.5, None)]
         for name, fn, mult, which in calls:
             fn()
             torch.cuda.synchronize()

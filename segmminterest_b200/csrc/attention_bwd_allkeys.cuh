@@ -20,9 +20,12 @@ constexpr uint32_t AK_TMEM_COLS = 512;
 constexpr uint32_t AK_QSTAGE = 3 * TILE64Q;      // Qa | Qb | dO
 
 struct AKBars {
-  uint64_t once, q_full[2], q_empty[2], a_ready, s_free, p_ready, p_free, dq_ready, dq_free, done;
+  // p_ready[tile parity]: a warp whose lane quarter holds no key of tile t (nothing to compute) can finish tile t + 1 before
+  // a slow warp has finished tile t; with ONE barrier its early arrival would complete tile t's phase (seen as garbage in
+  // dK / dV of a partially filled key tile).  The issuer waits for p_ready of tile t before it can release S^T of tile
+  // t + 2, so two alternating barriers are enough.
+  uint64_t once, q_full[2], q_empty[2], a_ready, s_free, p_ready[2], p_free, dq_ready, dq_free, done;
   uint32_t tmem_slot, pad;
-  float colsum[2][DH];
 };
 
 template <bool DROP>
@@ -82,7 +85,8 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
       for (int s = 0; s < 2; ++s) { mbar_init(&bars->q_full[s], 1); mbar_init(&bars->q_empty[s], 1); }
       mbar_init(&bars->a_ready, 1);
       mbar_init(&bars->s_free, 512);
-      mbar_init(&bars->p_ready, 512);
+      mbar_init(&bars->p_ready[0], 512);
+      mbar_init(&bars->p_ready[1], 512);
       mbar_init(&bars->p_free, 1);
       mbar_init(&bars->dq_ready, 1);
       mbar_init(&bars->dq_free, 512);
@@ -99,7 +103,6 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
     __syncwarp();
     fetch(0);
   }
-  if (threadIdx.x < 2 * DH) (&bars->colsum[0][0])[threadIdx.x] = 0.f;
   // ---- softmax threads: which of their key rows (one per key tile) exist / are unmasked
   uint32_t kin_bits = 0u, mk_bits = 0u;
   if (warp >= 2) {
@@ -156,22 +159,25 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
     const uint32_t tS = uniform(tmem), tdPTu = uniform(tdPT), tdQu = uniform(tdQ), tdKVu = uniform(tdKV);
     mbar_wait(&bars->once, 0);
     const uint32_t aKV = smem_u32(sKV), aQs = smem_u32(sQ), aPT = smem_u32(sPT), adST = smem_u32(sdST);
-    auto issue_back = [&](int u) {
-      const int iu = u / NT, ju = u - iu * NT, su = iu & 1;
+    // (the issuer's operands must live in UNIFORM registers: anything data-dependent is routed through uniform(), and the
+    // tile index is never divided -- a waterfall loop around every UTCHMMA costs ~80 cycles per MMA)
+    auto issue_back = [&](int u, int iu, int ju) {
+      const int su = iu & 1;
       const int blk = ju < nt0 ? 0 : 1, kt = blk ? ju - nt0 : ju;
-      mbar_wait_bg(&bars->p_ready, u & 1);
+      mbar_wait_bg(&bars->p_ready[u & 1], (u >> 1) & 1);
       if (ju == 0 && iu >= 1) mbar_wait_bg(&bars->dq_free, (iu - 1) & 1);      // last query tile's dQ has left the accumulators
       tcgen05_fence_after();
+      const uint32_t aQ = uniform(aQs + su * AK_QSTAGE + blk * TILE64Q), adO = uniform(aQs + su * AK_QSTAGE + 2 * TILE64Q);
+      const uint32_t aK = uniform(aKV + ju * 2 * TILE128);
+      const uint32_t tdK = uniform(tdKVu + ju * 2 * DH), tdV = tdK + DH, tdQb = uniform(tdQu + blk * DH);
+      const uint32_t acc0 = uniform(iu > 0 ? 1u : 0u), accq = uniform(kt > 0 ? 1u : 0u);
       if (elect_one()) {
-        const uint32_t aQ = aQs + su * AK_QSTAGE + blk * TILE64Q, adO = aQs + su * AK_QSTAGE + 2 * TILE64Q;
-        const uint32_t aK = aKV + ju * 2 * TILE128;
-        const uint32_t tdK = tdKVu + ju * 2 * DH, tdV = tdK + DH;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tdV, desc_k128(aPT, k), desc_mn64(adO, k), IDESC_O, (iu > 0 || k > 0) ? 1u : 0u);    // dV_j += P^T dO
+        for (int k = 0; k < 4; ++k) umma_f16(tdV, desc_k128(aPT, k), desc_mn64(adO, k), IDESC_O, k > 0 ? 1u : acc0);    // dV_j += P^T dO
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tdK, desc_k128(adST, k), desc_mn64(aQ, k), IDESC_O, (iu > 0 || k > 0) ? 1u : 0u);    // dK_j += dS^T Q
+        for (int k = 0; k < 4; ++k) umma_f16(tdK, desc_k128(adST, k), desc_mn64(aQ, k), IDESC_O, k > 0 ? 1u : acc0);    // dK_j += dS^T Q
 #pragma unroll
-        for (int k = 0; k < 8; ++k) umma_f16(tdQu + blk * DH, desc_mn128(adST, k), desc_mn64(aK, k), IDESC_DQ, (kt > 0 || k > 0) ? 1u : 0u);   // dQ_blk += dS K_j
+        for (int k = 0; k < 8; ++k) umma_f16(tdQb, desc_mn128(adST, k), desc_mn64(aK, k), IDESC_DQ, k > 0 ? 1u : accq);  // dQ_blk += dS K_j
         umma_commit(&bars->p_free);
         if (ju == NT - 1) {
           umma_commit(&bars->q_empty[su]);
@@ -180,7 +186,7 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
       }
       __syncwarp();
     };
-    int t = 0;
+    int t = 0, pi = 0, pj = 0;                            // (pi, pj) = the (i, j) of tile t - 1
     for (int i = 0; i < T; ++i) {
       const int st = i & 1;
       mbar_wait_bg(&bars->q_full[st], (i >> 1) & 1);
@@ -188,9 +194,9 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
         const int blk = j < nt0 ? 0 : 1;
         if (t >= 1) mbar_wait_bg(&bars->s_free, (t - 1) & 1);
         tcgen05_fence_after();
+        const uint32_t aQ = uniform(aQs + st * AK_QSTAGE + blk * TILE64Q), adO = uniform(aQs + st * AK_QSTAGE + 2 * TILE64Q);
+        const uint32_t aK = uniform(aKV + j * 2 * TILE128), aV = aK + TILE128;
         if (elect_one()) {
-          const uint32_t aQ = aQs + st * AK_QSTAGE + blk * TILE64Q, adO = aQs + st * AK_QSTAGE + 2 * TILE64Q;
-          const uint32_t aK = aKV + j * 2 * TILE128, aV = aK + TILE128;
 #pragma unroll
           for (int k = 0; k < 2; ++k) umma_f16(tS, desc_k64(aK, k), desc_k64(aQ, k), IDESC_S64T, k);        // S^T  = K_j Q^T
 #pragma unroll
@@ -199,18 +205,19 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
         }
         __syncwarp();
         TRACE(t * 8 + 6);
-        if (t >= 1) issue_back(t - 1);
+        if (t >= 1) issue_back(t - 1, pi, pj);
         TRACE(t * 8 + 7);
+        pi = i; pj = j;
       }
     }
-    issue_back(total - 1);
+    issue_back(total - 1, pi, pj);
     if (elect_one()) umma_commit(&bars->done);
     __syncwarp();
   } else {
     // ================================================================= softmax + dQ drain + epilogue (16 warps)
     const int qd = warp & 3, c16 = (warp - 2) >> 2, row = qd * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(qd * 32) << 16;
-    const uint32_t a_ready_a = smem_u32(&bars->a_ready), s_free_a = smem_u32(&bars->s_free), p_ready_a = smem_u32(&bars->p_ready);
+    const uint32_t a_ready_a = smem_u32(&bars->a_ready), s_free_a = smem_u32(&bars->s_free), p_ready_a = smem_u32(&bars->p_ready[0]);
     const uint32_t p_free_a = smem_u32(&bars->p_free), q_full_a = smem_u32(&bars->q_full[0]), qv_a = smem_u32(qv);
     const uint32_t dq_ready_a = smem_u32(&bars->dq_ready), dq_free_a = smem_u32(&bars->dq_free);
     const uint32_t ptrow_a = smem_u32(sPT) + row * 128, dstrow_a = smem_u32(sdST) + row * 128, swz = row & 7;
@@ -219,6 +226,7 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
       if (__any_sync(0xffffffffu, (kin_bits >> j) & 1u)) act_bits |= 1u << j;
       if (__all_sync(0xffffffffu, (mk_bits >> j) & 1u)) allmk_bits |= 1u << j;
     }
+    float dbq_run = 0.f;                                  // lane l < 16: running column sum of dQ column (c16 & 1) * 16 + l, block c16 >> 1
     auto drain = [&](int i) {                             // dQ of query tile i: warp (qd, c16) owns rows qd*16 + lane, columns
       mbar_wait_a(dq_ready_a, i & 1);                     // (c16 & 1) * 16 .. +16 of block c16 >> 1
       tcgen05_fence_after();
@@ -239,14 +247,24 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
           dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
           dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
         }
-        if (p.dbq[bq] != nullptr) {                       // column sums over the tile's rows -> bias gradient of the query projection
+        if (p.dbq[bq] != nullptr) {
+          // column sums over the tile's rows -> bias gradient of the query projection: a transposing butterfly over the 16
+          // row-holding lanes (15 shuffles) leaves column l's sum on lane l, which keeps ONE running register across the
+          // query tiles (shared-memory float atomics from 16 warps in lockstep cost ~6 000 cycles per query tile here)
+          float v[16];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            float v = ok ? __uint_as_float(r[c]) : 0.f;
+          for (int c = 0; c < 16; ++c) v[c] = ok ? __uint_as_float(r[c]) : 0.f;
 #pragma unroll
-            for (int o = 8; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) atomicAdd(&bars->colsum[bq][colh + c], v);
+          for (int o = 8; o >= 1; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int c = 0; c < o; ++c) {
+              const float send = up ? v[c] : v[c + o];
+              const float keep = up ? v[c + o] : v[c];
+              v[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
           }
+          dbq_run += v[0];
         }
       }
     };
@@ -267,7 +285,6 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
       if constexpr (DROP) rh = lds_u1(qva + QV_RH + (lane & 15) * 4);
       uint32_t kq2 = 0u;                                   // DROP: keep bits of this thread's key for the 16 queries, tiles j (low half) and j + 1 (high half)
       for (int j = 0; j < NT; ++j, ++t) {
-        const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
         const bool act = (act_bits >> j) & 1u;
         const bool mk = (mk_bits >> j) & 1u;
         const bool fast = !DROP && ((allmk_bits >> j) & 1u) && wq == 0xffffu;
@@ -361,13 +378,15 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
           sts_u4(dstrow_a + off, pd[4 * v], pd[4 * v + 1], pd[4 * v + 2], pd[4 * v + 3]);
         }
         fence_proxy_async_smem();
-        mbar_arrive_a(p_ready_a);
+        mbar_arrive_a(p_ready_a + (t & 1) * 8);
         if (warp == 2) TRACE(t * 8 + 5);
         if (j == 0 && i >= 1) drain(i - 1);               // the previous query tile's dQ: complete long ago, never waited for
       }
     }
     if (warp == 2) TRACE(4093);
     drain(T - 1);
+    if ((c16 >> 1) < p.nblk && p.dbq[c16 >> 1] != nullptr && lane < 16)
+      atomicAdd(p.dbq[c16 >> 1] + h * DH + (c16 & 1) * 16 + lane, dbq_run);
     // ---- epilogue: 2 NT accumulators (dK_j, dV_j) spread over the four warps of each lane quarter
     mbar_wait(&bars->done, 0);
     tcgen05_fence_after();
@@ -395,9 +414,5 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(AK_TMEM_COLS) : "memory");
-  }
-  if (threadIdx.x < 2 * DH) {
-    const int bq = threadIdx.x >> 5, c = threadIdx.x & 31;
-    if (bq < p.nblk && p.dbq[bq] != nullptr) atomicAdd(p.dbq[bq] + h * DH + c, bars->colsum[bq][c]);
   }
 }

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--heads", type=int, default=16)
     ap.add_argument("--sides", default="usr,vid")
+    ap.add_argument("--dropout", action="store_true", help="logits dropout 0.1 live (the train()-mode kernels)")
+    ap.add_argument("--bias", action="store_true", help="with the fused bias-gradient sums")
     ap.add_argument("--fused", action="store_true", help="also time the per-key-block fused kernel")
     ap.add_argument("--no-two", action="store_true", help="skip the dq + dk/dv kernel pair")
     ap.add_argument("--valid-cand", type=int, default=-1, help="valid candidate segments (default: workload's S)")
@@ -58,7 +60,15 @@ def main():
             idx = [(("usr", 2), ("vid", 4), ("vid", 5)), (("usr", 3), ("usr", 4), ("usr", 5))]
         blocks = [dict(q=col(qkv, *q), k=col(qkv, *k), v=col(qkv, *v), mask_k=mask[k[0]], Lk=L[k[0]]) for q, k, v in idx]
         grads = [dict(dq=col(dqkv, *q), dk=col(dqkv, *k), dv=col(dqkv, *v)) for q, k, v in idx]
-        side = ops.AttnSide(ops.BF16, ops.IMPL_TC, B, H, dh, Lq, mask[s], out, d, lse, blocks)
+        if a.bias:                       # fused bias-gradient column sums, as the engine asks for them
+            dbs = [torch.zeros(d, device=dev) for _ in range(6)]
+            for i_, g_ in enumerate(grads):
+                g_.update(dbq=dbs[3 * i_].data_ptr(), dbk=dbs[3 * i_ + 1].data_ptr(), dbv=dbs[3 * i_ + 2].data_ptr())
+        site = None
+        if a.dropout:
+            from segmminterest_b200.dropout import DropSite, quantise
+            site = DropSite(0x1234ABCD, *quantise(0.1))
+        side = ops.AttnSide(ops.BF16, ops.IMPL_TC, B, H, dh, Lq, mask[s], out, d, lse, blocks, drop=site)
         side.set_bwd(dout, d, delta, grads)
         acc = [torch.zeros(B * Lq, d, device=dev) for _ in range(2)]
         cnt = [torch.zeros(B * H, device=dev, dtype=torch.int32) for _ in range(2)]

@@ -101,26 +101,6 @@ __device__ __forceinline__ float ex2(float x) {
 // score the softmax loops are MUFU-bound while the warps compute, so a fixed share of the scores of every tile takes
 // its exponential on the FMA / ALU pipes instead: round-to-nearest split x = n + f (magic-number add), 2^f by a
 // degree-3 minimax polynomial on [-1/2, 1/2] (relative error 7.5e-5, bf16 keeps 3.9e-3), 2^n added into the exponent.
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-  return d;
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-  float2 d;
-  asm("{.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;}"
-      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-  return d;
-}
-__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 __device__ __forceinline__ float2 ex2_mufu2(float2 x) { return make_float2(ex2(x.x), ex2(x.y)); }
 __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   constexpr float kMagic = 12582912.0f;                        // 1.5 * 2^23: x + kMagic holds round(x) in its low mantissa bits

@@ -291,29 +291,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               const float a0 = __uint_as_float(aw[j] << 16), a1 = __uint_as_float(aw[j] & 0xffff0000u);
               if (aux_add) { x[2 * j] += a0; x[2 * j + 1] += a1; }
               else if (p.mul_is_grad) { x[2 * j] *= a0; x[2 * j + 1] *= a1; }
-              else { x[2 * j] *= gelu_grad_fast(a0); x[2 * j + 1] *= gelu_grad_fast(a1); }
+              else { float2 gg, dg; gelu_pair<false, true>(make_float2(a0, a1), gg, dg); x[2 * j] *= dg.x; x[2 * j + 1] *= dg.y; }
             }
           }
           if (second) {
             float z[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float cdf, e;
-              z[j] = x[j];
+            for (int j = 0; j < 8; j += 2) {
+              z[j] = x[j]; z[j + 1] = x[j + 1];
               if (do_gelu || p.save_act_grad) {
-                gelu_parts(x[j], cdf, e);
-                if (p.save_act_grad) z[j] = fmaf(x[j] * 0.39894228040143267794f, e, cdf);
-                if (do_gelu) x[j] *= cdf;
+                float2 gg, dg;
+                gelu_pair<true, true>(make_float2(x[j], x[j + 1]), gg, dg);
+                if (p.save_act_grad) { z[j] = dg.x; z[j + 1] = dg.y; }
+                if (do_gelu) { x[j] = gg.x; x[j + 1] = gg.y; }
               }
               if (drop_on && do_gelu) {                  // dropout(gelu(z)); the saved gelu'(z) carries the same factor
-                x[j] = ((kb8 >> j) & 1u) ? x[j] * p.drop.scale : 0.f;
-                if (p.save_act_grad) z[j] = ((kb8 >> j) & 1u) ? z[j] * p.drop.scale : 0.f;
+                const float2 ds2 = splat2(p.drop.scale);
+                const float2 xs = mul2(make_float2(x[j], x[j + 1]), ds2);
+                x[j] = ((kb8 >> j) & 1u) ? xs.x : 0.f;
+                x[j + 1] = ((kb8 >> (j + 1)) & 1u) ? xs.y : 0.f;
+                if (p.save_act_grad) {
+                  const float2 zs = mul2(make_float2(z[j], z[j + 1]), ds2);
+                  z[j] = ((kb8 >> j) & 1u) ? zs.x : 0.f;
+                  z[j + 1] = ((kb8 >> (j + 1)) & 1u) ? zs.y : 0.f;
+                }
               }
             }
             *reinterpret_cast<uint4*>(row2 + phys) = make_uint4(pack_bf16x2(z[0], z[1]), pack_bf16x2(z[2], z[3]), pack_bf16x2(z[4], z[5]), pack_bf16x2(z[6], z[7]));
           } else if (do_gelu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = (drop_on && !((kb8 >> j) & 1u)) ? 0.f : gelu_fast(x[j]) * (drop_on ? p.drop.scale : 1.0f);
+            for (int j = 0; j < 8; j += 2) {
+              float2 gg, dg;
+              gelu_pair<true, false>(make_float2(x[j], x[j + 1]), gg, dg);
+              if (drop_on) gg = mul2(gg, splat2(p.drop.scale));
+              x[j] = (drop_on && !((kb8 >> j) & 1u)) ? 0.f : gg.x;
+              x[j + 1] = (drop_on && !((kb8 >> (j + 1)) & 1u)) ? 0.f : gg.y;
+            }
           }
           *reinterpret_cast<uint4*>(row1 + phys) = make_uint4(pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]), pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
         }

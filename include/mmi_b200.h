@@ -34,6 +34,7 @@ extern "C" {
 
 #define MMI_ACT_NONE 0
 #define MMI_ACT_GELU 1    /* erf GELU, kn_util/nn_utils/layers/mlp.py:30-31 */
+#define MMI_ACT_RELU 2    /* MLP_Block of the SelfMLP / CrossMLP ablations, models/encoder.py:210-252 */
 
 /* GEMM operand layouts (mmi_gemm): C[M,N] = op(A) * op(B)                          */
 #define MMI_GEMM_NT 0     /* A [M,K] row-major, B [N,K] row-major  (y = x W^T)       */
@@ -87,6 +88,8 @@ int mmi_gather_l1norm_fwd(const void* table, int table_dtype, int64_t n_rows, in
  *                 epilogue's y *= preact applies the dropout gradient for free); element index (m, n), BEFORE `add`
  *   if mul_gelu_grad: y *= gelu'(mul_gelu_grad[m,n])     (dgrad through GELU; mul_is_grad = 0)
  *                     y *= mul_gelu_grad[m,n]            (mul_is_grad = 1: operand saved by save_act_grad)
+ *                     y *= mul_gelu_grad[m,n] > 0 ? mul_scale : 0   (mul_is_grad = 2: the operand is the OUTPUT of a
+ *                          ReLU (+ dropout) layer, dgrad through dropout(relu(z)): kept and positive <=> output > 0)
  *   if add:  y += add[(m % add_mod) * ld_add + n]        (residual / position embedding)
  *   C    = y                (accumulate == 0)
  *   C   += y                (accumulate == 1, C must be fp32; used for weight grads)
@@ -116,10 +119,17 @@ typedef struct {
   int accumulate;
   int split_k;
   int save_act_grad;   /* 1: preact receives gelu'(z) instead of z */
-  int mul_is_grad;     /* 1: mul_gelu_grad already holds gelu'(z)  */
+  int mul_is_grad;     /* 1: mul_gelu_grad already holds gelu'(z); 2: it holds a ReLU (+ dropout) output */
   mmi_dropout drop;    /* applied to act(z) before `add`; thr8 = 0: off (not with accumulate / split-K) */
+  float mul_scale;     /* mul_is_grad == 2: survivors' scale of the dropout that followed the ReLU (1 = none) */
 } mmi_gemm_args;
 int mmi_gemm(const mmi_gemm_args* args, mmi_stream_t stream);
+
+/* ---- AdaptiveAvgPool1d(out_len) along the token axis (the CrossMLP ablation, models/encoder.py:395,504-506):
+ * x [B, L, d] -> y [B, out_len, d], window j = [floor(j L / out_len), ceil((j + 1) L / out_len)).
+ * bwd: dx[b, t, :] = sum over the windows that contain t of dy[b, j, :] / window length.                       */
+int mmi_adaptive_pool_fwd(const void* x, int dtype, int B, int L, int d, int out_len, void* y, mmi_stream_t stream);
+int mmi_adaptive_pool_bwd(const void* dy, int dtype, int B, int L, int d, int out_len, void* dx, mmi_stream_t stream);
 
 /* column sums: out[n] += sum_m X[m,n]  (bias gradients).  out is fp32.               */
 int mmi_colsum_acc(const void* x, int dtype, int64_t M, int N, int64_t ldx, float* out,
@@ -266,14 +276,16 @@ int mmi_loss_fwd_bwd(const mmi_loss_args* args, mmi_stream_t stream);
 
 /* ---- ID-embedding inputs and the bilinear fusion head ------------------------------------
  * mmi_id_embed_fwd: models/encoder.py:352-362,426-435,478-488.  out[b,l,c] = (c < tw ? table[ids[b], c]
- *   : l * frame_w[c-tw] + frame_b[c-tw]) + pe[l,c]   (video: tw = d/2, L = 40; user: tw = d, L = 1, no frame
- *   projection).  table fp32 [n_rows, tw], ids int64 [B], pe fp32 [L, d] or NULL, out [B*L, d].
- * mmi_id_embed_bwd: dtable[ids[b], c] += sum_l de[b,l,c]; dframe_w += sum_{b,l} l*de; dframe_b += sum de (atomics). */
+ *   : pos * frame_w[c-tw] + frame_b[c-tw]) + pe[l,c]   (video: tw = d/2, L = 40; user: tw = d, L = 1, no frame
+ *   projection).  table fp32 [n_rows, tw], ids int64 [B], pe fp32 [L, d] or NULL, out [B*L, d].  pos = l, or
+ *   frame_pos[b*L + l] (fp32 [B, L], may be NULL): the 'noPos' ablation feeds a random permutation of the frame
+ *   positions per interaction (models/encoder.py:428-429).
+ * mmi_id_embed_bwd: dtable[ids[b], c] += sum_l de[b,l,c]; dframe_w += sum_{b,l} pos*de; dframe_b += sum de (atomics). */
 int mmi_id_embed_fwd(const float* table, int64_t n_rows, int tw, const int64_t* ids, int B, int L, int d,
-                     const float* frame_w, const float* frame_b, const float* pe, void* out, int out_dtype,
-                     mmi_stream_t stream);
+                     const float* frame_w, const float* frame_b, const float* pe, const float* frame_pos, void* out,
+                     int out_dtype, mmi_stream_t stream);
 int mmi_id_embed_bwd(const void* de, int dtype, const int64_t* ids, int64_t n_rows, int tw, int B, int L, int d,
-                     float* dtable, float* dframe_w, float* dframe_b, mmi_stream_t stream);
+                     float* dtable, float* dframe_w, float* dframe_b, const float* frame_pos, mmi_stream_t stream);
 /* InteractionAggregation (models/decoder_leave_focal.py:411-423) after the two X_h W_h GEMMs:
  *   out[r] = sum_c T[r,c] * Y[r,c] (+ add1[r]) (+ add2[r]);   backward: dT = g*Y, dY = g*T (+ dy_add), g *= gscale[0]. */
 int mmi_rowdot_fwd(const void* t, int64_t ldt, const void* y, int64_t ldy, int dtype, int64_t R, int C,

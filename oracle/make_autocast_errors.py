@@ -28,14 +28,14 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 SIMPLE = ["model_small_dh32", "model_small_dh16", "model_small_crossatt", "model_small_selfatt", "model_small_selfmlp",
           "model_small_crossmlp", "model_small_woatt"]
 GENERAL = ["model_both_small", "model_id_small", "model_both_fh0", "model_both_fh-1", "model_both_fh-2", "model_both_fh-3",
-           "model_both_bias", "model_image_bias"]
+           "model_both_bias", "model_image_bias", "model_both_nopos", "model_id_nopos"]
 
 
 def _build(z, cfg, general):
     if general:
         args = ref_shim.make_args(d_model=cfg["d_model"], nhead=cfg["nhead"], num_layers_enc=cfg["num_layers_enc"],
                                   loss_type_list=list(cfg["loss_types"]), input_type=cfg["input_type"], fusion_heads=cfg["fusion_heads"],
-                                  learnable_bias=cfg.get("learnable_bias", 0))
+                                  learnable_bias=cfg.get("learnable_bias", 0), ablation_type=cfg.get("ablation_type", "ours"))
         model = ref_shim.build_reference_model_general(args, din=cfg["din"], n_users=cfg["n_users"], n_items=cfg["n_items"], seed=cfg["seed"])
     else:
         args = ref_shim.make_args(d_model=cfg["d_model"], nhead=cfg["nhead"], num_layers_enc=cfg["num_layers_enc"],
@@ -45,8 +45,10 @@ def _build(z, cfg, general):
     return model.eval()
 
 
-def _run(model, z, general, autocast):
+def _run(model, z, general, autocast, draw_seed=None):
     B = z["usr_mask"].shape[0]
+    if draw_seed is not None:          # 'noPos': the same frame permutations in both runs
+        torch.manual_seed(draw_seed)
     for p in model.parameters():
         p.grad = None
     batch = dict(usr_image=torch.from_numpy(z["usr_image"]), usr_mask=torch.from_numpy(z["usr_mask"]), vid_image=torch.from_numpy(z["vid_image"]),
@@ -74,9 +76,9 @@ def main():
         cfg = json.loads(str(z["cfg"]))
         general = name in GENERAL
         model = _build(z, cfg, general)
-        lg32, loss32, g32 = _run(model, z, general, False)
+        lg32, loss32, g32 = _run(model, z, general, False, cfg.get("draw_seed"))
         assert rel(lg32, z["logits"].astype(np.float64)) < 1e-6, name          # the fp32 run IS the fixture
-        lg16, loss16, g16 = _run(model, z, general, True)
+        lg16, loss16, g16 = _run(model, z, general, True, cfg.get("draw_seed"))
         e2 = r2 = 0.0
         per = {}
         for k, g in g32.items():

@@ -112,11 +112,14 @@ def _cuda_is_identity():
 
 
 def run_general_case(name, input_type, d_model, nhead, nlayers, din, B, seed, loss_types, n_users=23, n_items=57, fusion_heads=2,
-                     learnable_bias=0):
+                     learnable_bias=0, ablation_type="ours", draw_seed=None):
+    """draw_seed: torch.manual_seed(draw_seed) right before the training forward -- the 'noPos' ablation draws one
+    torch.randperm(40) per interaction and ID tower per forward call (encoder.py:428-429); the test replays the stream."""
     """SURVEY 8f-1: ID inputs / two backbones + InteractionAggregation (the reference's default 'both' config), history
     padded to the reference's 100 tokens.  Stores the full state_dict, inputs, outputs and gradients."""
     args = ref_shim.make_args(d_model=d_model, nhead=nhead, num_layers_enc=nlayers, loss_type_list=list(loss_types),
-                              input_type=input_type, fusion_heads=fusion_heads, learnable_bias=learnable_bias)
+                              input_type=input_type, fusion_heads=fusion_heads, learnable_bias=learnable_bias,
+                              ablation_type=ablation_type)
     model = ref_shim.build_reference_model_general(args, din=din, n_users=n_users, n_items=n_items, seed=seed)
     g = torch.Generator().manual_seed(seed + 1)
     with torch.no_grad():
@@ -140,12 +143,15 @@ def run_general_case(name, input_type, d_model, nhead, nlayers, din, B, seed, lo
     batch = dict(usr_image=torch.from_numpy(usr), usr_id=torch.from_numpy(usr_id), usr_mask=torch.from_numpy(usr_mask),
                  vid_image=torch.from_numpy(vid), vid_id=torch.from_numpy(vid_id), vid_mask=torch.from_numpy(vid_mask),
                  gt=torch.from_numpy(gt.copy()))
+    if draw_seed is not None:
+        torch.manual_seed(draw_seed)
     with _cuda_is_identity():
         out = ref_shim.run_reference(model, batch, mode="train")
     out["loss"].backward()
     save = dict(cfg=json.dumps(dict(d_model=d_model, nhead=nhead, num_layers_enc=nlayers, din=din, Lt=Lt, B=B, seed=seed,
                                     loss_types=list(loss_types), input_type=input_type, n_users=n_users, n_items=n_items,
-                                    fusion_heads=fusion_heads, learnable_bias=learnable_bias)),
+                                    fusion_heads=fusion_heads, learnable_bias=learnable_bias, ablation_type=ablation_type,
+                                    draw_seed=draw_seed)),
                 usr_image=usr, vid_image=vid, usr_id=usr_id, vid_id=vid_id, usr_mask=usr_mask, vid_mask=vid_mask, gt_in=gt,
                 logits=out["logits"].detach().numpy(), gt_out=out["gt"].numpy(), loss=np.float64(out["loss"].item()),
                 mse=np.float64(out["mse"].item()), mse2=np.float64(out["mse2"].item()))
@@ -378,6 +384,15 @@ def run_general_cases():
                      loss_types=("focal",))
     run_fusion_variants()
     run_bias_cases()
+    run_nopos_cases()
+
+
+def run_nopos_cases():
+    """the 'noPos' ablation (encoder.py:428-429): random frame positions into the ID tower's frame projection, per call"""
+    run_general_case("model_both_nopos", {"user": "both", "photo": "both"}, d_model=64, nhead=2, nlayers=3, din=24, B=4, seed=81,
+                     loss_types=("interestBPR",), ablation_type="noPos", draw_seed=4321)
+    run_general_case("model_id_nopos", {"user": "id", "photo": "id"}, d_model=64, nhead=2, nlayers=3, din=24, B=4, seed=82,
+                     loss_types=("focal",), ablation_type="noPos", draw_seed=99)
 
 
 def run_bias_cases():
@@ -432,6 +447,8 @@ if __name__ == "__main__":
         run_topk_case()
     elif "--bias-only" in sys.argv:
         run_bias_cases()
+    elif "--nopos-only" in sys.argv:
+        run_nopos_cases()
     elif "--fusion-only" in sys.argv:
         run_fusion_variants()
     elif "--ablation-only" in sys.argv:

@@ -53,7 +53,7 @@ def torch_dropout(p=0.1):
     return drop
 
 
-def embed(sd, prefix, usr, vid, use_pe=True, drop=None):
+def embed(sd, prefix, usr, vid, use_pe=True, drop=None, no_pos=False):
     """models/encoder.py:425-473.  Image inputs are [B,L,Din] floats (Linear projections); ID inputs
     are int64 [B] (encoder.py:352-362,426-435,478-488): the video id is repeated over the 40 segments
     and embedded into d/2 columns, the other d/2 come from Linear(1 -> d/2) of the segment position; the user id
@@ -62,7 +62,10 @@ def embed(sd, prefix, usr, vid, use_pe=True, drop=None):
     if vid.ndim == 1:
         B, Lv = vid.shape[0], 40
         emb = sd[prefix + "vid_proj.weight"][vid][:, None, :].expand(B, Lv, -1)
-        pos = torch.arange(Lv, dtype=emb.dtype)[None, :, None].expand(B, Lv, 1)
+        if no_pos:      # 'noPos' (encoder.py:428-429): one torch.randperm(Lv) per interaction from the default generator
+            pos = torch.stack([torch.randperm(Lv) for _ in range(B)]).to(emb.dtype)[:, :, None]
+        else:
+            pos = torch.arange(Lv, dtype=emb.dtype)[None, :, None].expand(B, Lv, 1)
         fr = F.linear(pos, sd[prefix + "frameid_proj.weight"], sd[prefix + "frameid_proj.bias"])
         v = torch.cat([emb, fr], -1)
     else:
@@ -190,11 +193,12 @@ def mlp_block(sd, prefix, x, drop=None, tower=0):
     return x
 
 
-def backbone(sd, prefix, usr, usr_mask, vid, vid_mask, nhead, num_layers, use_pe=True, ablation="ours", drop=None, full_usr=False):
+def backbone(sd, prefix, usr, usr_mask, vid, vid_mask, nhead, num_layers, use_pe=True, ablation="ours", drop=None, full_usr=False,
+             no_pos=False):
     """models/encoder.py:302-324,475-520.  intermediate_states records vid_feat
     BEFORE each layer and the caller takes [-1], so layer N-1 never reaches the
     output, nor does the history side of layer N-2."""
-    v, u = embed(sd, prefix, usr, vid, use_pe, drop)
+    v, u = embed(sd, prefix, usr, vid, use_pe, drop, no_pos)
     tw = _tower(prefix)
     # the MLP ablations replace the attention encoder (encoder.py:503-511); none of them looks at the masks
     if ablation == "CrossMLP":     # MLP over [history ; candidate] tokens, then AdaptiveAvgPool1d(40) along the token axis
@@ -396,11 +400,12 @@ def forward(sd, usr_image, usr_mask, vid_image, vid_mask, gt, *, nhead, num_laye
         return image if kind == "image" else ident
 
     abl = ablation_type if ablation_type in MLP_ABLATIONS else attn_ablation(ablation_type)
+    no_pos = "noPos" in (ablation_type or "")
     x1 = backbone(sd, "backbone1.", pick(it["user"], usr_image, usr_id, 1), usr_mask.bool(),
-                  pick(it["photo"], vid_image, vid_id, 1), vid_mask.bool(), nhead, num_layers, use_pe, abl, drop, full_usr)
+                  pick(it["photo"], vid_image, vid_id, 1), vid_mask.bool(), nhead, num_layers, use_pe, abl, drop, full_usr, no_pos)
     if two:
         x2 = backbone(sd, "backbone2.", pick(it["user"], usr_image, usr_id, 2), usr_mask.bool(),
-                      pick(it["photo"], vid_image, vid_id, 2), vid_mask.bool(), nhead, num_layers, use_pe, abl, drop, full_usr)
+                      pick(it["photo"], vid_image, vid_id, 2), vid_mask.bool(), nhead, num_layers, use_pe, abl, drop, full_usr, no_pos)
         if fusion_heads > 0:
             logits = fusion_logits(sd, x1, x2, fusion_heads)
         elif fusion_heads == 0:      # models/decoder_leave_focal.py:630-631: stage_mlp1(x1) + stage_mlp2(x2)

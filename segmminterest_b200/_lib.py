@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MMI_LIB_PATH") or os.path.join(HERE, "libmmi_b200.so")   # override: A/B builds of the kernels (tools/)
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
 IMPL_SIMT, IMPL_TC = 0, 1
 
@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
                 ("mul_gelu_grad", c_p), ("ld_mul", i64),
                 ("add", c_p), ("ld_add", i64), ("add_mod", i64), ("add_dtype", C.c_int),
                 ("accumulate", C.c_int), ("split_k", C.c_int), ("save_act_grad", C.c_int), ("mul_is_grad", C.c_int),
-                ("drop", Dropout)]
+                ("drop", Dropout), ("mul_scale", C.c_float)]
 
 
 class AttnBlock(C.Structure):
@@ -69,6 +69,8 @@ _SIGS = {
     "mmi_has_tc": (C.c_int, []),
     "mmi_gather_l1norm_fwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, i64, c_p, C.c_int, c_p, C.c_int, c_p]),
     "mmi_gemm": (C.c_int, [C.POINTER(GemmArgs), c_p]),
+    "mmi_adaptive_pool_fwd": (C.c_int, [c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p]),
+    "mmi_adaptive_pool_bwd": (C.c_int, [c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p]),
     "mmi_colsum_acc": (C.c_int, [c_p, C.c_int, i64, C.c_int, i64, c_p, c_p, i64, c_p]),
     "mmi_layernorm_fwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, C.c_float, c_p, c_p, c_p]),
     "mmi_layernorm_fwd_drop": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, C.c_float, c_p, c_p, C.POINTER(Dropout), c_p]),
@@ -87,8 +89,8 @@ _SIGS = {
     "mmi_head_bwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "mmi_focal_loss_fwd_bwd": (C.c_int, [c_p, c_p, C.c_int, C.c_int, c_p, C.c_float, C.c_float, C.c_int, c_p, c_p, c_p]),
     "mmi_loss_fwd_bwd": (C.c_int, [C.POINTER(LossArgs), c_p]),
-    "mmi_id_embed_fwd": (C.c_int, [c_p, i64, C.c_int, c_p, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, c_p, C.c_int, c_p]),
-    "mmi_id_embed_bwd": (C.c_int, [c_p, C.c_int, c_p, i64, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, c_p]),
+    "mmi_id_embed_fwd": (C.c_int, [c_p, i64, C.c_int, c_p, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, c_p, c_p, C.c_int, c_p]),
+    "mmi_id_embed_bwd": (C.c_int, [c_p, C.c_int, c_p, i64, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, c_p, c_p]),
     "mmi_rowdot_fwd": (C.c_int, [c_p, i64, c_p, i64, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p]),
     "mmi_rowdot_bwd": (C.c_int, [c_p, c_p, c_p, i64, c_p, i64, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p]),
     "mmi_clip_adamw_workspace": (i64, [i64]),

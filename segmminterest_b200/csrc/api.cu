@@ -48,6 +48,9 @@ extern "C" int mmi_gemm(const mmi_gemm_args* a, mmi_stream_t stream) {
   p.accumulate = a->accumulate; p.split_k = a->split_k;
   p.save_act_grad = a->save_act_grad; p.mul_is_grad = a->mul_is_grad;
   p.drop = make_drop(a->drop);
+  p.mul_scale = a->mul_scale;
+  MMI_CHECK_ARG(a->act >= MMI_ACT_NONE && a->act <= MMI_ACT_RELU, "gemm: bad activation %d", a->act);
+  MMI_CHECK_ARG(!(a->act == MMI_ACT_RELU && a->preact), "gemm: ReLU saves nothing (its backward reads the layer's output)");
   MMI_CHECK_ARG(p.drop.thr8 < 256u, "gemm: dropout thr8 must be < 256");
   MMI_CHECK_ARG(!(p.drop.thr8 && (a->accumulate || a->split_k > 1)), "gemm: dropout cannot be combined with accumulate / split-K");
   MMI_CHECK_ARG(!(p.drop.thr8 && a->mul_gelu_grad && a->act != MMI_ACT_NONE), "gemm: dropout with both act and mul_gelu_grad is undefined");

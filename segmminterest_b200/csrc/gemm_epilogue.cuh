@@ -22,6 +22,7 @@ struct GemmParams {
   int save_act_grad;
   int mul_is_grad;
   DropParams drop;     // dropout of act(z) before `add` (and of the saved gelu'(z)); thr8 = 0: off
+  float mul_scale;     // mul_is_grad == 2: y *= (mul > 0 ? mul_scale : 0)
 };
 
 // 4 consecutive columns n..n+3 of row m.  `lead` = this CTA owns the bias/add terms
@@ -47,6 +48,9 @@ __device__ __forceinline__ void gemm_epilogue4(const GemmParams& p, int64_t m, i
   if (p.act == MMI_ACT_GELU) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = gelu_f(v[j]);
+  } else if (p.act == MMI_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (p.drop.thr8 != 0u) {
 #pragma unroll
@@ -54,7 +58,10 @@ __device__ __forceinline__ void gemm_epilogue4(const GemmParams& p, int64_t m, i
   }
   if (p.mul_gelu_grad != nullptr) {
     const float4 z = load4(reinterpret_cast<const TIN*>(p.mul_gelu_grad) + m * p.ld_mul + n);
-    if (p.mul_is_grad) { v[0] *= z.x; v[1] *= z.y; v[2] *= z.z; v[3] *= z.w; }
+    if (p.mul_is_grad == 2) {
+      v[0] = z.x > 0.f ? v[0] * p.mul_scale : 0.f; v[1] = z.y > 0.f ? v[1] * p.mul_scale : 0.f;
+      v[2] = z.z > 0.f ? v[2] * p.mul_scale : 0.f; v[3] = z.w > 0.f ? v[3] * p.mul_scale : 0.f;
+    } else if (p.mul_is_grad) { v[0] *= z.x; v[1] *= z.y; v[2] *= z.z; v[3] *= z.w; }
     else { v[0] *= gelu_grad_f(z.x); v[1] *= gelu_grad_f(z.y); v[2] *= gelu_grad_f(z.z); v[3] *= gelu_grad_f(z.w); }
   }
   if (lead && p.add != nullptr) {
@@ -141,10 +148,12 @@ __device__ __forceinline__ void gemm_epilogue2(const GemmParams& p, int64_t m, i
     store2(reinterpret_cast<TIN*>(p.preact) + m * p.ld_preact + n,
            p.save_act_grad ? make_float2(gelu_grad_fast(v0) * k0, gelu_grad_fast(v1) * k1) : make_float2(v0, v1));
   if (p.act == MMI_ACT_GELU) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); }
+  else if (p.act == MMI_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
   v0 *= k0; v1 *= k1;
   if (p.mul_gelu_grad != nullptr) {
     const float2 z = load2(reinterpret_cast<const TIN*>(p.mul_gelu_grad) + m * p.ld_mul + n);
-    if (p.mul_is_grad) { v0 *= z.x; v1 *= z.y; }
+    if (p.mul_is_grad == 2) { v0 = z.x > 0.f ? v0 * p.mul_scale : 0.f; v1 = z.y > 0.f ? v1 * p.mul_scale : 0.f; }
+    else if (p.mul_is_grad) { v0 *= z.x; v1 *= z.y; }
     else { v0 *= gelu_grad_fast(z.x); v1 *= gelu_grad_fast(z.y); }
   }
   if (lead && p.add != nullptr) {

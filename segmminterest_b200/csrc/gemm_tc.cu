@@ -185,7 +185,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const bool aux_add = p.add != nullptr && !pe_add, aux_mul = p.mul_gelu_grad != nullptr;
     const bool has_aux = aux_add || aux_mul;
     const bool second = p.preact != nullptr;           // host: never together with an aux operand
-    const bool do_gelu = p.act == MMI_ACT_GELU;
+    const bool do_gelu = p.act == MMI_ACT_GELU, do_relu = p.act == MMI_ACT_RELU;
     constexpr bool drop_on = DROP;
     // Linear -> dropout -> (+ residual): the survivors' scale rides in the bias add (x = acc * s + b * s), the mask is a
     // select on bits of the row's keep words (compile-time bit positions: ptxas turns a byte of them into one R2P)
@@ -279,6 +279,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               x[j] += a.x; x[j + 1] += a.y; x[j + 2] += a.z; x[j + 3] += a.w;
             }
           }
+          if (do_relu) {                                 // relu(z) (times the survivors' scale, already folded into x)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+          }
           if (drop_on && !do_gelu) {                     // dropout(x W^T + b) BEFORE the residual is added
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = ((kb8 >> j) & 1u) ? x[j] : 0.f;
@@ -290,6 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             for (int j = 0; j < 4; ++j) {
               const float a0 = __uint_as_float(aw[j] << 16), a1 = __uint_as_float(aw[j] & 0xffff0000u);
               if (aux_add) { x[2 * j] += a0; x[2 * j + 1] += a1; }
+              else if (p.mul_is_grad == 2) { x[2 * j] = a0 > 0.f ? x[2 * j] * p.mul_scale : 0.f; x[2 * j + 1] = a1 > 0.f ? x[2 * j + 1] * p.mul_scale : 0.f; }
               else if (p.mul_is_grad) { x[2 * j] *= a0; x[2 * j + 1] *= a1; }
               else { float2 gg, dg; gelu_pair<false, true>(make_float2(a0, a1), gg, dg); x[2 * j] *= dg.x; x[2 * j + 1] *= dg.y; }
             }

@@ -9,11 +9,13 @@
 
 namespace mmi {
 
-// out[b, l, c] = (c < tw ? table[id_b, c] : l * frame_w[c - tw] + frame_b[c - tw]) + pe[l, c]
+// out[b, l, c] = (c < tw ? table[id_b, c] : pos(b, l) * frame_w[c - tw] + frame_b[c - tw]) + pe[l, c]
+// pos(b, l) = l, or frame_pos[b, l] when given (the 'noPos' ablation feeds a random permutation of 0..L-1 per row, encoder.py:428-429)
 template <typename TO>
 __global__ void __launch_bounds__(256) id_embed_fwd_kernel(const float* __restrict__ table, int64_t n_rows, int tw, const int64_t* __restrict__ ids,
                                                            int B, int L, int d, const float* __restrict__ frame_w,
-                                                           const float* __restrict__ frame_b, const float* __restrict__ pe, TO* __restrict__ out) {
+                                                           const float* __restrict__ frame_b, const float* __restrict__ pe,
+                                                           const float* __restrict__ frame_pos, TO* __restrict__ out) {
   const int64_t total = (int64_t)B * L * d;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % d);
@@ -25,7 +27,7 @@ __global__ void __launch_bounds__(256) id_embed_fwd_kernel(const float* __restri
       r = r < 0 ? 0 : (r >= n_rows ? n_rows - 1 : r);       // torch would raise; the C ABI clamps (caller validates)
       v = table[r * tw + c];
     } else {
-      v = (float)l * frame_w[c - tw] + frame_b[c - tw];
+      v = (frame_pos ? frame_pos[(int64_t)b * L + l] : (float)l) * frame_w[c - tw] + frame_b[c - tw];
     }
     if (pe != nullptr) v += pe[(int64_t)l * d + c];
     out[i] = from_f32<TO>(v);
@@ -37,7 +39,7 @@ __global__ void __launch_bounds__(256) id_embed_fwd_kernel(const float* __restri
 template <typename TI>
 __global__ void __launch_bounds__(256) id_embed_bwd_kernel(const TI* __restrict__ de, const int64_t* __restrict__ ids, int64_t n_rows, int tw,
                                                            int B, int L, int d, float* __restrict__ dtable, float* __restrict__ dframe_w,
-                                                           float* __restrict__ dframe_b) {
+                                                           float* __restrict__ dframe_b, const float* __restrict__ frame_pos) {
   const int b = blockIdx.x;
   int64_t r = ids[b];
   r = r < 0 ? 0 : (r >= n_rows ? n_rows - 1 : r);
@@ -46,7 +48,7 @@ __global__ void __launch_bounds__(256) id_embed_bwd_kernel(const TI* __restrict_
     for (int l = 0; l < L; ++l) {
       const float g = to_f32(de[((int64_t)b * L + l) * d + c]);
       s += g;
-      sl += (float)l * g;
+      sl += (frame_pos ? frame_pos[(int64_t)b * L + l] : (float)l) * g;
     }
     if (c < tw) atomicAdd(dtable + r * tw + c, s);
     else {
@@ -97,13 +99,82 @@ __global__ void __launch_bounds__(256) rowdot_bwd_kernel(const float* __restrict
   }
 }
 
+// AdaptiveAvgPool1d(P) along the token axis (the CrossMLP ablation, models/encoder.py:395,504-506): window j of a length-L
+// axis is [floor(j L / P), ceil((j + 1) L / P)) -- torch's definition; windows overlap when L is not a multiple of P.
+__device__ __forceinline__ int pool_start(int j, int L, int P) { return (int)(((int64_t)j * L) / P); }
+__device__ __forceinline__ int pool_end(int j, int L, int P) { return (int)((((int64_t)j + 1) * L + P - 1) / P); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) adaptive_pool_fwd_kernel(const T* __restrict__ x, int B, int L, int d, int P, T* __restrict__ y) {
+  const int64_t total = (int64_t)B * P * (d / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (d / 4)) * 4;
+    const int j = (int)((i / (d / 4)) % P);
+    const int b = (int)(i / ((int64_t)(d / 4) * P));
+    const int s = pool_start(j, L, P), e = pool_end(j, L, P);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = s; t < e; ++t) {
+      const float4 v = load4(x + ((int64_t)b * L + t) * d + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float inv = 1.0f / (float)(e - s);
+    store4(y + ((int64_t)b * P + j) * d + c, make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) adaptive_pool_bwd_kernel(const T* __restrict__ dy, int B, int L, int d, int P, T* __restrict__ dx) {
+  const int64_t total = (int64_t)B * L * (d / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (d / 4)) * 4;
+    const int t = (int)((i / (d / 4)) % L);
+    const int b = (int)(i / ((int64_t)(d / 4) * L));
+    // windows that contain t: j with floor(j L / P) <= t < ceil((j + 1) L / P); start from a lower bound and scan
+    int j = (int)(((int64_t)t * P) / L);
+    while (j > 0 && pool_end(j - 1, L, P) > t) --j;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (; j < P && pool_start(j, L, P) <= t; ++j) {
+      const int e = pool_end(j, L, P), s0 = pool_start(j, L, P);
+      if (t >= e) continue;
+      const float inv = 1.0f / (float)(e - s0);
+      const float4 g = load4(dy + ((int64_t)b * P + j) * d + c);
+      acc.x += g.x * inv; acc.y += g.y * inv; acc.z += g.z * inv; acc.w += g.w * inv;
+    }
+    store4(dx + ((int64_t)b * L + t) * d + c, acc);
+  }
+}
+
 }  // namespace mmi
 
 using namespace mmi;
 
+static int pool_launch(bool fwd, const void* in, int dtype, int B, int L, int d, int P, void* out, mmi_stream_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMI_CHECK_ARG(in && out, "adaptive_pool: null pointer");
+  MMI_CHECK_ARG(B > 0 && L > 0 && P > 0 && d > 0 && d % 4 == 0, "adaptive_pool: need B, L, out_len > 0 and d a positive multiple of 4");
+  const int64_t total = (int64_t)B * (fwd ? P : L) * (d / 4);
+  int64_t grid = (total + 255) / 256;
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  if (dtype == MMI_F32) {
+    if (fwd) adaptive_pool_fwd_kernel<float><<<(unsigned)grid, 256, 0, st>>>((const float*)in, B, L, d, P, (float*)out);
+    else adaptive_pool_bwd_kernel<float><<<(unsigned)grid, 256, 0, st>>>((const float*)in, B, L, d, P, (float*)out);
+  } else if (dtype == MMI_BF16) {
+    if (fwd) adaptive_pool_fwd_kernel<__nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>((const __nv_bfloat16*)in, B, L, d, P, (__nv_bfloat16*)out);
+    else adaptive_pool_bwd_kernel<__nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>((const __nv_bfloat16*)in, B, L, d, P, (__nv_bfloat16*)out);
+  } else { set_error("adaptive_pool: bad dtype %d", dtype); return MMI_EINVAL; }
+  MMI_CHECK_LAUNCH();
+  return MMI_OK;
+}
+extern "C" int mmi_adaptive_pool_fwd(const void* x, int dtype, int B, int L, int d, int out_len, void* y, mmi_stream_t stream) {
+  return pool_launch(true, x, dtype, B, L, d, out_len, y, stream);
+}
+extern "C" int mmi_adaptive_pool_bwd(const void* dy, int dtype, int B, int L, int d, int out_len, void* dx, mmi_stream_t stream) {
+  return pool_launch(false, dy, dtype, B, L, d, out_len, dx, stream);
+}
+
 extern "C" int mmi_id_embed_fwd(const float* table, int64_t n_rows, int tw, const int64_t* ids, int B, int L, int d,
-                                const float* frame_w, const float* frame_b, const float* pe, void* out, int out_dtype,
-                                mmi_stream_t stream) {
+                                const float* frame_w, const float* frame_b, const float* pe, const float* frame_pos, void* out,
+                                int out_dtype, mmi_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MMI_CHECK_ARG(table && ids && out, "id_embed_fwd: null pointer");
   MMI_CHECK_ARG(B > 0 && L > 0 && d > 0 && tw > 0 && tw <= d && n_rows > 0, "id_embed_fwd: bad sizes");
@@ -111,20 +182,20 @@ extern "C" int mmi_id_embed_fwd(const float* table, int64_t n_rows, int tw, cons
   const int64_t total = (int64_t)B * L * d;
   int64_t grid = (total + 255) / 256;
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  if (out_dtype == MMI_F32) id_embed_fwd_kernel<float><<<(unsigned)grid, 256, 0, st>>>(table, n_rows, tw, ids, B, L, d, frame_w, frame_b, pe, (float*)out);
-  else if (out_dtype == MMI_BF16) id_embed_fwd_kernel<__nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(table, n_rows, tw, ids, B, L, d, frame_w, frame_b, pe, (__nv_bfloat16*)out);
+  if (out_dtype == MMI_F32) id_embed_fwd_kernel<float><<<(unsigned)grid, 256, 0, st>>>(table, n_rows, tw, ids, B, L, d, frame_w, frame_b, pe, frame_pos, (float*)out);
+  else if (out_dtype == MMI_BF16) id_embed_fwd_kernel<__nv_bfloat16><<<(unsigned)grid, 256, 0, st>>>(table, n_rows, tw, ids, B, L, d, frame_w, frame_b, pe, frame_pos, (__nv_bfloat16*)out);
   else { set_error("id_embed_fwd: bad dtype %d", out_dtype); return MMI_EINVAL; }
   MMI_CHECK_LAUNCH();
   return MMI_OK;
 }
 
 extern "C" int mmi_id_embed_bwd(const void* de, int dtype, const int64_t* ids, int64_t n_rows, int tw, int B, int L, int d,
-                                float* dtable, float* dframe_w, float* dframe_b, mmi_stream_t stream) {
+                                float* dtable, float* dframe_w, float* dframe_b, const float* frame_pos, mmi_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MMI_CHECK_ARG(de && ids && dtable, "id_embed_bwd: null pointer");
   MMI_CHECK_ARG(B > 0 && L > 0 && d > 0 && tw > 0 && tw <= d && n_rows > 0, "id_embed_bwd: bad sizes");
-  if (dtype == MMI_F32) id_embed_bwd_kernel<float><<<B, 256, 0, st>>>((const float*)de, ids, n_rows, tw, B, L, d, dtable, dframe_w, dframe_b);
-  else if (dtype == MMI_BF16) id_embed_bwd_kernel<__nv_bfloat16><<<B, 256, 0, st>>>((const __nv_bfloat16*)de, ids, n_rows, tw, B, L, d, dtable, dframe_w, dframe_b);
+  if (dtype == MMI_F32) id_embed_bwd_kernel<float><<<B, 256, 0, st>>>((const float*)de, ids, n_rows, tw, B, L, d, dtable, dframe_w, dframe_b, frame_pos);
+  else if (dtype == MMI_BF16) id_embed_bwd_kernel<__nv_bfloat16><<<B, 256, 0, st>>>((const __nv_bfloat16*)de, ids, n_rows, tw, B, L, d, dtable, dframe_w, dframe_b, frame_pos);
   else { set_error("id_embed_bwd: bad dtype %d", dtype); return MMI_EINVAL; }
   MMI_CHECK_LAUNCH();
   return MMI_OK;

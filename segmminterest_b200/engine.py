@@ -21,7 +21,7 @@ import torch
 
 from . import _lib, ops
 from .dropout import DropSite, quantise, site_key
-from .ops import ACT_GELU, ACT_NONE, GEMM_NN, GEMM_NT, GEMM_TN, IMPL_SIMT, IMPL_TC
+from .ops import ACT_GELU, ACT_NONE, ACT_RELU, GEMM_NN, GEMM_NT, GEMM_TN, IMPL_SIMT, IMPL_TC
 
 ALIGN = 64  # floats (256 B): every parameter group starts on a TMA-friendly boundary
 
@@ -36,11 +36,15 @@ PROJ_ORDER = {"vid": [("v2v", 0), ("v2v", 1), ("v2v", 2), ("t2v", 0), ("v2t", 1)
 ATTN_BLOCKS = {"ours": {"vid": ("v2v", "t2v"), "usr": ("v2t", "t2t")},
                "CrossAtt": {"vid": ("t2v",), "usr": ("v2t",)},
                "SelfAtt": {"vid": ("v2v",), "usr": ()}}
+MLP_ABLATIONS = ("SelfMLP", "CrossMLP", "w/oAtt")
 
 
 def attn_ablation(ablation_type):
-    """the reference tests substrings ('noUser_SelfAtt' is SelfAtt for the model; 'noUser' lives in the driver)"""
+    """the reference tests substrings for the attention ablations ('noUser_SelfAtt' is SelfAtt for the model; 'noUser' lives
+    in the driver; 'noPos' keeps the full encoder) and equality for the MLP ablations (encoder.py:392-400,503-511)"""
     a = ablation_type or "ours"
+    if a in MLP_ABLATIONS:
+        return a
     return "CrossAtt" if "CrossAtt" in a else ("SelfAtt" if "SelfAtt" in a else "ours")
 
 
@@ -55,7 +59,8 @@ class EngineConfig:
     max_vid_len: int = 40
     use_pe: bool = True
     precision: str = "fp32"   # 'fp32' (FFMA, strict parity) | 'bf16' (tcgen05 tensor cores)
-    ablation: str = "ours"    # 'ours' | 'CrossAtt' | 'SelfAtt'
+    ablation: str = "ours"    # 'ours' | 'CrossAtt' | 'SelfAtt' | 'SelfMLP' | 'CrossMLP' | 'w/oAtt'
+    no_pos: bool = False      # 'noPos': a fresh random permutation of the frame positions per call (ID-input towers only)
 
 
 class _View:
@@ -140,6 +145,10 @@ class Engine:
         self.red_ws = torch.empty(int(n_red), device=device, dtype=torch.float32)
         self.scalars = torch.zeros(16, device=device, dtype=torch.float32)
 
+    @property
+    def mlp_ablation(self):
+        return self.cfg.ablation in MLP_ABLATIONS
+
     def layer_plan(self, i):
         """(query sides that are computed in layer i, {token side: [(block, j), ...] projections in buffer order})."""
         blocks = ATTN_BLOCKS[self.cfg.ablation]
@@ -150,7 +159,8 @@ class Engine:
 
     @property
     def uses_history(self):
-        return self.cfg.ablation != "SelfAtt"
+        """SelfAtt, SelfMLP and w/oAtt never read the history tokens (their usr_* parameters stay at grad = None)"""
+        return self.cfg.ablation not in ("SelfAtt", "SelfMLP", "w/oAtt")
 
     # ------------------------------------------------------------------ parameter layout
     def _layout(self):
@@ -187,7 +197,12 @@ class Engine:
                 ln = getattr(bb, s + "_ln")
                 group(k(f"{s}_ln.g"), [(f"{P}{s}_ln.weight", ln.weight)])
                 group(k(f"{s}_ln.b"), [(f"{P}{s}_ln.bias", ln.bias)])
-            for i in range(N - 1):
+            if self.mlp_ablation and cfg.ablation != "w/oAtt":     # MLP_Block encoder (w/oAtt builds it and never calls it)
+                for n, lin in enumerate(bb.encoder_mlp.linears()):
+                    idx = bb.encoder_mlp.linear_indices()[n]
+                    group(k(f"M{n}.w1"), [(f"{P}encoder_mlp.mlp.{idx}.weight", lin.weight)])
+                    group(k(f"M{n}.b1"), [(f"{P}encoder_mlp.mlp.{idx}.bias", lin.bias)])
+            for i in range(0 if self.mlp_ablation else N - 1):
                 L = bb.encoder.layers[i]
                 ca = L.cross_attn
                 qsides, projs = self.layer_plan(i)
@@ -333,7 +348,7 @@ class Engine:
         return IMPL_TC if ok else IMPL_SIMT
 
     # ------------------------------------------------------------------ dropout sites
-    DROP_EMB, DROP_ATTN, DROP_ATTN_OUT, DROP_MLP1, DROP_MLP2 = range(5)
+    DROP_EMB, DROP_ATTN, DROP_ATTN_OUT, DROP_MLP1, DROP_MLP2, DROP_BLOCK = range(6)   # DROP_BLOCK: hidden units of MLP_Block
 
     def _site(self, tw, layer, side, kind):
         """DropSite of one nn.Dropout call of the reference in the forward in flight (None when dropout is off):
@@ -361,7 +376,7 @@ class Engine:
                  drop=drop)
 
     def _linear_bwd(self, dy, x, M, N, K, wkey, bkey, dx, *, mul_gelu_grad=None, add=None, need_dx=True, bias_done=False,
-                    drop=None):
+                    drop=None, relu_out=None, relu_scale=1.0):
         """dW += dy^T x ; db += colsum(dy) ; dx = dy W (* gelu'(mul)) (+ add).  bias_done: the kernel that produced dy
         (LayerNorm backward) already accumulated the bias gradient.  drop: dropout of the site that FOLLOWED the GELU whose
         derivative is multiplied in (strict-parity path only: the tensor-core path folds it into the saved gelu')."""
@@ -376,12 +391,15 @@ class Engine:
             split = max(1, min(32, (2 * 148) // tiles, (M + 4095) // 4096))
         ops.gemm(GEMM_TN, impl_w, dy, N, x, K, self.g(wkey), K, N, K, M, accumulate=True, split_k=split, out_dtype=_lib.F32)
         if need_dx:
+            # relu_out: x itself is dropout(relu(.)) of the previous MLP_Block unit -- dx is multiplied by its derivative
+            # (x > 0 ? relu_scale : 0) in the epilogue, which makes dx the gradient w.r.t. that unit's pre-activation
+            mul, mig = (relu_out, 2) if relu_out is not None else (mul_gelu_grad, 1 if self.use_tc else 0)
             if self._impl(M, K, N, GEMM_NT) == IMPL_TC:
-                ops.gemm(GEMM_NT, IMPL_TC, dy, N, self.wT(wkey), N, dx, K, M, K, N, mul_gelu_grad=mul_gelu_grad, add=add,
-                         add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=self.use_tc, drop=drop)
+                ops.gemm(GEMM_NT, IMPL_TC, dy, N, self.wT(wkey), N, dx, K, M, K, N, mul_gelu_grad=mul, add=add,
+                         add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=mig, drop=drop, mul_scale=relu_scale)
             else:
-                ops.gemm(GEMM_NN, IMPL_SIMT, dy, N, self.w(wkey, lp), K, dx, K, M, K, N, mul_gelu_grad=mul_gelu_grad,
-                         add=add, add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=self.use_tc, drop=drop)
+                ops.gemm(GEMM_NN, IMPL_SIMT, dy, N, self.w(wkey, lp), K, dx, K, M, K, N, mul_gelu_grad=mul,
+                         add=add, add_mod=M if add is not None else 0, ld_add=K, mul_is_grad=mig, drop=drop, mul_scale=relu_scale)
 
     # ------------------------------------------------------------------ forward
     def forward(self, usr_image, usr_mask, vid_image, vid_mask, usr_id=None, vid_id=None, refresh=True, need_bwd=True):
@@ -504,13 +522,23 @@ class Engine:
                 table = self.w(k(f"{s}_proj.w"))
                 tw_cols = d // 2 if s == "vid" else d
                 table = table.view(-1, tw_cols)
+                fpos = None
+                if s == "vid" and cfg.no_pos:
+                    # 'noPos' (encoder.py:428-429): one torch.randperm(Lv) per interaction, drawn on the host from torch's
+                    # default generator exactly like the reference, fed to the frame projection instead of 0..Lv-1
+                    fpos = torch.stack([torch.randperm(Ls[s]) for _ in range(B)]).float().to(self.device).contiguous()
+                if s == "vid":
+                    ts["frame_pos"] = fpos
                 ops.id_embed_fwd(table, ids, B, Ls[s], d, e, frame_w=self.w(k("frameid.w")) if s == "vid" else None,
-                                 frame_b=self.w(k("frameid.b")) if s == "vid" else None, pe=pe)
+                                 frame_b=self.w(k("frameid.b")) if s == "vid" else None, pe=pe, frame_pos=fpos)
             ts[f"drop.emb.{s}"] = self._site(tw, 63, s, self.DROP_EMB)
             ops.layernorm_fwd(e, Ts[s], d, self.w(k(f"{s}_ln.g")), self.w(k(f"{s}_ln.b")), x0, st, drop=ts[f"drop.emb.{s}"])
             ts[f"emb_pre.{s}"], ts[f"emb_st.{s}"] = e, st
             X[s] = x0
         esz = x0.element_size()
+        if self.mlp_ablation:
+            sv["towers"][tw.tag] = ts
+            return self._mlp_encoder_forward(tw, ts, X, B, Lt, Lv), B, Lv
         for i in range(N - 1):
             sides, projs = self.layer_plan(i)
             nq = {s: len(projs[s]) for s in ("vid", "usr")}
@@ -563,6 +591,70 @@ class Engine:
             ts["layers"].append(lay)
         sv["towers"][tw.tag] = ts
         return X["vid"], B, Lv
+
+    # ------------------------------------------------------------------ MLP ablations (SelfMLP / CrossMLP / w/oAtt)
+    def _mlp_encoder_forward(self, tw, ts, X, B, Lt, Lv):
+        """models/encoder.py:503-511: the attention encoder is replaced by MLP_Block ([Linear -> ReLU -> Dropout] x hidden,
+        Linear) over the candidate tokens (SelfMLP), over [history ; candidate] tokens followed by AdaptiveAvgPool1d(40)
+        along the token axis (CrossMLP), or by nothing at all (w/oAtt: the embedded candidate tokens go to the head)."""
+        cfg, k = self.cfg, tw.k
+        T, d = self.act_dtype, cfg.d_model
+        if cfg.ablation == "w/oAtt":
+            ts["mlp"] = None
+            return X["vid"]
+        if cfg.ablation == "CrossMLP":
+            L = Lt + Lv
+            xcat = self._buf(k("mlp.xcat"), (B, L, d), T)           # torch.cat((usr_feat, vid_feat), dim=-2): a strided copy
+            xcat[:, :Lt].copy_(X["usr"].view(B, Lt, d))
+            xcat[:, Lt:].copy_(X["vid"].view(B, Lv, d))
+            h, rows = xcat.view(B * L, d), B * L
+        else:
+            L = Lv
+            h, rows = X["vid"], B * Lv
+        nlin = len(tw.m.encoder_mlp.linears())
+        units = []
+        for n in range(nlin):
+            last = n == nlin - 1
+            site = None if last else self._site(tw, n, "vid", self.DROP_BLOCK)
+            y = self._buf(k(f"mlp.y{n}"), (rows, d), T)
+            self._linear(h, rows, d, k(f"M{n}.w1"), k(f"M{n}.b1"), d, y, act=ACT_NONE if last else ACT_RELU, drop=site)
+            units.append(dict(x=h, y=y, scale=site.scale if site is not None else 1.0))
+            h = y
+        ts["mlp"] = dict(units=units, rows=rows, L=L)
+        if cfg.ablation == "CrossMLP":
+            out = self._buf(k("mlp.pool"), (B * Lv, d), T)
+            ops.adaptive_pool_fwd(h, B, L, d, Lv, out)
+            return out
+        return h
+
+    def _mlp_encoder_backward(self, tw, ts, dx_out):
+        """gradient w.r.t. the embedded tokens {side: tensor} from the gradient of the encoder output"""
+        cfg, k = self.cfg, tw.k
+        T, d = self.act_dtype, cfg.d_model
+        B, Lt, Lv = ts["B"], ts["Lt"], ts["Lv"]
+        m = ts["mlp"]
+        if m is None:
+            return {"vid": dx_out, "usr": None}
+        rows, L, units = m["rows"], m["L"], m["units"]
+        g = dx_out
+        if cfg.ablation == "CrossMLP":
+            g = self._buf(k("bw.mlp.dpool"), (rows, d), T)
+            ops.adaptive_pool_bwd(dx_out, B, L, d, Lv, g)
+        for n in reversed(range(len(units))):
+            u = units[n]
+            dx = self._buf(k(f"bw.mlp.dx{n & 1}"), (rows, d), T)
+            prev = units[n - 1] if n > 0 else None      # the unit whose dropout(relu(.)) output is this Linear's input
+            self._linear_bwd(g, u["x"], rows, d, d, k(f"M{n}.w1"), k(f"M{n}.b1"), dx,
+                             relu_out=prev["y"] if prev is not None else None, relu_scale=prev["scale"] if prev is not None else 1.0)
+            g = dx
+        if cfg.ablation == "CrossMLP":
+            gv = g.view(B, L, d)
+            du = self._buf(k("bw.mlp.du"), (B * Lt, d), T)
+            dv = self._buf(k("bw.mlp.dv"), (B * Lv, d), T)
+            du.view(B, Lt, d).copy_(gv[:, :Lt])
+            dv.view(B, Lv, d).copy_(gv[:, Lt:])
+            return {"vid": dv, "usr": du}
+        return {"vid": g, "usr": None}
 
     # ------------------------------------------------------------------ loss
     def loss(self, logits, gt, exposure_prob, inv_bsz, loss_cfg=None, bpr_scale=1.0, need_grad=True):
@@ -687,7 +779,11 @@ class Engine:
 
         dX = {"vid": dx_out, "usr": None}
         token_sides = ("vid", "usr") if self.uses_history else ("vid",)
-        for i in reversed(range(N - 1)):
+        if self.mlp_ablation:
+            dX = self._mlp_encoder_backward(tw, ts, dx_out)
+            if on_ready is not None and cfg.ablation != "w/oAtt":
+                on_ready(self.groups[k("M0.w1")][0])
+        for i in reversed(range(0 if self.mlp_ablation else N - 1)):
             lay = ts["layers"][i]
             sides, nq, cols, Xin = lay["sides"], lay["nq"], lay["cols"], lay["x"]
             dP1, dA = {}, {}
@@ -780,9 +876,13 @@ class Engine:
                                   self.g(k(f"{s}_ln.g")), self.g(k(f"{s}_ln.b")), self.red_ws, dxsum=self.g(k(f"{s}_proj.b")),
                                   dy_drop=ts[f"drop.emb.{s}"])
             else:
+                # one token per row (the ID tower's user token): d pe[0, :] is the plain column sum of dE, taken by the
+                # LayerNorm backward from its fp32 values (a separate pass over the bf16 dE loses digits to cancellation)
+                pe_fused = cfg.use_pe and Ls[s] == 1
                 ops.layernorm_bwd(dX[s], ts[f"emb_pre.{s}"], Ts[s], d, self.w(k(f"{s}_ln.g")), ts[f"emb_st.{s}"], None, de,
-                                  self.g(k(f"{s}_ln.g")), self.g(k(f"{s}_ln.b")), self.red_ws, dy_drop=ts[f"drop.emb.{s}"])
-            if cfg.use_pe:
+                                  self.g(k(f"{s}_ln.g")), self.g(k(f"{s}_ln.b")), self.red_ws, dy_drop=ts[f"drop.emb.{s}"],
+                                  dxsum=self.g(k(f"{s}_pe"))[:d] if pe_fused else None)
+            if cfg.use_pe and not (kind != "image" and Ls[s] == 1):
                 # d pe[l,:] = sum_b dE[b,l,:]  -> column sums of dE viewed as [B, L*d]
                 ops.colsum_acc(de, B, Ls[s] * d, Ls[s] * d, self.g(k(f"{s}_pe"))[: Ls[s] * d], self.red_ws)
             if kind == "image":
@@ -793,6 +893,7 @@ class Engine:
                 gtab = self.g(k(f"{s}_proj.w"))
                 ops.id_embed_bwd(de, ts["ids"][s], gtab.numel() // tw_cols, tw_cols, B, Ls[s], d, gtab,
                                  dframe_w=self.g(k("frameid.w")) if s == "vid" else None,
-                                 dframe_b=self.g(k("frameid.b")) if s == "vid" else None)
+                                 dframe_b=self.g(k("frameid.b")) if s == "vid" else None,
+                                 frame_pos=ts.get("frame_pos") if s == "vid" else None)
         if on_ready is not None:
             on_ready(self.groups[k("vid_proj.w")][0])

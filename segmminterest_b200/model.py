@@ -102,6 +102,34 @@ class SegFormerXEncoder(_Container):
             nn.Conv1d(lv[i - 1], lv[i], kernel_size=3, stride=2, padding=1) for i in range(1, len(lv))])
 
 
+class MLP_Block(_Container):
+    """Parameters of models/encoder.py:210-252 as SegFormerX builds it for the MLP ablations (:392-400): per hidden unit
+    Linear -> ReLU -> Dropout inside one nn.Sequential named `mlp`, then the output Linear -- so the Linear layers sit at
+    indices 0, 3, 6, ... of `mlp`, like in the reference's state_dict."""
+
+    def __init__(self, input_dim, hidden_units, output_dim, dropout_rates=0.0):
+        super().__init__()
+        layers = []
+        dims = [input_dim] + list(hidden_units)
+        for i in range(len(dims) - 1):
+            layers.append(nn.Linear(dims[i], dims[i + 1]))
+            layers.append(nn.ReLU())
+            if dropout_rates > 0:
+                layers.append(nn.Dropout(p=dropout_rates))
+        layers.append(nn.Linear(dims[-1], output_dim))
+        self.mlp = nn.Sequential(*layers)
+        self.dropout_p = float(dropout_rates)
+
+    def linears(self):
+        return [m for m in self.mlp if isinstance(m, nn.Linear)]
+
+    def linear_indices(self):
+        return [i for i, m in enumerate(self.mlp) if isinstance(m, nn.Linear)]
+
+
+MLP_ABLATIONS = ("SelfMLP", "CrossMLP", "w/oAtt")      # compared with == in the reference (encoder.py:392-400,503-511)
+
+
 class SegFormerX(_Container):
     """Constructor signature of models/encoder.py:330-350."""
 
@@ -112,11 +140,11 @@ class SegFormerX(_Container):
                  video_id_max=-1, use_pe=1):
         super().__init__()
         abl = getattr(model_cfg, "ablation_type", "ours") if model_cfg is not None else "ours"
-        if abl not in ("ours", "CrossAtt", "SelfAtt", "noUser", "noUser_SelfAtt"):
-            # 'noUser*' only changes what the DRIVER feeds (random user features, main...SegMM.py:275-277); the MLP ablations
-            # ('SelfMLP', 'CrossMLP', 'w/oAtt') replace the encoder by an MLP_Block and 'noPos' draws a random permutation
-            # of the frame positions per call (encoder.py:392-400,428-429): not built
-            raise NotImplementedError(f"ablation_type={abl!r}: 'ours', 'CrossAtt', 'SelfAtt' (and the driver-side 'noUser' variants) are built")
+        if abl not in ("ours", "CrossAtt", "SelfAtt", "noUser", "noUser_SelfAtt", "noPos") + MLP_ABLATIONS:
+            # every choice of the driver's --ablation_type (main...SegMM.py:532): 'noUser*' only changes what the DRIVER feeds
+            # (random user features, :275-277); 'SelfMLP' / 'CrossMLP' / 'w/oAtt' replace the encoder by an MLP_Block
+            # (encoder.py:392-400,503-511); 'noPos' draws a random permutation of the frame positions per call (:428-429)
+            raise NotImplementedError(f"ablation_type={abl!r} is not one of the reference's choices")
         if any(use_patch_merge) or any(s != 1 for s in sr_ratio_lvls):
             raise NotImplementedError("patch_merge / sr_ratio>1 are never enabled by the reference drivers")
         if any(d != d_model_in for d in d_model_lvls) or any(f != d_model_in for f in ff_dim_lvls) \
@@ -142,8 +170,14 @@ class SegFormerX(_Container):
         self.vid_ln = nn.LayerNorm(d_model_in, eps=1e-12)
         self.usr_ln = nn.LayerNorm(d_model_in, eps=1e-12)
         self.ablation_type = abl
-        self.encoder = SegFormerXEncoder(d_model_in, list(d_model_lvls), list(num_head_lvls), list(sr_ratio_lvls),
-                                         list(ff_dim_lvls), list(use_patch_merge), dropout, abl)
+        if abl == "CrossMLP":
+            self.encoder_mlp = MLP_Block(d_model_lvls[0], list(d_model_lvls[2:-2]), d_model_lvls[0], dropout_rates=dropout)
+            self.encoder_pooling = nn.AdaptiveAvgPool1d(40)
+        elif abl in ("SelfMLP", "w/oAtt"):
+            self.encoder_mlp = MLP_Block(d_model_lvls[0], list(d_model_lvls[1:-1]), d_model_lvls[0], dropout_rates=dropout)
+        else:
+            self.encoder = SegFormerXEncoder(d_model_in, list(d_model_lvls), list(num_head_lvls), list(sr_ratio_lvls),
+                                             list(ff_dim_lvls), list(use_patch_merge), dropout, abl)
         self.output_layers = list(output_layers)
         self.dropout_p = dropout
         self.d_model = d_model_in
@@ -254,7 +288,7 @@ class MultiScaleTemporalDetrLeaveFocal(nn.Module):
             cfg = EngineConfig(d_model=bb.d_model, nhead=bb.nhead, num_layers=bb.num_layers_enc,
                                din_vid=bb.input_vid_dim, din_usr=bb.input_usr_dim, max_usr_len=bb.max_usr_len,
                                max_vid_len=bb.max_vid_len, use_pe=bool(bb.use_pe), precision=self.precision,
-                               ablation=attn_ablation(bb.ablation_type))
+                               ablation=attn_ablation(bb.ablation_type), no_pos="noPos" in (bb.ablation_type or ""))
             self._engine = Engine(cfg, self, dev)
         self._engine.ensure_bound()
         return self._engine

@@ -8,7 +8,7 @@ import torch
 
 from . import _lib
 from .profiler import TIMER
-from ._lib import ACT_GELU, ACT_NONE, BF16, F32, GEMM_NN, GEMM_NT, GEMM_TN, IMPL_SIMT, IMPL_TC  # noqa: F401
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, BF16, F32, GEMM_NN, GEMM_NT, GEMM_TN, IMPL_SIMT, IMPL_TC  # noqa: F401
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
@@ -75,7 +75,7 @@ def gather_l1norm(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor, mas
 
 def gemm(layout, impl, A, lda, B, ldb, Cm, ldc, M, N, K, *, bias=None, act=ACT_NONE, preact=None, mul_gelu_grad=None,
          add=None, add_mod=0, ld_add=0, accumulate=False, split_k=1, in_dtype=None, out_dtype=None, save_act_grad=False,
-         mul_is_grad=False, drop=None):
+         mul_is_grad=False, drop=None, mul_scale=1.0):
     lib = _lib.load()
     a = _lib.GemmArgs()
     a.layout, a.impl = layout, impl
@@ -96,7 +96,8 @@ def gemm(layout, impl, A, lda, B, ldb, Cm, ldc, M, N, K, *, bias=None, act=ACT_N
     a.accumulate = 1 if accumulate else 0
     a.split_k = split_k
     a.save_act_grad = 1 if save_act_grad else 0
-    a.mul_is_grad = 1 if mul_is_grad else 0
+    a.mul_is_grad = int(mul_is_grad)        # 0: gelu'(operand), 1: operand is gelu'(z), 2: operand is a ReLU (+ dropout) output
+    a.mul_scale = float(mul_scale)
     a.drop = _drop(drop)
     cat = "gemm_tc" if impl == IMPL_TC else "gemm_simt"
     if TIMER.detail:
@@ -105,6 +106,21 @@ def gemm(layout, impl, A, lda, B, ldb, Cm, ldc, M, N, K, *, bias=None, act=ACT_N
     with TIMER.region(cat, 2.0 * M * N * K):
         rc = lib.mmi_gemm(C.byref(a), _stream())
     _lib.check(rc, "mmi_gemm")
+    LaunchCounter.n += 1
+
+
+def adaptive_pool_fwd(x, B, L, d, out_len, y):
+    """AdaptiveAvgPool1d(out_len) along the token axis: x [B, L, d] -> y [B, out_len, d]"""
+    with TIMER.region("pool"):
+        rc = _lib.load().mmi_adaptive_pool_fwd(x.data_ptr(), dt(x), B, L, d, out_len, y.data_ptr(), _stream())
+    _lib.check(rc, "mmi_adaptive_pool_fwd")
+    LaunchCounter.n += 1
+
+
+def adaptive_pool_bwd(dy, B, L, d, out_len, dx):
+    with TIMER.region("pool"):
+        rc = _lib.load().mmi_adaptive_pool_bwd(dy.data_ptr(), dt(dy), B, L, d, out_len, dx.data_ptr(), _stream())
+    _lib.check(rc, "mmi_adaptive_pool_bwd")
     LaunchCounter.n += 1
 
 
@@ -289,19 +305,21 @@ def loss_fwd_bwd(logits, gt, exposure_prob, *, inv_bsz, scalars, dlogits, use_fo
     LaunchCounter.n += 1
 
 
-def id_embed_fwd(table, ids, B, L, d, out, frame_w=None, frame_b=None, pe=None):
+def id_embed_fwd(table, ids, B, L, d, out, frame_w=None, frame_b=None, pe=None, frame_pos=None):
+    """frame_pos: fp32 [B, L] positions fed to the frame projection instead of 0..L-1 (the 'noPos' ablation)"""
     assert ids.dtype == torch.int64 and ids.is_contiguous() and table.dtype == torch.float32
+    assert frame_pos is None or (frame_pos.dtype == torch.float32 and frame_pos.is_contiguous() and frame_pos.numel() == B * L)
     with TIMER.region("id_embed"):
         rc = _lib.load().mmi_id_embed_fwd(table.data_ptr(), table.shape[0], table.shape[1], ids.data_ptr(), B, L, d, _ptr(frame_w),
-                                          _ptr(frame_b), _ptr(pe), out.data_ptr(), dt(out), _stream())
+                                          _ptr(frame_b), _ptr(pe), _ptr(frame_pos), out.data_ptr(), dt(out), _stream())
     _lib.check(rc, "mmi_id_embed_fwd")
     LaunchCounter.n += 1
 
 
-def id_embed_bwd(de, ids, n_rows, tw, B, L, d, dtable, dframe_w=None, dframe_b=None):
+def id_embed_bwd(de, ids, n_rows, tw, B, L, d, dtable, dframe_w=None, dframe_b=None, frame_pos=None):
     with TIMER.region("id_embed"):
         rc = _lib.load().mmi_id_embed_bwd(de.data_ptr(), dt(de), ids.data_ptr(), n_rows, tw, B, L, d, dtable.data_ptr(), _ptr(dframe_w),
-                                          _ptr(dframe_b), _stream())
+                                          _ptr(dframe_b), _ptr(frame_pos), _stream())
     _lib.check(rc, "mmi_id_embed_bwd")
     LaunchCounter.n += 1
 

@@ -227,7 +227,8 @@ def _oracle_drop(eng, H):
     return drop
 
 
-@pytest.mark.parametrize("name", ["model_small_dh32", "model_small_dh16", "model_small_crossatt", "model_small_selfatt"])
+@pytest.mark.parametrize("name", ["model_small_dh32", "model_small_dh16", "model_small_crossatt", "model_small_selfatt",
+                                  "model_small_selfmlp", "model_small_crossmlp"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_train_mode_model_vs_oracle_with_the_same_masks(dev, name, precision):
     from oracle import mmi_oracle

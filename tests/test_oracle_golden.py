@@ -128,7 +128,7 @@ def test_dropout_sites_match_reference_generator_stream(name):
 
 
 @pytest.mark.parametrize("name", ["model_both_small", "model_id_small", "model_both_fh0", "model_both_fh-1", "model_both_fh-2", "model_both_fh-3",
-                                  "model_both_bias", "model_image_bias"])
+                                  "model_both_bias", "model_image_bias", "model_both_nopos", "model_id_nopos"])
 def test_general_config_matches_reference(name):
     """ID-embedding inputs, two backbones + InteractionAggregation (the reference default 'both'),
     interestBPR: the oracle against the unmodified reference."""
@@ -140,9 +140,11 @@ def test_general_config_matches_reference(name):
             v.requires_grad_(True)
     kw = dict(nhead=cfg["nhead"], num_layers=cfg["num_layers_enc"], loss_type_list=tuple(cfg["loss_types"]),
               usr_id=torch.from_numpy(z["usr_id"]), vid_id=torch.from_numpy(z["vid_id"]), input_type=cfg["input_type"],
-              fusion_heads=cfg["fusion_heads"])
+              fusion_heads=cfg["fusion_heads"], ablation_type=cfg.get("ablation_type", "ours"))
     args = (torch.from_numpy(z["usr_image"]), torch.from_numpy(z["usr_mask"]), torch.from_numpy(z["vid_image"]),
             torch.from_numpy(z["vid_mask"]), torch.from_numpy(z["gt_in"]))
+    if cfg.get("draw_seed") is not None:      # 'noPos': replay the reference's torch.randperm stream (training forward, then inference)
+        torch.manual_seed(cfg["draw_seed"])
     out = mmi_oracle.forward(sd, *args, **kw)
     assert _rel(out["logits"].detach().numpy(), z["logits"]) < 1e-5
     assert abs(out["loss"].item() - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))

@@ -175,3 +175,49 @@ def test_c2_shapes_against_the_cpu_oracle():
                 assert e < (4 * tol if k.endswith(".bias") else 3 * tol), (k, e)
         del model
         torch.cuda.empty_cache()
+
+
+def test_c3_shapes_one_interaction_against_the_cpu_oracle():
+    """BASELINE config 3 end to end (history 200 videos x 20 segments = 4 000 tokens, Din 768, 6 layers, d 512, 16 heads):
+    ONE interaction -- what the CPU oracle finishes in about a minute (16 x 4 000 x 4 040 scores per layer and side, ~1 GB
+    of logits per block) -- through the fp32 and the bf16 path: logits, loss and gradients against the oracle.  The history
+    needs 32 key tiles, so this also runs the dq + dk/dv kernel pair that long histories fall back to."""
+    import os
+    from oracle import gather_oracle, mmi_oracle
+    from segmminterest_b200 import synth
+    wl = synth.WORKLOADS["c3"]
+    dev = torch.device("cuda:0")
+    n_rows, B = 8192, 1
+    table = synth.make_table(n_rows, wl.din, seed=1234)
+    ui, vi, gt = synth.make_teacher_batch(table, B, wl.lt, wl.segs_per_video, seed=33)
+    ui[0, 3901:] = -1                                    # a ragged tail: 99 padded history tokens inside the last key tiles
+    u, um = gather_oracle.gather_dense(table, ui)
+    c, cm = gather_oracle.gather_dense(table, vi)
+    u, c = gather_oracle.l1_normalise(u), gather_oracle.l1_normalise(c)
+    torch.set_num_threads(os.cpu_count())
+    ref = None
+    for precision, tol in (("fp32", FP32_TOL), ("bf16", BF16_TOL)):
+        model = _model(wl, precision)
+        sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        out = _run(model, u, um, c, cm, gt, dev)
+        out["loss"].backward()
+        live = mmi_oracle.live_param_names(list(sd.keys()), 6)
+        if ref is None:
+            osd = {k: v.requires_grad_(k in live) for k, v in sd.items()}
+            ref = mmi_oracle.forward(osd, torch.from_numpy(u), torch.from_numpy(um), torch.from_numpy(c), torch.from_numpy(cm),
+                                     torch.from_numpy(gt), nhead=16, num_layers=6)
+            ref["loss"].backward()
+        assert _rel(out["logits"].cpu().numpy(), ref["logits"].detach().numpy()) < tol
+        assert abs(out["loss"].item() - ref["loss"].item()) < tol * abs(ref["loss"].item())
+        got = np.concatenate([p.grad.cpu().numpy().ravel() for k, p in model.named_parameters() if k in live])
+        want = np.concatenate([osd[k].grad.numpy().ravel() for k, p in model.named_parameters() if k in live])
+        errs = sorted(((_rel(p.grad.cpu().numpy(), osd[k].grad.numpy()), k) for k, p in model.named_parameters() if k in live), reverse=True)
+        print(precision, "c3 whole-gradient error", _rel(got, want), "worst tensors", [(round(e, 5), k) for e, k in errs[:4]])
+        assert _rel(got, want) < tol
+        if precision == "fp32":
+            for e, k in errs:
+                assert e < 3 * tol, (k, e)
+        else:
+            assert errs[len(errs) // 2][0] < tol
+        del model
+        torch.cuda.empty_cache()

@@ -32,10 +32,18 @@ import torch  # noqa: E402
 from segmminterest_b200 import synth  # noqa: E402
 
 
-def model_args(precision):
-    return SimpleNamespace(debug=0, input_type={"user": "image", "photo": "image"}, d_model=512, nhead=16,
-                           learnable_bias=0, exposure_prob=[1.0] * 40, fusion_heads=2, loss_type_list=["focal"],
-                           loss_weight={"focal": 1.0}, mask_loss=0, num_layers_enc=6, ablation_type="ours", use_pe=1,
+N_USERS, N_ITEMS = 1903, 352494      # the reference reader's table sizes (utils/dataloader_SegMM.py:78-79)
+
+
+def model_args(precision, model="image"):
+    """image: the single image backbone + focal (BCE family) the metric is quoted on (SURVEY 8d);
+    both: the reference's DEFAULT configuration (main...SegMM.py:506-509,527): image backbone + ID backbone fused by
+    InteractionAggregation(2 heads), interestBPR, embedding tables of the full dataset's size."""
+    it = {"user": "both", "photo": "both"} if model == "both" else {"user": "image", "photo": "image"}
+    return SimpleNamespace(debug=0, input_type=it, d_model=512, nhead=16,
+                           learnable_bias=0, exposure_prob=[1.0] * 40, fusion_heads=2,
+                           loss_type_list=["interestBPR"] if model == "both" else ["focal"],
+                           loss_weight={"focal": 1.0, "interestBPR": 1.0}, mask_loss=0, num_layers_enc=6, ablation_type="ours", use_pe=1,
                            mmi_precision=precision)
 
 
@@ -163,6 +171,76 @@ def reference_arm(args, wl):
     print(json.dumps(line), flush=True)
 
 
+def fp32_leg(args, wl, table, dev, batch=64, steps=2):
+    """The strict-parity fp32 mode (the reference's own precision) on the same workload at a reduced batch."""
+    from segmminterest_b200.model import build_model
+    from segmminterest_b200.train import TrainStep
+    torch.manual_seed(42)
+    m = build_model(model_args("fp32"), din=wl.din, max_usr_len=wl.lt).to(dev)
+    m.train(args.dropout > 0)
+    ts = TrainStep(m, table, global_batch=batch, dropout=args.dropout)
+    u, v, gt = synth.make_indices(batch, wl.lt, wl.segs_per_video, wl.n_rows, seed=4242)
+    u, v, gt = torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev), torch.from_numpy(gt).to(dev)
+    ts.step(u, v, gt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ts.step(u, v, gt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del ts, m
+    torch.cuda.empty_cache()
+    return {"value": batch / (ms * 1e-3), "unit": "interactions/s", "ms_per_step": ms, "batch": batch,
+            "note": "fp32 FFMA path (logits / gradients within 1e-4 of the reference), same workload shapes, reduced batch"}
+
+
+def loader_leg(dev, n=256):
+    """Batch construction, ours vs the reference's Python loader, on BASELINE config 1: the first 256
+    train interactions of SegMM_inter_sample.csv as prepared by the reference's own reader (tests/golden/config1.npz).
+    ours: HostFrameIndex (vectorised index build) + device gather + pad + mask, synchronised per batch;
+    reference: the oracle's restatement of FrameDatasetSeq_SegMM._getitem + DataCollator on the host cores."""
+    import io
+    import random
+    import pandas as pd
+    from oracle import gather_oracle
+    from segmminterest_b200.loader import DeviceFrameLoader
+    path = os.path.join(ROOT, "tests", "golden", "config1.npz")
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    meta = json.loads(str(z["meta"]))
+    df = pd.read_csv(io.BytesIO(z["files/train_his.csv"].tobytes()), sep="\t").reset_index(drop=True).sort_values(by=["user_id", "time_ms"])
+    lineid = json.loads(z["files/SegMM_photoidframeid2lineid.json"].tobytes())
+    uid = json.loads(z["files/user_input_dict.json"].tobytes())
+    u2i, i2i = json.loads(z["files/second_map_user2id.json"].tobytes()), json.loads(z["files/second_map_item2id.json"].tobytes())
+    table = np.random.default_rng(meta["table_seed"]).standard_normal((meta["n_rows"], meta["din"]), dtype=np.float32)
+    corpus = SimpleNamespace(data_df={"train": df.iloc[:n]}, user_input_dict=uid)
+    # reference port
+    rows = df.iloc[:n].to_dict("records")
+    random.seed(42)
+    t0 = time.perf_counter()
+    batch = gather_oracle.collate_port([gather_oracle.getitem_port(r, lineid, uid, table, u2i, i2i) for r in rows])
+    t_ref = time.perf_counter() - t0
+    # ours
+    tab_d = torch.from_numpy(table).to(dev)
+    ldr = DeviceFrameLoader(corpus, lineid, tab_d, phase="train", batch_size=n, user2id=u2i, item2id=i2i)
+    random.seed(42)
+    b0 = next(iter(ldr))
+    torch.cuda.synchronize()
+    same = bool(np.array_equal(b0["user"].cpu().numpy(), batch["user"]) and np.array_equal(b0["photo"].cpu().numpy(), batch["photo"]))
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        random.seed(42)
+        b0 = next(iter(ldr))
+        torch.cuda.synchronize()
+    t_ours = (time.perf_counter() - t0) / reps
+    return {"ours_samples_per_s": n / t_ours, "reference_port_samples_per_s": n / t_ref, "sample": f"{n} interactions of config 1 (Lt 100, Din 1024)",
+            "batches_identical": same, "note": "one-time parse of the line-id map / CSV columns excluded on both sides"}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -177,6 +255,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0)
     ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: seconds of CPU work the whole run is sized for")
+    ap.add_argument("--model", default="image", choices=["image", "both"],
+                    help="image: single image backbone + focal (the quoted configuration); both: the reference's default two-tower model")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp32-mode and loader legs (multi-GPU scaling runs)")
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="dropout probability of every nn.Dropout site (reference training default 0.1); 0 = eval()-mode arithmetic")
     args = ap.parse_args()
@@ -202,16 +283,22 @@ def main():
     W = max(3, args.warmup)
     K = max(1, args.steps)
     B = args.batch or wl.batch
-    if args.workload in ("c3", "c4") and not args.batch:
+    strong = args.workload in ("c3", "c4") and not args.batch      # BASELINE: global batch 4 096 / 8 192 split over the GPUs
+    if strong:
         B = max(1, wl.batch // max(world, 1))
     Lt = wl.lt
 
     torch.manual_seed(42)
-    model = build_model(model_args(args.precision), din=wl.din, max_usr_len=Lt).to(dev)
+    both = args.model == "both"
+    model = build_model(model_args(args.precision, args.model), din=wl.din, max_usr_len=Lt, n_users=N_USERS, n_items=N_ITEMS).to(dev)
     model.train(args.dropout > 0)   # train(): every nn.Dropout site of the reference is live (counter-based masks, csrc/dropout.cuh)
     g = torch.Generator(device=dev).manual_seed(1234)
     table = torch.randn(wl.n_rows, wl.din, generator=g, device=dev, dtype=torch.float32)
     ts = TrainStep(model, table, lr=1e-3, weight_decay=1e-4, max_norm=None, global_batch=B * world, dropout=args.dropout)
+    ts.gather.valid_hint = {"usr": B * Lt, "vid": B * min(wl.segs_per_video, 40)}     # full histories: algorithmic gather bytes
+    idg = torch.Generator(device=dev).manual_seed(77 + rank)
+    ids = (dict(usr_id=torch.randint(1, N_USERS + 1, (B,), generator=idg, device=dev), vid_id=torch.randint(1, N_ITEMS + 1, (B,), generator=idg, device=dev))
+           if both else {})
 
     n_batches = 4
     host, devb = [], []
@@ -236,7 +323,7 @@ def main():
 
     mb = args.micro_batch
     for i in range(W):
-        ts.step(*devb[i % n_batches], micro_batch=mb)
+        ts.step(*devb[i % n_batches], micro_batch=mb, **ids)
     barrier()
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------
@@ -248,7 +335,7 @@ def main():
     barrier()
     e0.record()
     for i in range(K):
-        scal = ts.step(*devb[i % n_batches], micro_batch=mb)
+        scal = ts.step(*devb[i % n_batches], micro_batch=mb, **ids)
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -258,11 +345,11 @@ def main():
     value = K * B * world / (ms_total * 1e-3)
 
     # ---- timed region 2: end to end from pinned host buffers, loss read back every step -----------
-    ts.step_host(*host[0], staging, micro_batch=mb)
+    ts.step_host(*host[0], staging, micro_batch=mb, **ids)
     barrier()
     e0.record()
     for i in range(K):
-        ts.step_host(*host[i % n_batches], staging, micro_batch=mb)
+        ts.step_host(*host[i % n_batches], staging, micro_batch=mb, **ids)
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
@@ -273,11 +360,11 @@ def main():
     drop_off = None
     if args.dropout > 0:
         ts.dropout = 0.0
-        ts.step(*devb[0], micro_batch=mb)
+        ts.step(*devb[0], micro_batch=mb, **ids)
         barrier()
         e0.record()
         for i in range(K):
-            ts.step(*devb[i % n_batches], micro_batch=mb)
+            ts.step(*devb[i % n_batches], micro_batch=mb, **ids)
         e1.record()
         barrier()
         ms_off = max_over_ranks(e0.elapsed_time(e1))
@@ -290,7 +377,7 @@ def main():
     TIMER.reset()
     barrier()
     for i in range(K):
-        ts.step(*devb[i % n_batches], micro_batch=mb)
+        ts.step(*devb[i % n_batches], micro_batch=mb, **ids)
     summ = TIMER.summary()
     TIMER.enabled = False
     TIMER.detail = False
@@ -317,9 +404,10 @@ def main():
     roof["avg_launch_ms"] = d["ms"] / d["launches"]
     roof["launches_per_step"] = d["launches"] // K
     if dom.startswith("attn"):
-        # second yardstick for the attention kernels: one ex2 per score (dq and dk/dv recompute P, so every launch pays
-        # B*H*Lq*Lk of them) against the measured MUFU rate of 16 ex2 / clk / SM (tools/micro/pipe_rates.cu)
-        per_flop = {"attn_fwd": 1.0 / (4 * 32), "attn_bwd_dq": 1.0 / (6 * 32), "attn_bwd_dkv": 1.0 / (8 * 32)}[dom.split(" ")[0]]
+        # second yardstick for the attention kernels: one ex2 per score (the dq / dk,dv pair recomputes P, so each of its
+        # launches pays B*H*Lq*Lk of them; the one-launch backward pays them once for 10 * dh FLOPs per score) against the measured MUFU rate of 16 ex2 / clk / SM (tools/micro/pipe_rates.cu)
+        per_flop = {"attn_fwd": 1.0 / (4 * 32), "attn_bwd_dq": 1.0 / (6 * 32), "attn_bwd_dkv": 1.0 / (8 * 32), "attn_bwd_all": 1.0 / (10 * 32),
+                    "attn_bwd_fused": 1.0 / (10 * 32)}[dom.split(" ")[0]]
         ex2_per_s = d["work"] * per_flop / (d["ms"] * 1e-3)
         sm_hz = ((clocks or {}).get("sm_mhz") or 1800.0) * 1e6
         roof["mufu"] = {"achieved": ex2_per_s / 1e12, "peak": 16 * 148 * sm_hz / 1e12, "unit": "Tex2/s",
@@ -350,10 +438,22 @@ def main():
         tf = gs["work"] / (gs["ms"] * 1e-3) / 1e12
         gemm_roof = {"achieved": tf, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": tf / pk["tf_sust"], "ms_per_step": gs["ms"] / K}
 
+    # ---- whole-step roofline: algorithmic model FLOPs (live compute, valid tokens) / step time / sustained bf16 peak
+    fl = synth.model_flops(Lt, min(wl.segs_per_video, 40), wl.din) * (1 if not both else 1)      # image backbone (the ID tower adds < 8 %)
+    step_roof = {"flops_per_interaction": fl, "achieved": fl * B * world / (ms_total / K * 1e-3) / 1e12, "peak": pk["tf_sust"] * world,
+                 "unit": "TFLOP/s", "bound": "tensor", "note": "SURVEY 8d formula x interactions / step time, against the sustained bf16 peak x GPUs"}
+    step_roof["frac"] = step_roof["achieved"] / step_roof["peak"]
+
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras["fp32_mode"] = fp32_leg(args, wl, table, dev)
+        extras["loader"] = loader_leg(dev)
+
     line = {"metric": "train_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": wl.name, "per_gpu_batch": B, "micro_batch": mb or B, "global_batch": B * world, "hist_len": Lt, "cand_pad": 40,
+            "config": {"workload": wl.name, "model": ("both: image + ID backbones, InteractionAggregation(2), interestBPR, tables 1904 x 512 / 352495 x 256"
+                                                      if both else "image backbone, focal"), "per_gpu_batch": B, "micro_batch": mb or B, "global_batch": B * world, "hist_len": Lt, "cand_pad": 40,
                        "cand_valid": wl.segs_per_video, "din": wl.din, "d_model": 512, "heads": 16, "layers": 6,
                        "table_rows": wl.n_rows, "parallelism": f"dp{world}", "optimizer": "AdamW lr1e-3 wd1e-4, no clip (the reference's clip_grad_norm_ walks an exhausted generator)",
                        "dropout": (f"{args.dropout} at every reference site (train() mode; counter-based masks, realised drop probability "
@@ -361,7 +461,9 @@ def main():
             "e2e": {"value": e2e_val, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "gather_roofline": gather_roof, "gemm_roofline": gemm_roof,
+            "step_roofline": step_roof,
             "kernel_breakdown": breakdown, "loss_last": loss_last, "use_tc": bool(ts.engine.use_tc), "dropout_off": drop_off}
+    line.update(extras)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             val, b, cores, ms = run_cpu_sample(wl, args.cpu_budget, 2, 1, dropout=args.dropout)

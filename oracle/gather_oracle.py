@@ -85,3 +85,33 @@ def l1_normalise(x: np.ndarray) -> np.ndarray:
     x = x.astype(np.float32)
     n = np.abs(x).sum(-1, keepdims=True, dtype=np.float32)
     return x / (n + np.float32(1e-6))
+
+
+def getitem_port(row: dict, lineid_map: dict, user_input_dict: dict, table: np.ndarray, user2id: dict, item2id: dict) -> dict:
+    """One sample of FrameDatasetSeq_SegMM._getitem (utils/dataloader_SegMM.py:281-362) restated with the functions above:
+    per-segment f-string keys + dict lookups + one table-row copy per hit, np.vstack, zero pad, mask; users with more than
+    100 tokens are sub-sampled with random.sample exactly like the reference.  `row` holds the columns of a *_his.csv row.
+    Used by bench.py's loader baseline (samples/s of the reference's Python loader on the box's host cores)."""
+    import random
+    hist_items = parse_int_list(row["history_items"]) if row["history_lengths"] > 0 else []
+    hist_play = parse_int_list(row["history_playing"]) if row["history_lengths"] > 0 else []
+    out = {"play_time": int(row["playing_time_x"] / 5000), "duration": int(row["duration_ms"] / 5000)}
+    urows = history_rows(row["user_id"], hist_items, hist_play, lineid_map, user_input_dict)
+    feats = np.array([table[r, :] for r in urows])                       # one row read per hit, like the memmap reads (:327,338)
+    if feats.shape[0] > USER_MAX:
+        feats = feats[random.sample(range(feats.shape[0]), USER_MAX)]
+    user = np.zeros((USER_MAX, table.shape[1]), dtype=table.dtype)
+    user[:feats.shape[0]] = feats
+    umask = np.zeros(USER_MAX, dtype=bool)
+    umask[:feats.shape[0]] = True
+    out.update(user=user, user_mask=umask, user_id=row["user_id"], user_identity_id=int(user2id[str(row["user_id"])]))
+    vrows = candidate_rows(row["video_id"], row["duration_ms"], lineid_map)
+    photo, pmask = gather_pad_mask(table, vrows, PHOTO_MAX)
+    out.update(photo=photo, photo_mask=pmask, photo_id=row["video_id"], photo_identity_id=int(item2id[str(row["video_id"])]),
+               time_ms=row["time_ms"], label=pad_labels(row["label_1D"]))
+    return out
+
+
+def collate_port(samples: list) -> dict:
+    """DataCollator.__call__ (utils/dataloader_SegMM.py:370-382) without the prints: np.stack per key"""
+    return {k: np.stack([s_[k] for s_ in samples]) for k in samples[0]}

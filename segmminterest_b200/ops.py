@@ -61,12 +61,16 @@ class LaunchCounter:
 
 
 def gather_l1norm(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor, mask: torch.Tensor | None,
-                  normalise: bool = True):
+                  normalise: bool = True, n_valid: int | None = None):
+    """n_valid (profiling only): number of ids >= 0, so that the timer credits the ALGORITHMIC bytes -- table rows are read
+    for valid ids only; every output row, id and mask byte is written / read."""
     _need_cuda(table, idx, out)
     lib = _lib.load()
     assert idx.dtype == torch.int32 and idx.is_contiguous() and table.is_contiguous() and out.is_contiguous()
     n_tokens = idx.numel()
-    with TIMER.region("gather", float(n_tokens) * table.shape[1] * (table.element_size() + out.element_size())):
+    nv_ = n_tokens if n_valid is None else int(n_valid)
+    work = float(table.shape[1]) * (nv_ * table.element_size() + n_tokens * out.element_size()) + 5.0 * n_tokens
+    with TIMER.region("gather", work):
         rc = lib.mmi_gather_l1norm_fwd(table.data_ptr(), dt(table), table.shape[0], table.shape[1], idx.data_ptr(), n_tokens,
                                        out.data_ptr(), dt(out), _ptr(mask), 1 if normalise else 0, _stream())
     _lib.check(rc, "mmi_gather_l1norm_fwd")

@@ -31,6 +31,17 @@ class Workload:
         return self.hist_videos * self.segs_per_video
 
 
+def model_flops(nt: int, nv: int, din: int, d: int = 512, n_layers: int = 6, train: bool = True) -> float:
+    """Algorithmic FLOPs of ONE interaction through one image backbone: live compute only, valid
+    tokens only (nt history / nv candidate tokens), MAC = 2 FLOP; the dead layer N-1 and pad rows are not credited.
+      MACs_fwd = (nt+nv) Din d  +  (N-2) [9 (nt+nv) d^2 + 2 (nt+nv)^2 d]  +  [(7 nv + 2 nt) d^2 + 2 nv (nv+nt) d]  +  nv d
+    (input projection; N-2 full layers = 12 q/k/v projections + 2 output projections + 2 x 2 FFN + QK^T + PV; the
+    candidate-only layer N-2; head).  Training = 3 x forward."""
+    t = nt + nv
+    macs = t * din * d + (n_layers - 2) * (9 * t * d * d + 2 * t * t * d) + ((7 * nv + 2 * nt) * d * d + 2 * nv * (nv + nt) * d) + nv * d
+    return 2.0 * macs * (3.0 if train else 1.0)
+
+
 WORKLOADS = {
     # configs[0]: reference shapes (Lt=100, Din=1024)
     "c1": Workload("c1_segmm_reference_shapes", 1024, 10, 10, 1024, 1 << 17),

@@ -23,6 +23,7 @@ class DeviceGather:
         self.table = table.contiguous()
         self.out_dtype = out_dtype
         self._buf = {}
+        self.valid_hint = {}     # profiling only: tag -> number of valid ids per call (host-known; see ops.gather_l1norm)
 
     def __call__(self, idx: torch.Tensor, tag: str, normalise: bool = True):
         B, L = idx.shape
@@ -31,7 +32,7 @@ class DeviceGather:
             self._buf[key] = (torch.empty(B, L, self.table.shape[1], device=idx.device, dtype=self.out_dtype),
                               torch.empty(B, L, device=idx.device, dtype=torch.uint8))
         out, mask = self._buf[key]
-        ops.gather_l1norm(self.table, idx, out, mask, normalise)
+        ops.gather_l1norm(self.table, idx, out, mask, normalise, n_valid=self.valid_hint.get(tag))
         return out, mask.view(torch.bool)
 
 
@@ -118,12 +119,12 @@ class TrainStep:
             if t.numel() and int(t.max()) >= n:
                 raise IndexError(f"row id {int(t.max())} is past the embedding table ({n} rows)")
 
-    def step_host(self, usr_idx_h, vid_idx_h, gt_h, dev_bufs, micro_batch: int = 0):
+    def step_host(self, usr_idx_h, vid_idx_h, gt_h, dev_bufs, micro_batch: int = 0, usr_id=None, vid_id=None):
         """End-to-end variant: pinned host index/label buffers -> H2D inside the call, loss read
         back to the host (one D2H + sync), as the reference loop's `loss.item()` does."""
         u, v, g = dev_bufs
         u.copy_(usr_idx_h, non_blocking=True)
         v.copy_(vid_idx_h, non_blocking=True)
         g.copy_(gt_h, non_blocking=True)
-        scal = self.step(u, v, g, micro_batch=micro_batch)
+        scal = self.step(u, v, g, usr_id=usr_id, vid_id=vid_id, micro_batch=micro_batch)
         return float(scal[3].item())

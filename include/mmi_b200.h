@@ -286,6 +286,13 @@ int mmi_id_embed_fwd(const float* table, int64_t n_rows, int tw, const int64_t* 
                      int out_dtype, mmi_stream_t stream);
 int mmi_id_embed_bwd(const void* de, int dtype, const int64_t* ids, int64_t n_rows, int tw, int B, int L, int d,
                      float* dtable, float* dframe_w, float* dframe_b, const float* frame_pos, mmi_stream_t stream);
+/* Row-sparse table gradient for data parallelism (the reference has no DP and keeps nn.Embedding's dense gradient):
+ * mmi_id_rows_bwd writes rows[b, c] = sum_l de[b,l,c] (c < tw; fp32 [B, tw]) instead of adding into the table, the frame
+ * projection's gradients are accumulated as in mmi_id_embed_bwd; after the ranks have exchanged (ids, rows),
+ * mmi_scatter_rows_add does dtable[ids[i], :] += rows[i, :] for the gathered n = world x B rows.                  */
+int mmi_id_rows_bwd(const void* de, int dtype, int tw, int B, int L, int d, float* rows, float* dframe_w, float* dframe_b,
+                    const float* frame_pos, mmi_stream_t stream);
+int mmi_scatter_rows_add(const int64_t* ids, const float* rows, int64_t n, int tw, int64_t n_rows, float* dtable, mmi_stream_t stream);
 /* InteractionAggregation (models/decoder_leave_focal.py:411-423) after the two X_h W_h GEMMs:
  *   out[r] = sum_c T[r,c] * Y[r,c] (+ add1[r]) (+ add2[r]);   backward: dT = g*Y, dY = g*T (+ dy_add), g *= gscale[0]. */
 int mmi_rowdot_fwd(const void* t, int64_t ldt, const void* y, int64_t ldy, int dtype, int64_t R, int C,

@@ -91,6 +91,8 @@ _SIGS = {
     "mmi_loss_fwd_bwd": (C.c_int, [C.POINTER(LossArgs), c_p]),
     "mmi_id_embed_fwd": (C.c_int, [c_p, i64, C.c_int, c_p, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, c_p, c_p, C.c_int, c_p]),
     "mmi_id_embed_bwd": (C.c_int, [c_p, C.c_int, c_p, i64, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, c_p, c_p]),
+    "mmi_id_rows_bwd": (C.c_int, [c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p, c_p, c_p, c_p]),
+    "mmi_scatter_rows_add": (C.c_int, [c_p, c_p, i64, C.c_int, i64, c_p, c_p]),
     "mmi_rowdot_fwd": (C.c_int, [c_p, i64, c_p, i64, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p]),
     "mmi_rowdot_bwd": (C.c_int, [c_p, c_p, c_p, i64, c_p, i64, C.c_int, i64, C.c_int, c_p, c_p, c_p, c_p]),
     "mmi_clip_adamw_workspace": (i64, [i64]),

@@ -58,6 +58,42 @@ __global__ void __launch_bounds__(256) id_embed_bwd_kernel(const TI* __restrict_
   }
 }
 
+// Row-sparse form of the table gradient (data parallelism): rows[b, c] = sum_l de[b, l, c] for c < tw -- ONE row
+// per interaction, no atomics on the table -- so that ranks exchange (ids, rows) instead of all-reducing a dense
+// [n_rows, tw] table (361 MB for the reference's 352 495 x 256 video table).  The frame projection's gradients are dense
+// parameters and are accumulated as in id_embed_bwd_kernel.
+template <typename TI>
+__global__ void __launch_bounds__(256) id_rows_bwd_kernel(const TI* __restrict__ de, int tw, int B, int L, int d, float* __restrict__ rows,
+                                                          float* __restrict__ dframe_w, float* __restrict__ dframe_b,
+                                                          const float* __restrict__ frame_pos) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float s = 0.f, sl = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const float g = to_f32(de[((int64_t)b * L + l) * d + c]);
+      s += g;
+      sl += (frame_pos ? frame_pos[(int64_t)b * L + l] : (float)l) * g;
+    }
+    if (c < tw) rows[(int64_t)b * tw + c] = s;
+    else {
+      if (dframe_w) atomicAdd(dframe_w + (c - tw), sl);
+      if (dframe_b) atomicAdd(dframe_b + (c - tw), s);
+    }
+  }
+}
+// dtable[ids[i], :] += rows[i, :] for i < n (duplicates of an id meet in atomicAdd); ids are clamped like id_embed_fwd
+__global__ void __launch_bounds__(256) scatter_rows_add_kernel(const int64_t* __restrict__ ids, const float* __restrict__ rows, int64_t n, int tw,
+                                                               int64_t n_rows, float* __restrict__ dtable) {
+  const int64_t total = n * tw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r_ = i / tw;
+    const int c = (int)(i - r_ * tw);
+    int64_t r = ids[r_];
+    r = r < 0 ? 0 : (r >= n_rows ? n_rows - 1 : r);
+    atomicAdd(dtable + r * tw + c, rows[i]);
+  }
+}
+
 // out[r] = sum_c T[r,c] * Y[r,c] (+ add1[r]) (+ add2[r]);  warp per row, C % 4 == 0
 template <typename T>
 __global__ void __launch_bounds__(256) rowdot_fwd_kernel(const T* __restrict__ t, int64_t ldt, const T* __restrict__ y, int64_t ldy, int64_t R,
@@ -197,6 +233,30 @@ extern "C" int mmi_id_embed_bwd(const void* de, int dtype, const int64_t* ids, i
   if (dtype == MMI_F32) id_embed_bwd_kernel<float><<<B, 256, 0, st>>>((const float*)de, ids, n_rows, tw, B, L, d, dtable, dframe_w, dframe_b, frame_pos);
   else if (dtype == MMI_BF16) id_embed_bwd_kernel<__nv_bfloat16><<<B, 256, 0, st>>>((const __nv_bfloat16*)de, ids, n_rows, tw, B, L, d, dtable, dframe_w, dframe_b, frame_pos);
   else { set_error("id_embed_bwd: bad dtype %d", dtype); return MMI_EINVAL; }
+  MMI_CHECK_LAUNCH();
+  return MMI_OK;
+}
+
+extern "C" int mmi_id_rows_bwd(const void* de, int dtype, int tw, int B, int L, int d, float* rows, float* dframe_w, float* dframe_b,
+                               const float* frame_pos, mmi_stream_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMI_CHECK_ARG(de && rows, "id_rows_bwd: null pointer");
+  MMI_CHECK_ARG(B > 0 && L > 0 && d > 0 && tw > 0 && tw <= d, "id_rows_bwd: bad sizes");
+  if (dtype == MMI_F32) id_rows_bwd_kernel<float><<<B, 256, 0, st>>>((const float*)de, tw, B, L, d, rows, dframe_w, dframe_b, frame_pos);
+  else if (dtype == MMI_BF16) id_rows_bwd_kernel<__nv_bfloat16><<<B, 256, 0, st>>>((const __nv_bfloat16*)de, tw, B, L, d, rows, dframe_w, dframe_b, frame_pos);
+  else { set_error("id_rows_bwd: bad dtype %d", dtype); return MMI_EINVAL; }
+  MMI_CHECK_LAUNCH();
+  return MMI_OK;
+}
+
+extern "C" int mmi_scatter_rows_add(const int64_t* ids, const float* rows, int64_t n, int tw, int64_t n_rows, float* dtable, mmi_stream_t stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  MMI_CHECK_ARG(ids && rows && dtable, "scatter_rows_add: null pointer");
+  MMI_CHECK_ARG(n >= 0 && tw > 0 && n_rows > 0, "scatter_rows_add: bad sizes");
+  if (n == 0) return MMI_OK;
+  int64_t grid = (n * tw + 255) / 256;
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  scatter_rows_add_kernel<<<(unsigned)grid, 256, 0, st>>>(ids, rows, n, tw, n_rows, dtable);
   MMI_CHECK_LAUNCH();
   return MMI_OK;
 }

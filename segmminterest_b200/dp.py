@@ -11,9 +11,12 @@ import torch.distributed as dist
 
 
 class GradBuckets:
-    def __init__(self, flat_grad: torch.Tensor, group=None, bucket_bytes: int = 25 << 20):
+    def __init__(self, flat_grad: torch.Tensor, group=None, bucket_bytes: int = 25 << 20, skip=()):
+        """skip: [(offset, numel), ...] ranges of the flat buffer that are NOT all-reduced (embedding tables whose
+        gradients travel row-sparse, see exchange_rows)."""
         self.flat = flat_grad
         self.group = group
+        self.skip = sorted((int(o), int(o) + int(n)) for o, n in skip)
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -40,9 +43,14 @@ class GradBuckets:
             return
         # all_reduce(async_op=True) orders the NCCL kernel after everything already queued on the
         # current (compute) stream and runs it on the process group's own stream.
-        w = dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._works.append(w)
-        self.n_collectives += 1
+        a = lo
+        for s0, s1 in self.skip + [(hi, hi)]:            # the pieces of [lo, hi) outside the skipped ranges
+            b = min(max(s0, a), hi)
+            if b > a:
+                w = dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self._works.append(w)
+                self.n_collectives += 1
+            a = max(a, min(s1, hi))
         self._hi = lo
 
     def finish(self):
@@ -53,6 +61,20 @@ class GradBuckets:
         for w in self._works:
             w.wait()
         self._works = []
+
+
+def exchange_rows(ids: torch.Tensor, rows: torch.Tensor, group=None):
+    """Row-sparse gradient exchange for an embedding table: every rank contributes its B (id, gradient row)
+    pairs; returns the concatenation over ranks ([world * B] ids, [world * B, tw] rows).  Payload per rank B x (8 + 4 tw)
+    bytes instead of a dense n_rows x tw x 4 all-reduce (1 MB against 361 MB for the reference's video table at B = 1024)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return ids, rows
+    all_ids = torch.empty(world * ids.numel(), dtype=ids.dtype, device=ids.device)
+    all_rows = torch.empty(world * rows.shape[0], rows.shape[1], dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_rows, rows.contiguous(), group=group)
+    return all_ids, all_rows
 
 
 def shard_rows(n_rows: int, rank: int, world: int):

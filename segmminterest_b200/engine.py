@@ -133,6 +133,10 @@ class Engine:
         self._drop_cur = None      # (thr8, scale, call) of the forward in flight, None = off
         self._ws = {}
         self._saved = None
+        # data parallelism: ID-table gradients leave backward as (ids, rows) pairs instead of being added into the dense
+        # table gradient; TrainStep exchanges them between the ranks and scatters the union (dp.exchange_rows)
+        self.sparse_tables = False
+        self.table_rows = []       # [(group key, tw, ids [B], rows [B, tw])] of the backward in flight
         self.use_tc = cfg.precision == "bf16" and bool(_lib.load().mmi_has_tc())
         # attention backward on the tensor-core path: "all" = one CTA per (b, h) owning every key (default, <= 640 keys),
         # "fused" = one kernel per key block with dQ reduced through an fp32 accumulator (measured slower than the pair it
@@ -148,6 +152,16 @@ class Engine:
     @property
     def mlp_ablation(self):
         return self.cfg.ablation in MLP_ABLATIONS
+
+    def table_groups(self):
+        """[(offset, numel)] of the embedding tables inside the flat buffers (towers with ID inputs)"""
+        out = []
+        for tw in self.towers:
+            for s_, kind in (("vid", tw.vid_kind), ("usr", tw.usr_kind)):
+                key = tw.k(f"{s_}_proj.w")
+                if kind == "id" and key in self.groups:
+                    out.append(self.groups[key])
+        return out
 
     def layer_plan(self, i):
         """(query sides that are computed in layer i, {token side: [(block, j), ...] projections in buffer order})."""
@@ -891,9 +905,16 @@ class Engine:
             else:
                 tw_cols = d // 2 if s == "vid" else d
                 gtab = self.g(k(f"{s}_proj.w"))
-                ops.id_embed_bwd(de, ts["ids"][s], gtab.numel() // tw_cols, tw_cols, B, Ls[s], d, gtab,
-                                 dframe_w=self.g(k("frameid.w")) if s == "vid" else None,
-                                 dframe_b=self.g(k("frameid.b")) if s == "vid" else None,
-                                 frame_pos=ts.get("frame_pos") if s == "vid" else None)
+                if self.sparse_tables:
+                    rows = torch.empty(B, tw_cols, device=self.device, dtype=torch.float32)
+                    ops.id_rows_bwd(de, tw_cols, B, Ls[s], d, rows, dframe_w=self.g(k("frameid.w")) if s == "vid" else None,
+                                    dframe_b=self.g(k("frameid.b")) if s == "vid" else None,
+                                    frame_pos=ts.get("frame_pos") if s == "vid" else None)
+                    self.table_rows.append((k(f"{s}_proj.w"), tw_cols, ts["ids"][s], rows))
+                else:
+                    ops.id_embed_bwd(de, ts["ids"][s], gtab.numel() // tw_cols, tw_cols, B, Ls[s], d, gtab,
+                                     dframe_w=self.g(k("frameid.w")) if s == "vid" else None,
+                                     dframe_b=self.g(k("frameid.b")) if s == "vid" else None,
+                                     frame_pos=ts.get("frame_pos") if s == "vid" else None)
         if on_ready is not None:
             on_ready(self.groups[k("vid_proj.w")][0])

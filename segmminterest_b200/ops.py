@@ -328,6 +328,24 @@ def id_embed_bwd(de, ids, n_rows, tw, B, L, d, dtable, dframe_w=None, dframe_b=N
     LaunchCounter.n += 1
 
 
+def id_rows_bwd(de, tw, B, L, d, rows, dframe_w=None, dframe_b=None, frame_pos=None):
+    """rows [B, tw] fp32 = per-interaction gradient rows of an ID table (no table atomics): the row-sparse exchange of dp.py"""
+    with TIMER.region("id_embed"):
+        rc = _lib.load().mmi_id_rows_bwd(de.data_ptr(), dt(de), tw, B, L, d, rows.data_ptr(), _ptr(dframe_w), _ptr(dframe_b),
+                                         _ptr(frame_pos), _stream())
+    _lib.check(rc, "mmi_id_rows_bwd")
+    LaunchCounter.n += 1
+
+
+def scatter_rows_add(ids, rows, tw, n_rows, dtable):
+    """dtable[ids[i], :] += rows[i, :]"""
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and rows.dtype == torch.float32 and rows.is_contiguous()
+    with TIMER.region("id_embed"):
+        rc = _lib.load().mmi_scatter_rows_add(ids.data_ptr(), rows.data_ptr(), ids.numel(), tw, n_rows, dtable.data_ptr(), _stream())
+    _lib.check(rc, "mmi_scatter_rows_add")
+    LaunchCounter.n += 1
+
+
 def rowdot_fwd(t, ldt, y, ldy, R, C_, out, add1=None, add2=None):
     with TIMER.region("head"):
         rc = _lib.load().mmi_rowdot_fwd(t.data_ptr(), ldt, y.data_ptr(), ldy, dt(t), R, C_, _ptr(add1), _ptr(add2), out.data_ptr(), _stream())

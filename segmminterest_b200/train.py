@@ -7,7 +7,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib, ops
-from .dp import GradBuckets
+from .dp import GradBuckets, exchange_rows
 
 PHOTO_MAX = 40
 
@@ -38,7 +38,7 @@ class DeviceGather:
 
 class TrainStep:
     def __init__(self, model, table: torch.Tensor, lr=1e-3, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8,
-                 max_norm=None, process_group=None, global_batch=None, bucket_bytes=25 << 20, dropout=None):
+                 max_norm=None, process_group=None, global_batch=None, bucket_bytes=25 << 20, dropout=None, sparse_tables=None):
         """max_norm: None / 0 (default) applies no gradient clipping -- what the reference driver effectively does: its
         `clip_grad_norm_(param_dict, 10.0)` (main...SegMM.py:298) receives the generator AdamW already consumed (:224-225),
         so nothing is clipped; a float opts in to real global-norm clipping (the norm is reported either way).
@@ -55,7 +55,14 @@ class TrainStep:
         self.norm = torch.zeros(2, device=eng.device)
         self.ws = torch.empty(int(_lib.load().mmi_clip_adamw_workspace(eng.n_flat)), device=eng.device)
         self.step_no = 0
-        self.buckets = GradBuckets(eng.flat_grad, process_group, bucket_bytes)
+        # sparse_tables: embedding-table gradients of ID towers travel as (ids, rows) between the ranks instead of through a
+        # dense all-reduce (None: on whenever there is more than one rank and the model has ID tables)
+        import torch.distributed as dist
+        world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        tables = eng.table_groups()
+        self.sparse_tables = bool(tables) and (world > 1 if sparse_tables is None else bool(sparse_tables))
+        eng.sparse_tables = self.sparse_tables
+        self.buckets = GradBuckets(eng.flat_grad, process_group, bucket_bytes, skip=tables if self.sparse_tables else ())
         eng.drop_seed = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * self.buckets.rank) & 0xFFFFFFFFFFFFFFFF
         self.global_batch = global_batch
         self.loss_cfg = model.loss_cfg()
@@ -80,7 +87,8 @@ class TrainStep:
             # moments stay valid; only the bucket views move.
             if self.exp_avg.numel() != eng.flat.numel():
                 raise _lib.MMIError("the engine's parameter layout changed under a live TrainStep; build a new TrainStep")
-            self.buckets = GradBuckets(eng.flat_grad, self.buckets.group, self.buckets.bucket_elems * 4)
+            self.buckets = GradBuckets(eng.flat_grad, self.buckets.group, self.buckets.bucket_elems * 4,
+                                       skip=eng.table_groups() if self.sparse_tables else ())
         eng.bind_grads()           # Parameters' .grad alias the flat gradient buffer
         eng.flat_grad.zero_()
         eng.drop_p = self.model.dropout_p() if self.dropout is None else float(self.dropout)
@@ -99,7 +107,12 @@ class TrainStep:
             last = si == n_slices - 1
             if last:
                 self.buckets.begin()
+            eng.table_rows = []
             eng.backward(None, on_ready=self.buckets.ready if last else None)
+            for key, tw_cols, ids_, rows_ in eng.table_rows:       # row-sparse exchange of this slice's table gradients
+                all_ids, all_rows = exchange_rows(ids_, rows_, self.buckets.group)
+                gtab = eng.g(key)
+                ops.scatter_rows_add(all_ids, all_rows, tw_cols, gtab.numel() // tw_cols, gtab)
             if n_slices > 1:
                 total = scal.clone() if total is None else total.add_(scal)
         if n_slices > 1:

@@ -75,3 +75,47 @@ def test_shard_rows_partitions_the_global_batch():
         assert spans[0][0] == 0 and spans[-1][1] == n
         for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
             assert a1 == b0 and a1 > a0
+
+
+def _worker_skip(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from segmminterest_b200.dp import exchange_rows
+        n = 1000
+        flat = torch.full((n,), float(rank + 1))
+        buckets = GradBuckets(flat, None, 256, skip=[(100, 50), (600, 100)])      # two "embedding tables" inside the flat buffer
+        buckets.begin()
+        for lo in (900, 640, 620, 300, 120, 0):
+            buckets.ready(lo)
+        buckets.finish()
+        total = float(sum(range(1, world + 1)))
+        keep = torch.zeros(n, dtype=torch.bool)
+        keep[100:150] = True
+        keep[600:700] = True
+        ok = bool(torch.all(flat[keep] == rank + 1)) and bool(torch.all(flat[~keep] == total))
+        # row-sparse exchange: every rank ends up with the concatenation of all ranks' (ids, rows)
+        ids = torch.tensor([rank, 7, 7], dtype=torch.int64)
+        rows = torch.full((3, 4), float(rank + 1))
+        all_ids, all_rows = exchange_rows(ids, rows)
+        ok = ok and all_ids.tolist() == [0, 7, 7, 1, 7, 7][: 3 * world] and all_rows[:, 0].tolist() == [1.0] * 3 + [2.0] * 3
+        out.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_skipped_table_ranges_stay_local_and_rows_are_exchanged_world2_gloo():
+    """the dense all-reduce leaves the embedding-table ranges alone (their gradients travel as (ids, rows))."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_skip, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok in res), res

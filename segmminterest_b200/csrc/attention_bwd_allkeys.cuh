@@ -14,6 +14,11 @@
 // dV_j += P^T dO,  dK_j += dS^T Q_blk,  dQ_blk += dS K_j  (A = the dS^T staging tile read MN-major, M = 64).
 // smem: K,V of all tiles 80 KB | Q ring [2][Qa | Qb | dO] 24 KB | P^T 16 KB | dS^T 16 KB | vectors, barriers   (~140 KB, 1 CTA / SM)
 // TMEM: S^T @0 (64) | dP^T @64 (64) | dQa @128 | dQb @160 | dK_j @192+64j | dV_j @224+64j                        (512 columns)
+// PERSISTENT: one CTA per SM walks the (b, h) items  blockIdx.x, + gridDim.x, ...  with every barrier phase running on
+// global counters (t = key-tile steps, g = query tiles, n = items).  K/V tile j of the NEXT item is requested the moment
+// the last product that reads tile j of the current item has retired (kv_empty[j]), so its load hides behind the remaining
+// key tiles and the epilogue; barrier initialisation, the TMEM allocation and the launch tail are paid once per SM instead
+// of once per (b, h) -- at the candidate side's shapes (one query tile per item) those were 3/4 of a CTA's life.
 constexpr int AK_MAXT = 5;
 constexpr int AK_THREADS = 64 + 16 * 32;
 constexpr uint32_t AK_TMEM_COLS = 512;
@@ -24,7 +29,7 @@ struct AKBars {
   // a slow warp has finished tile t; with ONE barrier its early arrival would complete tile t's phase (seen as garbage in
   // dK / dV of a partially filled key tile).  The issuer waits for p_ready of tile t before it can release S^T of tile
   // t + 2, so two alternating barriers are enough.
-  uint64_t once, q_full[2], q_empty[2], a_ready, s_free, p_ready[2], p_free, dq_ready, dq_free, done;
+  uint64_t kv_full[AK_MAXT], kv_empty[AK_MAXT], q_full[2], q_empty[2], a_ready, s_free, p_ready[2], p_free, dq_ready, dq_free, done, acc_free;
   uint32_t tmem_slot, pad;
 };
 
@@ -36,7 +41,7 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
                            const __grid_constant__ CUtensorMap tmdO, const AttnTcParams p,
                            __nv_bfloat16* __restrict__ dk0, __nv_bfloat16* __restrict__ dk1, __nv_bfloat16* __restrict__ dv0,
                            __nv_bfloat16* __restrict__ dv1, int64_t lddk0, int64_t lddk1, int64_t lddv0, int64_t lddv1,
-                           float* dbk0, float* dbk1, float* dbv0, float* dbv1) {
+                           float* dbk0, float* dbk1, float* dbv0, float* dbv1, int n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sKV = smem;                                    // [AK_MAXT][K 8 KB | V 8 KB]
@@ -47,17 +52,15 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
   AKBars* bars = reinterpret_cast<AKBars*>(qv + 2);
 
   const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
-  const int b = blockIdx.y, h = blockIdx.x;
   const int nt0 = (p.Lk[0] + QT - 1) / QT, nt1 = p.nblk > 1 ? (p.Lk[1] + QT - 1) / QT : 0;
   const int NT = nt0 + nt1;                               // <= AK_MAXT (host)
   const int T = (p.Lq + QN - 1) / QN;
-  const int total = T * NT;
 
   // ---- producer state (warp 0): per-query scalars of the query tile about to be staged, two queries per lane
   float nl_n[2] = {0.f, 0.f}, nd_n[2] = {0.f, 0.f};
   uint32_t rh_n[2] = {0u, 0u};
   bool mq_n[2] = {false, false};
-  auto fetch = [&](int i) {
+  auto fetch = [&](int b, int h, int i) {
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int qi = i * QN + u * 32 + lane;
@@ -81,7 +84,7 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
   };
   if (warp == 0) {
     if (elect_one()) {
-      mbar_init(&bars->once, 1);
+      for (int j = 0; j < AK_MAXT; ++j) { mbar_init(&bars->kv_full[j], 1); mbar_init(&bars->kv_empty[j], 1); }
       for (int s = 0; s < 2; ++s) { mbar_init(&bars->q_full[s], 1); mbar_init(&bars->q_empty[s], 1); }
       mbar_init(&bars->a_ready, 1);
       mbar_init(&bars->s_free, 512);
@@ -91,32 +94,26 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
       mbar_init(&bars->dq_ready, 1);
       mbar_init(&bars->dq_free, 512);
       mbar_init(&bars->done, 1);
+      mbar_init(&bars->acc_free, 512);
       fence_barrier_init();
-      mbar_expect_tx(&bars->once, NT * 2 * TILE128);
-      for (int j = 0; j < NT; ++j) {
-        const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
-        const int row = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * QT;
-        tma_load_2d(blk ? &tmKb : &tmKa, &bars->once, sKV + j * 2 * TILE128, h * DH, row);
-        tma_load_2d(blk ? &tmVb : &tmVa, &bars->once, sKV + j * 2 * TILE128 + TILE128, h * DH, row);
-      }
     }
     __syncwarp();
-    fetch(0);
+    if ((int)blockIdx.x < n_items) fetch(blockIdx.x / p.H, blockIdx.x % p.H, 0);
   }
-  // ---- softmax threads: which of their key rows (one per key tile) exist / are unmasked
-  uint32_t kin_bits = 0u, mk_bits = 0u;
-  if (warp >= 2) {
+  // ---- softmax threads: which of their key rows (one per key tile) exist / are unmasked in item (b, .)
+  auto key_bits = [&](int b, uint32_t& kin, uint32_t& mk) {
     const int row = (warp & 3) * 32 + lane;
+    kin = 0u; mk = 0u;
     for (int j = 0; j < NT; ++j) {
       const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
       const int Lk = blk ? p.Lk[1] : p.Lk[0];
       const int kj = kt * QT + row;
       if (kj < Lk) {
-        kin_bits |= 1u << j;
-        if ((blk ? p.mask_k[1] : p.mask_k[0])[(int64_t)b * Lk + kj] != 0) mk_bits |= 1u << j;
+        kin |= 1u << j;
+        if ((blk ? p.mask_k[1] : p.mask_k[0])[(int64_t)b * Lk + kj] != 0) mk |= 1u << j;
       }
     }
-  }
+  };
   if (warp == 2) TRACE(4090);
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "r"(AK_TMEM_COLS) : "memory");
@@ -131,9 +128,12 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
 
   if (warp == 0) {
     // ================================================================= producer
-    for (int i = 0; i < T; ++i) {
-      const int st = i & 1;
-      if (i >= 2) mbar_wait_bg(&bars->q_empty[st], ((i >> 1) & 1) ^ 1);
+    int g = 0;
+    for (int w = blockIdx.x, n = 0; w < n_items; w += gridDim.x, ++n) {
+    const int b = w / p.H, h = w % p.H;
+    for (int i = 0; i < T; ++i, ++g) {
+      const int st = g & 1;
+      if (g >= 2) mbar_wait_bg(&bars->q_empty[st], ((g >> 1) & 1) ^ 1);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         qv[st].nlse2[u * 32 + lane] = nl_n[u];
@@ -152,20 +152,36 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
         tma_load_2d(&tmdO, &bars->q_full[st], dst + 2 * TILE64Q, h * DH, row);
       }
       __syncwarp();
-      if (i + 1 < T) fetch(i + 1);
+      if (i == 0) {
+        // K / V of this item, tile by tile as the previous item's last reader of each slot retires
+        for (int j = 0; j < NT; ++j) {
+          if (n >= 1) mbar_wait_bg(&bars->kv_empty[j], (n - 1) & 1);
+          if (elect_one()) {
+            const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
+            const int krow = b * (blk ? p.Lk[1] : p.Lk[0]) + kt * QT;
+            mbar_expect_tx(&bars->kv_full[j], 2 * TILE128);
+            tma_load_2d(blk ? &tmKb : &tmKa, &bars->kv_full[j], sKV + j * 2 * TILE128, h * DH, krow);
+            tma_load_2d(blk ? &tmVb : &tmVa, &bars->kv_full[j], sKV + j * 2 * TILE128 + TILE128, h * DH, krow);
+          }
+          __syncwarp();
+        }
+      }
+      if (i + 1 < T) fetch(b, h, i + 1);
+      else if (w + (int)gridDim.x < n_items) fetch((w + gridDim.x) / p.H, (w + gridDim.x) % p.H, 0);
+    }
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
     const uint32_t tS = uniform(tmem), tdPTu = uniform(tdPT), tdQu = uniform(tdQ), tdKVu = uniform(tdKV);
-    mbar_wait(&bars->once, 0);
     const uint32_t aKV = smem_u32(sKV), aQs = smem_u32(sQ), aPT = smem_u32(sPT), adST = smem_u32(sdST);
     // (the issuer's operands must live in UNIFORM registers: anything data-dependent is routed through uniform(), and the
     // tile index is never divided -- a waterfall loop around every UTCHMMA costs ~80 cycles per MMA)
-    auto issue_back = [&](int u, int iu, int ju) {
-      const int su = iu & 1;
+    auto issue_back = [&](int u, int iu, int ju, int gu, int nu) {
+      const int su = gu & 1;
       const int blk = ju < nt0 ? 0 : 1, kt = blk ? ju - nt0 : ju;
       mbar_wait_bg(&bars->p_ready[u & 1], (u >> 1) & 1);
-      if (ju == 0 && iu >= 1) mbar_wait_bg(&bars->dq_free, (iu - 1) & 1);      // last query tile's dQ has left the accumulators
+      if (ju == 0 && gu >= 1) mbar_wait_bg(&bars->dq_free, (gu - 1) & 1);      // last query tile's dQ has left the accumulators
+      if (iu == 0 && ju == 0 && nu >= 1) mbar_wait_bg(&bars->acc_free, (nu - 1) & 1);   // last item's dK / dV have been read out
       tcgen05_fence_after();
       const uint32_t aQ = uniform(aQs + su * AK_QSTAGE + blk * TILE64Q), adO = uniform(aQs + su * AK_QSTAGE + 2 * TILE64Q);
       const uint32_t aK = uniform(aKV + ju * 2 * TILE128);
@@ -179,19 +195,26 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_f16(tdQb, desc_mn128(adST, k), desc_mn64(aK, k), IDESC_DQ, k > 0 ? 1u : accq);  // dQ_blk += dS K_j
         umma_commit(&bars->p_free);
+        if (iu == T - 1) umma_commit(&bars->kv_empty[ju]);                      // the item's last reader of K_j / V_j
         if (ju == NT - 1) {
           umma_commit(&bars->q_empty[su]);
           umma_commit(&bars->dq_ready);
+          if (iu == T - 1) umma_commit(&bars->done);
         }
       }
       __syncwarp();
     };
-    int t = 0, pi = 0, pj = 0;                            // (pi, pj) = the (i, j) of tile t - 1
-    for (int i = 0; i < T; ++i) {
-      const int st = i & 1;
-      mbar_wait_bg(&bars->q_full[st], (i >> 1) & 1);
+    int t = 0, g = 0, pi = 0, pj = 0, pg = 0, pn = 0;     // (pi, pj, pg, pn) = the (i, j, g, n) of step t - 1
+    bool pending = false;                                 // the products of step t - 1 are still to be issued
+    for (int w = blockIdx.x, n = 0; w < n_items; w += gridDim.x, ++n) {
+    for (int i = 0; i < T; ++i, ++g) {
+      const int st = g & 1;
+      mbar_wait_bg(&bars->q_full[st], (g >> 1) & 1);
       for (int j = 0; j < NT; ++j, ++t) {
         const int blk = j < nt0 ? 0 : 1;
+        // (a single key tile: the producer refills slot 0 only after the previous item's products have retired)
+        if (NT == 1 && i == 0 && pending) { issue_back(t - 1, pi, pj, pg, pn); pending = false; }
+        if (i == 0) mbar_wait_bg(&bars->kv_full[j], n & 1);
         if (t >= 1) mbar_wait_bg(&bars->s_free, (t - 1) & 1);
         tcgen05_fence_after();
         const uint32_t aQ = uniform(aQs + st * AK_QSTAGE + blk * TILE64Q), adO = uniform(aQs + st * AK_QSTAGE + 2 * TILE64Q);
@@ -204,15 +227,14 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
           umma_commit(&bars->a_ready);
         }
         __syncwarp();
-        TRACE(t * 8 + 6);
-        if (t >= 1) issue_back(t - 1, pi, pj);
-        TRACE(t * 8 + 7);
-        pi = i; pj = j;
+        if (t < 500) TRACE(t * 8 + 6);
+        if (pending) issue_back(t - 1, pi, pj, pg, pn);
+        if (t < 500) TRACE(t * 8 + 7);
+        pi = i; pj = j; pg = g; pn = n; pending = true;
       }
     }
-    issue_back(total - 1, pi, pj);
-    if (elect_one()) umma_commit(&bars->done);
-    __syncwarp();
+    }
+    if (pending) issue_back(t - 1, pi, pj, pg, pn);
   } else {
     // ================================================================= softmax + dQ drain + epilogue (16 warps)
     const int qd = warp & 3, c16 = (warp - 2) >> 2, row = qd * 32 + lane;
@@ -221,14 +243,9 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
     const uint32_t p_free_a = smem_u32(&bars->p_free), q_full_a = smem_u32(&bars->q_full[0]), qv_a = smem_u32(qv);
     const uint32_t dq_ready_a = smem_u32(&bars->dq_ready), dq_free_a = smem_u32(&bars->dq_free);
     const uint32_t ptrow_a = smem_u32(sPT) + row * 128, dstrow_a = smem_u32(sdST) + row * 128, swz = row & 7;
-    uint32_t act_bits = 0u, allmk_bits = 0u;               // warp-uniform: tile j has a real key in this lane quarter / no masked key
-    for (int j = 0; j < NT; ++j) {
-      if (__any_sync(0xffffffffu, (kin_bits >> j) & 1u)) act_bits |= 1u << j;
-      if (__all_sync(0xffffffffu, (mk_bits >> j) & 1u)) allmk_bits |= 1u << j;
-    }
     float dbq_run = 0.f;                                  // lane l < 16: running column sum of dQ column (c16 & 1) * 16 + l, block c16 >> 1
-    auto drain = [&](int i) {                             // dQ of query tile i: warp (qd, c16) owns rows qd*16 + lane, columns
-      mbar_wait_a(dq_ready_a, i & 1);                     // (c16 & 1) * 16 .. +16 of block c16 >> 1
+    auto drain = [&](int b, int h, int i, int gq) {       // dQ of query tile i (global count gq): warp (qd, c16) owns rows qd*16 + lane,
+      mbar_wait_a(dq_ready_a, gq & 1);                    // columns (c16 & 1) * 16 .. +16 of block c16 >> 1
       tcgen05_fence_after();
       const int bq = c16 >> 1, colh = (c16 & 1) * 16;
       uint32_t r[16];
@@ -268,10 +285,22 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
         }
       }
     };
-    int t = 0;
-    for (int i = 0; i < T; ++i) {
-      const int st = i & 1;
-      mbar_wait_a(q_full_a + st * 8, (i >> 1) & 1);       // acquire the producer's per-query vectors
+    int t = 0, g = 0;
+    uint32_t kin_next = 0u, mk_next = 0u;
+    if ((int)blockIdx.x < n_items) key_bits(blockIdx.x / p.H, kin_next, mk_next);
+    for (int w = blockIdx.x, n = 0; w < n_items; w += gridDim.x, ++n) {
+    const int b = w / p.H, h = w % p.H;
+    const uint32_t kin_bits = kin_next, mk_bits = mk_next;
+    if (w + (int)gridDim.x < n_items) key_bits((w + gridDim.x) / p.H, kin_next, mk_next);   // the next item's mask bytes: in flight early
+    uint32_t act_bits = 0u, allmk_bits = 0u;               // warp-uniform: tile j has a real key in this lane quarter / no masked key
+    for (int j = 0; j < NT; ++j) {
+      if (__any_sync(0xffffffffu, (kin_bits >> j) & 1u)) act_bits |= 1u << j;
+      if (__all_sync(0xffffffffu, (mk_bits >> j) & 1u)) allmk_bits |= 1u << j;
+    }
+    if (warp == 2 && n < 20) TRACE(4000 + n * 4);
+    for (int i = 0; i < T; ++i, ++g) {
+      const int st = g & 1;
+      mbar_wait_a(q_full_a + st * 8, (g >> 1) & 1);       // acquire the producer's per-query vectors
       const uint32_t qva = qv_a + st * (uint32_t)sizeof(QVec64) + c16 * 16 * 4;    // this warp's 16 queries
       const uint32_t wq = (lds_u1(qv_a + st * (uint32_t)sizeof(QVec64) + QV_MQ + (c16 >> 1) * 4) >> ((c16 & 1) * 16)) & 0xffffu;
       float nl[16], nd[16];                                // per-query constants: in registers across the key tiles
@@ -300,10 +329,10 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
           }
           kq = (j & 1) ? (kq2 >> 16) : (kq2 & 0xffffu);
         }
-        if (warp == 2) TRACE(t * 8 + 0);
+        if (warp == 2 && t < 500) TRACE(t * 8 + 0);
         mbar_wait_a(a_ready_a, t & 1);
         tcgen05_fence_after();
-        if (warp == 2) TRACE(t * 8 + 1);
+        if (warp == 2 && t < 500) TRACE(t * 8 + 1);
         uint32_t rs[16], rp[16];
         if (act) {
           tmem_ld_32x32b_x16(tmem + lane_addr + c16 * 16, rs);
@@ -312,7 +341,7 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
         }
         tcgen05_fence_before();
         mbar_arrive_a(s_free_a);
-        if (warp == 2) TRACE(t * 8 + 2);
+        if (warp == 2 && t < 500) TRACE(t * 8 + 2);
         uint32_t pp[8], pd[8];
         if (!act) {
 #pragma unroll
@@ -368,9 +397,9 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
             pd[c >> 1] = pack_bf16x2(ds[0], ds[1]);
           }
         }
-        if (warp == 2) TRACE(t * 8 + 3);
+        if (warp == 2 && t < 500) TRACE(t * 8 + 3);
         if (t >= 1) mbar_wait_a(p_free_a, (t - 1) & 1);    // the products of the previous tile have consumed the staging tiles
-        if (warp == 2) TRACE(t * 8 + 4);
+        if (warp == 2 && t < 500) TRACE(t * 8 + 4);
 #pragma unroll
         for (uint32_t v = 0; v < 2; ++v) {
           const uint32_t off = ((c16 * 2 + v) ^ swz) << 4;
@@ -379,17 +408,19 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
         }
         fence_proxy_async_smem();
         mbar_arrive_a(p_ready_a + (t & 1) * 8);
-        if (warp == 2) TRACE(t * 8 + 5);
-        if (j == 0 && i >= 1) drain(i - 1);               // the previous query tile's dQ: complete long ago, never waited for
+        if (warp == 2 && t < 500) TRACE(t * 8 + 5);
+        if (j == 0 && i >= 1) drain(b, h, i - 1, g - 1);   // the previous query tile's dQ: complete long ago, never waited for
       }
     }
-    if (warp == 2) TRACE(4093);
-    drain(T - 1);
+    if (warp == 2 && n < 20) TRACE(4000 + n * 4 + 1);
+    drain(b, h, T - 1, g - 1);
     if ((c16 >> 1) < p.nblk && p.dbq[c16 >> 1] != nullptr && lane < 16)
       atomicAdd(p.dbq[c16 >> 1] + h * DH + (c16 & 1) * 16 + lane, dbq_run);
+    dbq_run = 0.f;
     // ---- epilogue: 2 NT accumulators (dK_j, dV_j) spread over the four warps of each lane quarter
-    mbar_wait(&bars->done, 0);
+    mbar_wait(&bars->done, n & 1);
     tcgen05_fence_after();
+    if (warp == 2 && n < 20) TRACE(4000 + n * 4 + 2);
     for (int a = c16; a < 2 * NT; a += 4) {
       const int j = a >> 1, isv = a & 1;
       const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
@@ -405,6 +436,10 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
       float* db = isv ? (blk ? dbv1 : dbv0) : (blk ? dbk1 : dbk0);
       if (k_in && dst != nullptr) store_row32_bf16(dst + ((int64_t)b * Lk + kj) * ldd + h * DH, rk, 1.0f);
       if (db != nullptr) add_bias_grad(db + h * DH, rk, k_in, lane);
+    }
+    tcgen05_fence_before();
+    mbar_arrive(&bars->acc_free);                         // (every tcgen05.ld of this thread has completed: tmem_ld_wait above)
+    if (warp == 2 && n < 20) TRACE(4000 + n * 4 + 3);
     }
   }
   if (warp == 2) TRACE(4094);

@@ -1335,7 +1335,14 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     if (!map_rows(a->dout, a->lddo, q_rows, width, QN, &mdO)) return MMI_ECUDA;
     const mmi_attn_block& s0 = a->blk[0];
     const mmi_attn_block& s1 = a->blk[a->nblk > 1 ? 1 : 0];
-    dim3 grid(a->H, a->B);
+    // persistent: one CTA per SM walks the (b, h) items
+    static int sm_count = 0;
+    if (sm_count == 0) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
+    }
+    const int n_items = a->B * a->H;
+    dim3 grid(n_items < sm_count ? n_items : sm_count);
     const size_t smem = AK_MAXT * 2 * TILE128 + 2 * AK_QSTAGE + 2 * STILE + 2 * sizeof(QVec64) + sizeof(AKBars) + 1024;
     static bool configured = false;
     if (!configured) {
@@ -1346,10 +1353,10 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
     auto bf = [](void* x) { return reinterpret_cast<__nv_bfloat16*>(x); };
     if (drop_on)
       attn_bwd_allkeys_tc_kernel<true><<<grid, AK_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p, bf(s0.dk), bf(s1.dk), bf(s0.dv),
-                                                                        bf(s1.dv), s0.lddk, s1.lddk, s0.lddv, s1.lddv, s0.dbk, s1.dbk, s0.dbv, s1.dbv);
+                                                                        bf(s1.dv), s0.lddk, s1.lddk, s0.lddv, s1.lddv, s0.dbk, s1.dbk, s0.dbv, s1.dbv, n_items);
     else
       attn_bwd_allkeys_tc_kernel<false><<<grid, AK_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p, bf(s0.dk), bf(s1.dk), bf(s0.dv),
-                                                                         bf(s1.dv), s0.lddk, s1.lddk, s0.lddv, s1.lddv, s0.dbk, s1.dbk, s0.dbv, s1.dbv);
+                                                                         bf(s1.dv), s0.lddk, s1.lddk, s0.lddv, s1.lddv, s0.dbk, s1.dbk, s0.dbv, s1.dbv, n_items);
   } else if (kind == 3) {
     MMI_CHECK_ARG(which >= 0 && which < a->nblk, "attn_tc fused bwd: bad block index %d", which);
     MMI_CHECK_ARG(a->dout && a->out && a->lse, "attn_tc fused bwd: null dout / out / lse");

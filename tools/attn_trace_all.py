@@ -49,9 +49,16 @@ t = list(buf)
 NT = (La + 127) // 128 + (Lb + 127) // 128
 T = (Lq + 63) // 64
 base = t[4090]
-print(f"cycles from CTA entry: tmem ready @{t[4091]-base}  loop done @{t[4093]-base}  epilogue stored @{t[4094]-base}  after final sync @{t[4092]-base}")
+print(f"cycles from CTA entry: tmem ready @{t[4091]-base}  CTA done @{t[4094]-base}  after final sync @{t[4092]-base}")
+print("items of this CTA (cycles from entry): start@  key loop done@  accumulators complete@  epilogue stored@   (item length)")
+for n in range(20):
+    s = t[4000 + 4 * n: 4004 + 4 * n]
+    if s[0] == 0 and n > 0:
+        break
+    nxt = t[4004 + 4 * n] if n < 19 and t[4004 + 4 * n] else s[3]
+    print(f"  item {n:2d}: start@{s[0]-base:8d}  loop done +{s[1]-s[0]:6d}  acc done +{s[2]-s[1]:6d}  epilogue +{s[3]-s[2]:6d}   total {s[3]-s[0]:6d}")
 print("softmax warp 2 per tile (cycles): start@  wait a_ready | tmem ld | compute | wait p_free | write+fence+arrive   || MMA warp: S issued@  back issued@")
-for u in range(min(T * NT, 30)):
+for u in range(min(T * NT * 3, 45)):
     s = t[u * 8: u * 8 + 8]
-    print(f"  t={u:2d} (i={u // NT}, j={u % NT}) start@{s[0]-base:7d}  a_ready {s[1]-s[0]:5d}  ld {s[2]-s[1]:5d}  compute {s[3]-s[2]:5d}  p_free {s[4]-s[3]:5d}  "
+    print(f"  t={u:2d} (i={(u // NT) % T}, j={u % NT}) start@{s[0]-base:7d}  a_ready {s[1]-s[0]:5d}  ld {s[2]-s[1]:5d}  compute {s[3]-s[2]:5d}  p_free {s[4]-s[3]:5d}  "
           f"write {s[5]-s[4]:5d}   || S@{s[6]-base:7d} back@{s[7]-base:7d}")

@@ -23,6 +23,7 @@ constexpr int AK_MAXT = 5;
 constexpr int AK_THREADS = 64 + 16 * 32;
 constexpr uint32_t AK_TMEM_COLS = 512;
 constexpr uint32_t AK_QSTAGE = 3 * TILE64Q;      // Qa | Qb | dO
+constexpr uint32_t AK_OUT = 32 * DH * 2;         // 2 KB: one warp's 32 key rows x 32 columns of dK or dV
 
 struct AKBars {
   // p_ready[tile parity]: a warp whose lane quarter holds no key of tile t (nothing to compute) can finish tile t + 1 before
@@ -38,9 +39,9 @@ __global__ void __launch_bounds__(AK_THREADS, 1)
 attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
                            const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
                            const __grid_constant__ CUtensorMap tmVa, const __grid_constant__ CUtensorMap tmVb,
-                           const __grid_constant__ CUtensorMap tmdO, const AttnTcParams p,
-                           __nv_bfloat16* __restrict__ dk0, __nv_bfloat16* __restrict__ dk1, __nv_bfloat16* __restrict__ dv0,
-                           __nv_bfloat16* __restrict__ dv1, int64_t lddk0, int64_t lddk1, int64_t lddv0, int64_t lddv1,
+                           const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmdK0,
+                           const __grid_constant__ CUtensorMap tmdK1, const __grid_constant__ CUtensorMap tmdV0,
+                           const __grid_constant__ CUtensorMap tmdV1, const AttnTcParams p, int kv_store,
                            float* dbk0, float* dbk1, float* dbv0, float* dbv1, int n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -48,7 +49,8 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
   uint8_t* sQ = sKV + AK_MAXT * 2 * TILE128;              // [2][Qa | Qb | dO]
   uint8_t* sPT = sQ + 2 * AK_QSTAGE;                      // 104 KB from the base: 1024-aligned
   uint8_t* sdST = sPT + STILE;
-  QVec64* qv = reinterpret_cast<QVec64*>(sdST + STILE);
+  uint8_t* sOut = sdST + STILE;                           // [16 softmax warps][32 rows x 64 B, SWIZZLE_64B]: dK / dV slices on their way out
+  QVec64* qv = reinterpret_cast<QVec64*>(sOut + 16 * AK_OUT);
   AKBars* bars = reinterpret_cast<AKBars*>(qv + 2);
 
   const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -244,6 +246,81 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
     const uint32_t dq_ready_a = smem_u32(&bars->dq_ready), dq_free_a = smem_u32(&bars->dq_free);
     const uint32_t ptrow_a = smem_u32(sPT) + row * 128, dstrow_a = smem_u32(sdST) + row * 128, swz = row & 7;
     float dbq_run = 0.f;                                  // lane l < 16: running column sum of dQ column (c16 & 1) * 16 + l, block c16 >> 1
+    // dK_j / dV_j leave by TMA: warp (qd, c16) takes rows qd*32 + lane of dK (c16 even) or dV (c16 odd) of the key tiles with
+    // parity c16 >> 1, converts its 32 x 32 slice into a private SWIZZLE_64B staging tile and stores it with ONE
+    // cp.async.bulk.tensor (3-D map: rows past Lk of this batch item are clipped).  Thread-per-row global stores put 32
+    // different lines into every STG and made the LSU the bound of the epilogue (~6 000 cycles per item).
+    // Bias-gradient column sums stay in registers over the tiles and items of one head (lanes l, l ^ 1 hold columns l >> 1
+    // and 16 + (l >> 1); one pair per key block) and leave with one atomic per column when the head changes or the CTA ends.
+    const int isv = c16 & 1;
+    const uint32_t out_a = smem_u32(sOut) + (uint32_t)(warp - 2) * AK_OUT;
+    const uint32_t outrow_a = out_a + lane * 64, oswz = (lane >> 1) & 3;
+    float bs00 = 0.f, bs01 = 0.f, bs10 = 0.f, bs11 = 0.f;  // [key block][column half]
+    int cur_h = -1;
+    auto flush = [&]() {
+      if (cur_h >= 0) {
+        if ((c16 >> 1) < p.nblk && p.dbq[c16 >> 1] != nullptr && lane < 16)
+          atomicAdd(p.dbq[c16 >> 1] + cur_h * DH + (c16 & 1) * 16 + lane, dbq_run);
+        if ((lane & 1) == 0) {
+          float* d0 = isv ? dbv0 : dbk0;
+          float* d1 = isv ? dbv1 : dbk1;
+          if (d0 != nullptr) { atomicAdd(d0 + cur_h * DH + (lane >> 1), bs00); atomicAdd(d0 + cur_h * DH + 16 + (lane >> 1), bs01); }
+          if (nt1 > 0 && d1 != nullptr) { atomicAdd(d1 + cur_h * DH + (lane >> 1), bs10); atomicAdd(d1 + cur_h * DH + 16 + (lane >> 1), bs11); }
+        }
+      }
+      dbq_run = 0.f; bs00 = 0.f; bs01 = 0.f; bs10 = 0.f; bs11 = 0.f;
+    };
+    auto drain_kv = [&](int b, int h, int j, uint32_t act_bits) {   // accumulators of key tile j are final (their last products retired)
+      if ((c16 >> 1) != (j & 1)) return;                   // the other warp of this (lane quarter, accumulator) pair takes this tile
+      if (!((act_bits >> j) & 1u)) return;                 // no key of the tile in this lane quarter (warp-uniform)
+      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
+      const int Lk = blk ? p.Lk[1] : p.Lk[0];
+      const bool k_in = kt * QT + row < Lk;
+      const bool want_sum = (isv ? (blk ? dbv1 : dbv0) : (blk ? dbk1 : dbk0)) != nullptr;
+      const bool want_store = (kv_store >> (blk * 2 + isv)) & 1;
+      tcgen05_fence_after();
+      if (lane == 0) bulk_wait_read0();                    // this warp's previous store has read the staging tile
+      __syncwarp();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t rk[16];
+        tmem_ld_32x32b_x16(tdKV + lane_addr + j * 2 * DH + isv * DH + half * 16, rk);
+        tmem_ld_wait();
+#pragma unroll
+        for (uint32_t v = 0; v < 2; ++v)
+          sts_u4(outrow_a + (((half * 2 + v) ^ oswz) << 4), pack_bf16x2(__uint_as_float(rk[8 * v]), __uint_as_float(rk[8 * v + 1])),
+                 pack_bf16x2(__uint_as_float(rk[8 * v + 2]), __uint_as_float(rk[8 * v + 3])),
+                 pack_bf16x2(__uint_as_float(rk[8 * v + 4]), __uint_as_float(rk[8 * v + 5])),
+                 pack_bf16x2(__uint_as_float(rk[8 * v + 6]), __uint_as_float(rk[8 * v + 7])));
+        if (want_sum) {
+          float f[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) f[c] = k_in ? __uint_as_float(rk[c]) : 0.f;
+#pragma unroll
+          for (int o = 16, hv = 8; o >= 2; o >>= 1, hv >>= 1) {    // transposing butterfly: 16 columns x 32 rows -> column l >> 1
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int c = 0; c < hv; ++c) {
+              const float send = up ? f[c] : f[c + hv];
+              const float keep = up ? f[c + hv] : f[c];
+              f[c] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          f[0] += __shfl_xor_sync(0xffffffffu, f[0], 1);
+          if (blk) { if (half) bs11 += f[0]; else bs10 += f[0]; }
+          else { if (half) bs01 += f[0]; else bs00 += f[0]; }
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (want_store && elect_one()) {
+        const CUtensorMap* m = isv ? (blk ? &tmdV1 : &tmdV0) : (blk ? &tmdK1 : &tmdK0);
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(m)), "r"(out_a), "r"(h * DH), "r"(kt * QT + qd * 32), "r"(b) : "memory");
+        bulk_commit();
+      }
+      __syncwarp();
+    };
     auto drain = [&](int b, int h, int i, int gq) {       // dQ of query tile i (global count gq): warp (qd, c16) owns rows qd*16 + lane,
       mbar_wait_a(dq_ready_a, gq & 1);                    // columns (c16 & 1) * 16 .. +16 of block c16 >> 1
       tcgen05_fence_after();
@@ -297,19 +374,17 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
       if (__any_sync(0xffffffffu, (kin_bits >> j) & 1u)) act_bits |= 1u << j;
       if (__all_sync(0xffffffffu, (mk_bits >> j) & 1u)) allmk_bits |= 1u << j;
     }
+    if (h != cur_h) { flush(); cur_h = h; }
     if (warp == 2 && n < 20) TRACE(4000 + n * 4);
     for (int i = 0; i < T; ++i, ++g) {
       const int st = g & 1;
       mbar_wait_a(q_full_a + st * 8, (g >> 1) & 1);       // acquire the producer's per-query vectors
       const uint32_t qva = qv_a + st * (uint32_t)sizeof(QVec64) + c16 * 16 * 4;    // this warp's 16 queries
       const uint32_t wq = (lds_u1(qv_a + st * (uint32_t)sizeof(QVec64) + QV_MQ + (c16 >> 1) * 4) >> ((c16 & 1) * 16)) & 0xffffu;
-      float nl[16], nd[16];                                // per-query constants: in registers across the key tiles
-#pragma unroll
-      for (int c = 0; c < 16; c += 4) {
-        const float4 a = lds_f4(qva + c * 4), d4 = lds_f4(qva + QV_NDS + c * 4);
-        nl[c] = a.x; nl[c + 1] = a.y; nl[c + 2] = a.z; nl[c + 3] = a.w;
-        nd[c] = d4.x; nd[c + 1] = d4.y; nd[c + 2] = d4.z; nd[c + 3] = d4.w;
-      }
+      // per-query constants -log2e*lse and -scale*delta: re-read from shared memory (broadcast LDS.64) next to their use -- kept
+      // in registers across the key tiles they cost 32 registers and pushed the loop into local-memory spills at 96 regs/thread
+      auto NL2 = [&](int c) { return lds_f2(qva + c * 4); };
+      auto ND2 = [&](int c) { return lds_f2(qva + QV_NDS + c * 4); };
       uint32_t rh = 0u;
       if constexpr (DROP) rh = lds_u1(qva + QV_RH + (lane & 15) * 4);
       uint32_t kq2 = 0u;                                   // DROP: keep bits of this thread's key for the 16 queries, tiles j (low half) and j + 1 (high half)
@@ -354,8 +429,8 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
             for (int c = 0; c < 16; c += 2) {
               const bool k0_ = (kq >> c) & 1u, k1_ = (kq >> (c + 1)) & 1u;
               const float s0 = k0_ ? __uint_as_float(rs[c]) : 0.f, s1 = k1_ ? __uint_as_float(rs[c + 1]) : 0.f;
-              const float2 pr = ex2_mufu2(fma2(make_float2(s0, s1), sl2, make_float2(nl[c], nl[c + 1])));
-              const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, mul2(make_float2(nd[c], nd[c + 1]), dsc2)));
+              const float2 pr = ex2_mufu2(fma2(make_float2(s0, s1), sl2, NL2(c)));
+              const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, mul2(ND2(c), dsc2)));
               pp[c >> 1] = pack_bf16x2(pr.x, pr.y);
               pd[c >> 1] = pack_bf16x2(k0_ ? ds.x : 0.f, k1_ ? ds.y : 0.f);
             }
@@ -365,8 +440,8 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
               const bool k0_ = (kq >> c) & 1u, k1_ = (kq >> (c + 1)) & 1u;
               const bool v0 = mk && ((wq >> c) & 1u), v1 = mk && ((wq >> (c + 1)) & 1u);
               const float s0 = k0_ ? (v0 ? __uint_as_float(rs[c]) : -10000.0f) : 0.f, s1 = k1_ ? (v1 ? __uint_as_float(rs[c + 1]) : -10000.0f) : 0.f;
-              const float2 pr = ex2_mufu2(fma2(make_float2(s0, s1), sl2, make_float2(nl[c], nl[c + 1])));
-              const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, mul2(make_float2(nd[c], nd[c + 1]), dsc2)));
+              const float2 pr = ex2_mufu2(fma2(make_float2(s0, s1), sl2, NL2(c)));
+              const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, mul2(ND2(c), dsc2)));
               pp[c >> 1] = pack_bf16x2(pr.x, pr.y);
               pd[c >> 1] = pack_bf16x2((k0_ && v0) ? ds.x : 0.f, (k1_ && v1) ? ds.y : 0.f);
             }
@@ -375,9 +450,9 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
           const float2 sl2 = splat2(p.scale_log2), sc2 = splat2(p.scale);
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
-            const float2 x = fma2(make_float2(__uint_as_float(rs[c]), __uint_as_float(rs[c + 1])), sl2, make_float2(nl[c], nl[c + 1]));
+            const float2 x = fma2(make_float2(__uint_as_float(rs[c]), __uint_as_float(rs[c + 1])), sl2, NL2(c));
             const float2 pr = ex2_mufu2(x);
-            const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, make_float2(nd[c], nd[c + 1])));
+            const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, ND2(c)));
             pp[c >> 1] = pack_bf16x2(pr.x, pr.y);
             pd[c >> 1] = pack_bf16x2(ds.x, ds.y);
           }
@@ -385,13 +460,15 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
             float pr[2], ds[2];
+            const float2 nl2 = NL2(c), nd2 = ND2(c);
+            const float nl[2] = {nl2.x, nl2.y}, nd[2] = {nd2.x, nd2.y};
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               const int cc = c + u;
               const bool valid = mk && (((wq >> cc) & 1u) != 0);
               const float x = valid ? __uint_as_float(rs[cc]) * p.scale_log2 : p.fill_log2;
-              pr[u] = ex2(x + nl[cc]);                    // queries past Lq: nlse2 = -inf => 0
-              ds[u] = valid ? pr[u] * fmaf(__uint_as_float(rp[cc]), p.scale, nd[cc]) : 0.f;
+              pr[u] = ex2(x + nl[u]);                    // queries past Lq: nlse2 = -inf => 0
+              ds[u] = valid ? pr[u] * fmaf(__uint_as_float(rp[cc]), p.scale, nd[u]) : 0.f;
             }
             pp[c >> 1] = pack_bf16x2(pr[0], pr[1]);
             pd[c >> 1] = pack_bf16x2(ds[0], ds[1]);
@@ -410,37 +487,25 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
         mbar_arrive_a(p_ready_a + (t & 1) * 8);
         if (warp == 2 && t < 500) TRACE(t * 8 + 5);
         if (j == 0 && i >= 1) drain(b, h, i - 1, g - 1);   // the previous query tile's dQ: complete long ago, never waited for
+        // last query tile: dK / dV of the previous key tile are final (p_free of its products was waited for above) and
+        // leave while the tensor pipe works on this tile's products
+        if (i == T - 1 && j >= 1) drain_kv(b, h, j - 1, act_bits);
       }
     }
     if (warp == 2 && n < 20) TRACE(4000 + n * 4 + 1);
     drain(b, h, T - 1, g - 1);
-    if ((c16 >> 1) < p.nblk && p.dbq[c16 >> 1] != nullptr && lane < 16)
-      atomicAdd(p.dbq[c16 >> 1] + h * DH + (c16 & 1) * 16 + lane, dbq_run);
-    dbq_run = 0.f;
-    // ---- epilogue: 2 NT accumulators (dK_j, dV_j) spread over the four warps of each lane quarter
+    // ---- the last key tile's accumulators
     mbar_wait(&bars->done, n & 1);
     tcgen05_fence_after();
     if (warp == 2 && n < 20) TRACE(4000 + n * 4 + 2);
-    for (int a = c16; a < 2 * NT; a += 4) {
-      const int j = a >> 1, isv = a & 1;
-      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
-      const int Lk = blk ? p.Lk[1] : p.Lk[0];
-      const int kj = kt * QT + row;
-      const bool k_in = kj < Lk;
-      if (!((act_bits >> j) & 1u)) continue;
-      uint32_t rk[32];
-      tmem_ld_32x32(tdKV + lane_addr + j * 2 * DH + isv * DH, rk);
-      tmem_ld_wait();
-      __nv_bfloat16* dst = isv ? (blk ? dv1 : dv0) : (blk ? dk1 : dk0);
-      const int64_t ldd = isv ? (blk ? lddv1 : lddv0) : (blk ? lddk1 : lddk0);
-      float* db = isv ? (blk ? dbv1 : dbv0) : (blk ? dbk1 : dbk0);
-      if (k_in && dst != nullptr) store_row32_bf16(dst + ((int64_t)b * Lk + kj) * ldd + h * DH, rk, 1.0f);
-      if (db != nullptr) add_bias_grad(db + h * DH, rk, k_in, lane);
-    }
+    drain_kv(b, h, NT - 1, act_bits);
     tcgen05_fence_before();
     mbar_arrive(&bars->acc_free);                         // (every tcgen05.ld of this thread has completed: tmem_ld_wait above)
     if (warp == 2 && n < 20) TRACE(4000 + n * 4 + 3);
     }
+    flush();
+    if (lane == 0) bulk_wait0();                          // the staging tiles stay valid until the last stores have read them
+    __syncwarp();
   }
   if (warp == 2) TRACE(4094);
   tcgen05_fence_before();

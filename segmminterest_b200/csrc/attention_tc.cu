@@ -1342,21 +1342,36 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
       if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0) sm_count = 148;
     }
     const int n_items = a->B * a->H;
-    dim3 grid(n_items < sm_count ? n_items : sm_count);
-    const size_t smem = AK_MAXT * 2 * TILE128 + 2 * AK_QSTAGE + 2 * STILE + 2 * sizeof(QVec64) + sizeof(AKBars) + 1024;
+    // a CTA count that is a multiple of H keeps one head per CTA (item w -> h = w % H), so the bias-gradient sums it holds in
+    // registers leave once per CTA instead of once per item
+    int ctas = sm_count >= a->H ? (sm_count / a->H) * a->H : sm_count;
+    if (ctas > n_items) ctas = n_items;
+    dim3 grid(ctas);
+    // dK / dV leave by TMA through 3-D maps [B, Lk, H*dh] (a box never spills into the next batch item's rows)
+    CUtensorMap mdK[2], mdV[2];
+    int kv_store = 0;
+    for (int i = 0; i < 2; ++i) {
+      const mmi_attn_block& s = a->blk[i < a->nblk ? i : 0];
+      MMI_CHECK_ARG(s.lddk % 8 == 0 && s.lddv % 8 == 0, "attn_tc all-keys bwd: lddk / lddv must be multiples of 8");
+      MMI_CHECK_ARG(((reinterpret_cast<uintptr_t>(s.dk) | reinterpret_cast<uintptr_t>(s.dv)) & 15) == 0, "attn_tc all-keys bwd: dk / dv must be 16-byte aligned");
+      // (a null gradient pointer: the map is built on k / v and never used)
+      if (!get_tensor_map_3d(s.dk ? s.dk : s.k, width, s.Lk, a->B, s.dk ? s.lddk : s.ldk, DH, 32, CU_TENSOR_MAP_SWIZZLE_64B, &mdK[i])) return MMI_ECUDA;
+      if (!get_tensor_map_3d(s.dv ? s.dv : s.v, width, s.Lk, a->B, s.dv ? s.lddv : s.ldv, DH, 32, CU_TENSOR_MAP_SWIZZLE_64B, &mdV[i])) return MMI_ECUDA;
+      if (i < a->nblk) kv_store |= (s.dk ? 1 : 0) << (2 * i) | (s.dv ? 1 : 0) << (2 * i + 1);
+    }
+    const size_t smem = AK_MAXT * 2 * TILE128 + 2 * AK_QSTAGE + 2 * STILE + 16 * AK_OUT + 2 * sizeof(QVec64) + sizeof(AKBars) + 1024;
     static bool configured = false;
     if (!configured) {
       int rc = set_smem(attn_bwd_allkeys_tc_kernel<false>, smem); if (rc) return rc;
       rc = set_smem(attn_bwd_allkeys_tc_kernel<true>, smem); if (rc) return rc;
       configured = true;
     }
-    auto bf = [](void* x) { return reinterpret_cast<__nv_bfloat16*>(x); };
     if (drop_on)
-      attn_bwd_allkeys_tc_kernel<true><<<grid, AK_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p, bf(s0.dk), bf(s1.dk), bf(s0.dv),
-                                                                        bf(s1.dv), s0.lddk, s1.lddk, s0.lddv, s1.lddv, s0.dbk, s1.dbk, s0.dbv, s1.dbv, n_items);
+      attn_bwd_allkeys_tc_kernel<true><<<grid, AK_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, mdK[0], mdK[1], mdV[0], mdV[1], p,
+                                                                        kv_store, s0.dbk, s1.dbk, s0.dbv, s1.dbv, n_items);
     else
-      attn_bwd_allkeys_tc_kernel<false><<<grid, AK_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, p, bf(s0.dk), bf(s1.dk), bf(s0.dv),
-                                                                         bf(s1.dv), s0.lddk, s1.lddk, s0.lddv, s1.lddv, s0.dbk, s1.dbk, s0.dbv, s1.dbv, n_items);
+      attn_bwd_allkeys_tc_kernel<false><<<grid, AK_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mdO, mdK[0], mdK[1], mdV[0], mdV[1], p,
+                                                                        kv_store, s0.dbk, s1.dbk, s0.dbv, s1.dbv, n_items);
   } else if (kind == 3) {
     MMI_CHECK_ARG(which >= 0 && which < a->nblk, "attn_tc fused bwd: bad block index %d", which);
     MMI_CHECK_ARG(a->dout && a->out && a->lse, "attn_tc fused bwd: null dout / out / lse");

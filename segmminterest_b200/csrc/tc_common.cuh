@@ -111,6 +111,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // the issuing thread's bulk groups have finished READING shared memory (buffers may be rewritten)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -203,6 +207,9 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // host: cached cuTensorMapEncodeTiled for a row-major 2-D bf16 tensor [outer, inner] (stride in elements)
 bool get_tensor_map(const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride_elems, uint32_t box_inner,
                     uint32_t box_outer, CUtensorMapSwizzle swizzle, CUtensorMap* out);
+// [batch, rows, inner] with a box of {box_inner, box_rows, 1}: a box never crosses into the next batch item (stores clip at `rows`)
+bool get_tensor_map_3d(const void* ptr, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t stride_elems, uint32_t box_inner,
+                       uint32_t box_rows, CUtensorMapSwizzle swizzle, CUtensorMap* out);
 bool encode_available();
 
 }  // namespace tc

@@ -846,10 +846,10 @@ class Engine:
                 delta = self._buf(f"delta.{tw.tag}.{s}", (B, H, Ls[s]), torch.float32)
                 names = ATTN_BLOCKS[cfg.ablation][s]
                 side.set_bwd(dA[s], d, delta, [gset(n) for n in names])
-                # one launch: dq, dk, dv of both key blocks by one CTA per (b, h) (<= 640 keys).  Measured at the c2 shapes with
-                # dropout and bias sums live: history-side queries 6.66 ms against 7.02 ms for dq + 2 x dk/dv; a single 64-query
-                # tile (the candidate side) does not amortise the CTA's prologue / epilogue (2.05 against 1.67 ms) and keeps the pair
-                if side.a.impl == IMPL_TC and self.allkeys_attn_bwd and Ls[s] > 64 and side.bwd_all():
+                # one launch: dq, dk, dv of both key blocks by persistent CTAs that own every key of a (b, h) item (<= 640 keys).
+                # Measured at the c2 shapes with dropout and bias sums live (tools/attn_bench.py, profiles/r02_s8_*): history-side
+                # queries 5.86 ms against 6.99 ms for dq + 2 x dk/dv, candidate-side queries 1.28 against 1.65 ms
+                if side.a.impl == IMPL_TC and self.allkeys_attn_bwd and side.bwd_all():
                     continue
                 if side.a.impl == IMPL_TC and self.fused_attn_bwd:
                     # one kernel per key block: dK, dV and that block's dQ (partial tiles reduced through an fp32 accumulator

@@ -46,35 +46,34 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int R, int noise_war
   __syncthreads();
   if (warp == 0) {
     uint32_t ph = 0;
+    const uint32_t tmu = uniform(tm), a0u = uniform(a0), b0u = uniform(b0);
     for (int cfg = 0; cfg < NCFG; ++cfg) {
-      long long t0 = 0, t1 = 0, t2 = 0;
-      if (lane == 0) {
-        t0 = clock64();
-        for (int r = 0; r < R; ++r) {
-          const uint32_t acc = r > 0;
-          switch (cfg) {
-            case 0: umma_f16(tm, d_k64(a0, r & 1), d_k64(b0, r & 1), make_idesc(128, 64, false, false), acc); break;          // S^T / dP^T
-            case 1: umma_f16(tm, d_k128(a0, r & 3), d_mn64(b0, r & 3), make_idesc(128, 32, false, true), acc); break;         // dV / dK (SS)
-            case 2: umma_f16(tm, d_mn128(a0, r & 7), d_mn64(b0, r & 7), make_idesc(64, 32, true, true), acc); break;          // dQ (M = 64, A MN-major)
-            case 3: umma_ts(tm, tm + 256 + (r & 3) * 8, d_mn64(b0, r & 3), make_idesc(128, 32, false, true), acc); break;     // dV / dK with A in TMEM
-            case 4: umma_f16(tm, make_smem_desc(a0 + (r & 3) * 32, 16, 1024), make_smem_desc(b0 + (r & 3) * 32, 16, 1024), make_idesc(128, 256, false, false), acc); break;  // GEMM
-            case 5: umma_f16(tm, d_k64(a0, r & 1), d_k64(b0, r & 1), make_idesc(128, 32, false, false), acc); break;          // 128 x 32, both K-major
-            case 6: umma_f16(tm, d_mn128(a0, r & 7), d_mn64(b0, r & 7), make_idesc(128, 32, true, true), acc); break;         // dQ shape at M = 128
-            case 7: umma_f16(tm, d_k128(a0, r & 3), d_k64(b0, r & 1), make_idesc(128, 32, false, false), acc); break;         // dV with a K-major B
-            case 8: umma_ts(tm, tm + 256 + (r & 3) * 8, d_k64(b0, r & 1), make_idesc(128, 32, false, false), acc); break;     // TS, K-major B
-            case 9: umma_f16(tm, d_k64(a0, r & 1), d_k64(b0, r & 1), make_idesc(128, 128, false, false), acc); break;         // 128 x 128 K-major SW64
-            case 10: umma_f16(tm, d_k64(a0, r & 1), d_k64(b0, r & 1), make_idesc(64, 64, false, false), acc); break;          // M = 64, N = 64 K-major
-            case 11: umma_ts(tm, tm + 256 + (r & 3) * 8, d_mn64(b0, r & 3), make_idesc(128, 64, false, true), acc); break;    // TS, N = 64
-          }
-        }
-        t1 = clock64();
-        umma_commit(&bar);
+      long long t0 = clock64(), t1 = 0, t2 = 0;
+      // warp-uniform loop, one elected lane issues: the operands stay in uniform registers (a lane-0-only loop makes
+      // ptxas wrap every UTCHMMA in a waterfall loop and measures that instead)
+#define LOOP(EXPR) for (int r = 0; r < R; r += 8) { if (elect_one()) { _Pragma("unroll") for (int q = 0; q < 8; ++q) { const uint32_t acc = (r + q) > 0; EXPR; } } __syncwarp(); }
+      switch (cfg) {
+        case 0: LOOP(umma_f16(tmu, d_k64(a0u, q & 1), d_k64(b0u, q & 1), make_idesc(128, 64, false, false), acc)); break;
+        case 1: LOOP(umma_f16(tmu, d_k128(a0u, q & 3), d_mn64(b0u, q & 3), make_idesc(128, 32, false, true), acc)); break;
+        case 2: LOOP(umma_f16(tmu, d_mn128(a0u, q & 7), d_mn64(b0u, q & 7), make_idesc(64, 32, true, true), acc)); break;
+        case 3: LOOP(umma_ts(tmu, tmu + 256 + (q & 3) * 8, d_mn64(b0u, q & 3), make_idesc(128, 32, false, true), acc)); break;
+        case 4: LOOP(umma_f16(tmu, make_smem_desc(a0u + (q & 3) * 32, 16, 1024), make_smem_desc(b0u + (q & 3) * 32, 16, 1024), make_idesc(128, 256, false, false), acc)); break;
+        case 5: LOOP(umma_f16(tmu, d_k64(a0u, q & 1), d_k64(b0u, q & 1), make_idesc(128, 32, false, false), acc)); break;
+        case 6: LOOP(umma_f16(tmu, d_mn128(a0u, q & 7), d_mn64(b0u, q & 7), make_idesc(128, 32, true, true), acc)); break;
+        case 7: LOOP(umma_f16(tmu, d_k128(a0u, q & 3), d_k64(b0u, q & 1), make_idesc(128, 32, false, false), acc)); break;
+        case 8: LOOP(umma_ts(tmu, tmu + 256 + (q & 3) * 8, d_k64(b0u, q & 1), make_idesc(128, 32, false, false), acc)); break;
+        case 9: LOOP(umma_f16(tmu, d_k64(a0u, q & 1), d_k64(b0u, q & 1), make_idesc(128, 128, false, false), acc)); break;
+        case 10: LOOP(umma_f16(tmu, d_k64(a0u, q & 1), d_k64(b0u, q & 1), make_idesc(64, 64, false, false), acc)); break;
+        case 11: LOOP(umma_ts(tmu, tmu + 256 + (q & 3) * 8, d_mn64(b0u, q & 3), make_idesc(128, 64, false, true), acc)); break;
       }
+      t1 = clock64();
+      if (elect_one()) umma_commit(&bar);
       __syncwarp();
       mbar_wait(&bar, ph);
       ph ^= 1;
       tcgen05_fence_after();
-      if (lane == 0) { t2 = clock64(); out[cfg * 2] = t1 - t0; out[cfg * 2 + 1] = t2 - t0; }
+      t2 = clock64();
+      if (lane == 0) { out[cfg * 2] = t1 - t0; out[cfg * 2 + 1] = t2 - t0; }
       __syncwarp();
     }
     if (lane == 0) stop = 1;

@@ -32,8 +32,12 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;     // two warps per TMEM lane quarter, each takes half of the columns
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-9: epilogue
+// epilogue warps: warp 0 = TMA, warp 1 = MMA + TMEM alloc, then 8 (register epilogue: two per TMEM lane quarter, each half of the
+// columns) or 16 (TMA epilogue: four per lane quarter, 32-column chunks -- with eight, two warps per scheduler could not hide
+// the tcgen05.ld / MUFU / shared-memory latencies of the GELU and dropout epilogues: 40 % issue utilisation, 0.2-0.4 of peak)
+__host__ __device__ constexpr int epi_warps(bool tma_epi) { return tma_epi ? 16 : 8; }
+__host__ __device__ constexpr int num_threads(bool tma_epi) { return 64 + 32 * epi_warps(tma_epi); }
+constexpr int EPI_WARPS = 8;     // register epilogue
 constexpr int STG_COLS = 64;     // epilogue staging: 32 rows x 64 fp32 per warp (8 KB), XOR-swizzled
 constexpr int STG_BYTES = 32 * STG_COLS * 4;
 __host__ __device__ constexpr int stages_for(int bn) { return bn == 256 ? 3 : 4; }
@@ -59,12 +63,13 @@ struct EpiMaps {
   CUtensorMap c, aux, c2;   // output, prefetched add / mul operand, second output (saved pre-activation)
 };
 
-constexpr int EBUF_BYTES = 32 * 64 * 2;   // 32 rows x 64 bf16 (one SWIZZLE_128B box per warp and chunk)
+constexpr int ECOLS = 32;                       // TMA epilogue: columns per chunk
+constexpr int EBUF_BYTES = 32 * ECOLS * 2;      // 32 rows x 32 bf16 (one SWIZZLE_64B box per warp and chunk)
 
 // DROP (TMA epilogue only): dropout of act(z) fused into the epilogue.  The no-dropout instantiation is byte-for-byte the
 // kernel that existed before dropout was added; the generic register epilogue handles dropout at run time.
 template <int BN, bool MN_MAJOR, typename TOUT, bool TMA_EPI, bool DROP = false>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(num_threads(TMA_EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ EpiMaps em, const GemmParams p, int m_tiles, int n_tiles, int num_kb, int split) {
   extern __shared__ uint8_t smem_raw[];
@@ -78,8 +83,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
-  uint64_t* aux_bars = tmem_empty + 2;        // [EPI_WARPS][2]  (TMA epilogue)
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(aux_bars + 2 * EPI_WARPS);
+  constexpr int EW = epi_warps(TMA_EPI);
+  uint64_t* aux_bars = tmem_empty + 2;        // [EW][2]  (TMA epilogue)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(aux_bars + 2 * EW);
   uint8_t* stg_base = smem + STAGES * STAGE_BYTES + 256;   // 1024-aligned: STAGE_BYTES is a multiple of 1024
 
   const int warp = (int)uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;   // warp index in a uniform register
@@ -89,8 +95,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * EPI_WARPS); }
-    for (int b = 0; b < 2 * EPI_WARPS; ++b) mbar_init(&aux_bars[b], 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 32 * EW); }
+    for (int b = 0; b < 2 * EW; ++b) mbar_init(&aux_bars[b], 1);
     if constexpr (TMA_EPI) { tma_prefetch_desc(&em.c); tma_prefetch_desc(&em.aux); tma_prefetch_desc(&em.c2); }
     fence_barrier_init();
   }
@@ -169,15 +175,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else if constexpr (TMA_EPI) {
-    // ===================================================================== TMA epilogue (8 warps)
-    // warp = 32 accumulator rows (its TMEM lane quarter) x every other 64-column chunk of the tile.
+    // ===================================================================== TMA epilogue (16 warps)
+    // warp = 32 accumulator rows (its TMEM lane quarter) x every fourth 32-column chunk of the tile.
     const int ew = warp - 2;
     const int q = warp & 3;
-    const int half = ew >> 2;
+    const int cq = ew >> 2;
     constexpr int CPW = BN / 128;                      // chunks per warp per tile
     uint8_t* epi_base = smem + STAGES * STAGE_BYTES + 1024;            // 1024-aligned (SWIZZLE_128B); barriers sit below
     uint8_t* ebuf = epi_base + ew * (2 * EBUF_BYTES);
-    float* sbias = reinterpret_cast<float*>(epi_base + EPI_WARPS * 2 * EBUF_BYTES) + ew * 64;
+    float* sbias = reinterpret_cast<float*>(epi_base + EW * 2 * EBUF_BYTES) + ew * ECOLS;
     uint64_t* aux_bar = aux_bars + 2 * ew;
     // position-embedding add (fp32 table [add_mod, N], row = m mod add_mod): read straight from L1/L2 by the thread
     // that owns the accumulator row -- the table is ~1 MB and shared by every batch item, so it never leaves cache
@@ -195,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
       for (int k = 0; k < CPW; ++k) {
         mbar_expect_tx(&aux_bar[k], EBUF_BYTES);
-        tma_load_2d(&em.aux, &aux_bar[k], ebuf + k * EBUF_BYTES, ti.n_blk * BN + (half + 2 * k) * 64, ti.m_blk * BM + q * 32);
+        tma_load_2d(&em.aux, &aux_bar[k], ebuf + k * EBUF_BYTES, ti.n_blk * BN + (cq + 4 * k) * ECOLS, ti.m_blk * BM + q * 32);
       }
     };
     if (has_aux && (int)blockIdx.x < total_tiles && elect_one()) issue_aux(blockIdx.x);
@@ -214,16 +220,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
 #pragma unroll 1
       for (int k = 0; k < CPW; ++k) {
-        const int n0 = ti.n_blk * BN + (half + 2 * k) * 64;
-        uint32_t acc[64];
-        {
-          uint32_t (&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&acc[0]);
-          uint32_t (&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&acc[32]);
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + (half + 2 * k) * 64;
-          tmem_ld_32x32(taddr, lo);
-          tmem_ld_32x32(taddr + 32, hi);
-          tmem_ld_wait();
-        }
+        const int n0 = ti.n_blk * BN + (cq + 4 * k) * ECOLS;
+        uint32_t acc[ECOLS];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + (cq + 4 * k) * ECOLS, acc);
+        tmem_ld_wait();
         if (k == CPW - 1) {                            // accumulator fully read: hand it back to the MMA warp
           tcgen05_fence_before();
           mbar_arrive(&tmem_empty[buf]);
@@ -233,29 +233,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           __syncwarp();
         }
         {
-          const int n = n0 + 2 * lane;
-          float2 b = make_float2(0.f, 0.f);
-          if (p.bias != nullptr && n < p.N) b = *reinterpret_cast<const float2*>(p.bias + n);
-          if constexpr (drop_on) { b.x *= dscale; b.y *= dscale; }
-          *reinterpret_cast<float2*>(sbias + 2 * lane) = b;
+          const int n = n0 + lane;
+          float b = 0.f;
+          if (p.bias != nullptr && n < p.N) b = p.bias[n];
+          if constexpr (drop_on) b *= dscale;
+          sbias[lane] = b;
         }
         __syncwarp();
         uint8_t* tile1 = ebuf + (second ? 0 : k * EBUF_BYTES);          // warp-uniform staging tiles
         uint8_t* tile2 = ebuf + EBUF_BYTES;
-        uint8_t* row1 = tile1 + lane * 128;
-        uint8_t* row2 = tile2 + lane * 128;
+        uint8_t* row1 = tile1 + lane * (ECOLS * 2);
+        uint8_t* row2 = tile2 + lane * (ECOLS * 2);
         if (has_aux) mbar_wait(&aux_bar[k], it & 1);
         const float* pe_row = pe_add ? reinterpret_cast<const float*>(p.add) + ((int64_t)(m0 + lane) % p.add_mod) * p.ld_add + n0 : nullptr;
-        // dropout: the two keep words of this row's 64 columns (dropout.cuh); bit c of kw[w] = column n0 + 32 w + c survives
-        uint32_t kw0 = 0xffffffffu, kw1 = 0xffffffffu;
-        if constexpr (drop_on) {
-          kw0 = drop_keep_word(rowh, (uint32_t)(n0 >> 5), p.drop.thr8);
-          kw1 = drop_keep_word(rowh, (uint32_t)(n0 >> 5) + 1u, p.drop.thr8);
-        }
+        // dropout: the keep word of this row's 32 columns (dropout.cuh); bit c = column n0 + c survives
+        uint32_t kw0 = 0xffffffffu;
+        if constexpr (drop_on) kw0 = drop_keep_word(rowh, (uint32_t)(n0 >> 5), p.drop.thr8);
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          const int phys = (v ^ (lane & 7)) << 4;
-          const uint32_t kb8 = (v < 4 ? kw0 : kw1) >> ((8 * v) & 31);      // bits 0..7: this vector's columns
+        for (int v = 0; v < ECOLS / 8; ++v) {
+          const int phys = (v ^ ((lane >> 1) & 3)) << 4;                   // SWIZZLE_64B: 16-byte chunk ^ row bits 1..2
+          const uint32_t kb8 = kw0 >> (8 * v);                             // bits 0..7: this vector's columns
           float x[8];
 #pragma unroll
           for (int j = 0; j < 8; j += 4) {
@@ -416,7 +413,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 template <int BN, bool TMA_EPI>
 constexpr size_t smem_bytes() {
   return stages_for(BN) * (BM * BK * 2 + BN * BK * 2) + 1024 /*align*/ +
-         (TMA_EPI ? 1024 /*barriers*/ + EPI_WARPS * 2 * EBUF_BYTES + EPI_WARPS * 64 * 4 : 256 /*barriers*/ + EPI_WARPS * STG_BYTES);
+         (TMA_EPI ? 1024 /*barriers*/ + epi_warps(true) * 2 * EBUF_BYTES + epi_warps(true) * ECOLS * 4 : 256 /*barriers*/ + EPI_WARPS * STG_BYTES);
 }
 
 template <int BN, bool MN_MAJOR, typename TOUT, bool TMA_EPI, bool DROP = false>
@@ -431,7 +428,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& e
   }
   const int total = m_tiles * n_tiles * split;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  gemm_tc_kernel<BN, MN_MAJOR, TOUT, TMA_EPI, DROP><<<grid, NUM_THREADS, smem, st>>>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split);
+  gemm_tc_kernel<BN, MN_MAJOR, TOUT, TMA_EPI, DROP><<<grid, num_threads(TMA_EPI), smem, st>>>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split);
   MMI_CHECK_LAUNCH();
   return MMI_OK;
 }
@@ -500,10 +497,10 @@ int gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   if (tma_epi) {
     const void* aux = pe_add ? nullptr : (p.add ? p.add : p.mul_gelu_grad);
     const int64_t ld_aux = p.add ? p.ld_add : p.ld_mul;
-    if (!get_tensor_map(p.C, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldc, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &em.c)) return MMI_ECUDA;
+    if (!get_tensor_map(p.C, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldc, ECOLS, 32, CU_TENSOR_MAP_SWIZZLE_64B, &em.c)) return MMI_ECUDA;
     em.aux = em.c; em.c2 = em.c;
-    if (aux && !get_tensor_map(aux, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)ld_aux, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &em.aux)) return MMI_ECUDA;
-    if (p.preact && !get_tensor_map(p.preact, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ld_preact, 64, 32, CU_TENSOR_MAP_SWIZZLE_128B, &em.c2)) return MMI_ECUDA;
+    if (aux && !get_tensor_map(aux, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)ld_aux, ECOLS, 32, CU_TENSOR_MAP_SWIZZLE_64B, &em.aux)) return MMI_ECUDA;
+    if (p.preact && !get_tensor_map(p.preact, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ld_preact, ECOLS, 32, CU_TENSOR_MAP_SWIZZLE_64B, &em.c2)) return MMI_ECUDA;
     if (p.drop.thr8 != 0u) {
       if (bn == 256) return launch<256, false, __nv_bfloat16, true, true>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st);
       return launch<128, false, __nv_bfloat16, true, true>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st);

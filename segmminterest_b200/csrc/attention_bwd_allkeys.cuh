@@ -32,6 +32,7 @@ struct AKBars {
   // t + 2, so two alternating barriers are enough.
   uint64_t kv_full[AK_MAXT], kv_empty[AK_MAXT], q_full[2], q_empty[2], a_ready, s_free, p_ready[2], p_free, dq_ready, dq_free, done, acc_free;
   uint32_t tmem_slot, pad;
+  uint32_t kmask[2][AK_MAXT * 4];   // [item parity][key tile][lane quarter]: bit l = key (tile, quarter, l) exists and is unmasked
 };
 
 template <bool DROP>
@@ -84,6 +85,27 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
       rh_n[u] = DROP ? drop_rowhash(p.drop.key, (uint64_t)(((int64_t)b * p.H + h) * p.Lq + qi)) : 0u;
     }
   };
+  // key-validity words of item (b, .), built by the producer warp one item ahead (coalesced byte loads + ballots): the softmax
+  // threads used to fetch their own mask bytes at the start of an item -- five dependent global loads in front of its first tile
+  auto fetch_mask = [&](int b, int slot) {
+    uint8_t v[AK_MAXT * 4];                                // every byte load in flight before the first ballot needs one
+#pragma unroll
+    for (int j = 0; j < AK_MAXT; ++j) {
+      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
+      const int Lk = blk ? p.Lk[1] : p.Lk[0];
+      const uint8_t* mk = (blk ? p.mask_k[1] : p.mask_k[0]) + (int64_t)b * Lk;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int kj = kt * QT + q4 * 32 + lane;
+        v[j * 4 + q4] = (j < NT && kj < Lk) ? __ldg(mk + kj) : (uint8_t)0;
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < AK_MAXT * 4; ++x) {
+      const uint32_t word = __ballot_sync(0xffffffffu, v[x] != 0);
+      if (lane == 0) bars->kmask[slot][x] = word;
+    }
+  };
   if (warp == 0) {
     if (elect_one()) {
       for (int j = 0; j < AK_MAXT; ++j) { mbar_init(&bars->kv_full[j], 1); mbar_init(&bars->kv_empty[j], 1); }
@@ -100,22 +122,8 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
       fence_barrier_init();
     }
     __syncwarp();
-    if ((int)blockIdx.x < n_items) fetch(blockIdx.x / p.H, blockIdx.x % p.H, 0);
+    if ((int)blockIdx.x < n_items) { fetch(blockIdx.x / p.H, blockIdx.x % p.H, 0); fetch_mask(blockIdx.x / p.H, 0); }
   }
-  // ---- softmax threads: which of their key rows (one per key tile) exist / are unmasked in item (b, .)
-  auto key_bits = [&](int b, uint32_t& kin, uint32_t& mk) {
-    const int row = (warp & 3) * 32 + lane;
-    kin = 0u; mk = 0u;
-    for (int j = 0; j < NT; ++j) {
-      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
-      const int Lk = blk ? p.Lk[1] : p.Lk[0];
-      const int kj = kt * QT + row;
-      if (kj < Lk) {
-        kin |= 1u << j;
-        if ((blk ? p.mask_k[1] : p.mask_k[0])[(int64_t)b * Lk + kj] != 0) mk |= 1u << j;
-      }
-    }
-  };
   if (warp == 2) TRACE(4090);
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_slot)), "r"(AK_TMEM_COLS) : "memory");
@@ -169,7 +177,10 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
         }
       }
       if (i + 1 < T) fetch(b, h, i + 1);
-      else if (w + (int)gridDim.x < n_items) fetch((w + gridDim.x) / p.H, (w + gridDim.x) % p.H, 0);
+      else if (w + (int)gridDim.x < n_items) {
+        fetch((w + gridDim.x) / p.H, (w + gridDim.x) % p.H, 0);
+        fetch_mask((w + gridDim.x) / p.H, (n + 1) & 1);    // (its last readers were the softmax warps at the start of item n - 1)
+      }
     }
     }
   } else if (warp == 1) {
@@ -362,19 +373,35 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
         }
       }
     };
+    // the END of an item -- dQ of its last query tile, dK / dV of its last key tile -- is not waited for: it is picked up
+    // behind the first key tile of the NEXT item, while the tensor pipe already works on that tile's products (which wait for
+    // dq_free / acc_free, arrived here).  At one query tile per item this tail was 1/5 of the item.
+    int pend_b = -1, pend_h = 0, pend_n = 0;
+    uint32_t pend_act = 0u;
+    auto finish_item = [&](int gq) {                      // gq = global count of the item's last query tile
+      drain(pend_b, pend_h, T - 1, gq);
+      mbar_wait(&bars->done, pend_n & 1);
+      if (warp == 2 && pend_n < 20) TRACE(4000 + pend_n * 4 + 2);
+      drain_kv(pend_b, pend_h, NT - 1, pend_act);
+      tcgen05_fence_before();
+      mbar_arrive(&bars->acc_free);                       // (every tcgen05.ld of this thread has completed)
+      if (warp == 2 && pend_n < 20) TRACE(4000 + pend_n * 4 + 3);
+      pend_b = -1;
+    };
     int t = 0, g = 0;
-    uint32_t kin_next = 0u, mk_next = 0u;
-    if ((int)blockIdx.x < n_items) key_bits(blockIdx.x / p.H, kin_next, mk_next);
     for (int w = blockIdx.x, n = 0; w < n_items; w += gridDim.x, ++n) {
     const int b = w / p.H, h = w % p.H;
-    const uint32_t kin_bits = kin_next, mk_bits = mk_next;
-    if (w + (int)gridDim.x < n_items) key_bits((w + gridDim.x) / p.H, kin_next, mk_next);   // the next item's mask bytes: in flight early
+    mbar_wait_a(q_full_a + (g & 1) * 8, (g >> 1) & 1);    // the item's first query tile: its arrival also publishes kmask[n & 1]
+    uint32_t mk_bits = 0u;                                 // bit j: this thread's key of tile j exists and is unmasked
     uint32_t act_bits = 0u, allmk_bits = 0u;               // warp-uniform: tile j has a real key in this lane quarter / no masked key
     for (int j = 0; j < NT; ++j) {
-      if (__any_sync(0xffffffffu, (kin_bits >> j) & 1u)) act_bits |= 1u << j;
-      if (__all_sync(0xffffffffu, (mk_bits >> j) & 1u)) allmk_bits |= 1u << j;
+      const int blk = j < nt0 ? 0 : 1, kt = blk ? j - nt0 : j;
+      const uint32_t word = bars->kmask[n & 1][j * 4 + qd];
+      mk_bits |= ((word >> lane) & 1u) << j;
+      if (kt * QT + qd * 32 < (blk ? p.Lk[1] : p.Lk[0])) act_bits |= 1u << j;
+      if (word == 0xffffffffu) allmk_bits |= 1u << j;
     }
-    if (h != cur_h) { flush(); cur_h = h; }
+    if (n == 0) cur_h = h;
     if (warp == 2 && n < 20) TRACE(4000 + n * 4);
     for (int i = 0; i < T; ++i, ++g) {
       const int st = g & 1;
@@ -489,20 +516,17 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
         if (j == 0 && i >= 1) drain(b, h, i - 1, g - 1);   // the previous query tile's dQ: complete long ago, never waited for
         // last query tile: dK / dV of the previous key tile are final (p_free of its products was waited for above) and
         // leave while the tensor pipe works on this tile's products
+        if (i == 0 && j == 0 && pend_b >= 0) {             // the previous item's tail, then (maybe) a new head
+          finish_item(g - 1);
+          if (h != cur_h) { flush(); cur_h = h; }
+        }
         if (i == T - 1 && j >= 1) drain_kv(b, h, j - 1, act_bits);
       }
     }
     if (warp == 2 && n < 20) TRACE(4000 + n * 4 + 1);
-    drain(b, h, T - 1, g - 1);
-    // ---- the last key tile's accumulators
-    mbar_wait(&bars->done, n & 1);
-    tcgen05_fence_after();
-    if (warp == 2 && n < 20) TRACE(4000 + n * 4 + 2);
-    drain_kv(b, h, NT - 1, act_bits);
-    tcgen05_fence_before();
-    mbar_arrive(&bars->acc_free);                         // (every tcgen05.ld of this thread has completed: tmem_ld_wait above)
-    if (warp == 2 && n < 20) TRACE(4000 + n * 4 + 3);
+    pend_b = b; pend_h = h; pend_n = n; pend_act = act_bits;
     }
+    if (pend_b >= 0) finish_item(g - 1);
     flush();
     if (lane == 0) bulk_wait0();                          // the staging tiles stay valid until the last stores have read them
     __syncwarp();

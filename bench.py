@@ -171,11 +171,13 @@ def reference_arm(args, wl):
     print(json.dumps(line), flush=True)
 
 
-def fp32_leg(args, wl, table, dev, batch=64, steps=2):
-    """The strict-parity fp32 mode (the reference's own precision) on the same workload at a reduced batch."""
+def fp32_leg(args, wl, table, dev, batch=64, steps=2, split_tc=True):
+    """The strict-parity fp32 mode (the reference's own precision) on the same workload at a reduced batch.
+    split_tc (default): GEMMs on the tensor cores as split-bf16 products; False: the FFMA kernels (MMI_FP32_TC=0)."""
     from segmminterest_b200.model import build_model
     from segmminterest_b200.train import TrainStep
     torch.manual_seed(42)
+    os.environ["MMI_FP32_TC"] = "1" if split_tc else "0"
     m = build_model(model_args("fp32"), din=wl.din, max_usr_len=wl.lt).to(dev)
     m.train(args.dropout > 0)
     ts = TrainStep(m, table, global_batch=batch, dropout=args.dropout)
@@ -192,8 +194,11 @@ def fp32_leg(args, wl, table, dev, batch=64, steps=2):
     ms = e0.elapsed_time(e1) / steps
     del ts, m
     torch.cuda.empty_cache()
-    return {"value": batch / (ms * 1e-3), "unit": "interactions/s", "ms_per_step": ms, "batch": batch,
-            "note": "fp32 FFMA path (logits / gradients within 1e-4 of the reference), same workload shapes, reduced batch"}
+    os.environ.pop("MMI_FP32_TC", None)
+    note = ("fp32 mode (logits / gradients within 1e-4 of the reference): GEMMs as six bf16 products of an exact three-term split on "
+            "the tensor cores, attention / LayerNorm fp32 SIMT; same workload shapes, reduced batch" if split_tc else
+            "fp32 mode with the FFMA GEMM kernels (MMI_FP32_TC=0)")
+    return {"value": batch / (ms * 1e-3), "unit": "interactions/s", "ms_per_step": ms, "batch": batch, "note": note}
 
 
 def loader_leg(dev, n=256):
@@ -447,6 +452,7 @@ def main():
     extras = {}
     if rank == 0 and world == 1 and not args.no_extras:
         extras["fp32_mode"] = fp32_leg(args, wl, table, dev)
+        extras["fp32_ffma_mode"] = fp32_leg(args, wl, table, dev, split_tc=False)
         extras["loader"] = loader_leg(dev)
 
     line = {"metric": "train_interactions_per_s", "value": value, "unit": "interactions/s", "n_gpus": world, "steps": K, "warmup": W,

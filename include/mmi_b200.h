@@ -122,8 +122,16 @@ typedef struct {
   int mul_is_grad;     /* 1: mul_gelu_grad already holds gelu'(z); 2: it holds a ReLU (+ dropout) output */
   mmi_dropout drop;    /* applied to act(z) before `add`; thr8 = 0: off (not with accumulate / split-K) */
   float mul_scale;     /* mul_is_grad == 2: survivors' scale of the dropout that followed the ReLU (1 = none) */
+  /* fp32 operands on the tensor cores (impl = MMI_IMPL_TC with in_dtype = MMI_F32): A and B are split into three bf16
+   * terms each (x = hi + mid + lo, 24 mantissa bits) in this caller-owned workspace and the six products
+   * hi*hi, hi*mid, mid*hi, mid*mid, hi*lo, lo*hi accumulate in the fp32 TMEM accumulator -- fp32-grade results (the
+   * dropped terms are below 2^-24) at ~1/6 of the bf16 rate instead of the FFMA path's 1/40.
+   * At least mmi_gemm_split_workspace(layout, M, N, K) bytes, 1024-byte aligned.                                     */
+  void* split_ws;
+  int64_t split_ws_bytes;
 } mmi_gemm_args;
 int mmi_gemm(const mmi_gemm_args* args, mmi_stream_t stream);
+int64_t mmi_gemm_split_workspace(int layout, int64_t M, int64_t N, int64_t K);
 
 /* ---- AdaptiveAvgPool1d(out_len) along the token axis (the CrossMLP ablation, models/encoder.py:395,504-506):
  * x [B, L, d] -> y [B, out_len, d], window j = [floor(j L / out_len), ceil((j + 1) L / out_len)).

@@ -31,7 +31,8 @@ class GemmArgs(C.Structure):
                 ("mul_gelu_grad", c_p), ("ld_mul", i64),
                 ("add", c_p), ("ld_add", i64), ("add_mod", i64), ("add_dtype", C.c_int),
                 ("accumulate", C.c_int), ("split_k", C.c_int), ("save_act_grad", C.c_int), ("mul_is_grad", C.c_int),
-                ("drop", Dropout), ("mul_scale", C.c_float)]
+                ("drop", Dropout), ("mul_scale", C.c_float),
+                ("split_ws", c_p), ("split_ws_bytes", i64)]
 
 
 class AttnBlock(C.Structure):
@@ -69,6 +70,7 @@ _SIGS = {
     "mmi_has_tc": (C.c_int, []),
     "mmi_gather_l1norm_fwd": (C.c_int, [c_p, C.c_int, i64, C.c_int, c_p, i64, c_p, C.c_int, c_p, C.c_int, c_p]),
     "mmi_gemm": (C.c_int, [C.POINTER(GemmArgs), c_p]),
+    "mmi_gemm_split_workspace": (i64, [C.c_int, i64, i64, i64]),
     "mmi_adaptive_pool_fwd": (C.c_int, [c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p]),
     "mmi_adaptive_pool_bwd": (C.c_int, [c_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_p, c_p]),
     "mmi_colsum_acc": (C.c_int, [c_p, C.c_int, i64, C.c_int, i64, c_p, c_p, i64, c_p]),

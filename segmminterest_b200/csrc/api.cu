@@ -27,6 +27,8 @@ extern "C" int mmi_version(void) { return 100; }
 extern "C" const char* mmi_last_error(void) { return g_err; }
 extern "C" int mmi_has_tc(void) { return tc_available() ? 1 : 0; }
 
+extern "C" int64_t mmi_gemm_split_workspace(int layout, int64_t M, int64_t N, int64_t K) { return gemm_split_workspace(layout, M, N, K); }
+
 extern "C" int mmi_gemm(const mmi_gemm_args* a, mmi_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   MMI_CHECK_ARG(a != nullptr, "gemm: null args");
@@ -49,6 +51,7 @@ extern "C" int mmi_gemm(const mmi_gemm_args* a, mmi_stream_t stream) {
   p.save_act_grad = a->save_act_grad; p.mul_is_grad = a->mul_is_grad;
   p.drop = make_drop(a->drop);
   p.mul_scale = a->mul_scale;
+  p.split_ws = a->split_ws; p.split_ws_bytes = a->split_ws_bytes;
   MMI_CHECK_ARG(a->act >= MMI_ACT_NONE && a->act <= MMI_ACT_RELU, "gemm: bad activation %d", a->act);
   MMI_CHECK_ARG(!(a->act == MMI_ACT_RELU && a->preact), "gemm: ReLU saves nothing (its backward reads the layer's output)");
   MMI_CHECK_ARG(p.drop.thr8 < 256u, "gemm: dropout thr8 must be < 256");

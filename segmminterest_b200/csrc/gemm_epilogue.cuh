@@ -23,6 +23,9 @@ struct GemmParams {
   int mul_is_grad;
   DropParams drop;     // dropout of act(z) before `add` (and of the saved gelu'(z)); thr8 = 0: off
   float mul_scale;     // mul_is_grad == 2: y *= (mul > 0 ? mul_scale : 0)
+  void* split_ws = nullptr; int64_t split_ws_bytes = 0;   // fp32 operands on the tensor cores (three-term bf16 split)
+  int split_terms = 0;  // tcgen05 kernel: 6 = the K loop walks six (A term, B term) segment pairs of seg_kb k-blocks each
+  int seg_kb = 0;
 };
 
 // 4 consecutive columns n..n+3 of row m.  `lead` = this CTA owns the bias/add terms
@@ -144,16 +147,24 @@ __device__ __forceinline__ void gemm_epilogue2(const GemmParams& p, int64_t m, i
     k0 = (w & 1u) ? p.drop.scale : 0.f;
     k1 = (w & 2u) ? p.drop.scale : 0.f;
   }
-  if (p.preact != nullptr)
-    store2(reinterpret_cast<TIN*>(p.preact) + m * p.ld_preact + n,
-           p.save_act_grad ? make_float2(gelu_grad_fast(v0) * k0, gelu_grad_fast(v1) * k1) : make_float2(v0, v1));
-  if (p.act == MMI_ACT_GELU) { v0 = gelu_fast(v0); v1 = gelu_fast(v1); }
+  // fp32 side operands = the strict-parity mode (split-bf16 products): exact erf GELU like the FFMA path
+  constexpr bool kExact = sizeof(TIN) == 4;
+  if (p.preact != nullptr) {
+    float2 z = make_float2(v0, v1);
+    if (p.save_act_grad) z = kExact ? make_float2(gelu_grad_f(v0) * k0, gelu_grad_f(v1) * k1) : make_float2(gelu_grad_fast(v0) * k0, gelu_grad_fast(v1) * k1);
+    store2(reinterpret_cast<TIN*>(p.preact) + m * p.ld_preact + n, z);
+  }
+  if (p.act == MMI_ACT_GELU) {
+    if constexpr (kExact) { v0 = gelu_f(v0); v1 = gelu_f(v1); }
+    else { v0 = gelu_fast(v0); v1 = gelu_fast(v1); }
+  }
   else if (p.act == MMI_ACT_RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
   v0 *= k0; v1 *= k1;
   if (p.mul_gelu_grad != nullptr) {
     const float2 z = load2(reinterpret_cast<const TIN*>(p.mul_gelu_grad) + m * p.ld_mul + n);
     if (p.mul_is_grad == 2) { v0 = z.x > 0.f ? v0 * p.mul_scale : 0.f; v1 = z.y > 0.f ? v1 * p.mul_scale : 0.f; }
     else if (p.mul_is_grad) { v0 *= z.x; v1 *= z.y; }
+    else if constexpr (kExact) { v0 *= gelu_grad_f(z.x); v1 *= gelu_grad_f(z.y); }
     else { v0 *= gelu_grad_fast(z.x); v1 *= gelu_grad_fast(z.y); }
   }
   if (lead && p.add != nullptr) {
@@ -181,6 +192,7 @@ __device__ __forceinline__ void gemm_epilogue2(const GemmParams& p, int64_t m, i
 
 int gemm_simt(const GemmParams& p, cudaStream_t st);
 int gemm_tc(const GemmParams& p, cudaStream_t st);
+int64_t gemm_split_workspace(int layout, int64_t M, int64_t N, int64_t K);
 bool tc_available();
 
 }  // namespace mmi

@@ -68,11 +68,20 @@ constexpr int EBUF_BYTES = 32 * ECOLS * 2;      // 32 rows x 32 bf16 (one SWIZZL
 
 // DROP (TMA epilogue only): dropout of act(z) fused into the epilogue.  The no-dropout instantiation is byte-for-byte the
 // kernel that existed before dropout was added; the generic register epilogue handles dropout at run time.
-template <int BN, bool MN_MAJOR, typename TOUT, bool TMA_EPI, bool DROP = false>
+// TAUX: element type of the side operands (preact / mul_gelu_grad) of the register epilogue: bf16, or float for the
+// split-fp32 mode (three bf16 terms per operand, six segment products: see GemmParams::split_terms).
+template <int BN, bool MN_MAJOR, typename TOUT, bool TMA_EPI, bool DROP = false, typename TAUX = __nv_bfloat16>
 __global__ void __launch_bounds__(num_threads(TMA_EPI), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ EpiMaps em, const GemmParams p, int m_tiles, int n_tiles, int num_kb, int split) {
   extern __shared__ uint8_t smem_raw[];
+  // split-fp32 mode (TAUX = float): k-block range [kb0, kb1) of a tile is PER TERM; the loops walk the six (A term, B term)
+  // pairs over it.  hi*hi goes to the tile's main accumulator, the five small products to a second one (the tensor core
+  // truncates every addend to the accumulator's ulp: ~0.5 ulp per MMA step towards zero -- the small terms must not
+  // spend steps on the main accumulator, and split-K slices keep the hi*hi chain short); the epilogue adds the two.
+  constexpr bool SPLIT = sizeof(TAUX) == 4;
+  constexpr uint32_t TMEM_COLS = SPLIT ? 4 * BN : 2 * BN;
+  static_assert(!SPLIT || BN == 128, "split-fp32 mode: two accumulators per tile need BN = 128");
   constexpr int STAGES = stages_for(BN);
   constexpr uint32_t A_BYTES = BM * BK * 2;
   constexpr uint32_t B_BYTES = BN * BK * 2;
@@ -101,7 +110,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     fence_barrier_init();
   }
   if (warp == 1) {  // one warp owns TMEM alloc + dealloc; 2 accumulator buffers of BN fp32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(2 * BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
@@ -116,22 +125,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint32_t stage = 0, phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const TileInfo ti = get_tile(t, m_tiles, n_tiles, num_kb, split);
-      for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
+      const int len = ti.kb1 - ti.kb0, n_it = SPLIT ? 6 * len : len;
+      for (int i2 = 0; i2 < n_it; ++i2) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        // split-fp32 mode: pair sg = i2 / len of A terms (hi, hi, mid, mid, hi, lo) x B terms (hi, mid, hi, mid, lo, hi);
+        // term t of an operand is the block of seg_kb k-blocks starting at t * seg_kb
+        int ka = ti.kb0 + i2, kbb = ka;
+        if constexpr (SPLIT) {
+          const int sg = i2 / len, r = i2 - sg * len;
+          ka = (int)((0x201100u >> (4 * sg)) & 0xfu) * p.seg_kb + ti.kb0 + r;
+          kbb = (int)((0x021010u >> (4 * sg)) & 0xfu) * p.seg_kb + ti.kb0 + r;
+        }
         if (elect_one()) {
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           if constexpr (!MN_MAJOR) {
-            tma_load_2d(&tma_a, &full_bar[stage], sa, kb * BK, ti.m_blk * BM);   // box {64 k, 128 rows}
-            tma_load_2d(&tma_b, &full_bar[stage], sb, kb * BK, ti.n_blk * BN);   // box {64 k, BN rows}
+            tma_load_2d(&tma_a, &full_bar[stage], sa, ka * BK, ti.m_blk * BM);    // box {64 k, 128 rows}
+            tma_load_2d(&tma_b, &full_bar[stage], sb, kbb * BK, ti.n_blk * BN);   // box {64 k, BN rows}
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)                                    // boxes {64 mn, 64 k}
-              tma_load_2d(&tma_a, &full_bar[stage], sa + j * (64 * BK * 2), ti.m_blk * BM + j * 64, kb * BK);
+              tma_load_2d(&tma_a, &full_bar[stage], sa + j * (64 * BK * 2), ti.m_blk * BM + j * 64, ka * BK);
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(&tma_b, &full_bar[stage], sb + j * (64 * BK * 2), ti.n_blk * BN + j * 64, kb * BK);
+              tma_load_2d(&tma_b, &full_bar[stage], sb + j * (64 * BK * 2), ti.n_blk * BN + j * 64, kbb * BK);
           }
         }
         __syncwarp();
@@ -148,10 +166,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t buf = it & 1, use = it >> 1;
       mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);   // epilogue drained this accumulator
       tcgen05_fence_after();
-      const uint32_t d_tmem = tbase + buf * BN;
-      for (int kb = ti.kb0; kb < ti.kb1; ++kb) {
+      const uint32_t d_main = tbase + buf * (SPLIT ? 2 * BN : BN);
+      const int len = ti.kb1 - ti.kb0, n_it = SPLIT ? 6 * len : len;
+      for (int i2 = 0; i2 < n_it; ++i2) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
+        // (split mode: pair 0 = hi*hi -> main accumulator; pairs 1..5 -> the second accumulator, BN columns further)
+        const bool small = SPLIT && i2 >= len;
+        const uint32_t d_tmem = uniform(small ? d_main + BN : d_main);
+        const uint32_t first = uniform((i2 == 0 || (SPLIT && i2 == len)) ? 1u : 0u);
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
@@ -165,10 +188,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               ad = make_smem_desc(sa + k * (UMMA_K * 128), 64 * BK * 2, 1024);
               bd = make_smem_desc(sb + k * (UMMA_K * 128), 64 * BK * 2, 1024);
             }
-            umma_f16(d_tmem, ad, bd, idesc, (kb > ti.kb0 || k > 0) ? 1u : 0u);
+            umma_f16(d_tmem, ad, bd, idesc, (!first || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);             // smem slot free once these MMAs retire
-          if (kb == ti.kb1 - 1) umma_commit(&tmem_full[buf]);   // accumulator complete -> epilogue
+          if (i2 == n_it - 1) umma_commit(&tmem_full[buf]);   // accumulator(s) complete -> epilogue
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -372,10 +395,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       for (int cc = half; cc < CHUNKS; cc += 2) {
         {
           uint32_t r0[32], r1[32];
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN + cc * STG_COLS;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (SPLIT ? 2 * BN : BN) + cc * STG_COLS;
           tmem_ld_32x32(taddr, r0);
           tmem_ld_32x32(taddr + 32, r1);
           tmem_ld_wait();
+          if constexpr (SPLIT) {                           // + the five small products (round-to-nearest adds)
+            uint32_t s0[32];
+            tmem_ld_32x32(taddr + BN, s0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) r0[c] = __float_as_uint(__uint_as_float(r0[c]) + __uint_as_float(s0[c]));
+            tmem_ld_32x32(taddr + BN + 32, s0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) r1[c] = __float_as_uint(__uint_as_float(r1[c]) + __uint_as_float(s0[c]));
+          }
 #pragma unroll
           for (int v = 0; v < 8; ++v) {
             *reinterpret_cast<uint4*>(stg + lane * STG_COLS + ((v ^ (lane & 7)) << 2)) = make_uint4(r0[4 * v], r0[4 * v + 1], r0[4 * v + 2], r0[4 * v + 3]);
@@ -391,7 +425,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll 4
           for (int rr = 0; rr < rows; ++rr) {
             const float2 x = *reinterpret_cast<const float2*>(stg + rr * STG_COLS + (((lane >> 1) ^ (rr & 7)) << 2) + ((lane & 1) << 1));
-            gemm_epilogue2<__nv_bfloat16, TOUT>(p, m_base + rr, n, x.x, x.y, b0, b1, ti.lead, add_row);
+            gemm_epilogue2<TAUX, TOUT>(p, m_base + rr, n, x.x, x.y, b0, b1, ti.lead, add_row);
             if (++add_row == p.add_mod) add_row = 0;
           }
         }
@@ -405,7 +439,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -416,26 +450,85 @@ constexpr size_t smem_bytes() {
          (TMA_EPI ? 1024 /*barriers*/ + epi_warps(true) * 2 * EBUF_BYTES + epi_warps(true) * ECOLS * 4 : 256 /*barriers*/ + EPI_WARPS * STG_BYTES);
 }
 
-template <int BN, bool MN_MAJOR, typename TOUT, bool TMA_EPI, bool DROP = false>
+template <int BN, bool MN_MAJOR, typename TOUT, bool TMA_EPI, bool DROP = false, typename TAUX = __nv_bfloat16>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, const GemmParams& p, int m_tiles, int n_tiles,
                   int num_kb, int split, cudaStream_t st) {
   constexpr size_t smem = smem_bytes<BN, TMA_EPI>();
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MN_MAJOR, TOUT, TMA_EPI, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MN_MAJOR, TOUT, TMA_EPI, DROP, TAUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return MMI_ECUDA; }
     configured = true;
   }
   const int total = m_tiles * n_tiles * split;
   const int grid = total < kNumSMs ? total : kNumSMs;
-  gemm_tc_kernel<BN, MN_MAJOR, TOUT, TMA_EPI, DROP><<<grid, num_threads(TMA_EPI), smem, st>>>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split);
+  gemm_tc_kernel<BN, MN_MAJOR, TOUT, TMA_EPI, DROP, TAUX><<<grid, num_threads(TMA_EPI), smem, st>>>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split);
   MMI_CHECK_LAUNCH();
   return MMI_OK;
 }
 
 static bool tma_ok(const void* ptr, int64_t ld) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && ld % 8 == 0; }
 
+// ------------------------------------------------------------------------------ fp32 operands: three-term bf16 split
+// x = hi + mid + lo with hi = bf16(x), mid = bf16(x - hi), lo = bf16(x - hi - mid): 3 x 8 mantissa bits, exact for every
+// fp32 x in bf16's exponent range.  src [R, C] fp32 (row stride ld) -> three bf16 copies in dst:
+//   term_stride elements apart, each [Rp, ldd] with rows >= R and columns >= C (up to Cp) zero-filled.
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
+  h = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(h);
+  m = __float2bfloat16_rn(r1);
+  l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+}
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ src, int64_t ld, int64_t R, int64_t C, __nv_bfloat16* __restrict__ dst,
+                                                     int64_t ldd, int64_t Rp, int64_t Cp, int64_t term_stride) {
+  const int64_t cq = Cp / 4;                 // Cp is a multiple of 4
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Rp * cq; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cq, c = (i - r * cq) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < R) {
+      if (c + 3 < C && (ld & 3) == 0) { const float4 t = *reinterpret_cast<const float4*>(src + r * ld + c); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+      else { for (int j = 0; j < 4; ++j) if (c + j < C) v[j] = src[r * ld + c + j]; }
+    }
+    __nv_bfloat16 h[4], m[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split3(v[j], h[j], m[j], l[j]);
+    __nv_bfloat16* d = dst + r * ldd + c;
+    *reinterpret_cast<uint2*>(d) = *reinterpret_cast<uint2*>(h);
+    *reinterpret_cast<uint2*>(d + term_stride) = *reinterpret_cast<uint2*>(m);
+    *reinterpret_cast<uint2*>(d + 2 * term_stride) = *reinterpret_cast<uint2*>(l);
+  }
+}
+// transposing variant (the [K, N] operand of an NN product): src [R, C] -> terms [C, 3 x Rp] (term t at column t * Rp),
+// columns r >= R zero-filled up to Rp.  32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256) split3_transpose_kernel(const float* __restrict__ src, int64_t ld, int64_t R, int64_t C,
+                                                               __nv_bfloat16* __restrict__ dst, int64_t ldd, int64_t Rp) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < R && c < C) ? src[r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t c = c0 + j, r = r0 + tx;      // output row = source column
+    if (c < C && r < Rp) {
+      __nv_bfloat16 h, m, l;
+      split3(tile[tx][j], h, m, l);
+      dst[c * ldd + r] = h; dst[c * ldd + Rp + r] = m; dst[c * ldd + 2 * Rp + r] = l;
+    }
+  }
+}
+
+static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
 }  // namespace tc
+
+int64_t gemm_split_workspace(int layout, int64_t M, int64_t N, int64_t K) {
+  const int64_t Kp = tc::round_up(K, tc::BK);
+  if (layout == MMI_GEMM_TN) return 3 * Kp * (tc::round_up(M, 8) + tc::round_up(N, 8)) * 2 + 2048;
+  return (M + N) * 3 * Kp * 2 + 2048;
+}
 
 bool tc_available() {
   static int ok = -1;
@@ -453,15 +546,54 @@ bool tc_available() {
 int gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   using namespace tc;
   GemmParams p = p_in;
-  MMI_CHECK_ARG(p.in_dtype == MMI_BF16, "gemm_tc: inputs must be bf16");
+  if (p.in_dtype == MMI_F32) {
+    // split-fp32 mode: three bf16 terms per operand in the caller's workspace, then the bf16 kernel over six segment pairs
+    MMI_CHECK_ARG(p.out_dtype == MMI_F32, "gemm_tc: fp32 operands need an fp32 C");
+    MMI_CHECK_ARG(p.split_ws != nullptr && p.split_ws_bytes >= gemm_split_workspace(p.layout, p.M, p.N, p.K),
+                  "gemm_tc: fp32 operands need split_ws of mmi_gemm_split_workspace() bytes");
+    const int64_t Kp = round_up(p.K, BK);
+    __nv_bfloat16* wa = reinterpret_cast<__nv_bfloat16*>((reinterpret_cast<uintptr_t>(p.split_ws) + 1023) & ~static_cast<uintptr_t>(1023));
+    const float* A = reinterpret_cast<const float*>(p.A);
+    const float* B = reinterpret_cast<const float*>(p.B);
+    auto blocks = [](int64_t n) { const int64_t b = (n + 255) / 256; return (unsigned)(b < 148 * 16 ? (b > 0 ? b : 1) : 148 * 16); };
+    __nv_bfloat16* wb;
+    if (p.layout == MMI_GEMM_TN) {      // A [K, M], B [K, N]: the terms are stacked along the rows (k)
+      const int64_t lda3 = round_up(p.M, 8), ldb3 = round_up(p.N, 8);
+      wb = wa + 3 * Kp * lda3;
+      split3_kernel<<<blocks(Kp * lda3 / 4), 256, 0, st>>>(A, p.lda, p.K, p.M, wa, lda3, Kp, lda3, Kp * lda3);
+      split3_kernel<<<blocks(Kp * ldb3 / 4), 256, 0, st>>>(B, p.ldb, p.K, p.N, wb, ldb3, Kp, ldb3, Kp * ldb3);
+      p.lda = lda3; p.ldb = ldb3;
+    } else {                             // NT: A [M, K], B [N, K]; NN: B [K, N] is transposed on the way
+      wb = wa + p.M * 3 * Kp;
+      split3_kernel<<<blocks(p.M * Kp / 4), 256, 0, st>>>(A, p.lda, p.M, p.K, wa, 3 * Kp, p.M, Kp, Kp);
+      if (p.layout == MMI_GEMM_NT) split3_kernel<<<blocks(p.N * Kp / 4), 256, 0, st>>>(B, p.ldb, p.N, p.K, wb, 3 * Kp, p.N, Kp, Kp);
+      else {
+        dim3 g((unsigned)((p.N + 31) / 32), (unsigned)(Kp / 32));
+        split3_transpose_kernel<<<g, 256, 0, st>>>(B, p.ldb, p.K, p.N, wb, 3 * Kp, Kp);
+      }
+      p.lda = 3 * Kp; p.ldb = 3 * Kp;
+      p.layout = MMI_GEMM_NT;
+    }
+    MMI_CHECK_LAUNCH();
+    p.A = wa; p.B = wb;
+    p.K = Kp;                            // one term; the kernel walks 6 x (Kp / 64) k-blocks
+    p.split_terms = 6; p.seg_kb = (int)(Kp / BK);
+  }
+  MMI_CHECK_ARG(p.in_dtype == MMI_BF16 || p.split_terms, "gemm_tc: inputs must be bf16 (or fp32 with a split workspace)");
   MMI_CHECK_ARG(p.layout == MMI_GEMM_NT || p.layout == MMI_GEMM_TN, "gemm_tc: layouts NT and TN only (dgrad uses the transposed weight shadow)");
   MMI_CHECK_ARG((reinterpret_cast<uintptr_t>(p.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.B) & 15) == 0, "gemm_tc: A/B must be 16-byte aligned");
   MMI_CHECK_ARG(p.lda % 8 == 0 && p.ldb % 8 == 0, "gemm_tc: lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
   const bool mn = p.layout == MMI_GEMM_TN;
-  const int bn = (p.N % 256 == 0) ? 256 : 128;
+  const int bn = (p.N % 256 == 0 && !p.split_terms) ? 256 : 128;   // split-fp32 mode: two accumulators per tile, BN = 128
   const int m_tiles = (int)((p.M + BM - 1) / BM), n_tiles = (int)((p.N + bn - 1) / bn);
-  const int num_kb = (int)((p.K + BK - 1) / BK);
+  const int num_kb = (int)((p.K + BK - 1) / BK);     // (split-fp32 mode: per term)
   int split = p.split_k;
+  if (p.split_terms && p.accumulate) {
+    // weight gradients (K = tokens): slices of <= 8 k-blocks per term keep the hi*hi chain at 32 MMA steps; the slices meet
+    // in C through round-to-nearest atomics
+    split = (num_kb + 7) / 8;
+    if (split > 4096) split = 4096;
+  }
   if (split <= 0) {  // auto: fill the 148 SMs
     split = kNumSMs / (m_tiles * n_tiles);
     if (split < 1) split = 1;
@@ -475,18 +607,20 @@ int gemm_tc(const GemmParams& p_in, cudaStream_t st) {
   p.split_k = split;
   CUtensorMap ta, tb;
   if (!mn) {
-    if (!get_tensor_map(p.A, (uint64_t)p.K, (uint64_t)p.M, (uint64_t)p.lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B, &ta)) return MMI_ECUDA;
-    if (!get_tensor_map(p.B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)p.ldb, BK, (uint32_t)bn, CU_TENSOR_MAP_SWIZZLE_128B, &tb)) return MMI_ECUDA;
+    const uint64_t kext = (uint64_t)p.K * (p.split_terms ? 3 : 1);       // split mode: the three terms side by side along k
+    if (!get_tensor_map(p.A, kext, (uint64_t)p.M, (uint64_t)p.lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B, &ta)) return MMI_ECUDA;
+    if (!get_tensor_map(p.B, kext, (uint64_t)p.N, (uint64_t)p.ldb, BK, (uint32_t)bn, CU_TENSOR_MAP_SWIZZLE_128B, &tb)) return MMI_ECUDA;
   } else {
-    if (!get_tensor_map(p.A, (uint64_t)p.M, (uint64_t)p.K, (uint64_t)p.lda, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B, &ta)) return MMI_ECUDA;
-    if (!get_tensor_map(p.B, (uint64_t)p.N, (uint64_t)p.K, (uint64_t)p.ldb, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B, &tb)) return MMI_ECUDA;
+    const uint64_t kext = (uint64_t)p.K * (p.split_terms ? 3 : 1);
+    if (!get_tensor_map(p.A, (uint64_t)p.M, kext, (uint64_t)p.lda, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B, &ta)) return MMI_ECUDA;
+    if (!get_tensor_map(p.B, (uint64_t)p.N, kext, (uint64_t)p.ldb, 64, BK, CU_TENSOR_MAP_SWIZZLE_128B, &tb)) return MMI_ECUDA;
   }
   const bool f32out = p.out_dtype == MMI_F32;
   MMI_CHECK_ARG(f32out || p.out_dtype == MMI_BF16, "gemm_tc: bad out dtype");
   EpiMaps em;
   memset(&em, 0, sizeof(em));
   // TMA epilogue: bf16 output tiles leave through shared memory; at most one tile-shaped bf16 side operand
-  bool tma_epi = !mn && !f32out && !p.accumulate && split == 1 && tma_ok(p.C, p.ldc) && !(p.add && p.mul_gelu_grad);
+  bool tma_epi = !p.split_terms && !mn && !f32out && !p.accumulate && split == 1 && tma_ok(p.C, p.ldc) && !(p.add && p.mul_gelu_grad);
   const bool pe_add = p.add != nullptr && p.add_mod < p.M;   // position table: fp32 rows read directly, no TMA box
   if (tma_epi && p.add)
     tma_epi = pe_add ? (p.add_dtype == MMI_F32 && p.add_mod > 0 && p.ld_add % 4 == 0 && (reinterpret_cast<uintptr_t>(p.add) & 15) == 0 && !p.mul_gelu_grad)
@@ -508,6 +642,9 @@ int gemm_tc(const GemmParams& p_in, cudaStream_t st) {
     if (bn == 256) return launch<256, false, __nv_bfloat16, true>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st);
     return launch<128, false, __nv_bfloat16, true>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st);
   }
+  if (p.split_terms)     // fp32 side operands, exact erf GELU, two accumulators per tile
+    return mn ? launch<128, true, float, false, false, float>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st)
+              : launch<128, false, float, false, false, float>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st);
 #define MMI_TC_LAUNCH(BN_, MN_)                                                                                         \
   (f32out ? launch<BN_, MN_, float, false>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st)                          \
           : launch<BN_, MN_, __nv_bfloat16, false>(ta, tb, em, p, m_tiles, n_tiles, num_kb, split, st))

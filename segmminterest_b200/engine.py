@@ -138,6 +138,12 @@ class Engine:
         self.sparse_tables = False
         self.table_rows = []       # [(group key, tw, ids [B], rows [B, tw])] of the backward in flight
         self.use_tc = cfg.precision == "bf16" and bool(_lib.load().mmi_has_tc())
+        # fp32 mode: GEMMs on the tensor cores as six bf16 x bf16 products of an exact three-term split of each fp32 operand
+        # (hi*hi in one TMEM accumulator, the five small products in a second one, weight gradients in slices of 512 tokens
+        # that meet through round-to-nearest atomics: 4.7e-7 / 3.2e-6 relative at K = 512 / 3072 against 4.1e-7 / 9.9e-7 for
+        # the FFMA kernel, profiles/r02_s12_split_gemm_error.txt).  MMI_FP32_TC=0 keeps the FFMA kernels.  Attention,
+        # LayerNorm and the loss stay fp32 SIMT.
+        self.fp32_tc = cfg.precision != "bf16" and bool(_lib.load().mmi_has_tc()) and os.environ.get("MMI_FP32_TC", "1") != "0"
         # attention backward on the tensor-core path: "all" = one CTA per (b, h) owning every key (default, <= 640 keys),
         # "fused" = one kernel per key block with dQ reduced through an fp32 accumulator (measured slower than the pair it
         # replaces, kept for A/B runs), anything else = the dq + dk/dv kernel pair (also the fallback for long histories)
@@ -421,6 +427,7 @@ class Engine:
         main...SegMM.py:272-273; our own data path fuses it into the gather); usr_id / vid_id int64 [B] for towers with
         ID inputs.  Returns fp32 logits [B, Lv] before the position bias (a workspace tensor: clone before the next call)."""
         cfg = self.cfg
+        ops.FP32_TC["on"] = self.fp32_tc
         self.ensure_bound()
         if refresh:                      # bf16 weight shadows; a micro-batched step refreshes them once, not per slice
             self.refresh_low_precision()
@@ -717,6 +724,7 @@ class Engine:
         sv = self._saved
         if sv is None or "dlogits" not in sv:
             raise RuntimeError("backward() called before forward()+loss()")
+        ops.FP32_TC["on"] = self.fp32_tc
         self.bind_grads()
         cfg = self.cfg
         T = self.act_dtype

@@ -77,13 +77,36 @@ def gather_l1norm(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor, mas
     LaunchCounter.n += 1
 
 
+# fp32 GEMMs routed to the split-bf16 tensor-core path (set by the engine for precision="fp32" on a tcgen05 device;
+# MMI_FP32_TC=0 keeps the FFMA kernels).  One shared workspace, grown to the largest product seen.
+FP32_TC = {"on": False, "ws": None}
+
+
+def _split_ok(layout, M, N, K, lda, ldb):
+    """shapes the tcgen05 kernel takes: N a multiple of 8 (fp32 epilogue pairs + TMA strides of a TN operand), M >= 1"""
+    if layout == GEMM_TN:
+        return N % 8 == 0 and M % 8 == 0
+    return N % 8 == 0
+
+
 def gemm(layout, impl, A, lda, B, ldb, Cm, ldc, M, N, K, *, bias=None, act=ACT_NONE, preact=None, mul_gelu_grad=None,
          add=None, add_mod=0, ld_add=0, accumulate=False, split_k=1, in_dtype=None, out_dtype=None, save_act_grad=False,
          mul_is_grad=False, drop=None, mul_scale=1.0):
     lib = _lib.load()
     a = _lib.GemmArgs()
+    in_dt = dt(A) if in_dtype is None else in_dtype
+    if impl == IMPL_SIMT and FP32_TC["on"] and in_dt == F32 and (dt(Cm) if out_dtype is None else out_dtype) == F32 and _split_ok(layout, M, N, K, lda, ldb):
+        # strict-parity mode on the tensor cores: fp32 operands as three bf16 terms each, six products in fp32 accumulators
+        impl = IMPL_TC
+        need = int(lib.mmi_gemm_split_workspace(layout, M, N, K))
+        ws = FP32_TC.get("ws")
+        dev = getattr(A, "device", None) or (ws.device if ws is not None else torch.device("cuda", torch.cuda.current_device()))
+        if ws is None or ws.numel() < need or ws.device != dev:
+            FP32_TC["ws"] = ws = None          # release before growing
+            FP32_TC["ws"] = ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        a.split_ws, a.split_ws_bytes = ws.data_ptr(), ws.numel()
     a.layout, a.impl = layout, impl
-    a.in_dtype = dt(A) if in_dtype is None else in_dtype
+    a.in_dtype = in_dt
     a.out_dtype = dt(Cm) if out_dtype is None else out_dtype
     a.M, a.N, a.K = M, N, K
     a.A, a.lda, a.B, a.ldb, a.C, a.ldc = A.data_ptr(), lda, B.data_ptr(), ldb, Cm.data_ptr(), ldc

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FIELDS = {
     "mmi_dropout": ["key", "thr8", "scale"],
     "mmi_gemm_args": ["layout", "M", "A", "lda", "C", "bias", "act", "preact", "mul_gelu_grad", "add", "add_mod", "add_dtype", "accumulate",
-                      "split_k", "save_act_grad", "mul_is_grad", "drop", "mul_scale"],
+                      "split_k", "save_act_grad", "mul_is_grad", "drop", "mul_scale", "split_ws", "split_ws_bytes"],
     "mmi_attn_block": ["q", "ldq", "mask_k", "Lk", "dq", "lddv", "dbq", "dbv"],
     "mmi_attn_args": ["dtype", "Lq", "mask_q", "nblk", "blk", "out", "lse", "dout", "delta", "drop", "dq_acc", "dq_count"],
     "mmi_loss_args": ["logits", "gt", "B", "exposure_prob", "inv_bsz", "use_focal", "logits_out", "dbias_bias", "use_huber", "kl_after_focal",

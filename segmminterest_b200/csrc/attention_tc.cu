@@ -493,7 +493,8 @@ template <bool DROP>
 __global__ void __launch_bounds__(ATT_THREADS, 4)
 attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_constant__ CUtensorMap tmQb,
                      const __grid_constant__ CUtensorMap tmKa, const __grid_constant__ CUtensorMap tmKb,
-                     const __grid_constant__ CUtensorMap tmVa, const __grid_constant__ CUtensorMap tmVb, const AttnTcParams p) {
+                     const __grid_constant__ CUtensorMap tmVa, const __grid_constant__ CUtensorMap tmVb,
+                     const __grid_constant__ CUtensorMap tmO, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sQ = smem;
@@ -719,10 +720,29 @@ attn_fwd_tc64_kernel(const __grid_constant__ CUtensorMap tmQa, const __grid_cons
     uint32_t ro[32];
     tmem_ld_32x32(tO + lane_addr, ro);
     tmem_ld_wait();
-    if (q_in) {
-      const float l = l0 + l1;
-      store_row32_bf16(p.out + ((int64_t)b * p.Lq + qi) * p.ldo + h * DH, ro, 1.0f / l);
-      p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = m * kLn2 + logf(l);
+    {
+      // O rows leave by TMA (3-D map [B, Lq, H dh]: rows past Lq of this batch item are clipped): thread-per-row global
+      // stores put 32 different lines into every STG.  The warp's 32 x 64 B slice is staged in the Q buffer, which no
+      // product reads any more (`done` covers every MMA of the CTA).
+      const float inv = 1.0f / (l0 + l1);
+      const uint32_t out_a = smem_u32(sQ) + (uint32_t)qd * (32 * DH * 2), orow_a = out_a + lane * 64, oswz = (lane >> 1) & 3;
+#pragma unroll
+      for (uint32_t v = 0; v < 4; ++v)
+        sts_u4(orow_a + ((v ^ oswz) << 4),
+               pack_bf16x2(__uint_as_float(ro[8 * v]) * inv, __uint_as_float(ro[8 * v + 1]) * inv),
+               pack_bf16x2(__uint_as_float(ro[8 * v + 2]) * inv, __uint_as_float(ro[8 * v + 3]) * inv),
+               pack_bf16x2(__uint_as_float(ro[8 * v + 4]) * inv, __uint_as_float(ro[8 * v + 5]) * inv),
+               pack_bf16x2(__uint_as_float(ro[8 * v + 6]) * inv, __uint_as_float(ro[8 * v + 7]) * inv));
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        tma_store_3d(&tmO, reinterpret_cast<const void*>(sQ + qd * (32 * DH * 2)), h * DH, q0 + qd * 32, b);
+        bulk_commit();
+      }
+      __syncwarp();
+      if (q_in) p.lse[((int64_t)b * p.H + h) * p.Lq + qi] = m * kLn2 + logf(l0 + l1);
+      if (lane == 0) bulk_wait_read0();                    // the staging tile must outlive the store's read
+      __syncwarp();
     }
   }
   tmem_teardown(tmem, warp, 128);
@@ -1293,8 +1313,11 @@ int attn_tc(int kind, const mmi_attn_args* a, int which, cudaStream_t st) {
         rc = set_smem(attn_fwd_tc64_kernel<true>, smem); if (rc) return rc;
         cfg64 = smem;
       }
-      if (drop_on) attn_fwd_tc64_kernel<true><<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
-      else attn_fwd_tc64_kernel<false><<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], p);
+      CUtensorMap mO;
+      MMI_CHECK_ARG(a->ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "attn_tc fwd: out must be 16-byte aligned with ldo a multiple of 8");
+      if (!get_tensor_map_3d(a->out, width, a->Lq, a->B, a->ldo, DH, 32, CU_TENSOR_MAP_SWIZZLE_64B, &mO)) return MMI_ECUDA;
+      if (drop_on) attn_fwd_tc64_kernel<true><<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mO, p);
+      else attn_fwd_tc64_kernel<false><<<grid, ATT_THREADS, smem, st>>>(mQ[0], mQ[1], mK[0], mK[1], mV[0], mV[1], mO, p);
     } else if (kind == 0) {
       const size_t T = (a->blk[0].Lk + NT - 1) / NT + (a->nblk > 1 ? (a->blk[1].Lk + NT - 1) / NT : 0);
       const size_t smem = 2 * TILE128 + FWD_STAGES * 2 * TILE32 + 2 * TILE128 + bar_bytes + T * 8;

@@ -19,6 +19,12 @@
 // the last product that reads tile j of the current item has retired (kv_empty[j]), so its load hides behind the remaining
 // key tiles and the epilogue; barrier initialisation, the TMEM allocation and the launch tail are paid once per SM instead
 // of once per (b, h) -- at the candidate side's shapes (one query tile per item) those were 3/4 of a CTA's life.
+// score pairs (of the 8 a thread computes per tile) whose exponential runs as a degree-3 polynomial on the FMA pipe instead
+// of MUFU.EX2: the 16 softmax warps hit the MUFU unit in lockstep (8 192 ex2 per tile = 512 cycles at 16 / clk / SM)
+#ifndef AK_POLY
+#define AK_POLY 0x00
+#endif
+__device__ __forceinline__ float2 ak_ex2(float2 x, int pair) { return ((AK_POLY >> pair) & 1) ? ex2_poly2(x) : ex2_mufu2(x); }
 constexpr int AK_MAXT = 5;
 constexpr int AK_THREADS = 64 + 16 * 32;
 constexpr uint32_t AK_TMEM_COLS = 512;
@@ -456,7 +462,7 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
             for (int c = 0; c < 16; c += 2) {
               const bool k0_ = (kq >> c) & 1u, k1_ = (kq >> (c + 1)) & 1u;
               const float s0 = k0_ ? __uint_as_float(rs[c]) : 0.f, s1 = k1_ ? __uint_as_float(rs[c + 1]) : 0.f;
-              const float2 pr = ex2_mufu2(fma2(make_float2(s0, s1), sl2, NL2(c)));
+              const float2 pr = ak_ex2(fma2(make_float2(s0, s1), sl2, NL2(c)), c >> 1);
               const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, mul2(ND2(c), dsc2)));
               pp[c >> 1] = pack_bf16x2(pr.x, pr.y);
               pd[c >> 1] = pack_bf16x2(k0_ ? ds.x : 0.f, k1_ ? ds.y : 0.f);
@@ -478,7 +484,7 @@ attn_bwd_allkeys_tc_kernel(const __grid_constant__ CUtensorMap tmQa, const __gri
 #pragma unroll
           for (int c = 0; c < 16; c += 2) {
             const float2 x = fma2(make_float2(__uint_as_float(rs[c]), __uint_as_float(rs[c + 1])), sl2, NL2(c));
-            const float2 pr = ex2_mufu2(x);
+            const float2 pr = ak_ex2(x, c >> 1);
             const float2 ds = mul2(pr, fma2(make_float2(__uint_as_float(rp[c]), __uint_as_float(rp[c + 1])), sc2, ND2(c)));
             pp[c >> 1] = pack_bf16x2(pr.x, pr.y);
             pd[c >> 1] = pack_bf16x2(ds.x, ds.y);

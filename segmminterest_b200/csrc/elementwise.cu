@@ -213,38 +213,48 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_b
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; if (WITH_DXSUM) ds[i][j] = 0.f; }
   }
-  for (int64_t row0 = (int64_t)blockIdx.x * 8 + warp; row0 < rows; row0 += 2 * wstride) {
-    const int64_t rr[2] = {row0, row0 + wstride};
-    const bool in1 = rr[1] < rows;
-    uint4 xv[2][NV], dv[2][NV];
-    float2 st[2];
-    if (MMI_LN_PREFETCH) {
-      // the next iteration's rows are pulled into L2 now: the register budget (dgamma / dbeta / dx-sum accumulators + two
-      // rows of x and dy) leaves no room for a register-level software pipeline, so the DRAM latency of the next row pair
-      // is hidden behind this iteration's arithmetic by a prefetch instead
+  // x / dy rows travel through a per-warp cp.async ring (3 stages x 2 rows x {x, dy}): the loads of the next two row pairs
+  // are in flight while this pair is worked on.  With plain loads the kernel alternated between a burst of requests and a
+  // stretch of arithmetic (45 % of the HBM peak, 63 % issue) -- the dgamma / dbeta / dx-sum accumulators leave no registers
+  // for a software pipeline, shared memory does.  Every lane copies and later reads its OWN 16-byte chunks: no barriers.
+  constexpr int LN_STAGES = 3;
+  constexpr uint32_t STAGE_BYTES = 2 * 2 * d * 2;        // 2 rows x (x, dy) x d bf16
+  uint8_t* ring = reinterpret_cast<uint8_t*>(sm) + (size_t)warp * LN_STAGES * STAGE_BYTES;
+  const uint32_t ring_a = static_cast<uint32_t>(__cvta_generic_to_shared(ring));
+  auto issue = [&](int64_t r0, int stage) {
+    if (r0 < rows) {
+      const int64_t r1 = r0 + wstride < rows ? r0 + wstride : r0;
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
-        const int64_t nr = rr[r] + 2 * wstride;
-        if (nr < rows) {
+        const int64_t base = (r ? r1 : r0) * (int64_t)d;
 #pragma unroll
-          for (int i = 0; i < NV; ++i) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(x + nr * (int64_t)d) + lane + 32 * i));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint4*>(dy + nr * (int64_t)d) + lane + 32 * i));
-          }
+        for (int i = 0; i < NV; ++i) {
+          const uint32_t dst = ring_a + stage * STAGE_BYTES + ((r * 2) * NV * 32 + lane + 32 * i) * 16;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const uint4*>(x + base) + lane + 32 * i) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + NV * 32 * 16), "l"(reinterpret_cast<const uint4*>(dy + base) + lane + 32 * i) : "memory");
         }
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int64_t first = (int64_t)blockIdx.x * 8 + warp;
+  issue(first, 0);
+  issue(first + 2 * wstride, 1);
+  int stage = 0;
+  for (int64_t row0 = first; row0 < rows; row0 += 2 * wstride) {
+    const int64_t rr[2] = {row0, row0 + wstride};
+    const bool in1 = rr[1] < rows;
+    float2 st[2];
+    issue(row0 + 4 * wstride, stage >= 1 ? stage - 1 : LN_STAGES - 1);     // the stage read in the previous iteration
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    // this lane's chunks of the current row pair stay in shared memory and are read once per pass (registers go to the
+    // column-sum accumulators)
+    uint8_t* cur = ring + stage * STAGE_BYTES + lane * 16;
+    auto XV = [&](int r, int i) -> uint4& { return *reinterpret_cast<uint4*>(cur + ((r * 2) * NV * 32 + 32 * i) * 16); };
+    auto DV = [&](int r, int i) -> uint4& { return *reinterpret_cast<uint4*>(cur + ((r * 2 + 1) * NV * 32 + 32 * i) * 16); };
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const bool in = r == 0 || in1;
-      const int64_t base = (in ? rr[r] : row0) * (int64_t)d;
-      st[r] = *reinterpret_cast<const float2*>(stats + 2 * (in ? rr[r] : row0));
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        xv[r][i] = ldg_stream(reinterpret_cast<const uint4*>(x + base) + lane + 32 * i);
-        dv[r][i] = ldg_stream(reinterpret_cast<const uint4*>(dy + base) + lane + 32 * i);
-      }
-    }
+    for (int r = 0; r < 2; ++r) st[r] = *reinterpret_cast<const float2*>(stats + 2 * ((r == 0 || in1) ? rr[r] : row0));
+    stage = stage + 1 == LN_STAGES ? 0 : stage + 1;
     if (DROP && dy_drop.thr8) {                            // backward of y = dropout(LN(x)): dy <- mask * scale * dy, in registers
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
@@ -252,11 +262,11 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_b
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           float df[8], kf[8];
-          bf16x8_to_f32(dv[r][i], df);
+          bf16x8_to_f32(DV(r, i), df);
           drop_factors8(dy_drop, rowh, lane + 32 * i, kf);
 #pragma unroll
           for (int j = 0; j < 8; ++j) df[j] *= kf[j];
-          dv[r][i] = f32_to_bf16x8(df);
+          DV(r, i) = f32_to_bf16x8(df);
         }
       }
     }
@@ -266,8 +276,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_b
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         float xf[8], df[8];
-        bf16x8_to_f32(xv[r][i], xf);
-        bf16x8_to_f32(dv[r][i], df);
+        bf16x8_to_f32(XV(r, i), xf);
+        bf16x8_to_f32(DV(r, i), df);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = (xf[j] - st[r].x) * st[r].y, g = df[j] * gm[i][j];
@@ -290,8 +300,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_b
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         float xf[8], df[8], o[8];
-        bf16x8_to_f32(xv[r][i], xf);
-        bf16x8_to_f32(dv[r][i], df);
+        bf16x8_to_f32(XV(r, i), xf);
+        bf16x8_to_f32(DV(r, i), df);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xh = (xf[j] - st[r].x) * st[r].y;
@@ -323,7 +333,9 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_b
       }
     }
   }
-  // CTA reduction of the per-warp column sums (fixed order)
+  // CTA reduction of the per-warp column sums (fixed order); the buffer aliases the rings
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
   constexpr int NQ = WITH_DXSUM ? 3 : 2;
   float* mine = sm + (size_t)warp * NQ * d;
 #pragma unroll
@@ -949,7 +961,9 @@ extern "C" int mmi_layernorm_bwd_drop(const void* dy, const void* x, int dtype, 
     // bandwidth path: 16-byte vectors, two rows per warp in flight, dx column sums fused
     const int grid = grid_for_rows((rows + 1) / 2, 8, kNumSMs * 2);
     const int nq = dxsum ? 3 : 2;
-    const size_t smem = (size_t)8 * nq * d * sizeof(float);
+    const size_t ring = (size_t)8 * 3 * 2 * 2 * d * 2;          // 8 warps x 3 stages x 2 rows x (x, dy) x d bf16
+    const size_t red = (size_t)8 * nq * d * sizeof(float);
+    const size_t smem = ring > red ? ring : red;
 #define MMI_LN_BWD16_K(NV_, DS_, DR_)                                                                                          \
   do {                                                                                                                        \
     if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_bwd_bf16_kernel<NV_, DS_, DR_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

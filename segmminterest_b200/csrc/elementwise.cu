@@ -194,6 +194,90 @@ __device__ __forceinline__ void drop_factors8(const DropParams& dp, uint32_t row
   for (int j = 0; j < 8; ++j) kf[j] = ((w >> j) & 1u) ? dp.scale : 0.f;
 }
 
+// LayerNorm forward, bf16 fast path (d = 256 * NV): rows travel through a per-warp cp.async ring (3 stages x 2 rows) so the
+// loads of the next two row pairs are in flight while this pair is normalised; 16-byte vectors, gamma / beta in registers.
+// (The generic kernel: one row per warp with 8-byte loads, 58 % of the HBM peak at 69 % issue utilisation.)
+template <int NV, bool DROP>
+__global__ void __launch_bounds__(256) layernorm_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                                 __nv_bfloat16* __restrict__ y, float* __restrict__ stats, const DropParams drop) {
+  extern __shared__ float sm[];
+  constexpr int d = 256 * NV;
+  constexpr int LN_STAGES = 3;
+  constexpr uint32_t STAGE_BYTES = 2 * d * 2;            // 2 rows x d bf16
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t wstride = (int64_t)gridDim.x * 8;
+  uint8_t* ring = reinterpret_cast<uint8_t*>(sm) + (size_t)warp * LN_STAGES * STAGE_BYTES;
+  const uint32_t ring_a = static_cast<uint32_t>(__cvta_generic_to_shared(ring));
+  float gm[NV][8], bt[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(gamma + (lane + 32 * i) * 8 + j), b = *reinterpret_cast<const float4*>(beta + (lane + 32 * i) * 8 + j);
+      gm[i][j] = a.x; gm[i][j + 1] = a.y; gm[i][j + 2] = a.z; gm[i][j + 3] = a.w;
+      bt[i][j] = b.x; bt[i][j + 1] = b.y; bt[i][j + 2] = b.z; bt[i][j + 3] = b.w;
+    }
+  }
+  auto issue = [&](int64_t r0, int stage) {
+    if (r0 < rows) {
+      const int64_t r1 = r0 + wstride < rows ? r0 + wstride : r0;
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_a + stage * STAGE_BYTES + (r * NV * 32 + lane + 32 * i) * 16),
+                       "l"(reinterpret_cast<const uint4*>(x + (r ? r1 : r0) * (int64_t)d) + lane + 32 * i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int64_t first = (int64_t)blockIdx.x * 8 + warp;
+  issue(first, 0);
+  issue(first + 2 * wstride, 1);
+  int stage = 0;
+  for (int64_t row0 = first; row0 < rows; row0 += 2 * wstride) {
+    issue(row0 + 4 * wstride, stage >= 1 ? stage - 1 : LN_STAGES - 1);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    const uint8_t* cur = ring + stage * STAGE_BYTES + lane * 16;
+    stage = stage + 1 == LN_STAGES ? 0 : stage + 1;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int64_t row = row0 + r * wstride;
+      if (row >= rows) break;
+      float v[NV][8];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(cur + (r * NV * 32 + 32 * i) * 16), v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      }
+      const float mean = warp_sum(s) * (1.0f / d);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float a = v[i][j] - mean; q = fmaf(a, a, q); }
+      const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / d) + eps);
+      if (lane == 0 && stats != nullptr) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+      const uint32_t rowh = (DROP && drop.thr8) ? drop_rowhash(drop.key, (uint64_t)row) : 0u;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gm[i][j] + bt[i][j];
+        if (DROP && drop.thr8) {
+          float kf[8];
+          drop_factors8(drop, rowh, lane + 32 * i, kf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] *= kf[j];
+        }
+        stg_stream(reinterpret_cast<uint4*>(y + row * (int64_t)d) + lane + 32 * i, f32_to_bf16x8(o));
+      }
+    }
+  }
+}
+
 template <int NV, bool WITH_DXSUM, bool DROP>
 __global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                                     int64_t rows, const float* __restrict__ gamma,
@@ -917,6 +1001,26 @@ extern "C" int mmi_layernorm_fwd_drop(const void* x, int dtype, int64_t rows, in
   MMI_CHECK_ARG(x && y && gamma && beta, "layernorm_fwd: null pointer");
   MMI_CHECK_ARG(d % 4 == 0 && d <= 128 * kMaxVecPerLane && d > 0, "layernorm: d=%d must be a multiple of 4 and <= %d", d, 128 * kMaxVecPerLane);
   if (rows == 0) return MMI_OK;
+  if (dtype == MMI_BF16 && (d == 256 || d == 512 || d == 768 || d == 1024) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0) {
+    // bandwidth path: 16-byte vectors through a cp.async ring, two rows per warp and stage
+    const int grid16 = grid_for_rows((rows + 1) / 2, 8, kNumSMs * 4);
+    const size_t smem = (size_t)8 * 3 * 2 * d * 2;
+#define MMI_LN_FWD16(NV_)                                                                                                     \
+  do {                                                                                                                        \
+    if (dp.thr8) {                                                                                                            \
+      if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_fwd_bf16_kernel<NV_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      layernorm_fwd_bf16_kernel<NV_, true><<<grid16, 256, smem, st>>>((const __nv_bfloat16*)x, rows, gamma, beta, eps, (__nv_bfloat16*)y, stats, dp); \
+    } else {                                                                                                                  \
+      if (smem > 48 * 1024) cudaFuncSetAttribute(layernorm_fwd_bf16_kernel<NV_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      layernorm_fwd_bf16_kernel<NV_, false><<<grid16, 256, smem, st>>>((const __nv_bfloat16*)x, rows, gamma, beta, eps, (__nv_bfloat16*)y, stats, dp); \
+    }                                                                                                                         \
+  } while (0)
+    if (d == 256) MMI_LN_FWD16(1); else if (d == 512) MMI_LN_FWD16(2); else if (d == 768) MMI_LN_FWD16(3); else MMI_LN_FWD16(4);
+#undef MMI_LN_FWD16
+    MMI_CHECK_LAUNCH();
+    return MMI_OK;
+  }
   const int grid = grid_for_rows(rows, 8, kNumSMs * 8);
   const int nv = d <= 128 ? 1 : (d <= 256 ? 2 : (d <= 512 ? 4 : 8));
 #define MMI_LN_FWD(T_, NV_) layernorm_fwd_kernel<T_, NV_><<<grid, 256, 0, st>>>((const T_*)x, rows, d, gamma, beta, eps, (T_*)y, stats, dp)

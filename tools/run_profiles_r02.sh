@@ -20,12 +20,10 @@ cap() {  # name, kernel regex, skip, count, keep-report(0/1), extra ncu flags
     python tools/ncu_hot_lines.py $tmp/${tag}_$name.ncu-rep >> $out/${tag}_ncu_$name.txt 2>&1
     if [ "$keep" = 1 ] && [ $(stat -c %s $tmp/${tag}_$name.ncu-rep) -lt 12000000 ]; then cp $tmp/${tag}_$name.ncu-rep $out/; fi
 }
-# step 2 = the launches after the warm-up step's; per step: 4 all-keys (history side), 8 forward (2 sides x 4 layers),
-# 4 dq + 8 dkv (candidate side), 2 gathers, 20 + 20 LayerNorm, head fwd/bwd, loss, adamw = 70 launches, one report
-cap step "(attn_|gather_l1norm|layernorm_|head_fwd|head_bwd|loss_kernel|adamw_kernel)" 70 70 0
+# step 2 = the launches after the warm-up step's; per step: 9 all-keys backward (4 history-side + 5 candidate-side), 9 forward,
+# 2 gathers, 20 + 20 LayerNorm, head fwd/bwd, loss, adamw = 64 launches, one report (summarised on the box: ~7 GPU-minutes)
+cap step "(attn_|gather_l1norm|layernorm_|head_fwd|head_bwd|loss_kernel|adamw_kernel)" 64 64 0
 cap gemm gemm_tc 115 36 0
-# the GELU + dropout instantiation alone (demangled names carry the template arguments)
-cap gemm_gelu_drop "gemm_tc_kernel<256, false, __nv_bfloat16, true, true>" 8 2 1 --kernel-name-base demangled
 du -sh $out
 ls -la $out | grep $tag
 MMI_LIB_PATH=segmminterest_b200/build/variants/libmmi_trace.so python tools/attn_trace_all.py 40 1 > $out/${tag}_trace_allkeys_cand.txt 2>&1

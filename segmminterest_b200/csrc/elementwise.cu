@@ -376,11 +376,32 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_b
       c1[0] += __shfl_xor_sync(0xffffffffu, c1[0], o); c2[0] += __shfl_xor_sync(0xffffffffu, c2[0], o);
       c1[1] += __shfl_xor_sync(0xffffffffu, c1[1], o); c2[1] += __shfl_xor_sync(0xffffffffu, c2[1], o);
     }
+    // keep words of the second output: the 4 lanes that share 32 columns need the same word for each (row, vector) pair,
+    // 2 NV of them per iteration -- lane k of the group hashes pairs k, k + 4, ... and a shuffle hands them round
+    // (every lane hashing all of its own words was a quarter of the kernel's instructions)
+    uint32_t kwx[2][NV];
+    if (DROP && dx_drop.thr8) {
+      constexpr int NW = (2 * NV + 3) / 4;                 // words hashed per lane
+      uint32_t mine[NW];
+#pragma unroll
+      for (int k = 0; k < NW; ++k) {
+        const int c = (lane & 3) + 4 * k;                  // pair index r * NV + i (c >= 2 NV: unused)
+        const int r = c / NV, i = c - r * NV;
+        const uint32_t rowh = drop_rowhash(dx_drop.key, (uint64_t)((r == 1 && in1) ? rr[1] : rr[0]));
+        mine[k] = drop_keep_word(rowh, (uint32_t)((lane >> 2) + 8 * i), dx_drop.thr8);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = r * NV + i;
+          kwx[r][i] = __shfl_sync(0xffffffffu, mine[c >> 2], (lane & ~3) | (c & 3));
+        }
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       if (r == 1 && !in1) break;
       const float m1 = c1[r] * (1.0f / d), m2 = c2[r] * (1.0f / d);
-      const uint32_t rowh_x = (DROP && dx_drop.thr8) ? drop_rowhash(dx_drop.key, (uint64_t)rr[r]) : 0u;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         float xf[8], df[8], o[8];
@@ -400,10 +421,9 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_bf16_kernel(const __nv_b
         const uint4 packed = f32_to_bf16x8(o);
         uint4 summed = packed;
         if (DROP && dx_drop.thr8) {                        // second output: the gradient behind the residual's dropout
-          float kf[8];
-          drop_factors8(dx_drop, rowh_x, lane + 32 * i, kf);
+          const uint32_t w8 = (kwx[r][i] >> ((lane & 3) * 8)) & 0xffu;      // byte (lane & 3) of keep word (lane + 32 i) >> 2
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] *= kf[j];
+          for (int j = 0; j < 8; ++j) o[j] *= ((w8 >> j) & 1u) ? dx_drop.scale : 0.f;
           summed = f32_to_bf16x8(o);
           stg_stream(reinterpret_cast<uint4*>(dx_dropped + rr[r] * (int64_t)d) + lane + 32 * i, summed);
         }
